@@ -1,0 +1,1178 @@
+// TEST INFRASTRUCTURE ONLY — see oracle_chromap.h.  CPU restatement of Chromap's paired-end
+// mapping hot path in our own flat data layout.  File:line citations are into /root/reference/src.
+#include "oracle_chromap.h"
+
+#include <omp.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <string>
+#include <tuple>
+#include <vector>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+// ----------------------------------------------------------------------------------------------
+// Base coding (utils.h:87-104): A/a=0 C/c=1 G/g=2 T/t=3, everything else 4.
+static uint8_t g_code[256];
+static struct CodeInit {
+  CodeInit() {
+    memset(g_code, 4, sizeof(g_code));
+    g_code['A'] = g_code['a'] = 0;
+    g_code['C'] = g_code['c'] = 1;
+    g_code['G'] = g_code['g'] = 2;
+    g_code['T'] = g_code['t'] = 3;
+  }
+} g_code_init;
+static inline uint8_t code(char c) { return g_code[(uint8_t)c]; }
+
+// Invertible 64-bit mix (utils.h:76-85).
+static inline u64 mix64(u64 key, u64 mask) {
+  key = (~key + (key << 21)) & mask;
+  key = key ^ key >> 24;
+  key = ((key + (key << 3)) + (key << 8)) & mask;
+  key = key ^ key >> 14;
+  key = ((key + (key << 2)) + (key << 4)) & mask;
+  key = key ^ key >> 28;
+  key = (key + (key << 31)) & mask;
+  return key;
+}
+
+struct Mm {
+  u64 hash;
+  u64 hit;  // ((seq_index<<32 | end_pos) << 1) | strand
+};
+
+// minimizer_generator.cc:7-139.  (k,w)-minimizers, strand-canonical, double-hashed key, N-aware.
+static void gen_minimizers(const char *seq, u32 len, u32 seq_index, int k, int w, std::vector<Mm> &out) {
+  const u64 shift = 2 * (k - 1);
+  const u64 mask = (((u64)1) << (2 * k)) - 1;
+  u64 fwd = 0, rev = 0;
+  Mm ring[256];
+  for (int i = 0; i < w; ++i) ring[i] = {UINT64_MAX, UINT64_MAX};
+  Mm best = {UINT64_MAX, UINT64_MAX};
+  int run = 0;       // unambiguous_length
+  int slot = 0;      // position_in_buffer
+  int best_slot = 0; // min_position
+  for (u32 pos = 0; pos < len; ++pos) {
+    const uint8_t b = code(seq[pos]);
+    Mm cur = {UINT64_MAX, UINT64_MAX};
+    if (b < 4) {
+      fwd = ((fwd << 2) | b) & mask;
+      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
+      if (fwd == rev) continue;  // :42-45 — skips ring write and ring advance too
+      const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
+      const u64 strand = hf < hr ? 0 : 1;  // tie -> reverse (:51-52)
+      ++run;
+      if (run >= k) {
+        cur.hash = mix64(strand ? hr : hf, mask);  // Hash64(Hash64(kmer)) (:55)
+        cur.hit = ((((u64)seq_index) << 32 | pos) << 1) | strand;
+      }
+    } else {
+      run = 0;
+    }
+    ring[slot] = cur;
+    if (run == w + k - 1 && best.hash != UINT64_MAX && best.hash < cur.hash) {
+      // first full window: identical k-mers not stored yet (:66-77)
+      for (int j = slot + 1; j < w; ++j)
+        if (best.hash == ring[j].hash && ring[j].hit != best.hit) out.push_back(ring[j]);
+      for (int j = 0; j < slot; ++j)
+        if (best.hash == ring[j].hash && ring[j].hit != best.hit) out.push_back(ring[j]);
+    }
+    if (cur.hash <= best.hash) {
+      if (run >= w + k && best.hash != UINT64_MAX) out.push_back(best);
+      best = cur;
+      best_slot = slot;
+    } else if (slot == best_slot) {
+      if (run >= w + k - 1 && best.hash != UINT64_MAX) out.push_back(best);
+      best.hash = UINT64_MAX;
+      for (int j = slot + 1; j < w; ++j)
+        if (best.hash >= ring[j].hash) { best = ring[j]; best_slot = j; }
+      for (int j = 0; j <= slot; ++j)
+        if (best.hash >= ring[j].hash) { best = ring[j]; best_slot = j; }
+      if (run >= w + k - 1 && best.hash != UINT64_MAX) {
+        for (int j = slot + 1; j < w; ++j)
+          if (best.hash == ring[j].hash && best.hit != ring[j].hit) out.push_back(ring[j]);
+        for (int j = 0; j <= slot; ++j)
+          if (best.hash == ring[j].hash && best.hit != ring[j].hit) out.push_back(ring[j]);
+      }
+    }
+    if (++slot == w) slot = 0;
+  }
+  if (best.hash != UINT64_MAX) out.push_back(best);
+}
+
+// ----------------------------------------------------------------------------------------------
+struct orc_reference {
+  std::vector<std::string> names;
+  std::vector<std::string> seqs;  // each padded with 64 NULs past the end (kseq leaves a NUL + slack)
+  std::vector<u32> lens;
+};
+
+struct orc_index {
+  int k = 0, w = 0;
+  u32 n_buckets = 0, size = 0, n_occupied = 0, upper_bound = 0;
+  std::vector<u32> flags;
+  std::vector<u64> keys, vals, occ;
+  // khash.h:232-245 with hash = key>>1 truncated to 32 bit (index_utils.h:13-17), triangular probing.
+  bool lookup(u64 mm_hash, u64 &key, u64 &val) const {
+    if (!n_buckets) return false;
+    const u64 q = mm_hash << 1;
+    const u32 m = n_buckets - 1;
+    u32 i = (u32)(q >> 1) & m, last = i, step = 0;
+    for (;;) {
+      const u32 f = (flags[i >> 4] >> ((i & 0xfU) << 1)) & 3;
+      if (f & 2) return false;  // empty
+      if (!(f & 1) && (keys[i] >> 1) == (q >> 1)) { key = keys[i]; val = vals[i]; return true; }
+      i = (i + (++step)) & m;
+      if (i == last) return false;
+    }
+  }
+};
+
+struct Cand {
+  u64 pos;
+  uint8_t cnt;
+};
+static inline bool cand_less(const Cand &a, const Cand &b) {  // candidate.h:23-33
+  if (a.cnt != b.cnt) return a.cnt > b.cnt;
+  return a.pos < b.pos;
+}
+struct Draft {
+  int err;
+  u64 pos;  // rid<<32 | end position
+};
+
+struct ReadState {  // mapping_metadata.h:24-175
+  std::vector<Mm> mm;
+  std::vector<u64> hits[2];     // [0]=positive [1]=negative
+  std::vector<Cand> cand[2], buf[2];
+  std::vector<Draft> map[2];
+  int min_err, second_min_err, n_best, n_second_best;
+  u32 rep_len;
+  void reset() {
+    mm.clear();
+    for (int s = 0; s < 2; ++s) { hits[s].clear(); cand[s].clear(); buf[s].clear(); map[s].clear(); }
+    rep_len = 0;
+  }
+};
+
+struct RepStats {  // index_utils.h:21-26
+  u32 len = 0, prev = UINT32_MAX;
+  int count = 0;
+};
+static void rep_update(int k, int w, u32 read_pos, RepStats &st) {  // index.cc:507-523
+  if (st.prev > read_pos) st.len += k;
+  else if (read_pos < st.prev + k + w - 1) st.len += read_pos - st.prev;
+  else st.len += k;
+  st.prev = read_pos;
+  ++st.count;
+}
+static inline u64 hit_to_candidate(int k, u64 ref_hit, u64 read_hit) {  // index.cc:491-505
+  const u32 rp = (u32)(ref_hit >> 1), qp = (u32)(read_hit >> 1);
+  const bool same = ((ref_hit ^ read_hit) & 1) == 0;
+  const u32 start = same ? rp - qp : rp + qp - (u32)k + 1;  // u32 wrap kept
+  return ((ref_hit >> 33) << 32) | start;
+}
+
+// index.cc:237-349.  Fills sorted +/- hit lists; returns repetitive seed count.
+static int gen_hits(const orc_index &ix, u32 max_freq, u32 rep_freq, ReadState &rs) {
+  RepStats st;
+  for (const Mm &m : rs.mm) {
+    u64 key, val;
+    if (!ix.lookup(m.hash, key, val)) continue;
+    if (key & 1) {
+      rs.hits[((val ^ m.hit) & 1) ? 1 : 0].push_back(hit_to_candidate(ix.k, val, m.hit));
+      continue;
+    }
+    const u32 n = (u32)val, off = (u32)(val >> 32);
+    if (n < max_freq)
+      for (u32 i = 0; i < n; ++i) {
+        const u64 rh = ix.occ[off + i];
+        rs.hits[((rh ^ m.hit) & 1) ? 1 : 0].push_back(hit_to_candidate(ix.k, rh, m.hit));
+      }
+    if (n >= rep_freq) rep_update(ix.k, ix.w, (u32)(m.hit >> 1), st);
+  }
+  // heap merge (round 2) and std::sort (round 1) yield the same sorted multiset (index.cc:317-333)
+  std::sort(rs.hits[0].begin(), rs.hits[0].end());
+  std::sort(rs.hits[1].begin(), rs.hits[1].end());
+  rs.rep_len = st.len;
+  return st.count;
+}
+
+// candidate_processor.cc:283-342.  Linear clustering scan; sentinel stays in `hits`.
+static void cluster_hits(int e, int need, u32 n_mm, std::vector<u64> &hits, std::vector<Cand> &out) {
+  hits.push_back(UINT64_MAX);
+  int mcount = 1, eq = 1, best_eq = 1;
+  u64 prev = hits[0], best = hits[0];
+  u32 prev_rid = (u32)(prev >> 32), prev_pos = (u32)prev;
+  for (size_t i = 1; i < hits.size(); ++i) {
+    const u32 rid = (u32)(hits[i] >> 32), pos = (u32)hits[i];
+    if (rid != prev_rid || pos > prev_pos + (u32)e ||
+        ((u32)mcount >= n_mm && pos > (u32)best + (u32)e)) {
+      if (mcount >= need) out.push_back({best, (uint8_t)best_eq});
+      mcount = 1; eq = 1; best_eq = 1; best = hits[i];
+    } else {
+      if (hits[i] == best) { ++eq; ++best_eq; }
+      else if (hits[i] == prev) { ++eq; if (eq > best_eq) { best = prev; best_eq = eq; } }
+      else eq = 1;
+      ++mcount;
+    }
+    prev = hits[i]; prev_rid = rid; prev_pos = pos;
+  }
+}
+
+// candidate_processor.cc:12-71.
+static void gen_candidates(const orc_params &P, const orc_index &ix, ReadState &rs) {
+  rs.rep_len = 0;
+  int rep = gen_hits(ix, P.max_seed_freq0, P.max_seed_freq0, rs);
+  bool high = false;
+  if (rs.hits[0].size() + rs.hits[1].size() == 0) {
+    rs.hits[0].clear(); rs.hits[1].clear(); rs.rep_len = 0;
+    rep = gen_hits(ix, P.max_seed_freq1, P.max_seed_freq0, rs);
+    high = !(rs.hits[0].empty() || rs.hits[1].empty());
+  }
+  int need = (int)rs.mm.size() - rep;
+  need = need > 1 ? need : 1;
+  need = need > P.min_num_seeds ? P.min_num_seeds : need;
+  if (high) need = P.min_num_seeds;
+  cluster_hits(P.error_threshold, need, rs.mm.size(), rs.hits[0], rs.cand[0]);
+  cluster_hits(P.error_threshold, need, rs.mm.size(), rs.hits[1], rs.cand[1]);
+}
+
+// index.cc:351-489: mate-guided lookup on one strand.  Returns +max count or -max count on bail-out.
+static int rescue_hits(const orc_params &P, const orc_index &ix, int strand, u32 range,
+                       const std::vector<Mm> &mm, const std::vector<Cand> &mate, u32 &rep_len,
+                       std::vector<u64> &hits) {
+  int max_cnt = 0, n_best = 0;
+  for (const Cand &c : mate) {
+    if (c.cnt > max_cnt) { max_cnt = c.cnt; n_best = 1; }
+    else if (c.cnt == max_cnt) ++n_best;
+  }
+  if (n_best >= 300 || mate.size() > (size_t)P.max_seed_freq0 ||
+      (max_cnt <= P.min_num_seeds && n_best >= 200))
+    return -max_cnt;
+  std::vector<std::pair<u64, u64>> win;
+  for (const Cand &c : mate)
+    if (c.cnt == max_cnt) win.push_back({c.pos < range ? 0 : c.pos - range, c.pos + range});
+  if (win.empty()) return max_cnt;
+  size_t nw = 1;
+  for (size_t i = 1; i < win.size(); ++i) {
+    if (win[nw - 1].second < win[i].first) win[nw++] = win[i];
+    else win[nw - 1].second = win[i].second;
+  }
+  win.resize(nw);
+  RepStats st;
+  for (const Mm &m : mm) {
+    u64 key, val;
+    if (!ix.lookup(m.hash, key, val)) continue;
+    if (key & 1) {
+      const bool same = ((val ^ m.hit) & 1) == 0;
+      if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(ix.k, val, m.hit));
+      continue;
+    }
+    const u32 off = (u32)(val >> 32), n = (u32)val;
+    int32_t prev_l = 0;
+    for (size_t bi = 0; bi < nw; ++bi) {
+      int32_t l = prev_l, mid = 0, r = (int32_t)n - 1;
+      const u64 lo = win[bi].first;
+      while (l <= r) {  // index.cc:447-459 — `mid` is the last probe, not a lower bound
+        mid = (l + r) / 2;
+        const u64 p = ix.occ[off + mid] >> 1;
+        if (p < lo) l = mid + 1;
+        else if (p > lo) r = mid - 1;
+        else break;
+      }
+      prev_l = mid;
+      for (u32 oi = (u32)mid; oi < n; ++oi) {
+        const u64 rh = ix.occ[off + oi];
+        if ((rh >> 1) > win[bi].second) break;
+        const bool same = ((rh ^ m.hit) & 1) == 0;
+        if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(ix.k, rh, m.hit));
+      }
+    }
+    if (n >= (u32)P.max_seed_freq0) rep_update(ix.k, ix.w, (u32)(m.hit >> 1), st);
+  }
+  std::sort(hits.begin(), hits.end());
+  rep_len = st.len;
+  return max_cnt;
+}
+
+// candidate_processor.cc:345-414.
+static void merge_cands(int e, std::vector<Cand> &c1, std::vector<Cand> &c2) {
+  if (c1.empty()) { c1.swap(c2); return; }
+  std::vector<Cand> o;
+  size_t i = 0, j = 0;
+  auto far = [&](u64 p) { return o.empty() || p > o.back().pos + (u64)e; };
+  while (i < c1.size() && j < c2.size()) {
+    if (c1[i].pos == c2[j].pos) {
+      if (far(c1[i].pos)) o.push_back(c1[i].cnt > c2[j].cnt ? c1[i] : c2[j]);
+      ++i; ++j;
+    } else if (c1[i].pos < c2[j].pos) { if (far(c1[i].pos)) o.push_back(c1[i]); ++i; }
+    else { if (far(c2[j].pos)) o.push_back(c2[j]); ++j; }
+  }
+  for (; i < c1.size(); ++i) if (far(c1[i].pos)) o.push_back(c1[i]);
+  for (; j < c2.size(); ++j) if (far(c2[j].pos)) o.push_back(c2[j]);
+  c1.swap(o);
+}
+
+// candidate_processor.cc:75-231.  Returns 1 when MAPQ must be forced to 0.
+static int supplement(const orc_params &P, const orc_index &ix, ReadState rs[2]) {
+  std::vector<Cand> aug[2][2];  // [mate][strand]
+  int ret = 0;
+  const u32 range = 2 * (u32)P.max_insert_size;
+  for (int mate = 0; mate < 2; ++mate) {
+    ReadState &me = rs[mate], &ot = rs[1 - mate];
+    const u32 n_mm = me.mm.size();
+    bool aug_flag = true;
+    for (int s = 0; s < 2 && aug_flag; ++s)
+      for (const Cand &c : me.cand[s])
+        if (c.cnt >= n_mm / 2) { aug_flag = false; break; }
+    if (!aug_flag) continue;
+    me.hits[0].clear(); me.hits[1].clear();
+    int pr = 0, nr = 0;
+    if (!ot.cand[0].empty()) {
+      pr = rescue_hits(P, ix, 1, range, me.mm, ot.cand[0], me.rep_len, me.hits[1]);
+      cluster_hits(P.error_threshold, 1, n_mm, me.hits[1], aug[mate][1]);
+    }
+    if (!ot.cand[1].empty()) {
+      nr = rescue_hits(P, ix, 0, range, me.mm, ot.cand[1], me.rep_len, me.hits[0]);
+      cluster_hits(P.error_threshold, 1, n_mm, me.hits[0], aug[mate][0]);
+    }
+    if (((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) &&
+        me.cand[0].size() + me.cand[1].size() == 0)
+      ret = 1;
+  }
+  for (int mate = 0; mate < 2; ++mate)
+    for (int s = 0; s < 2; ++s)
+      if (!aug[mate][s].empty()) merge_cands(P.error_threshold, rs[mate].cand[s], aug[mate][s]);
+  return ret;
+}
+
+// candidate_processor.cc:416-484.
+static void pe_filter_dir(u32 dist, const std::vector<Cand> &c1, const std::vector<Cand> &c2,
+                          std::vector<Cand> &f1, std::vector<Cand> &f2) {
+  u32 i1 = 0, i2 = 0, prev_end = 0;
+  int un1 = 0, un2 = 0, max1 = 6, max2 = 6;
+  while (i1 < c1.size() && i2 < c2.size()) {
+    if (c1[i1].pos > c2[i2].pos + dist) {
+      if (i2 >= prev_end && un2 < 5 && (c1[i1].pos >> 32) == (c2[i2].pos >> 32) && c2[i2].cnt >= max2) {
+        f2.push_back(c2[i2]); ++un2;
+      }
+      ++i2;
+    } else if (c2[i2].pos > c1[i1].pos + dist) {
+      if (un1 < 5 && (c1[i1].pos >> 32) == (c2[i2].pos >> 32) && c1[i1].cnt >= max1) {
+        f1.push_back(c1[i1]); ++un1;
+      }
+      ++i1;
+    } else {
+      f1.push_back(c1[i1]);
+      if (c1[i1].cnt > max1) max1 = c1[i1].cnt;
+      u32 j = i2;
+      while (j < c2.size() && c2[j].pos <= c1[i1].pos + dist) {
+        if (j >= prev_end) { f2.push_back(c2[j]); if (c2[j].cnt > max2) max2 = c2[j].cnt; }
+        ++j;
+      }
+      prev_end = j;
+      ++i1;
+    }
+  }
+}
+
+// alignment.cc:141-192.
+static int banded_align(int e, const char *pat, const char *text, int L, int *end_pos) {
+  u32 Peq[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 2 * e; ++i) Peq[code(pat[i])] |= (1u << i);
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0;
+  int err = 0;
+  for (int i = 0; i < L; ++i) {
+    Peq[code(pat[i + 2 * e])] |= hi;
+    u32 X = Peq[code(text[i])] | VN;
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    err += 1 - (int)(D0 & 1u);
+    if (err > 3 * e) return e + 1;
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  int best = err;
+  *end_pos = L - 1;
+  for (int i = 0; i < 2 * e; ++i) {
+    err += (int)((VP >> i) & 1u);
+    err -= (int)((VN >> i) & 1u);
+    if (err < best || (err == best && i + 1 == e)) { best = err; *end_pos = L + i; }
+  }
+  return best;
+}
+
+// alignment.cc:656-718.
+static void banded_traceback(int e, int min_err, const char *pat, const char *text, int L, int *start) {
+  if (min_err == 0) { *start = e; return; }
+  int ham = 0;
+  for (int i = 0; i < L; ++i) if (pat[i + e] != text[i]) ++ham;  // raw chars, case-sensitive (:665-669)
+  if (ham == min_err) { *start = e; return; }
+  u32 Peq[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 2 * e; ++i) Peq[code(pat[L - 1 + 2 * e - i])] |= (1u << i);
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0;
+  int err = 0;
+  for (int i = 0; i < L; ++i) {
+    Peq[code(pat[L - 1 - i])] |= hi;
+    u32 X = Peq[code(text[L - 1 - i])] | VN;
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    err += 1 - (int)(D0 & 1u);
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  *start = 2 * e;
+  for (int i = 0; i < 2 * e; ++i) {
+    err += (int)((VP >> i) & 1u);
+    err -= (int)((VN >> i) & 1u);
+    if (err == min_err) { *start = 2 * e - (1 + i); if (i + 1 == e) return; }
+  }
+}
+
+static inline bool valid_cand(int e, u32 ref_len, u32 pos, u32 L) {  // draft_mapping_generator.cc:59-70
+  return !(pos < (u32)e || pos >= ref_len || pos + L + (u32)e >= ref_len);
+}
+static inline void tally(ReadState &rs, int err) {  // the best/second-best bookkeeping, :217-230 etc.
+  if (err < rs.min_err) { rs.second_min_err = rs.min_err; rs.n_second_best = rs.n_best; rs.min_err = err; rs.n_best = 1; }
+  else if (err == rs.min_err) rs.n_best++;
+  else if (err == rs.second_min_err) rs.n_second_best++;
+  else if (err < rs.second_min_err) { rs.n_second_best = 1; rs.second_min_err = err; }
+}
+
+// draft_mapping_generator.cc:9-57 (non-split), with :72-157 fast path, :159-357 lane-group driver and
+// :359-557 per-candidate driver.  The SSE kernels agree with the scalar routine on accept/reject,
+// distance and end position, so groups are replayed with the scalar routine.
+static void verify_read(const orc_params &P, const orc_reference &ref, const char *read,
+                        const std::string &neg, u32 L, ReadState &rs) {
+  const int e = P.error_threshold;
+  rs.min_err = e + 1; rs.n_best = 0; rs.second_min_err = e + 1; rs.n_second_best = 0;
+  // fast path: exactly one candidate overall and it is supported by all minimizers
+  if (rs.cand[0].size() + rs.cand[1].size() == 1) {
+    int n_all = 0, idx = 0, strand = 0;
+    for (size_t i = 0; i < rs.cand[0].size(); ++i) if (rs.cand[0][i].cnt == rs.mm.size()) { idx = i; ++n_all; }
+    for (size_t i = 0; i < rs.cand[1].size(); ++i) if (rs.cand[1][i].cnt == rs.mm.size()) { idx = i; strand = 1; ++n_all; }
+    if (n_all == 1) {
+      rs.min_err = 0; rs.n_best = 1; rs.n_second_best = 0;  // set before the validity check (:113-115)
+      const Cand &c = rs.cand[strand][idx];
+      const u32 rid = (u32)(c.pos >> 32);
+      const u32 pos = strand == 0 ? (u32)c.pos : (u32)c.pos - L + 1;
+      if (valid_cand(e, ref.lens[rid], pos, L)) {
+        rs.map[strand].push_back({0, strand == 0 ? c.pos + L - 1 : c.pos});
+        return;
+      }
+    }
+  }
+  std::sort(rs.cand[0].begin(), rs.cand[0].end(), cand_less);
+  std::sort(rs.cand[1].begin(), rs.cand[1].end(), cand_less);
+  const int lanes = e < 8 ? 8 : (e < 16 ? 4 : 0);  // mapping_parameters.h:80-88
+  for (int s = 0; s < 2; ++s) {
+    const std::vector<Cand> &cs = rs.cand[s];
+    const char *text = s == 0 ? read : neg.data();
+    auto run_one = [&](const Cand &c, bool &failed) {
+      const u32 rid = (u32)(c.pos >> 32);
+      const u32 pos = s == 0 ? (u32)c.pos : (u32)c.pos - L + 1;
+      int endp = 0;
+      const int err = banded_align(e, ref.seqs[rid].data() + pos - e, text, L, &endp);
+      failed = err > e;
+      if (!failed) {
+        tally(rs, err);
+        rs.map[s].push_back({err, s == 0 ? c.pos - e + endp : c.pos - L + 1 - e + endp});
+      }
+    };
+    if (cs.size() < (size_t)lanes) {
+      for (const Cand &c : cs) {
+        const u32 pos = s == 0 ? (u32)c.pos : (u32)c.pos - L + 1;
+        if (!valid_cand(e, ref.lens[(u32)(c.pos >> 32)], pos, L)) continue;
+        bool f; run_one(c, f);
+      }
+      continue;
+    }
+    std::vector<Cand> group;
+    u32 threshold = 0;
+    size_t ci = 0;
+    while (ci < cs.size()) {
+      if (cs[ci].cnt < threshold) break;
+      const u32 pos = s == 0 ? (u32)cs[ci].pos : (u32)cs[ci].pos - L + 1;
+      if (!valid_cand(e, ref.lens[(u32)(cs[ci].pos >> 32)], pos, L)) { ++ci; continue; }
+      group.push_back(cs[ci]); ++ci;
+      if ((int)group.size() < lanes) continue;
+      for (const Cand &c : group) { bool f; run_one(c, f); if (f) threshold = c.cnt; }
+      group.clear();
+    }
+    for (const Cand &c : group) { bool f; run_one(c, f); }
+  }
+}
+
+struct PairState {
+  int min_sum, second_min_sum, n_best, n_second_best;
+  std::vector<std::pair<u32, u32>> best[2];  // [0]=F1R2, [1]=F2R1
+};
+
+// mapping_generator.h:346-484 (non-split branch).
+static void pair_dir(const orc_params &P, int s1, u32 L1, u32 L2, const std::vector<Draft> &m1,
+                     const std::vector<Draft> &m2, PairState &ps, std::vector<std::pair<u32, u32>> &best) {
+  u32 i1 = 0, i2 = 0;
+  const u64 ins = P.max_insert_size, ovl = P.min_read_length;
+  while (i1 < m1.size() && i2 < m2.size()) {
+    if ((s1 == 1 && m1[i1].pos > m2[i2].pos + ins - L2) || (s1 == 0 && m1[i1].pos > m2[i2].pos + L1 - ovl)) ++i2;
+    else if ((s1 == 0 && m2[i2].pos > m1[i1].pos + ins - L1) || (s1 == 1 && m2[i2].pos > m1[i1].pos + L2 - ovl)) ++i1;
+    else {
+      u32 j = i2;
+      while (j < m2.size() && ((s1 == 0 && m2[j].pos <= m1[i1].pos + ins - L1) ||
+                               (s1 == 1 && m2[j].pos <= m1[i1].pos + L2 - ovl))) {
+        const int sum = m1[i1].err + m2[j].err;
+        if (sum < ps.min_sum) {
+          ps.second_min_sum = ps.min_sum; ps.n_second_best = ps.n_best; ps.min_sum = sum; ps.n_best = 1;
+          best.clear(); best.push_back({i1, j});
+        } else if (sum == ps.min_sum) { ps.n_best++; best.push_back({i1, j}); }
+        else if (sum == ps.second_min_sum) ps.n_second_best++;
+        else if (sum < ps.second_min_sum) { ps.second_min_sum = sum; ps.n_second_best = 1; }
+        ++j;
+      }
+      ++i1;
+    }
+  }
+}
+
+// mapping_generator.h:920-1022 (non-split).
+static uint8_t mapq_se(int num_errors, uint16_t aln_len, int read_len, int max_diff, const ReadState &rs) {
+  const int coef_len = 50;
+  const int coef_frac = log(coef_len);  // == 3 (:925)
+  aln_len = aln_len > read_len ? aln_len : read_len;
+  const double ident = 1 - (double)num_errors / aln_len;
+  int mapq = 0;
+  int second = rs.second_min_err;
+  if (rs.n_best > 1) {
+  } else {
+    if (second > num_errors + max_diff) second = num_errors + max_diff;
+    double tmp = aln_len < coef_len ? 1.0 : coef_frac / log(aln_len);
+    tmp *= ident * ident;
+    mapq = 5 * 6.02 * (second - num_errors) * tmp * tmp + 0.499;
+  }
+  if (rs.n_second_best > 0) mapq -= (int)(4.343 * log(rs.n_second_best + 1) + 0.499);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  if (rs.rep_len > 0) {
+    double frac = rs.rep_len / (double)read_len;
+    if (rs.rep_len >= (u32)read_len) frac = 0.999;
+    if (ident <= 0.95) mapq = mapq * (1 - sqrt(frac)) + 0.499;
+    else if (ident <= 0.97) mapq = mapq * (1 - frac) + 0.499;
+    else if (ident >= 0.999) mapq = mapq * (1 - frac * frac * frac * frac) + 0.499;
+    else mapq = mapq * (1 - frac * frac) + 0.499;
+  }
+  return (uint8_t)mapq;
+}
+
+#define ORC_RAW_MAPQ(diff, a) ((int)(5 * 6.02 * (diff) / (a) + .499))
+// mapping_generator.h:1027-1192 (non-split).
+static uint8_t mapq_pe(int e1, int e2, uint16_t al1, uint16_t al2, int L1, int L2, int force,
+                       const PairState &ps, const ReadState rs[2]) {
+  uint8_t pe = 0;
+  const int unpaired = rs[0].min_err + rs[1].min_err + 3;
+  if (ps.n_best <= 1) {
+    const int adj = ps.second_min_sum < unpaired ? ps.second_min_sum : unpaired;
+    pe = ORC_RAW_MAPQ(adj - ps.min_sum, 1);
+    if (ps.n_second_best > 0) pe -= (int)(4.343 * log(ps.n_second_best + 1) + 0.499);  // uint8 wrap (:1073)
+    if (pe > 60) pe = 60;
+    const int rep = rs[0].rep_len + rs[1].rep_len;
+    if (rep > 0) {
+      const double total = L1 + L2;
+      double frac = (double)rep / total;
+      if (rep >= total) frac = 0.999;
+      const double id1 = 1 - (double)e1 / (L1 > al1 ? L1 : al1);
+      const double id2 = 1 - (double)e2 / (L2 > al2 ? L2 : al2);
+      const double ident = id1 < id2 ? id1 : id2;
+      if (ident <= 0.95) pe = pe * (1 - sqrt(frac)) + 0.499;
+      else if (ident <= 0.97) pe = pe * (1 - frac) + 0.499;
+      else if (ident >= 0.999) pe = pe * (1 - frac * frac * frac * frac) + 0.499;
+      else pe = pe * (1 - frac * frac) + 0.499;
+    }
+  }
+  uint8_t q1 = mapq_se(e1, al1, L1, 2, rs[0]);
+  uint8_t q2 = mapq_se(e2, al2, L2, 2, rs[1]);
+  q1 = q1 > pe ? q1 : pe < q1 + pe * 0.65 ? pe : q1 + pe * 0.65;
+  q2 = q2 > pe ? q2 : pe < q2 + pe * 0.65 ? pe : q2 + pe * 0.65;
+  q1 *= 1.2; if (q1 > 60) q1 = 60;
+  q2 *= 1.2; if (q2 > 60) q2 = 60;
+  uint8_t q = q1 < q2 ? q1 : q2;
+  if (q < 60 && force >= 0 && force < q) q = force;
+  return q;
+}
+
+// mapping_generator.h:657-917, BED branch, non-split: start from traceback, end = draft end.
+static void ref_span(const orc_params &P, const orc_reference &ref, const Draft &d, const char *read_seq,
+                     int L, u32 &start, u32 &end) {
+  const int e = P.error_threshold;
+  const u32 rid = (u32)(d.pos >> 32), rp = (u32)d.pos;
+  u32 vws = rp + 1 > (u32)(L + e) ? rp + 1 - L - e : 0;
+  if (rp + e >= ref.lens[rid]) vws = ref.lens[rid] - e - L;
+  int s = 0;
+  banded_traceback(e, d.err, ref.seqs[rid].data() + vws, read_seq, L, &s);
+  start = vws + s;
+  end = rp;
+}
+
+static const bool g_debug = getenv("ORC_DEBUG") != nullptr;
+struct orc_mapper {
+  orc_params P;
+  const orc_index *ix;
+  const orc_reference *ref;
+};
+
+static void revcomp(const char *s, u32 L, std::string &out) {  // sequence_batch.h:123-134
+  static const char tab[8] = {'A', 'C', 'G', 'T', 'N', 'N', 'N', 'N'};
+  out.resize(L);
+  for (u32 i = 0; i < L; ++i) out[i] = tab[(uint8_t)3 ^ code(s[L - 1 - i])];
+}
+
+// chromap.cc:176-289.  Works on copies; returns trimmed lengths.  neg strings are trimmed from the front.
+static void trim_adapters(const orc_params &P, std::string &r1, std::string &r2, std::string &n1, std::string &n2) {
+  const u32 raw1 = r1.size(), raw2 = r2.size();
+  const bool swap = !(raw1 <= raw2);
+  const char *read1 = swap ? r2.data() : r1.data();
+  const std::string &neg2 = swap ? n1 : n2;
+  const u32 L1 = swap ? raw2 : raw1, L2 = swap ? raw1 : raw2;
+  const int min_ovl = P.min_read_length, seed = min_ovl / 2, max_err = 1;
+  for (int si = 0; si < max_err + 1; ++si) {
+    size_t sp = neg2.find(read1 + si * seed, 0, seed);
+    while (sp != std::string::npos) {
+      const bool before_ok = sp >= (size_t)(si * seed);
+      const bool ovl_ok = (int)(L2 - sp + seed * si) >= min_ovl;
+      if (!before_ok || !ovl_ok) { sp = neg2.find(read1 + si * seed, sp + 1, seed); continue; }
+      bool ok = true;
+      int ne = 0;
+      for (int i = 0; i < seed * si; ++i) {
+        if (neg2[sp - si * seed + i] != read1[i]) ++ne;
+        if (ne > max_err) { ok = false; break; }
+      }
+      for (u32 i = seed; i + sp < L2 && si * seed + i < L1; ++i) {
+        if (neg2[sp + i] != read1[si * seed + i]) ++ne;
+        if (ne > max_err) { ok = false; break; }
+      }
+      if (ok) {
+        int ovl = L2 - sp + si * seed, off2 = 0;
+        if (ovl > (int)L1) { off2 = ovl - L1; ovl = L1; }
+        const int t1 = swap ? ovl + off2 : ovl, t2 = swap ? ovl : ovl + off2;
+        auto trim = [](std::string &r, std::string &n, int len) {  // sequence_batch.h:136-151
+          if (len >= (int)r.size()) return;
+          n.erase(0, r.size() - len);
+          r.resize(len);
+        };
+        trim(r1, n1, t1);
+        trim(r2, n2, t2);
+        return;
+      }
+      sp = neg2.find(read1 + si * seed, sp + 1, seed);
+    }
+  }
+}
+
+// One iteration of the taskloop, chromap.h:892-1143 (bulk data, BED, non-split).
+static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_reference &ref, std::mt19937 &gen,
+                        const char *s1, u32 len1, const char *s2, u32 len2, u32 read_id, u32 pair_index,
+                        orc_pe_record *out, int cap, orc_pair_trace *tr) {
+  if (tr) memset(tr, 0, sizeof(*tr));
+  if (len1 < (u32)P.min_read_length || len2 < (u32)P.min_read_length) return 0;
+  std::string r[2] = {std::string(s1, len1), std::string(s2, len2)}, neg[2];
+  revcomp(r[0].data(), len1, neg[0]);
+  revcomp(r[1].data(), len2, neg[1]);
+  if (P.trim_adapters) trim_adapters(P, r[0], r[1], neg[0], neg[1]);
+  const u32 L[2] = {(u32)r[0].size(), (u32)r[1].size()};
+  if (tr) { tr->trimmed_len[0] = L[0]; tr->trimmed_len[1] = L[1]; }
+  ReadState rs[2];
+  rs[0].reset(); rs[1].reset();
+  gen_minimizers(r[0].data(), L[0], pair_index, ix.k, ix.w, rs[0].mm);
+  gen_minimizers(r[1].data(), L[1], pair_index, ix.k, ix.w, rs[1].mm);
+  if (tr) { tr->n_minimizers[0] = rs[0].mm.size(); tr->n_minimizers[1] = rs[1].mm.size(); }
+  if (rs[0].mm.empty() || rs[1].mm.empty()) return 0;
+  gen_candidates(P, ix, rs[0]);
+  gen_candidates(P, ix, rs[1]);
+  if (tr) for (int m = 0; m < 2; ++m) { tr->n_pos_candidates_gen[m] = rs[m].cand[0].size(); tr->n_neg_candidates_gen[m] = rs[m].cand[1].size(); }
+  int sup = 0;
+  if (!P.split_alignment) sup = supplement(P, ix, rs);
+  if (tr) tr->supplement_result = sup;
+  size_t nc1 = rs[0].cand[0].size() + rs[0].cand[1].size(), nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
+  if (nc1 > 0 && nc2 > 0 && !P.split_alignment) {
+    for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) { rs[m].cand[s].swap(rs[m].buf[s]); rs[m].cand[s].clear(); }
+    pe_filter_dir(P.max_insert_size, rs[0].buf[0], rs[1].buf[1], rs[0].cand[0], rs[1].cand[1]);
+    pe_filter_dir(P.max_insert_size, rs[0].buf[1], rs[1].buf[0], rs[0].cand[1], rs[1].cand[0]);
+    nc1 = rs[0].cand[0].size() + rs[0].cand[1].size();
+    nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
+  }
+  if (tr) for (int m = 0; m < 2; ++m) {
+    tr->n_pos_candidates[m] = rs[m].cand[0].size(); tr->n_neg_candidates[m] = rs[m].cand[1].size();
+    tr->repetitive_seed_length[m] = rs[m].rep_len;
+  }
+  if (!(nc1 > 0 && nc2 > 0)) return 0;
+  verify_read(P, ref, r[0].data(), neg[0], L[0], rs[0]);
+  verify_read(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  if (tr) for (int m = 0; m < 2; ++m) {
+    tr->n_pos_mappings[m] = rs[m].map[0].size(); tr->n_neg_mappings[m] = rs[m].map[1].size();
+    tr->min_errors[m] = rs[m].min_err; tr->second_min_errors[m] = rs[m].second_min_err;
+    tr->n_best[m] = rs[m].n_best; tr->n_second_best[m] = rs[m].n_second_best;
+  }
+  if (rs[0].map[0].size() + rs[0].map[1].size() == 0 || rs[1].map[0].size() + rs[1].map[1].size() == 0) return 0;
+  // mapping_metadata.h:70-78 sorts by position only; equal positions are interchangeable for the
+  // output (the lower-error one is the only one that can be in a best pair), so (pos, err) is used.
+  auto by_pos = [](const Draft &a, const Draft &b) { return a.pos != b.pos ? a.pos < b.pos : a.err < b.err; };
+  for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) std::sort(rs[m].map[s].begin(), rs[m].map[s].end(), by_pos);
+  const int force = sup != 0 ? 0 : -1;
+  // mapping_generator.h:160-253
+  PairState ps;
+  ps.min_sum = 2 * P.error_threshold + 1; ps.n_best = 0; ps.second_min_sum = ps.min_sum; ps.n_second_best = 0;
+  pair_dir(P, 0, L[0], L[1], rs[0].map[0], rs[1].map[1], ps, ps.best[0]);
+  pair_dir(P, 1, L[0], L[1], rs[0].map[1], rs[1].map[0], ps, ps.best[1]);
+  if (tr) { tr->min_sum_errors = ps.min_sum; tr->second_min_sum_errors = ps.second_min_sum; tr->n_best_pairs = ps.n_best; tr->n_second_best_pairs = ps.n_second_best; }
+  if (ps.n_best > P.drop_repetitive_reads) return 0;
+  std::vector<int> sel(P.max_num_best_mappings);
+  std::iota(sel.begin(), sel.end(), 0);
+  if (ps.n_best > P.max_num_best_mappings) {
+    for (int i = P.max_num_best_mappings; i < ps.n_best; ++i) {
+      std::uniform_int_distribution<int> dist(0, i);
+      const int j = dist(gen);
+      if (j < P.max_num_best_mappings) sel[j] = i;
+    }
+    std::sort(sel.begin(), sel.end());
+  }
+  int idx = 0, reported = 0;
+  const int to_report = std::min(P.max_num_best_mappings, ps.n_best);
+  const uint8_t uniq = (ps.n_best == 1 || rs[0].n_best == 1 || rs[1].n_best == 1) ? 1 : 0;
+  for (int dir = 0; dir < 2 && reported != to_report; ++dir) {  // mapping_generator.h:486-654
+    const int s1 = dir, s2 = 1 - dir;
+    const std::vector<Draft> &m1 = rs[0].map[s1], &m2 = rs[1].map[s2];
+    for (const auto &bp : ps.best[dir]) {
+      const Draft &d1 = m1[bp.first], &d2 = m2[bp.second];
+      if (d1.err + d2.err > ps.min_sum) continue;
+      if (idx == sel[reported]) {
+        u32 st1, en1, st2, en2;
+        ref_span(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1);
+        ref_span(P, ref, d2, s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2);
+        const uint16_t al1 = en1 - st1 + 1, al2 = en2 - st2 + 1;
+        if (g_debug)  // same fields as the reference's -DCHROMAP_DEBUG line (mapping_generator.h:1038-1071)
+          fprintf(stderr, " rl1:%d rl2:%d pal:%d nal:%d me:%d #bm:%d sme:%d #sbm:%d ne1:%d ne2:%d me1:%d me2:%d #bm1:%d #bm2:%d sme1:%d sme2:%d #sbm1:%d #sbm2:%d idx:%u\n",
+                  (int)rs[0].rep_len, (int)rs[1].rep_len, (int)al1, (int)al2, ps.min_sum, ps.n_best, ps.second_min_sum, ps.n_second_best,
+                  d1.err, d2.err, rs[0].min_err, rs[1].min_err, rs[0].n_best, rs[1].n_best, rs[0].second_min_err, rs[1].second_min_err,
+                  rs[0].n_second_best, rs[1].n_second_best, pair_index);
+        const uint8_t q = mapq_pe(d1.err, d2.err, al1, al2, L[0], L[1], force, ps, rs);
+        if (reported < cap) {
+          orc_pe_record &o = out[reported];
+          o.read_id = read_id;
+          o.rid = (u32)(d1.pos >> 32);
+          o.fragment_start = s1 == 0 ? st1 : st2;
+          o.fragment_length = (uint16_t)(s1 == 0 ? (int)(en2 - st1 + 1) : (int)(en1 - st2 + 1));
+          o.mapq = q;
+          o.direction = s1 == 0 ? 1 : 0;
+          o.is_unique = uniq;
+          o.num_dups = 1;
+          o.positive_alignment_length = s1 == 0 ? al1 : al2;
+          o.negative_alignment_length = s1 == 1 ? al1 : al2;
+        }
+        if (++reported == to_report) break;
+      }
+      ++idx;
+    }
+  }
+  if (tr) tr->n_records = reported;
+  return reported;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host-side pieces: FASTA/FASTQ reader (kseq.h semantics: name = first token, multi-line sequence),
+// index file I/O, post-processing, BED text.
+struct SeqReader {
+  gzFile f = nullptr;
+  std::vector<char> buf;
+  size_t pos = 0, end = 0;
+  int last = 0;  // pending header char
+  bool eof = false;
+  bool open(const char *p) { f = gzopen(p, "r"); buf.resize(1 << 20); return f != nullptr; }
+  void close() { if (f) gzclose(f); f = nullptr; }
+  int getc_() {
+    if (pos >= end) {
+      if (eof) return -1;
+      int n = gzread(f, buf.data(), buf.size());
+      if (n <= 0) { eof = true; return -1; }
+      pos = 0; end = n;
+    }
+    return (unsigned char)buf[pos++];
+  }
+  bool getline_(std::string &s) {  // without the newline; false at EOF with nothing read
+    s.clear();
+    int c;
+    bool any = false;
+    while ((c = getc_()) != -1) {
+      any = true;
+      if (c == '\n') break;
+      s.push_back((char)c);
+    }
+    if (!s.empty() && s.back() == '\r') s.pop_back();
+    return any;
+  }
+  // returns false at EOF
+  bool next(std::string &name, std::string &seq, std::string &qual) {
+    name.clear(); seq.clear(); qual.clear();
+    int c;
+    if (last == 0) {
+      while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+      if (c == -1) return false;
+      last = c;
+    }
+    std::string line;
+    getline_(line);
+    size_t sp = line.find_first_of(" \t");
+    name = sp == std::string::npos ? line : line.substr(0, sp);
+    last = 0;
+    while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+      if (c == '\n') continue;
+      seq.push_back((char)c);
+      std::string rest;
+      getline_(rest);
+      seq += rest;
+    }
+    if (c == '>' || c == '@') last = c;
+    if (c != '+') return true;
+    getline_(line);  // rest of '+' line
+    while (qual.size() < seq.size()) {
+      std::string q;
+      if (!getline_(q)) break;
+      qual += q;
+    }
+    return true;
+  }
+};
+
+extern "C" {
+
+void orc_default_params(orc_params *p) {
+  p->error_threshold = 8; p->min_num_seeds = 2; p->max_seed_freq0 = 500; p->max_seed_freq1 = 1000;
+  p->max_num_best_mappings = 1; p->max_insert_size = 1000; p->mapq_threshold = 30; p->min_read_length = 30;
+  p->drop_repetitive_reads = 500000; p->trim_adapters = 0; p->remove_pcr_duplicates = 0; p->tn5_shift = 0;
+  p->split_alignment = 0; p->low_memory_mode = 0; p->output_format = 1;
+}
+
+int orc_apply_preset(orc_params *p, const char *preset) {  // chromap_driver.cc:247-275
+  std::string s = preset ? preset : "";
+  if (s.empty()) return 0;
+  if (s == "atac") { p->max_insert_size = 2000; p->trim_adapters = 1; p->remove_pcr_duplicates = 1; p->tn5_shift = 1; p->low_memory_mode = 1; p->output_format = 1; return 0; }
+  if (s == "chip") { p->max_insert_size = 2000; p->remove_pcr_duplicates = 1; p->low_memory_mode = 1; p->output_format = 1; return 0; }
+  if (s == "hic") { p->error_threshold = 4; p->mapq_threshold = 1; p->split_alignment = 1; p->low_memory_mode = 1; p->output_format = 5; return 0; }
+  return -1;
+}
+
+orc_reference *orc_reference_load(const char *path) {
+  SeqReader rd;
+  if (!rd.open(path)) return nullptr;
+  orc_reference *r = new orc_reference;
+  std::string n, s, q;
+  while (rd.next(n, s, q)) {
+    if (s.empty()) continue;  // sequence_batch.cc:84-118 keeps only length > 0
+    r->names.push_back(n);
+    r->lens.push_back(s.size());
+    s.append(64, '\0');
+    r->seqs.push_back(std::move(s));
+  }
+  rd.close();
+  return r;
+}
+orc_reference *orc_reference_from_memory(uint32_t n, const char *concat, const uint64_t *off, const char *const *names) {
+  orc_reference *r = new orc_reference;
+  for (u32 i = 0; i < n; ++i) {
+    std::string s(concat + off[i], off[i + 1] - off[i]);
+    r->lens.push_back(s.size());
+    s.append(64, '\0');
+    r->seqs.push_back(std::move(s));
+    r->names.push_back(names ? names[i] : ("chr" + std::to_string(i + 1)));
+  }
+  return r;
+}
+void orc_reference_free(orc_reference *r) { delete r; }
+uint32_t orc_reference_num_sequences(const orc_reference *r) { return r->seqs.size(); }
+uint32_t orc_reference_length(const orc_reference *r, uint32_t rid) { return r->lens[rid]; }
+const char *orc_reference_name(const orc_reference *r, uint32_t rid) { return r->names[rid].c_str(); }
+const char *orc_reference_seq(const orc_reference *r, uint32_t rid) { return r->seqs[rid].data(); }
+
+orc_index *orc_index_load(const char *path) {  // index.cc:132-169, khash.h:358-373
+  FILE *f = fopen(path, "rb");
+  if (!f) return nullptr;
+  orc_index *ix = new orc_index;
+  u32 lookup_size = 0, n_occ = 0;
+  bool ok = fread(&ix->k, 4, 1, f) == 1 && fread(&ix->w, 4, 1, f) == 1 && fread(&lookup_size, 4, 1, f) == 1;
+  ok = ok && fread(&ix->n_buckets, 4, 1, f) == 1 && fread(&ix->size, 4, 1, f) == 1 &&
+       fread(&ix->n_occupied, 4, 1, f) == 1 && fread(&ix->upper_bound, 4, 1, f) == 1;
+  if (ok && ix->n_buckets) {
+    const size_t fs = ix->n_buckets < 16 ? 1 : ix->n_buckets >> 4;
+    ix->flags.resize(fs); ix->keys.resize(ix->n_buckets); ix->vals.resize(ix->n_buckets);
+    ok = fread(ix->flags.data(), 4, fs, f) == fs && fread(ix->keys.data(), 8, ix->n_buckets, f) == ix->n_buckets &&
+         fread(ix->vals.data(), 8, ix->n_buckets, f) == ix->n_buckets;
+  }
+  ok = ok && fread(&n_occ, 4, 1, f) == 1;
+  if (ok && n_occ) { ix->occ.resize(n_occ); ok = fread(ix->occ.data(), 8, n_occ, f) == n_occ; }
+  fclose(f);
+  if (!ok) { delete ix; return nullptr; }
+  return ix;
+}
+
+int orc_index_save(const orc_index *ix, const char *path) {  // index.cc:91-130, khash.h:374-386
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  fwrite(&ix->k, 4, 1, f); fwrite(&ix->w, 4, 1, f); fwrite(&ix->size, 4, 1, f);
+  fwrite(&ix->n_buckets, 4, 1, f); fwrite(&ix->size, 4, 1, f); fwrite(&ix->n_occupied, 4, 1, f); fwrite(&ix->upper_bound, 4, 1, f);
+  if (ix->n_buckets) {
+    fwrite(ix->flags.data(), 4, ix->flags.size(), f);
+    fwrite(ix->keys.data(), 8, ix->n_buckets, f);
+    fwrite(ix->vals.data(), 8, ix->n_buckets, f);
+  }
+  const u32 n_occ = ix->occ.size();
+  fwrite(&n_occ, 4, 1, f);
+  if (n_occ) fwrite(ix->occ.data(), 8, n_occ, f);
+  fclose(f);
+  return 0;
+}
+
+orc_index *orc_index_build(const orc_reference *ref, int k, int w) {  // index.cc:12-89
+  std::vector<Mm> all;
+  for (u32 i = 0; i < ref->seqs.size(); ++i) gen_minimizers(ref->seqs[i].data(), ref->lens[i], i, k, w, all);
+  std::stable_sort(all.begin(), all.end(), [](const Mm &a, const Mm &b) { return a.hash < b.hash || (a.hash == b.hash && a.hit < b.hit); });
+  orc_index *ix = new orc_index;
+  ix->k = k; ix->w = w;
+  size_t n_keys = 0;
+  for (size_t i = 0; i < all.size(); ++i) if (i == 0 || all[i].hash != all[i - 1].hash) ++n_keys;
+  u32 nb = 4;
+  while ((u32)(nb * 0.77 + 0.5) < n_keys) nb <<= 1;  // kh_put grows when n_occupied >= upper_bound
+  ix->n_buckets = nb; ix->size = ix->n_occupied = n_keys; ix->upper_bound = (u32)(nb * 0.77 + 0.5);
+  ix->flags.assign(nb < 16 ? 1 : nb >> 4, 0xaaaaaaaau);
+  ix->keys.assign(nb, 0); ix->vals.assign(nb, 0);
+  const u32 m = nb - 1;
+  for (size_t i = 0; i < all.size();) {
+    size_t j = i;
+    while (j < all.size() && all[j].hash == all[i].hash) ++j;
+    u64 key = all[i].hash << 1, val;
+    if (j - i == 1) { key |= 1; val = all[i].hit; }
+    else { val = ((u64)ix->occ.size() << 32) | (u32)(j - i); for (size_t t = i; t < j; ++t) ix->occ.push_back(all[t].hit); }
+    u32 b = (u32)(all[i].hash) & m, step = 0;
+    while (!((ix->flags[b >> 4] >> ((b & 0xfU) << 1)) & 2)) b = (b + (++step)) & m;
+    ix->flags[b >> 4] &= ~(3u << ((b & 0xfU) << 1));
+    ix->keys[b] = key; ix->vals[b] = val;
+    i = j;
+  }
+  return ix;
+}
+void orc_index_free(orc_index *ix) { delete ix; }
+int orc_index_k(const orc_index *ix) { return ix->k; }
+int orc_index_w(const orc_index *ix) { return ix->w; }
+uint32_t orc_index_arrays(const orc_index *ix, const uint32_t **flags, const uint64_t **keys, const uint64_t **vals,
+                          const uint64_t **occ, uint32_t *n_occ) {
+  *flags = ix->flags.data(); *keys = ix->keys.data(); *vals = ix->vals.data(); *occ = ix->occ.data(); *n_occ = ix->occ.size();
+  return ix->n_buckets;
+}
+int orc_index_lookup(const orc_index *ix, uint64_t h, uint64_t *key, uint64_t *val) {
+  u64 k, v;
+  if (!ix->lookup(h, k, v)) return 0;
+  *key = k; *val = v;
+  return 1;
+}
+
+int orc_minimizers(const char *seq, uint32_t len, uint32_t seq_index, int k, int w, uint64_t *hash, uint64_t *hit, int cap) {
+  std::vector<Mm> v;
+  gen_minimizers(seq, len, seq_index, k, w, v);
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) { hash[i] = v[i].hash; hit[i] = v[i].hit; }
+  return v.size();
+}
+int orc_banded_align(int e, const char *pattern, const char *text, int read_len, int *end_pos) { return banded_align(e, pattern, text, read_len, end_pos); }
+void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len, int *start_pos) { banded_traceback(e, min_errors, pattern, text, read_len, start_pos); }
+
+orc_mapper *orc_mapper_create(const orc_params *p, const orc_index *ix, const orc_reference *ref) {
+  if (p->split_alignment || p->error_threshold >= 16 || p->output_format != 1) return nullptr;  // BED, non-split only
+  orc_mapper *m = new orc_mapper;
+  m->P = *p; m->ix = ix; m->ref = ref;
+  return m;
+}
+void orc_mapper_free(orc_mapper *m) { delete m; }
+
+extern "C" int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2,
+                         const uint32_t *off2, uint32_t first_read_id, orc_pe_record *out, int64_t cap_out, int n_threads,
+                         orc_pair_trace *trace);
+// Chunking of `#pragma omp taskloop grainsize(5000)` (chromap.h:892) by this image's libgomp (measured with
+// a stand-alone OpenMP probe): num_tasks = n/5000 (min 1); chunk = n/num_tasks, the first n%num_tasks
+// chunks one longer.  `generator` (chromap.h:863) is private to the parallel region, hence FIRSTPRIVATE
+// in every generated task: each chunk starts from a fresh copy of mt19937(11) and only pairs inside the
+// same chunk share a sampling stream.  So multi-mapper choices depend on (pair index in batch, batch
+// size) only — not on the thread count or the order tasks run in.
+int orc_ref_task_chunks(uint32_t n, uint32_t *starts, uint32_t *ends, int cap) {
+  u32 nt = n / 5000;
+  if (nt < 1) nt = 1;
+  if ((int)nt > cap) return -1;
+  const u32 chunk = n / nt, rem = n % nt;
+  u32 s = 0;
+  for (u32 t = 0; t < nt; ++t) { const u32 len = chunk + (t < rem ? 1 : 0); starts[t] = s; ends[t] = s + len; s += len; }
+  return nt;
+}
+
+int64_t orc_map_pairs(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2,
+                      const uint32_t *off2, uint32_t first_read_id, orc_pe_record *out, int64_t cap_out,
+                      orc_pair_trace *trace) {
+  return orc_map_pairs_mt(m, n, seq1, off1, seq2, off2, first_read_id, out, cap_out, 1, trace);
+}
+
+int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2,
+                         const uint32_t *off2, uint32_t first_read_id, orc_pe_record *out, int64_t cap_out, int n_threads,
+                         orc_pair_trace *trace) {
+  const int per = m->P.max_num_best_mappings;
+  std::vector<orc_pe_record> all((size_t)n * per);
+  std::vector<int> cnt(n, 0);
+  const u32 max_tasks = n / 5000 + 2;
+  std::vector<u32> st(max_tasks), en(max_tasks);
+  const int nt = orc_ref_task_chunks(n, st.data(), en.data(), max_tasks);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int t = 0; t < nt; ++t) {
+    std::mt19937 gen(11);  // firstprivate copy per task
+    for (u32 i = st[t]; i < en[t]; ++i)
+      cnt[i] = map_one_pair(m->P, *m->ix, *m->ref, gen, seq1 + off1[i], off1[i + 1] - off1[i], seq2 + off2[i],
+                            off2[i + 1] - off2[i], first_read_id + i, i, &all[(size_t)i * per], per, trace ? trace + i : nullptr);
+  }
+  int64_t n_out = 0;
+  for (u32 i = 0; i < n; ++i) for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) out[n_out++] = all[(size_t)i * per + j];
+  return n_out;
+}
+
+static inline auto rec_key(const orc_pe_record &r) {  // bed_mapping.h:208-215, prefixed by rid
+  return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, r.mapq, r.direction, r.is_unique, r.read_id,
+                         r.positive_alignment_length, r.negative_alignment_length);
+}
+static inline void tn5(orc_pe_record &r) {  // bed_mapping.h:225-230
+  r.fragment_start += 4; r.positive_alignment_length -= 4; r.fragment_length -= 9; r.negative_alignment_length -= 5;
+}
+
+int64_t orc_postprocess(const orc_params *p, orc_pe_record *recs, int64_t n) {
+  if (n == 0) return 0;
+  auto less = [](const orc_pe_record &a, const orc_pe_record &b) { return rec_key(a) < rec_key(b); };
+  auto same = [](const orc_pe_record &a, const orc_pe_record &b) {
+    return a.rid == b.rid && a.fragment_start == b.fragment_start && a.fragment_length == b.fragment_length;
+  };
+  int64_t o = 0;
+  if (p->low_memory_mode) {  // mapping_writer.h:166-376: merge == global sort; dedup; MAPQ filter; Tn5 last
+    std::sort(recs, recs + n, less);
+    int64_t i = 0;
+    while (i < n) {
+      orc_pe_record keep = recs[i];
+      u32 dups = 1;
+      int64_t j = i + 1;
+      if (p->remove_pcr_duplicates)
+        for (; j < n && same(recs[j], recs[i]); ++j) { ++dups; if (recs[j].mapq > keep.mapq) keep = recs[j]; }
+      if (keep.mapq >= p->mapq_threshold) {
+        keep.num_dups = std::min<u32>(255, dups);
+        if (p->tn5_shift) tn5(keep);
+        recs[o++] = keep;
+      }
+      i = j;
+    }
+    return o;
+  }
+  // chromap.h:1322-1355: Tn5 first, then sort (+ dedup keeping the last of each run), MAPQ filter at output
+  if (p->tn5_shift) for (int64_t i = 0; i < n; ++i) tn5(recs[i]);
+  std::sort(recs, recs + n, less);
+  if (p->remove_pcr_duplicates) {
+    int64_t i = 0, w = 0;
+    while (i < n) {
+      int64_t j = i + 1;
+      while (j < n && same(recs[j], recs[i])) ++j;
+      orc_pe_record keep = recs[j - 1];
+      keep.num_dups = std::min<u32>(255, (u32)(j - i));
+      recs[w++] = keep;
+      i = j;
+    }
+    n = w;
+  }
+  for (int64_t i = 0; i < n; ++i) if (recs[i].mapq >= p->mapq_threshold) recs[o++] = recs[i];
+  return o;
+}
+
+int64_t orc_format_bed(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf, int64_t cap) {
+  int64_t len = 0;
+  char line[512];
+  for (int64_t i = 0; i < n; ++i) {  // mapping_writer.cc:75-83
+    const orc_pe_record &r = recs[i];
+    const int l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t%c\t%u\n", ref->names[r.rid].c_str(), r.fragment_start,
+                           (u32)(r.fragment_start + r.fragment_length), (u32)r.mapq, r.direction ? '+' : '-', (u32)r.num_dups);
+    if (buf && len + l <= cap) memcpy(buf + len, line, l);
+    len += l;
+  }
+  return len;
+}
+
+int orc_run_files(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path,
+                  const char *read2_path, const char *out_path, int n_threads, double *mapping_seconds, uint64_t *n_pairs_out) {
+  orc_reference *ref = orc_reference_load(ref_path);
+  orc_index *ix = orc_index_load(index_path);
+  if (!ref || !ix) return -1;
+  orc_mapper *m = orc_mapper_create(p, ix, ref);
+  if (!m) return -2;
+  SeqReader r1, r2;
+  if (!r1.open(read1_path) || !r2.open(read2_path)) return -3;
+  std::vector<orc_pe_record> recs;
+  const u32 batch = 500000;  // chromap.h:182
+  u32 read_id = 0;
+  double secs = 0;
+  uint64_t total = 0;
+  for (;;) {
+    std::string s1, s2;
+    std::vector<u32> o1{0}, o2{0};
+    std::string n, s, q;
+    u32 cnt = 0;
+    while (cnt < batch) {
+      bool a = r1.next(n, s, q);
+      while (a && s.empty()) a = r1.next(n, s, q);  // sequence_batch.cc:28-31 skips empty reads
+      if (!a) break;
+      s1 += s; o1.push_back(s1.size());
+      bool b = r2.next(n, s, q);
+      while (b && s.empty()) b = r2.next(n, s, q);
+      if (!b) { fprintf(stderr, "Numbers of reads don't match!\n"); return -4; }
+      s2 += s; o2.push_back(s2.size());
+      ++cnt;
+    }
+    if (cnt == 0) break;
+    const size_t base = recs.size();
+    recs.resize(base + (size_t)cnt * p->max_num_best_mappings);
+    auto t0 = std::chrono::steady_clock::now();
+    int64_t got = orc_map_pairs_mt(m, cnt, s1.data(), o1.data(), s2.data(), o2.data(), read_id, recs.data() + base, recs.size() - base, n_threads, nullptr);
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    recs.resize(base + got);
+    read_id += cnt;
+    total += cnt;
+  }
+  r1.close(); r2.close();
+  const int64_t keep = orc_postprocess(p, recs.data(), recs.size());
+  const int64_t bytes = orc_format_bed(ref, recs.data(), keep, nullptr, 0);
+  std::vector<char> text(bytes + 1);
+  orc_format_bed(ref, recs.data(), keep, text.data(), bytes);
+  FILE *f = fopen(out_path, "wb");
+  if (!f) return -5;
+  fwrite(text.data(), 1, bytes, f);
+  fclose(f);
+  if (mapping_seconds) *mapping_seconds = secs;
+  if (n_pairs_out) *n_pairs_out = total;
+  orc_mapper_free(m); orc_index_free(ix); orc_reference_free(ref);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// TEST INFRASTRUCTURE ONLY — CPU restatement ("oracle") of Chromap's per-read mapping hot path.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// build, link, import or execute anything under oracle/.  The product (chromap_b200/) never does.
+//
+// Parity pinning: this restatement is checked (tests/test_oracle_vs_reference.py, run in the build
+// container where /root/reference exists) against the UNMODIFIED reference binary compiled by
+// oracle/Makefile into oracle/_ref/chromap: BED output md5-identical on the reference's own
+// test/ data (SURVEY.md §4 golden md5s) and on seeded synthetic data for --preset chip / atac.
+// The reference ships no unit tests or golden vectors of its own, so the compiled
+// binary is the only pin; the committed fixtures under tests/golden/ were produced by it.
+//
+// Every function cites the reference file:line it restates (paths relative to /root/reference/src).
+#ifndef ORACLE_CHROMAP_H_
+#define ORACLE_CHROMAP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// Mirror of the MappingParameters fields used on the path (mapping_parameters.h:18-78).
+typedef struct {
+  int32_t error_threshold;        // -e, default 8
+  int32_t min_num_seeds;          // -s, default 2
+  int32_t max_seed_freq0;         // -f first, default 500
+  int32_t max_seed_freq1;         // -f second, default 1000
+  int32_t max_num_best_mappings;  // -n, default 1
+  int32_t max_insert_size;        // -l, default 1000
+  int32_t mapq_threshold;         // -q, default 30
+  int32_t min_read_length;        // --min-read-length, default 30
+  int32_t drop_repetitive_reads;  // default 500000
+  int32_t trim_adapters;
+  int32_t remove_pcr_duplicates;
+  int32_t tn5_shift;
+  int32_t split_alignment;
+  int32_t low_memory_mode;
+  int32_t output_format;  // 1 = BED (only BED is restated)
+} orc_params;
+
+void orc_default_params(orc_params *p);
+// preset: "chip" | "atac" | "hic" | "" (chromap_driver.cc:247-275).  Returns 0, or -1 if unknown.
+int orc_apply_preset(orc_params *p, const char *preset);
+
+typedef struct orc_index orc_index;
+typedef struct orc_reference orc_reference;
+
+// Index file loader (index.cc:132-169, khash.h:358-373) and builder (index.cc:12-89; the hash table
+// layout differs from khash's insertion history but answers every lookup identically).
+orc_index *orc_index_load(const char *path);
+orc_index *orc_index_build(const orc_reference *ref, int k, int w);
+int orc_index_save(const orc_index *idx, const char *path);
+void orc_index_free(orc_index *idx);
+int orc_index_k(const orc_index *idx);
+int orc_index_w(const orc_index *idx);
+// Raw views for uploading the same index to the device: khash arrays + occurrence table.
+uint32_t orc_index_arrays(const orc_index *idx, const uint32_t **flags, const uint64_t **keys,
+                          const uint64_t **vals, const uint64_t **occ, uint32_t *n_occ);
+// kh_get + key/value fetch (khash.h:232-245).  Returns 1 if found.
+int orc_index_lookup(const orc_index *idx, uint64_t minimizer_hash, uint64_t *key, uint64_t *val);
+
+orc_reference *orc_reference_load(const char *fasta_path);
+// Build from memory: n sequences, concatenated bases + offsets[n+1]; names may be NULL.
+orc_reference *orc_reference_from_memory(uint32_t n, const char *concat, const uint64_t *offsets,
+                                         const char *const *names);
+void orc_reference_free(orc_reference *ref);
+uint32_t orc_reference_num_sequences(const orc_reference *ref);
+uint32_t orc_reference_length(const orc_reference *ref, uint32_t rid);
+const char *orc_reference_name(const orc_reference *ref, uint32_t rid);
+const char *orc_reference_seq(const orc_reference *ref, uint32_t rid);
+
+// minimizer_generator.cc:7-139.  Writes up to cap (hash, hit) pairs; returns the count.
+int orc_minimizers(const char *seq, uint32_t len, uint32_t seq_index, int k, int w, uint64_t *hash,
+                   uint64_t *hit, int cap);
+
+// alignment.cc:141-192 (scalar banded Myers).  pattern = reference window of read_len + 2e bytes.
+int orc_banded_align(int e, const char *pattern, const char *text, int read_len, int *end_pos);
+// alignment.cc:656-718.
+void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len,
+                          int *start_pos);
+
+// One PE record as emitted by mapping_generator.cc:110-123 (before sort/dedup).
+typedef struct {
+  uint32_t read_id;
+  uint32_t rid;
+  uint32_t fragment_start;
+  uint16_t fragment_length;
+  uint8_t mapq;
+  uint8_t direction;  // 1 = read1 on + strand
+  uint8_t is_unique;
+  uint8_t num_dups;
+  uint16_t positive_alignment_length;
+  uint16_t negative_alignment_length;
+} orc_pe_record;
+
+// Optional per-stage trace of one pair (for stage-level parity tests against the CUDA stages).
+typedef struct {
+  // per mate (index 0/1)
+  int32_t n_minimizers[2];
+  int32_t n_pos_candidates_gen[2], n_neg_candidates_gen[2];  // after GenerateCandidates
+  int32_t n_pos_candidates[2], n_neg_candidates[2];          // entering verification
+  int32_t n_pos_mappings[2], n_neg_mappings[2];
+  int32_t min_errors[2], second_min_errors[2], n_best[2], n_second_best[2];
+  uint32_t repetitive_seed_length[2];
+  int32_t supplement_result;
+  int32_t min_sum_errors, second_min_sum_errors, n_best_pairs, n_second_best_pairs;
+  int32_t n_records;
+  int32_t trimmed_len[2];
+} orc_pair_trace;
+
+typedef struct orc_mapper orc_mapper;  // params + borrowed index/reference
+orc_mapper *orc_mapper_create(const orc_params *p, const orc_index *idx, const orc_reference *ref);
+void orc_mapper_free(orc_mapper *m);
+
+// The taskloop body, chromap.h:892-1143, for ONE reference batch: pairs [0, n) (n <= 500000 in the
+// reference, chromap.h:182) given as concatenated ASCII + offsets.  Records are written to `out`
+// (capacity cap_out) in read order; returns the number written.  first_read_id = running read counter
+// (sequence_batch.cc:38-39).  trace may be NULL (else n entries).  Multi-mapper sampling restarts from
+// mt19937(11) at every taskloop chunk (see orc_ref_task_chunks), exactly like the reference at any -t.
+int64_t orc_map_pairs(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1,
+                      const char *seq2, const uint32_t *off2, uint32_t first_read_id,
+                      orc_pe_record *out, int64_t cap_out, orc_pair_trace *trace);
+// Task chunks [starts[t], ends[t]) the reference's taskloop cuts pairs [0,n) into.  Returns #chunks.
+int orc_ref_task_chunks(uint32_t n, uint32_t *starts, uint32_t *ends, int cap);
+// Same as orc_map_pairs with chunks spread over n_threads host threads (results are identical).
+int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1,
+                         const char *seq2, const uint32_t *off2, uint32_t first_read_id,
+                         orc_pe_record *out, int64_t cap_out, int n_threads, orc_pair_trace *trace);
+
+// Post-processing (mapping_processor.h:100-202, mapping_writer.h:166-376, chromap.h:1305-1355):
+// sort / dedup / Tn5 / MAPQ filter, in place.  Returns the number of surviving records, sorted in
+// output order (rid, then record operator<).
+int64_t orc_postprocess(const orc_params *p, orc_pe_record *recs, int64_t n);
+// BED text (mapping_writer.cc:75-83).  Returns bytes written into buf (or needed if buf==NULL).
+int64_t orc_format_bed(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf,
+                       int64_t cap);
+
+// Whole-file driver: FASTQ pair -> BED file, equivalent to `chromap -x idx -r ref -1 r1 -2 r2 -o out`.
+int orc_run_files(const orc_params *p, const char *index_path, const char *ref_path,
+                  const char *read1_path, const char *read2_path, const char *out_path,
+                  int n_threads, double *mapping_seconds, uint64_t *n_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  // ORACLE_CHROMAP_H_

@@ -1,0 +1,33 @@
+#!/bin/bash
+# Regenerates tests/golden/ from the UNMODIFIED reference binary (oracle/_ref/chromap, built by
+# oracle/Makefile from /root/reference).  Run in the build container only.  Outputs are committed.
+set -e
+cd "$(dirname "$0")"
+REPO=$(cd ../.. && pwd)
+REF=$REPO/oracle/_ref/chromap
+rm -rf synth_small && mkdir -p synth_small
+python $REPO/tools/gen_synth.py --out synth_small --seed 11 --n-seq 3 --seq-len 300000 --n-pairs 6000 \
+  --repeat-copies 20 --repeat-len 2000 --fam-copies 700 --short-frac 0.3 --lowercase-frac 0.05
+cd synth_small
+$REF -i -r ref.fa -o ref.index 2> /dev/null
+run() { name=$1; shift; $REF "$@" -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o $name.bed -t 1 2> /dev/null; }
+run chip --preset chip
+run atac --preset atac
+run default
+run q0dedup --remove-pcr-duplicates -q 0
+run e5 -e 5 -q 10 --Tn5-shift --remove-pcr-duplicates
+run e12l300 -e 12 -l 300 -q 0
+md5sum *.bed > md5.txt
+gzip -9 -n ref.fa read1.fq read2.fq *.bed
+rm -f ref.index
+# the reference's own test data (README quick start): golden BEDs for SURVEY.md §4's md5s
+cd .. && rm -rf ref_test && mkdir ref_test && cd ref_test
+T=/root/reference/test
+cp $T/ref.fa $T/read1.fq $T/read2.fq .
+$REF -i -r ref.fa -o ref.index 2> /dev/null
+$REF -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o default.bed -t 1 2> /dev/null
+$REF --preset chip -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o chip.bed -t 1 2> /dev/null
+$REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o atac.bed -t 1 2> /dev/null
+$REF --preset hic -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o hic.pairs -t 1 2> /dev/null
+md5sum default.bed chip.bed atac.bed hic.pairs ref.index > md5.txt
+gzip -9 -n ref.fa

@@ -1,0 +1,97 @@
+"""The CPU oracle (oracle/) against golden vectors produced by the UNMODIFIED reference binary
+(tests/golden/make_golden.sh).  CPU only."""
+import gzip
+import hashlib
+import os
+
+import pytest
+
+from oracle import oracle_py as orc
+
+
+def _md5s(d):
+    out = {}
+    for line in open(os.path.join(d, "md5.txt")):
+        h, name = line.split()
+        out[name] = h
+    return out
+
+
+CASES = {
+    "chip": dict(preset="chip"),
+    "atac": dict(preset="atac"),
+    "default": dict(preset=""),
+    "q0dedup": dict(preset="", remove_pcr_duplicates=1, mapq_threshold=0),
+    "e5": dict(preset="", error_threshold=5, mapq_threshold=10, tn5_shift=1, remove_pcr_duplicates=1),
+    "e12l300": dict(preset="", error_threshold=12, max_insert_size=300, mapq_threshold=0),
+}
+
+
+@pytest.fixture(scope="module")
+def synth_index(golden_dir, tmp_path_factory):
+    d = os.path.join(golden_dir, "synth_small")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)  # our builder; lookups must equal the reference's khash index
+    p = str(tmp_path_factory.mktemp("idx") / "synth.index")
+    assert idx.save(p) == 0
+    return d, p
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_synth_small_matches_reference_binary(case, synth_index, tmp_path):
+    d, index_path = synth_index
+    kw = dict(CASES[case])
+    params = orc.make_params(kw.pop("preset"), **kw)
+    out = str(tmp_path / "o.bed")
+    orc.run_files(params, index_path, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"),
+                  os.path.join(d, "read2.fq.gz"), out, n_threads=1)
+    got = open(out, "rb").read()
+    want = gzip.open(os.path.join(d, case + ".bed.gz")).read()
+    assert hashlib.md5(want).hexdigest() == _md5s(d)[case + ".bed"]
+    assert got == want
+
+
+@pytest.mark.parametrize("case,preset", [("default", ""), ("chip", "chip"), ("atac", "atac")])
+def test_reference_quickstart_data(case, preset, golden_dir, tmp_path):
+    """SURVEY.md §4 golden md5s on /root/reference/test data, with the reference-built index file."""
+    d = os.path.join(golden_dir, "ref_test")
+    out = str(tmp_path / "o.bed")
+    orc.run_files(orc.make_params(preset), os.path.join(d, "ref.index"), os.path.join(d, "ref.fa.gz"),
+                  os.path.join(d, "read1.fq"), os.path.join(d, "read2.fq"), out)
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == _md5s(d)[case + ".bed"]
+    want = {"default": "e311f0a0848edca7196d839f47b3e007", "chip": "e311f0a0848edca7196d839f47b3e007",
+            "atac": "63b977e6e8af35be7861f35b6163f714"}[case]
+    assert _md5s(d)[case + ".bed"] == want
+
+
+def test_threads_do_not_change_output(synth_index, tmp_path):
+    d, index_path = synth_index
+    params = orc.make_params("", remove_pcr_duplicates=1, mapq_threshold=0)
+    outs = []
+    for t in (1, 4):
+        out = str(tmp_path / ("o%d.bed" % t))
+        orc.run_files(params, index_path, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"),
+                      os.path.join(d, "read2.fq.gz"), out, n_threads=t)
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1]
+
+
+def test_index_builder_equals_reference_index(golden_dir):
+    """Our index builder answers every lookup like the khash table the reference binary wrote."""
+    import numpy as np
+    d = os.path.join(golden_dir, "ref_test")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    theirs = orc.Index(os.path.join(d, "ref.index"))
+    ours = orc.Index(ref=ref, k=theirs.k, w=theirs.w)
+    a, b = theirs.arrays(), ours.arrays()
+    assert a["n_buckets"] == b["n_buckets"] == 32768
+    assert np.array_equal(a["occ"], b["occ"])
+    import ctypes as C
+    h, _ = orc.minimizers(ref.seq(0), theirs.k, theirs.w)
+    assert len(h) == 25079
+    L = orc.lib()
+    for x in h[::7]:
+        k1, v1, k2, v2 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        assert L.orc_index_lookup(theirs.h, int(x), C.byref(k1), C.byref(v1)) == 1
+        assert L.orc_index_lookup(ours.h, int(x), C.byref(k2), C.byref(v2)) == 1
+        assert (k1.value, v1.value) == (k2.value, v2.value)
