@@ -1,0 +1,260 @@
+"""ctypes binding of include/chromap_b200.h.  Mirrors the reference's paired-end mapping call
+(Chromap::MapPairedEndReads, chromap.h:636) at batch granularity."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libchromap_b200.so")
+
+
+class CmxError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "error_threshold", "min_num_seeds", "max_seed_freq0", "max_seed_freq1", "max_num_best_mappings",
+        "max_insert_size", "mapq_threshold", "min_read_length", "drop_repetitive_reads", "trim_adapters",
+        "remove_pcr_duplicates", "tn5_shift", "split_alignment", "low_memory_mode", "output_format",
+        "batch_size", "max_read_length")]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint32), ("seq1", C.c_void_p), ("off1", C.c_void_p), ("seq2", C.c_void_p),
+                ("off2", C.c_void_p), ("first_read_id", C.c_uint32), ("on_device", C.c_int32)]
+
+
+class Records(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("capacity", C.c_uint64), ("n_records", C.c_uint64), ("on_device", C.c_int32),
+                ("n_mapped_pairs", C.c_uint64), ("n_uniquely_mapped_pairs", C.c_uint64), ("n_candidates", C.c_uint64),
+                ("n_overflow_pairs", C.c_uint64)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms",
+                                         "select_ms", "emit_ms", "d2h_ms", "total_ms")] + \
+               [(n, C.c_uint64) for n in ("n_minimizers", "n_probe_steps", "n_found", "n_occ_reads", "n_verified",
+                                          "n_launches")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u4"), ("fragment_length", "<u2"),
+                      ("mapq", "u1"), ("direction", "u1"), ("is_unique", "u1"), ("num_dups", "u1"),
+                      ("positive_alignment_length", "<u2"), ("negative_alignment_length", "<u2")], align=True)
+assert PE_RECORD.itemsize == 24
+
+PAIR_TRACE = np.dtype([("n_minimizers", "<i4", 2), ("n_pos_candidates_gen", "<i4", 2), ("n_neg_candidates_gen", "<i4", 2),
+                       ("n_pos_candidates", "<i4", 2), ("n_neg_candidates", "<i4", 2), ("n_pos_mappings", "<i4", 2),
+                       ("n_neg_mappings", "<i4", 2), ("min_errors", "<i4", 2), ("second_min_errors", "<i4", 2),
+                       ("n_best", "<i4", 2), ("n_second_best", "<i4", 2), ("repetitive_seed_length", "<u4", 2),
+                       ("supplement_result", "<i4"), ("min_sum_errors", "<i4"), ("second_min_sum_errors", "<i4"),
+                       ("n_best_pairs", "<i4"), ("n_second_best_pairs", "<i4"), ("n_records", "<i4"),
+                       ("trimmed_len", "<i4", 2)], align=True)
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA C-ABI library.  Fails loudly when it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise CmxError("chromap_b200: %s is missing — run __graft_entry__.build() (nvcc, sm_100a). "
+                       "There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    vp, u32, u64, i32, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int64
+    L.cmx_default_params.argtypes = [C.POINTER(Params)]
+    L.cmx_apply_preset.argtypes = [C.POINTER(Params), C.c_char_p]
+    L.cmx_create.argtypes = [C.POINTER(vp), i32, C.POINTER(Params)]
+    L.cmx_destroy.argtypes = [vp]
+    L.cmx_last_error.restype = C.c_char_p; L.cmx_last_error.argtypes = [vp]
+    L.cmx_upload_reference.argtypes = [vp, u32, vp, vp]
+    L.cmx_upload_index.argtypes = [vp, i32, i32, u32, vp, vp, vp, vp, u32]
+    L.cmx_build_index.argtypes = [vp, i32, i32]
+    L.cmx_download_index.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), vp, vp, vp, C.POINTER(u32), vp]
+    L.cmx_index_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.cmx_map_batch_pe.argtypes = [vp, C.POINTER(Batch), C.POINTER(Records), vp]
+    L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
+    L.cmx_stage_minimizers.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, u32]
+    L.cmx_stage_probe.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.cmx_stage_banded_align.argtypes = [vp, i32, i32, vp, vp, u64, vp, vp]
+    L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
+    L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
+    _lib = L
+    return L
+
+
+def make_params(preset="", **kw):
+    L = load_library()
+    p = Params()
+    L.cmx_default_params(C.byref(p))
+    if L.cmx_apply_preset(C.byref(p), preset.encode()) != 0:
+        raise CmxError("Unrecognized preset parameters " + preset)
+    for k, v in kw.items():
+        setattr(p, k, int(v))
+    return p
+
+
+def taskloop_chunks(n, grain=5000):
+    """Chunk starts of the reference's `taskloop grainsize(5000)` (chromap.h:892) over n pairs."""
+    nt = max(1, n // grain)
+    chunk, rem = divmod(n, nt)
+    starts, s = [], 0
+    for t in range(nt):
+        starts.append(s)
+        s += chunk + (1 if t < rem else 0)
+    return starts
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return a.data_ptr()
+    return int(a)
+
+
+class Mapper:
+    """One GPU context: reference + index resident in HBM, batches of read pairs in, PE records out."""
+
+    def __init__(self, params=None, device=0):
+        self.L = load_library()
+        self.params = params if params is not None else make_params()
+        h = C.c_void_p()
+        rc = self.L.cmx_create(C.byref(h), device, C.byref(self.params))
+        if rc == -1:
+            raise CmxError("chromap_b200: no CUDA device — the product path has no CPU fallback")
+        if rc != 0:
+            raise CmxError("cmx_create failed (%d): unsupported parameters" % rc)
+        self.h = h
+        self.names = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cmx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CmxError("%s failed (%d): %s" % (what, rc, self.L.cmx_last_error(self.h).decode()))
+
+    def upload_reference(self, seqs, names=None):
+        """seqs: list of uint8 arrays (ASCII bases as loaded)."""
+        concat = np.ascontiguousarray(np.concatenate(seqs).astype(np.uint8))
+        offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+        self._check(self.L.cmx_upload_reference(self.h, len(seqs), offs.ctypes.data, concat.ctypes.data), "cmx_upload_reference")
+        self.names = names or ["chr%d" % (i + 1) for i in range(len(seqs))]
+
+    def upload_index(self, k, w, n_buckets, flags, keys, vals, occ):
+        flags = np.ascontiguousarray(flags, dtype=np.uint32); keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint64); occ = np.ascontiguousarray(occ, dtype=np.uint64)
+        self._check(self.L.cmx_upload_index(self.h, k, w, n_buckets, flags.ctypes.data, keys.ctypes.data, vals.ctypes.data,
+                                            occ.ctypes.data if len(occ) else None, len(occ)), "cmx_upload_index")
+
+    def build_index(self, k=17, w=7):
+        self._check(self.L.cmx_build_index(self.h, k, w), "cmx_build_index")
+
+    def index_info(self):
+        k, w = C.c_int(), C.c_int()
+        nk, no, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.cmx_index_info(self.h, C.byref(k), C.byref(w), C.byref(nk), C.byref(no), C.byref(ns)), "cmx_index_info")
+        return dict(k=k.value, w=w.value, n_keys=nk.value, n_occ=no.value, table_slots=ns.value)
+
+    def download_index(self):
+        nb, nk, no = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self.L.cmx_download_index(self.h, C.byref(nb), C.byref(nk), None, None, None, C.byref(no), None), "cmx_download_index")
+        flags = np.zeros(max(1, nb.value >> 4), dtype=np.uint32)
+        keys = np.zeros(nb.value, dtype=np.uint64); vals = np.zeros(nb.value, dtype=np.uint64)
+        occ = np.zeros(no.value, dtype=np.uint64)
+        self._check(self.L.cmx_download_index(self.h, C.byref(nb), C.byref(nk), flags.ctypes.data, keys.ctypes.data, vals.ctypes.data,
+                                              C.byref(no), occ.ctypes.data if no.value else None), "cmx_download_index")
+        return dict(n_buckets=nb.value, n_keys=nk.value, flags=flags, keys=keys, vals=vals, occ=occ)
+
+    def map_batch(self, seq1, off1, seq2, off2, first_read_id=0, on_device=False, n_pairs=None, out=None, out_on_device=False):
+        """Host numpy arrays (or device pointers / torch tensors when on_device).  Returns (records, stats)."""
+        n = n_pairs if n_pairs is not None else len(off1) - 1
+        if not on_device:
+            seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
+            off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
+        b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), first_read_id, 1 if on_device else 0)
+        mb = self.params.max_num_best_mappings
+        if out is None:
+            out = np.zeros(n * mb, dtype=PE_RECORD)
+        cap = (out.numel() * out.element_size() // 24) if hasattr(out, "data_ptr") else len(out)
+        r = Records(_ptr(out), cap, 0, 1 if out_on_device else 0, 0, 0, 0, 0)
+        rc = self.L.cmx_map_batch_pe(self.h, C.byref(b), C.byref(r), None)
+        self._check(rc, "cmx_map_batch_pe")
+        stats = dict(n_records=r.n_records, n_mapped_pairs=r.n_mapped_pairs, n_uniquely_mapped_pairs=r.n_uniquely_mapped_pairs,
+                     n_candidates=r.n_candidates, n_overflow_pairs=r.n_overflow_pairs)
+        if out_on_device:
+            return out, stats
+        return out[:r.n_records], stats
+
+    def timing(self):
+        t = Timing()
+        self._check(self.L.cmx_last_batch_timing(self.h, C.byref(t)), "cmx_last_batch_timing")
+        return t.asdict()
+
+    def trace(self, n_pairs):
+        out = np.zeros(n_pairs, dtype=PAIR_TRACE)
+        self._check(self.L.cmx_last_batch_trace(self.h, out.ctypes.data, n_pairs), "cmx_last_batch_trace")
+        return out
+
+    def postprocess(self, recs):
+        recs = np.ascontiguousarray(recs.copy())
+        n = C.c_uint64()
+        self._check(self.L.cmx_postprocess(self.h, recs.ctypes.data, len(recs), C.byref(n)), "cmx_postprocess")
+        return recs[:n.value]
+
+    def format_bed(self, recs, names=None):
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        recs = np.ascontiguousarray(recs)
+        n = self.L.cmx_format_bed(arr, recs.ctypes.data, len(recs), None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.cmx_format_bed(arr, recs.ctypes.data, len(recs), buf, n)
+        return buf.raw[:n]
+
+    # ---- stage entry points
+    def stage_minimizers(self, seq1, off1, seq2, off2, stride):
+        n = len(off1) - 1
+        seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
+        off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
+        b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), 0, 0)
+        h = np.zeros((2 * n, stride), dtype=np.uint64); p = np.zeros((2 * n, stride), dtype=np.uint32)
+        cnt = np.zeros(2 * n, dtype=np.int32)
+        self._check(self.L.cmx_stage_minimizers(self.h, C.byref(b), h.ctypes.data, p.ctypes.data, cnt.ctypes.data, stride), "cmx_stage_minimizers")
+        return h, p, cnt
+
+    def stage_probe(self, hashes):
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        n = len(hashes)
+        f = np.zeros(n, dtype=np.uint8); k = np.zeros(n, dtype=np.uint64); v = np.zeros(n, dtype=np.uint64)
+        self._check(self.L.cmx_stage_probe(self.h, hashes.ctypes.data, n, f.ctypes.data, k.ctypes.data, v.ctypes.data), "cmx_stage_probe")
+        return f, k, v
+
+    def stage_banded_align(self, e, read_len, patterns, texts):
+        patterns = np.ascontiguousarray(patterns, dtype=np.uint8); texts = np.ascontiguousarray(texts, dtype=np.uint8)
+        n = texts.size // read_len
+        err = np.zeros(n, dtype=np.int32); endp = np.zeros(n, dtype=np.int32)
+        self._check(self.L.cmx_stage_banded_align(self.h, e, read_len, patterns.ctypes.data, texts.ctypes.data, n, err.ctypes.data, endp.ctypes.data), "cmx_stage_banded_align")
+        return err, endp

@@ -1,0 +1,719 @@
+// chromap_b200 — C-ABI implementation (include/chromap_b200.h): context, device index / reference,
+// batch pipeline driver (tiers, streams, events), stage entry points.  sm_100a.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/chromap_b200.h"
+#include "index_build.cuh"
+#include "pipeline_kernels.cuh"
+
+static_assert(sizeof(OutRecord) == sizeof(cmx_pe_record), "record layout");
+static_assert(sizeof(cmx_pe_record) == 24, "record size");
+
+#define N_TIERS 3
+
+struct DevBuf {  // grow-only device buffer
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Tier {
+  Caps caps;
+  int slots_cap = 0;
+  DevBuf mem;
+  DevBuf ovf_list;   // pairs that overflowed THIS tier
+  int n_slots = 0;   // used in the current batch
+  const int *pair_list = nullptr;
+  Scratch view;
+};
+
+struct cmx_ctx {
+  int device = 0;
+  cmx_params params;
+  DevParams dp;
+  std::string err;
+  // reference
+  u8 *ref_seq = nullptr;
+  u64 *ref_off = nullptr;
+  u32 *ref_len = nullptr;
+  u32 n_seq = 0;
+  u64 ref_bytes = 0;
+  std::vector<u64> h_ref_off;
+  std::vector<u32> h_ref_len;
+  // index
+  ulonglong2 *slots = nullptr;
+  u64 n_slots = 0;
+  u64 *occ = nullptr;
+  u32 n_occ = 0;
+  u64 n_keys = 0;
+  int k = 0, w = 0;
+  // mapq tables
+  double *inv_log = nullptr;
+  int *pen_thr = nullptr;
+  // per-batch buffers
+  DevBuf seq1, off1, seq2, off2, nbest, sel, out_rec, out_n, offs, out_compact, chunk_start, cub_tmp, trace;
+  Counters *ctr = nullptr;
+  int *d_count = nullptr;
+  Tier tiers[N_TIERS];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10];
+  cmx_timing timing;
+  u32 last_n_pairs = 0;
+  int last_tiers_used = 0;
+};
+
+static int fail(cmx_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static cudaError_t ensure(DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e == cudaSuccess) b.cap = want;
+  return e;
+}
+static void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+extern "C" {
+
+void cmx_default_params(cmx_params *p) {
+  p->error_threshold = 8; p->min_num_seeds = 2; p->max_seed_freq0 = 500; p->max_seed_freq1 = 1000;
+  p->max_num_best_mappings = 1; p->max_insert_size = 1000; p->mapq_threshold = 30; p->min_read_length = 30;
+  p->drop_repetitive_reads = 500000; p->trim_adapters = 0; p->remove_pcr_duplicates = 0; p->tn5_shift = 0;
+  p->split_alignment = 0; p->low_memory_mode = 0; p->output_format = 1; p->batch_size = 500000; p->max_read_length = 160;
+}
+
+int cmx_apply_preset(cmx_params *p, const char *preset) {  // chromap_driver.cc:247-275
+  const std::string s = preset ? preset : "";
+  if (s.empty()) return CMX_OK;
+  if (s == "atac") { p->max_insert_size = 2000; p->trim_adapters = 1; p->remove_pcr_duplicates = 1; p->tn5_shift = 1; p->low_memory_mode = 1; p->output_format = 1; return CMX_OK; }
+  if (s == "chip") { p->max_insert_size = 2000; p->remove_pcr_duplicates = 1; p->low_memory_mode = 1; p->output_format = 1; return CMX_OK; }
+  if (s == "hic") { p->error_threshold = 4; p->mapq_threshold = 1; p->split_alignment = 1; p->low_memory_mode = 1; p->output_format = 5; return CMX_OK; }
+  return CMX_ERR_INVALID;
+}
+
+const char *cmx_last_error(const cmx_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
+  if (!out || !params) return CMX_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device >= n_dev) return CMX_ERR_NO_DEVICE;
+  if (params->split_alignment || params->output_format != 1) return CMX_ERR_INVALID;  // BED, non-split this round
+  if (params->error_threshold < 1 || params->error_threshold >= 16) return CMX_ERR_INVALID;  // mapping_parameters.h:80-88
+  if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
+  if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
+  cmx_ctx *ctx = new cmx_ctx;
+  ctx->device = device;
+  ctx->params = *params;
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
+  CU(cudaMalloc(&ctx->ctr, sizeof(Counters)));
+  CU(cudaMalloc(&ctx->d_count, sizeof(int) * 4));
+  // MAPQ tables from the host libm, so truncations match the reference bit for bit (mapping_generator.h:920-1022)
+  {
+    std::vector<double> il(65536, 0.0);
+    const int coef_frac = log(50);
+    for (int a = 2; a < 65536; ++a) il[a] = coef_frac / log((unsigned short)a);
+    std::vector<int> thr(96, 0x7fffffff);
+    for (int v = 0; v < 96; ++v) {  // smallest n >= 0 with (int)(4.343*log(n+1)+0.499) >= v (monotone in n)
+      long long lo = 0, hi = 0x7ffffffeLL;
+      auto pen = [](long long n) { return (int)(4.343 * log((double)(n + 1)) + 0.499); };
+      if (pen(hi) < v) { thr[v] = 0x7fffffff; continue; }
+      while (lo < hi) { const long long mid = (lo + hi) / 2; if (pen(mid) >= v) hi = mid; else lo = mid + 1; }
+      thr[v] = (int)lo;
+    }
+    CU(cudaMalloc(&ctx->inv_log, 65536 * sizeof(double)));
+    CU(cudaMalloc(&ctx->pen_thr, 96 * sizeof(int)));
+    CU(cudaMemcpy(ctx->inv_log, il.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->pen_thr, thr.data(), 96 * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const int mrl = params->max_read_length;
+  ctx->tiers[0].caps = {mrl, 64, 32, 32};
+  ctx->tiers[1].caps = {mrl * 2, 1024, 256, 256};
+  ctx->tiers[2].caps = {mrl * 4, 65536, 8192, 8192};
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  *out = ctx;
+  return CMX_OK;
+}
+
+void cmx_destroy(cmx_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
+  cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr);
+  cudaFree(ctx->ctr); cudaFree(ctx->d_count);
+  for (DevBuf *b : {&ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->nbest, &ctx->sel, &ctx->out_rec, &ctx->out_n, &ctx->offs,
+                    &ctx->out_compact, &ctx->chunk_start, &ctx->cub_tmp, &ctx->trace})
+    release(*b);
+  for (auto &t : ctx->tiers) { release(t.mem); release(t.ovf_list); }
+  for (auto &e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int cmx_upload_reference(cmx_ctx *ctx, uint32_t n_seq, const uint64_t *offsets, const char *concat) {
+  if (!ctx || !offsets || !concat || n_seq == 0) return CMX_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
+  ctx->ref_seq = nullptr; ctx->ref_off = nullptr; ctx->ref_len = nullptr;
+  // device layout: [64 NUL][seq0][64.. NUL][seq1]...  every sequence start 64-byte aligned, >= 64 NULs after each
+  const u64 PAD = 64;
+  std::vector<u64> doff(n_seq);
+  std::vector<u32> dlen(n_seq);
+  u64 cur = PAD;
+  for (u32 i = 0; i < n_seq; ++i) {
+    const u64 len = offsets[i + 1] - offsets[i];
+    if (len >= 0xFFFFFFFFull) return fail(ctx, CMX_ERR_INVALID, "reference sequence %u too long for 32-bit positions", i);
+    doff[i] = cur; dlen[i] = (u32)len;
+    cur = (cur + len + PAD + 63) / 64 * 64;
+  }
+  ctx->ref_bytes = cur + PAD;
+  CU(cudaMalloc(&ctx->ref_seq, ctx->ref_bytes));
+  CU(cudaMemset(ctx->ref_seq, 0, ctx->ref_bytes));
+  for (u32 i = 0; i < n_seq; ++i)
+    CU(cudaMemcpy(ctx->ref_seq + doff[i], concat + offsets[i], dlen[i], cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&ctx->ref_off, n_seq * sizeof(u64)));
+  CU(cudaMalloc(&ctx->ref_len, n_seq * sizeof(u32)));
+  CU(cudaMemcpy(ctx->ref_off, doff.data(), n_seq * sizeof(u64), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->ref_len, dlen.data(), n_seq * sizeof(u32), cudaMemcpyHostToDevice));
+  ctx->n_seq = n_seq; ctx->h_ref_off = doff; ctx->h_ref_len = dlen;
+  return CMX_OK;
+}
+
+// Allocate the device table for n_keys keys (load <= 0.5) and clear it.
+static int alloc_table(cmx_ctx *ctx, u64 n_keys) {
+  cudaFree(ctx->slots); ctx->slots = nullptr;
+  u64 n = 1024;
+  while (n < 2 * n_keys) n <<= 1;
+  ctx->n_slots = n;
+  CU(cudaMalloc(&ctx->slots, n * sizeof(ulonglong2)));
+  CU(cudaMemset(ctx->slots, 0xFF, n * sizeof(ulonglong2)));
+  return CMX_OK;
+}
+static int table_shift(u64 n_slots) { int lg = 0; while ((1ull << lg) < n_slots) ++lg; return 64 - lg; }
+
+int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint32_t *flags, const uint64_t *keys,
+                     const uint64_t *vals, const uint64_t *occ, uint32_t n_occ) {
+  if (!ctx || !flags || !keys || !vals || (n_occ && !occ)) return CMX_ERR_INVALID;
+  if (k < 2 || k > 28 || w < 1 || w > CMX_W_MAX) return fail(ctx, CMX_ERR_INVALID, "unsupported k=%d w=%d", k, w);
+  CU(cudaSetDevice(ctx->device));
+  // occupied buckets (khash.h:165: 2 flag bits per bucket: 10 empty, 01 deleted, 00 occupied)
+  std::vector<ulonglong2> kv;
+  kv.reserve(n_buckets / 2);
+  for (u64 i = 0; i < n_buckets; ++i)
+    if (((flags[i >> 4] >> ((i & 0xfU) << 1)) & 3) == 0) kv.push_back(make_ulonglong2(keys[i], vals[i]));
+  ctx->n_keys = kv.size();
+  int rc = alloc_table(ctx, kv.size());
+  if (rc) return rc;
+  ulonglong2 *d_kv = nullptr;
+  const size_t CH = 1u << 24;
+  CU(cudaMalloc(&d_kv, std::min(kv.size(), CH) * sizeof(ulonglong2) + 16));
+  for (size_t o = 0; o < kv.size(); o += CH) {
+    const size_t n = std::min(CH, kv.size() - o);
+    CU(cudaMemcpy(d_kv, kv.data() + o, n * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    table_insert_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_kv, n, ctx->slots, ctx->n_slots - 1, table_shift(ctx->n_slots));
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  cudaFree(d_kv);
+  cudaFree(ctx->occ); ctx->occ = nullptr;
+  CU(cudaMalloc(&ctx->occ, (size_t)std::max<u32>(n_occ, 1) * sizeof(u64)));
+  if (n_occ) CU(cudaMemcpy(ctx->occ, occ, (size_t)n_occ * sizeof(u64), cudaMemcpyHostToDevice));
+  ctx->n_occ = n_occ; ctx->k = k; ctx->w = w;
+  return CMX_OK;
+}
+
+int cmx_index_info(const cmx_ctx *ctx, int *k, int *w, uint64_t *n_keys, uint64_t *n_occ, uint64_t *table_slots) {
+  if (!ctx || !ctx->slots) return CMX_ERR_STATE;
+  if (k) *k = ctx->k;
+  if (w) *w = ctx->w;
+  if (n_keys) *n_keys = ctx->n_keys;
+  if (n_occ) *n_occ = ctx->n_occ;
+  if (table_slots) *table_slots = ctx->n_slots;
+  return CMX_OK;
+}
+
+int cmx_build_index(cmx_ctx *ctx, int k, int w) {
+  if (!ctx) return CMX_ERR_INVALID;
+  if (!ctx->ref_seq) return fail(ctx, CMX_ERR_STATE, "upload the reference first");
+  if (k < 2 || k > 28 || w < 1 || w > CMX_W_MAX) return fail(ctx, CMX_ERR_INVALID, "unsupported k=%d w=%d", k, w);
+  CU(cudaSetDevice(ctx->device));
+  IndexBuildResult r;
+  std::string err;
+  const int rc = build_index_on_device(ctx->ref_seq, ctx->h_ref_off, ctx->h_ref_len, k, w, &r, &err);
+  if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+  cudaFree(ctx->slots); cudaFree(ctx->occ);
+  ctx->slots = r.slots; ctx->n_slots = r.n_slots; ctx->occ = r.occ; ctx->n_occ = r.n_occ; ctx->n_keys = r.n_keys;
+  ctx->k = k; ctx->w = w;
+  return CMX_OK;
+}
+
+int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint32_t *flags, uint64_t *keys, uint64_t *vals,
+                       uint32_t *n_occ, uint64_t *occ) {
+  if (!ctx || !ctx->slots) return CMX_ERR_STATE;
+  CU(cudaSetDevice(ctx->device));
+  // khash geometry the reference would have after inserting n_keys keys (khash.h:295-300: grow when
+  // n_occupied >= upper_bound = n_buckets*0.77+0.5)
+  u32 nb = 4;
+  while ((u32)(nb * 0.77 + 0.5) < ctx->n_keys) nb <<= 1;
+  if (n_buckets) *n_buckets = nb;
+  if (n_keys) *n_keys = (u32)ctx->n_keys;
+  if (n_occ) *n_occ = ctx->n_occ;
+  if (occ && ctx->n_occ) CU(cudaMemcpy(occ, ctx->occ, (size_t)ctx->n_occ * sizeof(u64), cudaMemcpyDeviceToHost));
+  if (flags && keys && vals) {
+    // re-insert every (key, val) with khash's own probe sequence (hash = key>>1 truncated to 32 bit,
+    // triangular steps; khash.h:232-245) so the reference's kh_get finds them.
+    const size_t nf = nb < 16 ? 1 : nb >> 4;
+    for (size_t i = 0; i < nf; ++i) flags[i] = 0xaaaaaaaau;
+    memset(keys, 0, (size_t)nb * 8);
+    memset(vals, 0, (size_t)nb * 8);
+    std::vector<ulonglong2> h(1u << 22);
+    const u32 m = nb - 1;
+    for (u64 o = 0; o < ctx->n_slots; o += h.size()) {
+      const size_t n = std::min<u64>(h.size(), ctx->n_slots - o);
+      CU(cudaMemcpy(h.data(), ctx->slots + o, n * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; ++i) {
+        if (h[i].x == CMX_EMPTY_KEY) continue;
+        u32 b = (u32)(h[i].x >> 1) & m, step = 0;
+        while (!((flags[b >> 4] >> ((b & 0xfU) << 1)) & 2)) b = (b + (++step)) & m;
+        flags[b >> 4] &= ~(3u << ((b & 0xfU) << 1));
+        keys[b] = h[i].x; vals[b] = h[i].y;
+      }
+    }
+  }
+  return CMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off = (off + bytes + 255) / 256 * 256; return r; };
+  const size_t R = 2 * slots;
+  o[0] = take(R * sizeof(ReadMeta));
+  o[1] = take(slots * sizeof(PairMeta));
+  o[2] = take(R * c.maxmm * 8);
+  o[3] = take(R * c.maxmm * 8);
+  o[4] = take(R * c.maxmm * 4);
+  o[5] = take(R * 2 * (size_t)c.hc * 8);
+  o[6] = take(R * 6 * (size_t)c.cc * 8);
+  o[7] = take(R * 6 * (size_t)c.cc);
+  o[8] = take(R * 2 * (size_t)c.mc * 8);
+  o[9] = take(R * 2 * (size_t)c.mc);
+  return off;
+}
+static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list) {
+  if (n_slots > t.slots_cap) {
+    size_t o[10];
+    const size_t want_slots = (size_t)n_slots + n_slots / 8 + 16;
+    const size_t bytes = tier_bytes(t.caps, want_slots, o);
+    release(t.mem);
+    cudaError_t e = ensure(t.mem, bytes);
+    if (e != cudaSuccess) return e;
+    t.slots_cap = (int)want_slots;
+  }
+  size_t o[10];
+  tier_bytes(t.caps, t.slots_cap, o);
+  char *b = (char *)t.mem.p;
+  Scratch &S = t.view;
+  S.caps = t.caps; S.n_slots = n_slots; S.pair_list = pair_list;
+  S.rmeta = (ReadMeta *)(b + o[0]); S.pmeta = (PairMeta *)(b + o[1]);
+  S.mm_hash = (u64 *)(b + o[2]); S.mm_val = (u64 *)(b + o[3]); S.mm_pos = (u32 *)(b + o[4]);
+  S.hits = (u64 *)(b + o[5]); S.cand_pos = (u64 *)(b + o[6]); S.cand_cnt = (u8 *)(b + o[7]);
+  S.map_pos = (u64 *)(b + o[8]); S.map_err = (signed char *)(b + o[9]);
+  t.n_slots = n_slots; t.pair_list = pair_list;
+  return cudaSuccess;
+}
+
+// Task chunks of `#pragma omp taskloop grainsize(5000)` (chromap.h:892) over one reference batch of n pairs
+// as cut by libgomp: num_tasks = n/5000 (min 1), chunk = n/num_tasks, first n%num_tasks chunks one longer.
+static void taskloop_chunks(u32 base, u32 n, std::vector<int> &starts) {
+  u32 nt = n / 5000;
+  if (nt < 1) nt = 1;
+  const u32 chunk = n / nt, rem = n % nt;
+  u32 s = base;
+  for (u32 t = 0; t < nt; ++t) { starts.push_back((int)s); s += chunk + (t < rem ? 1 : 0); }
+}
+
+static DevParams make_dev_params(const cmx_ctx *ctx) {
+  const cmx_params &p = ctx->params;
+  DevParams d;
+  d.e = p.error_threshold; d.min_seeds = p.min_num_seeds; d.f0 = p.max_seed_freq0; d.f1 = p.max_seed_freq1;
+  d.max_best = p.max_num_best_mappings; d.max_insert = p.max_insert_size; d.min_read_len = p.min_read_length;
+  d.drop_rep = p.drop_repetitive_reads; d.trim = p.trim_adapters; d.k = ctx->k; d.w = ctx->w;
+  d.lanes = p.error_threshold < 8 ? 8 : 4;  // mapping_parameters.h:80-88
+  return d;
+}
+
+static int upload_batch(cmx_ctx *ctx, const cmx_batch *in, DevBatch *B) {
+  const u32 n = in->n_pairs;
+  if (in->on_device) {
+    B->seq1 = (const u8 *)in->seq1; B->off1 = in->off1; B->seq2 = (const u8 *)in->seq2; B->off2 = in->off2;
+  } else {
+    const size_t b1 = in->off1[n], b2 = in->off2[n];
+    CU(ensure(ctx->seq1, b1 + 64)); CU(ensure(ctx->seq2, b2 + 64));
+    CU(ensure(ctx->off1, (n + 1) * 4)); CU(ensure(ctx->off2, (n + 1) * 4));
+    CU(cudaMemcpyAsync(ctx->seq1.p, in->seq1, b1, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->seq2.p, in->seq2, b2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    B->seq1 = (const u8 *)ctx->seq1.p; B->off1 = (const u32 *)ctx->off1.p;
+    B->seq2 = (const u8 *)ctx->seq2.p; B->off2 = (const u32 *)ctx->off2.p;
+  }
+  B->n_pairs = n; B->first_read_id = in->first_read_id;
+  return CMX_OK;
+}
+
+int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *user_stream) {
+  if (!ctx || !in || !out) return CMX_ERR_INVALID;
+  if (!ctx->slots || !ctx->ref_seq) return fail(ctx, CMX_ERR_STATE, "index and reference must be uploaded first");
+  const u32 n = in->n_pairs;
+  const int mb = ctx->params.max_num_best_mappings;
+  out->n_records = 0; out->n_mapped_pairs = out->n_uniquely_mapped_pairs = out->n_candidates = out->n_overflow_pairs = 0;
+  if (n == 0) return CMX_OK;
+  if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
+  CU(cudaSetDevice(ctx->device));
+  (void)user_stream;  // the context's own stream is used; the call is synchronous
+  cudaStream_t st = ctx->stream;
+  const DevParams P = make_dev_params(ctx);
+  DevIndex ix;
+  ix.slots = ctx->slots; ix.n_slots_mask = ctx->n_slots - 1; ix.shift = table_shift(ctx->n_slots); ix.occ = ctx->occ; ix.n_occ = ctx->n_occ; ix.k = ctx->k; ix.w = ctx->w;
+  DevRef R;
+  R.seq = ctx->ref_seq; R.off = ctx->ref_off; R.len = ctx->ref_len; R.n_seq = ctx->n_seq;
+  MapqTables T;
+  T.inv_log = ctx->inv_log; T.pen_thr = ctx->pen_thr;
+  DevBatch B;
+  CU(cudaEventRecord(ctx->ev[0], st));
+  int rc = upload_batch(ctx, in, &B);
+  if (rc) return rc;
+  CU(ensure(ctx->nbest, (size_t)n * 4)); CU(ensure(ctx->sel, (size_t)n * mb * 4));
+  CU(ensure(ctx->out_rec, (size_t)n * mb * sizeof(OutRecord))); CU(ensure(ctx->out_n, (size_t)(n + 1) * 4));
+  CU(ensure(ctx->offs, (size_t)(n + 1) * 8));
+  CU(cudaMemsetAsync(ctx->nbest.p, 0, (size_t)n * 4, st));
+  CU(cudaMemsetAsync(ctx->out_n.p, 0, (size_t)(n + 1) * 4, st));
+  CU(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), st));
+  CU(cudaEventRecord(ctx->ev[1], st));
+  float ms_seed = 0, ms_pc = 0, ms_ver = 0, ms_pair = 0;
+  u64 launches = 0;
+  int n_slots = (int)n;
+  const int *pair_list = nullptr;
+  int tiers_used = 0;
+  u64 n_overflow_final = 0;
+  const int TB = 128;
+  for (int t = 0; t < N_TIERS && n_slots > 0; ++t) {
+    Tier &tier = ctx->tiers[t];
+    CU(tier_prepare(tier, n_slots, pair_list));
+    const Scratch S = tier.view;
+    cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6], e2 = ctx->ev[7], e3 = ctx->ev[8], e4 = ctx->ev[9];
+    CU(cudaEventRecord(e0, st));
+    prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
+    seed_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, B, S, ctx->ctr);
+    CU(cudaEventRecord(e1, st));
+    pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr);
+    CU(cudaEventRecord(e2, st));
+    verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
+    CU(cudaEventRecord(e3, st));
+    pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
+    CU(cudaEventRecord(e4, st));
+    launches += 5;
+    CU(ensure(tier.ovf_list, (size_t)n_slots * 4));
+    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), st));
+    collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, ctx->d_count);
+    launches += 1;
+    int n_ovf = 0;
+    CU(cudaMemcpyAsync(&n_ovf, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float f;
+    cudaEventElapsedTime(&f, e0, e1); ms_seed += f;
+    cudaEventElapsedTime(&f, e1, e2); ms_pc += f;
+    cudaEventElapsedTime(&f, e2, e3); ms_ver += f;
+    cudaEventElapsedTime(&f, e3, e4); ms_pair += f;
+    tiers_used = t + 1;
+    if (n_ovf > 0 && t + 1 < N_TIERS) {
+      // deterministic order for the next tier: sort the pair list (atomic append order is arbitrary)
+      std::vector<int> h(n_ovf);
+      CU(cudaMemcpy(h.data(), tier.ovf_list.p, (size_t)n_ovf * 4, cudaMemcpyDeviceToHost));
+      std::sort(h.begin(), h.end());
+      CU(cudaMemcpy(tier.ovf_list.p, h.data(), (size_t)n_ovf * 4, cudaMemcpyHostToDevice));
+      pair_list = (const int *)tier.ovf_list.p;
+    } else if (n_ovf > 0) {
+      n_overflow_final = n_ovf;
+    }
+    n_slots = n_ovf;
+  }
+  // multi-mapper sampling: one thread per taskloop chunk of every reference batch in this call
+  std::vector<int> chunks;
+  for (u32 b0 = 0; b0 < n; b0 += (u32)ctx->params.batch_size) taskloop_chunks(b0, std::min<u32>((u32)ctx->params.batch_size, n - b0), chunks);
+  const int n_chunks = (int)chunks.size();
+  chunks.push_back((int)n);
+  CU(ensure(ctx->chunk_start, chunks.size() * 4));
+  CU(cudaEventRecord(ctx->ev[2], st));
+  CU(cudaMemcpyAsync(ctx->chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
+  select_kernel<<<(n_chunks + 31) / 32, 32, 0, st>>>(P, n_chunks, (const int *)ctx->chunk_start.p, (const int *)ctx->nbest.p, (int *)ctx->sel.p);
+  CU(cudaEventRecord(ctx->ev[3], st));
+  for (int t = 0; t < tiers_used; ++t) {
+    const Scratch S = ctx->tiers[t].view;
+    emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutRecord *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
+  }
+  launches += 1 + tiers_used;
+  // read-order compaction
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
+  CU(ensure(ctx->cub_tmp, tmp_bytes));
+  // out_n has n entries plus one trailing zero so that offs[n] = total
+  cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
+  OutRecord *dst;
+  if (out->on_device) dst = (OutRecord *)out->records;
+  else { CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)ctx->out_compact.p; }
+  compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)ctx->out_rec.p, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, dst);
+  launches += 2;
+  CU(cudaEventRecord(ctx->ev[4], st));
+  u64 total = 0;
+  CU(cudaMemcpyAsync(&total, (u64 *)ctx->offs.p + n, 8, cudaMemcpyDeviceToHost, st));
+  Counters hc;
+  CU(cudaMemcpyAsync(&hc, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (!out->on_device && total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev[5], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  out->n_records = total;
+  out->n_mapped_pairs = hc.n_mapped; out->n_uniquely_mapped_pairs = hc.n_unique; out->n_candidates = hc.n_candidates;
+  out->n_overflow_pairs = n_overflow_final;
+  cmx_timing &tm = ctx->timing;
+  memset(&tm, 0, sizeof(tm));
+  cudaEventElapsedTime(&tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+  tm.seed_ms = ms_seed; tm.pair_candidates_ms = ms_pc; tm.verify_ms = ms_ver; tm.pairing_ms = ms_pair;
+  cudaEventElapsedTime(&tm.select_ms, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&tm.emit_ms, ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[4], ctx->ev[5]);
+  cudaEventElapsedTime(&tm.total_ms, ctx->ev[0], ctx->ev[5]);
+  tm.n_minimizers = hc.n_minimizers; tm.n_probe_steps = hc.n_probe_steps; tm.n_found = hc.n_found; tm.n_occ_reads = hc.n_occ_reads;
+  tm.n_verified = hc.n_verified; tm.n_launches = launches;
+  ctx->last_n_pairs = n; ctx->last_tiers_used = tiers_used;
+  if (n_overflow_final) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)n_overflow_final);
+  return CMX_OK;
+}
+
+int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out) {
+  if (!ctx || !out) return CMX_ERR_INVALID;
+  *out = ctx->timing;
+  return CMX_OK;
+}
+
+__global__ void trace_kernel(Scratch S, cmx_pair_trace *out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  const PairMeta &pm = S.pmeta[slot];
+  if (pm.status == ST_OVERFLOW) return;
+  cmx_pair_trace t;
+  memset(&t, 0, sizeof(t));
+  const ReadMeta *rm = S.rmeta + 2 * slot;
+  for (int m = 0; m < 2; ++m) {
+    t.trimmed_len[m] = rm[m].len;
+    t.n_minimizers[m] = rm[m].n_mm;
+    t.n_pos_candidates_gen[m] = rm[m].n_cand_gen[0]; t.n_neg_candidates_gen[m] = rm[m].n_cand_gen[1];
+    t.n_pos_candidates[m] = rm[m].n_cand[0]; t.n_neg_candidates[m] = rm[m].n_cand[1];
+    t.n_pos_mappings[m] = rm[m].n_map[0]; t.n_neg_mappings[m] = rm[m].n_map[1];
+    t.min_errors[m] = rm[m].min_err; t.second_min_errors[m] = rm[m].second_min_err;
+    t.n_best[m] = rm[m].n_best; t.n_second_best[m] = rm[m].n_second_best;
+    t.repetitive_seed_length[m] = rm[m].rep_len;
+  }
+  t.supplement_result = pm.sup;
+  t.min_sum_errors = pm.min_sum; t.second_min_sum_errors = pm.second_min_sum; t.n_best_pairs = pm.n_best; t.n_second_best_pairs = pm.n_second_best;
+  t.n_records = pm.n_rec;
+  out[slot_pair(S, slot)] = t;
+}
+
+int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs) {
+  if (!ctx || !out || n_pairs != ctx->last_n_pairs) return CMX_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(ensure(ctx->trace, (size_t)n_pairs * sizeof(cmx_pair_trace)));
+  CU(cudaMemset(ctx->trace.p, 0, (size_t)n_pairs * sizeof(cmx_pair_trace)));
+  for (int t = 0; t < ctx->last_tiers_used; ++t) {
+    const Scratch S = ctx->tiers[t].view;
+    trace_kernel<<<(S.n_slots + 255) / 256, 256>>>(S, (cmx_pair_trace *)ctx->trace.p);
+  }
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, ctx->trace.p, (size_t)n_pairs * sizeof(cmx_pair_trace), cudaMemcpyDeviceToHost));
+  return CMX_OK;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------
+__global__ void stage_minimizers_kernel(DevBatch B, int k, int w, u64 *out_hash, u32 *out_pos, int *out_n, u32 stride) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 2 * (int)B.n_pairs) return;
+  const int pair = r >> 1, mate = r & 1;
+  out_n[r] = gen_minimizers_thread(read_ptr(B, pair, mate), read_raw_len(B, pair, mate), k, w, out_hash + (size_t)r * stride, out_pos + (size_t)r * stride, (int)stride);
+}
+
+int cmx_stage_minimizers(cmx_ctx *ctx, const cmx_batch *in, uint64_t *out_hash, uint32_t *out_pos, int32_t *out_n, uint32_t stride) {
+  if (!ctx || !in || !out_hash || !out_pos || !out_n) return CMX_ERR_INVALID;
+  if (!ctx->k) return fail(ctx, CMX_ERR_STATE, "index (k, w) not set");
+  CU(cudaSetDevice(ctx->device));
+  DevBatch B;
+  int rc = upload_batch(ctx, in, &B);
+  if (rc) return rc;
+  const size_t R = 2 * (size_t)in->n_pairs;
+  u64 *dh; u32 *dp; int *dn;
+  CU(cudaMalloc(&dh, R * stride * 8)); CU(cudaMalloc(&dp, R * stride * 4)); CU(cudaMalloc(&dn, R * 4));
+  stage_minimizers_kernel<<<(unsigned)((R + 127) / 128), 128, 0, ctx->stream>>>(B, ctx->k, ctx->w, dh, dp, dn, stride);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out_hash, dh, R * stride * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out_pos, dp, R * stride * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out_n, dn, R * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dh); cudaFree(dp); cudaFree(dn);
+  return CMX_OK;
+}
+
+__global__ void stage_probe_kernel(DevIndex ix, const u64 *h, u64 n, u8 *found, u64 *key, u64 *val) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 v = 0;
+  int steps;
+  const int kind = index_lookup(ix, h[i], &v, &steps);
+  found[i] = kind != 0;
+  key[i] = kind ? ((h[i] << 1) | (kind == 1 ? 1u : 0u)) : 0;
+  val[i] = v;
+}
+
+int cmx_stage_probe(cmx_ctx *ctx, const uint64_t *hashes, uint64_t n, uint8_t *found, uint64_t *key, uint64_t *val) {
+  if (!ctx || !hashes || !found || !key || !val) return CMX_ERR_INVALID;
+  if (!ctx->slots) return fail(ctx, CMX_ERR_STATE, "index not uploaded");
+  CU(cudaSetDevice(ctx->device));
+  DevIndex ix;
+  ix.slots = ctx->slots; ix.n_slots_mask = ctx->n_slots - 1; ix.shift = table_shift(ctx->n_slots); ix.occ = ctx->occ; ix.n_occ = ctx->n_occ; ix.k = ctx->k; ix.w = ctx->w;
+  u64 *dh, *dk, *dv; u8 *df;
+  CU(cudaMalloc(&dh, n * 8 + 8)); CU(cudaMalloc(&dk, n * 8 + 8)); CU(cudaMalloc(&dv, n * 8 + 8)); CU(cudaMalloc(&df, n + 8));
+  CU(cudaMemcpy(dh, hashes, n * 8, cudaMemcpyHostToDevice));
+  if (n) stage_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ix, dh, n, df, dk, dv);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(found, df, n, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(key, dk, n * 8, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(val, dv, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dh); cudaFree(dk); cudaFree(dv); cudaFree(df);
+  return CMX_OK;
+}
+
+__global__ void stage_align_kernel(int e, int L, const u8 *pat, const u8 *txt, u64 n, int *err, int *endp) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8 *p = pat + i * (size_t)(L + 2 * e), *t = txt + i * (size_t)L;
+  int ep = 0;
+  err[i] = banded_align(e, L, [&](int j) { return base_code(p[j]); }, [&](int j) { return base_code(t[j]); }, &ep);
+  endp[i] = ep;
+}
+
+int cmx_stage_banded_align(cmx_ctx *ctx, int e, int read_len, const char *patterns, const char *texts, uint64_t n, int32_t *num_errors, int32_t *end_pos) {
+  if (!ctx || !patterns || !texts || !num_errors || !end_pos || e < 1 || e > 15 || read_len < 1) return CMX_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  u8 *dp, *dt; int *de, *dq;
+  const size_t pb = n * (size_t)(read_len + 2 * e), tb = n * (size_t)read_len;
+  CU(cudaMalloc(&dp, pb + 8)); CU(cudaMalloc(&dt, tb + 8)); CU(cudaMalloc(&de, n * 4 + 8)); CU(cudaMalloc(&dq, n * 4 + 8));
+  CU(cudaMemcpy(dp, patterns, pb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dt, texts, tb, cudaMemcpyHostToDevice));
+  if (n) stage_align_kernel<<<(unsigned)((n + 127) / 128), 128>>>(e, read_len, dp, dt, n, de, dq);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(num_errors, de, n * 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(end_pos, dq, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dp); cudaFree(dt); cudaFree(de); cudaFree(dq);
+  return CMX_OK;
+}
+
+// ---- post-processing (host side of the writer; GPU sort is a later row) ----------------------------
+static inline auto rec_key(const cmx_pe_record &r) {  // bed_mapping.h:208-215 prefixed by rid
+  return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, r.mapq, r.direction, r.is_unique, r.read_id,
+                         r.positive_alignment_length, r.negative_alignment_length);
+}
+static inline void tn5(cmx_pe_record &r) {  // bed_mapping.h:225-230
+  r.fragment_start += 4; r.positive_alignment_length -= 4; r.fragment_length -= 9; r.negative_alignment_length -= 5;
+}
+
+int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t n, uint64_t *n_out) {
+  if (!ctx || (!recs && n) || !n_out) return CMX_ERR_INVALID;
+  const cmx_params &p = ctx->params;
+  *n_out = 0;
+  if (n == 0) return CMX_OK;
+  auto less = [](const cmx_pe_record &a, const cmx_pe_record &b) { return rec_key(a) < rec_key(b); };
+  auto same = [](const cmx_pe_record &a, const cmx_pe_record &b) { return a.rid == b.rid && a.fragment_start == b.fragment_start && a.fragment_length == b.fragment_length; };
+  uint64_t o = 0;
+  if (p.low_memory_mode) {  // mapping_writer.h:166-376
+    std::sort(recs, recs + n, less);
+    uint64_t i = 0;
+    while (i < n) {
+      cmx_pe_record keep = recs[i];
+      uint32_t dups = 1;
+      uint64_t j = i + 1;
+      if (p.remove_pcr_duplicates)
+        for (; j < n && same(recs[j], recs[i]); ++j) { ++dups; if (recs[j].mapq > keep.mapq) keep = recs[j]; }
+      if (keep.mapq >= p.mapq_threshold) {
+        keep.num_dups = (uint8_t)std::min<uint32_t>(255, dups);
+        if (p.tn5_shift) tn5(keep);
+        recs[o++] = keep;
+      }
+      i = j;
+    }
+    *n_out = o;
+    return CMX_OK;
+  }
+  if (p.tn5_shift) for (uint64_t i = 0; i < n; ++i) tn5(recs[i]);  // chromap.h:1322-1355
+  std::sort(recs, recs + n, less);
+  if (p.remove_pcr_duplicates) {  // mapping_processor.h:161-202: keeps the last of each run
+    uint64_t i = 0, w = 0;
+    while (i < n) {
+      uint64_t j = i + 1;
+      while (j < n && same(recs[j], recs[i])) ++j;
+      cmx_pe_record keep = recs[j - 1];
+      keep.num_dups = (uint8_t)std::min<uint64_t>(255, j - i);
+      recs[w++] = keep;
+      i = j;
+    }
+    n = w;
+  }
+  for (uint64_t i = 0; i < n; ++i) if (recs[i].mapq >= p.mapq_threshold) recs[o++] = recs[i];
+  *n_out = o;
+  return CMX_OK;
+}
+
+int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {
+  int64_t len = 0;
+  char line[1100];
+  for (uint64_t i = 0; i < n; ++i) {  // mapping_writer.cc:75-83
+    const cmx_pe_record &r = recs[i];
+    const int l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t%c\t%u\n", names[r.rid], r.fragment_start,
+                           (uint32_t)(r.fragment_start + r.fragment_length), (uint32_t)r.mapq, r.direction ? '+' : '-', (uint32_t)r.num_dups);
+    if (buf && len + l <= cap) memcpy(buf + len, line, l);
+    len += l;
+  }
+  return len;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// chromap_b200 — shared device types and helpers.  sm_100a only.
+// File:line citations are into the reference's src/ (what each routine must reproduce bit-exactly).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+#define CMX_W_MAX 64       // ring size bound for the minimizer window
+#define CMX_MAX_BEST 8     // upper bound on max_num_best_mappings (-n)
+
+// Parameters the kernels read (subset of cmx_params + index k/w).
+struct DevParams {
+  int e, min_seeds, f0, f1, max_best, max_insert, min_read_len, drop_rep, trim, k, w, lanes;
+};
+
+struct Caps {  // per-read (per-strand where applicable) scratch capacities of one tier
+  int maxmm, hc, cc, mc;
+};
+
+// pair status
+enum { ST_OK = 0, ST_DROP = 1, ST_OVERFLOW = 2 };
+
+struct ReadMeta {
+  int len;  // after adapter trimming
+  int n_mm;
+  int n_hits[2];
+  int n_cand[2];
+  int n_buf[2];
+  int n_aug[2];
+  int n_map[2];
+  int n_cand_gen[2];
+  int min_err, second_min_err, n_best, n_second_best;
+  u32 rep_len;
+  int pad;
+};
+
+struct PairMeta {
+  int status;
+  int sup;  // SupplementCandidates result
+  int min_sum, second_min_sum, n_best, n_second_best;
+  int n_rec;
+  int pad;
+};
+
+// Device index: open-addressing table of 16-byte slots {key = hash<<1|singleton, val}, linear probing,
+// slot = fibonacci(hash) >> shift.  Layout is ours; lookups answer exactly like kh_get on the
+// reference's khash (khash.h:232-245): found / key / value.
+struct DevIndex {
+  const ulonglong2 *slots;
+  u64 n_slots_mask;  // n_slots - 1 (power of two)
+  int shift;         // 64 - log2(n_slots)
+  const u64 *occ;
+  u32 n_occ;
+  int k, w;
+};
+#define CMX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+struct DevRef {
+  const u8 *seq;     // concatenated ASCII, each sequence followed by >= 64 NUL bytes
+  const u64 *off;    // [n_seq]
+  const u32 *len;    // [n_seq]
+  u32 n_seq;
+};
+
+struct DevBatch {
+  const u8 *seq1;
+  const u32 *off1;
+  const u8 *seq2;
+  const u32 *off2;
+  u32 n_pairs;
+  u32 first_read_id;
+};
+
+// One scratch tier: arrays indexed by slot (pair slot s -> read slots 2s, 2s+1).
+struct Scratch {
+  Caps caps;
+  int n_slots;
+  const int *pair_list;  // slot -> pair index in batch (nullptr = identity)
+  ReadMeta *rmeta;       // [2*n_slots]
+  PairMeta *pmeta;       // [n_slots]
+  u64 *mm_hash;          // [2n][maxmm]
+  u64 *mm_val;           // [2n][maxmm]   lookup value
+  u32 *mm_pos;           // [2n][maxmm]   (pos<<1|strand) | kind<<30   kind: 0 absent 1 singleton 2 multi
+  u64 *hits;             // [2n][2][hc]
+  u64 *cand_pos;         // [2n][3][2][cc]   set 0 = candidates, 1 = buffer, 2 = augment
+  u8 *cand_cnt;          // same shape
+  u64 *map_pos;          // [2n][2][mc]
+  signed char *map_err;  // [2n][2][mc]
+};
+
+__device__ __forceinline__ int slot_pair(const Scratch &S, int slot) { return S.pair_list ? S.pair_list[slot] : slot; }
+
+// utils.h:87-104
+__device__ __forceinline__ u32 base_code(u8 c) {
+  // A/a=0 C/c=1 G/g=2 T/t=3 else 4
+  u32 u = c & 0xDF;  // fold case
+  return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+}
+// careful: (c & 0xDF) folds e.g. 0x01 -> 0x01, 'a'(0x61)->'A'.  Bytes like 0xE1 fold to 0xC1 (not a base),
+// '!'(0x21)->0x01: no false positives because only exact 'A','C','G','T' after folding match, and the
+// pre-images of those under &0xDF are {0x41,0x61}, {0x43,0x63}, {0x47,0x67}, {0x54,0x74} only.
+
+// utils.h:76-85
+__device__ __forceinline__ u64 mix64(u64 key, u64 mask) {
+  key = (~key + (key << 21)) & mask;
+  key = key ^ key >> 24;
+  key = ((key + (key << 3)) + (key << 8)) & mask;
+  key = key ^ key >> 14;
+  key = ((key + (key << 2)) + (key << 4)) & mask;
+  key = key ^ key >> 28;
+  key = (key + (key << 31)) & mask;
+  return key;
+}
+
+// Table probe.  Returns kind (0 absent, 1 singleton, 2 multi); *val = table value.  *steps counts slots read.
+__device__ __forceinline__ int index_lookup(const DevIndex &ix, u64 mm_hash, u64 *val, int *steps) {
+  u64 s = (mm_hash * 0x9E3779B97F4A7C15ull) >> ix.shift;
+  int n = 0;
+  for (;;) {
+    const ulonglong2 kv = __ldg(&ix.slots[s]);
+    ++n;
+    if (kv.x == CMX_EMPTY_KEY) { *steps = n; return 0; }
+    if ((kv.x >> 1) == mm_hash) { *val = kv.y; *steps = n; return (kv.x & 1) ? 1 : 2; }
+    s = (s + 1) & ix.n_slots_mask;
+  }
+}
+
+// index.cc:491-505 (u32 wrap kept)
+__device__ __forceinline__ u64 hit_to_candidate(int k, u64 ref_hit, u32 read_pos, u32 read_strand, bool *same) {
+  const u32 rp = (u32)(ref_hit >> 1);
+  const bool sm = ((u32)(ref_hit & 1)) == read_strand;
+  const u32 start = sm ? rp - read_pos : rp + read_pos - (u32)k + 1u;
+  *same = sm;
+  return ((ref_hit >> 33) << 32) | start;
+}
+
+// In-place ascending sort of u64 keys by one thread: insertion for short lists, heapsort otherwise.
+__device__ inline void sort_u64(u64 *a, int n) {
+  if (n <= 24) {
+    for (int i = 1; i < n; ++i) {
+      const u64 v = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+      a[j + 1] = v;
+    }
+    return;
+  }
+  for (int start = n / 2 - 1; start >= 0; --start) {
+    int root = start;
+    const u64 v = a[root];
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[child] < a[child + 1]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child];
+      root = child;
+    }
+    a[root] = v;
+  }
+  for (int end = n - 1; end > 0; --end) {
+    const u64 v = a[end];
+    a[end] = a[0];
+    int root = 0;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child] < a[child + 1]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child];
+      root = child;
+    }
+    a[root] = v;
+  }
+}
+
+// Sort (key, tag) pairs ascending by `less(ka,ta,kb,tb)` — used for candidates (count desc, pos asc) and
+// draft mappings (pos asc, err asc).  Insertion for short lists, heapsort otherwise.
+template <typename T, typename Less>
+__device__ inline void sort_pairs(u64 *k, T *t, int n, Less less) {
+  if (n <= 24) {
+    for (int i = 1; i < n; ++i) {
+      const u64 kv = k[i];
+      const T tv = t[i];
+      int j = i - 1;
+      while (j >= 0 && less(kv, tv, k[j], t[j])) { k[j + 1] = k[j]; t[j + 1] = t[j]; --j; }
+      k[j + 1] = kv; t[j + 1] = tv;
+    }
+    return;
+  }
+  auto sift = [&](int root, int end, u64 kv, T tv) {
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && less(k[child], t[child], k[child + 1], t[child + 1])) ++child;
+      if (!less(kv, tv, k[child], t[child])) break;
+      k[root] = k[child]; t[root] = t[child];
+      root = child;
+    }
+    k[root] = kv; t[root] = tv;
+  };
+  for (int start = n / 2 - 1; start >= 0; --start) sift(start, n, k[start], t[start]);
+  for (int end = n - 1; end > 0; --end) {
+    const u64 kv = k[end];
+    const T tv = t[end];
+    k[end] = k[0]; t[end] = t[0];
+    sift(0, end, kv, tv);
+  }
+}

@@ -1,0 +1,944 @@
+// chromap_b200 — paired-end mapping pipeline kernels (general tier: one thread per read / per pair,
+// state in global scratch).  Exact restatement of the reference's per-pair semantics; the fast
+// warp-cooperative kernels for the common small case share this scratch layout.
+// File:line citations are into the reference's src/.
+#pragma once
+#include "device_common.cuh"
+
+struct MapqTables {
+  const double *inv_log;  // [65536]: 3 / log(alignment_length) as computed by the host libm (mapping_generator.h:956-958)
+  const int *pen_thr;     // [96]: smallest n with (int)(4.343*log(n+1)+0.499) >= v   (mapping_generator.h:964-967)
+};
+
+struct Counters {  // device-side statistics (atomics)
+  u64 n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_candidates, n_mapped, n_unique, n_overflow;
+};
+
+__device__ __forceinline__ const u8 *read_ptr(const DevBatch &B, int pair, int mate) {
+  return mate == 0 ? B.seq1 + B.off1[pair] : B.seq2 + B.off2[pair];
+}
+__device__ __forceinline__ int read_raw_len(const DevBatch &B, int pair, int mate) {
+  return mate == 0 ? (int)(B.off1[pair + 1] - B.off1[pair]) : (int)(B.off2[pair + 1] - B.off2[pair]);
+}
+// base of the reverse-complement strand string (sequence_batch.h:123-134): index i of negative read
+__device__ __forceinline__ u32 neg_code(const u8 *read, int L, int i) {
+  const u32 c = base_code(read[L - 1 - i]);
+  return c < 4 ? 3u ^ c : 4u;
+}
+__device__ __forceinline__ u8 code_char(u32 c) { return c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : c == 3 ? 'T' : 'N'; }
+
+// ------------------------------------------------------------------------------------------------
+// K0: per pair — length filter (chromap.h:911-916) and adapter trimming (chromap.cc:176-289).
+__global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  const int pair = slot_pair(S, slot);
+  PairMeta pm;
+  pm.status = ST_OK; pm.sup = 0; pm.min_sum = 0; pm.second_min_sum = 0; pm.n_best = 0; pm.n_second_best = 0; pm.n_rec = 0; pm.pad = 0;
+  int len1 = read_raw_len(B, pair, 0), len2 = read_raw_len(B, pair, 1);
+  if (len1 < P.min_read_len || len2 < P.min_read_len) pm.status = ST_DROP;
+  else if (len1 > S.caps.maxmm || len2 > S.caps.maxmm) pm.status = ST_OVERFLOW;  // longer than max_read_length
+  else if (P.trim) {
+    const u8 *raw1 = read_ptr(B, pair, 0), *raw2 = read_ptr(B, pair, 1);
+    const bool swp = !(len1 <= len2);
+    const u8 *r1 = swp ? raw2 : raw1;   // the shorter read
+    const u8 *r2 = swp ? raw1 : raw2;   // the other one; we search in its reverse complement
+    const int L1 = swp ? len2 : len1, L2 = swp ? len1 : len2;
+    const int min_ovl = P.min_read_len, seed = min_ovl / 2;
+    bool merged = false;
+    for (int si = 0; si < 2 && !merged; ++si) {
+      // std::string::find of r1[si*seed .. +seed) in neg2, scanning start positions upward
+      for (int sp = 0; sp + seed <= L2 && !merged; ++sp) {
+        bool hit = true;
+        for (int j = 0; j < seed; ++j)
+          if (code_char(neg_code(r2, L2, sp + j)) != r1[si * seed + j]) { hit = false; break; }
+        if (!hit) continue;
+        if (!(sp >= si * seed) || !((int)(L2 - sp + seed * si) >= min_ovl)) continue;
+        bool ok = true;
+        int ne = 0;
+        for (int i = 0; i < seed * si; ++i) {
+          if (code_char(neg_code(r2, L2, sp - si * seed + i)) != r1[i]) ++ne;
+          if (ne > 1) { ok = false; break; }
+        }
+        if (ok)
+          for (int i = seed; i + sp < L2 && si * seed + i < L1; ++i) {
+            if (code_char(neg_code(r2, L2, sp + i)) != r1[si * seed + i]) ++ne;
+            if (ne > 1) { ok = false; break; }
+          }
+        if (!ok) continue;
+        int ovl = L2 - sp + si * seed, off2 = 0;
+        if (ovl > L1) { off2 = ovl - L1; ovl = L1; }
+        const int t1 = swp ? ovl + off2 : ovl, t2 = swp ? ovl : ovl + off2;
+        if (t1 < len1) len1 = t1;
+        if (t2 < len2) len2 = t2;
+        merged = true;
+      }
+    }
+  }
+  S.pmeta[slot] = pm;
+  S.rmeta[2 * slot].len = len1;
+  S.rmeta[2 * slot + 1].len = len2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// minimizer_generator.cc:7-139 for one read, by one thread.  Emits (hash, pos<<1|strand).
+__device__ inline int gen_minimizers_thread(const u8 *seq, int len, int k, int w, u64 *out_hash, u32 *out_pos, int cap) {
+  const u64 shift = 2 * (k - 1);
+  const u64 mask = (((u64)1) << (2 * k)) - 1;
+  u64 fwd = 0, rev = 0;
+  u64 ring_h[CMX_W_MAX];
+  u32 ring_p[CMX_W_MAX];
+  for (int i = 0; i < w; ++i) { ring_h[i] = ~0ull; ring_p[i] = ~0u; }
+  u64 best_h = ~0ull;
+  u32 best_p = ~0u;
+  int run = 0, slot = 0, best_slot = 0, n = 0;
+#define EMIT(h, p) do { if (n < cap) { out_hash[n] = (h); out_pos[n] = (p); } ++n; } while (0)
+  for (int pos = 0; pos < len; ++pos) {
+    const u32 b = base_code(seq[pos]);
+    u64 cur_h = ~0ull;
+    u32 cur_p = ~0u;
+    if (b < 4) {
+      fwd = ((fwd << 2) | b) & mask;
+      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
+      if (fwd == rev) continue;
+      const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
+      const u32 strand = hf < hr ? 0u : 1u;
+      ++run;
+      if (run >= k) { cur_h = mix64(strand ? hr : hf, mask); cur_p = ((u32)pos << 1) | strand; }
+    } else {
+      run = 0;
+    }
+    ring_h[slot] = cur_h; ring_p[slot] = cur_p;
+    if (run == w + k - 1 && best_h != ~0ull && best_h < cur_h) {
+      for (int j = slot + 1; j < w; ++j) if (best_h == ring_h[j] && ring_p[j] != best_p) EMIT(ring_h[j], ring_p[j]);
+      for (int j = 0; j < slot; ++j) if (best_h == ring_h[j] && ring_p[j] != best_p) EMIT(ring_h[j], ring_p[j]);
+    }
+    if (cur_h <= best_h) {
+      if (run >= w + k && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = cur_h; best_p = cur_p; best_slot = slot;
+    } else if (slot == best_slot) {
+      if (run >= w + k - 1 && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = ~0ull;
+      for (int j = slot + 1; j < w; ++j) if (best_h >= ring_h[j]) { best_h = ring_h[j]; best_p = ring_p[j]; best_slot = j; }
+      for (int j = 0; j <= slot; ++j) if (best_h >= ring_h[j]) { best_h = ring_h[j]; best_p = ring_p[j]; best_slot = j; }
+      if (run >= w + k - 1 && best_h != ~0ull) {
+        for (int j = slot + 1; j < w; ++j) if (best_h == ring_h[j] && best_p != ring_p[j]) EMIT(ring_h[j], ring_p[j]);
+        for (int j = 0; j <= slot; ++j) if (best_h == ring_h[j] && best_p != ring_p[j]) EMIT(ring_h[j], ring_p[j]);
+      }
+    }
+    if (++slot == w) slot = 0;
+  }
+  if (best_h != ~0ull) EMIT(best_h, best_p);
+#undef EMIT
+  return n;
+}
+
+struct RepStats { u32 len, prev; int count; };
+__device__ __forceinline__ void rep_update(int k, int w, u32 read_pos, RepStats &st) {  // index.cc:507-523
+  if (st.prev > read_pos) st.len += k;
+  else if (read_pos < st.prev + k + w - 1) st.len += read_pos - st.prev;
+  else st.len += k;
+  st.prev = read_pos;
+  ++st.count;
+}
+
+// candidate_processor.cc:283-342 — clustering scan over sorted hits (sentinel handled implicitly).
+__device__ inline int cluster_hits(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap) {
+  if (nh == 0) return 0;
+  int n = 0, mcount = 1, eq = 1, best_eq = 1;
+  u64 prev = hits[0], best = hits[0];
+  u32 prev_rid = (u32)(prev >> 32), prev_pos = (u32)prev;
+  for (int i = 1; i <= nh; ++i) {
+    const u64 h = i < nh ? hits[i] : ~0ull;
+    const u32 rid = (u32)(h >> 32), pos = (u32)h;
+    if (rid != prev_rid || pos > prev_pos + (u32)e || ((u32)mcount >= n_mm && pos > (u32)best + (u32)e)) {
+      if (mcount >= need) { if (n < cap) { cpos[n] = best; ccnt[n] = (u8)best_eq; } ++n; }
+      mcount = 1; eq = 1; best_eq = 1; best = h;
+    } else {
+      if (h == best) { ++eq; ++best_eq; }
+      else if (h == prev) { ++eq; if (eq > best_eq) { best = prev; best_eq = eq; } }
+      else eq = 1;
+      ++mcount;
+    }
+    prev = h; prev_rid = rid; prev_pos = pos;
+  }
+  return n;
+}
+
+// K1: per read — minimizers, index probe, hit lists, sort, clustering (candidate_processor.cc:12-71,
+// index.cc:237-349).
+__global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr) {
+  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sr >= 2 * S.n_slots) return;
+  const int slot = sr >> 1, mate = sr & 1;
+  if (S.pmeta[slot].status != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const u8 *seq = read_ptr(B, pair, mate);
+  const int L = rm.len;
+  const Caps c = S.caps;
+  u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
+  u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
+  u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
+  const int n_mm = gen_minimizers_thread(seq, L, P.k, P.w, mmh, mmp, c.maxmm);
+  rm.n_mm = n_mm;
+  rm.n_hits[0] = rm.n_hits[1] = 0; rm.n_cand[0] = rm.n_cand[1] = 0; rm.n_buf[0] = rm.n_buf[1] = 0;
+  rm.n_aug[0] = rm.n_aug[1] = 0; rm.n_map[0] = rm.n_map[1] = 0; rm.n_cand_gen[0] = rm.n_cand_gen[1] = 0;
+  rm.rep_len = 0; rm.min_err = 0; rm.second_min_err = 0; rm.n_best = 0; rm.n_second_best = 0;
+  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  if (n_mm == 0) return;
+  // probe all minimizers once; remember kind + value
+  u64 steps_total = 0, found = 0;
+  long long cnt1 = 0;  // round-1 hit count
+  for (int i = 0; i < n_mm; ++i) {
+    u64 val = 0;
+    int steps;
+    const int kind = index_lookup(ix, mmh[i], &val, &steps);
+    steps_total += steps;
+    mmv[i] = val;
+    mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
+    if (kind == 1) { ++cnt1; ++found; }
+    else if (kind == 2) { ++found; if ((u32)val < (u32)P.f0) cnt1 += (u32)val; }
+  }
+  // round 1 (f0) or, if it yields no hits at all, round 2 (f1)  (candidate_processor.cc:30-50)
+  const bool round2 = cnt1 == 0;
+  const u32 max_freq = round2 ? (u32)P.f1 : (u32)P.f0;
+  u64 *hp = S.hits + ((size_t)sr * 2 + 0) * c.hc, *hn = S.hits + ((size_t)sr * 2 + 1) * c.hc;
+  int np = 0, nn = 0;
+  bool ovf = false;
+  RepStats st = {0u, 0xFFFFFFFFu, 0};
+  u64 occ_reads = 0;
+  for (int i = 0; i < n_mm; ++i) {
+    const u32 kind = mmp[i] >> 30;
+    if (kind == 0) continue;
+    const u32 rpos = (mmp[i] & 0x3FFFFFFFu) >> 1, rstrand = mmp[i] & 1u;
+    const u64 val = mmv[i];
+    bool same;
+    if (kind == 1) {
+      const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
+      if (same) { if (np < c.hc) hp[np] = cp; ++np; } else { if (nn < c.hc) hn[nn] = cp; ++nn; }
+      continue;
+    }
+    const u32 n = (u32)val, off = (u32)(val >> 32);
+    if (n < max_freq) {
+      for (u32 j = 0; j < n; ++j) {
+        const u64 rh = __ldg(&ix.occ[off + j]);
+        const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
+        if (same) { if (np < c.hc) hp[np] = cp; ++np; } else { if (nn < c.hc) hn[nn] = cp; ++nn; }
+      }
+      occ_reads += n;
+    }
+    if (n >= (u32)P.f0) rep_update(P.k, P.w, rpos, st);
+  }
+  if (np > c.hc || nn > c.hc) ovf = true;
+  atomicAdd(&ctr->n_minimizers, (u64)n_mm);
+  atomicAdd(&ctr->n_probe_steps, steps_total);
+  atomicAdd(&ctr->n_found, found);
+  atomicAdd(&ctr->n_occ_reads, occ_reads);
+  if (ovf) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  sort_u64(hp, np);
+  sort_u64(hn, nn);
+  rm.rep_len = st.len;
+  rm.n_hits[0] = np; rm.n_hits[1] = nn;
+  int need = n_mm - st.count;
+  need = need > 1 ? need : 1;
+  need = need > P.min_seeds ? P.min_seeds : need;
+  if (round2 && np > 0 && nn > 0) need = P.min_seeds;
+  u64 *cp0 = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cp1 = cp0 + c.cc;
+  u8 *cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cc1 = cc0 + c.cc;
+  const int nc0 = cluster_hits(P.e, need, (u32)n_mm, hp, np, cp0, cc0, c.cc);
+  const int nc1 = cluster_hits(P.e, need, (u32)n_mm, hn, nn, cp1, cc1, c.cc);
+  if (nc0 > c.cc || nc1 > c.cc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  rm.n_cand[0] = nc0; rm.n_cand[1] = nc1;
+  rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index.cc:351-489 — mate-guided lookup on one strand for one read (by one thread).
+// Returns +max count or -max count (bail-out); hits appended (sorted) into `hits`, *nh set (may exceed cap).
+__device__ inline int rescue_hits(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv,
+                                  const u32 *mmp, const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len,
+                                  u64 *hits, int cap, int *nh_out) {
+  int max_cnt = 0, n_best = 0;
+  for (int i = 0; i < n_mate; ++i) {
+    const int cnt = mate_cnt[i];
+    if (cnt > max_cnt) { max_cnt = cnt; n_best = 1; }
+    else if (cnt == max_cnt) ++n_best;
+  }
+  *nh_out = 0;
+  if (n_best >= 300 || n_mate > P.f0 || (max_cnt <= P.min_seeds && n_best >= 200)) return -max_cnt;
+  // (raw_boundary_size == 0 cannot happen when n_mate > 0)
+  int nh = 0;
+  RepStats st = {0u, 0xFFFFFFFFu, 0};
+  for (int mi = 0; mi < n_mm; ++mi) {
+    const u32 kind = mmp[mi] >> 30;
+    if (kind == 0) continue;
+    const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
+    const u64 val = mmv[mi];
+    bool same;
+    if (kind == 1) {
+      const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
+      if ((same && strand == 0) || (!same && strand == 1)) { if (nh < cap) hits[nh] = cp; ++nh; }
+      continue;
+    }
+    const u32 off = (u32)(val >> 32), n = (u32)val;
+    int prev_l = 0;
+    // iterate merged windows (index.cc:383-412) generated on the fly from the sorted mate candidates
+    int ci = 0;
+    while (ci < n_mate) {
+      while (ci < n_mate && mate_cnt[ci] != max_cnt) ++ci;
+      if (ci >= n_mate) break;
+      u64 lo = mate_pos[ci] < range ? 0 : mate_pos[ci] - range;
+      u64 hi = mate_pos[ci] + range;
+      ++ci;
+      for (;;) {
+        int cj = ci;
+        while (cj < n_mate && mate_cnt[cj] != max_cnt) ++cj;
+        if (cj >= n_mate) { ci = cj; break; }
+        const u64 lo2 = mate_pos[cj] < range ? 0 : mate_pos[cj] - range;
+        if (hi < lo2) { ci = cj; break; }
+        hi = mate_pos[cj] + range;
+        ci = cj + 1;
+      }
+      int l = prev_l, mid = 0, r = (int)n - 1;
+      while (l <= r) {
+        mid = (l + r) / 2;
+        const u64 p = __ldg(&ix.occ[off + mid]) >> 1;
+        if (p < lo) l = mid + 1;
+        else if (p > lo) r = mid - 1;
+        else break;
+      }
+      prev_l = mid;
+      for (u32 oi = (u32)mid; oi < n; ++oi) {
+        const u64 rh = __ldg(&ix.occ[off + oi]);
+        if ((rh >> 1) > hi) break;
+        const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
+        if ((same && strand == 0) || (!same && strand == 1)) { if (nh < cap) hits[nh] = cp; ++nh; }
+      }
+    }
+    if (n >= (u32)P.f0) rep_update(P.k, P.w, rpos, st);
+  }
+  *nh_out = nh;
+  if (nh <= cap) sort_u64(hits, nh);
+  *rep_len = st.len;
+  return max_cnt;
+}
+
+// candidate_processor.cc:345-414 — merge c2 into c1 using `out` as the buffer, result copied back to c1.
+// Returns the new size of c1 (may exceed cap -> overflow).
+__device__ inline int merge_cands(int e, u64 *p1, u8 *c1, int n1, const u64 *p2, const u8 *c2, int n2, u64 *po, u8 *co, int cap) {
+  if (n1 == 0) {
+    for (int i = 0; i < n2 && i < cap; ++i) { p1[i] = p2[i]; c1[i] = c2[i]; }
+    return n2;
+  }
+  int i = 0, j = 0, n = 0;
+  u64 last = 0;
+#define FAR(p) (n == 0 || (p) > last + (u64)e)
+#define PUSH(p, c) do { if (n < cap) { po[n] = (p); co[n] = (c); } last = (p); ++n; } while (0)
+  while (i < n1 && j < n2) {
+    if (p1[i] == p2[j]) { if (FAR(p1[i])) { if (c1[i] > c2[j]) PUSH(p1[i], c1[i]); else PUSH(p2[j], c2[j]); } ++i; ++j; }
+    else if (p1[i] < p2[j]) { if (FAR(p1[i])) PUSH(p1[i], c1[i]); ++i; }
+    else { if (FAR(p2[j])) PUSH(p2[j], c2[j]); ++j; }
+  }
+  for (; i < n1; ++i) if (FAR(p1[i])) PUSH(p1[i], c1[i]);
+  for (; j < n2; ++j) if (FAR(p2[j])) PUSH(p2[j], c2[j]);
+#undef FAR
+#undef PUSH
+  for (int t = 0; t < n && t < cap; ++t) { p1[t] = po[t]; c1[t] = co[t]; }
+  return n;
+}
+
+// candidate_processor.cc:416-484
+__device__ inline void pe_filter_dir(u32 dist, const u64 *p1, const u8 *c1, int n1, const u64 *p2, const u8 *c2, int n2,
+                                     u64 *f1p, u8 *f1c, int *nf1, u64 *f2p, u8 *f2c, int *nf2) {
+  int i1 = 0, i2 = 0, prev_end = 0, a = 0, b = 0;
+  int un1 = 0, un2 = 0, max1 = 6, max2 = 6;
+  while (i1 < n1 && i2 < n2) {
+    if (p1[i1] > p2[i2] + dist) {
+      if (i2 >= prev_end && un2 < 5 && (p1[i1] >> 32) == (p2[i2] >> 32) && c2[i2] >= max2) { f2p[b] = p2[i2]; f2c[b] = c2[i2]; ++b; ++un2; }
+      ++i2;
+    } else if (p2[i2] > p1[i1] + dist) {
+      if (un1 < 5 && (p1[i1] >> 32) == (p2[i2] >> 32) && c1[i1] >= max1) { f1p[a] = p1[i1]; f1c[a] = c1[i1]; ++a; ++un1; }
+      ++i1;
+    } else {
+      f1p[a] = p1[i1]; f1c[a] = c1[i1]; ++a;
+      if (c1[i1] > max1) max1 = c1[i1];
+      int j = i2;
+      while (j < n2 && p2[j] <= p1[i1] + dist) {
+        if (j >= prev_end) { f2p[b] = p2[j]; f2c[b] = c2[j]; ++b; if (c2[j] > max2) max2 = c2[j]; }
+        ++j;
+      }
+      prev_end = j;
+      ++i1;
+    }
+  }
+  *nf1 = a; *nf2 = b;
+}
+
+// K2: per pair — SupplementCandidates (candidate_processor.cc:75-231), MoveCandidiatesToBuffer +
+// ReduceCandidatesForPairedEndRead (chromap.h:1036-1052, candidate_processor.cc:233-263).
+__global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  if (pm.status != ST_OK) return;
+  const Caps c = S.caps;
+  ReadMeta *rm = S.rmeta + 2 * slot;
+  if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
+  auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
+  auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
+  int ret = 0;
+  const u32 range = 2u * (u32)P.max_insert;
+  bool ovf = false;
+  for (int mate = 0; mate < 2; ++mate) {
+    ReadMeta &me = rm[mate];
+    const ReadMeta &ot = rm[1 - mate];
+    const u32 n_mm = me.n_mm;
+    bool aug = true;
+    for (int s = 0; s < 2 && aug; ++s) {
+      const u8 *cc = CC(mate, 0, s);
+      for (int i = 0; i < me.n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { aug = false; break; }
+    }
+    if (!aug) continue;
+    const size_t sr = 2 * slot + mate;
+    const u64 *mmv = S.mm_val + sr * c.maxmm;
+    const u32 *mmp = S.mm_pos + sr * c.maxmm;
+    u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
+    int pr = 0, nr = 0;
+    if (ot.n_cand[0] > 0) {
+      int nh;
+      pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
+      if (nh > c.hc) { ovf = true; break; }
+      const int na = cluster_hits(P.e, 1, n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc);
+      if (na > c.cc) { ovf = true; break; }
+      me.n_aug[1] = na;
+    }
+    if (ot.n_cand[1] > 0) {
+      int nh;
+      nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
+      if (nh > c.hc) { ovf = true; break; }
+      const int na = cluster_hits(P.e, 1, n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc);
+      if (na > c.cc) { ovf = true; break; }
+      me.n_aug[0] = na;
+    }
+    if (((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) ret = 1;
+  }
+  if (ovf) { pm.status = ST_OVERFLOW; return; }
+  for (int mate = 0; mate < 2 && !ovf; ++mate)
+    for (int s = 0; s < 2; ++s) {
+      ReadMeta &me = rm[mate];
+      if (me.n_aug[s] > 0) {
+        const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
+                                  CP(mate, 1, s), CC(mate, 1, s), c.cc);
+        if (n > c.cc) { ovf = true; break; }
+        me.n_cand[s] = n;
+      }
+    }
+  if (ovf) { pm.status = ST_OVERFLOW; return; }
+  pm.sup = ret;
+  int nc1 = rm[0].n_cand[0] + rm[0].n_cand[1], nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+  if (nc1 > 0 && nc2 > 0) {
+    // move candidates to the buffer set (1), filter back into set 0
+    for (int mate = 0; mate < 2; ++mate)
+      for (int s = 0; s < 2; ++s) {
+        const int n = rm[mate].n_cand[s];
+        u64 *src = CP(mate, 0, s), *dst = CP(mate, 1, s);
+        u8 *srcc = CC(mate, 0, s), *dstc = CC(mate, 1, s);
+        for (int i = 0; i < n; ++i) { dst[i] = src[i]; dstc[i] = srcc[i]; }
+        rm[mate].n_buf[s] = n;
+      }
+    int a, b;
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), rm[0].n_buf[0], CP(1, 1, 1), CC(1, 1, 1), rm[1].n_buf[1],
+                  CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
+    rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), rm[0].n_buf[1], CP(1, 1, 0), CC(1, 1, 0), rm[1].n_buf[0],
+                  CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
+    rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
+    nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
+    nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+  }
+  if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
+  atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// alignment.cc:141-192 — banded Myers/Hyyro bit-vector edit distance, band 2e+1, u32 words.
+// PAT(i) -> base code of the reference window at i; TXT(i) -> base code of the read at i.
+template <typename PatF, typename TxtF>
+__device__ __forceinline__ int banded_align(int e, int L, PatF PAT, TxtF TXT, int *end_pos) {
+  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) {
+    const u32 b = PAT(i);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
+  }
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0;
+  int err = 0;
+  for (int i = 0; i < L; ++i) {
+    const u32 pb = PAT(i + 2 * e);
+    const u32 tb = TXT(i);
+    u32 X = VN;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      Peq[a] |= (pb == (u32)a) ? hi : 0u;
+      X |= (tb == (u32)a) ? Peq[a] : 0u;
+    }
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    err += 1 - (int)(D0 & 1u);
+    if (err > 3 * e) return e + 1;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  int best = err;
+  *end_pos = L - 1;
+  for (int i = 0; i < 2 * e; ++i) {
+    err += (int)((VP >> i) & 1u);
+    err -= (int)((VN >> i) & 1u);
+    if (err < best || (err == best && i + 1 == e)) { best = err; *end_pos = L + i; }
+  }
+  return best;
+}
+
+__device__ __forceinline__ bool valid_cand(int e, u32 ref_len, u32 pos, u32 L) {  // draft_mapping_generator.cc:59-70
+  return !(pos < (u32)e || pos >= ref_len || pos + L + (u32)e >= ref_len);
+}
+
+struct Tally { int min_err, second_min_err, n_best, n_second_best; };
+__device__ __forceinline__ void tally(Tally &t, int err) {
+  if (err < t.min_err) { t.second_min_err = t.min_err; t.n_second_best = t.n_best; t.min_err = err; t.n_best = 1; }
+  else if (err == t.min_err) t.n_best++;
+  else if (err == t.second_min_err) t.n_second_best++;
+  else if (err < t.second_min_err) { t.n_second_best = 1; t.second_min_err = err; }
+}
+
+// K3: per read — GenerateDraftMappings (draft_mapping_generator.cc:9-57; fast path :72-157; lane-group
+// driver :159-357 replayed with the scalar routine; per-candidate driver :359-557), non-split.
+__global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr) {
+  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sr >= 2 * S.n_slots) return;
+  const int slot = sr >> 1, mate = sr & 1;
+  if (S.pmeta[slot].status != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  const u8 *read = read_ptr(B, pair, mate);
+  const int L = rm.len, e = P.e;
+  Tally t = {e + 1, e + 1, 0, 0};
+  u64 *mp[2] = {S.map_pos + ((size_t)sr * 2 + 0) * c.mc, S.map_pos + ((size_t)sr * 2 + 1) * c.mc};
+  signed char *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
+  int nm[2] = {0, 0};
+  u64 *cp[2] = {S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
+  u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
+  const int nc[2] = {rm.n_cand[0], rm.n_cand[1]};
+  bool done = false;
+  if (nc[0] + nc[1] == 1) {
+    int n_all = 0, idx = 0, strand = 0;
+    for (int i = 0; i < nc[0]; ++i) if (cc[0][i] == rm.n_mm) { idx = i; ++n_all; }
+    for (int i = 0; i < nc[1]; ++i) if (cc[1][i] == rm.n_mm) { idx = i; strand = 1; ++n_all; }
+    if (n_all == 1) {
+      t.min_err = 0; t.n_best = 1; t.n_second_best = 0;
+      const u64 cpos = cp[strand][idx];
+      const u32 rid = (u32)(cpos >> 32);
+      const u32 pos = strand == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+      if (valid_cand(e, R.len[rid], pos, (u32)L)) {
+        mp[strand][0] = strand == 0 ? cpos + (u64)L - 1 : cpos;
+        me[strand][0] = 0;
+        nm[strand] = 1;
+        done = true;
+      }
+    }
+  }
+  u64 n_verified = 0;
+  if (!done) {
+    auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };  // candidate.h:23-33
+    sort_pairs<u8>(cp[0], cc[0], nc[0], cless);
+    sort_pairs<u8>(cp[1], cc[1], nc[1], cless);
+    for (int s = 0; s < 2; ++s) {
+      auto run_one = [&](u64 cpos) -> bool {  // returns true if the candidate failed (> e errors)
+        const u32 rid = (u32)(cpos >> 32);
+        const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+        const u8 *win = R.seq + R.off[rid] + pos - e;
+        int endp = 0, err;
+        if (s == 0) err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return base_code(read[i]); }, &endp);
+        else err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp);
+        ++n_verified;
+        if (err > e) return true;
+        tally(t, err);
+        if (nm[s] < c.mc) {
+          mp[s][nm[s]] = s == 0 ? cpos - (u64)e + (u64)endp : cpos - (u64)L + 1 - (u64)e + (u64)endp;
+          me[s][nm[s]] = (signed char)err;
+        }
+        ++nm[s];
+        return false;
+      };
+      if (nc[s] < P.lanes) {
+        for (int i = 0; i < nc[s]; ++i) {
+          const u64 cpos = cp[s][i];
+          const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+          if (!valid_cand(e, R.len[(u32)(cpos >> 32)], pos, (u32)L)) continue;
+          run_one(cpos);
+        }
+        continue;
+      }
+      int group[8];
+      int ng = 0;
+      u32 threshold = 0;
+      int ci = 0;
+      while (ci < nc[s]) {
+        if (cc[s][ci] < threshold) break;
+        const u64 cpos = cp[s][ci];
+        const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+        if (!valid_cand(e, R.len[(u32)(cpos >> 32)], pos, (u32)L)) { ++ci; continue; }
+        group[ng++] = ci; ++ci;
+        if (ng < P.lanes) continue;
+        for (int g = 0; g < ng; ++g) if (run_one(cp[s][group[g]])) threshold = cc[s][group[g]];
+        ng = 0;
+      }
+      for (int g = 0; g < ng; ++g) run_one(cp[s][group[g]]);
+    }
+  }
+  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
+  rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
+  if (n_verified) atomicAdd(&ctr->n_verified, n_verified);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mapping_generator.h:346-484 (non-split): two-pointer sweep over end positions.  VISIT(i1, j, sum) is
+// called for every in-window pair in the reference's enumeration order.
+template <typename Visit>
+__device__ __forceinline__ void pair_sweep(const DevParams &P, int s1, u32 L1, u32 L2, const u64 *p1, const signed char *e1, int n1,
+                                           const u64 *p2, const signed char *e2, int n2, Visit VISIT) {
+  int i1 = 0, i2 = 0;
+  const u64 ins = (u64)P.max_insert, ovl = (u64)(u32)P.min_read_len;
+  while (i1 < n1 && i2 < n2) {
+    if ((s1 == 1 && p1[i1] > p2[i2] + ins - L2) || (s1 == 0 && p1[i1] > p2[i2] + L1 - ovl)) ++i2;
+    else if ((s1 == 0 && p2[i2] > p1[i1] + ins - L1) || (s1 == 1 && p2[i2] > p1[i1] + L2 - ovl)) ++i1;
+    else {
+      int j = i2;
+      while (j < n2 && ((s1 == 0 && p2[j] <= p1[i1] + ins - L1) || (s1 == 1 && p2[j] <= p1[i1] + L2 - ovl))) {
+        VISIT(i1, j, (int)e1[i1] + (int)e2[j]);
+        ++j;
+      }
+      ++i1;
+    }
+  }
+}
+
+// K4: per pair — SortMappingsByPositions (mapping_metadata.h:70-78) + best-pair statistics
+// (mapping_generator.h:160-197).  pair_nbest[pair] = #best pairs if the pair reaches sampling/emit, else 0.
+__global__ void pairing_kernel(DevParams P, Scratch S, int *pair_nbest) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status != ST_OK) { if (pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
+  const Caps c = S.caps;
+  ReadMeta *rm = S.rmeta + 2 * slot;
+  if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; return; }
+  // equal positions are interchangeable for the output; (pos, err) makes the order canonical
+  auto mless = [](u64 pa, signed char ea, u64 pb, signed char eb) { return pa != pb ? pa < pb : ea < eb; };
+  u64 *mp[2][2];
+  signed char *me[2][2];
+  for (int m = 0; m < 2; ++m)
+    for (int s = 0; s < 2; ++s) {
+      mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
+      me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
+      sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], mless);
+    }
+  int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;
+  auto visit = [&](int, int, int sum) {
+    if (sum < min_sum) { second = min_sum; n_second = n_best; min_sum = sum; n_best = 1; }
+    else if (sum == min_sum) n_best++;
+    else if (sum == second) n_second++;
+    else if (sum < second) { second = sum; n_second = 1; }
+  };
+  pair_sweep(P, 0, (u32)rm[0].len, (u32)rm[1].len, mp[0][0], me[0][0], rm[0].n_map[0], mp[1][1], me[1][1], rm[1].n_map[1], visit);
+  pair_sweep(P, 1, (u32)rm[0].len, (u32)rm[1].len, mp[0][1], me[0][1], rm[0].n_map[1], mp[1][0], me[1][0], rm[1].n_map[0], visit);
+  pm.min_sum = min_sum; pm.second_min_sum = second; pm.n_best = n_best; pm.n_second_best = n_second;
+  pair_nbest[pair] = (n_best > P.drop_rep) ? 0 : n_best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: multi-mapper sampling (mapping_generator.h:199-214).  One thread per taskloop chunk: `generator`
+// (chromap.h:863) is firstprivate in each task the taskloop (chromap.h:892) generates, so every chunk
+// replays std::mt19937(11) from scratch, consumed by its pairs in index order.
+struct Mt19937 {
+  u32 mt[624];
+  int idx;
+  __device__ void seed(u32 s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (u32)i;
+    idx = 624;
+  }
+  __device__ u32 next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const u32 y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    u32 y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+};
+// libstdc++ 13 std::uniform_int_distribution<int>(0, hi) on a 32-bit URNG: Lemire's nearly-divisionless
+// method (bits/uniform_int_dist.h, _S_nd).  hi < 2^31.
+__device__ __forceinline__ u32 uniform_0_hi(Mt19937 &g, u32 hi) {
+  const u32 range = hi + 1u;
+  u64 product = (u64)g.next() * (u64)range;
+  u32 low = (u32)product;
+  if (low < range) {
+    const u32 threshold = (0u - range) % range;
+    while (low < threshold) { product = (u64)g.next() * (u64)range; low = (u32)product; }
+  }
+  return (u32)(product >> 32);
+}
+
+__global__ void select_kernel(DevParams P, int n_chunks, const int *chunk_start, const int *pair_nbest, int *pair_sel) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= n_chunks) return;
+  Mt19937 g;
+  bool seeded = false;
+  const int mb = P.max_best;
+  for (int pair = chunk_start[ch]; pair < chunk_start[ch + 1]; ++pair) {
+    const int nb = pair_nbest[pair];
+    int *sel = pair_sel + (size_t)pair * mb;
+    for (int j = 0; j < mb; ++j) sel[j] = j;
+    if (nb > mb) {
+      if (!seeded) { g.seed(11u); seeded = true; }
+      for (int i = mb; i < nb; ++i) {
+        const int j = (int)uniform_0_hi(g, (u32)i);
+        if (j < mb) sel[j] = i;
+      }
+      for (int a = 1; a < mb; ++a) {  // std::sort of <= CMX_MAX_BEST ints
+        const int v = sel[a];
+        int b = a - 1;
+        while (b >= 0 && sel[b] > v) { sel[b + 1] = sel[b]; --b; }
+        sel[b + 1] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// alignment.cc:656-718 — start coordinate.  PATC(i)/TXTC(i): raw chars (the Hamming shortcut compares raw
+// chars, case-sensitively, :665-669); codes via base_code().
+template <typename PatC, typename TxtC>
+__device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC PATC, TxtC TXTC) {
+  if (min_err == 0) return e;
+  int ham = 0;
+  for (int i = 0; i < L; ++i) if (PATC(i + e) != TXTC(i)) ++ham;
+  if (ham == min_err) return e;
+  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) {
+    const u32 b = base_code(PATC(L - 1 + 2 * e - i));
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
+  }
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0;
+  int err = 0;
+  for (int i = 0; i < L; ++i) {
+    const u32 pb = base_code(PATC(L - 1 - i));
+    const u32 tb = base_code(TXTC(L - 1 - i));
+    u32 X = VN;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      Peq[a] |= (pb == (u32)a) ? hi : 0u;
+      X |= (tb == (u32)a) ? Peq[a] : 0u;
+    }
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    err += 1 - (int)(D0 & 1u);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  int start = 2 * e;
+  for (int i = 0; i < 2 * e; ++i) {
+    err += (int)((VP >> i) & 1u);
+    err -= (int)((VN >> i) & 1u);
+    if (err == min_err) { start = 2 * e - (1 + i); if (i + 1 == e) return start; }
+  }
+  return start;
+}
+
+// IEEE double ops without FMA contraction: the reference is x86-64 SSE2 scalar code (no FMA).
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ int second_best_penalty(const MapqTables &T, int n) {  // (int)(4.343*log(n+1)+0.499)
+  int v = 0;
+  while (v + 1 < 96 && T.pen_thr[v + 1] <= n) ++v;
+  return v;
+}
+__device__ __forceinline__ double rep_scale(double ident, double frac) {  // the 1 - f(frac_rep) factor
+  if (ident <= 0.95) return xsub(1.0, __dsqrt_rn(frac));
+  if (ident <= 0.97) return xsub(1.0, frac);
+  if (ident >= 0.999) return xsub(1.0, xmul(xmul(xmul(frac, frac), frac), frac));
+  return xsub(1.0, xmul(frac, frac));
+}
+// mapping_generator.h:920-1022 (non-split)
+__device__ inline u8 mapq_se(const MapqTables &T, int num_errors, unsigned short aln_len, int read_len, int max_diff, const ReadMeta &rm) {
+  const int coef_len = 50;
+  aln_len = (unsigned short)((int)aln_len > read_len ? (int)aln_len : read_len);
+  const double ident = xsub(1.0, xdiv((double)num_errors, (double)aln_len));
+  int mapq = 0;
+  int second = rm.second_min_err;
+  if (rm.n_best > 1) {
+  } else {
+    if (second > num_errors + max_diff) second = num_errors + max_diff;
+    double tmp = (int)aln_len < coef_len ? 1.0 : T.inv_log[aln_len];
+    tmp = xmul(tmp, xmul(ident, ident));
+    // 5 * 6.02 * (second - num_errors) * tmp * tmp + 0.499, left to right
+    const double v = xadd(xmul(xmul(xmul(5 * 6.02, (double)(second - num_errors)), tmp), tmp), 0.499);
+    mapq = (int)v;
+  }
+  if (rm.n_second_best > 0) mapq -= second_best_penalty(T, rm.n_second_best);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  if (rm.rep_len > 0) {
+    double frac = xdiv((double)rm.rep_len, (double)read_len);
+    if (rm.rep_len >= (u32)read_len) frac = 0.999;
+    mapq = (int)xadd(xmul((double)mapq, rep_scale(ident, frac)), 0.499);
+  }
+  return (u8)mapq;
+}
+// mapping_generator.h:1027-1192 (non-split)
+__device__ inline u8 mapq_pe(const MapqTables &T, int e1, int e2, unsigned short al1, unsigned short al2, int L1, int L2, int force,
+                             const PairMeta &pm, const ReadMeta *rm) {
+  u8 pe = 0;
+  const int unpaired = rm[0].min_err + rm[1].min_err + 3;
+  if (pm.n_best <= 1) {
+    const int adj = pm.second_min_sum < unpaired ? pm.second_min_sum : unpaired;
+    pe = (u8)(int)xadd(xdiv(xmul(5 * 6.02, (double)(adj - pm.min_sum)), 1.0), .499);
+    if (pm.n_second_best > 0) pe = (u8)((int)pe - second_best_penalty(T, pm.n_second_best));  // uint8 wrap (:1073)
+    if (pe > 60) pe = 60;
+    const int rep = (int)(rm[0].rep_len + rm[1].rep_len);
+    if (rep > 0) {
+      const double total = (double)(L1 + L2);
+      double frac = xdiv((double)rep, total);
+      if ((double)rep >= total) frac = 0.999;
+      const double id1 = xsub(1.0, xdiv((double)e1, (double)(L1 > (int)al1 ? L1 : (int)al1)));
+      const double id2 = xsub(1.0, xdiv((double)e2, (double)(L2 > (int)al2 ? L2 : (int)al2)));
+      const double ident = id1 < id2 ? id1 : id2;
+      pe = (u8)xadd(xmul((double)pe, rep_scale(ident, frac)), 0.499);
+    }
+  }
+  u8 q1 = mapq_se(T, e1, al1, L1, 2, rm[0]);
+  u8 q2 = mapq_se(T, e2, al2, L2, 2, rm[1]);
+  {
+    const double a = xadd((double)q1, xmul((double)pe, 0.65));
+    q1 = q1 > pe ? q1 : ((double)pe < a ? pe : (u8)a);
+    const double b = xadd((double)q2, xmul((double)pe, 0.65));
+    q2 = q2 > pe ? q2 : ((double)pe < b ? pe : (u8)b);
+  }
+  q1 = (u8)xmul((double)q1, 1.2); if (q1 > 60) q1 = 60;
+  q2 = (u8)xmul((double)q2, 1.2); if (q2 > 60) q2 = 60;
+  u8 q = q1 < q2 ? q1 : q2;
+  if (q < 60 && force >= 0 && force < q) q = (u8)force;
+  return q;
+}
+
+struct OutRecord {  // == cmx_pe_record
+  u32 read_id, rid, fragment_start;
+  unsigned short fragment_length;
+  u8 mapq, direction, is_unique, num_dups;
+  unsigned short positive_alignment_length, negative_alignment_length;
+};
+
+// K6: per pair — ProcessBestMappingsForPairedEndReadOnOneDirection (mapping_generator.h:486-654):
+// the selected best pair(s), start coordinates (mapping_generator.h:657-917 BED branch), MAPQ, record.
+__global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, const int *pair_sel, OutRecord *out,
+                            int *out_n, Counters *ctr) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status == ST_OVERFLOW) return;  // re-done in the large tier (or reported)
+  if (pm.status != ST_OK || pm.n_best > P.drop_rep || pm.n_best == 0) { out_n[pair] = 0; return; }
+  const Caps c = S.caps;
+  const ReadMeta *rm = S.rmeta + 2 * slot;
+  const int mb = P.max_best;
+  const int to_report = mb < pm.n_best ? mb : pm.n_best;
+  const int *sel = pair_sel + (size_t)pair * mb;
+  const u8 uniq = (pm.n_best == 1 || rm[0].n_best == 1 || rm[1].n_best == 1) ? 1 : 0;
+  const int force = pm.sup != 0 ? 0 : -1;
+  int idx = 0, reported = 0;
+  const int e = P.e;
+  const int L[2] = {rm[0].len, rm[1].len};
+  const u8 *rd[2] = {read_ptr(B, pair, 0), read_ptr(B, pair, 1)};
+  auto span = [&](int m, int s, u64 dpos, int derr, u32 *st, u32 *en) {
+    const u32 rid = (u32)(dpos >> 32), rp = (u32)dpos;
+    const int Lm = L[m];
+    u32 vws = rp + 1u > (u32)(Lm + e) ? rp + 1u - (u32)Lm - (u32)e : 0u;
+    if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)Lm;
+    const u8 *win = R.seq + R.off[rid] + vws;
+    const u8 *r = rd[m];
+    int s0;
+    if (s == 0) s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[i]; });
+    else s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return code_char(neg_code(r, Lm, i)); });
+    *st = vws + (u32)s0;
+    *en = rp;
+  };
+  for (int dir = 0; dir < 2 && reported != to_report; ++dir) {
+    const int s1 = dir, s2 = 1 - dir;
+    const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const signed char *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    pair_sweep(P, s1, (u32)L[0], (u32)L[1], p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) {
+      if (sum != pm.min_sum || reported == to_report) return;
+      if (idx == sel[reported]) {
+        u32 st1, en1, st2, en2;
+        span(0, s1, p1[i1], e1[i1], &st1, &en1);
+        span(1, s2, p2[j], e2[j], &st2, &en2);
+        const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
+        OutRecord o;
+        o.read_id = B.first_read_id + (u32)pair;
+        o.rid = (u32)(p1[i1] >> 32);
+        o.fragment_start = s1 == 0 ? st1 : st2;
+        o.fragment_length = (unsigned short)(s1 == 0 ? (int)(en2 - st1 + 1u) : (int)(en1 - st2 + 1u));
+        o.mapq = mapq_pe(T, e1[i1], e2[j], al1, al2, L[0], L[1], force, pm, rm);
+        o.direction = s1 == 0 ? 1 : 0;
+        o.is_unique = uniq;
+        o.num_dups = 1;
+        o.positive_alignment_length = s1 == 0 ? al1 : al2;
+        o.negative_alignment_length = s1 == 1 ? al1 : al2;
+        out[(size_t)pair * mb + reported] = o;
+        ++reported;
+      }
+      ++idx;
+    });
+  }
+  out_n[pair] = reported;
+  pm.n_rec = reported;
+  if (reported > 0) { atomicAdd(&ctr->n_mapped, 1ull); if (pm.n_best == 1) atomicAdd(&ctr->n_unique, 1ull); }
+}
+
+// compaction of per-pair records into read order
+__global__ void compact_kernel(int n_pairs, int mb, const OutRecord *in, const int *n_rec, const u64 *offs, OutRecord *out) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  const int n = n_rec[pair];
+  for (int j = 0; j < n; ++j) out[offs[pair] + j] = in[(size_t)pair * mb + j];
+}
+
+// collect pairs whose small-tier run overflowed
+__global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  if (S.pmeta[slot].status == ST_OVERFLOW) list[atomicAdd(count, 1)] = slot_pair(S, slot);
+}

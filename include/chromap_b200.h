@@ -1,0 +1,171 @@
+/* chromap_b200 — C ABI of the B200-native replacement for Chromap's per-read mapping hot path.
+ *
+ * The reference (haowenz/chromap) has NO plugin / FFI interface: it is one executable whose hot path is
+ * the body of the OpenMP taskloop in src/chromap.h:892-1143 (paired-end).  This header DEFINES the
+ * boundary a maintainer would bind (INTEGRATION.md shows the call sites to replace).  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference's src/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * cmx_status; nothing exits or throws across the ABI (the reference calls exit(-1), utils.h:71-74).
+ * There is no CPU fallback: without a CUDA device cmx_create() fails with CMX_ERR_NO_DEVICE.
+ */
+#ifndef CHROMAP_B200_H_
+#define CHROMAP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CMX_OK = 0,
+  CMX_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run */
+  CMX_ERR_CUDA = -2,        /* a CUDA runtime call failed; see cmx_last_error() */
+  CMX_ERR_INVALID = -3,     /* bad argument / unsupported parameter combination */
+  CMX_ERR_STATE = -4,       /* index or reference not uploaded yet */
+  CMX_ERR_OVERFLOW = -5,    /* a pair exceeded even the large scratch tier (reported, never silent) */
+  CMX_ERR_IO = -6
+} cmx_status;
+
+/* POD mirror of the MappingParameters fields the path reads (mapping_parameters.h:18-78). */
+typedef struct {
+  int32_t error_threshold;        /* -e   (8)   */
+  int32_t min_num_seeds;          /* -s   (2)   */
+  int32_t max_seed_freq0;         /* -f a (500) */
+  int32_t max_seed_freq1;         /* -f b (1000)*/
+  int32_t max_num_best_mappings;  /* -n   (1)   */
+  int32_t max_insert_size;        /* -l   (1000)*/
+  int32_t mapq_threshold;         /* -q   (30)  */
+  int32_t min_read_length;        /* --min-read-length (30) */
+  int32_t drop_repetitive_reads;  /* (500000) */
+  int32_t trim_adapters;
+  int32_t remove_pcr_duplicates;
+  int32_t tn5_shift;
+  int32_t split_alignment;        /* must be 0 in this round (Hi-C split alignment: next) */
+  int32_t low_memory_mode;
+  int32_t output_format;          /* 1 = BED */
+  int32_t batch_size;             /* pairs per reference batch (chromap.h:182: 500000); fixes the
+                                     taskloop chunking that seeds multi-mapper sampling */
+  int32_t max_read_length;        /* upper bound on read length in any batch (sizing), default 160 */
+} cmx_params;
+
+void cmx_default_params(cmx_params *p);
+/* chromap_driver.cc:247-275.  preset = "chip" | "atac" | "hic" | "".  -3 if unknown. */
+int cmx_apply_preset(cmx_params *p, const char *preset);
+
+typedef struct cmx_ctx cmx_ctx; /* one per GPU */
+
+/* Replaces the Chromap(MappingParameters) constructor + stage objects (chromap.h:176-215,803-812). */
+int cmx_create(cmx_ctx **out, int device, const cmx_params *params);
+void cmx_destroy(cmx_ctx *ctx);
+const char *cmx_last_error(const cmx_ctx *ctx);
+
+/* Replaces SequenceBatch::LoadAllSequences for the reference (chromap.h:641-644, sequence_batch.cc:84):
+ * n_seq sequences, bases as loaded (ASCII, case preserved), concatenated; offsets[n_seq+1]. Host buffers
+ * are borrowed for the duration of the call. */
+int cmx_upload_reference(cmx_ctx *ctx, uint32_t n_seq, const uint64_t *offsets, const char *concat_ascii);
+
+/* Replaces Index::Load (index.cc:132-169): the khash arrays of the index file (khash.h:358-373) and the
+ * occurrence table, re-laid-out on the device (layout is free; every lookup answers identically). */
+int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint32_t *flags,
+                     const uint64_t *keys, const uint64_t *vals, const uint64_t *occ, uint32_t n_occ);
+/* Replaces Index::Construct (index.cc:12-89) on the device, from the uploaded reference. */
+int cmx_build_index(cmx_ctx *ctx, int k, int w);
+/* Download the index in the reference's file layout pieces (for Index::Save, index.cc:91-130).
+ * Pass NULL buffers to query sizes. */
+int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint32_t *flags,
+                       uint64_t *keys, uint64_t *vals, uint32_t *n_occ, uint64_t *occ);
+int cmx_index_info(const cmx_ctx *ctx, int *k, int *w, uint64_t *n_keys, uint64_t *n_occ,
+                   uint64_t *table_slots);
+
+/* One batch of read pairs = the inputs of the taskloop (read_batch1, read_batch2; chromap.h:892).
+ * Bases are ASCII exactly as in the FASTQ; pair i's mates are seq1[off1[i]..off1[i+1]) and
+ * seq2[off2[i]..off2[i+1]).  on_device != 0: all four pointers are device pointers. */
+typedef struct {
+  uint32_t n_pairs;
+  const char *seq1;
+  const uint32_t *off1; /* n_pairs + 1 */
+  const char *seq2;
+  const uint32_t *off2;   /* n_pairs + 1 */
+  uint32_t first_read_id; /* running read counter (sequence_batch.cc:38-39) */
+  int32_t on_device;
+} cmx_batch;
+
+/* PairedEndMappingWithoutBarcode (bed_mapping.h:170-238) without the vptr, plus rid. 24 bytes. */
+typedef struct {
+  uint32_t read_id;
+  uint32_t rid;
+  uint32_t fragment_start;
+  uint16_t fragment_length;
+  uint8_t mapq;
+  uint8_t direction; /* 1 = read 1 on + strand */
+  uint8_t is_unique;
+  uint8_t num_dups;
+  uint16_t positive_alignment_length;
+  uint16_t negative_alignment_length;
+} cmx_pe_record;
+
+typedef struct {
+  cmx_pe_record *records; /* caller-owned, capacity >= n_pairs * max_num_best_mappings */
+  uint64_t capacity;
+  uint64_t n_records;    /* out */
+  int32_t on_device;     /* records is a device pointer (n_records still returned on the host) */
+  /* out: counters the reference prints (chromap.cc:808-823) */
+  uint64_t n_mapped_pairs, n_uniquely_mapped_pairs, n_candidates, n_overflow_pairs;
+} cmx_records;
+
+/* Replaces the taskloop body over one batch, chromap.h:892-1143: trimming, minimizers, index probe,
+ * candidate clustering, mate supplementation, paired-end filter, banded verification, pairing,
+ * multi-mapper sampling, start-coordinate traceback, MAPQ, record emit.  Records come back in read
+ * order.  Synchronous: returns when the records are in `out`. `stream` (cudaStream_t) may be NULL. */
+int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *stream);
+
+/* Post-processing on the device (mapping_processor.h:100-202, mapping_writer.h:166-376,
+ * chromap.h:1305-1355): sort by (rid, record order), duplicate removal, Tn5 shift, MAPQ filter.
+ * In place on host records; returns the surviving count in *n_out. */
+int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *records, uint64_t n, uint64_t *n_out);
+/* BED text (mapping_writer.cc:75-83); names = n_seq C strings.  Returns bytes (or needed size if buf NULL). */
+int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, uint64_t n, char *buf,
+                       int64_t cap);
+
+/* ---- stage-level entry points: fixture-level parity tests and ncu isolation ------------------- */
+/* MinimizerGenerator::GenerateMinimizers (minimizer_generator.cc:7-139) for every read of a host batch.
+ * out_hash/out_pos hold n_reads*stride entries (stride = max_read_length); out_n the per-read count.
+ * out_pos = (end_position << 1) | strand.  Reads are numbered 2*pair + mate. */
+int cmx_stage_minimizers(cmx_ctx *ctx, const cmx_batch *in, uint64_t *out_hash, uint32_t *out_pos,
+                         int32_t *out_n, uint32_t stride);
+/* kh_get (khash.h:232-245) for n minimizer hashes: found[i], key[i] (hash<<1|singleton), val[i]. */
+int cmx_stage_probe(cmx_ctx *ctx, const uint64_t *hashes, uint64_t n, uint8_t *found, uint64_t *key,
+                    uint64_t *val);
+/* BandedAlignPatternToText (alignment.cc:141-192) on n (pattern, text) problems of equal read_len:
+ * patterns n*(read_len+2e) bytes, texts n*read_len bytes. */
+int cmx_stage_banded_align(cmx_ctx *ctx, int e, int read_len, const char *patterns, const char *texts,
+                           uint64_t n, int32_t *num_errors, int32_t *end_pos);
+/* Per-pair counters after a full cmx_map_batch_pe (same fields as the oracle's trace). */
+typedef struct {
+  int32_t n_minimizers[2];
+  int32_t n_pos_candidates_gen[2], n_neg_candidates_gen[2];
+  int32_t n_pos_candidates[2], n_neg_candidates[2];
+  int32_t n_pos_mappings[2], n_neg_mappings[2];
+  int32_t min_errors[2], second_min_errors[2], n_best[2], n_second_best[2];
+  uint32_t repetitive_seed_length[2];
+  int32_t supplement_result;
+  int32_t min_sum_errors, second_min_sum_errors, n_best_pairs, n_second_best_pairs;
+  int32_t n_records;
+  int32_t trimmed_len[2];
+} cmx_pair_trace;
+int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs);
+
+/* Kernel timing of the last cmx_map_batch_pe (CUDA events on the launching stream), in ms. */
+typedef struct {
+  float h2d_ms, seed_ms, pair_candidates_ms, verify_ms, pairing_ms, select_ms, emit_ms, d2h_ms, total_ms;
+  uint64_t n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_launches;
+} cmx_timing;
+int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMAP_B200_H_ */

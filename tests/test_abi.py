@@ -1,0 +1,54 @@
+"""CPU-only checks of the product boundary: the C-ABI library loads and exports every symbol that
+include/chromap_b200.h declares; without a GPU the product refuses to run (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import chromap_b200 as cb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "chromap_b200.h")).read()
+    return sorted(set(re.findall(r"\b(cmx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(cb.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(cb.lib_path())
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_presets_match_reference_driver():
+    for preset, want in (("chip", dict(max_insert_size=2000, remove_pcr_duplicates=1, low_memory_mode=1, trim_adapters=0)),
+                         ("atac", dict(max_insert_size=2000, remove_pcr_duplicates=1, low_memory_mode=1, trim_adapters=1, tn5_shift=1)),
+                         ("", dict(max_insert_size=1000, error_threshold=8, mapq_threshold=30, low_memory_mode=0))):
+        p = cb.make_params(preset)
+        for k, v in want.items():
+            assert getattr(p, k) == v
+    with pytest.raises(cb.CmxError):
+        cb.make_params("nope")
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb.CmxError):
+        cb.Mapper(cb.make_params("chip"))
+
+
+def test_taskloop_chunks_match_libgomp_probe():
+    # measured with a stand-alone OpenMP probe on this image's libgomp
+    assert cb.taskloop_chunks(23459) == [0, 5865, 11730, 17595]
+    assert cb.taskloop_chunks(9999) == [0]
+    assert cb.taskloop_chunks(10001) == [0, 5001]
+    assert len(cb.taskloop_chunks(500000)) == 100

@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors made by
+the reference binary.  Run with `-m gpu` on the B200 box."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import chromap_b200 as cb
+from oracle import oracle_py as orc
+from tests.util import load_pairs, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "chip": dict(preset="chip"),
+    "atac": dict(preset="atac"),
+    "default": dict(preset=""),
+    "q0dedup": dict(preset="", remove_pcr_duplicates=1, mapq_threshold=0),
+    "e5": dict(preset="", error_threshold=5, mapq_threshold=10, tn5_shift=1, remove_pcr_duplicates=1),
+    "e12l300": dict(preset="", error_threshold=12, max_insert_size=300, mapq_threshold=0),
+}
+
+
+@pytest.fixture(scope="module")
+def synth(golden_dir):
+    d = os.path.join(golden_dir, "synth_small")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    return dict(d=d, names=names, seqs=seqs, oref=oref, oidx=oidx, pairs=load_pairs(d))
+
+
+def _mapper(synth, kw, build_on_device=False):
+    kw = dict(kw)
+    p = cb.make_params(kw.pop("preset"), max_read_length=64, **kw)
+    m = cb.Mapper(p)
+    m.upload_reference(synth["seqs"], synth["names"])
+    if build_on_device:
+        m.build_index(17, 7)
+    else:
+        a = synth["oidx"].arrays()
+        m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    return m
+
+
+def _oparams(kw):
+    kw = dict(kw)
+    return orc.make_params(kw.pop("preset"), **kw)
+
+
+def test_stage_minimizers_equal_oracle(synth):
+    m = _mapper(synth, CASES["default"])
+    s1, o1, s2, o2 = synth["pairs"]
+    n = 1500
+    h, p, cnt = m.stage_minimizers(s1[:o1[n]], o1[:n + 1], s2[:o2[n]], o2[:n + 1], 64)
+    for i in range(n):
+        for mate, (s, o) in enumerate(((s1, o1), (s2, o2))):
+            oh, ot = orc.minimizers(s[o[i]:o[i + 1]], 17, 7)
+            r = 2 * i + mate
+            assert cnt[r] == len(oh)
+            assert np.array_equal(h[r, :cnt[r]], oh)
+            assert np.array_equal(p[r, :cnt[r]].astype(np.uint64), ot & np.uint64(0xFFFFFFFF))
+
+
+def test_stage_probe_equals_khash_lookup(synth):
+    import ctypes as C
+    m = _mapper(synth, CASES["default"])
+    rng = np.random.default_rng(5)
+    hs = [orc.minimizers(synth["seqs"][0][:200000], 17, 7)[0][::3]]
+    hs.append(rng.integers(0, 1 << 34, 5000, dtype=np.uint64))  # mostly absent
+    hashes = np.concatenate(hs)
+    f, k, v = m.stage_probe(hashes)
+    L = orc.lib()
+    for i in range(0, len(hashes), 5):
+        kk, vv = C.c_uint64(), C.c_uint64()
+        found = L.orc_index_lookup(synth["oidx"].h, int(hashes[i]), C.byref(kk), C.byref(vv))
+        assert found == f[i]
+        if found:
+            assert (kk.value, vv.value) == (int(k[i]), int(v[i]))
+
+
+@pytest.mark.parametrize("e,L", [(8, 50), (4, 150), (15, 36), (1, 30)])
+def test_stage_banded_align_equals_oracle(synth, e, L):
+    import ctypes as C
+    m = _mapper(synth, CASES["default"])
+    rng = np.random.default_rng(e * 1000 + L)
+    n = 3000
+    acgt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    pats = acgt[rng.integers(0, 4, (n, L + 2 * e))].copy()
+    texts = np.zeros((n, L), dtype=np.uint8)
+    for i in range(n):  # read = window shifted by up to +-e, with substitutions / an indel
+        sh = int(rng.integers(0, 2 * e + 1))
+        t = pats[i, sh:sh + L].copy()
+        if len(t) < L:
+            t = np.concatenate([t, acgt[rng.integers(0, 4, L - len(t))]])
+        nsub = int(rng.integers(0, e + 3))
+        t[rng.integers(0, L, nsub)] = acgt[rng.integers(0, 5, nsub)]
+        if rng.random() < 0.3:
+            p = int(rng.integers(1, L - 1))
+            t = np.concatenate([t[:p], t[p + 1:], acgt[rng.integers(0, 4, 1)]])
+        texts[i] = t
+    err, endp = m.stage_banded_align(e, L, pats, texts)
+    Lb = orc.lib()
+    for i in range(n):
+        ep = C.c_int(0)
+        oe = Lb.orc_banded_align(e, pats[i].ctypes.data, texts[i].ctypes.data, L, C.byref(ep))
+        assert oe == err[i]
+        if oe <= e:
+            assert ep.value == endp[i]
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_map_batch_records_equal_oracle_and_golden(synth, case):
+    kw = CASES[case]
+    m = _mapper(synth, kw)
+    s1, o1, s2, o2 = synth["pairs"]
+    recs, stats = m.map_batch(s1, o1, s2, o2)
+    orecs, otrace = orc.map_pairs(_oparams(kw), synth["oidx"], synth["oref"], s1, o1, s2, o2, trace=True)
+    tr = m.trace(len(o1) - 1)
+    for f in ("n_minimizers", "n_pos_candidates_gen", "n_neg_candidates_gen", "supplement_result"):
+        assert np.array_equal(tr[f], otrace[f]), f
+    alive = otrace["n_records"] > 0
+    for f in ("n_pos_candidates", "n_neg_candidates", "n_pos_mappings", "n_neg_mappings", "min_errors", "n_best",
+              "min_sum_errors", "n_best_pairs", "n_second_best_pairs", "repetitive_seed_length", "trimmed_len"):
+        assert np.array_equal(tr[f][alive], otrace[f][alive]), f
+    assert len(recs) == len(orecs)
+    assert recs.tobytes() == orecs.tobytes()
+    assert stats["n_overflow_pairs"] == 0
+    bed = m.format_bed(m.postprocess(recs))
+    want = gzip.open(os.path.join(synth["d"], case + ".bed.gz")).read()
+    assert bed == want
+
+
+def test_index_built_on_device_equals_reference_semantics(synth):
+    m = _mapper(synth, CASES["default"], build_on_device=True)
+    a = synth["oidx"].arrays()
+    info = m.index_info()
+    assert info["n_occ"] == len(a["occ"])
+    d = m.download_index()
+    assert np.array_equal(d["occ"], a["occ"])
+    assert d["n_buckets"] == a["n_buckets"] and d["n_keys"] == info["n_keys"]
+    # every key of the oracle's table is found with the same value, and nothing else is present
+    occupied = ((a["flags"][np.arange(a["n_buckets"]) >> 4] >> ((np.arange(a["n_buckets"]) & 15) << 1)) & 3) == 0
+    keys, vals = a["keys"][occupied], a["vals"][occupied]
+    assert len(keys) == info["n_keys"]
+    f, k, v = m.stage_probe(keys >> np.uint64(1))
+    assert f.all() and np.array_equal(k, keys) and np.array_equal(v, vals)
+    # and mapping through the device-built index gives the golden BED
+    s1, o1, s2, o2 = synth["pairs"]
+    recs, _ = m.map_batch(s1, o1, s2, o2)
+    bed = m.format_bed(m.postprocess(recs))
+    assert bed == gzip.open(os.path.join(synth["d"], "default.bed.gz")).read()
+
+
+def test_reference_quickstart_golden(golden_dir):
+    """BASELINE config 1 (reference test/ data): md5 e311f0a0… / 63b977e6…"""
+    import hashlib
+    d = os.path.join(golden_dir, "ref_test")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(os.path.join(d, "ref.index"))  # the index file the reference binary wrote
+    a = oidx.arrays()
+    s1, o1, s2, o2 = load_pairs(d, "read1.fq", "read2.fq")
+    for preset, md5 in (("", "e311f0a0848edca7196d839f47b3e007"), ("chip", "e311f0a0848edca7196d839f47b3e007"),
+                        ("atac", "63b977e6e8af35be7861f35b6163f714")):
+        m = cb.Mapper(cb.make_params(preset, max_read_length=128))
+        m.upload_reference(seqs, names)
+        m.upload_index(oidx.k, oidx.w, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+        recs, _ = m.map_batch(s1, o1, s2, o2)
+        assert hashlib.md5(m.format_bed(m.postprocess(recs))).hexdigest() == md5
+
+
+def test_bigger_synthetic_with_heavy_repeats_equals_oracle(tmp_path):
+    """100k pairs on 4 x 2 Mbp with planted repeats: exercises every scratch tier and the sampling chunks."""
+    import subprocess
+    import sys
+    d = str(tmp_path)
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "gen_synth.py"),
+                           "--out", d, "--n-seq", "4", "--seq-len", "2000000", "--n-pairs", "100000", "--short-frac", "0.2"])
+    names, seqs = read_fasta(os.path.join(d, "ref.fa"))
+    oref = orc.Reference(os.path.join(d, "ref.fa"))
+    s1, o1, s2, o2 = load_pairs(d, "read1.fq", "read2.fq")
+    for preset, kw in (("atac", {}), ("", dict(mapq_threshold=0, remove_pcr_duplicates=1))):
+        m = cb.Mapper(cb.make_params(preset, max_read_length=64, **kw))
+        m.upload_reference(seqs, names)
+        m.build_index(17, 7)
+        d_idx = m.download_index()
+        oidx_path = os.path.join(d, "dev.index")
+        # write the device-built index in the reference's file format and let the ORACLE load it
+        with open(oidx_path, "wb") as f:
+            np.array([17, 7], dtype=np.int32).tofile(f)
+            np.array([d_idx["n_keys"], d_idx["n_buckets"], d_idx["n_keys"], d_idx["n_keys"],
+                      int(d_idx["n_buckets"] * 0.77 + 0.5)], dtype=np.uint32).tofile(f)
+            d_idx["flags"].tofile(f); d_idx["keys"].tofile(f); d_idx["vals"].tofile(f)
+            np.array([len(d_idx["occ"])], dtype=np.uint32).tofile(f)
+            d_idx["occ"].tofile(f)
+        oidx = orc.Index(oidx_path)
+        recs, stats = m.map_batch(s1, o1, s2, o2)
+        orecs, _ = orc.map_pairs(orc.make_params(preset, **kw), oidx, oref, s1, o1, s2, o2, n_threads=8)
+        assert stats["n_overflow_pairs"] == 0
+        assert recs.tobytes() == orecs.tobytes()
+        obed = orc.format_bed(oref, orc.postprocess(orc.make_params(preset, **kw), orecs))
+        assert m.format_bed(m.postprocess(recs)) == obed
