@@ -76,8 +76,10 @@ __global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
     }
   }
   S.pmeta[slot] = pm;
-  S.rmeta[2 * slot].len = len1;
-  S.rmeta[2 * slot + 1].len = len2;
+  ReadMeta z;
+  memset(&z, 0, sizeof(z));
+  z.len = len1; S.rmeta[2 * slot] = z;
+  z.len = len2; S.rmeta[2 * slot + 1] = z;
 }
 
 // ------------------------------------------------------------------------------------------------
