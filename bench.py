@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — paired-end reads mapped/sec on a synthetic hg38-scale reference (BASELINE.json configs[1]:
+--preset chip, 3 Gbp synthetic reference, 2x50 bp pairs).
+
+A "step" is one pass of the mapping hot path (trim -> minimizers -> index probe -> candidates -> mate
+supplement / PE filter -> banded verification -> pairing -> sampling -> traceback -> MAPQ -> record) over
+one batch of `--pairs-per-step` synthetic pairs, through the C ABI (include/chromap_b200.h).
+
+  value : pairs/s with the batch already resident in HBM (records stay on the device)
+  e2e   : pairs/s through the same call with HOST buffers (pinned), H2D of the reads and D2H of the
+          records inside the timed region
+  --impl reference : the UNMODIFIED reference binary (oracle/_ref/chromap) on the box's host cores, same
+          reference / index / read distribution; each step = one 500 000-pair reference batch, timed by
+          the reference's own per-batch "Mapped N read pairs in Xs" lines.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_MER, WINDOW = 17, 7
+ACGT = b"ACGT"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic data, generated on the device with torch (plumbing, not the product)
+def gen_reference(torch, dev, total_bp, n_seq, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    seq_len = total_bp // n_seq
+    lut = torch.tensor(list(ACGT), dtype=torch.uint8, device=dev)
+    ref = torch.empty(seq_len * n_seq, dtype=torch.uint8, device=dev)
+    CH = 1 << 28
+    for o in range(0, ref.numel(), CH):
+        n = min(CH, ref.numel() - o)
+        ref[o:o + n] = lut[torch.randint(0, 4, (n,), device=dev, generator=g, dtype=torch.int64)]
+    # planted segmental repeats: per sequence one 5 kb segment x 50 copies (odd copies 1 % diverged)
+    rep_len, rep_copies = 5000, 50
+    if seq_len > 4 * rep_len * rep_copies:
+        for s in range(n_seq):
+            base = s * seq_len
+            seg = lut[torch.randint(0, 4, (rep_len,), device=dev, generator=g)]
+            starts = torch.randint(0, seq_len - rep_len, (rep_copies,), device=dev, generator=g)
+            for ci in range(rep_copies):
+                c = seg.clone()
+                if ci % 2 == 1:
+                    m = torch.rand(rep_len, device=dev, generator=g) < 0.01
+                    c[m] = lut[torch.randint(0, 4, (int(m.sum()),), device=dev, generator=g)]
+                st = base + int(starts[ci])
+                ref[st:st + rep_len] = c
+    # 300 bp family, ~1e5 copies genome-wide at 3 Gbp (exercises the f=500/1000 caps)
+    fam_len = 300
+    fam_copies = int(1e5 * total_bp / 3e9)
+    if fam_copies > 0:
+        fam = lut[torch.randint(0, 4, (fam_len,), device=dev, generator=g)]
+        sid = torch.randint(0, n_seq, (fam_copies,), device=dev, generator=g)
+        st = sid * seq_len + torch.randint(0, seq_len - fam_len, (fam_copies,), device=dev, generator=g)
+        idx = st[:, None] + torch.arange(fam_len, device=dev)[None, :]
+        vals = fam[None, :].repeat(fam_copies, 1)
+        m = torch.rand(fam_copies, fam_len, device=dev, generator=g) < 0.005
+        vals[m] = lut[torch.randint(0, 4, (int(m.sum()),), device=dev, generator=g)]
+        ref[idx.reshape(-1)] = vals.reshape(-1)
+    # N runs, 0.1 %
+    n_runs = int(total_bp * 0.001 / 100)
+    if n_runs > 0:
+        sid = torch.randint(0, n_seq, (n_runs,), device=dev, generator=g)
+        ln = torch.randint(1, 200, (n_runs,), device=dev, generator=g)
+        st = sid * seq_len + torch.randint(0, seq_len - 200, (n_runs,), device=dev, generator=g)
+        ar = torch.arange(200, device=dev)[None, :]
+        idx = (st[:, None] + ar)[ar < ln[:, None]]
+        ref[idx] = ord("N")
+    offsets = np.arange(n_seq + 1, dtype=np.uint64) * np.uint64(seq_len)
+    return ref, offsets, seq_len
+
+
+def gen_pairs(torch, ref, n_seq, seq_len, n_pairs, read_len, seed, dev):
+    """2x read_len pairs: fragment length U[80,500], uniform origin, random strand, 1 % substitutions,
+    0.1 % single-base indels, 5 % PCR duplicates (exact fragment copies), 1 % junk pairs."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sid = torch.randint(0, n_seq, (n_pairs,), device=dev, generator=g)
+    fl = torch.randint(80, 501, (n_pairs,), device=dev, generator=g)
+    st = torch.randint(0, seq_len - 600, (n_pairs,), device=dev, generator=g)
+    strand = torch.randint(0, 2, (n_pairs,), device=dev, generator=g)
+    # duplicates copy an earlier fragment of the same batch
+    dup = torch.rand(n_pairs, device=dev, generator=g) < 0.05
+    src = (torch.rand(n_pairs, device=dev, generator=g) * torch.arange(n_pairs, device=dev)).long()
+    sid = torch.where(dup, sid[src], sid); fl = torch.where(dup, fl[src], fl)
+    st = torch.where(dup, st[src], st); strand = torch.where(dup, strand[src], strand)
+    base = sid * seq_len + st
+    ar = torch.arange(read_len, device=dev)[None, :]
+    comp = torch.full((256,), ord("N"), dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+
+    def indel_index(n):
+        # single-base deletion (skip one reference base) or insertion (repeat one index) in 0.1 %*L of reads
+        p = torch.randint(1, read_len - 1, (n, 1), device=dev, generator=g)
+        kind = torch.rand(n, 1, device=dev, generator=g)
+        has = kind < 0.001 * read_len
+        dele = kind < 0.0005 * read_len
+        shift = torch.where(ar >= p, torch.where(dele, 1, -1), 0)
+        return torch.where(has, shift, 0)
+
+    left = ref[(base[:, None] + ar + indel_index(n_pairs))]                       # forward strand, 5' end
+    ridx = base[:, None] + fl[:, None] - 1 - ar - indel_index(n_pairs)
+    right = comp[ref[ridx].long()]                                                # reverse complement of 3' end
+    fwd_first = (strand == 0)[:, None]
+    r1 = torch.where(fwd_first, left, right)
+    r2 = torch.where(fwd_first, right, left)
+    lut = torch.tensor(list(ACGT), dtype=torch.uint8, device=dev)
+    for r in (r1, r2):
+        m = torch.rand(n_pairs, read_len, device=dev, generator=g) < 0.01
+        r[m] = lut[torch.randint(0, 4, (int(m.sum()),), device=dev, generator=g)]
+    junk = torch.rand(n_pairs, device=dev, generator=g) < 0.01
+    nj = int(junk.sum())
+    if nj:
+        r1[junk] = lut[torch.randint(0, 4, (nj, read_len), device=dev, generator=g)]
+        r2[junk] = lut[torch.randint(0, 4, (nj, read_len), device=dev, generator=g)]
+    off = (torch.arange(n_pairs + 1, device=dev, dtype=torch.int64) * read_len).to(torch.int32)
+    return r1.contiguous().view(-1), r2.contiguous().view(-1), off
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = False
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def setup_world():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import chromap_b200 as cb
+    rank, local, world = setup_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total_bp = int(a.ref_gbp * 1e9)
+    t0 = time.time()
+    ref, offsets, seq_len = gen_reference(torch, dev, total_bp, a.n_seq, a.seed)
+    torch.cuda.synchronize()
+    log("rank %d: reference %.2f Gbp in %d sequences generated in %.1fs" % (rank, ref.numel() / 1e9, a.n_seq, time.time() - t0))
+    params = cb.make_params(a.preset, max_read_length=max(64, a.read_len + 14))
+    m = cb.Mapper(params, device=local)
+    m.upload_reference_ptr(ref.data_ptr(), offsets)
+    t0 = time.time()
+    m.build_index(K_MER, WINDOW)
+    info = m.index_info()
+    t_index = time.time() - t0
+    log("rank %d: index built on device in %.1fs: %s" % (rank, t_index, info))
+    n = a.pairs_per_step
+    pool = max(1, min(a.steps + a.warmup, a.pool))
+    # weak scaling: every rank maps its own batches (batch b -> rank b mod world)
+    dev_batches, host_batches = [], []
+    for b in range(pool):
+        gb = b * world + rank
+        r1, r2, off = gen_pairs(torch, ref, a.n_seq, seq_len, n, a.read_len, a.seed * 1000003 + gb, dev)
+        dev_batches.append((r1, r2, off))
+        host_batches.append(tuple(t.cpu().pin_memory() for t in (r1, r2, off)))
+    torch.cuda.synchronize()
+    mb = params.max_num_best_mappings
+    out_dev = torch.empty(n * mb * 24, dtype=torch.uint8, device=dev)
+    out_host = torch.empty(n * mb * 24, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        r1, r2, off = dev_batches[i % pool]
+        _, st = m.map_batch(r1, off, r2, off, first_read_id=(i * world + rank) * n, on_device=True, n_pairs=n, out=out_dev, out_on_device=True)
+        return st
+
+    def step_host(i):
+        r1, r2, off = host_batches[i % pool]
+        _, st = m.map_batch(r1.numpy(), off.numpy().view(np.uint32), r2.numpy(), off.numpy().view(np.uint32),
+                            first_read_id=(i * world + rank) * n, out=out_host.numpy().view(cb.PE_RECORD))
+        return st
+
+    res = {}
+    for name, fn in (("device", step_device), ("e2e", step_host)):
+        for i in range(a.warmup):
+            fn(i)
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        stage = {}
+        n_rec = n_map = launches = 0
+        counters = {}
+        for i in range(a.steps):
+            st = fn(a.warmup + i)
+            tm = m.timing()
+            for k_, v in tm.items():
+                stage[k_] = stage.get(k_, 0) + v
+            n_rec += st["n_records"]; n_map += st["n_mapped_pairs"]
+        barrier()
+        dt = time.perf_counter() - t0
+        sampler.stop_flag = True
+        sampler.join()
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        res[name] = dict(dt=dt, stage=stage, n_rec=n_rec, n_map=n_map, clocks=sampler.summary())
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu_baseline = cpu_port_baseline(a, m, ref, offsets, seq_len, host_batches[0])
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dv, ee = res["device"], res["e2e"]
+    value = a.steps * n * world / dv["dt"]
+    e2e = a.steps * n * world / ee["dt"]
+    st = dv["stage"]
+    kern = {k_: st[k_] / a.steps for k_ in ("seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms", "select_ms", "emit_ms")}
+    top = max(kern, key=kern.get)
+    peaks, peak_src = measured_peaks()
+    # algorithmic bytes of the seed (minimizer + index-probe + clustering) kernel per launch:
+    # read bases in + 16 B per probed table slot + 8 B per occurrence entry read
+    seed_bytes = (2 * a.read_len * n) + (st["n_probe_steps"] / a.steps) * 16 + (st["n_occ_reads"] / a.steps) * 8
+    achieved = seed_bytes / (kern["seed_ms"] * 1e-3) / 1e9 if kern["seed_ms"] > 0 else 0.0
+    line = {
+        "metric": "paired-end reads mapped/sec (hg38-scale, 2x50bp)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dv["dt"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "--preset %s, synthetic %.2f Gbp reference (%d seqs, planted repeats, N runs), 2x%d bp PE pairs, %d pairs/step/GPU"
+                               % (a.preset, ref.numel() / 1e9, a.n_seq, a.read_len, n),
+                   "preset": a.preset, "k": K_MER, "w": WINDOW, "pairs_per_step": n, "ref_bp": int(ref.numel()),
+                   "index": {"keys": info["n_keys"], "occurrences": info["n_occ"], "table_slots": info["table_slots"], "build_s": round(t_index, 2)},
+                   "l2": "inputs (%.0f MB reads/step) and the %.1f GB index exceed L2; distinct batches cycle through a pool of %d"
+                         % (2 * a.read_len * n / 1e6, info["table_slots"] * 16 / 1e9, pool),
+                   "sharding": "batch b -> rank b mod N, index+reference replicated per GPU, no data-path collective"},
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * a.read_len * n + 8 * (n + 1)),
+                "d2h_bytes_per_step": int(24 * ee["n_rec"] / a.steps), "ms_per_step": ee["dt"] / a.steps * 1e3},
+        "gpu_launches": int(st["n_launches"]),
+        "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
+        "kernel_ms_per_step": {k_: round(v, 3) for k_, v in kern.items()},
+        "mapped_fraction": dv["n_map"] / (a.steps * n),
+        "roofline": {"kernel": "seed_kernel (minimizers + index probe + hit sort + clustering)", "bound": "hbm",
+                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "peak_source": peak_src, "traffic": None, "top_stage": top,
+                     "probe_steps_per_pair": st["n_probe_steps"] / (a.steps * n), "minimizers_per_pair": st["n_minimizers"] / (a.steps * n),
+                     "verified_candidates_per_pair": st["n_verified"] / (a.steps * n),
+                     "cell_updates_per_s": (st["n_verified"] / a.steps) * a.read_len * (2 * params.error_threshold + 1) / (kern["verify_ms"] * 1e-3) if kern["verify_ms"] > 0 else None},
+    }
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_baseline(a, m, ref, offsets, seq_len, host_batch):
+    """The CPU oracle (a port, oracle/) on a bounded sample of the same workload, all host cores."""
+    from oracle import oracle_py as orc
+    import psutil
+    cores = os.cpu_count() or 1
+    need = m.index_info()["n_keys"] * 2 * 16 * 2.2 + ref.numel() * 2
+    if psutil.virtual_memory().available < need:
+        log("cpu_baseline skipped: not enough host RAM for a second copy of the index")
+        return None
+    t0 = time.time()
+    idx = m.download_index()
+    oidx = orc.Index(arrays=idx, k=K_MER, w=WINDOW)
+    del idx
+    href = ref.cpu().numpy()
+    oref = orc.Reference(seqs=[href[int(offsets[i]):int(offsets[i + 1])] for i in range(len(offsets) - 1)])
+    log("cpu_baseline: index + reference copied to the host in %.1fs" % (time.time() - t0))
+    r1, r2, off = (t.numpy() for t in host_batch)
+    n = min(len(off) - 1, a.cpu_sample_pairs)
+    L = a.read_len
+    p = orc.make_params(a.preset)
+    s1, s2, o = r1[:n * L], r2[:n * L], off[:n + 1].view(np.uint32)
+    orc.map_pairs(p, oidx, oref, s1[:20000 * L], o[:20001], s2[:20000 * L], o[:20001], n_threads=cores)  # warm-up
+    t0 = time.perf_counter()
+    recs, _ = orc.map_pairs(p, oidx, oref, s1, o, s2, o, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "%d pairs of step 0 through oracle/ (CPU restatement, OpenMP over taskloop chunks), same index arrays" % n}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """The unmodified reference binary on the host cores.  Needs a GPU only to synthesise the same data and
+    to build the (identical-lookup) index in seconds; chromap itself runs on the CPU, untouched."""
+    rank, local, world = setup_world()
+    if rank != 0:
+        return
+    binp = os.path.join(ROOT, "oracle", "_ref", "chromap")
+    if not os.path.exists(binp):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/chromap not built (needs /root/reference at build time)"}))
+        return
+    import torch
+    import chromap_b200 as cb
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    total_bp = int(a.ref_gbp * 1e9)
+    ref, offsets, seq_len = gen_reference(torch, dev, total_bp, a.n_seq, a.seed)
+    m = cb.Mapper(cb.make_params(a.preset, max_read_length=max(64, a.read_len + 14)), device=local)
+    m.upload_reference_ptr(ref.data_ptr(), offsets)
+    m.build_index(K_MER, WINDOW)
+    work = a.workdir or ("/dev/shm/chromap_b200_bench" if os.path.isdir("/dev/shm") else "/tmp/chromap_b200_bench")
+    os.makedirs(work, exist_ok=True)
+    t0 = time.time()
+    idx = m.download_index()
+    with open(os.path.join(work, "ref.index"), "wb") as f:  # index.cc:91-130 / khash.h:374-386 layout
+        np.array([K_MER, WINDOW], dtype=np.int32).tofile(f)
+        np.array([idx["n_keys"], idx["n_buckets"], idx["n_keys"], idx["n_keys"], int(idx["n_buckets"] * 0.77 + 0.5)], dtype=np.uint32).tofile(f)
+        idx["flags"].tofile(f); idx["keys"].tofile(f); idx["vals"].tofile(f)
+        np.array([len(idx["occ"])], dtype=np.uint32).tofile(f)
+        idx["occ"].tofile(f)
+    del idx
+    href = ref.cpu().numpy()
+    with open(os.path.join(work, "ref.fa"), "wb") as f:
+        for i in range(a.n_seq):
+            f.write(b">chr%d\n" % (i + 1))
+            href[int(offsets[i]):int(offsets[i + 1])].tofile(f)
+            f.write(b"\n")
+    n_batches = a.warmup + a.steps
+    n = 500000  # one reference batch (chromap.h:182) per step
+    L = a.read_len
+    for which in (0, 1):
+        with open(os.path.join(work, "read%d.fq" % (which + 1)), "wb") as f:
+            for b in range(n_batches):
+                r = gen_pairs(torch, ref, a.n_seq, seq_len, n, L, a.seed * 1000003 + b, dev)[which].cpu().numpy().reshape(n, L)
+                rec = np.empty((n, 2 * L + 16), dtype=np.uint8)  # "@" + 9-digit id + "\n" + seq + "\n+\n" + qual + "\n"
+                ids = np.char.zfill((np.arange(n) + b * n).astype(str), 9).astype("S9")
+                rec[:, 0] = ord("@"); rec[:, 1:10] = np.frombuffer(ids.tobytes(), dtype=np.uint8).reshape(n, 9)
+                rec[:, 10] = 10; rec[:, 11:11 + L] = r; rec[:, 11 + L] = 10; rec[:, 12 + L] = ord("+"); rec[:, 13 + L] = 10
+                rec[:, 14 + L:14 + 2 * L] = ord("I"); rec[:, 14 + 2 * L] = 10
+                rec[:, :15 + 2 * L].tofile(f)
+    del ref, m
+    torch.cuda.empty_cache()
+    log("reference arm: inputs written to %s in %.1fs" % (work, time.time() - t0))
+    cores = os.cpu_count() or 1
+    cmd = [binp, "--preset", a.preset, "-x", os.path.join(work, "ref.index"), "-r", os.path.join(work, "ref.fa"),
+           "-1", os.path.join(work, "read1.fq"), "-2", os.path.join(work, "read2.fq"), "-o", os.path.join(work, "out.bed"), "-t", str(cores)]
+    t0 = time.time()
+    pr = subprocess.run(cmd, capture_output=True, text=True)
+    wall = time.time() - t0
+    per_batch = []
+    for line in pr.stderr.splitlines():
+        if line.startswith("Mapped ") and "read pairs in" in line:
+            per_batch.append(float(line.split(" in ")[1].rstrip("s.")))
+    for f in ("ref.index", "ref.fa", "read1.fq", "read2.fq", "out.bed"):
+        try:
+            os.remove(os.path.join(work, f))
+        except OSError:
+            pass
+    if pr.returncode != 0 or len(per_batch) < n_batches:
+        print(json.dumps({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (pr.returncode, pr.stderr[-300:].replace("\n", " | "))}))
+        return
+    timed = per_batch[a.warmup:a.warmup + a.steps]
+    dt = sum(timed)
+    v = a.steps * n / dt
+    line = {"impl": "reference", "metric": "paired-end reads mapped/sec (hg38-scale, 2x50bp)", "value": v, "unit": "pairs/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "--preset %s, synthetic %.2f Gbp reference (%d seqs), 2x%d bp PE pairs; reference chromap 0.3.3 -t %d, step = one 500000-pair batch (its own per-batch timer)"
+                                   % (a.preset, total_bp / 1e9, a.n_seq, L, cores), "total_wall_s": round(wall, 1)},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                             "sample": "%d batches of 500000 pairs, reference binary 'Mapped N read pairs in Xs' lines" % a.steps},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="chip")
+    ap.add_argument("--ref-gbp", type=float, default=3.0)
+    ap.add_argument("--n-seq", type=int, default=24)
+    ap.add_argument("--read-len", type=int, default=50)
+    ap.add_argument("--pairs-per-step", type=int, default=2000000)
+    ap.add_argument("--pool", type=int, default=6)
+    ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1000000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workdir", default=None)
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,6 +164,12 @@ class Mapper:
         self._check(self.L.cmx_upload_reference(self.h, len(seqs), offs.ctypes.data, concat.ctypes.data), "cmx_upload_reference")
         self.names = names or ["chr%d" % (i + 1) for i in range(len(seqs))]
 
+    def upload_reference_ptr(self, ptr, offsets, names=None):
+        """Reference already concatenated in (host or device) memory at `ptr`; offsets uint64[n_seq+1]."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self.L.cmx_upload_reference(self.h, len(offs) - 1, offs.ctypes.data, int(ptr)), "cmx_upload_reference")
+        self.names = names or ["chr%d" % (i + 1) for i in range(len(offs) - 1)]
+
     def upload_index(self, k, w, n_buckets, flags, keys, vals, occ):
         flags = np.ascontiguousarray(flags, dtype=np.uint32); keys = np.ascontiguousarray(keys, dtype=np.uint64)
         vals = np.ascontiguousarray(vals, dtype=np.uint64); occ = np.ascontiguousarray(occ, dtype=np.uint64)

@@ -63,7 +63,7 @@ struct cmx_ctx {
   double *inv_log = nullptr;
   int *pen_thr = nullptr;
   // per-batch buffers
-  DevBuf seq1, off1, seq2, off2, nbest, sel, out_rec, out_n, offs, out_compact, chunk_start, cub_tmp, trace;
+  DevBuf rescue_list, seq1, off1, seq2, off2, nbest, sel, out_rec, out_n, offs, out_compact, chunk_start, cub_tmp, trace;
   Counters *ctr = nullptr;
   int *d_count = nullptr;
   Tier tiers[N_TIERS];
@@ -171,7 +171,7 @@ void cmx_destroy(cmx_ctx *ctx) {
   cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
   cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr);
   cudaFree(ctx->ctr); cudaFree(ctx->d_count);
-  for (DevBuf *b : {&ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->nbest, &ctx->sel, &ctx->out_rec, &ctx->out_n, &ctx->offs,
+  for (DevBuf *b : {&ctx->rescue_list, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->nbest, &ctx->sel, &ctx->out_rec, &ctx->out_n, &ctx->offs,
                     &ctx->out_compact, &ctx->chunk_start, &ctx->cub_tmp, &ctx->trace})
     release(*b);
   for (auto &t : ctx->tiers) { release(t.mem); release(t.ovf_list); }
@@ -200,7 +200,7 @@ int cmx_upload_reference(cmx_ctx *ctx, uint32_t n_seq, const uint64_t *offsets, 
   CU(cudaMalloc(&ctx->ref_seq, ctx->ref_bytes));
   CU(cudaMemset(ctx->ref_seq, 0, ctx->ref_bytes));
   for (u32 i = 0; i < n_seq; ++i)
-    CU(cudaMemcpy(ctx->ref_seq + doff[i], concat + offsets[i], dlen[i], cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->ref_seq + doff[i], concat + offsets[i], dlen[i], cudaMemcpyDefault));  // host or device source
   CU(cudaMalloc(&ctx->ref_off, n_seq * sizeof(u64)));
   CU(cudaMalloc(&ctx->ref_len, n_seq * sizeof(u32)));
   CU(cudaMemcpy(ctx->ref_off, doff.data(), n_seq * sizeof(u64), cudaMemcpyHostToDevice));
@@ -277,11 +277,38 @@ int cmx_build_index(cmx_ctx *ctx, int k, int w) {
   return CMX_OK;
 }
 
+// khash geometry + layout on the device: every (key, val) re-inserted with khash's own probe sequence
+// (hash = key>>1 truncated to 32 bit, triangular steps; khash.h:232-245) so the reference's kh_get finds it.
+__global__ void khash_layout_kernel(const ulonglong2 *slots, u64 n_slots, u64 *keys, u64 *vals, u32 mask) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const ulonglong2 kv = slots[i];
+  if (kv.x == CMX_EMPTY_KEY) return;
+  u32 b = (u32)(kv.x >> 1) & mask, step = 0;
+  for (;;) {
+    const u64 old = atomicCAS((unsigned long long *)&keys[b], (unsigned long long)CMX_EMPTY_KEY, (unsigned long long)kv.x);
+    if (old == CMX_EMPTY_KEY) { vals[b] = kv.y; return; }
+    b = (b + (++step)) & mask;
+  }
+}
+__global__ void khash_flags_kernel(u64 *keys, u64 *vals, u32 n_buckets, u32 *flags) {
+  const u32 wi = blockIdx.x * blockDim.x + threadIdx.x;  // one flag word = 16 buckets (khash.h:165)
+  const u32 nf = n_buckets < 16 ? 1 : n_buckets >> 4;
+  if (wi >= nf) return;
+  u32 f = 0;
+  for (u32 j = 0; j < 16; ++j) {
+    const u32 b = wi * 16 + j;
+    const bool empty = b >= n_buckets || keys[b] == CMX_EMPTY_KEY;
+    if (empty) { f |= 2u << (j << 1); if (b < n_buckets) { keys[b] = 0; vals[b] = 0; } }
+  }
+  flags[wi] = f;
+}
+
 int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint32_t *flags, uint64_t *keys, uint64_t *vals,
                        uint32_t *n_occ, uint64_t *occ) {
   if (!ctx || !ctx->slots) return CMX_ERR_STATE;
   CU(cudaSetDevice(ctx->device));
-  // khash geometry the reference would have after inserting n_keys keys (khash.h:295-300: grow when
+  // bucket count the reference's khash has after inserting n_keys keys (khash.h:295-300: it grows when
   // n_occupied >= upper_bound = n_buckets*0.77+0.5)
   u32 nb = 4;
   while ((u32)(nb * 0.77 + 0.5) < ctx->n_keys) nb <<= 1;
@@ -290,25 +317,19 @@ int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint
   if (n_occ) *n_occ = ctx->n_occ;
   if (occ && ctx->n_occ) CU(cudaMemcpy(occ, ctx->occ, (size_t)ctx->n_occ * sizeof(u64), cudaMemcpyDeviceToHost));
   if (flags && keys && vals) {
-    // re-insert every (key, val) with khash's own probe sequence (hash = key>>1 truncated to 32 bit,
-    // triangular steps; khash.h:232-245) so the reference's kh_get finds them.
     const size_t nf = nb < 16 ? 1 : nb >> 4;
-    for (size_t i = 0; i < nf; ++i) flags[i] = 0xaaaaaaaau;
-    memset(keys, 0, (size_t)nb * 8);
-    memset(vals, 0, (size_t)nb * 8);
-    std::vector<ulonglong2> h(1u << 22);
-    const u32 m = nb - 1;
-    for (u64 o = 0; o < ctx->n_slots; o += h.size()) {
-      const size_t n = std::min<u64>(h.size(), ctx->n_slots - o);
-      CU(cudaMemcpy(h.data(), ctx->slots + o, n * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
-      for (size_t i = 0; i < n; ++i) {
-        if (h[i].x == CMX_EMPTY_KEY) continue;
-        u32 b = (u32)(h[i].x >> 1) & m, step = 0;
-        while (!((flags[b >> 4] >> ((b & 0xfU) << 1)) & 2)) b = (b + (++step)) & m;
-        flags[b >> 4] &= ~(3u << ((b & 0xfU) << 1));
-        keys[b] = h[i].x; vals[b] = h[i].y;
-      }
-    }
+    u64 *dk = nullptr, *dv = nullptr;
+    u32 *df = nullptr;
+    CU(cudaMalloc(&dk, (size_t)nb * 8)); CU(cudaMalloc(&dv, (size_t)nb * 8)); CU(cudaMalloc(&df, nf * 4));
+    CU(cudaMemset(dk, 0xFF, (size_t)nb * 8)); CU(cudaMemset(dv, 0, (size_t)nb * 8));
+    khash_layout_kernel<<<(unsigned)((ctx->n_slots + 255) / 256), 256>>>(ctx->slots, ctx->n_slots, dk, dv, nb - 1);
+    khash_flags_kernel<<<(unsigned)((nf + 255) / 256), 256>>>(dk, dv, nb, df);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(keys, dk, (size_t)nb * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vals, dv, (size_t)nb * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(flags, df, nf * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dk); cudaFree(dv); cudaFree(df);
   }
   return CMX_OK;
 }
@@ -435,15 +456,29 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6], e2 = ctx->ev[7], e3 = ctx->ev[8], e4 = ctx->ev[9];
     CU(cudaEventRecord(e0, st));
     prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
-    seed_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, B, S, ctx->ctr);
-    CU(cudaEventRecord(e1, st));
-    pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr);
-    CU(cudaEventRecord(e2, st));
-    verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
-    CU(cudaEventRecord(e3, st));
-    pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
-    CU(cudaEventRecord(e4, st));
-    launches += 5;
+    if (t == 0) {
+      seed_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, B, S, ctx->ctr);
+      CU(cudaEventRecord(e1, st));
+      CU(ensure(ctx->rescue_list, (size_t)n_slots * 4));
+      CU(cudaMemsetAsync(ctx->d_count + 1, 0, sizeof(int), st));
+      pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr, 0, (int *)ctx->rescue_list.p, ctx->d_count + 1);
+      pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, ctx->ctr, 1, (int *)ctx->rescue_list.p, ctx->d_count + 1);
+      CU(cudaEventRecord(e2, st));
+      verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
+      CU(cudaEventRecord(e3, st));
+      pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      CU(cudaEventRecord(e4, st));
+    } else {  // overflow tiers: one CTA per read / pair
+      seed_cta_kernel<<<2 * n_slots, CTA_NT, 0, st>>>(P, ix, B, S, ctx->ctr);
+      CU(cudaEventRecord(e1, st));
+      pair_candidates_cta_kernel<<<n_slots, CTA_NT, 0, st>>>(P, ix, S, ctx->ctr);
+      CU(cudaEventRecord(e2, st));
+      verify_cta_kernel<<<2 * n_slots, CTA_NT, 0, st>>>(P, R, B, S, ctx->ctr);
+      CU(cudaEventRecord(e3, st));
+      pairing_cta_kernel<<<n_slots, CTA_NT, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      CU(cudaEventRecord(e4, st));
+    }
+    launches += 6;
     CU(ensure(tier.ovf_list, (size_t)n_slots * 4));
     CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), st));
     collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, ctx->d_count);
@@ -478,7 +513,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   CU(ensure(ctx->chunk_start, chunks.size() * 4));
   CU(cudaEventRecord(ctx->ev[2], st));
   CU(cudaMemcpyAsync(ctx->chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
-  select_kernel<<<(n_chunks + 31) / 32, 32, 0, st>>>(P, n_chunks, (const int *)ctx->chunk_start.p, (const int *)ctx->nbest.p, (int *)ctx->sel.p);
+  select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)ctx->chunk_start.p, (const int *)ctx->nbest.p, (int *)ctx->sel.p);
   CU(cudaEventRecord(ctx->ev[3], st));
   for (int t = 0; t < tiers_used; ++t) {
     const Scratch S = ctx->tiers[t].view;

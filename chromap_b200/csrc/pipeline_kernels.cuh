@@ -379,65 +379,90 @@ __device__ inline void pe_filter_dir(u32 dist, const u64 *p1, const u8 *c1, int 
 
 // K2: per pair — SupplementCandidates (candidate_processor.cc:75-231), MoveCandidiatesToBuffer +
 // ReduceCandidatesForPairedEndRead (chromap.h:1036-1052, candidate_processor.cc:233-263).
-__global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= S.n_slots) return;
+// Two launches: mode 0 handles every pair that needs no mate-guided rescue (the common case: a few loads
+// and two short sweeps) and appends the others to `list`; mode 1 runs the rescue pairs densely packed, so a
+// warp is no longer held up by its one rescuing pair.
+__global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int mode, int *list, int *list_count) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int slot = tid;
+  if (mode == 1) {
+    if (tid >= *list_count) return;
+    slot = list[tid];
+  } else if (slot >= S.n_slots) return;
   PairMeta &pm = S.pmeta[slot];
   if (pm.status != ST_OK) return;
   const Caps c = S.caps;
   ReadMeta *rm = S.rmeta + 2 * slot;
-  if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
-  int ret = 0;
-  const u32 range = 2u * (u32)P.max_insert;
-  bool ovf = false;
-  for (int mate = 0; mate < 2; ++mate) {
-    ReadMeta &me = rm[mate];
-    const ReadMeta &ot = rm[1 - mate];
-    const u32 n_mm = me.n_mm;
-    bool aug = true;
-    for (int s = 0; s < 2 && aug; ++s) {
-      const u8 *cc = CC(mate, 0, s);
-      for (int i = 0; i < me.n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { aug = false; break; }
-    }
-    if (!aug) continue;
-    const size_t sr = 2 * slot + mate;
-    const u64 *mmv = S.mm_val + sr * c.maxmm;
-    const u32 *mmp = S.mm_pos + sr * c.maxmm;
-    u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
-    int pr = 0, nr = 0;
-    if (ot.n_cand[0] > 0) {
-      int nh;
-      pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
-      if (nh > c.hc) { ovf = true; break; }
-      const int na = cluster_hits(P.e, 1, n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc);
-      if (na > c.cc) { ovf = true; break; }
-      me.n_aug[1] = na;
-    }
-    if (ot.n_cand[1] > 0) {
-      int nh;
-      nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
-      if (nh > c.hc) { ovf = true; break; }
-      const int na = cluster_hits(P.e, 1, n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc);
-      if (na > c.cc) { ovf = true; break; }
-      me.n_aug[0] = na;
-    }
-    if (((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) ret = 1;
-  }
-  if (ovf) { pm.status = ST_OVERFLOW; return; }
-  for (int mate = 0; mate < 2 && !ovf; ++mate)
-    for (int s = 0; s < 2; ++s) {
-      ReadMeta &me = rm[mate];
-      if (me.n_aug[s] > 0) {
-        const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
-                                  CP(mate, 1, s), CC(mate, 1, s), c.cc);
-        if (n > c.cc) { ovf = true; break; }
-        me.n_cand[s] = n;
+  bool aug[2];
+  if (mode == 0) {
+    if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
+    bool need = false;
+    for (int mate = 0; mate < 2; ++mate) {
+      const u32 n_mm = rm[mate].n_mm;
+      bool a = true;
+      for (int s = 0; s < 2 && a; ++s) {
+        const u8 *cc = CC(mate, 0, s);
+        for (int i = 0; i < rm[mate].n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
       }
+      aug[mate] = a;
+      // a rescue lookup only happens when the mate has candidates to guide it (candidate_processor.cc:163-181)
+      if (a && rm[1 - mate].n_cand[0] + rm[1 - mate].n_cand[1] > 0) need = true;
     }
-  if (ovf) { pm.status = ST_OVERFLOW; return; }
-  pm.sup = ret;
+    if (need) { list[atomicAdd(list_count, 1)] = slot; return; }
+    // no rescue: hits are cleared in the reference but nothing reads them afterwards; ret stays 0
+  } else {
+    int ret = 0;
+    const u32 range = 2u * (u32)P.max_insert;
+    bool ovf = false;
+    for (int mate = 0; mate < 2; ++mate) {
+      ReadMeta &me = rm[mate];
+      const ReadMeta &ot = rm[1 - mate];
+      const u32 n_mm = me.n_mm;
+      bool a = true;
+      for (int s = 0; s < 2 && a; ++s) {
+        const u8 *cc = CC(mate, 0, s);
+        for (int i = 0; i < me.n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
+      }
+      if (!a) continue;
+      const size_t sr = 2 * slot + mate;
+      const u64 *mmv = S.mm_val + sr * c.maxmm;
+      const u32 *mmp = S.mm_pos + sr * c.maxmm;
+      u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
+      int pr = 0, nr = 0;
+      if (ot.n_cand[0] > 0) {
+        int nh;
+        pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
+        if (nh > c.hc) { ovf = true; break; }
+        const int na = cluster_hits(P.e, 1, n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc);
+        if (na > c.cc) { ovf = true; break; }
+        me.n_aug[1] = na;
+      }
+      if (ot.n_cand[1] > 0) {
+        int nh;
+        nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
+        if (nh > c.hc) { ovf = true; break; }
+        const int na = cluster_hits(P.e, 1, n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc);
+        if (na > c.cc) { ovf = true; break; }
+        me.n_aug[0] = na;
+      }
+      if (((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) ret = 1;
+    }
+    if (ovf) { pm.status = ST_OVERFLOW; return; }
+    for (int mate = 0; mate < 2 && !ovf; ++mate)
+      for (int s = 0; s < 2; ++s) {
+        ReadMeta &me = rm[mate];
+        if (me.n_aug[s] > 0) {
+          const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
+                                    CP(mate, 1, s), CC(mate, 1, s), c.cc);
+          if (n > c.cc) { ovf = true; break; }
+          me.n_cand[s] = n;
+        }
+      }
+    if (ovf) { pm.status = ST_OVERFLOW; return; }
+    pm.sup = ret;
+  }
   int nc1 = rm[0].n_cand[0] + rm[0].n_cand[1], nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
   if (nc1 > 0 && nc2 > 0) {
     // move candidates to the buffer set (1), filter back into set 0
@@ -705,28 +730,45 @@ __device__ __forceinline__ u32 uniform_0_hi(Mt19937 &g, u32 hi) {
   return (u32)(product >> 32);
 }
 
+// one warp per chunk: all lanes scan 32 pairs at a time and write the identity selection; lane 0 replays the
+// generator for the (rare) pairs with more best pairs than -n, in pair order.
 __global__ void select_kernel(DevParams P, int n_chunks, const int *chunk_start, const int *pair_nbest, int *pair_sel) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (ch >= n_chunks) return;
   Mt19937 g;
   bool seeded = false;
   const int mb = P.max_best;
-  for (int pair = chunk_start[ch]; pair < chunk_start[ch + 1]; ++pair) {
-    const int nb = pair_nbest[pair];
-    int *sel = pair_sel + (size_t)pair * mb;
-    for (int j = 0; j < mb; ++j) sel[j] = j;
-    if (nb > mb) {
-      if (!seeded) { g.seed(11u); seeded = true; }
-      for (int i = mb; i < nb; ++i) {
-        const int j = (int)uniform_0_hi(g, (u32)i);
-        if (j < mb) sel[j] = i;
+  const int p0 = chunk_start[ch], p1 = chunk_start[ch + 1];
+  for (int base = p0; base < p1; base += 32) {
+    const int pair = base + lane;
+    int nb = 0;
+    if (pair < p1) {
+      nb = pair_nbest[pair];
+      int *sel = pair_sel + (size_t)pair * mb;
+      for (int j = 0; j < mb; ++j) sel[j] = j;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, nb > mb);
+    __syncwarp();
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const int nbl = __shfl_sync(0xffffffffu, nb, l);
+      if (lane == 0) {
+        if (!seeded) { g.seed(11u); seeded = true; }
+        int *sel = pair_sel + (size_t)(base + l) * mb;
+        for (int i = mb; i < nbl; ++i) {
+          const int j = (int)uniform_0_hi(g, (u32)i);
+          if (j < mb) sel[j] = i;
+        }
+        for (int a = 1; a < mb; ++a) {  // std::sort of <= CMX_MAX_BEST ints
+          const int v = sel[a];
+          int b = a - 1;
+          while (b >= 0 && sel[b] > v) { sel[b + 1] = sel[b]; --b; }
+          sel[b + 1] = v;
+        }
       }
-      for (int a = 1; a < mb; ++a) {  // std::sort of <= CMX_MAX_BEST ints
-        const int v = sel[a];
-        int b = a - 1;
-        while (b >= 0 && sel[b] > v) { sel[b + 1] = sel[b]; --b; }
-        sel[b + 1] = v;
-      }
+      __syncwarp();
     }
   }
 }
@@ -943,4 +985,550 @@ __global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= S.n_slots) return;
   if (S.pmeta[slot].status == ST_OVERFLOW) list[atomicAdd(count, 1)] = slot_pair(S, slot);
+}
+
+// =================================================================================================
+// CTA-cooperative kernels for the overflow tiers (one CTA per read / per pair).  Same scratch layout and
+// the same results as the general kernels; the expensive primitives — table probes, hit expansion,
+// sorting, banded verification — are spread over the CTA's threads, the order-dependent scans stay on
+// thread 0 and read their input through shared memory.
+#define CTA_NT 256
+#define CTA_SORT_SMEM 4096  // u64 entries staged in shared memory (32 KB)
+#define CTA_MM_SMEM 1024    // max minimizers per read handled by the CTA kernels
+
+// ascending bitonic sort of n keys; pads a[n..np2) with ~0 (capacity must be a power of two >= n).
+__device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const int tid = threadIdx.x;
+  if (n <= 1) { __syncthreads(); return; }
+  u64 *w = a;
+  const bool in_smem = np2 <= CTA_SORT_SMEM;
+  if (in_smem) {
+    for (int i = tid; i < np2; i += CTA_NT) sm[i] = i < n ? a[i] : ~0ull;
+    w = sm;
+  } else {
+    for (int i = n + tid; i < np2; i += CTA_NT) a[i] = ~0ull;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+        const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+        const u64 x = w[i], y = w[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { w[i] = y; w[l] = x; }
+      }
+      __syncthreads();
+    }
+  if (in_smem) {
+    for (int i = tid; i < n; i += CTA_NT) a[i] = sm[i];
+    __syncthreads();
+  }
+}
+
+// same for (key, tag) pairs under `less`; pads with (pad_key, pad_tag) which must compare greatest.
+template <typename T, typename Less>
+__device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_tag, Less less, u64 *smk, T *smt) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const int tid = threadIdx.x;
+  if (n <= 1) { __syncthreads(); return; }
+  u64 *wk = k_;
+  T *wt = t_;
+  const bool in_smem = np2 <= CTA_SORT_SMEM;
+  if (in_smem) {
+    for (int i = tid; i < np2; i += CTA_NT) { smk[i] = i < n ? k_[i] : pad_key; smt[i] = i < n ? t_[i] : pad_tag; }
+    wk = smk; wt = smt;
+  } else {
+    for (int i = n + tid; i < np2; i += CTA_NT) { k_[i] = pad_key; t_[i] = pad_tag; }
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+        const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+        const u64 xk = wk[i], yk = wk[l];
+        const T xt = wt[i], yt = wt[l];
+        const bool up = (i & k) == 0;
+        const bool sw = up ? less(yk, yt, xk, xt) : less(xk, xt, yk, yt);
+        if (sw) { wk[i] = yk; wt[i] = yt; wk[l] = xk; wt[l] = xt; }
+      }
+      __syncthreads();
+    }
+  if (in_smem) {
+    for (int i = tid; i < n; i += CTA_NT) { k_[i] = smk[i]; t_[i] = smt[i]; }
+    __syncthreads();
+  }
+}
+
+// candidate_processor.cc:283-342 with the sorted hits streamed through shared memory; thread 0 scans.
+// Returns the candidate count on every thread.
+__device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int *s_ret) {
+  const int tid = threadIdx.x;
+  int n = 0, mcount = 1, eq = 1, best_eq = 1;
+  u64 prev = 0, best = 0;
+  u32 prev_rid = 0, prev_pos = 0;
+  for (int base = 0; base < nh; base += CTA_SORT_SMEM) {
+    const int m = min(CTA_SORT_SMEM, nh - base);
+    for (int i = tid; i < m; i += CTA_NT) sm[i] = hits[base + i];
+    __syncthreads();
+    if (tid == 0) {
+      int i0 = 0;
+      if (base == 0) { prev = sm[0]; best = prev; prev_rid = (u32)(prev >> 32); prev_pos = (u32)prev; i0 = 1; }
+      for (int i = i0; i <= m; ++i) {
+        if (i == m && base + m < nh) break;  // more chunks follow
+        const u64 h = i < m ? sm[i] : ~0ull;  // final sentinel
+        const u32 rid = (u32)(h >> 32), pos = (u32)h;
+        if (rid != prev_rid || pos > prev_pos + (u32)e || ((u32)mcount >= n_mm && pos > (u32)best + (u32)e)) {
+          if (mcount >= need) { if (n < cap) { cpos[n] = best; ccnt[n] = (u8)best_eq; } ++n; }
+          mcount = 1; eq = 1; best_eq = 1; best = h;
+        } else {
+          if (h == best) { ++eq; ++best_eq; }
+          else if (h == prev) { ++eq; if (eq > best_eq) { best = prev; best_eq = eq; } }
+          else eq = 1;
+          ++mcount;
+        }
+        prev = h; prev_rid = rid; prev_pos = pos;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *s_ret = n;
+  __syncthreads();
+  const int r = *s_ret;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr) {
+  __shared__ u64 sm[CTA_SORT_SMEM];
+  __shared__ u32 s_c1[CTA_MM_SMEM], s_c2[CTA_MM_SMEM];
+  __shared__ int s_off[CTA_MM_SMEM + 1];
+  __shared__ int s_i[8];
+  __shared__ unsigned long long s_steps;
+  const int sr = blockIdx.x, tid = threadIdx.x;
+  const int slot = sr >> 1, mate = sr & 1;
+  // the mate's CTA may flag the pair concurrently: read the status once, uniformly
+  if (tid == 0) s_i[7] = S.pmeta[slot].status;
+  __syncthreads();
+  if (s_i[7] != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
+  u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
+  u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
+  if (tid == 0) {
+    const int n_mm = gen_minimizers_thread(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm);
+    rm.n_mm = n_mm;
+    s_i[0] = n_mm;
+    s_steps = 0;
+    s_i[5] = 0;  // found
+  }
+  __syncthreads();
+  const int n_mm = s_i[0];
+  if (n_mm > c.maxmm || n_mm > CTA_MM_SMEM) { if (tid == 0) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW); return; }
+  if (n_mm == 0) return;
+  for (int i = tid; i < n_mm; i += CTA_NT) {
+    u64 val = 0;
+    int steps;
+    const int kind = index_lookup(ix, mmh[i], &val, &steps);
+    mmv[i] = val;
+    mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
+    u32 c1 = 0, c2 = 0;
+    if (kind == 1) { c1 = c2 = 1; }
+    else if (kind == 2) { const u32 n = (u32)val; if (n < (u32)P.f0) c1 = n; if (n < (u32)P.f1) c2 = n; }
+    s_c1[i] = c1; s_c2[i] = c2;
+    atomicAdd(&s_steps, (unsigned long long)steps);
+    if (kind) atomicAdd(&s_i[5], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long cnt1 = 0;
+    for (int i = 0; i < n_mm; ++i) cnt1 += s_c1[i];
+    const bool round2 = cnt1 == 0;
+    long long tot = 0;
+    RepStats st = {0u, 0xFFFFFFFFu, 0};
+    for (int i = 0; i < n_mm; ++i) {
+      s_off[i] = (int)tot;
+      tot += round2 ? s_c2[i] : s_c1[i];
+      if ((mmp[i] >> 30) == 2 && (u32)mmv[i] >= (u32)P.f0) rep_update(P.k, P.w, (mmp[i] & 0x3FFFFFFFu) >> 1, st);
+      if (tot > 2ll * c.hc) break;
+    }
+    s_off[n_mm] = (int)(tot > 2ll * c.hc ? 2ll * c.hc + 1 : tot);
+    s_i[1] = round2;
+    s_i[2] = st.count;
+    rm.rep_len = st.len;
+    atomicAdd(&ctr->n_minimizers, (u64)n_mm);
+    atomicAdd(&ctr->n_probe_steps, (u64)s_steps);
+    atomicAdd(&ctr->n_found, (u64)s_i[5]);
+  }
+  __syncthreads();
+  const int T = s_off[n_mm];
+  if (T > 2 * c.hc) { if (tid == 0) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW); return; }
+  u64 *hits = S.hits + (size_t)sr * 2 * c.hc;  // [2][hc] contiguous: positives first, negatives right behind them
+  for (int j = tid; j < T; j += CTA_NT) {
+    int lo = 0, hi = n_mm;  // last i with s_off[i] <= j
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= j) lo = mid; else hi = mid; }
+    // skip empty minimizers sharing the same offset
+    const int i = lo;
+    const u32 rpos = (mmp[i] & 0x3FFFFFFFu) >> 1, rstrand = mmp[i] & 1u;
+    const u64 val = mmv[i];
+    const u64 rh = (mmp[i] >> 30) == 1 ? val : __ldg(&ix.occ[(u32)(val >> 32) + (u32)(j - s_off[i])]);
+    bool same;
+    const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
+    hits[j] = cp | (same ? 0ull : (1ull << 63));
+  }
+  if (tid == 0) { u64 occ_reads = 0; for (int i = 0; i < n_mm; ++i) if ((mmp[i] >> 30) == 2) occ_reads += s_off[i + 1] - s_off[i]; atomicAdd(&ctr->n_occ_reads, occ_reads); }
+  __syncthreads();
+  cta_sort_keys(hits, T, sm);
+  if (tid == 0) {
+    int lo = 0, hi = T;  // first index with the strand tag set
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid] >> 63) hi = mid; else lo = mid + 1; }
+    s_i[3] = lo;
+  }
+  __syncthreads();
+  const int np = s_i[3], nn = T - np;
+  for (int j = np + tid; j < T; j += CTA_NT) hits[j] &= ~(1ull << 63);
+  __syncthreads();
+  int need = n_mm - s_i[2];
+  need = need > 1 ? need : 1;
+  need = need > P.min_seeds ? P.min_seeds : need;
+  if (s_i[1] && np > 0 && nn > 0) need = P.min_seeds;
+  u64 *cp0 = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cp1 = cp0 + c.cc;
+  u8 *cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cc1 = cc0 + c.cc;
+  const int nc0 = cta_cluster(P.e, need, (u32)n_mm, hits, np, cp0, cc0, c.cc, sm, &s_i[4]);
+  const int nc1 = cta_cluster(P.e, need, (u32)n_mm, hits + np, nn, cp1, cc1, c.cc, sm, &s_i[4]);
+  if (tid == 0) {
+    if (nc0 > c.cc || nc1 > c.cc) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW);
+    else {
+      rm.n_hits[0] = np; rm.n_hits[1] = nn;
+      rm.n_cand[0] = nc0; rm.n_cand[1] = nc1; rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
+    }
+  }
+}
+
+// index.cc:351-489 cooperatively: thread 0 builds the merged windows, threads take minimizers (the binary
+// search state `prev_l` chains the windows of one minimizer, so windows stay sequential per minimizer),
+// hits are appended with a shared counter (order is irrelevant: they are sorted next).
+__device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv, const u32 *mmp,
+                                 const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm,
+                                 u64 *win_lo, u64 *win_hi, int *s_i, int *nh_out) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int max_cnt = 0, n_best = 0;
+    for (int i = 0; i < n_mate; ++i) {
+      const int cnt = mate_cnt[i];
+      if (cnt > max_cnt) { max_cnt = cnt; n_best = 1; }
+      else if (cnt == max_cnt) ++n_best;
+    }
+    s_i[0] = max_cnt;
+    s_i[1] = (n_best >= 300 || n_mate > P.f0 || (max_cnt <= P.min_seeds && n_best >= 200)) ? 1 : 0;
+    int nw = 0;
+    if (!s_i[1]) {
+      for (int i = 0; i < n_mate; ++i) {
+        if (mate_cnt[i] != max_cnt) continue;
+        const u64 lo = mate_pos[i] < range ? 0 : mate_pos[i] - range, hi = mate_pos[i] + range;
+        if (nw > 0 && !(win_hi[nw - 1] < lo)) win_hi[nw - 1] = hi;
+        else { win_lo[nw] = lo; win_hi[nw] = hi; ++nw; }
+      }
+    }
+    s_i[2] = nw;
+    s_i[3] = 0;  // hit counter
+  }
+  __syncthreads();
+  const int max_cnt = s_i[0];
+  *nh_out = 0;
+  if (s_i[1]) { __syncthreads(); return -max_cnt; }
+  const int nw = s_i[2];
+  for (int mi = tid; mi < n_mm; mi += CTA_NT) {
+    const u32 kind = mmp[mi] >> 30;
+    if (kind == 0) continue;
+    const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
+    const u64 val = mmv[mi];
+    bool same;
+    if (kind == 1) {
+      const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
+      if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
+      continue;
+    }
+    const u32 off = (u32)(val >> 32), n = (u32)val;
+    int prev_l = 0;
+    for (int bi = 0; bi < nw; ++bi) {
+      const u64 lo = win_lo[bi], hi = win_hi[bi];
+      int l = prev_l, mid = 0, r = (int)n - 1;
+      while (l <= r) {
+        mid = (l + r) / 2;
+        const u64 p = __ldg(&ix.occ[off + mid]) >> 1;
+        if (p < lo) l = mid + 1;
+        else if (p > lo) r = mid - 1;
+        else break;
+      }
+      prev_l = mid;
+      for (u32 oi = (u32)mid; oi < n; ++oi) {
+        const u64 rh = __ldg(&ix.occ[off + oi]);
+        if ((rh >> 1) > hi) break;
+        const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
+        if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
+      }
+    }
+  }
+  __syncthreads();
+  const int nh = s_i[3];
+  *nh_out = nh;
+  if (tid == 0) {
+    RepStats st = {0u, 0xFFFFFFFFu, 0};
+    for (int mi = 0; mi < n_mm; ++mi)
+      if ((mmp[mi] >> 30) == 2 && (u32)mmv[mi] >= (u32)P.f0) rep_update(P.k, P.w, (mmp[mi] & 0x3FFFFFFFu) >> 1, st);
+    *rep_len = st.len;
+  }
+  __syncthreads();
+  if (nh <= cap) cta_sort_keys(hits, nh, sm);
+  return max_cnt;
+}
+
+__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
+  __shared__ u64 sm[CTA_SORT_SMEM];
+  __shared__ u64 win_lo[300], win_hi[300];
+  __shared__ int s_i[8];
+  __shared__ int s_flag[4];
+  const int slot = blockIdx.x, tid = threadIdx.x;
+  PairMeta &pm = S.pmeta[slot];
+  if (pm.status != ST_OK) return;
+  const Caps c = S.caps;
+  ReadMeta *rm = S.rmeta + 2 * slot;
+  auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
+  auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
+  if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { __syncthreads(); if (tid == 0) pm.status = ST_DROP; return; }
+  if (tid == 0) {
+    for (int mate = 0; mate < 2; ++mate) {
+      const u32 n_mm = rm[mate].n_mm;
+      bool a = true;
+      for (int s = 0; s < 2 && a; ++s) {
+        const u8 *cc = CC(mate, 0, s);
+        for (int i = 0; i < rm[mate].n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
+      }
+      s_flag[mate] = a;
+    }
+    s_flag[2] = 0;  // ret
+    s_flag[3] = 0;  // overflow
+  }
+  __syncthreads();
+  const u32 range = 2u * (u32)P.max_insert;
+  for (int mate = 0; mate < 2; ++mate) {
+    if (!s_flag[mate]) continue;
+    ReadMeta &me = rm[mate];
+    const ReadMeta &ot = rm[1 - mate];
+    const int n_mm = me.n_mm;
+    const size_t sr = 2 * slot + mate;
+    const u64 *mmv = S.mm_val + sr * c.maxmm;
+    const u32 *mmp = S.mm_pos + sr * c.maxmm;
+    u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
+    int pr = 0, nr = 0;
+    bool ovf = false;
+    if (ot.n_cand[0] > 0) {
+      int nh;
+      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, win_lo, win_hi, s_i, &nh);
+      if (nh > c.hc) ovf = true;
+      else {
+        const int na = cta_cluster(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, &s_i[4]);
+        if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[1] = na;
+      }
+    }
+    if (!ovf && ot.n_cand[1] > 0) {
+      int nh;
+      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, win_lo, win_hi, s_i, &nh);
+      if (nh > c.hc) ovf = true;
+      else {
+        const int na = cta_cluster(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, &s_i[4]);
+        if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[0] = na;
+      }
+    }
+    if (ovf) { __syncthreads(); if (tid == 0) pm.status = ST_OVERFLOW; return; }  // uniform: every thread computed the same ovf
+    if (tid == 0 && ((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) s_flag[2] = 1;
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  // merges + PE filter: linear passes, thread 0
+  for (int mate = 0; mate < 2; ++mate)
+    for (int s = 0; s < 2; ++s) {
+      ReadMeta &me = rm[mate];
+      if (me.n_aug[s] > 0) {
+        const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
+                                  CP(mate, 1, s), CC(mate, 1, s), c.cc);
+        if (n > c.cc) { pm.status = ST_OVERFLOW; return; }
+        me.n_cand[s] = n;
+      }
+    }
+  pm.sup = s_flag[2];
+  int nc1 = rm[0].n_cand[0] + rm[0].n_cand[1], nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+  if (nc1 > 0 && nc2 > 0) {
+    for (int mate = 0; mate < 2; ++mate)
+      for (int s = 0; s < 2; ++s) {
+        const int n = rm[mate].n_cand[s];
+        u64 *src = CP(mate, 0, s), *dst = CP(mate, 1, s);
+        u8 *srcc = CC(mate, 0, s), *dstc = CC(mate, 1, s);
+        for (int i = 0; i < n; ++i) { dst[i] = src[i]; dstc[i] = srcc[i]; }
+        rm[mate].n_buf[s] = n;
+      }
+    int a, b;
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), rm[0].n_buf[0], CP(1, 1, 1), CC(1, 1, 1), rm[1].n_buf[1],
+                  CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
+    rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), rm[0].n_buf[1], CP(1, 1, 0), CC(1, 1, 0), rm[1].n_buf[0],
+                  CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
+    rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
+    nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
+    nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+  }
+  if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
+  atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
+}
+
+// GenerateDraftMappings for one read by one CTA: candidates sorted cooperatively, every valid candidate is
+// verified by its own thread (lane-per-candidate Myers), thread 0 then replays the reference's order-
+// dependent group / threshold rule over the stored results (verifying a candidate the reference would
+// have skipped is wasted work, never a different result).
+__global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr) {
+  __shared__ u64 smk[CTA_SORT_SMEM];
+  __shared__ u8 smt[CTA_SORT_SMEM];
+  __shared__ int s_done, s_status;
+  const int sr = blockIdx.x, tid = threadIdx.x;
+  const int slot = sr >> 1, mate = sr & 1;
+  if (tid == 0) s_status = S.pmeta[slot].status;  // the mate's CTA may flag the pair concurrently
+  __syncthreads();
+  if (s_status != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  const u8 *read = read_ptr(B, pair, mate);
+  const int L = rm.len, e = P.e;
+  u64 *mp[2] = {S.map_pos + ((size_t)sr * 2 + 0) * c.mc, S.map_pos + ((size_t)sr * 2 + 1) * c.mc};
+  signed char *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
+  u64 *cp[2] = {S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
+  u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
+  // per-candidate results live in the (now free) augment set: err in the count array, end position in the pos array
+  u64 *rend[2] = {S.cand_pos + (((size_t)sr * 3 + 2) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 2) * 2 + 1) * c.cc};
+  u8 *rerr[2] = {S.cand_cnt + (((size_t)sr * 3 + 2) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 2) * 2 + 1) * c.cc};
+  const int nc[2] = {rm.n_cand[0], rm.n_cand[1]};
+  if (tid == 0) {
+    s_done = 0;
+    Tally t = {e + 1, e + 1, 0, 0};
+    if (nc[0] + nc[1] == 1) {
+      int n_all = 0, idx = 0, strand = 0;
+      for (int i = 0; i < nc[0]; ++i) if (cc[0][i] == rm.n_mm) { idx = i; ++n_all; }
+      for (int i = 0; i < nc[1]; ++i) if (cc[1][i] == rm.n_mm) { idx = i; strand = 1; ++n_all; }
+      if (n_all == 1) {
+        t.min_err = 0; t.n_best = 1; t.n_second_best = 0;
+        const u64 cpos = cp[strand][idx];
+        const u32 rid = (u32)(cpos >> 32);
+        const u32 pos = strand == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+        if (valid_cand(e, R.len[rid], pos, (u32)L)) {
+          mp[strand][0] = strand == 0 ? cpos + (u64)L - 1 : cpos;
+          me[strand][0] = 0;
+          rm.n_map[strand] = 1; rm.n_map[1 - strand] = 0;
+          s_done = 1;
+        }
+      }
+    }
+    rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
+  }
+  __syncthreads();
+  if (s_done) return;
+  auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
+  cta_sort_pairs<u8>(cp[0], cc[0], nc[0], ~0ull, (u8)0, cless, smk, smt);
+  cta_sort_pairs<u8>(cp[1], cc[1], nc[1], ~0ull, (u8)0, cless, smk, smt);
+  u64 n_ver = 0;
+  for (int s = 0; s < 2; ++s)
+    for (int i = tid; i < nc[s]; i += CTA_NT) {
+      const u64 cpos = cp[s][i];
+      const u32 rid = (u32)(cpos >> 32);
+      const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+      if (!valid_cand(e, R.len[rid], pos, (u32)L)) { rerr[s][i] = 255; continue; }
+      const u8 *win = R.seq + R.off[rid] + pos - e;
+      int endp = 0, err;
+      if (s == 0) err = banded_align(e, L, [&](int q) { return base_code(__ldg(win + q)); }, [&](int q) { return base_code(read[q]); }, &endp);
+      else err = banded_align(e, L, [&](int q) { return base_code(__ldg(win + q)); }, [&](int q) { return neg_code(read, L, q); }, &endp);
+      rerr[s][i] = (u8)err;
+      rend[s][i] = (u64)endp;
+      ++n_ver;
+    }
+  if (n_ver) atomicAdd(&ctr->n_verified, n_ver);
+  __syncthreads();
+  if (tid != 0) return;
+  Tally t = {rm.min_err, rm.second_min_err, rm.n_best, rm.n_second_best};
+  int nm[2] = {0, 0};
+  for (int s = 0; s < 2; ++s) {
+    auto take = [&](int i) -> bool {  // true if candidate i failed
+      const int err = rerr[s][i];
+      if (err > e) return true;
+      tally(t, err);
+      const u64 cpos = cp[s][i];
+      if (nm[s] < c.mc) {
+        mp[s][nm[s]] = s == 0 ? cpos - (u64)e + rend[s][i] : cpos - (u64)L + 1 - (u64)e + rend[s][i];
+        me[s][nm[s]] = (signed char)err;
+      }
+      ++nm[s];
+      return false;
+    };
+    if (nc[s] < P.lanes) {
+      for (int i = 0; i < nc[s]; ++i) if (rerr[s][i] != 255) take(i);
+      continue;
+    }
+    int group[8];
+    int ng = 0;
+    u32 threshold = 0;
+    int ci = 0;
+    while (ci < nc[s]) {
+      if (cc[s][ci] < threshold) break;
+      if (rerr[s][ci] == 255) { ++ci; continue; }
+      group[ng++] = ci; ++ci;
+      if (ng < P.lanes) continue;
+      for (int g = 0; g < ng; ++g) if (take(group[g])) threshold = cc[s][group[g]];
+      ng = 0;
+    }
+    for (int g = 0; g < ng; ++g) take(group[g]);
+  }
+  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
+  rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
+}
+
+// pairing for one pair by one CTA: the four mapping lists are sorted cooperatively, thread 0 sweeps.
+__global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratch S, int *pair_nbest) {
+  __shared__ u64 smk[CTA_SORT_SMEM];
+  __shared__ signed char smt[CTA_SORT_SMEM];
+  const int slot = blockIdx.x, tid = threadIdx.x;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status != ST_OK) { if (tid == 0 && pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
+  const Caps c = S.caps;
+  ReadMeta *rm = S.rmeta + 2 * slot;
+  if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) {
+    __syncthreads();
+    if (tid == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
+    return;
+  }
+  auto mless = [](u64 pa, signed char ea, u64 pb, signed char eb) { return pa != pb ? pa < pb : ea < eb; };
+  u64 *mp[2][2];
+  signed char *me[2][2];
+  for (int m = 0; m < 2; ++m)
+    for (int s = 0; s < 2; ++s) {
+      mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
+      me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
+      cta_sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (signed char)127, mless, smk, smt);
+    }
+  if (tid != 0) return;
+  int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;
+  auto visit = [&](int, int, int sum) {
+    if (sum < min_sum) { second = min_sum; n_second = n_best; min_sum = sum; n_best = 1; }
+    else if (sum == min_sum) n_best++;
+    else if (sum == second) n_second++;
+    else if (sum < second) { second = sum; n_second = 1; }
+  };
+  pair_sweep(P, 0, (u32)rm[0].len, (u32)rm[1].len, mp[0][0], me[0][0], rm[0].n_map[0], mp[1][1], me[1][1], rm[1].n_map[1], visit);
+  pair_sweep(P, 1, (u32)rm[0].len, (u32)rm[1].len, mp[0][1], me[0][1], rm[0].n_map[1], mp[1][0], me[1][0], rm[1].n_map[0], visit);
+  pm.min_sum = min_sum; pm.second_min_sum = second; pm.n_best = n_best; pm.n_second_best = n_second;
+  pair_nbest[pair] = (n_best > P.drop_rep) ? 0 : n_best;
 }

@@ -977,6 +977,21 @@ orc_index *orc_index_build(const orc_reference *ref, int k, int w) {  // index.c
   }
   return ix;
 }
+orc_index *orc_index_from_arrays(int k, int w, uint32_t n_buckets, const uint32_t *flags, const uint64_t *keys,
+                                  const uint64_t *vals, const uint64_t *occ, uint32_t n_occ) {
+  orc_index *ix = new orc_index;
+  ix->k = k; ix->w = w; ix->n_buckets = n_buckets;
+  const size_t nf = n_buckets < 16 ? 1 : n_buckets >> 4;
+  ix->flags.assign(flags, flags + nf);
+  ix->keys.assign(keys, keys + n_buckets);
+  ix->vals.assign(vals, vals + n_buckets);
+  ix->occ.assign(occ, occ + n_occ);
+  u32 sz = 0;
+  for (u32 i = 0; i < n_buckets; ++i) if (((ix->flags[i >> 4] >> ((i & 0xfU) << 1)) & 3) == 0) ++sz;
+  ix->size = ix->n_occupied = sz;
+  ix->upper_bound = (u32)(n_buckets * 0.77 + 0.5);
+  return ix;
+}
 void orc_index_free(orc_index *ix) { delete ix; }
 int orc_index_k(const orc_index *ix) { return ix->k; }
 int orc_index_w(const orc_index *ix) { return ix->w; }

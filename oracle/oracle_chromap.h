@@ -51,6 +51,9 @@ typedef struct orc_reference orc_reference;
 orc_index *orc_index_load(const char *path);
 orc_index *orc_index_build(const orc_reference *ref, int k, int w);
 int orc_index_save(const orc_index *idx, const char *path);
+// From khash arrays in memory (copied), e.g. the arrays cmx_download_index() returns.
+orc_index *orc_index_from_arrays(int k, int w, uint32_t n_buckets, const uint32_t *flags, const uint64_t *keys,
+                                  const uint64_t *vals, const uint64_t *occ, uint32_t n_occ);
 void orc_index_free(orc_index *idx);
 int orc_index_k(const orc_index *idx);
 int orc_index_w(const orc_index *idx);

@@ -53,6 +53,7 @@ def lib():
         L.orc_index_load.restype = vp; L.orc_index_load.argtypes = [C.c_char_p]
         L.orc_index_build.restype = vp; L.orc_index_build.argtypes = [vp, i32, i32]
         L.orc_index_save.argtypes = [vp, C.c_char_p]
+        L.orc_index_from_arrays.restype = vp; L.orc_index_from_arrays.argtypes = [i32, i32, u32, vp, vp, vp, vp, u32]
         L.orc_index_free.argtypes = [vp]
         L.orc_index_k.argtypes = [vp]; L.orc_index_w.argtypes = [vp]
         L.orc_index_arrays.restype = u32
@@ -112,9 +113,16 @@ class Reference:
 
 
 class Index:
-    def __init__(self, path=None, ref=None, k=17, w=7):
+    def __init__(self, path=None, ref=None, k=17, w=7, arrays=None):
         L = lib()
-        self.h = L.orc_index_load(path.encode()) if path else L.orc_index_build(ref.h, k, w)
+        if arrays is not None:
+            a = arrays
+            fl = np.ascontiguousarray(a["flags"], dtype=np.uint32); ke = np.ascontiguousarray(a["keys"], dtype=np.uint64)
+            va = np.ascontiguousarray(a["vals"], dtype=np.uint64); oc = np.ascontiguousarray(a["occ"], dtype=np.uint64)
+            self.h = L.orc_index_from_arrays(k, w, a["n_buckets"], fl.ctypes.data, ke.ctypes.data, va.ctypes.data,
+                                             oc.ctypes.data if len(oc) else None, len(oc))
+        else:
+            self.h = L.orc_index_load(path.encode()) if path else L.orc_index_build(ref.h, k, w)
         if not self.h:
             raise IOError("cannot load index")
         self.k, self.w = L.orc_index_k(self.h), L.orc_index_w(self.h)
