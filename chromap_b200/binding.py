@@ -39,10 +39,12 @@ class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms",
                                          "select_ms", "emit_ms", "d2h_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("n_minimizers", "n_probe_steps", "n_found", "n_occ_reads", "n_verified",
-                                          "n_launches")]
+                                          "n_launches")] + [("tier_pairs", C.c_uint64 * 3), ("escalations", C.c_uint64 * 8)]
 
     def asdict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["tier_pairs"] = list(d["tier_pairs"]); d["escalations"] = list(d["escalations"])
+        return d
 
 
 PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u4"), ("fragment_length", "<u2"),

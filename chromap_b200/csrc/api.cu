@@ -468,14 +468,16 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
       CU(cudaEventRecord(e3, st));
       pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
       CU(cudaEventRecord(e4, st));
-    } else {  // overflow tiers: one CTA per read / pair
-      seed_cta_kernel<<<2 * n_slots, CTA_NT, 0, st>>>(P, ix, B, S, ctx->ctr);
+    } else {  // overflow tiers: one CTA per read / pair; shared-memory sort buffers sized to the tier
+      auto cap_of = [](int n) { int c = 1; while (c < n) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
+      const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
+      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 8 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, ctx->ctr, c_seed);
       CU(cudaEventRecord(e1, st));
-      pair_candidates_cta_kernel<<<n_slots, CTA_NT, 0, st>>>(P, ix, S, ctx->ctr);
+      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 8, st>>>(P, ix, S, ctx->ctr, c_pc);
       CU(cudaEventRecord(e2, st));
-      verify_cta_kernel<<<2 * n_slots, CTA_NT, 0, st>>>(P, R, B, S, ctx->ctr);
+      verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
       CU(cudaEventRecord(e3, st));
-      pairing_cta_kernel<<<n_slots, CTA_NT, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 9, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
       CU(cudaEventRecord(e4, st));
     }
     launches += 6;
@@ -554,6 +556,8 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   cudaEventElapsedTime(&tm.total_ms, ctx->ev[0], ctx->ev[5]);
   tm.n_minimizers = hc.n_minimizers; tm.n_probe_steps = hc.n_probe_steps; tm.n_found = hc.n_found; tm.n_occ_reads = hc.n_occ_reads;
   tm.n_verified = hc.n_verified; tm.n_launches = launches;
+  for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = t < tiers_used ? (u64)ctx->tiers[t].n_slots : 0;
+  for (int r = 0; r < 8; ++r) tm.escalations[r] = hc.ovf_reason[r];
   ctx->last_n_pairs = n; ctx->last_tiers_used = tiers_used;
   if (n_overflow_final) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)n_overflow_final);
   return CMX_OK;
@@ -608,7 +612,7 @@ __global__ void stage_minimizers_kernel(DevBatch B, int k, int w, u64 *out_hash,
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= 2 * (int)B.n_pairs) return;
   const int pair = r >> 1, mate = r & 1;
-  out_n[r] = gen_minimizers_thread(read_ptr(B, pair, mate), read_raw_len(B, pair, mate), k, w, out_hash + (size_t)r * stride, out_pos + (size_t)r * stride, (int)stride);
+  out_n[r] = gen_minimizers_any(read_ptr(B, pair, mate), read_raw_len(B, pair, mate), k, w, out_hash + (size_t)r * stride, out_pos + (size_t)r * stride, (int)stride);
 }
 
 int cmx_stage_minimizers(cmx_ctx *ctx, const cmx_batch *in, uint64_t *out_hash, uint32_t *out_pos, int32_t *out_n, uint32_t stride) {

@@ -93,15 +93,16 @@ struct Scratch {
 
 __device__ __forceinline__ int slot_pair(const Scratch &S, int slot) { return S.pair_list ? S.pair_list[slot] : slot; }
 
-// utils.h:87-104
+// utils.h:87-104: A/a=0 C/c=1 G/g=2 T/t=3, everything else 4.  Branch-free on purpose: a chain of ternaries
+// makes the compiler duplicate the caller's loop body per base and the warp then runs 4-way divergent.
 __device__ __forceinline__ u32 base_code(u8 c) {
-  // A/a=0 C/c=1 G/g=2 T/t=3 else 4
-  u32 u = c & 0xDF;  // fold case
-  return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+  const u32 u = (u32)c & 0xDFu;              // fold case: only {0x41,0x61}->'A', {0x43,0x63}->'C', {0x47,0x67}->'G', {0x54,0x74}->'T'
+  const u32 x = (u >> 1) & 3u;               // A:0 C:1 G:3 T:2
+  const u32 code = x ^ (x >> 1);             // A:0 C:1 G:2 T:3
+  const u32 in_row = ((u & 0xE0u) == 0x40u) ? 1u : 0u;                      // 0x40..0x5F
+  const u32 is_base = in_row & ((0x0010008Au >> (u & 31u)) & 1u);           // bits 1 (A), 3 (C), 7 (G), 20 (T)
+  return is_base ? code : 4u;
 }
-// careful: (c & 0xDF) folds e.g. 0x01 -> 0x01, 'a'(0x61)->'A'.  Bytes like 0xE1 fold to 0xC1 (not a base),
-// '!'(0x21)->0x01: no false positives because only exact 'A','C','G','T' after folding match, and the
-// pre-images of those under &0xDF are {0x41,0x61}, {0x43,0x63}, {0x47,0x67}, {0x54,0x74} only.
 
 // utils.h:76-85
 __device__ __forceinline__ u64 mix64(u64 key, u64 mask) {

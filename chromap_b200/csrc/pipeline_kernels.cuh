@@ -12,6 +12,7 @@ struct MapqTables {
 
 struct Counters {  // device-side statistics (atomics)
   u64 n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_candidates, n_mapped, n_unique, n_overflow;
+  u64 ovf_reason[8];  // tier-0 escalations by cause: 0 read length, 1 #minimizers, 2 seed hits, 3 seed candidates, 4 rescue hits, 5 rescue/merge candidates, 6 draft mappings
 };
 
 __device__ __forceinline__ const u8 *read_ptr(const DevBatch &B, int pair, int mate) {
@@ -135,6 +136,70 @@ __device__ inline int gen_minimizers_thread(const u8 *seq, int len, int k, int w
   return n;
 }
 
+// Same algorithm with the w-entry ring held in registers as a shift register (index 0 = oldest, W-1 = newest)
+// so that every scan has static indices; `best_age` = insertions since the current minimum was inserted
+// (the reference's `position_in_buffer == min_position` test is `best_age == W`).  Used when w == W.
+template <int W>
+__device__ __forceinline__ int gen_minimizers_regs(const u8 *seq, int len, int k, u64 *out_hash, u32 *out_pos, int cap) {
+  const u64 shift = 2 * (k - 1);
+  const u64 mask = (((u64)1) << (2 * k)) - 1;
+  u64 fwd = 0, rev = 0;
+  u64 rh[W];
+  u32 rp[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) { rh[i] = ~0ull; rp[i] = ~0u; }
+  u64 best_h = ~0ull;
+  u32 best_p = ~0u;
+  int run = 0, best_age = 0, n = 0;
+#define EMIT(h, p) do { if (n < cap) { out_hash[n] = (h); out_pos[n] = (p); } ++n; } while (0)
+  for (int pos = 0; pos < len; ++pos) {
+    const u32 b = base_code(seq[pos]);
+    u64 cur_h = ~0ull;
+    u32 cur_p = ~0u;
+    if (b < 4) {
+      fwd = ((fwd << 2) | b) & mask;
+      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
+      if (fwd == rev) continue;
+      const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
+      const u32 strand = hf < hr ? 0u : 1u;
+      ++run;
+      if (run >= k) { cur_h = mix64(strand ? hr : hf, mask); cur_p = ((u32)pos << 1) | strand; }
+    } else {
+      run = 0;
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < W; ++j) { rh[j] = rh[j + 1]; rp[j] = rp[j + 1]; }
+    rh[W - 1] = cur_h; rp[W - 1] = cur_p;
+    ++best_age;
+    if (run == W + k - 1 && best_h != ~0ull && best_h < cur_h) {
+#pragma unroll
+      for (int j = 0; j + 1 < W; ++j) if (best_h == rh[j] && rp[j] != best_p) EMIT(rh[j], rp[j]);
+    }
+    if (cur_h <= best_h) {
+      if (run >= W + k && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = cur_h; best_p = cur_p; best_age = 0;
+    } else if (best_age == W) {
+      if (run >= W + k - 1 && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = ~0ull;
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (best_h >= rh[j]) { best_h = rh[j]; best_p = rp[j]; best_age = W - 1 - j; }
+      if (run >= W + k - 1 && best_h != ~0ull) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (best_h == rh[j] && best_p != rp[j]) EMIT(rh[j], rp[j]);
+      }
+    }
+  }
+  if (best_h != ~0ull) EMIT(best_h, best_p);
+#undef EMIT
+  return n;
+}
+__device__ __forceinline__ int gen_minimizers_any(const u8 *seq, int len, int k, int w, u64 *out_hash, u32 *out_pos, int cap) {
+  if (w == 7) return gen_minimizers_regs<7>(seq, len, k, out_hash, out_pos, cap);    // default (-w 7)
+  if (w == 10) return gen_minimizers_regs<10>(seq, len, k, out_hash, out_pos, cap);  // --min-frag-length <= 80
+  if (w == 11) return gen_minimizers_regs<11>(seq, len, k, out_hash, out_pos, cap);  // --min-frag-length > 80
+  return gen_minimizers_thread(seq, len, k, w, out_hash, out_pos, cap);
+}
+
 struct RepStats { u32 len, prev; int count; };
 __device__ __forceinline__ void rep_update(int k, int w, u32 read_pos, RepStats &st) {  // index.cc:507-523
   if (st.prev > read_pos) st.len += k;
@@ -168,7 +233,8 @@ __device__ inline int cluster_hits(int e, int need, u32 n_mm, const u64 *hits, i
 }
 
 // K1: per read — minimizers, index probe, hit lists, sort, clustering (candidate_processor.cc:12-71,
-// index.cc:237-349).
+// index.cc:237-349).  Tier 0 takes only "light" reads: as soon as the exact hit count (known from the table
+// values before any occurrence is read) exceeds the tier's capacity the pair is escalated to the CTA tier.
 __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr) {
   const int sr = blockIdx.x * blockDim.x + threadIdx.x;
   if (sr >= 2 * S.n_slots) return;
@@ -182,34 +248,48 @@ __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Cou
   u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
   u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
   u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
-  const int n_mm = gen_minimizers_thread(seq, L, P.k, P.w, mmh, mmp, c.maxmm);
+  const int n_mm = gen_minimizers_any(seq, L, P.k, P.w, mmh, mmp, c.maxmm);
   rm.n_mm = n_mm;
-  rm.n_hits[0] = rm.n_hits[1] = 0; rm.n_cand[0] = rm.n_cand[1] = 0; rm.n_buf[0] = rm.n_buf[1] = 0;
-  rm.n_aug[0] = rm.n_aug[1] = 0; rm.n_map[0] = rm.n_map[1] = 0; rm.n_cand_gen[0] = rm.n_cand_gen[1] = 0;
-  rm.rep_len = 0; rm.min_err = 0; rm.second_min_err = 0; rm.n_best = 0; rm.n_second_best = 0;
-  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); return; }
   if (n_mm == 0) return;
-  // probe all minimizers once; remember kind + value
-  u64 steps_total = 0, found = 0;
-  long long cnt1 = 0;  // round-1 hit count
+  // all first-probe slots are independent: pull them towards L2 before the dependent probe chains start
+  for (int i = 0; i < n_mm; ++i) {
+    const u64 s0 = (mmh[i] * 0x9E3779B97F4A7C15ull) >> ix.shift;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.slots + s0));
+  }
+  u32 steps_total = 0, found = 0;
+  long long cnt1 = 0, cnt2 = 0;
+  RepStats st = {0u, 0xFFFFFFFFu, 0};
   for (int i = 0; i < n_mm; ++i) {
     u64 val = 0;
     int steps;
     const int kind = index_lookup(ix, mmh[i], &val, &steps);
     steps_total += steps;
     mmv[i] = val;
-    mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
-    if (kind == 1) { ++cnt1; ++found; }
-    else if (kind == 2) { ++found; if ((u32)val < (u32)P.f0) cnt1 += (u32)val; }
+    const u32 mp = mmp[i] & 0x3FFFFFFFu;
+    mmp[i] = mp | ((u32)kind << 30);
+    if (kind == 1) { ++cnt1; ++cnt2; ++found; }
+    else if (kind == 2) {
+      ++found;
+      const u32 n = (u32)val;
+      if (n < (u32)P.f0) cnt1 += n;
+      if (n < (u32)P.f1) cnt2 += n;
+      if (n >= (u32)P.f0) rep_update(P.k, P.w, mp >> 1, st);
+    }
+  }
+  {  // warp-aggregated statistics
+    const unsigned m = __activemask();
+    const u32 a = __reduce_add_sync(m, (u32)n_mm), b = __reduce_add_sync(m, steps_total), f = __reduce_add_sync(m, found);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(&ctr->n_minimizers, (u64)a); atomicAdd(&ctr->n_probe_steps, (u64)b); atomicAdd(&ctr->n_found, (u64)f); }
   }
   // round 1 (f0) or, if it yields no hits at all, round 2 (f1)  (candidate_processor.cc:30-50)
   const bool round2 = cnt1 == 0;
+  const long long total = round2 ? cnt2 : cnt1;
+  if (total > c.hc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[2], 1ull); return; }  // per-strand lists can then never exceed hc
   const u32 max_freq = round2 ? (u32)P.f1 : (u32)P.f0;
   u64 *hp = S.hits + ((size_t)sr * 2 + 0) * c.hc, *hn = S.hits + ((size_t)sr * 2 + 1) * c.hc;
   int np = 0, nn = 0;
-  bool ovf = false;
-  RepStats st = {0u, 0xFFFFFFFFu, 0};
-  u64 occ_reads = 0;
+  u32 occ_reads = 0;
   for (int i = 0; i < n_mm; ++i) {
     const u32 kind = mmp[i] >> 30;
     if (kind == 0) continue;
@@ -218,7 +298,7 @@ __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Cou
     bool same;
     if (kind == 1) {
       const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
-      if (same) { if (np < c.hc) hp[np] = cp; ++np; } else { if (nn < c.hc) hn[nn] = cp; ++nn; }
+      if (same) hp[np++] = cp; else hn[nn++] = cp;
       continue;
     }
     const u32 n = (u32)val, off = (u32)(val >> 32);
@@ -226,18 +306,12 @@ __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Cou
       for (u32 j = 0; j < n; ++j) {
         const u64 rh = __ldg(&ix.occ[off + j]);
         const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
-        if (same) { if (np < c.hc) hp[np] = cp; ++np; } else { if (nn < c.hc) hn[nn] = cp; ++nn; }
+        if (same) hp[np++] = cp; else hn[nn++] = cp;
       }
       occ_reads += n;
     }
-    if (n >= (u32)P.f0) rep_update(P.k, P.w, rpos, st);
   }
-  if (np > c.hc || nn > c.hc) ovf = true;
-  atomicAdd(&ctr->n_minimizers, (u64)n_mm);
-  atomicAdd(&ctr->n_probe_steps, steps_total);
-  atomicAdd(&ctr->n_found, found);
-  atomicAdd(&ctr->n_occ_reads, occ_reads);
-  if (ovf) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  if (occ_reads) atomicAdd(&ctr->n_occ_reads, (u64)occ_reads);
   sort_u64(hp, np);
   sort_u64(hn, nn);
   rm.rep_len = st.len;
@@ -250,7 +324,7 @@ __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Cou
   u8 *cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cc1 = cc0 + c.cc;
   const int nc0 = cluster_hits(P.e, need, (u32)n_mm, hp, np, cp0, cc0, c.cc);
   const int nc1 = cluster_hits(P.e, need, (u32)n_mm, hn, nn, cp1, cc1, c.cc);
-  if (nc0 > c.cc || nc1 > c.cc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  if (nc0 > c.cc || nc1 > c.cc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[3], 1ull); return; }
   rm.n_cand[0] = nc0; rm.n_cand[1] = nc1;
   rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
 }
@@ -434,17 +508,17 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       if (ot.n_cand[0] > 0) {
         int nh;
         pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
-        if (nh > c.hc) { ovf = true; break; }
+        if (nh > c.hc) { ovf = true; atomicAdd(&ctr->ovf_reason[4], 1ull); break; }
         const int na = cluster_hits(P.e, 1, n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc);
-        if (na > c.cc) { ovf = true; break; }
+        if (na > c.cc) { ovf = true; atomicAdd(&ctr->ovf_reason[5], 1ull); break; }
         me.n_aug[1] = na;
       }
       if (ot.n_cand[1] > 0) {
         int nh;
         nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
-        if (nh > c.hc) { ovf = true; break; }
+        if (nh > c.hc) { ovf = true; atomicAdd(&ctr->ovf_reason[4], 1ull); break; }
         const int na = cluster_hits(P.e, 1, n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc);
-        if (na > c.cc) { ovf = true; break; }
+        if (na > c.cc) { ovf = true; atomicAdd(&ctr->ovf_reason[5], 1ull); break; }
         me.n_aug[0] = na;
       }
       if (((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) ret = 1;
@@ -456,7 +530,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
         if (me.n_aug[s] > 0) {
           const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
                                     CP(mate, 1, s), CC(mate, 1, s), c.cc);
-          if (n > c.cc) { ovf = true; break; }
+          if (n > c.cc) { ovf = true; atomicAdd(&ctr->ovf_reason[5], 1ull); break; }
           me.n_cand[s] = n;
         }
       }
@@ -630,7 +704,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
       for (int g = 0; g < ng; ++g) run_one(cp[s][group[g]]);
     }
   }
-  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
   rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
   rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
   if (n_verified) atomicAdd(&ctr->n_verified, n_verified);
@@ -992,18 +1066,18 @@ __global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
 // the same results as the general kernels; the expensive primitives — table probes, hit expansion,
 // sorting, banded verification — are spread over the CTA's threads, the order-dependent scans stay on
 // thread 0 and read their input through shared memory.
-#define CTA_NT 256
-#define CTA_SORT_SMEM 4096  // u64 entries staged in shared memory (32 KB)
+#define CTA_NT 128
+#define CTA_SORT_SMEM_MAX 4096  // u64 entries staged in shared memory at most (32 KB); the launch picks the tier's size
 #define CTA_MM_SMEM 1024    // max minimizers per read handled by the CTA kernels
 
 // ascending bitonic sort of n keys; pads a[n..np2) with ~0 (capacity must be a power of two >= n).
-__device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm) {
+__device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm, int sm_cap) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
   u64 *w = a;
-  const bool in_smem = np2 <= CTA_SORT_SMEM;
+  const bool in_smem = np2 <= sm_cap;
   if (in_smem) {
     for (int i = tid; i < np2; i += CTA_NT) sm[i] = i < n ? a[i] : ~0ull;
     w = sm;
@@ -1029,14 +1103,14 @@ __device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm) {
 
 // same for (key, tag) pairs under `less`; pads with (pad_key, pad_tag) which must compare greatest.
 template <typename T, typename Less>
-__device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_tag, Less less, u64 *smk, T *smt) {
+__device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_tag, Less less, u64 *smk, T *smt, int sm_cap) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
   u64 *wk = k_;
   T *wt = t_;
-  const bool in_smem = np2 <= CTA_SORT_SMEM;
+  const bool in_smem = np2 <= sm_cap;
   if (in_smem) {
     for (int i = tid; i < np2; i += CTA_NT) { smk[i] = i < n ? k_[i] : pad_key; smt[i] = i < n ? t_[i] : pad_tag; }
     wk = smk; wt = smt;
@@ -1064,13 +1138,13 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
 
 // candidate_processor.cc:283-342 with the sorted hits streamed through shared memory; thread 0 scans.
 // Returns the candidate count on every thread.
-__device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int *s_ret) {
+__device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int sm_cap, int *s_ret) {
   const int tid = threadIdx.x;
   int n = 0, mcount = 1, eq = 1, best_eq = 1;
   u64 prev = 0, best = 0;
   u32 prev_rid = 0, prev_pos = 0;
-  for (int base = 0; base < nh; base += CTA_SORT_SMEM) {
-    const int m = min(CTA_SORT_SMEM, nh - base);
+  for (int base = 0; base < nh; base += sm_cap) {
+    const int m = min(sm_cap, nh - base);
     for (int i = tid; i < m; i += CTA_NT) sm[i] = hits[base + i];
     __syncthreads();
     if (tid == 0) {
@@ -1101,10 +1175,10 @@ __device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, in
   return r;
 }
 
-__global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr) {
-  __shared__ u64 sm[CTA_SORT_SMEM];
-  __shared__ u32 s_c1[CTA_MM_SMEM], s_c2[CTA_MM_SMEM];
-  __shared__ int s_off[CTA_MM_SMEM + 1];
+__global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
+  extern __shared__ u64 sm[];  // [sm_cap] sort buffer, then per-minimizer arrays sized by the tier's maxmm
+  int *s_off = (int *)(sm + sm_cap);
+  u32 *s_c1 = (u32 *)(s_off + S.caps.maxmm + 1), *s_c2 = s_c1 + S.caps.maxmm;
   __shared__ int s_i[8];
   __shared__ unsigned long long s_steps;
   const int sr = blockIdx.x, tid = threadIdx.x;
@@ -1120,7 +1194,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
   u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
   if (tid == 0) {
-    const int n_mm = gen_minimizers_thread(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm);
+    const int n_mm = gen_minimizers_any(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm);
     rm.n_mm = n_mm;
     s_i[0] = n_mm;
     s_steps = 0;
@@ -1128,7 +1202,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   }
   __syncthreads();
   const int n_mm = s_i[0];
-  if (n_mm > c.maxmm || n_mm > CTA_MM_SMEM) { if (tid == 0) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW); return; }
+  if (n_mm > c.maxmm) { if (tid == 0) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW); return; }
   if (n_mm == 0) return;
   for (int i = tid; i < n_mm; i += CTA_NT) {
     u64 val = 0;
@@ -1182,7 +1256,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   }
   if (tid == 0) { u64 occ_reads = 0; for (int i = 0; i < n_mm; ++i) if ((mmp[i] >> 30) == 2) occ_reads += s_off[i + 1] - s_off[i]; atomicAdd(&ctr->n_occ_reads, occ_reads); }
   __syncthreads();
-  cta_sort_keys(hits, T, sm);
+  cta_sort_keys(hits, T, sm, sm_cap);
   if (tid == 0) {
     int lo = 0, hi = T;  // first index with the strand tag set
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid] >> 63) hi = mid; else lo = mid + 1; }
@@ -1198,8 +1272,8 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   if (s_i[1] && np > 0 && nn > 0) need = P.min_seeds;
   u64 *cp0 = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cp1 = cp0 + c.cc;
   u8 *cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cc1 = cc0 + c.cc;
-  const int nc0 = cta_cluster(P.e, need, (u32)n_mm, hits, np, cp0, cc0, c.cc, sm, &s_i[4]);
-  const int nc1 = cta_cluster(P.e, need, (u32)n_mm, hits + np, nn, cp1, cc1, c.cc, sm, &s_i[4]);
+  const int nc0 = cta_cluster(P.e, need, (u32)n_mm, hits, np, cp0, cc0, c.cc, sm, sm_cap, &s_i[4]);
+  const int nc1 = cta_cluster(P.e, need, (u32)n_mm, hits + np, nn, cp1, cc1, c.cc, sm, sm_cap, &s_i[4]);
   if (tid == 0) {
     if (nc0 > c.cc || nc1 > c.cc) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW);
     else {
@@ -1213,7 +1287,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
 // search state `prev_l` chains the windows of one minimizer, so windows stay sequential per minimizer),
 // hits are appended with a shared counter (order is irrelevant: they are sorted next).
 __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv, const u32 *mmp,
-                                 const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm,
+                                 const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm, int sm_cap,
                                  u64 *win_lo, u64 *win_hi, int *s_i, int *nh_out) {
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -1284,12 +1358,12 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
     *rep_len = st.len;
   }
   __syncthreads();
-  if (nh <= cap) cta_sort_keys(hits, nh, sm);
+  if (nh <= cap) cta_sort_keys(hits, nh, sm, sm_cap);
   return max_cnt;
 }
 
-__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
-  __shared__ u64 sm[CTA_SORT_SMEM];
+__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap) {
+  extern __shared__ u64 sm[];
   __shared__ u64 win_lo[300], win_hi[300];
   __shared__ int s_i[8];
   __shared__ int s_flag[4];
@@ -1329,19 +1403,19 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
     bool ovf = false;
     if (ot.n_cand[0] > 0) {
       int nh;
-      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, win_lo, win_hi, s_i, &nh);
+      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh);
       if (nh > c.hc) ovf = true;
       else {
-        const int na = cta_cluster(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, &s_i[4]);
+        const int na = cta_cluster(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, sm_cap, &s_i[4]);
         if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[1] = na;
       }
     }
     if (!ovf && ot.n_cand[1] > 0) {
       int nh;
-      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, win_lo, win_hi, s_i, &nh);
+      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh);
       if (nh > c.hc) ovf = true;
       else {
-        const int na = cta_cluster(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, &s_i[4]);
+        const int na = cta_cluster(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, sm_cap, &s_i[4]);
         if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[0] = na;
       }
     }
@@ -1390,9 +1464,9 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
 // verified by its own thread (lane-per-candidate Myers), thread 0 then replays the reference's order-
 // dependent group / threshold rule over the stored results (verifying a candidate the reference would
 // have skipped is wasted work, never a different result).
-__global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr) {
-  __shared__ u64 smk[CTA_SORT_SMEM];
-  __shared__ u8 smt[CTA_SORT_SMEM];
+__global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
+  extern __shared__ u64 smk[];
+  u8 *smt = (u8 *)(smk + sm_cap);
   __shared__ int s_done, s_status;
   const int sr = blockIdx.x, tid = threadIdx.x;
   const int slot = sr >> 1, mate = sr & 1;
@@ -1437,8 +1511,8 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
   __syncthreads();
   if (s_done) return;
   auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
-  cta_sort_pairs<u8>(cp[0], cc[0], nc[0], ~0ull, (u8)0, cless, smk, smt);
-  cta_sort_pairs<u8>(cp[1], cc[1], nc[1], ~0ull, (u8)0, cless, smk, smt);
+  cta_sort_pairs<u8>(cp[0], cc[0], nc[0], ~0ull, (u8)0, cless, smk, smt, sm_cap);
+  cta_sort_pairs<u8>(cp[1], cc[1], nc[1], ~0ull, (u8)0, cless, smk, smt, sm_cap);
   u64 n_ver = 0;
   for (int s = 0; s < 2; ++s)
     for (int i = tid; i < nc[s]; i += CTA_NT) {
@@ -1496,9 +1570,9 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
 }
 
 // pairing for one pair by one CTA: the four mapping lists are sorted cooperatively, thread 0 sweeps.
-__global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratch S, int *pair_nbest) {
-  __shared__ u64 smk[CTA_SORT_SMEM];
-  __shared__ signed char smt[CTA_SORT_SMEM];
+__global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratch S, int *pair_nbest, int sm_cap) {
+  extern __shared__ u64 smk[];
+  signed char *smt = (signed char *)(smk + sm_cap);
   const int slot = blockIdx.x, tid = threadIdx.x;
   PairMeta &pm = S.pmeta[slot];
   const int pair = slot_pair(S, slot);
@@ -1517,7 +1591,7 @@ __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratc
     for (int s = 0; s < 2; ++s) {
       mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
       me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
-      cta_sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (signed char)127, mless, smk, smt);
+      cta_sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (signed char)127, mless, smk, smt, sm_cap);
     }
   if (tid != 0) return;
   int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;

@@ -162,6 +162,8 @@ int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs);
 typedef struct {
   float h2d_ms, seed_ms, pair_candidates_ms, verify_ms, pairing_ms, select_ms, emit_ms, d2h_ms, total_ms;
   uint64_t n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_launches;
+  uint64_t tier_pairs[3];      /* pairs processed per scratch tier */
+  uint64_t escalations[8];     /* tier-0 escalations by cause (see Counters::ovf_reason) */
 } cmx_timing;
 int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out);
 

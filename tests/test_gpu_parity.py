@@ -63,6 +63,29 @@ def test_stage_minimizers_equal_oracle(synth):
             assert np.array_equal(p[r, :cnt[r]].astype(np.uint64), ot & np.uint64(0xFFFFFFFF))
 
 
+@pytest.mark.parametrize("k,w", [(19, 10), (23, 11), (15, 5), (28, 20)])
+def test_stage_minimizers_other_k_w(synth, k, w):
+    p = cb.make_params("", max_read_length=64)
+    m = cb.Mapper(p)
+    m.upload_reference([synth["seqs"][0][:50000]], ["chr1"])
+    m.build_index(k, w)
+    s1, o1, s2, o2 = synth["pairs"]
+    n = 400
+    h, pos, cnt = m.stage_minimizers(s1[:o1[n]], o1[:n + 1], s2[:o2[n]], o2[:n + 1], 64)
+    for i in range(n):
+        for mate, (s, o) in enumerate(((s1, o1), (s2, o2))):
+            oh, ot = orc.minimizers(s[o[i]:o[i + 1]], k, w)
+            r = 2 * i + mate
+            assert cnt[r] == len(oh)
+            assert np.array_equal(h[r, :cnt[r]], oh)
+            assert np.array_equal(pos[r, :cnt[r]].astype(np.uint64), ot & np.uint64(0xFFFFFFFF))
+    # the device index builder uses the same generator on reference chunks: compare with the oracle's index
+    oref = orc.Reference(seqs=[synth["seqs"][0][:50000]])
+    oidx = orc.Index(ref=oref, k=k, w=w)
+    assert np.array_equal(m.download_index()["occ"], oidx.arrays()["occ"])
+    assert m.index_info()["n_keys"] == int((((oidx.arrays()["flags"][np.arange(oidx.arrays()["n_buckets"]) >> 4] >> ((np.arange(oidx.arrays()["n_buckets"]) & 15) << 1)) & 3) == 0).sum())
+
+
 def test_stage_probe_equals_khash_lookup(synth):
     import ctypes as C
     m = _mapper(synth, CASES["default"])
