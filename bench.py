@@ -255,7 +255,10 @@ def run_ours(a):
             st = fn(a.warmup + i)
             tm = m.timing()
             for k_, v in tm.items():
-                stage[k_] = stage.get(k_, 0) + v
+                if isinstance(v, list):
+                    stage[k_] = [x + y for x, y in zip(stage.get(k_, [0] * len(v)), v)]
+                else:
+                    stage[k_] = stage.get(k_, 0) + v
             n_rec += st["n_records"]; n_map += st["n_mapped_pairs"]
         barrier()
         dt = time.perf_counter() - t0
@@ -303,6 +306,7 @@ def run_ours(a):
         "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
         "kernel_ms_per_step": {k_: round(v, 3) for k_, v in kern.items()},
         "mapped_fraction": dv["n_map"] / (a.steps * n),
+        "tier_pairs_per_step": [x / a.steps for x in st["tier_pairs"]],
         "roofline": {"kernel": "seed_kernel (minimizers + index probe + hit sort + clustering)", "bound": "hbm",
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "peak_source": peak_src, "traffic": None, "top_stage": top,
@@ -434,7 +438,7 @@ def run_reference(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preset", default="chip")
