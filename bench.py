@@ -316,7 +316,7 @@ def run_ours(a):
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -359,7 +359,7 @@ def run_reference(a):
         return
     binp = os.path.join(ROOT, "oracle", "_ref", "chromap")
     if not os.path.exists(binp):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/chromap not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/chromap not built (needs /root/reference at build time)"})
         return
     import torch
     import chromap_b200 as cb
@@ -419,7 +419,7 @@ def run_reference(a):
         except OSError:
             pass
     if pr.returncode != 0 or len(per_batch) < n_batches:
-        print(json.dumps({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (pr.returncode, pr.stderr[-300:].replace("\n", " | "))}))
+        emit({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (pr.returncode, pr.stderr[-300:].replace("\n", " | "))})
         return
     timed = per_batch[a.warmup:a.warmup + a.steps]
     dt = sum(timed)
@@ -435,7 +435,20 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner,
+    torchrun notices) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

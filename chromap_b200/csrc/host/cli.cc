@@ -1,0 +1,180 @@
+// chromap-b200 — command-line front end that keeps the reference's CLI for the supported path
+// (chromap_driver.cc:16-159 option names, :247-275 presets, :451-531 checks): index construction (-i) on the
+// GPU with the reference's index file format, and paired-end mapping to BED through the C ABI.
+// Everything here is host plumbing around cmx_map_batch_pe; the batch loop replaces chromap.h:851-1290.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/chromap_b200.h"
+#include "seqio.h"
+
+using cmxhost::IndexFile;
+using cmxhost::Reference;
+using cmxhost::SeqReader;
+
+static void Die(const std::string &msg) {  // utils.h:71-74
+  fprintf(stderr, "%s\n", msg.c_str());
+  exit(255);
+}
+static double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Batch {
+  std::string s1, s2;
+  std::vector<uint32_t> o1{0}, o2{0};
+  uint32_t n = 0, first_id = 0;
+  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); n = 0; }
+};
+
+// LoadPairedEndReadsWithBarcodes (chromap.cc:93-174, non-barcode): empty reads are skipped per file
+// (sequence_batch.cc:28-31), the two files must run out together.
+static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b) {
+  std::string n, s, q;
+  b->Clear();
+  while (b->n < max_pairs) {
+    bool a = r1.Next(&n, &s, &q);
+    while (a && s.empty()) a = r1.Next(&n, &s, &q);
+    if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); }
+    bool c = r2.Next(&n, &s, &q);
+    while (c && s.empty()) c = r2.Next(&n, &s, &q);
+    if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
+    if (!a && !c) break;
+    if (a != c) Die("Numbers of reads and barcodes don't match!");
+    ++b->n;
+  }
+  return b->n;
+}
+
+int main(int argc, char **argv) {
+  cmx_params p;
+  cmx_default_params(&p);
+  std::string preset, ref_path, index_path, r1_path, r2_path, out_path;
+  bool build_index = false, bed = false, user_set_format = false;
+  int k = 17, w = 7, threads = 1;
+  (void)threads;
+  for (int i = 1; i < argc; ++i)
+    if (!strcmp(argv[i], "--preset") && i + 1 < argc) preset = argv[i + 1];
+  if (cmx_apply_preset(&p, preset.c_str()) != 0) Die("Unrecognized preset parameters " + preset + "\n");
+  if (!preset.empty()) fprintf(stderr, "Preset parameters for %s are used.\n", preset.c_str());
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto val = [&]() -> std::string { if (i + 1 >= argc) Die("Option " + a + " is missing an argument"); return argv[++i]; };
+    if (a == "--preset") val();
+    else if (a == "-i" || a == "--build-index") build_index = true;
+    else if (a == "-h" || a == "--help") { printf("chromap-b200: chromap's paired-end BED path on B200 GPUs (subset of chromap options; see DESIGN.md)\n"); return 0; }
+    else if (a == "-v" || a == "--version") { fprintf(stderr, "chromap-b200 0.1 (parity target: chromap 0.3.3-r521)\n"); return 0; }
+    else if (a == "-r" || a == "--ref") ref_path = val();
+    else if (a == "-x" || a == "--index") index_path = val();
+    else if (a == "-1" || a == "--read1") r1_path = val();
+    else if (a == "-2" || a == "--read2") r2_path = val();
+    else if (a == "-o" || a == "--output") out_path = val();
+    else if (a == "-t" || a == "--num-threads") threads = atoi(val().c_str());
+    else if (a == "-k" || a == "--kmer") k = atoi(val().c_str());
+    else if (a == "-w" || a == "--window") w = atoi(val().c_str());
+    else if (a == "--min-frag-length") { const int l = atoi(val().c_str()); if (l <= 60) { k = 17; w = 7; } else if (l <= 80) { k = 19; w = 10; } else { k = 23; w = 11; } }
+    else if (a == "-e" || a == "--error-threshold") p.error_threshold = atoi(val().c_str());
+    else if (a == "-s" || a == "--min-num-seeds") p.min_num_seeds = atoi(val().c_str());
+    else if (a == "-f" || a == "--max-seed-frequencies") { const std::string v = val(); if (sscanf(v.c_str(), "%d,%d", &p.max_seed_freq0, &p.max_seed_freq1) != 2) Die("-f expects two comma separated integers"); }
+    else if (a == "-l" || a == "--max-insert-size") p.max_insert_size = atoi(val().c_str());
+    else if (a == "-q" || a == "--MAPQ-threshold") p.mapq_threshold = atoi(val().c_str());
+    else if (a == "--min-read-length") p.min_read_length = atoi(val().c_str());
+    else if (a == "--trim-adapters") p.trim_adapters = 1;
+    else if (a == "--remove-pcr-duplicates") p.remove_pcr_duplicates = 1;
+    else if (a == "--Tn5-shift") p.tn5_shift = 1;
+    else if (a == "--low-mem") p.low_memory_mode = 1;
+    else if (a == "--BED") { bed = true; user_set_format = true; }
+    else if (a == "--split-alignment" || a == "--SAM" || a == "--TagAlign" || a == "--pairs" || a == "--PAF" || a == "-b" || a == "--barcode" ||
+             a == "--barcode-whitelist" || a == "-n" || a == "--summary")
+      Die("chromap-b200: option " + a + " is not on the GPU path yet (paired-end BED, non-split only); use the reference chromap for it");
+    else Die("Unknown option " + a);
+  }
+  (void)bed; (void)user_set_format;
+  if (p.output_format != 1 || p.split_alignment) Die("chromap-b200: this preset needs split alignment / pairs output, which is not on the GPU path yet");
+  cmx_ctx *ctx = nullptr;
+  const double t_start = Now();
+  if (build_index) {  // chromap_driver.cc:451-471
+    if (ref_path.empty() || out_path.empty()) Die("No reference specified!");
+    fprintf(stderr, "Build index for the reference.\nKmer length: %d, window size: %d\nReference file: %s\nOutput file: %s\n", k, w, ref_path.c_str(), out_path.c_str());
+    Reference ref;
+    if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);
+    int rc = cmx_create(&ctx, 0, &p);
+    if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: cmx_create failed");
+    if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
+    if (cmx_build_index(ctx, k, w)) Die(cmx_last_error(ctx));
+    IndexFile ix;
+    ix.k = k; ix.w = w;
+    uint32_t n_occ = 0;
+    if (cmx_download_index(ctx, &ix.n_buckets, &ix.size, nullptr, nullptr, nullptr, &n_occ, nullptr)) Die(cmx_last_error(ctx));
+    ix.flags.resize(ix.n_buckets < 16 ? 1 : ix.n_buckets >> 4); ix.keys.resize(ix.n_buckets); ix.vals.resize(ix.n_buckets); ix.occ.resize(n_occ);
+    if (cmx_download_index(ctx, &ix.n_buckets, &ix.size, ix.flags.data(), ix.keys.data(), ix.vals.data(), &n_occ, ix.occ.data())) Die(cmx_last_error(ctx));
+    ix.n_occupied = ix.size;
+    ix.upper_bound = (uint32_t)(ix.n_buckets * 0.77 + 0.5);
+    if (!ix.Save(out_path)) Die("Cannot write index file " + out_path);
+    fprintf(stderr, "Lookup table size: %u, # buckets: %u, occurrence table size: %u.\nBuilt and saved index in %.2fs.\n", ix.size, ix.n_buckets, n_occ, Now() - t_start);
+    cmx_destroy(ctx);
+    return 0;
+  }
+  if (ref_path.empty()) Die("No reference specified!");
+  if (index_path.empty()) Die("No index specified!");
+  if (r1_path.empty() || r2_path.empty()) Die("chromap-b200 maps paired-end reads: give -1 and -2");
+  if (out_path.empty()) Die("No output file specified!");
+  Reference ref;
+  if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);
+  fprintf(stderr, "Loaded all sequences successfully, number of sequences: %zu, number of bases: %zu.\n", ref.names.size(), ref.concat.size());
+  IndexFile ix;
+  if (!ix.Load(index_path)) Die("Cannot load index file " + index_path);
+  fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %zu.\n", ix.k, ix.w, ix.size, ix.occ.size());
+  int rc = cmx_create(&ctx, 0, &p);
+  if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: unsupported parameter combination");
+  if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
+  if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags.data(), ix.keys.data(), ix.vals.data(), ix.occ.data(), (uint32_t)ix.occ.size())) Die(cmx_last_error(ctx));
+  { IndexFile().flags.swap(ix.flags); std::vector<uint64_t>().swap(ix.keys); std::vector<uint64_t>().swap(ix.vals); std::vector<uint64_t>().swap(ix.occ); }
+  SeqReader r1, r2;
+  if (!r1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
+  if (!r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
+  // double-buffered batch loop: the loader thread parses batch b+1 while the GPU maps batch b (chromap.h:871-877)
+  Batch cur, next;
+  std::vector<cmx_pe_record> all, recs;
+  uint64_t n_pairs = 0, n_mapped = 0, n_unique = 0, n_cand = 0;
+  const double t_map = Now();
+  uint32_t read_id = 0;
+  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur);
+  while (cur.n > 0) {
+    cur.first_id = read_id;
+    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next); });
+    recs.resize((size_t)cur.n * p.max_num_best_mappings);
+    cmx_batch in{cur.n, cur.s1.data(), cur.o1.data(), cur.s2.data(), cur.o2.data(), cur.first_id, 0};
+    cmx_records out{recs.data(), recs.size(), 0, 0, 0, 0, 0, 0};
+    const double t0 = Now();
+    if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
+    fprintf(stderr, "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
+    all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
+    n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
+    read_id += cur.n;
+    loader.join();
+    std::swap(cur, next);
+  }
+  fprintf(stderr, "Mapped all reads in %.2fs.\n", Now() - t_map);
+  fprintf(stderr, "Number of reads: %llu.\nNumber of mapped reads: %llu.\nNumber of uniquely mapped reads: %llu.\nNumber of candidates: %llu.\n",
+          (unsigned long long)(2 * n_pairs), (unsigned long long)(2 * n_mapped), (unsigned long long)(2 * n_unique), (unsigned long long)n_cand);
+  uint64_t keep = 0;
+  const double t_pp = Now();
+  if (cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+  std::vector<const char *> names;
+  for (const auto &s : ref.names) names.push_back(s.c_str());
+  const int64_t bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
+  std::vector<char> text((size_t)bytes + 1);
+  cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);
+  FILE *fo = fopen(out_path.c_str(), "wb");
+  if (!fo) Die("Cannot open output file " + out_path);
+  fwrite(text.data(), 1, (size_t)bytes, fo);
+  fclose(fo);
+  fprintf(stderr, "Sorted, deduped and outputed mappings in %.2fs.\nNumber of output mappings (passed filters): %llu\nTotal time: %.2fs.\n", Now() - t_pp,
+          (unsigned long long)keep, Now() - t_start);
+  cmx_destroy(ctx);
+  return 0;
+}

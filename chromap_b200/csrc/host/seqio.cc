@@ -1,0 +1,136 @@
+#include "seqio.h"
+
+#include <cctype>
+#include <cstdio>
+
+namespace cmxhost {
+
+bool SeqReader::Open(const std::string &path) {
+  Close();
+  f_ = gzopen(path.c_str(), "r");
+  if (!f_) return false;
+  gzbuffer(f_, 1 << 20);
+  buf_.resize(1 << 20);
+  pos_ = end_ = 0;
+  eof_ = false;
+  pending_ = 0;
+  return true;
+}
+
+void SeqReader::Close() {
+  if (f_) gzclose(f_);
+  f_ = nullptr;
+}
+
+int SeqReader::GetC() {
+  if (pos_ >= end_) {
+    if (eof_) return -1;
+    const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+    if (n <= 0) { eof_ = true; return -1; }
+    pos_ = 0;
+    end_ = (size_t)n;
+  }
+  return buf_[pos_++];
+}
+
+bool SeqReader::GetLine(std::string *s) {
+  s->clear();
+  bool any = false;
+  for (;;) {
+    if (pos_ >= end_) {
+      if (eof_) break;
+      const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+      if (n <= 0) { eof_ = true; break; }
+      pos_ = 0;
+      end_ = (size_t)n;
+    }
+    any = true;
+    size_t i = pos_;
+    while (i < end_ && buf_[i] != '\n') ++i;
+    s->append((const char *)buf_.data() + pos_, i - pos_);
+    if (i < end_) { pos_ = i + 1; break; }
+    pos_ = end_;
+  }
+  if (s->size() > 1 && s->back() == '\r') s->pop_back();  // kseq.h:141 strips '\r' only when the line has more
+  return any;
+}
+
+bool SeqReader::Next(std::string *name, std::string *seq, std::string *qual) {
+  name->clear(); seq->clear(); qual->clear();
+  int c;
+  if (pending_ == 0) {
+    while ((c = GetC()) != -1 && c != '>' && c != '@') {}
+    if (c == -1) return false;
+  }
+  pending_ = 0;
+  std::string line;
+  GetLine(&line);
+  size_t sp = 0;
+  while (sp < line.size() && !isspace((unsigned char)line[sp])) ++sp;
+  name->assign(line, 0, sp);
+  while ((c = GetC()) != -1 && c != '>' && c != '+' && c != '@') {
+    if (c == '\n') continue;
+    seq->push_back((char)c);
+    GetLine(&line);
+    seq->append(line);
+  }
+  if (c == '>' || c == '@') pending_ = c;
+  if (c != '+') return true;
+  GetLine(&line);  // rest of the '+' line
+  while (qual->size() < seq->size()) {
+    if (!GetLine(&line)) break;
+    qual->append(line);
+  }
+  return true;
+}
+
+bool Reference::Load(const std::string &path) {
+  SeqReader rd;
+  if (!rd.Open(path)) return false;
+  names.clear(); concat.clear(); offsets.assign(1, 0);
+  std::string n, s, q;
+  while (rd.Next(&n, &s, &q)) {
+    if (s.empty()) continue;
+    names.push_back(n);
+    concat.append(s);
+    offsets.push_back(concat.size());
+  }
+  return !names.empty();
+}
+
+bool IndexFile::Load(const std::string &path) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  uint32_t lookup_size = 0, n_occ = 0;
+  bool ok = fread(&k, 4, 1, f) == 1 && fread(&w, 4, 1, f) == 1 && fread(&lookup_size, 4, 1, f) == 1 &&
+            fread(&n_buckets, 4, 1, f) == 1 && fread(&size, 4, 1, f) == 1 && fread(&n_occupied, 4, 1, f) == 1 &&
+            fread(&upper_bound, 4, 1, f) == 1;
+  if (ok && n_buckets) {
+    const size_t nf = n_buckets < 16 ? 1 : n_buckets >> 4;
+    flags.resize(nf); keys.resize(n_buckets); vals.resize(n_buckets);
+    ok = fread(flags.data(), 4, nf, f) == nf && fread(keys.data(), 8, n_buckets, f) == n_buckets &&
+         fread(vals.data(), 8, n_buckets, f) == n_buckets;
+  }
+  ok = ok && fread(&n_occ, 4, 1, f) == 1;
+  if (ok && n_occ) { occ.resize(n_occ); ok = fread(occ.data(), 8, n_occ, f) == n_occ; }
+  fclose(f);
+  return ok;
+}
+
+bool IndexFile::Save(const std::string &path) const {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const uint32_t n_occ = (uint32_t)occ.size();
+  bool ok = fwrite(&k, 4, 1, f) == 1 && fwrite(&w, 4, 1, f) == 1 && fwrite(&size, 4, 1, f) == 1 &&
+            fwrite(&n_buckets, 4, 1, f) == 1 && fwrite(&size, 4, 1, f) == 1 && fwrite(&n_occupied, 4, 1, f) == 1 &&
+            fwrite(&upper_bound, 4, 1, f) == 1;
+  if (ok && n_buckets)
+    ok = fwrite(flags.data(), 4, flags.size(), f) == flags.size() && fwrite(keys.data(), 8, n_buckets, f) == n_buckets &&
+         fwrite(vals.data(), 8, n_buckets, f) == n_buckets;
+  ok = ok && fwrite(&n_occ, 4, 1, f) == 1;
+  if (ok && n_occ) ok = fwrite(occ.data(), 8, n_occ, f) == n_occ;
+  fclose(f);
+  return ok;
+}
+
+}  // namespace cmxhost

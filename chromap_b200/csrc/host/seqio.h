@@ -1,0 +1,49 @@
+// chromap_b200 host side — FASTA/FASTQ reader with the behaviour of the reference's kseq.h
+// (kseq.h:177-222): record starts at '>' or '@'; name = header up to the first whitespace; sequence = all
+// following lines (newline and a trailing '\r' stripped, every other byte kept) until a line starting
+// with '>', '+' or '@'; FASTQ quality is consumed by length.  Plain or gzip (zlib), like gzopen.
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+namespace cmxhost {
+
+class SeqReader {
+ public:
+  bool Open(const std::string &path);
+  void Close();
+  // false at end of file.  `qual` stays empty for FASTA.
+  bool Next(std::string *name, std::string *seq, std::string *qual);
+  ~SeqReader() { Close(); }
+
+ private:
+  int GetC();
+  bool GetLine(std::string *s);
+  gzFile f_ = nullptr;
+  std::vector<unsigned char> buf_;
+  size_t pos_ = 0, end_ = 0;
+  bool eof_ = false;
+  int pending_ = 0;  // header character already consumed
+};
+
+struct Reference {
+  std::vector<std::string> names;
+  std::string concat;             // all sequences back to back, bytes as loaded
+  std::vector<uint64_t> offsets;  // n + 1
+  bool Load(const std::string &path);  // SequenceBatch::LoadAllSequences (sequence_batch.cc:84-118): empty records are skipped
+};
+
+// Index file, reference layout (index.cc:91-169, khash.h:358-386).
+struct IndexFile {
+  int k = 0, w = 0;
+  uint32_t n_buckets = 0, size = 0, n_occupied = 0, upper_bound = 0;
+  std::vector<uint32_t> flags;
+  std::vector<uint64_t> keys, vals, occ;
+  bool Load(const std::string &path);
+  bool Save(const std::string &path) const;
+};
+
+}  // namespace cmxhost

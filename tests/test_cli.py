@@ -1,0 +1,67 @@
+"""The C++ front end (chromap_b200/bin/chromap-b200): reference CLI names, presets, index file format."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "chromap_b200", "bin", "chromap-b200")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "chromap")
+
+
+def _ensure_cli():
+    if not os.path.exists(CLI):
+        import __graft_entry__
+        __graft_entry__.build()
+    return CLI
+
+
+def test_cli_rejects_unsupported_and_missing_gpu():
+    cli = _ensure_cli()
+    r = subprocess.run([cli, "--preset", "nope"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unrecognized preset" in r.stderr
+    r = subprocess.run([cli, "--preset", "hic", "-x", "a", "-r", "b"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not on the GPU path" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        d = os.path.join(ROOT, "tests", "golden", "ref_test")
+        r = subprocess.run([cli, "-x", os.path.join(d, "ref.index"), "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq"),
+                            "-2", os.path.join(d, "read2.fq"), "-o", "/tmp/never.bed"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,args", [("chip", ["--preset", "chip"]), ("atac", ["--preset", "atac"]), ("default", []),
+                                       ("q0dedup", ["--remove-pcr-duplicates", "-q", "0"]),
+                                       ("e5", ["-e", "5", "-q", "10", "--Tn5-shift", "--remove-pcr-duplicates"]),
+                                       ("e12l300", ["-e", "12", "-l", "300", "-q", "0"])])
+def test_cli_end_to_end_equals_reference_binary_output(case, args, tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    out = str(tmp_path / "out.bed")
+    subprocess.check_call([cli] + args + ["-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
+                                         "-2", os.path.join(d, "read2.fq.gz"), "-o", out], stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+
+
+@pytest.mark.gpu
+def test_index_file_written_by_cli_is_loadable_by_the_reference_binary(tmp_path, golden_dir):
+    """Index::Load + kh_get of the unmodified reference must find every key in the file we write."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/chromap not built")
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    ref = str(tmp_path / "ref.fa")
+    open(ref, "wb").write(gzip.open(os.path.join(d, "ref.fa.gz")).read())
+    for n in ("read1", "read2"):
+        open(str(tmp_path / (n + ".fq")), "wb").write(gzip.open(os.path.join(d, n + ".fq.gz")).read())
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", ref, "-o", idx], stderr=subprocess.DEVNULL)
+    out = str(tmp_path / "ref_out.bed")
+    subprocess.check_call([REF_BIN, "-x", idx, "-r", ref, "-1", str(tmp_path / "read1.fq"), "-2", str(tmp_path / "read2.fq"), "-o", out, "-t", "2"],
+                          stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, "default.bed.gz")).read()
