@@ -432,7 +432,7 @@ def run_reference(a):
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
                              "sample": "%d batches of 500000 pairs, reference binary 'Mapped N read pairs in Xs' lines" % a.steps},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 _REAL_STDOUT = None
