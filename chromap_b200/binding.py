@@ -37,7 +37,7 @@ class Records(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms",
-                                         "select_ms", "emit_ms", "d2h_ms", "total_ms")] + \
+                                         "select_ms", "emit_ms", "d2h_ms", "total_ms", "minimizer_ms", "probe_ms", "cluster_ms")] + \
                [(n, C.c_uint64) for n in ("n_minimizers", "n_probe_steps", "n_found", "n_occ_reads", "n_verified",
                                           "n_launches")] + [("tier_pairs", C.c_uint64 * 3), ("escalations", C.c_uint64 * 8)]
 
@@ -90,6 +90,7 @@ def load_library():
     L.cmx_stage_minimizers.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, u32]
     L.cmx_stage_probe.argtypes = [vp, vp, u64, vp, vp, vp]
     L.cmx_stage_banded_align.argtypes = [vp, i32, i32, vp, vp, u64, vp, vp]
+    L.cmx_stage_cta_sort.argtypes = [vp, vp, vp, u32, u32]
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
     _lib = L
@@ -259,6 +260,12 @@ class Mapper:
         f = np.zeros(n, dtype=np.uint8); k = np.zeros(n, dtype=np.uint64); v = np.zeros(n, dtype=np.uint64)
         self._check(self.L.cmx_stage_probe(self.h, hashes.ctypes.data, n, f.ctypes.data, k.ctypes.data, v.ctypes.data), "cmx_stage_probe")
         return f, k, v
+
+    def stage_cta_sort(self, keys, tags=None, sm_cap=4096):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        tags = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint8).copy()
+        self._check(self.L.cmx_stage_cta_sort(self.h, keys.ctypes.data, None if tags is None else tags.ctypes.data, len(keys), sm_cap), "cmx_stage_cta_sort")
+        return keys, tags
 
     def stage_banded_align(self, e, read_len, patterns, texts):
         patterns = np.ascontiguousarray(patterns, dtype=np.uint8); texts = np.ascontiguousarray(texts, dtype=np.uint8)

@@ -69,6 +69,8 @@ struct cmx_ctx {
   Tier tiers[N_TIERS];
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10];
+  cudaEvent_t ev_sub[2];
+  float ms_minimizer = 0, ms_probe = 0, ms_cluster = 0;
   cmx_timing timing;
   u32 last_n_pairs = 0;
   int last_tiers_used = 0;
@@ -136,6 +138,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   CU(cudaSetDevice(device));
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
+  for (auto &e : ctx->ev_sub) CU(cudaEventCreate(&e));
   CU(cudaMalloc(&ctx->ctr, sizeof(Counters)));
   CU(cudaMalloc(&ctx->d_count, sizeof(int) * 4));
   // MAPQ tables from the host libm, so truncations match the reference bit for bit (mapping_generator.h:920-1022)
@@ -156,6 +159,11 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
     CU(cudaMemcpy(ctx->inv_log, il.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->pen_thr, thr.data(), 96 * sizeof(int), cudaMemcpyHostToDevice));
   }
+  // the overflow-tier kernels may use more than the default 48 KB of (static + dynamic) shared memory
+  CU(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CU(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CU(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
   ctx->tiers[0].caps = {mrl, 64, 32, 32};
   ctx->tiers[1].caps = {mrl * 2, 1024, 256, 256};
@@ -457,7 +465,11 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     CU(cudaEventRecord(e0, st));
     prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
     if (t == 0) {
-      seed_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, B, S, ctx->ctr);
+      minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, ctx->ctr);
+      CU(cudaEventRecord(ctx->ev_sub[0], st));
+      probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, ctx->ctr);  // persistent: 8 CTAs per SM
+      CU(cudaEventRecord(ctx->ev_sub[1], st));
+      cluster_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr);
       CU(cudaEventRecord(e1, st));
       CU(ensure(ctx->rescue_list, (size_t)n_slots * 4));
       CU(cudaMemsetAsync(ctx->d_count + 1, 0, sizeof(int), st));
@@ -471,16 +483,16 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     } else {  // overflow tiers: one CTA per read / pair; shared-memory sort buffers sized to the tier
       auto cap_of = [](int n) { int c = 1; while (c < n) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
       const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
-      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 8 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, ctx->ctr, c_seed);
+      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, ctx->ctr, c_seed);
       CU(cudaEventRecord(e1, st));
-      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 8, st>>>(P, ix, S, ctx->ctr, c_pc);
+      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 11, st>>>(P, ix, S, ctx->ctr, c_pc);
       CU(cudaEventRecord(e2, st));
       verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
       CU(cudaEventRecord(e3, st));
       pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 9, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
       CU(cudaEventRecord(e4, st));
     }
-    launches += 6;
+    launches += (t == 0 ? 8 : 6);
     CU(ensure(tier.ovf_list, (size_t)n_slots * 4));
     CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), st));
     collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, ctx->d_count);
@@ -491,6 +503,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     CU(cudaGetLastError());
     float f;
     cudaEventElapsedTime(&f, e0, e1); ms_seed += f;
+    if (t == 0) { cudaEventElapsedTime(&ctx->ms_minimizer, e0, ctx->ev_sub[0]); cudaEventElapsedTime(&ctx->ms_probe, ctx->ev_sub[0], ctx->ev_sub[1]); cudaEventElapsedTime(&ctx->ms_cluster, ctx->ev_sub[1], e1); }
     cudaEventElapsedTime(&f, e1, e2); ms_pc += f;
     cudaEventElapsedTime(&f, e2, e3); ms_ver += f;
     cudaEventElapsedTime(&f, e3, e4); ms_pair += f;
@@ -549,7 +562,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   cmx_timing &tm = ctx->timing;
   memset(&tm, 0, sizeof(tm));
   cudaEventElapsedTime(&tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-  tm.seed_ms = ms_seed; tm.pair_candidates_ms = ms_pc; tm.verify_ms = ms_ver; tm.pairing_ms = ms_pair;
+  tm.seed_ms = ms_seed; tm.minimizer_ms = ctx->ms_minimizer; tm.probe_ms = ctx->ms_probe; tm.cluster_ms = ctx->ms_cluster; tm.pair_candidates_ms = ms_pc; tm.verify_ms = ms_ver; tm.pairing_ms = ms_pair;
   cudaEventElapsedTime(&tm.select_ms, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&tm.emit_ms, ctx->ev[3], ctx->ev[4]);
   cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[4], ctx->ev[5]);
@@ -684,6 +697,35 @@ int cmx_stage_banded_align(cmx_ctx *ctx, int e, int read_len, const char *patter
   CU(cudaGetLastError());
   CU(cudaMemcpy(num_errors, de, n * 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(end_pos, dq, n * 4, cudaMemcpyDeviceToHost));
   cudaFree(dp); cudaFree(dt); cudaFree(de); cudaFree(dq);
+  return CMX_OK;
+}
+
+__global__ void __launch_bounds__(CTA_NT) stage_cta_sort_kernel(u64 *keys, u8 *tags, int n, int sm_cap, int with_tags) {
+  extern __shared__ u64 smk[];
+  u8 *smt = (u8 *)(smk + sm_cap);
+  if (with_tags) {
+    auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };  // candidate order
+    cta_sort_pairs<u8>(keys, tags, n, ~0ull, (u8)0, cless, smk, smt, sm_cap);
+  } else {
+    cta_sort_keys(keys, n, smk, sm_cap);
+  }
+}
+
+int cmx_stage_cta_sort(cmx_ctx *ctx, uint64_t *keys, uint8_t *tags, uint32_t n, uint32_t sm_cap) {
+  if (!ctx || !keys || sm_cap < 2 || (sm_cap & (sm_cap - 1)) || sm_cap > CTA_SORT_SMEM_MAX) return CMX_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  size_t cap = 1;
+  while (cap < n) cap <<= 1;
+  u64 *dk; u8 *dt;
+  CU(cudaMalloc(&dk, cap * 8 + 8)); CU(cudaMalloc(&dt, cap + 8));
+  CU(cudaMemcpy(dk, keys, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (tags) CU(cudaMemcpy(dt, tags, n, cudaMemcpyHostToDevice));
+  stage_cta_sort_kernel<<<1, CTA_NT, (size_t)sm_cap * 9>>>(dk, dt, (int)n, (int)sm_cap, tags ? 1 : 0);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(keys, dk, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (tags) CU(cudaMemcpy(tags, dt, n, cudaMemcpyDeviceToHost));
+  cudaFree(dk); cudaFree(dt);
   return CMX_OK;
 }
 

@@ -232,55 +232,80 @@ __device__ inline int cluster_hits(int e, int need, u32 n_mm, const u64 *hits, i
   return n;
 }
 
-// K1: per read — minimizers, index probe, hit lists, sort, clustering (candidate_processor.cc:12-71,
-// index.cc:237-349).  Tier 0 takes only "light" reads: as soon as the exact hit count (known from the table
-// values before any occurrence is read) exceeds the tier's capacity the pair is escalated to the CTA tier.
-__global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr) {
+// K1a: per read — minimizers (minimizer_generator.cc:7-139).  Integer-ALU bound: 3 x Hash64 per k-mer position.
+__global__ void minimizer_kernel(DevParams P, DevBatch B, Scratch S, Counters *ctr) {
   const int sr = blockIdx.x * blockDim.x + threadIdx.x;
   if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1, mate = sr & 1;
   if (S.pmeta[slot].status != ST_OK) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
-  const u8 *seq = read_ptr(B, pair, mate);
-  const int L = rm.len;
   const Caps c = S.caps;
-  u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
-  u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
-  u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
-  const int n_mm = gen_minimizers_any(seq, L, P.k, P.w, mmh, mmp, c.maxmm);
+  const int n_mm = gen_minimizers_any(read_ptr(B, pair, mate), rm.len, P.k, P.w, S.mm_hash + (size_t)sr * c.maxmm, S.mm_pos + (size_t)sr * c.maxmm, c.maxmm);
   rm.n_mm = n_mm;
-  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); return; }
-  if (n_mm == 0) return;
-  // all first-probe slots are independent: pull them towards L2 before the dependent probe chains start
-  for (int i = 0; i < n_mm; ++i) {
-    const u64 s0 = (mmh[i] * 0x9E3779B97F4A7C15ull) >> ix.shift;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.slots + s0));
+  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); }
+}
+
+// K1b: the index-probe kernel (khash.h:232-245 semantics on our table).  PROBE_LANES threads per read, one
+// probe chain per minimizer: millions of independent 16-byte random reads in flight — the HBM random-sector
+// kernel of the path.  Writes the table value and the kind (absent / singleton / multi) next to the minimizer.
+#define PROBE_LANES 8
+__global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, Scratch S, Counters *ctr) {
+  // persistent grid-stride loop: statistics are accumulated per thread and reduced once per CTA (three
+  // same-address atomics per warp were the bottleneck of the first version of this kernel)
+  __shared__ u32 s_acc[3];
+  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
+  __syncthreads();
+  u32 steps_total = 0, found = 0, n_mine = 0;
+  const long long total = (long long)2 * S.n_slots * PROBE_LANES;
+  const Caps c = S.caps;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int sr = (int)(t / PROBE_LANES), j = (int)(t % PROBE_LANES);
+    if (S.pmeta[sr >> 1].status != ST_OK) continue;
+    const int n_mm = min(S.rmeta[sr].n_mm, c.maxmm);
+    const u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
+    u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
+    u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
+    for (int i = j; i < n_mm; i += PROBE_LANES) {
+      u64 val = 0;
+      int steps;
+      const int kind = index_lookup(ix, mmh[i], &val, &steps);
+      mmv[i] = val;
+      mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
+      steps_total += steps; found += kind != 0; ++n_mine;
+    }
   }
-  u32 steps_total = 0, found = 0;
+  const u32 a = __reduce_add_sync(0xffffffffu, n_mine), b2 = __reduce_add_sync(0xffffffffu, steps_total), f = __reduce_add_sync(0xffffffffu, found);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[0], a); atomicAdd(&s_acc[1], b2); atomicAdd(&s_acc[2], f); }
+  __syncthreads();
+  if (threadIdx.x == 0) { atomicAdd(&ctr->n_minimizers, (u64)s_acc[0]); atomicAdd(&ctr->n_probe_steps, (u64)s_acc[1]); atomicAdd(&ctr->n_found, (u64)s_acc[2]); }
+}
+
+// K1c: per read — hit lists from the probed values, sort, clustering (candidate_processor.cc:12-71,
+// index.cc:237-349).  Tier 0 takes only "light" reads: as soon as the exact hit count (known from the table
+// values before any occurrence is read) exceeds the tier's capacity the pair is escalated to the CTA tier.
+__global__ void cluster_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
+  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sr >= 2 * S.n_slots) return;
+  const int slot = sr >> 1;
+  if (S.pmeta[slot].status != ST_OK) return;
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  const int n_mm = rm.n_mm;
+  if (n_mm == 0) return;
+  const u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
+  const u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
   long long cnt1 = 0, cnt2 = 0;
   RepStats st = {0u, 0xFFFFFFFFu, 0};
   for (int i = 0; i < n_mm; ++i) {
-    u64 val = 0;
-    int steps;
-    const int kind = index_lookup(ix, mmh[i], &val, &steps);
-    steps_total += steps;
-    mmv[i] = val;
-    const u32 mp = mmp[i] & 0x3FFFFFFFu;
-    mmp[i] = mp | ((u32)kind << 30);
-    if (kind == 1) { ++cnt1; ++cnt2; ++found; }
+    const u32 kind = mmp[i] >> 30;
+    if (kind == 1) { ++cnt1; ++cnt2; }
     else if (kind == 2) {
-      ++found;
-      const u32 n = (u32)val;
+      const u32 n = (u32)mmv[i];
       if (n < (u32)P.f0) cnt1 += n;
       if (n < (u32)P.f1) cnt2 += n;
-      if (n >= (u32)P.f0) rep_update(P.k, P.w, mp >> 1, st);
+      if (n >= (u32)P.f0) rep_update(P.k, P.w, (mmp[i] & 0x3FFFFFFFu) >> 1, st);
     }
-  }
-  {  // warp-aggregated statistics
-    const unsigned m = __activemask();
-    const u32 a = __reduce_add_sync(m, (u32)n_mm), b = __reduce_add_sync(m, steps_total), f = __reduce_add_sync(m, found);
-    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(&ctr->n_minimizers, (u64)a); atomicAdd(&ctr->n_probe_steps, (u64)b); atomicAdd(&ctr->n_found, (u64)f); }
   }
   // round 1 (f0) or, if it yields no hits at all, round 2 (f1)  (candidate_processor.cc:30-50)
   const bool round2 = cnt1 == 0;
@@ -303,8 +328,8 @@ __global__ void seed_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Cou
     }
     const u32 n = (u32)val, off = (u32)(val >> 32);
     if (n < max_freq) {
-      for (u32 j = 0; j < n; ++j) {
-        const u64 rh = __ldg(&ix.occ[off + j]);
+      for (u32 q = 0; q < n; ++q) {
+        const u64 rh = __ldg(&ix.occ[off + q]);
         const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
         if (same) hp[np++] = cp; else hn[nn++] = cp;
       }
@@ -1071,33 +1096,65 @@ __global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
 #define CTA_MM_SMEM 1024    // max minimizers per read handled by the CTA kernels
 
 // ascending bitonic sort of n keys; pads a[n..np2) with ~0 (capacity must be a power of two >= n).
+// Lists that fit the shared-memory buffer are sorted there; longer ones run the sub-steps with stride >=
+// sm_cap in global memory and finish every tile of sm_cap keys in shared memory (10 global passes instead of
+// 136 for 65536 keys).
 __device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm, int sm_cap) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
-  u64 *w = a;
-  const bool in_smem = np2 <= sm_cap;
-  if (in_smem) {
+  if (np2 <= sm_cap) {
     for (int i = tid; i < np2; i += CTA_NT) sm[i] = i < n ? a[i] : ~0ull;
-    w = sm;
-  } else {
-    for (int i = n + tid; i < np2; i += CTA_NT) a[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+          const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+          const u64 x = sm[i], y = sm[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { sm[i] = y; sm[l] = x; }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < n; i += CTA_NT) a[i] = sm[i];
+    __syncthreads();
+    return;
   }
+  for (int i = n + tid; i < np2; i += CTA_NT) a[i] = ~0ull;
   __syncthreads();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  for (int k = 2; k <= np2; k <<= 1) {
+    int j = k >> 1;
+    for (; j >= sm_cap; j >>= 1) {  // wide strides: global memory
       for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
         const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
-        const u64 x = w[i], y = w[l];
+        const u64 x = a[i], y = a[l];
         const bool up = (i & k) == 0;
-        if ((x > y) == up) { w[i] = y; w[l] = x; }
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
       }
       __syncthreads();
     }
-  if (in_smem) {
-    for (int i = tid; i < n; i += CTA_NT) a[i] = sm[i];
-    __syncthreads();
+    // remaining strides (< sm_cap) stay inside tiles of sm_cap keys: finish each tile in shared memory.
+    // (when k <= sm_cap this also covers the whole k-stage; consecutive small k stages are fused per tile)
+    const bool fuse = k <= sm_cap;
+    for (int base = 0; base < np2; base += sm_cap) {
+      for (int i = tid; i < sm_cap; i += CTA_NT) sm[i] = a[base + i];
+      __syncthreads();
+      const int k_lo = fuse ? 2 : k, k_hi = fuse ? sm_cap : k;
+      for (int kk = k_lo; kk <= k_hi; kk <<= 1)
+        for (int jj = fuse ? (kk >> 1) : j; jj > 0; jj >>= 1) {
+          for (int p = tid; p < (sm_cap >> 1); p += CTA_NT) {
+            const int i = ((p / jj) * (jj << 1)) + (p % jj), l = i + jj;
+            const u64 x = sm[i], y = sm[l];
+            const bool up = ((base + i) & kk) == 0;
+            if ((x > y) == up) { sm[i] = y; sm[l] = x; }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < sm_cap; i += CTA_NT) a[base + i] = sm[i];
+      __syncthreads();
+    }
+    if (fuse) k = sm_cap;  // stages 2..sm_cap are done
   }
 }
 
@@ -1108,31 +1165,61 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
-  u64 *wk = k_;
-  T *wt = t_;
-  const bool in_smem = np2 <= sm_cap;
-  if (in_smem) {
+  if (np2 <= sm_cap) {
     for (int i = tid; i < np2; i += CTA_NT) { smk[i] = i < n ? k_[i] : pad_key; smt[i] = i < n ? t_[i] : pad_tag; }
-    wk = smk; wt = smt;
-  } else {
-    for (int i = n + tid; i < np2; i += CTA_NT) { k_[i] = pad_key; t_[i] = pad_tag; }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+          const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+          const u64 xk = smk[i], yk = smk[l];
+          const T xt = smt[i], yt = smt[l];
+          const bool up = (i & k) == 0;
+          const bool sw = up ? less(yk, yt, xk, xt) : less(xk, xt, yk, yt);
+          if (sw) { smk[i] = yk; smt[i] = yt; smk[l] = xk; smt[l] = xt; }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < n; i += CTA_NT) { k_[i] = smk[i]; t_[i] = smt[i]; }
+    __syncthreads();
+    return;
   }
+  for (int i = n + tid; i < np2; i += CTA_NT) { k_[i] = pad_key; t_[i] = pad_tag; }
   __syncthreads();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  for (int k = 2; k <= np2; k <<= 1) {
+    int j = k >> 1;
+    for (; j >= sm_cap; j >>= 1) {
       for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
         const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
-        const u64 xk = wk[i], yk = wk[l];
-        const T xt = wt[i], yt = wt[l];
+        const u64 xk = k_[i], yk = k_[l];
+        const T xt = t_[i], yt = t_[l];
         const bool up = (i & k) == 0;
         const bool sw = up ? less(yk, yt, xk, xt) : less(xk, xt, yk, yt);
-        if (sw) { wk[i] = yk; wt[i] = yt; wk[l] = xk; wt[l] = xt; }
+        if (sw) { k_[i] = yk; t_[i] = yt; k_[l] = xk; t_[l] = xt; }
       }
       __syncthreads();
     }
-  if (in_smem) {
-    for (int i = tid; i < n; i += CTA_NT) { k_[i] = smk[i]; t_[i] = smt[i]; }
-    __syncthreads();
+    const bool fuse = k <= sm_cap;
+    for (int base = 0; base < np2; base += sm_cap) {
+      for (int i = tid; i < sm_cap; i += CTA_NT) { smk[i] = k_[base + i]; smt[i] = t_[base + i]; }
+      __syncthreads();
+      const int k_lo = fuse ? 2 : k, k_hi = fuse ? sm_cap : k;
+      for (int kk = k_lo; kk <= k_hi; kk <<= 1)
+        for (int jj = fuse ? (kk >> 1) : j; jj > 0; jj >>= 1) {
+          for (int p = tid; p < (sm_cap >> 1); p += CTA_NT) {
+            const int i = ((p / jj) * (jj << 1)) + (p % jj), l = i + jj;
+            const u64 xk = smk[i], yk = smk[l];
+            const T xt = smt[i], yt = smt[l];
+            const bool up = ((base + i) & kk) == 0;
+            const bool sw = up ? less(yk, yt, xk, xt) : less(xk, xt, yk, yt);
+            if (sw) { smk[i] = yk; smt[i] = yt; smk[l] = xk; smt[l] = xt; }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < sm_cap; i += CTA_NT) { k_[base + i] = smk[i]; t_[base + i] = smt[i]; }
+      __syncthreads();
+    }
+    if (fuse) k = sm_cap;
   }
 }
 
@@ -1175,6 +1262,163 @@ __device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, in
   return r;
 }
 
+// Minimizer emission (minimizer_generator.cc:66-138) from per-position seeds computed in parallel, for reads
+// without ambiguous bases (run length == position + 1) and odd k (no strand-symmetric k-mers).
+template <int W>
+__device__ __forceinline__ int emit_minimizers_from_seeds(const u64 *sh, const u32 *sp, int len, int k, u64 *out_hash, u32 *out_pos, int cap) {
+  u64 rh[W];
+  u32 rp[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) { rh[i] = ~0ull; rp[i] = ~0u; }
+  u64 best_h = ~0ull;
+  u32 best_p = ~0u;
+  int best_age = 0, n = 0;
+#define EMIT(h, p) do { if (n < cap) { out_hash[n] = (h); out_pos[n] = (p); } ++n; } while (0)
+  for (int pos = 0; pos < len; ++pos) {
+    const int run = pos + 1;
+    const u64 cur_h = sh[pos];
+    const u32 cur_p = sp[pos];
+#pragma unroll
+    for (int j = 0; j + 1 < W; ++j) { rh[j] = rh[j + 1]; rp[j] = rp[j + 1]; }
+    rh[W - 1] = cur_h; rp[W - 1] = cur_p;
+    ++best_age;
+    if (run == W + k - 1 && best_h != ~0ull && best_h < cur_h) {
+#pragma unroll
+      for (int j = 0; j + 1 < W; ++j) if (best_h == rh[j] && rp[j] != best_p) EMIT(rh[j], rp[j]);
+    }
+    if (cur_h <= best_h) {
+      if (run >= W + k && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = cur_h; best_p = cur_p; best_age = 0;
+    } else if (best_age == W) {
+      if (run >= W + k - 1 && best_h != ~0ull) EMIT(best_h, best_p);
+      best_h = ~0ull;
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (best_h >= rh[j]) { best_h = rh[j]; best_p = rp[j]; best_age = W - 1 - j; }
+      if (run >= W + k - 1 && best_h != ~0ull) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (best_h == rh[j] && best_p != rp[j]) EMIT(rh[j], rp[j]);
+      }
+    }
+  }
+  if (best_h != ~0ull) EMIT(best_h, best_p);
+#undef EMIT
+  return n;
+}
+
+// CTA minimizers: every thread hashes the k-mers ending at its positions (3 x Hash64 each), thread 0 replays the
+// window logic over the seeds.  Falls back to the one-thread generator for reads with ambiguous bases, even k or
+// an unusual w.  `work` is scratch shared memory of at least len * 13 bytes.  Returns n_mm on thread 0 only.
+__device__ inline int cta_minimizers(const u8 *seq, int len, int k, int w, u64 *out_hash, u32 *out_pos, int cap, u64 *work, int *s_flag) {
+  const int tid = threadIdx.x;
+  u64 *sh = work;
+  u32 *sp = (u32 *)(work + len);
+  u8 *sc = (u8 *)(sp + len);
+  if (tid == 0) *s_flag = ((k & 1) && (w == 7 || w == 10 || w == 11)) ? 1 : 0;
+  __syncthreads();
+  for (int p = tid; p < len; p += CTA_NT) { const u32 c = base_code(seq[p]); sc[p] = (u8)c; if (c > 3) *s_flag = 0; }
+  __syncthreads();
+  const bool fast = *s_flag != 0;
+  if (fast) {
+    const u64 mask = (((u64)1) << (2 * k)) - 1;
+    for (int p = tid; p < len; p += CTA_NT) {
+      u64 h = ~0ull;
+      u32 pp = ~0u;
+      if (p >= k - 1) {
+        u64 fwd = 0, rev = 0;
+        for (int i = 0; i < k; ++i) { const u64 b = sc[p - k + 1 + i]; fwd = (fwd << 2) | b; rev |= (3ull ^ b) << (2 * i); }
+        const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
+        const u32 strand = hf < hr ? 0u : 1u;
+        h = mix64(strand ? hr : hf, mask);
+        pp = ((u32)p << 1) | strand;
+      }
+      sh[p] = h; sp[p] = pp;
+    }
+  }
+  __syncthreads();
+  int n = 0;
+  if (tid == 0) {
+    if (!fast) n = gen_minimizers_any(seq, len, k, w, out_hash, out_pos, cap);
+    else if (w == 7) n = emit_minimizers_from_seeds<7>(sh, sp, len, k, out_hash, out_pos, cap);
+    else if (w == 10) n = emit_minimizers_from_seeds<10>(sh, sp, len, k, out_hash, out_pos, cap);
+    else n = emit_minimizers_from_seeds<11>(sh, sp, len, k, out_hash, out_pos, cap);
+  }
+  __syncthreads();
+  return n;
+}
+
+// exclusive scan of one int per thread over the CTA; *total gets the sum.
+__device__ inline int cta_excl_scan(int v, int *s_warp, int *total) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  int base = 0;
+  for (int i = 0; i < wid; ++i) base += s_warp[i];
+  int tot = 0;
+  for (int i = 0; i < CTA_NT / 32; ++i) tot += s_warp[i];
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+
+// candidate_processor.cc:283-342 in parallel.  A new cluster always starts where the reference id changes or
+// the gap to the previous hit exceeds e — those boundaries depend only on neighbouring hits, so the list splits
+// into independent segments; the third, state-dependent rule (a cluster that already holds >= n_mm hits and
+// drifts more than e from its best hit) is applied by the thread that scans the segment.  Candidates are
+// written in place (a segment yields at most one candidate per hit consumed) and compacted in hit order.
+// Lists longer than the shared-memory tile use the streaming version above.  `aux` = 3 * sm_cap bytes.
+__device__ inline int cta_cluster_par(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int sm_cap,
+                                      u8 *aux, int *s_ret) {
+  if (nh > sm_cap) return cta_cluster(e, need, n_mm, hits, nh, cpos, ccnt, cap, sm, sm_cap, s_ret);
+  const int tid = threadIdx.x;
+  u8 *flag = aux, *vld = aux + sm_cap, *cnt = aux + 2 * sm_cap;
+  for (int i = tid; i < nh; i += CTA_NT) sm[i] = hits[i];
+  __syncthreads();
+  for (int i = tid; i < nh; i += CTA_NT) {
+    bool b = i == 0;
+    if (!b) {
+      const u64 h = sm[i], q = sm[i - 1];
+      b = (u32)(h >> 32) != (u32)(q >> 32) || (u32)h > (u32)q + (u32)e;
+    }
+    flag[i] = b; vld[i] = 0;
+  }
+  __syncthreads();
+  const int C = (nh + CTA_NT - 1) / CTA_NT;
+  const int r0 = tid * C, r1 = min(nh, r0 + C);
+  for (int i = r0; i < r1; ++i) {
+    if (!flag[i]) continue;
+    int out = i, mcount = 1, eq = 1, best_eq = 1;
+    u64 prev = sm[i], best = prev;
+    int q = i + 1;
+    for (; q < nh && !flag[q]; ++q) {
+      const u64 h = sm[q];
+      if ((u32)mcount >= n_mm && (u32)h > (u32)best + (u32)e) {
+        if (mcount >= need) { sm[out] = best; cnt[out] = (u8)best_eq; vld[out] = 1; ++out; }
+        mcount = 1; eq = 1; best_eq = 1; best = h;
+      } else {
+        if (h == best) { ++eq; ++best_eq; }
+        else if (h == prev) { ++eq; if (eq > best_eq) { best = prev; best_eq = eq; } }
+        else eq = 1;
+        ++mcount;
+      }
+      prev = h;
+    }
+    if (mcount >= need) { sm[out] = best; cnt[out] = (u8)best_eq; vld[out] = 1; ++out; }
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int i = r0; i < r1; ++i) mine += vld[i];
+  __shared__ int s_warp[CTA_NT / 32];
+  int total;
+  int at = cta_excl_scan(mine, s_warp, &total);
+  for (int i = r0; i < r1; ++i)
+    if (vld[i]) { if (at < cap) { cpos[at] = sm[i]; ccnt[at] = cnt[i]; } ++at; }
+  __syncthreads();
+  return total;
+}
+
 __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
   extern __shared__ u64 sm[];  // [sm_cap] sort buffer, then per-minimizer arrays sized by the tier's maxmm
   int *s_off = (int *)(sm + sm_cap);
@@ -1193,12 +1437,14 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
   u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
   u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
-  if (tid == 0) {
-    const int n_mm = gen_minimizers_any(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm);
-    rm.n_mm = n_mm;
-    s_i[0] = n_mm;
-    s_steps = 0;
-    s_i[5] = 0;  // found
+  {
+    const int n0 = cta_minimizers(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm, sm, &s_i[6]);
+    if (tid == 0) {
+      rm.n_mm = n0;
+      s_i[0] = n0;
+      s_steps = 0;
+      s_i[5] = 0;  // found
+    }
   }
   __syncthreads();
   const int n_mm = s_i[0];
@@ -1272,8 +1518,9 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   if (s_i[1] && np > 0 && nn > 0) need = P.min_seeds;
   u64 *cp0 = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cp1 = cp0 + c.cc;
   u8 *cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *cc1 = cc0 + c.cc;
-  const int nc0 = cta_cluster(P.e, need, (u32)n_mm, hits, np, cp0, cc0, c.cc, sm, sm_cap, &s_i[4]);
-  const int nc1 = cta_cluster(P.e, need, (u32)n_mm, hits + np, nn, cp1, cc1, c.cc, sm, sm_cap, &s_i[4]);
+  u8 *aux = (u8 *)(s_c2 + S.caps.maxmm);
+  const int nc0 = cta_cluster_par(P.e, need, (u32)n_mm, hits, np, cp0, cc0, c.cc, sm, sm_cap, aux, &s_i[4]);
+  const int nc1 = cta_cluster_par(P.e, need, (u32)n_mm, hits + np, nn, cp1, cc1, c.cc, sm, sm_cap, aux, &s_i[4]);
   if (tid == 0) {
     if (nc0 > c.cc || nc1 > c.cc) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW);
     else {
@@ -1283,12 +1530,20 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   }
 }
 
-// index.cc:351-489 cooperatively: thread 0 builds the merged windows, threads take minimizers (the binary
-// search state `prev_l` chains the windows of one minimizer, so windows stay sequential per minimizer),
-// hits are appended with a shared counter (order is irrelevant: they are sorted next).
+// index.cc:351-489 cooperatively.  Thread 0 builds the merged windows.  For a multi-occurrence minimizer the
+// reference runs, per window, a binary search that starts at the previous window's last probe (`prev_l`) and
+// then walks the occurrence list from that last probe — so the result depends on the probe path.  The path is
+// reproduced without touching memory: comparisons against a sorted list only depend on where the probe lies
+// relative to LB = first entry >= window start and LB+E (entries equal to it).  So
+//   phase 1 (all threads, one (minimizer, window) each): LB, E and UB = first entry > window end (3 searches);
+//   phase 2 (one thread per minimizer): replay the chained searches arithmetically -> first emitted index;
+//   phase 3 (all threads): emit [first, max(first, UB)) with a shared counter (order is irrelevant: sorted next).
+#define RESCUE_GROUP 8
+#define RESCUE_MAXWIN 300
 __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv, const u32 *mmp,
                                  const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm, int sm_cap,
-                                 u64 *win_lo, u64 *win_hi, int *s_i, int *nh_out) {
+                                 u64 *win_lo, u64 *win_hi, int *s_i, int *nh_out, int *s_lb, u8 *s_eq, int *s_ub) {
+  int *s_first = s_lb;  // phase 2 overwrites LB with the first emitted index (row-private, read before written)
   const int tid = threadIdx.x;
   if (tid == 0) {
     int max_cnt = 0, n_best = 0;
@@ -1316,39 +1571,72 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
   *nh_out = 0;
   if (s_i[1]) { __syncthreads(); return -max_cnt; }
   const int nw = s_i[2];
+  // singletons: one candidate each
   for (int mi = tid; mi < n_mm; mi += CTA_NT) {
-    const u32 kind = mmp[mi] >> 30;
-    if (kind == 0) continue;
-    const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
-    const u64 val = mmv[mi];
+    if ((mmp[mi] >> 30) != 1) continue;
     bool same;
-    if (kind == 1) {
-      const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
-      if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
-      continue;
-    }
-    const u32 off = (u32)(val >> 32), n = (u32)val;
-    int prev_l = 0;
-    for (int bi = 0; bi < nw; ++bi) {
+    const u64 cp = hit_to_candidate(P.k, mmv[mi], (mmp[mi] & 0x3FFFFFFFu) >> 1, mmp[mi] & 1u, &same);
+    if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
+  }
+  // multi-occurrence minimizers in groups of RESCUE_GROUP
+  for (int g0 = 0; g0 < n_mm; g0 += RESCUE_GROUP) {
+    const int gn = min(RESCUE_GROUP, n_mm - g0);
+    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 1
+      const int gi = t / nw, bi = t % nw, mi = g0 + gi;
+      if ((mmp[mi] >> 30) != 2) continue;
+      const u64 val = mmv[mi];
+      const u64 *O = ix.occ + (u32)(val >> 32);
+      const int n = (int)(u32)val;
       const u64 lo = win_lo[bi], hi = win_hi[bi];
-      int l = prev_l, mid = 0, r = (int)n - 1;
-      while (l <= r) {
-        mid = (l + r) / 2;
-        const u64 p = __ldg(&ix.occ[off + mid]) >> 1;
-        if (p < lo) l = mid + 1;
-        else if (p > lo) r = mid - 1;
-        else break;
+      int a = 0, b = n;
+      while (a < b) { const int m = (a + b) >> 1; if ((__ldg(&O[m]) >> 1) < lo) a = m + 1; else b = m; }
+      const int lb = a;
+      // entries equal to `lo` and entries inside the window are few: gallop from LB instead of bisecting [LB, n)
+      auto gallop_le = [&](int from, u64 bound) {  // first index >= from with (O[idx] >> 1) > bound
+        int step = 1, lo_i = from, hi_i = from;
+        while (hi_i < n && (__ldg(&O[hi_i]) >> 1) <= bound) { lo_i = hi_i + 1; hi_i += step; step <<= 1; }
+        if (hi_i > n) hi_i = n;
+        while (lo_i < hi_i) { const int m = (lo_i + hi_i) >> 1; if ((__ldg(&O[m]) >> 1) <= bound) lo_i = m + 1; else hi_i = m; }
+        return lo_i;
+      };
+      a = gallop_le(lb, lo);
+      const int eq = a - lb;
+      a = gallop_le(a, hi);
+      s_lb[gi * RESCUE_MAXWIN + bi] = lb; s_eq[gi * RESCUE_MAXWIN + bi] = (u8)min(eq, 255); s_ub[gi * RESCUE_MAXWIN + bi] = a;
+    }
+    __syncthreads();
+    if (tid < gn && (mmp[g0 + tid] >> 30) == 2) {  // phase 2: index.cc:443-459 replayed on (LB, E)
+      const int n = (int)(u32)mmv[g0 + tid];
+      int prev_l = 0;
+      for (int bi = 0; bi < nw; ++bi) {
+        const int lb = s_lb[tid * RESCUE_MAXWIN + bi], ue = lb + s_eq[tid * RESCUE_MAXWIN + bi];
+        int l = prev_l, mid = 0, r = n - 1;
+        while (l <= r) {
+          mid = (l + r) / 2;
+          if (mid < lb) l = mid + 1;
+          else if (mid >= ue) r = mid - 1;
+          else break;
+        }
+        prev_l = mid;
+        s_first[tid * RESCUE_MAXWIN + bi] = mid;
       }
-      prev_l = mid;
-      for (u32 oi = (u32)mid; oi < n; ++oi) {
-        const u64 rh = __ldg(&ix.occ[off + oi]);
-        if ((rh >> 1) > hi) break;
-        const u64 cp = hit_to_candidate(P.k, rh, rpos, rstrand, &same);
+    }
+    __syncthreads();
+    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 3
+      const int gi = t / nw, bi = t % nw, mi = g0 + gi;
+      if ((mmp[mi] >> 30) != 2) continue;
+      const u64 val = mmv[mi];
+      const u64 *O = ix.occ + (u32)(val >> 32);
+      const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
+      const int first = s_first[gi * RESCUE_MAXWIN + bi], end = max(first, s_ub[gi * RESCUE_MAXWIN + bi]);
+      for (int oi = first; oi < end; ++oi) {
+        bool same;
+        const u64 cp = hit_to_candidate(P.k, __ldg(&O[oi]), rpos, rstrand, &same);
         if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   const int nh = s_i[3];
   *nh_out = nh;
   if (tid == 0) {
@@ -1364,7 +1652,9 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
 
 __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap) {
   extern __shared__ u64 sm[];
-  __shared__ u64 win_lo[300], win_hi[300];
+  __shared__ u64 win_lo[RESCUE_MAXWIN], win_hi[RESCUE_MAXWIN];
+  __shared__ int s_lb[RESCUE_GROUP * RESCUE_MAXWIN], s_ub[RESCUE_GROUP * RESCUE_MAXWIN];
+  __shared__ u8 s_eq[RESCUE_GROUP * RESCUE_MAXWIN];
   __shared__ int s_i[8];
   __shared__ int s_flag[4];
   const int slot = blockIdx.x, tid = threadIdx.x;
@@ -1403,19 +1693,19 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
     bool ovf = false;
     if (ot.n_cand[0] > 0) {
       int nh;
-      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh);
+      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh, s_lb, s_eq, s_ub);
       if (nh > c.hc) ovf = true;
       else {
-        const int na = cta_cluster(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, sm_cap, &s_i[4]);
+        const int na = cta_cluster_par(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, sm_cap, (u8 *)(sm + sm_cap), &s_i[4]);
         if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[1] = na;
       }
     }
     if (!ovf && ot.n_cand[1] > 0) {
       int nh;
-      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh);
+      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh, s_lb, s_eq, s_ub);
       if (nh > c.hc) ovf = true;
       else {
-        const int na = cta_cluster(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, sm_cap, &s_i[4]);
+        const int na = cta_cluster_par(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, sm_cap, (u8 *)(sm + sm_cap), &s_i[4]);
         if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[0] = na;
       }
     }

@@ -143,6 +143,9 @@ int cmx_stage_probe(cmx_ctx *ctx, const uint64_t *hashes, uint64_t n, uint8_t *f
  * patterns n*(read_len+2e) bytes, texts n*read_len bytes. */
 int cmx_stage_banded_align(cmx_ctx *ctx, int e, int read_len, const char *patterns, const char *texts,
                            uint64_t n, int32_t *num_errors, int32_t *end_pos);
+/* The overflow tiers' CTA-cooperative bitonic sort on n keys (tags != NULL: (count desc, position asc) candidate
+ * order, mapping_metadata.h:65-68 / candidate.h:23-33); sm_cap = shared-memory tile (power of two <= 4096). */
+int cmx_stage_cta_sort(cmx_ctx *ctx, uint64_t *keys, uint8_t *tags, uint32_t n, uint32_t sm_cap);
 /* Per-pair counters after a full cmx_map_batch_pe (same fields as the oracle's trace). */
 typedef struct {
   int32_t n_minimizers[2];
@@ -161,6 +164,7 @@ int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs);
 /* Kernel timing of the last cmx_map_batch_pe (CUDA events on the launching stream), in ms. */
 typedef struct {
   float h2d_ms, seed_ms, pair_candidates_ms, verify_ms, pairing_ms, select_ms, emit_ms, d2h_ms, total_ms;
+  float minimizer_ms, probe_ms, cluster_ms; /* tier-0 parts of seed_ms (prep + these three + overflow tiers) */
   uint64_t n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_launches;
   uint64_t tier_pairs[3];      /* pairs processed per scratch tier */
   uint64_t escalations[8];     /* tier-0 escalations by cause (see Counters::ovf_reason) */

@@ -133,6 +133,20 @@ def test_stage_banded_align_equals_oracle(synth, e, L):
             assert ep.value == endp[i]
 
 
+@pytest.mark.parametrize("n,cap", [(1, 64), (2, 64), (63, 64), (64, 64), (65, 64), (1000, 256), (4096, 4096), (4097, 4096), (20000, 1024), (65536, 4096), (50001, 2048)])
+def test_cta_sort_matches_numpy(n, cap):
+    m = cb.Mapper(cb.make_params("", max_read_length=64))
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    keys[rng.integers(0, n, n // 3)] = keys[0]  # duplicates
+    got, _ = m.stage_cta_sort(keys, sm_cap=cap)
+    assert np.array_equal(got, np.sort(keys))
+    tags = rng.integers(1, 6, n).astype(np.uint8)
+    gk, gt = m.stage_cta_sort(keys, tags, sm_cap=cap)
+    order = np.lexsort((keys, 255 - tags.astype(np.int64)))  # count descending, then position ascending
+    assert np.array_equal(gk, keys[order]) and np.array_equal(gt, tags[order])
+
+
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_map_batch_records_equal_oracle_and_golden(synth, case):
     kw = CASES[case]
