@@ -67,7 +67,8 @@ struct cmx_ctx {
   Counters *ctr = nullptr;
   int *d_count = nullptr;
   Tier tiers[N_TIERS];
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
+  std::vector<cudaEvent_t> ev_up;
   cudaEvent_t ev[10];
   cudaEvent_t ev_sub[2];
   float ms_minimizer = 0, ms_probe = 0, ms_cluster = 0;
@@ -137,6 +138,8 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   ctx->params = *params;
   CU(cudaSetDevice(device));
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
   for (auto &e : ctx->ev_sub) CU(cudaEventCreate(&e));
   CU(cudaMalloc(&ctx->ctr, sizeof(Counters)));
@@ -184,7 +187,10 @@ void cmx_destroy(cmx_ctx *ctx) {
     release(*b);
   for (auto &t : ctx->tiers) { release(t.mem); release(t.ovf_list); }
   for (auto &e : ctx->ev) cudaEventDestroy(e);
+  for (auto &e : ctx->ev_up) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
   delete ctx;
 }
 
@@ -421,16 +427,21 @@ static int upload_batch(cmx_ctx *ctx, const cmx_batch *in, DevBatch *B) {
   return CMX_OK;
 }
 
-int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *user_stream) {
-  if (!ctx || !in || !out) return CMX_ERR_INVALID;
-  if (!ctx->slots || !ctx->ref_seq) return fail(ctx, CMX_ERR_STATE, "index and reference must be uploaded first");
-  const u32 n = in->n_pairs;
+struct BatchAcc {  // per-call accumulators over sub-batches
+  float ms_seed = 0, ms_pc = 0, ms_ver = 0, ms_pair = 0, ms_minimizer = 0, ms_probe = 0, ms_cluster = 0, ms_select = 0, ms_emit = 0;
+  u64 launches = 0, n_overflow = 0;
+  Counters c;
+  u64 tier_pairs[N_TIERS] = {0, 0, 0};
+  int tiers_used = 0;
+  BatchAcc() { memset(&c, 0, sizeof(c)); }
+};
+
+// The whole device pipeline over pairs already resident in HBM; records compacted in read order into `dst`
+// (device).  Synchronous on the context's stream.
+static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64 *total_out, BatchAcc &acc, u32 piece = 0,
+                            const std::vector<cudaEvent_t> *piece_ready = nullptr) {
+  const u32 n = B.n_pairs;
   const int mb = ctx->params.max_num_best_mappings;
-  out->n_records = 0; out->n_mapped_pairs = out->n_uniquely_mapped_pairs = out->n_candidates = out->n_overflow_pairs = 0;
-  if (n == 0) return CMX_OK;
-  if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
-  CU(cudaSetDevice(ctx->device));
-  (void)user_stream;  // the context's own stream is used; the call is synchronous
   cudaStream_t st = ctx->stream;
   const DevParams P = make_dev_params(ctx);
   DevIndex ix;
@@ -439,19 +450,12 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   R.seq = ctx->ref_seq; R.off = ctx->ref_off; R.len = ctx->ref_len; R.n_seq = ctx->n_seq;
   MapqTables T;
   T.inv_log = ctx->inv_log; T.pen_thr = ctx->pen_thr;
-  DevBatch B;
-  CU(cudaEventRecord(ctx->ev[0], st));
-  int rc = upload_batch(ctx, in, &B);
-  if (rc) return rc;
   CU(ensure(ctx->nbest, (size_t)n * 4)); CU(ensure(ctx->sel, (size_t)n * mb * 4));
   CU(ensure(ctx->out_rec, (size_t)n * mb * sizeof(OutRecord))); CU(ensure(ctx->out_n, (size_t)(n + 1) * 4));
   CU(ensure(ctx->offs, (size_t)(n + 1) * 8));
   CU(cudaMemsetAsync(ctx->nbest.p, 0, (size_t)n * 4, st));
   CU(cudaMemsetAsync(ctx->out_n.p, 0, (size_t)(n + 1) * 4, st));
   CU(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), st));
-  CU(cudaEventRecord(ctx->ev[1], st));
-  float ms_seed = 0, ms_pc = 0, ms_ver = 0, ms_pair = 0;
-  u64 launches = 0;
   int n_slots = (int)n;
   const int *pair_list = nullptr;
   int tiers_used = 0;
@@ -463,9 +467,26 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     const Scratch S = tier.view;
     cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6], e2 = ctx->ev[7], e3 = ctx->ev[8], e4 = ctx->ev[9];
     CU(cudaEventRecord(e0, st));
-    prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
+    if (t == 0 && piece_ready) {
+      // reads arrive in pieces on the upload stream: length filter / trimming and minimizers start on a piece as
+      // soon as it has landed, the rest of the upload hides behind them
+      for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += piece) {
+        const u32 np = std::min(piece, n - p0);
+        CU(cudaStreamWaitEvent(st, (*piece_ready)[q], 0));
+        Scratch V = S;
+        V.n_slots = (int)np; V.rmeta += 2 * (size_t)p0; V.pmeta += p0;
+        V.mm_hash += 2 * (size_t)p0 * S.caps.maxmm; V.mm_val += 2 * (size_t)p0 * S.caps.maxmm; V.mm_pos += 2 * (size_t)p0 * S.caps.maxmm;
+        DevBatch Bq = B;
+        Bq.off1 += p0; Bq.off2 += p0; Bq.n_pairs = np;
+        prep_kernel<<<(np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V);
+        minimizer_kernel<<<(2 * np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V, ctx->ctr);
+        acc.launches += 2;
+      }
+    } else {
+      prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
+      if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, ctx->ctr);
+    }
     if (t == 0) {
-      minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, ctx->ctr);
       CU(cudaEventRecord(ctx->ev_sub[0], st));
       probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, ctx->ctr);  // persistent: 8 CTAs per SM
       CU(cudaEventRecord(ctx->ev_sub[1], st));
@@ -492,21 +513,21 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
       pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 9, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
       CU(cudaEventRecord(e4, st));
     }
-    launches += (t == 0 ? 8 : 6);
+    acc.launches += (t == 0 ? 8 : 6);
     CU(ensure(tier.ovf_list, (size_t)n_slots * 4));
     CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), st));
     collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, ctx->d_count);
-    launches += 1;
+    acc.launches += 1;
     int n_ovf = 0;
     CU(cudaMemcpyAsync(&n_ovf, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     float f;
-    cudaEventElapsedTime(&f, e0, e1); ms_seed += f;
-    if (t == 0) { cudaEventElapsedTime(&ctx->ms_minimizer, e0, ctx->ev_sub[0]); cudaEventElapsedTime(&ctx->ms_probe, ctx->ev_sub[0], ctx->ev_sub[1]); cudaEventElapsedTime(&ctx->ms_cluster, ctx->ev_sub[1], e1); }
-    cudaEventElapsedTime(&f, e1, e2); ms_pc += f;
-    cudaEventElapsedTime(&f, e2, e3); ms_ver += f;
-    cudaEventElapsedTime(&f, e3, e4); ms_pair += f;
+    cudaEventElapsedTime(&f, e0, e1); acc.ms_seed += f;
+    if (t == 0) { cudaEventElapsedTime(&f, e0, ctx->ev_sub[0]); acc.ms_minimizer += f; cudaEventElapsedTime(&f, ctx->ev_sub[0], ctx->ev_sub[1]); acc.ms_probe += f; cudaEventElapsedTime(&f, ctx->ev_sub[1], e1); acc.ms_cluster += f; }
+    cudaEventElapsedTime(&f, e1, e2); acc.ms_pc += f;
+    cudaEventElapsedTime(&f, e2, e3); acc.ms_ver += f;
+    cudaEventElapsedTime(&f, e3, e4); acc.ms_pair += f;
     tiers_used = t + 1;
     if (n_ovf > 0 && t + 1 < N_TIERS) {
       // deterministic order for the next tier: sort the pair list (atomic append order is arbitrary)
@@ -534,45 +555,118 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     const Scratch S = ctx->tiers[t].view;
     emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutRecord *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
   }
-  launches += 1 + tiers_used;
+  acc.launches += 1 + tiers_used;
   // read-order compaction
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
   CU(ensure(ctx->cub_tmp, tmp_bytes));
   // out_n has n entries plus one trailing zero so that offs[n] = total
   cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
-  OutRecord *dst;
-  if (out->on_device) dst = (OutRecord *)out->records;
-  else { CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)ctx->out_compact.p; }
   compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)ctx->out_rec.p, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, dst);
-  launches += 2;
-  CU(cudaEventRecord(ctx->ev[4], st));
+  acc.launches += 2;
   u64 total = 0;
+  CU(cudaEventRecord(ctx->ev[4], st));
   CU(cudaMemcpyAsync(&total, (u64 *)ctx->offs.p + n, 8, cudaMemcpyDeviceToHost, st));
   Counters hc;
   CU(cudaMemcpyAsync(&hc, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (!out->on_device && total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
-  CU(cudaEventRecord(ctx->ev[5], st));
-  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  float f;
+  cudaEventElapsedTime(&f, ctx->ev[2], ctx->ev[3]); acc.ms_select += f;
+  cudaEventElapsedTime(&f, ctx->ev[3], ctx->ev[4]); acc.ms_emit += f;
+  {
+    u64 *a = (u64 *)&acc.c;
+    const u64 *b = (const u64 *)&hc;
+    for (size_t i = 0; i < sizeof(Counters) / 8; ++i) a[i] += b[i];
+  }
+  for (int t = 0; t < N_TIERS; ++t) if (t < tiers_used) acc.tier_pairs[t] += (u64)ctx->tiers[t].n_slots;
+  acc.tiers_used = std::max(acc.tiers_used, tiers_used);
+  acc.n_overflow += n_overflow_final;
+  *total_out = total;
+  ctx->last_tiers_used = tiers_used;
+  return CMX_OK;
+}
+
+int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *user_stream) {
+  if (!ctx || !in || !out) return CMX_ERR_INVALID;
+  if (!ctx->slots || !ctx->ref_seq) return fail(ctx, CMX_ERR_STATE, "index and reference must be uploaded first");
+  const u32 n = in->n_pairs;
+  const int mb = ctx->params.max_num_best_mappings;
+  out->n_records = 0; out->n_mapped_pairs = out->n_uniquely_mapped_pairs = out->n_candidates = out->n_overflow_pairs = 0;
+  if (n == 0) return CMX_OK;
+  if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
+  CU(cudaSetDevice(ctx->device));
+  (void)user_stream;  // the context's own streams are used; the call is synchronous
+  cudaStream_t st = ctx->stream;
+  BatchAcc acc;
+  u64 total = 0;
+  float ms_h2d = 0, ms_d2h = 0;
+  CU(cudaEventRecord(ctx->ev[0], st));
+  const u32 bs = (u32)ctx->params.batch_size;
+  if (in->on_device || out->on_device || n <= bs) {
+    // single pass: upload (if needed), map, download
+    DevBatch B;
+    int rc = upload_batch(ctx, in, &B);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], st));
+    OutRecord *dst;
+    if (out->on_device) dst = (OutRecord *)out->records;
+    else { CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)ctx->out_compact.p; }
+    rc = run_device_batch(ctx, B, dst, &total, acc);
+    if (rc) return rc;
+    cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);
+    CU(cudaEventRecord(ctx->ev[1], st));
+    if (!out->on_device && total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
+    ctx->last_n_pairs = n;
+  } else {
+    // host buffers, several reference batches: reads are uploaded in pieces (one per reference batch) on the
+    // upload stream; the first kernels start on piece 0 while the other pieces are still in flight.
+    const size_t b1 = in->off1[n], b2 = in->off2[n];
+    CU(ensure(ctx->seq1, b1 + 64)); CU(ensure(ctx->seq2, b2 + 64));
+    CU(ensure(ctx->off1, (size_t)(n + 1) * 4)); CU(ensure(ctx->off2, (size_t)(n + 1) * 4));
+    CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord)));
+    const u32 n_sub = (n + bs - 1) / bs;
+    while (ctx->ev_up.size() < n_sub) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
+    CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
+    CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
+    for (u32 s = 0; s < n_sub; ++s) {
+      const u32 p0 = s * bs, p1 = std::min(n, p0 + bs);
+      CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, ctx->up_stream));
+      CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, ctx->up_stream));
+      CU(cudaEventRecord(ctx->ev_up[s], ctx->up_stream));
+    }
+    DevBatch B;
+    B.seq1 = (const u8 *)ctx->seq1.p; B.off1 = (const u32 *)ctx->off1.p;
+    B.seq2 = (const u8 *)ctx->seq2.p; B.off2 = (const u32 *)ctx->off2.p;
+    B.n_pairs = n; B.first_read_id = in->first_read_id;
+    OutRecord *dst = (OutRecord *)ctx->out_compact.p;
+    const int rc = run_device_batch(ctx, B, dst, &total, acc, bs, &ctx->ev_up);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], st));
+    if (total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
+    ctx->last_n_pairs = n;
+  }
   CU(cudaGetLastError());
   out->n_records = total;
-  out->n_mapped_pairs = hc.n_mapped; out->n_uniquely_mapped_pairs = hc.n_unique; out->n_candidates = hc.n_candidates;
-  out->n_overflow_pairs = n_overflow_final;
+  out->n_mapped_pairs = acc.c.n_mapped; out->n_uniquely_mapped_pairs = acc.c.n_unique; out->n_candidates = acc.c.n_candidates;
+  out->n_overflow_pairs = acc.n_overflow;
   cmx_timing &tm = ctx->timing;
   memset(&tm, 0, sizeof(tm));
-  cudaEventElapsedTime(&tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-  tm.seed_ms = ms_seed; tm.minimizer_ms = ctx->ms_minimizer; tm.probe_ms = ctx->ms_probe; tm.cluster_ms = ctx->ms_cluster; tm.pair_candidates_ms = ms_pc; tm.verify_ms = ms_ver; tm.pairing_ms = ms_pair;
-  cudaEventElapsedTime(&tm.select_ms, ctx->ev[2], ctx->ev[3]);
-  cudaEventElapsedTime(&tm.emit_ms, ctx->ev[3], ctx->ev[4]);
-  cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[4], ctx->ev[5]);
+  tm.h2d_ms = ms_h2d; tm.d2h_ms = ms_d2h;
+  tm.seed_ms = acc.ms_seed; tm.minimizer_ms = acc.ms_minimizer; tm.probe_ms = acc.ms_probe; tm.cluster_ms = acc.ms_cluster;
+  tm.pair_candidates_ms = acc.ms_pc; tm.verify_ms = acc.ms_ver; tm.pairing_ms = acc.ms_pair; tm.select_ms = acc.ms_select; tm.emit_ms = acc.ms_emit;
   cudaEventElapsedTime(&tm.total_ms, ctx->ev[0], ctx->ev[5]);
-  tm.n_minimizers = hc.n_minimizers; tm.n_probe_steps = hc.n_probe_steps; tm.n_found = hc.n_found; tm.n_occ_reads = hc.n_occ_reads;
-  tm.n_verified = hc.n_verified; tm.n_launches = launches;
-  for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = t < tiers_used ? (u64)ctx->tiers[t].n_slots : 0;
-  for (int r = 0; r < 8; ++r) tm.escalations[r] = hc.ovf_reason[r];
-  ctx->last_n_pairs = n; ctx->last_tiers_used = tiers_used;
-  if (n_overflow_final) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)n_overflow_final);
+  tm.n_minimizers = acc.c.n_minimizers; tm.n_probe_steps = acc.c.n_probe_steps; tm.n_found = acc.c.n_found; tm.n_occ_reads = acc.c.n_occ_reads;
+  tm.n_verified = acc.c.n_verified; tm.n_launches = acc.launches;
+  for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = acc.tier_pairs[t];
+  for (int r = 0; r < 8; ++r) tm.escalations[r] = acc.c.ovf_reason[r];
+  if (acc.n_overflow) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)acc.n_overflow);
   return CMX_OK;
 }
 
