@@ -157,11 +157,12 @@ struct ReadState {  // mapping_metadata.h:24-175
   std::vector<u64> hits[2];     // [0]=positive [1]=negative
   std::vector<Cand> cand[2], buf[2];
   std::vector<Draft> map[2];
+  std::vector<int> split[2];  // split_sites_, parallel to map[] (draft_mapping_generator.cc:550-554)
   int min_err, second_min_err, n_best, n_second_best;
   u32 rep_len;
   void reset() {
     mm.clear();
-    for (int s = 0; s < 2; ++s) { hits[s].clear(); cand[s].clear(); buf[s].clear(); map[s].clear(); }
+    for (int s = 0; s < 2; ++s) { hits[s].clear(); cand[s].clear(); buf[s].clear(); map[s].clear(); split[s].clear(); }
     rep_len = 0;
   }
 };
@@ -449,6 +450,96 @@ static void banded_traceback(int e, int min_err, const char *pat, const char *te
   }
 }
 
+// alignment.cc:197-283 — banded Myers that stops when the band-bottom error count exceeds 2e (the read may be
+// chimeric); returns the best distance over the band at the stop column, the reference end offset (negated when
+// the stop is "at the beginning", :277-280) and the number of read bases consumed.
+static int align_dropoff(int e, const char *pat, const char *text, int L, int *end_pos, int *read_len_out) {
+  u32 Peq[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 2 * e; ++i) Peq[code(pat[i])] |= (1u << i);
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0, pVP = 0, pVN = 0;
+  int err = 0, perr = 0, i = 0, fail_beginning = 0;
+  for (; i < L; ++i) {
+    Peq[code(pat[i + 2 * e])] |= hi;
+    u32 X = Peq[code(text[i])] | VN;
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    pVN = VN; pVP = VP;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    perr = err;
+    err += 1 - (int)(D0 & 1u);
+    if (err > 2 * e) { if (i < 4 * e && i < L / 2) fail_beginning = 1; break; }
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  if (i < L) { err = perr; VN = pVN; VP = pVP; }
+  const int band_start = i - 1;
+  int best = err;
+  *read_len_out = i;
+  *end_pos = band_start;
+  for (int j = 0; j < 2 * e; ++j) {
+    err += (int)((VP >> j) & 1u);
+    err -= (int)((VN >> j) & 1u);
+    if (err < best || (err == best && j + 1 == e)) { best = err; *end_pos = band_start + 1 + j; }
+  }
+  if (fail_beginning || (L > 60 && *end_pos + 1 - e - best < 30)) *end_pos = -*end_pos;
+  return best;
+}
+// alignment.cc:285-376 — the same from the 3' end (used for the reverse-complement strand).
+static int align_dropoff_3end(int e, const char *pat, const char *text, int L, int *end_pos, int *read_len_out) {
+  u32 Peq[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 2 * e; ++i) Peq[code(pat[L + 2 * e - 1 - i])] |= (1u << i);
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0, pVP = 0, pVN = 0;
+  int err = 0, perr = 0, i = 0, fail_beginning = 0;
+  for (; i < L; ++i) {
+    Peq[code(pat[L - 1 - i])] |= hi;
+    u32 X = Peq[code(text[L - 1 - i])] | VN;
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    pVN = VN; pVP = VP;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    perr = err;
+    err += 1 - (int)(D0 & 1u);
+    if (err > 2 * e) { if (i < 4 * e && i < L / 2) fail_beginning = 1; break; }
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  if (i < L) { err = perr; VN = pVN; VP = pVP; }
+  const int band_start = i - 1;
+  int best = err;
+  *read_len_out = i;
+  *end_pos = band_start;
+  for (int j = 0; j < 2 * e; ++j) {
+    err += (int)((VP >> j) & 1u);
+    err -= (int)((VN >> j) & 1u);
+    if (err < best || (err == best && j + 1 == e)) { best = err; *end_pos = band_start + (1 + j); }
+  }
+  if (fail_beginning || (L > 60 && *end_pos + 1 - e - best < 30)) *end_pos = -*end_pos;
+  return best;
+}
+// alignment.cc:24-83 (n_cigar == 0 on the BED/pairs path): extend an exact match into the skipped 5' gap.
+// `ref` is the whole reference sequence (NUL padded), `read` NUL terminated.
+static int adjust_gap_beginning(int strand, const char *ref, const char *read, int *gap, int read_end, int ref_start, int ref_end) {
+  int i, j;
+  if (strand == 0) {
+    if (*gap <= 0) return ref_start;
+    for (i = *gap - 1, j = ref_start - 1; i >= 0 && j >= 0; --i, --j)
+      if (read[i] != ref[j] && read[i] != ref[j] - 'a' + 'A') break;
+    *gap = i + 1;
+    return j + 1;
+  }
+  if (*gap <= 0) return ref_end;
+  for (i = read_end + 1, j = ref_end + 1; read[i] && ref[j]; ++i, ++j)
+    if (read[i] != ref[j] && read[i] != ref[j] - 'a' + 'A') break;
+  *gap = *gap + i - (read_end + 1);
+  return j - 1;
+}
+
 static inline bool valid_cand(int e, u32 ref_len, u32 pos, u32 L) {  // draft_mapping_generator.cc:59-70
   return !(pos < (u32)e || pos >= ref_len || pos + L + (u32)e >= ref_len);
 }
@@ -523,9 +614,62 @@ static void verify_read(const orc_params &P, const orc_reference &ref, const cha
   }
 }
 
+// draft_mapping_generator.cc:9-57 + :359-557 with --split-alignment: per-candidate scalar driver, drop-off
+// alignment, optional skip of the first 20-e read bases, num_errors := -(matched length), count-threshold pruning.
+static void verify_read_split(const orc_params &P, const orc_reference &ref, const char *read, const std::string &neg, u32 L, ReadState &rs) {
+  const int e = P.error_threshold;
+  rs.min_err = e + 1; rs.n_best = 0; rs.second_min_err = e + 1; rs.n_second_best = 0;
+  std::sort(rs.cand[0].begin(), rs.cand[0].end(), cand_less);
+  std::sort(rs.cand[1].begin(), rs.cand[1].end(), cand_less);
+  for (int s = 0; s < 2; ++s) {
+    const std::vector<Cand> &cs = rs.cand[s];
+    u32 threshold = 0;
+    for (size_t ci = 0; ci < cs.size(); ++ci) {
+      if (cs[ci].cnt < threshold) break;
+      const u32 rid = (u32)(cs[ci].pos >> 32);
+      const u32 pos = s == 0 ? (u32)cs[ci].pos : (u32)cs[ci].pos - L + 1;
+      if (!valid_cand(e, ref.lens[rid], pos, L)) continue;
+      int endp = L, gap = 0, nerr = 0, actual = 0, rml = 0;
+      const int allow_gap = 20 - e;
+      const char *win = ref.seqs[rid].data() + pos - e;
+      if (s == 0) {
+        nerr = align_dropoff(e, win, read, L, &endp, &rml);
+        if (endp < 0 && allow_gap > 0) {
+          const int b_err = nerr, b_end = -endp, b_rml = rml;
+          nerr = align_dropoff(e, win + allow_gap, read + allow_gap, L - allow_gap, &endp, &rml);
+          if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
+          else { gap = allow_gap; endp += gap; rml += gap; }
+        }
+      } else {
+        nerr = align_dropoff_3end(e, win, neg.data(), L, &endp, &rml);
+        if (endp < 0 && allow_gap > 0) {
+          const int b_err = nerr, b_end = -endp, b_rml = rml;
+          nerr = align_dropoff_3end(e, win, neg.data(), L - allow_gap, &endp, &rml);
+          if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
+          else { gap = allow_gap; endp += gap; rml += gap; }
+        }
+      }
+      if (endp + 1 - e - nerr - gap >= 30) { actual = nerr; nerr = -(endp - e - nerr - gap); }
+      else { nerr = e + 1; actual = e + 1; }
+      // (GetLongestMatchLength, :474-483, only feeds a comparison between two per-iteration locals that are both
+      //  zero-initialised inside this loop — it cannot change anything)
+      if (nerr <= e) {
+        if (nerr < rs.min_err) {
+          rs.second_min_err = rs.min_err; rs.n_second_best = rs.n_best; rs.min_err = nerr; rs.n_best = 1;
+          threshold = cs.size() > 50 ? cs[ci].cnt : cs[ci].cnt / 2;
+        } else if (nerr == rs.min_err) rs.n_best++;
+        else if (nerr == rs.second_min_err) rs.n_second_best++;
+        else if (nerr < rs.second_min_err) { rs.n_second_best = 1; rs.second_min_err = nerr; }
+        rs.map[s].push_back({nerr, s == 0 ? cs[ci].pos - e + endp : cs[ci].pos - gap});
+        rs.split[s].push_back(((actual & 0xff) << 24) | ((gap & 0xff) << 16) | (rml & 0xffff));
+      }
+    }
+  }
+}
+
 struct PairState {
   int min_sum, second_min_sum, n_best, n_second_best;
-  std::vector<std::pair<u32, u32>> best[2];  // [0]=F1R2, [1]=F2R1
+  std::vector<std::pair<u32, u32>> best[4];  // [0]=F1R2, [1]=F2R1, [2]=F1F2, [3]=R1R2 (paired_end_mapping_metadata.h:66-98)
 };
 
 // mapping_generator.h:346-484 (non-split branch).
@@ -632,6 +776,88 @@ static void ref_span(const orc_params &P, const orc_reference &ref, const Draft 
   end = rp;
 }
 
+// mapping_generator.h:389-415 — split alignment pairs every best mapping of mate 1 with every best mapping of mate 2.
+static void pair_dir_split(const ReadState rs[2], int s1, int s2, PairState &ps, std::vector<std::pair<u32, u32>> &best) {
+  const std::vector<Draft> &m1 = rs[0].map[s1], &m2 = rs[1].map[s2];
+  if (m1.empty() || m2.empty()) return;
+  for (u32 i1 = 0; i1 < m1.size(); ++i1) {
+    if (m1[i1].err != rs[0].min_err) continue;
+    for (u32 i2 = 0; i2 < m2.size(); ++i2) {
+      if (m2[i2].err != rs[1].min_err) continue;
+      best.push_back({i1, i2});
+      ps.min_sum = rs[0].min_err + rs[1].min_err;
+      ps.n_best++;
+    }
+  }
+}
+
+// mapping_generator.h:920-1022 with split_alignment (num_errors = -(matched length)).
+static uint8_t mapq_se_split(const orc_params &P, int strand, int num_errors, uint16_t aln_len, int read_len, int max_diff, const ReadState &rs) {
+  const int coef_len = 50;
+  const int coef_frac = log(coef_len);
+  double ident = 1 - (double)num_errors / aln_len;
+  ident = (double)(-num_errors) / aln_len;
+  if (ident > 1) ident = 1;
+  int mapq = 0;
+  int second = rs.second_min_err;
+  if (rs.n_best > 1) {
+  } else {
+    if (second > num_errors + max_diff) second = num_errors + max_diff;
+    double tmp = aln_len < coef_len ? 1.0 : coef_frac / log(aln_len);
+    tmp *= ident * ident;
+    mapq = 5 * 6.02 * (second - num_errors) * tmp * tmp + 0.499;
+  }
+  if (rs.n_second_best > 0) mapq -= (int)(4.343 * log(rs.n_second_best + 1) + 0.499);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  if (rs.rep_len > 0) {
+    double frac = rs.rep_len / (double)read_len;
+    if (rs.rep_len >= (u32)read_len) frac = 0.999;
+    if (ident <= 0.95) mapq = mapq * (1 - sqrt(frac)) + 0.499;
+    else if (ident <= 0.97) mapq = mapq * (1 - frac) + 0.499;
+    else if (ident >= 0.999) mapq = mapq * (1 - frac * frac * frac * frac) + 0.499;
+    else mapq = mapq * (1 - frac * frac) + 0.499;
+  }
+  if (aln_len < read_len - P.error_threshold && second != num_errors) {
+    if (rs.rep_len >= aln_len && rs.rep_len < (u32)read_len && aln_len < read_len / 3) mapq = 0;
+    const int diff = second - num_errors;
+    const u32 num_candidates = rs.cand[strand].size();
+    if (second - num_errors <= P.error_threshold * 3 / 4 && num_candidates >= 5) mapq -= (num_candidates / 5 / diff);
+    if (mapq < 0) mapq = 0;
+    if (rs.n_second_best > 0 && second - num_errors <= P.error_threshold * 3 / 4) mapq /= (rs.n_second_best / diff + 1);
+  }
+  return (uint8_t)mapq;
+}
+
+// mapping_generator.h:657-917, BED/pairs branch with split_alignment.
+static void ref_span_split(const orc_params &P, const orc_reference &ref, const Draft &d, int strand, int split_word, const char *read_seq,
+                           int full_len, u32 &start, u32 &end) {
+  const int e = P.error_threshold;
+  const u32 rid = (u32)(d.pos >> 32), rp = (u32)d.pos;
+  const int split_site = split_word & 0xffff;
+  int gap = (split_word >> 16) & 0xff;
+  const int actual = (split_word >> 24) & 0xff;
+  int L = split_site - gap;
+  u32 vws = rp + 1 > (u32)(L + e) ? rp + 1 - L - e : 0;
+  if (rp + e >= ref.lens[rid]) vws = ref.lens[rid] - e - L;
+  const char *rseq = ref.seqs[rid].data();
+  if (strand == 0) {
+    int s = 0;
+    banded_traceback(e, actual, rseq + vws, read_seq + gap, L, &s);
+    if (gap > 0) s = adjust_gap_beginning(0, rseq, read_seq, &gap, L - 1, vws + s, rp) - vws;
+    start = vws + s;
+    end = rp;
+    return;
+  }
+  const int read_start_site = full_len - split_site;
+  int s = e, en = rp - vws + 1;
+  banded_align(e, rseq + vws, read_seq + read_start_site, L, &en);
+  en += 1;
+  if (gap > 0) en = adjust_gap_beginning(1, rseq, read_seq + read_start_site, &gap, L - 1, vws + s, vws + en) - vws + 1;
+  start = vws + s;
+  end = vws + en - 1;
+}
+
 static const bool g_debug = getenv("ORC_DEBUG") != nullptr;
 struct orc_mapper {
   orc_params P;
@@ -724,8 +950,13 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
     tr->repetitive_seed_length[m] = rs[m].rep_len;
   }
   if (!(nc1 > 0 && nc2 > 0)) return 0;
-  verify_read(P, ref, r[0].data(), neg[0], L[0], rs[0]);
-  verify_read(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  if (P.split_alignment) {
+    verify_read_split(P, ref, r[0].data(), neg[0], L[0], rs[0]);
+    verify_read_split(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  } else {
+    verify_read(P, ref, r[0].data(), neg[0], L[0], rs[0]);
+    verify_read(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  }
   if (tr) for (int m = 0; m < 2; ++m) {
     tr->n_pos_mappings[m] = rs[m].map[0].size(); tr->n_neg_mappings[m] = rs[m].map[1].size();
     tr->min_errors[m] = rs[m].min_err; tr->second_min_errors[m] = rs[m].second_min_err;
@@ -735,13 +966,21 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
   // mapping_metadata.h:70-78 sorts by position only; equal positions are interchangeable for the
   // output (the lower-error one is the only one that can be in a best pair), so (pos, err) is used.
   auto by_pos = [](const Draft &a, const Draft &b) { return a.pos != b.pos ? a.pos < b.pos : a.err < b.err; };
-  for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) std::sort(rs[m].map[s].begin(), rs[m].map[s].end(), by_pos);
+  if (!P.split_alignment)  // chromap.h:1099-1106: split alignment keeps verification order (mappings stay aligned with split sites)
+    for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) std::sort(rs[m].map[s].begin(), rs[m].map[s].end(), by_pos);
   const int force = sup != 0 ? 0 : -1;
   // mapping_generator.h:160-253
   PairState ps;
   ps.min_sum = 2 * P.error_threshold + 1; ps.n_best = 0; ps.second_min_sum = ps.min_sum; ps.n_second_best = 0;
-  pair_dir(P, 0, L[0], L[1], rs[0].map[0], rs[1].map[1], ps, ps.best[0]);
-  pair_dir(P, 1, L[0], L[1], rs[0].map[1], rs[1].map[0], ps, ps.best[1]);
+  if (P.split_alignment) {
+    pair_dir_split(rs, 0, 1, ps, ps.best[0]);
+    pair_dir_split(rs, 1, 0, ps, ps.best[1]);
+    pair_dir_split(rs, 0, 0, ps, ps.best[2]);
+    pair_dir_split(rs, 1, 1, ps, ps.best[3]);
+  } else {
+    pair_dir(P, 0, L[0], L[1], rs[0].map[0], rs[1].map[1], ps, ps.best[0]);
+    pair_dir(P, 1, L[0], L[1], rs[0].map[1], rs[1].map[0], ps, ps.best[1]);
+  }
   if (tr) { tr->min_sum_errors = ps.min_sum; tr->second_min_sum_errors = ps.second_min_sum; tr->n_best_pairs = ps.n_best; tr->n_second_best_pairs = ps.n_second_best; }
   if (ps.n_best > P.drop_repetitive_reads) return 0;
   std::vector<int> sel(P.max_num_best_mappings);
@@ -757,23 +996,45 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
   int idx = 0, reported = 0;
   const int to_report = std::min(P.max_num_best_mappings, ps.n_best);
   const uint8_t uniq = (ps.n_best == 1 || rs[0].n_best == 1 || rs[1].n_best == 1) ? 1 : 0;
-  for (int dir = 0; dir < 2 && reported != to_report; ++dir) {  // mapping_generator.h:486-654
-    const int s1 = dir, s2 = 1 - dir;
+  static const int DIR_S1[4] = {0, 1, 0, 1}, DIR_S2[4] = {1, 0, 0, 1};
+  const int n_dirs = P.split_alignment ? 4 : 2;
+  for (int dir = 0; dir < n_dirs && reported != to_report; ++dir) {  // mapping_generator.h:486-654
+    const int s1 = DIR_S1[dir], s2 = DIR_S2[dir];
     const std::vector<Draft> &m1 = rs[0].map[s1], &m2 = rs[1].map[s2];
     for (const auto &bp : ps.best[dir]) {
       const Draft &d1 = m1[bp.first], &d2 = m2[bp.second];
       if (d1.err + d2.err > ps.min_sum) continue;
       if (idx == sel[reported]) {
         u32 st1, en1, st2, en2;
+        uint8_t q;
+        if (P.split_alignment) {
+          ref_span_split(P, ref, d1, s1, rs[0].split[s1][bp.first], s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1);
+          ref_span_split(P, ref, d2, s2, rs[1].split[s2][bp.second], s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2);
+          const uint16_t al1 = en1 - st1 + 1, al2 = en2 - st2 + 1;
+          uint8_t q1 = mapq_se_split(P, s1, d1.err, al1, L[0], 2, rs[0]);
+          uint8_t q2 = mapq_se_split(P, s2, d2.err, al2, L[1], 2, rs[1]);
+          q1 *= 1.2; if (q1 > 60) q1 = 60;   // mapping_generator.h:1171-1179 (no mate mixing under split alignment)
+          q2 *= 1.2; if (q2 > 60) q2 = 60;
+          q = q1 < q2 ? q1 : q2;
+          if (q < 60 && force >= 0 && force < q) q = force;
+          if (reported < cap) {  // mapping_generator.cc:169-210
+            orc_pairs_record &o = reinterpret_cast<orc_pairs_record *>(out)[reported];
+            int rid1 = (u32)(d1.pos >> 32), rid2 = (u32)(d2.pos >> 32);
+            int pos1 = s1 == 0 ? st1 : en1, pos2 = s2 == 0 ? st2 : en2;
+            uint8_t str1 = s1 == 0 ? 1 : 0, str2 = s2 == 0 ? 1 : 0;
+            const bool smaller = rid1 < rid2 || (rid1 == rid2 && pos1 < pos2);  // identity chromosome ranks
+            if (!smaller) { std::swap(rid1, rid2); std::swap(pos1, pos2); std::swap(str1, str2); }
+            o.read_id = read_id; o.rid1 = rid1; o.rid2 = rid2; o.pos1 = pos1; o.pos2 = pos2;
+            o.strand1 = str1; o.strand2 = str2; o.mapq = q; o.is_unique = uniq;
+          }
+          if (++reported == to_report) break;
+          ++idx;
+          continue;
+        }
         ref_span(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1);
         ref_span(P, ref, d2, s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2);
         const uint16_t al1 = en1 - st1 + 1, al2 = en2 - st2 + 1;
-        if (g_debug)  // same fields as the reference's -DCHROMAP_DEBUG line (mapping_generator.h:1038-1071)
-          fprintf(stderr, " rl1:%d rl2:%d pal:%d nal:%d me:%d #bm:%d sme:%d #sbm:%d ne1:%d ne2:%d me1:%d me2:%d #bm1:%d #bm2:%d sme1:%d sme2:%d #sbm1:%d #sbm2:%d idx:%u\n",
-                  (int)rs[0].rep_len, (int)rs[1].rep_len, (int)al1, (int)al2, ps.min_sum, ps.n_best, ps.second_min_sum, ps.n_second_best,
-                  d1.err, d2.err, rs[0].min_err, rs[1].min_err, rs[0].n_best, rs[1].n_best, rs[0].second_min_err, rs[1].second_min_err,
-                  rs[0].n_second_best, rs[1].n_second_best, pair_index);
-        const uint8_t q = mapq_pe(d1.err, d2.err, al1, al2, L[0], L[1], force, ps, rs);
+        q = mapq_pe(d1.err, d2.err, al1, al2, L[0], L[1], force, ps, rs);
         if (reported < cap) {
           orc_pe_record &o = out[reported];
           o.read_id = read_id;
@@ -1017,7 +1278,8 @@ int orc_banded_align(int e, const char *pattern, const char *text, int read_len,
 void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len, int *start_pos) { banded_traceback(e, min_errors, pattern, text, read_len, start_pos); }
 
 orc_mapper *orc_mapper_create(const orc_params *p, const orc_index *ix, const orc_reference *ref) {
-  if (p->split_alignment || p->error_threshold >= 16 || p->output_format != 1) return nullptr;  // BED, non-split only
+  if (p->error_threshold >= 16) return nullptr;
+  if (!((p->output_format == 1 && !p->split_alignment) || (p->output_format == 5 && p->split_alignment))) return nullptr;  // BED or Hi-C pairs
   orc_mapper *m = new orc_mapper;
   m->P = *p; m->ix = ix; m->ref = ref;
   return m;
@@ -1135,6 +1397,47 @@ int64_t orc_format_bed(const orc_reference *ref, const orc_pe_record *recs, int6
   return len;
 }
 
+int64_t orc_postprocess_pairs(const orc_params *p, orc_pairs_record *recs, int64_t n) {
+  // records sit in the bucket of rid1; merge order = (bucket rid, PairsMapping::operator<) (pairs_mapping.h:40-43)
+  std::sort(recs, recs + n, [](const orc_pairs_record &a, const orc_pairs_record &b) {
+    return std::make_tuple(a.rid1, a.rid2, a.pos1, a.pos2, a.mapq, a.read_id) < std::make_tuple(b.rid1, b.rid2, b.pos1, b.pos2, b.mapq, b.read_id);
+  });
+  int64_t o = 0;
+  if (p->remove_pcr_duplicates) {  // mapping_writer.h:234-300 with PairsMapping::operator==
+    int64_t i = 0;
+    while (i < n) {
+      orc_pairs_record keep = recs[i];
+      int64_t j = i + 1;
+      for (; j < n && recs[j].rid1 == recs[i].rid1 && recs[j].pos1 == recs[i].pos1 && recs[j].rid2 == recs[i].rid2 && recs[j].pos2 == recs[i].pos2; ++j)
+        if (recs[j].mapq > keep.mapq) keep = recs[j];
+      if (keep.mapq >= p->mapq_threshold) recs[o++] = keep;
+      i = j;
+    }
+    return o;
+  }
+  for (int64_t i = 0; i < n; ++i) if (recs[i].mapq >= p->mapq_threshold) recs[o++] = recs[i];
+  return o;
+}
+
+int64_t orc_format_pairs(const orc_reference *ref, const orc_pairs_record *recs, int64_t n, const char *const *read_names,
+                         uint32_t first_read_id, char *buf, int64_t cap) {
+  int64_t len = 0;
+  std::string hdr = "## pairs format v1.0.0\n#shape: upper triangle\n";
+  for (size_t i = 0; i < ref->names.size(); ++i) hdr += "#chromsize: " + ref->names[i] + " " + std::to_string(ref->lens[i]) + "\n";
+  hdr += "#columns: readID chrom1 pos1 chrom2 pos2 strand1 strand2 pair_type mapq1 mapq2\n";
+  if (buf && (int64_t)hdr.size() <= cap) memcpy(buf, hdr.data(), hdr.size());
+  len += hdr.size();
+  for (int64_t i = 0; i < n; ++i) {
+    const orc_pairs_record &r = recs[i];
+    const std::string line = std::string(read_names[r.read_id - first_read_id]) + "\t" + ref->names[r.rid1] + "\t" + std::to_string(r.pos1 + 1) + "\t" +
+                             ref->names[r.rid2] + "\t" + std::to_string(r.pos2 + 1) + "\t" + (r.strand1 ? "+" : "-") + "\t" + (r.strand2 ? "+" : "-") +
+                             "\tUU\t" + std::to_string(r.mapq) + "\t" + std::to_string(r.mapq) + "\n";
+    if (buf && len + (int64_t)line.size() <= cap) memcpy(buf + len, line.data(), line.size());
+    len += line.size();
+  }
+  return len;
+}
+
 int orc_run_files(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path,
                   const char *read2_path, const char *out_path, int n_threads, double *mapping_seconds, uint64_t *n_pairs_out) {
   orc_reference *ref = orc_reference_load(ref_path);
@@ -1145,6 +1448,8 @@ int orc_run_files(const orc_params *p, const char *index_path, const char *ref_p
   SeqReader r1, r2;
   if (!r1.open(read1_path) || !r2.open(read2_path)) return -3;
   std::vector<orc_pe_record> recs;
+  std::vector<std::string> names1;  // read-1 names, only kept for pairs output
+  const bool pairs = p->output_format == 5;
   const u32 batch = 500000;  // chromap.h:182
   u32 read_id = 0;
   double secs = 0;
@@ -1159,6 +1464,7 @@ int orc_run_files(const orc_params *p, const char *index_path, const char *ref_p
       while (a && s.empty()) a = r1.next(n, s, q);  // sequence_batch.cc:28-31 skips empty reads
       if (!a) break;
       s1 += s; o1.push_back(s1.size());
+      if (pairs) names1.push_back(n);
       bool b = r2.next(n, s, q);
       while (b && s.empty()) b = r2.next(n, s, q);
       if (!b) { fprintf(stderr, "Numbers of reads don't match!\n"); return -4; }
@@ -1176,10 +1482,23 @@ int orc_run_files(const orc_params *p, const char *index_path, const char *ref_p
     total += cnt;
   }
   r1.close(); r2.close();
-  const int64_t keep = orc_postprocess(p, recs.data(), recs.size());
-  const int64_t bytes = orc_format_bed(ref, recs.data(), keep, nullptr, 0);
-  std::vector<char> text(bytes + 1);
-  orc_format_bed(ref, recs.data(), keep, text.data(), bytes);
+  int64_t bytes;
+  std::vector<char> text;
+  if (pairs) {
+    static_assert(sizeof(orc_pairs_record) == sizeof(orc_pe_record), "record sizes");
+    orc_pairs_record *pr = reinterpret_cast<orc_pairs_record *>(recs.data());
+    const int64_t keep = orc_postprocess_pairs(p, pr, recs.size());
+    std::vector<const char *> nm;
+    for (const auto &x : names1) nm.push_back(x.c_str());
+    bytes = orc_format_pairs(ref, pr, keep, nm.data(), 0, nullptr, 0);
+    text.resize(bytes + 1);
+    orc_format_pairs(ref, pr, keep, nm.data(), 0, text.data(), bytes);
+  } else {
+    const int64_t keep = orc_postprocess(p, recs.data(), recs.size());
+    bytes = orc_format_bed(ref, recs.data(), keep, nullptr, 0);
+    text.resize(bytes + 1);
+    orc_format_bed(ref, recs.data(), keep, text.data(), bytes);
+  }
   FILE *f = fopen(out_path, "wb");
   if (!f) return -5;
   fwrite(text.data(), 1, bytes, f);

@@ -36,7 +36,7 @@ typedef struct {
   int32_t tn5_shift;
   int32_t split_alignment;
   int32_t low_memory_mode;
-  int32_t output_format;  // 1 = BED (only BED is restated)
+  int32_t output_format;  // 1 = BED, 5 = pairs (Hi-C, with split_alignment)
 } orc_params;
 
 void orc_default_params(orc_params *p);
@@ -97,6 +97,16 @@ typedef struct {
   uint16_t negative_alignment_length;
 } orc_pe_record;
 
+// PairsMapping (pairs_mapping.h:11-49) without the read name: what --preset hic emits (mapping_generator.cc:169-210).
+// Written into the same record buffer (24 bytes as well) when output_format == 5 (pairs).
+typedef struct {
+  uint32_t read_id;
+  uint32_t rid1, rid2;
+  uint32_t pos1, pos2;  // 0-based 5' positions, (rid1, pos1) <= (rid2, pos2)
+  uint8_t strand1, strand2;  // 1 = +
+  uint8_t mapq, is_unique;
+} orc_pairs_record;
+
 // Optional per-stage trace of one pair (for stage-level parity tests against the CUDA stages).
 typedef struct {
   // per mate (index 0/1)
@@ -135,6 +145,11 @@ int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint
 // sort / dedup / Tn5 / MAPQ filter, in place.  Returns the number of surviving records, sorted in
 // output order (rid, then record operator<).
 int64_t orc_postprocess(const orc_params *p, orc_pe_record *recs, int64_t n);
+// Pairs post-processing (low-memory merge without dedup: sort by (rid1, rid2, pos1, pos2, mapq, read_id), MAPQ filter)
+int64_t orc_postprocess_pairs(const orc_params *p, orc_pairs_record *recs, int64_t n);
+// Pairs text with header (mapping_writer.cc:381-421); read_names[i] = name of read 1 of pair `read_id - first_read_id`.
+int64_t orc_format_pairs(const orc_reference *ref, const orc_pairs_record *recs, int64_t n, const char *const *read_names,
+                         uint32_t first_read_id, char *buf, int64_t cap);
 // BED text (mapping_writer.cc:75-83).  Returns bytes written into buf (or needed if buf==NULL).
 int64_t orc_format_bed(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf,
                        int64_t cap);

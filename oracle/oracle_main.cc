@@ -38,6 +38,8 @@ int main(int argc, char **argv) {
     else if (a == "--remove-pcr-duplicates") p.remove_pcr_duplicates = 1;
     else if (a == "--Tn5-shift") p.tn5_shift = 1;
     else if (a == "--low-mem") p.low_memory_mode = 1;
+    else if (a == "--split-alignment") p.split_alignment = 1;
+    else if (a == "--pairs") p.output_format = 5;
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 255; }
   }
   if (build) {

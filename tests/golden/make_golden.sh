@@ -31,3 +31,15 @@ $REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o atac.bed -t
 $REF --preset hic -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o hic.pairs -t 1 2> /dev/null
 md5sum default.bed chip.bed atac.bed hic.pairs ref.index > md5.txt
 gzip -9 -n ref.fa
+# Hi-C (--preset hic: split alignment, pairs output): 2x150 bp with chimeric reads
+cd .. && rm -rf synth_hic && mkdir -p synth_hic
+python $REPO/tools/gen_synth.py --out synth_hic --seed 12 --n-seq 3 --seq-len 250000 --n-pairs 3000 --read-len 150 \
+  --chimeric-frac 0.3 --repeat-copies 15 --repeat-len 2000 --fam-copies 500
+cd synth_hic
+$REF -i -r ref.fa -o ref.index 2> /dev/null
+$REF --preset hic -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o hic.pairs -t 1 2> /dev/null
+$REF --preset hic -q 0 -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o hic_q0.pairs -t 1 2> /dev/null
+$REF --preset hic -q 0 -e 6 --remove-pcr-duplicates -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o hic_e6dedup.pairs -t 1 2> /dev/null
+md5sum *.pairs > md5.txt
+gzip -9 -n ref.fa read1.fq read2.fq *.pairs
+rm -f ref.index

@@ -95,3 +95,33 @@ def test_index_builder_equals_reference_index(golden_dir):
         assert L.orc_index_lookup(theirs.h, int(x), C.byref(k1), C.byref(v1)) == 1
         assert L.orc_index_lookup(ours.h, int(x), C.byref(k2), C.byref(v2)) == 1
         assert (k1.value, v1.value) == (k2.value, v2.value)
+
+
+HIC_CASES = {
+    "hic": dict(),
+    "hic_q0": dict(mapq_threshold=0),
+    "hic_e6dedup": dict(mapq_threshold=0, error_threshold=6, remove_pcr_duplicates=1),
+}
+
+
+@pytest.mark.parametrize("case", sorted(HIC_CASES))
+def test_hic_split_alignment_pairs_match_reference_binary(case, golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "synth_hic")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    ip = str(tmp_path / "hic.index")
+    assert idx.save(ip) == 0
+    out = str(tmp_path / "o.pairs")
+    orc.run_files(orc.make_params("hic", **HIC_CASES[case]), ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"),
+                  os.path.join(d, "read2.fq.gz"), out)
+    want = gzip.open(os.path.join(d, case + ".pairs.gz")).read()
+    assert hashlib.md5(want).hexdigest() == _md5s(d)[case + ".pairs"]
+    assert open(out, "rb").read() == want
+
+
+def test_hic_reference_quickstart(golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "ref_test")
+    out = str(tmp_path / "o.pairs")
+    orc.run_files(orc.make_params("hic"), os.path.join(d, "ref.index"), os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq"),
+                  os.path.join(d, "read2.fq"), out)
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == "fc844a251ebdcec0f641b59fef804d0f"
