@@ -52,6 +52,10 @@ PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u
                       ("positive_alignment_length", "<u2"), ("negative_alignment_length", "<u2")], align=True)
 assert PE_RECORD.itemsize == 24
 
+PAIRS_RECORD = np.dtype([("read_id", "<u4"), ("rid1", "<u4"), ("rid2", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("strand1", "u1"),
+                         ("strand2", "u1"), ("mapq", "u1"), ("is_unique", "u1")], align=True)
+assert PAIRS_RECORD.itemsize == 24
+
 PAIR_TRACE = np.dtype([("n_minimizers", "<i4", 2), ("n_pos_candidates_gen", "<i4", 2), ("n_neg_candidates_gen", "<i4", 2),
                        ("n_pos_candidates", "<i4", 2), ("n_neg_candidates", "<i4", 2), ("n_pos_mappings", "<i4", 2),
                        ("n_neg_mappings", "<i4", 2), ("min_errors", "<i4", 2), ("second_min_errors", "<i4", 2),
@@ -87,6 +91,8 @@ def load_library():
     L.cmx_map_batch_pe.argtypes = [vp, C.POINTER(Batch), C.POINTER(Records), vp]
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
+    L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.cmx_format_pairs.restype = i64; L.cmx_format_pairs.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, i64]
     L.cmx_stage_minimizers.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, u32]
     L.cmx_stage_probe.argtypes = [vp, vp, u64, vp, vp, vp]
     L.cmx_stage_banded_align.argtypes = [vp, i32, i32, vp, vp, u64, vp, vp]
@@ -207,7 +213,7 @@ class Mapper:
         b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), first_read_id, 1 if on_device else 0)
         mb = self.params.max_num_best_mappings
         if out is None:
-            out = np.zeros(n * mb, dtype=PE_RECORD)
+            out = np.zeros(n * mb, dtype=PAIRS_RECORD if self.params.output_format == 5 else PE_RECORD)
         cap = (out.numel() * out.element_size() // 24) if hasattr(out, "data_ptr") else len(out)
         r = Records(_ptr(out), cap, 0, 1 if out_on_device else 0, 0, 0, 0, 0)
         rc = self.L.cmx_map_batch_pe(self.h, C.byref(b), C.byref(r), None)
@@ -233,6 +239,23 @@ class Mapper:
         n = C.c_uint64()
         self._check(self.L.cmx_postprocess(self.h, recs.ctypes.data, len(recs), C.byref(n)), "cmx_postprocess")
         return recs[:n.value]
+
+    def postprocess_pairs(self, recs):
+        recs = np.ascontiguousarray(recs.copy())
+        n = C.c_uint64()
+        self._check(self.L.cmx_postprocess_pairs(self.h, recs.ctypes.data, len(recs), C.byref(n)), "cmx_postprocess_pairs")
+        return recs[:n.value]
+
+    def format_pairs(self, recs, read_names, lengths, first_read_id=0, names=None):
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        rn = (C.c_char_p * len(read_names))(*[s if isinstance(s, bytes) else s.encode() for s in read_names])
+        lens = np.ascontiguousarray(lengths, dtype=np.uint32)
+        recs = np.ascontiguousarray(recs)
+        n = self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, buf, n)
+        return buf.raw[:n]
 
     def format_bed(self, recs, names=None):
         names = names or self.names

@@ -21,6 +21,7 @@
 
 static_assert(sizeof(OutRecord) == sizeof(cmx_pe_record), "record layout");
 static_assert(sizeof(cmx_pe_record) == 24, "record size");
+static_assert(sizeof(OutPairs) == 24 && sizeof(cmx_pairs_record) == 24, "pairs record size");
 
 #define N_TIERS 3
 
@@ -129,7 +130,8 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   *out = nullptr;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device >= n_dev) return CMX_ERR_NO_DEVICE;
-  if (params->split_alignment || params->output_format != 1) return CMX_ERR_INVALID;  // BED, non-split this round
+  if (!((params->output_format == 1 && !params->split_alignment) || (params->output_format == 5 && params->split_alignment)))
+    return CMX_ERR_INVALID;  // paired-end BED, or Hi-C pairs with split alignment
   if (params->error_threshold < 1 || params->error_threshold >= 16) return CMX_ERR_INVALID;  // mapping_parameters.h:80-88
   if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
   if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
@@ -167,6 +169,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CU(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
   ctx->tiers[0].caps = {mrl, 64, 32, 32};
   ctx->tiers[1].caps = {mrl * 2, 1024, 256, 256};
@@ -349,7 +352,7 @@ int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint
 }
 
 // ---------------------------------------------------------------------------------------------------
-static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {
+static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {  // o[11]
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t r = off; off = (off + bytes + 255) / 256 * 256; return r; };
   const size_t R = 2 * slots;
@@ -362,12 +365,13 @@ static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {
   o[6] = take(R * 6 * (size_t)c.cc * 8);
   o[7] = take(R * 6 * (size_t)c.cc);
   o[8] = take(R * 2 * (size_t)c.mc * 8);
-  o[9] = take(R * 2 * (size_t)c.mc);
+  o[9] = take(R * 2 * (size_t)c.mc * 2);
+  o[10] = take(R * 2 * (size_t)c.mc * 4);
   return off;
 }
 static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list) {
   if (n_slots > t.slots_cap) {
-    size_t o[10];
+    size_t o[11];
     const size_t want_slots = (size_t)n_slots + n_slots / 8 + 16;
     const size_t bytes = tier_bytes(t.caps, want_slots, o);
     release(t.mem);
@@ -375,7 +379,7 @@ static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list) {
     if (e != cudaSuccess) return e;
     t.slots_cap = (int)want_slots;
   }
-  size_t o[10];
+  size_t o[11];
   tier_bytes(t.caps, t.slots_cap, o);
   char *b = (char *)t.mem.p;
   Scratch &S = t.view;
@@ -383,7 +387,7 @@ static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list) {
   S.rmeta = (ReadMeta *)(b + o[0]); S.pmeta = (PairMeta *)(b + o[1]);
   S.mm_hash = (u64 *)(b + o[2]); S.mm_val = (u64 *)(b + o[3]); S.mm_pos = (u32 *)(b + o[4]);
   S.hits = (u64 *)(b + o[5]); S.cand_pos = (u64 *)(b + o[6]); S.cand_cnt = (u8 *)(b + o[7]);
-  S.map_pos = (u64 *)(b + o[8]); S.map_err = (signed char *)(b + o[9]);
+  S.map_pos = (u64 *)(b + o[8]); S.map_err = (short *)(b + o[9]); S.map_split = (int *)(b + o[10]);
   t.n_slots = n_slots; t.pair_list = pair_list;
   return cudaSuccess;
 }
@@ -405,6 +409,7 @@ static DevParams make_dev_params(const cmx_ctx *ctx) {
   d.max_best = p.max_num_best_mappings; d.max_insert = p.max_insert_size; d.min_read_len = p.min_read_length;
   d.drop_rep = p.drop_repetitive_reads; d.trim = p.trim_adapters; d.k = ctx->k; d.w = ctx->w;
   d.lanes = p.error_threshold < 8 ? 8 : 4;  // mapping_parameters.h:80-88
+  d.split = p.split_alignment;
   return d;
 }
 
@@ -497,9 +502,11 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
       pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr, 0, (int *)ctx->rescue_list.p, ctx->d_count + 1);
       pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, ctx->ctr, 1, (int *)ctx->rescue_list.p, ctx->d_count + 1);
       CU(cudaEventRecord(e2, st));
-      verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
+      if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
+      else verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
       CU(cudaEventRecord(e3, st));
-      pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      else pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
       CU(cudaEventRecord(e4, st));
     } else {  // overflow tiers: one CTA per read / pair; shared-memory sort buffers sized to the tier
       auto cap_of = [](int n) { int c = 1; while (c < n) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
@@ -508,9 +515,11 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
       CU(cudaEventRecord(e1, st));
       pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 11, st>>>(P, ix, S, ctx->ctr, c_pc);
       CU(cudaEventRecord(e2, st));
-      verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
+      if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
+      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
       CU(cudaEventRecord(e3, st));
-      pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 9, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
+      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
+      else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
       CU(cudaEventRecord(e4, st));
     }
     acc.launches += (t == 0 ? 8 : 6);
@@ -553,7 +562,8 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
   CU(cudaEventRecord(ctx->ev[3], st));
   for (int t = 0; t < tiers_used; ++t) {
     const Scratch S = ctx->tiers[t].view;
-    emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutRecord *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
+    if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutPairs *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
+    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutRecord *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
   }
   acc.launches += 1 + tiers_used;
   // read-order compaction
@@ -876,6 +886,50 @@ int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t n, uint64_t *n_o
   for (uint64_t i = 0; i < n; ++i) if (recs[i].mapq >= p.mapq_threshold) recs[o++] = recs[i];
   *n_out = o;
   return CMX_OK;
+}
+
+int cmx_postprocess_pairs(cmx_ctx *ctx, cmx_pairs_record *recs, uint64_t n, uint64_t *n_out) {
+  if (!ctx || (!recs && n) || !n_out) return CMX_ERR_INVALID;
+  const cmx_params &p = ctx->params;
+  // records live in the bucket of rid1; the merge order is (bucket, PairsMapping::operator<) (pairs_mapping.h:40-43)
+  std::sort(recs, recs + n, [](const cmx_pairs_record &a, const cmx_pairs_record &b) {
+    return std::make_tuple(a.rid1, a.rid2, a.pos1, a.pos2, a.mapq, a.read_id) < std::make_tuple(b.rid1, b.rid2, b.pos1, b.pos2, b.mapq, b.read_id);
+  });
+  uint64_t o = 0;
+  if (p.remove_pcr_duplicates) {  // mapping_writer.h:234-300 with PairsMapping::operator== (pairs_mapping.h:44-49)
+    uint64_t i = 0;
+    while (i < n) {
+      cmx_pairs_record keep = recs[i];
+      uint64_t j = i + 1;
+      for (; j < n && recs[j].rid1 == recs[i].rid1 && recs[j].pos1 == recs[i].pos1 && recs[j].rid2 == recs[i].rid2 && recs[j].pos2 == recs[i].pos2; ++j)
+        if (recs[j].mapq > keep.mapq) keep = recs[j];
+      if (keep.mapq >= p.mapq_threshold) recs[o++] = keep;
+      i = j;
+    }
+  } else {
+    for (uint64_t i = 0; i < n; ++i) if (recs[i].mapq >= p.mapq_threshold) recs[o++] = recs[i];
+  }
+  *n_out = o;
+  return CMX_OK;
+}
+
+int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint32_t n_seq, const cmx_pairs_record *recs, uint64_t n,
+                         const char *const *read_names, uint32_t first_read_id, char *buf, int64_t cap) {
+  int64_t len = 0;
+  std::string hdr = "## pairs format v1.0.0\n#shape: upper triangle\n";  // mapping_writer.cc:383-402
+  for (uint32_t i = 0; i < n_seq; ++i) hdr += std::string("#chromsize: ") + names[i] + " " + std::to_string(lengths[i]) + "\n";
+  hdr += "#columns: readID chrom1 pos1 chrom2 pos2 strand1 strand2 pair_type mapq1 mapq2\n";
+  if (buf && (int64_t)hdr.size() <= cap) memcpy(buf, hdr.data(), hdr.size());
+  len += (int64_t)hdr.size();
+  for (uint64_t i = 0; i < n; ++i) {  // mapping_writer.cc:405-421
+    const cmx_pairs_record &r = recs[i];
+    const std::string line = std::string(read_names[r.read_id - first_read_id]) + "\t" + names[r.rid1] + "\t" + std::to_string(r.pos1 + 1) + "\t" + names[r.rid2] +
+                             "\t" + std::to_string(r.pos2 + 1) + "\t" + (r.strand1 ? "+" : "-") + "\t" + (r.strand2 ? "+" : "-") + "\tUU\t" +
+                             std::to_string(r.mapq) + "\t" + std::to_string(r.mapq) + "\n";
+    if (buf && len + (int64_t)line.size() <= cap) memcpy(buf + len, line.data(), line.size());
+    len += (int64_t)line.size();
+  }
+  return len;
 }
 
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {

@@ -13,7 +13,7 @@ typedef unsigned char u8;
 
 // Parameters the kernels read (subset of cmx_params + index k/w).
 struct DevParams {
-  int e, min_seeds, f0, f1, max_best, max_insert, min_read_len, drop_rep, trim, k, w, lanes;
+  int e, min_seeds, f0, f1, max_best, max_insert, min_read_len, drop_rep, trim, k, w, lanes, split;
 };
 
 struct Caps {  // per-read (per-strand where applicable) scratch capacities of one tier
@@ -88,7 +88,8 @@ struct Scratch {
   u64 *cand_pos;         // [2n][3][2][cc]   set 0 = candidates, 1 = buffer, 2 = augment
   u8 *cand_cnt;          // same shape
   u64 *map_pos;          // [2n][2][mc]
-  signed char *map_err;  // [2n][2][mc]
+  short *map_err;        // [2n][2][mc]   (under --split-alignment: -(matched length))
+  int *map_split;        // [2n][2][mc]   split_sites word (draft_mapping_generator.cc:550-554)
 };
 
 __device__ __forceinline__ int slot_pair(const Scratch &S, int slot) { return S.pair_list ? S.pair_list[slot] : slot; }

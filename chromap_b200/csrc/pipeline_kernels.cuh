@@ -495,6 +495,14 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   bool aug[2];
+  if (P.split) {  // chromap.h:1021,1036-1038: no mate supplementation and no paired-end filter under split alignment
+    if (mode != 0) return;
+    if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
+    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1], a2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+    if (!(a1 > 0 && a2 > 0)) { pm.status = ST_DROP; return; }
+    atomicAdd(&ctr->n_candidates, (u64)(a1 + a2));
+    return;
+  }
   if (mode == 0) {
     if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
     bool need = false;
@@ -657,7 +665,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
   const int L = rm.len, e = P.e;
   Tally t = {e + 1, e + 1, 0, 0};
   u64 *mp[2] = {S.map_pos + ((size_t)sr * 2 + 0) * c.mc, S.map_pos + ((size_t)sr * 2 + 1) * c.mc};
-  signed char *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
+  short *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
   int nm[2] = {0, 0};
   u64 *cp[2] = {S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
   u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
@@ -698,7 +706,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
         tally(t, err);
         if (nm[s] < c.mc) {
           mp[s][nm[s]] = s == 0 ? cpos - (u64)e + (u64)endp : cpos - (u64)L + 1 - (u64)e + (u64)endp;
-          me[s][nm[s]] = (signed char)err;
+          me[s][nm[s]] = (short)err;
         }
         ++nm[s];
         return false;
@@ -739,8 +747,8 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
 // mapping_generator.h:346-484 (non-split): two-pointer sweep over end positions.  VISIT(i1, j, sum) is
 // called for every in-window pair in the reference's enumeration order.
 template <typename Visit>
-__device__ __forceinline__ void pair_sweep(const DevParams &P, int s1, u32 L1, u32 L2, const u64 *p1, const signed char *e1, int n1,
-                                           const u64 *p2, const signed char *e2, int n2, Visit VISIT) {
+__device__ __forceinline__ void pair_sweep(const DevParams &P, int s1, u32 L1, u32 L2, const u64 *p1, const short *e1, int n1,
+                                           const u64 *p2, const short *e2, int n2, Visit VISIT) {
   int i1 = 0, i2 = 0;
   const u64 ins = (u64)P.max_insert, ovl = (u64)(u32)P.min_read_len;
   while (i1 < n1 && i2 < n2) {
@@ -769,14 +777,14 @@ __global__ void pairing_kernel(DevParams P, Scratch S, int *pair_nbest) {
   ReadMeta *rm = S.rmeta + 2 * slot;
   if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; return; }
   // equal positions are interchangeable for the output; (pos, err) makes the order canonical
-  auto mless = [](u64 pa, signed char ea, u64 pb, signed char eb) { return pa != pb ? pa < pb : ea < eb; };
+  auto mless = [](u64 pa, short ea, u64 pb, short eb) { return pa != pb ? pa < pb : ea < eb; };
   u64 *mp[2][2];
-  signed char *me[2][2];
+  short *me[2][2];
   for (int m = 0; m < 2; ++m)
     for (int s = 0; s < 2; ++s) {
       mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
       me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
-      sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], mless);
+      sort_pairs<short>(mp[m][s], me[m][s], rm[m].n_map[s], mless);
     }
   int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;
   auto visit = [&](int, int, int sum) {
@@ -1041,7 +1049,7 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
   for (int dir = 0; dir < 2 && reported != to_report; ++dir) {
     const int s1 = dir, s2 = 1 - dir;
     const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    const signed char *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
     pair_sweep(P, s1, (u32)L[0], (u32)L[1], p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) {
       if (sum != pm.min_sum || reported == to_report) return;
       if (idx == sel[reported]) {
@@ -1665,6 +1673,12 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { __syncthreads(); if (tid == 0) pm.status = ST_DROP; return; }
+  if (P.split) {
+    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1], a2 = rm[1].n_cand[0] + rm[1].n_cand[1];
+    __syncthreads();
+    if (tid == 0) { if (!(a1 > 0 && a2 > 0)) pm.status = ST_DROP; else atomicAdd(&ctr->n_candidates, (u64)(a1 + a2)); }
+    return;
+  }
   if (tid == 0) {
     for (int mate = 0; mate < 2; ++mate) {
       const u32 n_mm = rm[mate].n_mm;
@@ -1769,7 +1783,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
   const u8 *read = read_ptr(B, pair, mate);
   const int L = rm.len, e = P.e;
   u64 *mp[2] = {S.map_pos + ((size_t)sr * 2 + 0) * c.mc, S.map_pos + ((size_t)sr * 2 + 1) * c.mc};
-  signed char *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
+  short *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
   u64 *cp[2] = {S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
   u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
   // per-candidate results live in the (now free) augment set: err in the count array, end position in the pos array
@@ -1831,7 +1845,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
       const u64 cpos = cp[s][i];
       if (nm[s] < c.mc) {
         mp[s][nm[s]] = s == 0 ? cpos - (u64)e + rend[s][i] : cpos - (u64)L + 1 - (u64)e + rend[s][i];
-        me[s][nm[s]] = (signed char)err;
+        me[s][nm[s]] = (short)err;
       }
       ++nm[s];
       return false;
@@ -1862,7 +1876,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
 // pairing for one pair by one CTA: the four mapping lists are sorted cooperatively, thread 0 sweeps.
 __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratch S, int *pair_nbest, int sm_cap) {
   extern __shared__ u64 smk[];
-  signed char *smt = (signed char *)(smk + sm_cap);
+  short *smt = (short *)(smk + sm_cap);
   const int slot = blockIdx.x, tid = threadIdx.x;
   PairMeta &pm = S.pmeta[slot];
   const int pair = slot_pair(S, slot);
@@ -1874,14 +1888,14 @@ __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratc
     if (tid == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
     return;
   }
-  auto mless = [](u64 pa, signed char ea, u64 pb, signed char eb) { return pa != pb ? pa < pb : ea < eb; };
+  auto mless = [](u64 pa, short ea, u64 pb, short eb) { return pa != pb ? pa < pb : ea < eb; };
   u64 *mp[2][2];
-  signed char *me[2][2];
+  short *me[2][2];
   for (int m = 0; m < 2; ++m)
     for (int s = 0; s < 2; ++s) {
       mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
       me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
-      cta_sort_pairs<signed char>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (signed char)127, mless, smk, smt, sm_cap);
+      cta_sort_pairs<short>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (short)32767, mless, smk, smt, sm_cap);
     }
   if (tid != 0) return;
   int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;
@@ -1895,4 +1909,396 @@ __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratc
   pair_sweep(P, 1, (u32)rm[0].len, (u32)rm[1].len, mp[0][1], me[0][1], rm[0].n_map[1], mp[1][0], me[1][0], rm[1].n_map[0], visit);
   pm.min_sum = min_sum; pm.second_min_sum = second; pm.n_best = n_best; pm.n_second_best = n_second;
   pair_nbest[pair] = (n_best > P.drop_rep) ? 0 : n_best;
+}
+
+
+// =================================================================================================
+// --split-alignment (Hi-C): draft_mapping_generator.cc:359-557 split branch, alignment.cc:197-376,
+// mapping_generator.h:389-415 (pairing), :657-917 split branches, :920-1022 split MAPQ, mapping_generator.cc:169-210.
+
+// alignment.cc:197-283 (from3 = false) and :285-376 (from3 = true).  PAT(i) / TXT(i): base codes at logical index i.
+template <typename PatF, typename TxtF>
+__device__ __forceinline__ int banded_align_dropoff(int e, int L, bool from3, PatF PAT, TxtF TXT, int *end_pos, int *read_len_out) {
+  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) {
+    const u32 b = from3 ? PAT(L + 2 * e - 1 - i) : PAT(i);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
+  }
+  const u32 hi = 1u << (2 * e);
+  u32 VP = 0, VN = 0, pVP = 0, pVN = 0;
+  int err = 0, perr = 0, i = 0, fail_beginning = 0;
+  for (; i < L; ++i) {
+    const u32 pb = from3 ? PAT(L - 1 - i) : PAT(i + 2 * e);
+    const u32 tb = from3 ? TXT(L - 1 - i) : TXT(i);
+    u32 X = VN;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      Peq[a] |= (pb == (u32)a) ? hi : 0u;
+      X |= (tb == (u32)a) ? Peq[a] : 0u;
+    }
+    const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+    const u32 HN = VP & D0;
+    const u32 HP = VN | ~(VP | D0);
+    X = D0 >> 1;
+    pVN = VN; pVP = VP;
+    VN = X & HP;
+    VP = HN | ~(X | HP);
+    perr = err;
+    err += 1 - (int)(D0 & 1u);
+    if (err > 2 * e) { if (i < 4 * e && i < L / 2) fail_beginning = 1; break; }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+  }
+  if (i < L) { err = perr; VN = pVN; VP = pVP; }
+  const int band_start = i - 1;
+  int best = err;
+  *read_len_out = i;
+  int ep = band_start;
+  for (int j = 0; j < 2 * e; ++j) {
+    err += (int)((VP >> j) & 1u);
+    err -= (int)((VN >> j) & 1u);
+    if (err < best || (err == best && j + 1 == e)) { best = err; ep = band_start + 1 + j; }
+  }
+  if (fail_beginning || (L > 60 && ep + 1 - e - best < 30)) ep = -ep;
+  *end_pos = ep;
+  return best;
+}
+
+struct SplitResult { int nerr, actual, endp, gap, rml; };  // nerr = -(matched length) or e+1
+// one candidate of the split driver (draft_mapping_generator.cc:410-487): drop-off alignment, retry without the first 20-e bases
+__device__ __forceinline__ SplitResult verify_split_candidate(int e, const u8 *win, const u8 *read, int L, int s) {
+  SplitResult r;
+  int endp = L, gap = 0, nerr, rml = 0;
+  const int allow_gap = 20 - e;
+  if (s == 0) {
+    nerr = banded_align_dropoff(e, L, false, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return base_code(read[i]); }, &endp, &rml);
+    if (endp < 0 && allow_gap > 0) {
+      const int b_err = nerr, b_end = -endp, b_rml = rml;
+      nerr = banded_align_dropoff(e, L - allow_gap, false, [&](int i) { return base_code(__ldg(win + allow_gap + i)); },
+                                  [&](int i) { return base_code(read[allow_gap + i]); }, &endp, &rml);
+      if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
+      else { gap = allow_gap; endp += gap; rml += gap; }
+    }
+  } else {
+    nerr = banded_align_dropoff(e, L, true, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp, &rml);
+    if (endp < 0 && allow_gap > 0) {
+      const int b_err = nerr, b_end = -endp, b_rml = rml;
+      nerr = banded_align_dropoff(e, L - allow_gap, true, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp, &rml);
+      if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
+      else { gap = allow_gap; endp += gap; rml += gap; }
+    }
+  }
+  if (endp + 1 - e - nerr - gap >= 30) { r.actual = nerr; r.nerr = -(endp - e - nerr - gap); }
+  else { r.nerr = e + 1; r.actual = e + 1; }
+  r.endp = endp; r.gap = gap; r.rml = rml;
+  return r;
+}
+
+// K3 (split): per read, sequential driver with count-threshold pruning.
+__global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr) {
+  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sr >= 2 * S.n_slots) return;
+  const int slot = sr >> 1, mate = sr & 1;
+  if (S.pmeta[slot].status != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  const u8 *read = read_ptr(B, pair, mate);
+  const int L = rm.len, e = P.e;
+  Tally t = {e + 1, e + 1, 0, 0};
+  auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
+  u64 n_verified = 0;
+  int nm[2] = {0, 0};
+  for (int s = 0; s < 2; ++s) {
+    u64 *cp = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
+    u8 *cc = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
+    u64 *mp = S.map_pos + ((size_t)sr * 2 + s) * c.mc;
+    short *me = S.map_err + ((size_t)sr * 2 + s) * c.mc;
+    int *ms = S.map_split + ((size_t)sr * 2 + s) * c.mc;
+    const int nc = rm.n_cand[s];
+    sort_pairs<u8>(cp, cc, nc, cless);
+    u32 threshold = 0;
+    for (int ci = 0; ci < nc; ++ci) {
+      if (cc[ci] < threshold) break;
+      const u64 cpos = cp[ci];
+      const u32 rid = (u32)(cpos >> 32);
+      const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+      if (!valid_cand(e, R.len[rid], pos, (u32)L)) continue;
+      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, read, L, s);
+      ++n_verified;
+      if (r.nerr <= e) {
+        if (r.nerr < t.min_err) {
+          t.second_min_err = t.min_err; t.n_second_best = t.n_best; t.min_err = r.nerr; t.n_best = 1;
+          threshold = nc > 50 ? (u32)cc[ci] : (u32)cc[ci] / 2;
+        } else if (r.nerr == t.min_err) t.n_best++;
+        else if (r.nerr == t.second_min_err) t.n_second_best++;
+        else if (r.nerr < t.second_min_err) { t.n_second_best = 1; t.second_min_err = r.nerr; }
+        if (nm[s] < c.mc) {
+          mp[nm[s]] = s == 0 ? cpos - (u64)e + (u64)r.endp : cpos - (u64)r.gap;
+          me[nm[s]] = (short)r.nerr;
+          ms[nm[s]] = ((r.actual & 0xff) << 24) | ((r.gap & 0xff) << 16) | (r.rml & 0xffff);
+        }
+        ++nm[s];
+      }
+    }
+  }
+  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
+  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
+  rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
+  if (n_verified) atomicAdd(&ctr->n_verified, n_verified);
+}
+
+// K3 (split, overflow tiers): every valid candidate verified by its own thread, thread 0 replays the pruning order.
+__global__ void __launch_bounds__(CTA_NT) verify_split_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
+  extern __shared__ u64 smk[];
+  u8 *smt = (u8 *)(smk + sm_cap);
+  __shared__ int s_status;
+  const int sr = blockIdx.x, tid = threadIdx.x;
+  const int slot = sr >> 1, mate = sr & 1;
+  if (tid == 0) s_status = S.pmeta[slot].status;
+  __syncthreads();
+  if (s_status != ST_OK) return;
+  const int pair = slot_pair(S, slot);
+  ReadMeta &rm = S.rmeta[sr];
+  const Caps c = S.caps;
+  const u8 *read = read_ptr(B, pair, mate);
+  const int L = rm.len, e = P.e;
+  auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
+  u64 *cp[2], *res[2];
+  u8 *cc[2], *vld[2];
+  for (int s = 0; s < 2; ++s) {
+    cp[s] = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + s) * c.cc; cc[s] = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
+    res[s] = S.cand_pos + (((size_t)sr * 3 + 2) * 2 + s) * c.cc; vld[s] = S.cand_cnt + (((size_t)sr * 3 + 2) * 2 + s) * c.cc;  // augment set is free here
+  }
+  const int nc[2] = {rm.n_cand[0], rm.n_cand[1]};
+  cta_sort_pairs<u8>(cp[0], cc[0], nc[0], ~0ull, (u8)0, cless, smk, smt, sm_cap);
+  cta_sort_pairs<u8>(cp[1], cc[1], nc[1], ~0ull, (u8)0, cless, smk, smt, sm_cap);
+  u64 n_ver = 0;
+  for (int s = 0; s < 2; ++s)
+    for (int i = tid; i < nc[s]; i += CTA_NT) {
+      const u64 cpos = cp[s][i];
+      const u32 rid = (u32)(cpos >> 32);
+      const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+      if (!valid_cand(e, R.len[rid], pos, (u32)L)) { vld[s][i] = 0; continue; }
+      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, read, L, s);
+      vld[s][i] = 1;
+      res[s][i] = ((u64)(u32)(r.nerr + 1024) << 48) | ((u64)(r.actual & 0xff) << 40) | ((u64)(r.gap & 0xff) << 32) | ((u64)(r.rml & 0xffff) << 16) | (u64)(r.endp & 0xffff);
+      ++n_ver;
+    }
+  if (n_ver) atomicAdd(&ctr->n_verified, n_ver);
+  __syncthreads();
+  if (tid != 0) return;
+  Tally t = {e + 1, e + 1, 0, 0};
+  int nm[2] = {0, 0};
+  for (int s = 0; s < 2; ++s) {
+    u64 *mp = S.map_pos + ((size_t)sr * 2 + s) * c.mc;
+    short *me = S.map_err + ((size_t)sr * 2 + s) * c.mc;
+    int *ms = S.map_split + ((size_t)sr * 2 + s) * c.mc;
+    u32 threshold = 0;
+    for (int ci = 0; ci < nc[s]; ++ci) {
+      if (cc[s][ci] < threshold) break;
+      if (!vld[s][ci]) continue;
+      const u64 w = res[s][ci];
+      const int nerr = (int)(w >> 48) - 1024, actual = (int)((w >> 40) & 0xff), gap = (int)((w >> 32) & 0xff), rml = (int)((w >> 16) & 0xffff), endp = (int)(w & 0xffff);
+      if (nerr <= e) {
+        if (nerr < t.min_err) {
+          t.second_min_err = t.min_err; t.n_second_best = t.n_best; t.min_err = nerr; t.n_best = 1;
+          threshold = nc[s] > 50 ? (u32)cc[s][ci] : (u32)cc[s][ci] / 2;
+        } else if (nerr == t.min_err) t.n_best++;
+        else if (nerr == t.second_min_err) t.n_second_best++;
+        else if (nerr < t.second_min_err) { t.n_second_best = 1; t.second_min_err = nerr; }
+        const u64 cpos = cp[s][ci];
+        if (nm[s] < c.mc) {
+          mp[nm[s]] = s == 0 ? cpos - (u64)e + (u64)endp : cpos - (u64)gap;
+          me[nm[s]] = (short)nerr;
+          ms[nm[s]] = ((actual & 0xff) << 24) | ((gap & 0xff) << 16) | (rml & 0xffff);
+        }
+        ++nm[s];
+      }
+    }
+  }
+  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
+  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
+  rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
+}
+
+// K4 (split): mapping_generator.h:389-415 — #best pairs = product of the mates' best-mapping counts per direction.
+__global__ void pairing_split_kernel(DevParams P, Scratch S, int *pair_nbest) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status != ST_OK) { if (pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
+  const Caps c = S.caps;
+  ReadMeta *rm = S.rmeta + 2 * slot;
+  if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; return; }
+  int cnt[2][2];
+  for (int m = 0; m < 2; ++m)
+    for (int s = 0; s < 2; ++s) {
+      const short *me = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
+      const int want = rm[m].min_err;
+      int k = 0;
+      for (int i = 0; i < rm[m].n_map[s]; ++i) k += me[i] == want;
+      cnt[m][s] = k;
+    }
+  const long long nb = (long long)cnt[0][0] * cnt[1][1] + (long long)cnt[0][1] * cnt[1][0] + (long long)cnt[0][0] * cnt[1][0] + (long long)cnt[0][1] * cnt[1][1];
+  const int n_best = nb > 0x7fffffffLL ? 0x7fffffff : (int)nb;
+  pm.min_sum = n_best > 0 ? rm[0].min_err + rm[1].min_err : 2 * P.e + 1;
+  pm.second_min_sum = 2 * P.e + 1; pm.n_best = n_best; pm.n_second_best = 0;
+  pair_nbest[pair] = (n_best > P.drop_rep) ? 0 : n_best;
+}
+
+__device__ __forceinline__ int sgn_char(u8 c) { return (int)(signed char)c; }
+// alignment.cc:24-83 with n_cigar == 0.  RD(i): raw read char at index i of the strand string (0 past its end).
+template <typename ReadC>
+__device__ __forceinline__ int adjust_gap_beginning(int strand, const u8 *ref, ReadC RD, int *gap, int read_end, int ref_start, int ref_end) {
+  int i, j;
+  if (strand == 0) {
+    if (*gap <= 0) return ref_start;
+    for (i = *gap - 1, j = ref_start - 1; i >= 0 && j >= 0; --i, --j) {
+      const int a = sgn_char(RD(i)), b = sgn_char(__ldg(ref + j));
+      if (a != b && a != b - 'a' + 'A') break;
+    }
+    *gap = i + 1;
+    return j + 1;
+  }
+  if (*gap <= 0) return ref_end;
+  for (i = read_end + 1, j = ref_end + 1; RD(i) && __ldg(ref + j); ++i, ++j) {
+    const int a = sgn_char(RD(i)), b = sgn_char(__ldg(ref + j));
+    if (a != b && a != b - 'a' + 'A') break;
+  }
+  *gap = *gap + i - (read_end + 1);
+  return j - 1;
+}
+
+// mapping_generator.h:920-1022 with split_alignment.
+__device__ inline u8 mapq_se_split(const MapqTables &T, const DevParams &P, int n_cand_strand, int num_errors, unsigned short aln_len, int read_len,
+                                   int max_diff, const ReadMeta &rm) {
+  const int coef_len = 50;
+  double ident = xdiv((double)(-num_errors), (double)aln_len);
+  if (ident > 1) ident = 1;
+  int mapq = 0;
+  int second = rm.second_min_err;
+  if (rm.n_best > 1) {
+  } else {
+    if (second > num_errors + max_diff) second = num_errors + max_diff;
+    double tmp = (int)aln_len < coef_len ? 1.0 : T.inv_log[aln_len];
+    tmp = xmul(tmp, xmul(ident, ident));
+    mapq = (int)xadd(xmul(xmul(xmul(5 * 6.02, (double)(second - num_errors)), tmp), tmp), 0.499);
+  }
+  if (rm.n_second_best > 0) mapq -= second_best_penalty(T, rm.n_second_best);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  if (rm.rep_len > 0) {
+    double frac = xdiv((double)rm.rep_len, (double)read_len);
+    if (rm.rep_len >= (u32)read_len) frac = 0.999;
+    mapq = (int)xadd(xmul((double)mapq, rep_scale(ident, frac)), 0.499);
+  }
+  if ((int)aln_len < read_len - P.e && second != num_errors) {
+    if (rm.rep_len >= (u32)aln_len && rm.rep_len < (u32)read_len && (int)aln_len < read_len / 3) mapq = 0;
+    const int diff = second - num_errors;
+    const u32 num_candidates = (u32)n_cand_strand;
+    if (second - num_errors <= P.e * 3 / 4 && num_candidates >= 5) mapq -= (num_candidates / 5 / diff);  // u32 arithmetic as in the reference
+    if (mapq < 0) mapq = 0;
+    if (rm.n_second_best > 0 && second - num_errors <= P.e * 3 / 4) mapq /= (rm.n_second_best / diff + 1);
+  }
+  return (u8)mapq;
+}
+
+struct OutPairs {  // == cmx_pairs_record
+  u32 read_id, rid1, rid2, pos1, pos2;
+  u8 strand1, strand2, mapq, is_unique;
+};
+
+// K6 (split): the selected best pair(s) -> PairsMapping (mapping_generator.cc:169-210).
+__global__ void emit_split_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, const int *pair_sel, OutPairs *out, int *out_n, Counters *ctr) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status == ST_OVERFLOW) return;
+  if (pm.status != ST_OK || pm.n_best > P.drop_rep || pm.n_best == 0) { out_n[pair] = 0; return; }
+  const Caps c = S.caps;
+  const ReadMeta *rm = S.rmeta + 2 * slot;
+  const int mb = P.max_best;
+  const int to_report = mb < pm.n_best ? mb : pm.n_best;
+  const int *sel = pair_sel + (size_t)pair * mb;
+  const u8 uniq = (pm.n_best == 1 || rm[0].n_best == 1 || rm[1].n_best == 1) ? 1 : 0;
+  const int e = P.e;
+  const int L[2] = {rm[0].len, rm[1].len};
+  const u8 *rd[2] = {read_ptr(B, pair, 0), read_ptr(B, pair, 1)};
+  // mapping_generator.h:657-917, BED/pairs branch with split_alignment
+  auto span = [&](int m, int s, u64 dpos, int split_word, u32 *st, u32 *en) {
+    const u32 rid = (u32)(dpos >> 32), rp = (u32)dpos;
+    const int full = L[m];
+    const int split_site = split_word & 0xffff;
+    int gap = (split_word >> 16) & 0xff;
+    const int actual = (split_word >> 24) & 0xff;
+    const int Ls = split_site - gap;
+    u32 vws = rp + 1u > (u32)(Ls + e) ? rp + 1u - (u32)Ls - (u32)e : 0u;
+    if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)Ls;
+    const u8 *rseq = R.seq + R.off[rid];
+    const u8 *win = rseq + vws;
+    const u8 *r = rd[m];
+    if (s == 0) {
+      int s0 = banded_traceback(e, actual, Ls, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[gap + i]; });
+      if (gap > 0) s0 = adjust_gap_beginning(0, rseq, [&](int i) { return i < full ? r[i] : (u8)0; }, &gap, Ls - 1, (int)vws + s0, (int)rp) - (int)vws;
+      *st = vws + (u32)s0;
+      *en = rp;
+      return;
+    }
+    const int rss = full - split_site;
+    const int s0 = e;
+    int en0 = (int)(rp - vws + 1u);  // kept when the aligner bails out early without writing it (mapping_generator.h:856-857)
+    banded_align(e, Ls, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(r, full, rss + i); }, &en0);
+    en0 += 1;
+    if (gap > 0)
+      en0 = adjust_gap_beginning(1, rseq, [&](int i) { return (rss + i) < full ? code_char(neg_code(r, full, rss + i)) : (u8)0; }, &gap, Ls - 1, (int)vws + s0,
+                                 (int)vws + en0) - (int)vws + 1;
+    *st = vws + (u32)s0;
+    *en = vws + (u32)en0 - 1u;
+  };
+  int idx = 0, reported = 0;
+  const int DS1[4] = {0, 1, 0, 1}, DS2[4] = {1, 0, 0, 1};
+  for (int dir = 0; dir < 4 && reported != to_report; ++dir) {
+    const int s1 = DS1[dir], s2 = DS2[dir];
+    const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const int *w1 = S.map_split + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *w2 = S.map_split + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const int want1 = rm[0].min_err, want2 = rm[1].min_err;
+    if (rm[0].n_map[s1] == 0 || rm[1].n_map[s2] == 0) continue;
+    for (int i1 = 0; i1 < rm[0].n_map[s1] && reported != to_report; ++i1) {
+      if (e1[i1] != want1) continue;
+      for (int i2 = 0; i2 < rm[1].n_map[s2]; ++i2) {
+        if (e2[i2] != want2) continue;
+        if (idx == sel[reported]) {
+          u32 st1, en1, st2, en2;
+          span(0, s1, p1[i1], w1[i1], &st1, &en1);
+          span(1, s2, p2[i2], w2[i2], &st2, &en2);
+          const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
+          u8 q1 = mapq_se_split(T, P, rm[0].n_cand[s1], rm[0].min_err, al1, L[0], 2, rm[0]);
+          u8 q2 = mapq_se_split(T, P, rm[1].n_cand[s2], rm[1].min_err, al2, L[1], 2, rm[1]);
+          q1 = (u8)xmul((double)q1, 1.2); if (q1 > 60) q1 = 60;
+          q2 = (u8)xmul((double)q2, 1.2); if (q2 > 60) q2 = 60;
+          const u8 q = q1 < q2 ? q1 : q2;
+          int rid1 = (int)(u32)(p1[i1] >> 32), rid2 = (int)(u32)(p2[i2] >> 32);
+          int pos1 = (int)(s1 == 0 ? st1 : en1), pos2 = (int)(s2 == 0 ? st2 : en2);
+          u8 str1 = s1 == 0 ? 1 : 0, str2 = s2 == 0 ? 1 : 0;
+          const bool smaller = rid1 < rid2 || (rid1 == rid2 && pos1 < pos2);
+          if (!smaller) { int tt = rid1; rid1 = rid2; rid2 = tt; tt = pos1; pos1 = pos2; pos2 = tt; const u8 ts = str1; str1 = str2; str2 = ts; }
+          OutPairs o;
+          o.read_id = B.first_read_id + (u32)pair; o.rid1 = (u32)rid1; o.rid2 = (u32)rid2; o.pos1 = (u32)pos1; o.pos2 = (u32)pos2;
+          o.strand1 = str1; o.strand2 = str2; o.mapq = q; o.is_unique = uniq;
+          out[(size_t)pair * mb + reported] = o;
+          ++reported;
+          if (reported == to_report) break;
+        }
+        ++idx;
+      }
+    }
+  }
+  out_n[pair] = reported;
+  pm.n_rec = reported;
+  if (reported > 0) { atomicAdd(&ctr->n_mapped, 1ull); if (pm.n_best == 1) atomicAdd(&ctr->n_unique, 1ull); }
 }

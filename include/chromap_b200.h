@@ -43,9 +43,9 @@ typedef struct {
   int32_t trim_adapters;
   int32_t remove_pcr_duplicates;
   int32_t tn5_shift;
-  int32_t split_alignment;        /* must be 0 in this round (Hi-C split alignment: next) */
+  int32_t split_alignment;        /* --split-alignment (Hi-C); requires output_format == 5 */
   int32_t low_memory_mode;
-  int32_t output_format;          /* 1 = BED */
+  int32_t output_format;          /* 1 = BED, 5 = pairs (MAPPINGFORMAT_PAIRS, mapping_parameters.h:9-16) */
   int32_t batch_size;             /* pairs per reference batch (chromap.h:182: 500000); fixes the
                                      taskloop chunking that seeds multi-mapper sampling */
   int32_t max_read_length;        /* upper bound on read length in any batch (sizing), default 160 */
@@ -107,8 +107,18 @@ typedef struct {
   uint16_t negative_alignment_length;
 } cmx_pe_record;
 
+/* PairsMapping (pairs_mapping.h:11-49) without the read name: what --preset hic emits (mapping_generator.cc:169-210).
+ * 24 bytes; written into the same record buffer when output_format == 5 (pairs). */
 typedef struct {
-  cmx_pe_record *records; /* caller-owned, capacity >= n_pairs * max_num_best_mappings */
+  uint32_t read_id;
+  uint32_t rid1, rid2;
+  uint32_t pos1, pos2;      /* 0-based 5' positions, (rid1, pos1) <= (rid2, pos2) */
+  uint8_t strand1, strand2; /* 1 = + */
+  uint8_t mapq, is_unique;
+} cmx_pairs_record;
+
+typedef struct {
+  cmx_pe_record *records; /* caller-owned, capacity >= n_pairs * max_num_best_mappings (cmx_pairs_record when pairs) */
   uint64_t capacity;
   uint64_t n_records;    /* out */
   int32_t on_device;     /* records is a device pointer (n_records still returned on the host) */
@@ -126,6 +136,11 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
  * chromap.h:1305-1355): sort by (rid, record order), duplicate removal, Tn5 shift, MAPQ filter.
  * In place on host records; returns the surviving count in *n_out. */
 int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *records, uint64_t n, uint64_t *n_out);
+/* Pairs post-processing (low-memory merge, mapping_writer.h:166-376 with PairsMapping order pairs_mapping.h:40-49) and
+ * text with header (mapping_writer.cc:381-421).  read_names[i] = name of read 1 of pair (read_id - first_read_id). */
+int cmx_postprocess_pairs(cmx_ctx *ctx, cmx_pairs_record *records, uint64_t n, uint64_t *n_out);
+int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint32_t n_seq, const cmx_pairs_record *records, uint64_t n,
+                         const char *const *read_names, uint32_t first_read_id, char *buf, int64_t cap);
 /* BED text (mapping_writer.cc:75-83); names = n_seq C strings.  Returns bytes (or needed size if buf NULL). */
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, uint64_t n, char *buf,
                        int64_t cap);

@@ -23,6 +23,9 @@ PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u
                       ("mapq", "u1"), ("direction", "u1"), ("is_unique", "u1"), ("num_dups", "u1"),
                       ("positive_alignment_length", "<u2"), ("negative_alignment_length", "<u2")], align=True)
 
+PAIRS_RECORD = np.dtype([("read_id", "<u4"), ("rid1", "<u4"), ("rid2", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("strand1", "u1"),
+                         ("strand2", "u1"), ("mapq", "u1"), ("is_unique", "u1")], align=True)
+
 TRACE = np.dtype([("n_minimizers", "<i4", 2), ("n_pos_candidates_gen", "<i4", 2), ("n_neg_candidates_gen", "<i4", 2),
                   ("n_pos_candidates", "<i4", 2), ("n_neg_candidates", "<i4", 2), ("n_pos_mappings", "<i4", 2),
                   ("n_neg_mappings", "<i4", 2), ("min_errors", "<i4", 2), ("second_min_errors", "<i4", 2),
@@ -161,7 +164,7 @@ def map_pairs(params, index, ref, seq1, off1, seq2, off2, first_read_id=0, n_thr
     if not m:
         raise ValueError("unsupported parameters for the oracle (BED, non-split, e < 16 only)")
     n = len(off1) - 1
-    out = np.zeros(n * params.max_num_best_mappings, dtype=PE_RECORD)
+    out = np.zeros(n * params.max_num_best_mappings, dtype=PAIRS_RECORD if params.output_format == 5 else PE_RECORD)
     tr = np.zeros(n, dtype=TRACE) if trace else None
     seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
     off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)

@@ -277,3 +277,62 @@ def test_bigger_synthetic_with_heavy_repeats_equals_oracle(tmp_path):
         assert_same_records(recs, orecs)
         obed = orc.format_bed(oref, orc.postprocess(orc.make_params(preset, **kw), orecs))
         assert m.format_bed(m.postprocess(recs)) == obed
+
+
+HIC_CASES = {
+    "hic": dict(),
+    "hic_q0": dict(mapq_threshold=0),
+    "hic_e6dedup": dict(mapq_threshold=0, error_threshold=6, remove_pcr_duplicates=1),
+}
+
+
+def _read_names(path):
+    import gzip as gz
+    names = []
+    with gz.open(path, "rb") as f:
+        for i, line in enumerate(f):
+            if i % 4 == 0:
+                names.append(line[1:].split()[0])
+    return names
+
+
+@pytest.mark.parametrize("case", sorted(HIC_CASES))
+def test_hic_split_alignment_equals_oracle_and_golden(case, golden_dir):
+    """--preset hic: split alignment, four pairing directions, pairs output (BASELINE config 5 semantics)."""
+    d = os.path.join(golden_dir, "synth_hic")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    kw = HIC_CASES[case]
+    m = cb.Mapper(cb.make_params("hic", max_read_length=160, **kw))
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    recs, stats = m.map_batch(s1, o1, s2, o2)
+    orecs, otrace = orc.map_pairs(orc.make_params("hic", **kw), oidx, oref, s1, o1, s2, o2, trace=True)
+    tr = m.trace(len(o1) - 1)
+    alive = otrace["n_records"] > 0
+    for f in ("n_minimizers", "n_pos_candidates", "n_neg_candidates", "n_pos_mappings", "n_neg_mappings", "min_errors", "n_best", "n_best_pairs"):
+        bad = np.nonzero((tr[f][alive] != otrace[f][alive]).reshape(alive.sum(), -1).any(axis=1))[0]
+        assert len(bad) == 0, (f, np.nonzero(alive)[0][bad[:5]], tr[f][alive][bad[:5]], otrace[f][alive][bad[:5]])
+    assert_same_records(recs, orecs)
+    assert stats["n_overflow_pairs"] == 0
+    text = m.format_pairs(m.postprocess_pairs(recs), _read_names(os.path.join(d, "read1.fq.gz")), [len(s) for s in seqs])
+    assert text == gzip.open(os.path.join(d, case + ".pairs.gz")).read()
+
+
+def test_hic_reference_quickstart_golden(golden_dir):
+    import hashlib
+    d = os.path.join(golden_dir, "ref_test")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(os.path.join(d, "ref.index"))
+    a = oidx.arrays()
+    s1, o1, s2, o2 = load_pairs(d, "read1.fq", "read2.fq")
+    m = cb.Mapper(cb.make_params("hic", max_read_length=128))
+    m.upload_reference(seqs, names)
+    m.upload_index(oidx.k, oidx.w, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    recs, _ = m.map_batch(s1, o1, s2, o2)
+    rn = [l[1:].split()[0] for i, l in enumerate(open(os.path.join(d, "read1.fq"), "rb")) if i % 4 == 0]
+    text = m.format_pairs(m.postprocess_pairs(recs), rn, [len(s) for s in seqs])
+    assert hashlib.md5(text).hexdigest() == "fc844a251ebdcec0f641b59fef804d0f"
