@@ -26,19 +26,20 @@ static double Now() { return std::chrono::duration<double>(std::chrono::steady_c
 struct Batch {
   std::string s1, s2;
   std::vector<uint32_t> o1{0}, o2{0};
+  std::vector<std::string> names1;  // read-1 names, kept for pairs output only
   uint32_t n = 0, first_id = 0;
-  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); n = 0; }
+  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); n = 0; }
 };
 
 // LoadPairedEndReadsWithBarcodes (chromap.cc:93-174, non-barcode): empty reads are skipped per file
 // (sequence_batch.cc:28-31), the two files must run out together.
-static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b) {
+static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names) {
   std::string n, s, q;
   b->Clear();
   while (b->n < max_pairs) {
     bool a = r1.Next(&n, &s, &q);
     while (a && s.empty()) a = r1.Next(&n, &s, &q);
-    if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); }
+    if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); if (keep_names) b->names1.push_back(n); }
     bool c = r2.Next(&n, &s, &q);
     while (c && s.empty()) c = r2.Next(&n, &s, &q);
     if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
@@ -87,13 +88,17 @@ int main(int argc, char **argv) {
     else if (a == "--Tn5-shift") p.tn5_shift = 1;
     else if (a == "--low-mem") p.low_memory_mode = 1;
     else if (a == "--BED") { bed = true; user_set_format = true; }
-    else if (a == "--split-alignment" || a == "--SAM" || a == "--TagAlign" || a == "--pairs" || a == "--PAF" || a == "-b" || a == "--barcode" ||
+    else if (a == "--split-alignment") p.split_alignment = 1;
+    else if (a == "--pairs") p.output_format = 5;
+    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "-b" || a == "--barcode" ||
              a == "--barcode-whitelist" || a == "-n" || a == "--summary")
-      Die("chromap-b200: option " + a + " is not on the GPU path yet (paired-end BED, non-split only); use the reference chromap for it");
+      Die("chromap-b200: option " + a + " is not on the GPU path yet (paired-end BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
   (void)bed; (void)user_set_format;
-  if (p.output_format != 1 || p.split_alignment) Die("chromap-b200: this preset needs split alignment / pairs output, which is not on the GPU path yet");
+  if (!((p.output_format == 1 && !p.split_alignment) || (p.output_format == 5 && p.split_alignment)))
+    Die("chromap-b200: supported outputs are paired-end BED (no split alignment) and Hi-C pairs (--split-alignment --pairs / --preset hic)");
+  const bool pairs = p.output_format == 5;
   cmx_ctx *ctx = nullptr;
   const double t_start = Now();
   if (build_index) {  // chromap_driver.cc:451-471
@@ -142,10 +147,11 @@ int main(int argc, char **argv) {
   uint64_t n_pairs = 0, n_mapped = 0, n_unique = 0, n_cand = 0;
   const double t_map = Now();
   uint32_t read_id = 0;
-  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur);
+  std::vector<std::string> all_names;
+  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs);
   while (cur.n > 0) {
     cur.first_id = read_id;
-    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next); });
+    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs); });
     recs.resize((size_t)cur.n * p.max_num_best_mappings);
     cmx_batch in{cur.n, cur.s1.data(), cur.o1.data(), cur.s2.data(), cur.o2.data(), cur.first_id, 0};
     cmx_records out{recs.data(), recs.size(), 0, 0, 0, 0, 0, 0};
@@ -153,6 +159,7 @@ int main(int argc, char **argv) {
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
     all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
+    if (pairs) all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
     n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
     read_id += cur.n;
     loader.join();
@@ -163,12 +170,26 @@ int main(int argc, char **argv) {
           (unsigned long long)(2 * n_pairs), (unsigned long long)(2 * n_mapped), (unsigned long long)(2 * n_unique), (unsigned long long)n_cand);
   uint64_t keep = 0;
   const double t_pp = Now();
-  if (cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
   std::vector<const char *> names;
   for (const auto &s : ref.names) names.push_back(s.c_str());
-  const int64_t bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
-  std::vector<char> text((size_t)bytes + 1);
-  cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);
+  std::vector<char> text;
+  int64_t bytes = 0;
+  if (pairs) {
+    cmx_pairs_record *pr = reinterpret_cast<cmx_pairs_record *>(all.data());
+    if (cmx_postprocess_pairs(ctx, pr, all.size(), &keep)) Die(cmx_last_error(ctx));
+    std::vector<const char *> rn;
+    for (const auto &s : all_names) rn.push_back(s.c_str());
+    std::vector<uint32_t> lens;
+    for (size_t i = 0; i + 1 < ref.offsets.size(); ++i) lens.push_back((uint32_t)(ref.offsets[i + 1] - ref.offsets[i]));
+    bytes = cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, nullptr, 0);
+    text.resize((size_t)bytes + 1);
+    cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
+  } else {
+    if (cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+    bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
+    text.resize((size_t)bytes + 1);
+    cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);
+  }
   FILE *fo = fopen(out_path.c_str(), "wb");
   if (!fo) Die("Cannot open output file " + out_path);
   fwrite(text.data(), 1, (size_t)bytes, fo);

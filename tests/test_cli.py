@@ -22,7 +22,7 @@ def test_cli_rejects_unsupported_and_missing_gpu():
     cli = _ensure_cli()
     r = subprocess.run([cli, "--preset", "nope"], capture_output=True, text=True)
     assert r.returncode != 0 and "Unrecognized preset" in r.stderr
-    r = subprocess.run([cli, "--preset", "hic", "-x", "a", "-r", "b"], capture_output=True, text=True)
+    r = subprocess.run([cli, "--SAM", "-x", "a", "-r", "b"], capture_output=True, text=True)
     assert r.returncode != 0 and "not on the GPU path" in r.stderr
     import torch
     if not torch.cuda.is_available():
@@ -65,3 +65,16 @@ def test_index_file_written_by_cli_is_loadable_by_the_reference_binary(tmp_path,
     subprocess.check_call([REF_BIN, "-x", idx, "-r", ref, "-1", str(tmp_path / "read1.fq"), "-2", str(tmp_path / "read2.fq"), "-o", out, "-t", "2"],
                           stderr=subprocess.DEVNULL)
     assert open(out, "rb").read() == gzip.open(os.path.join(d, "default.bed.gz")).read()
+
+
+@pytest.mark.gpu
+def test_cli_hic_preset_pairs_output(tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_hic")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for case, args in (("hic", []), ("hic_q0", ["-q", "0"]), ("hic_e6dedup", ["-q", "0", "-e", "6", "--remove-pcr-duplicates"])):
+        out = str(tmp_path / (case + ".pairs"))
+        subprocess.check_call([cli, "--preset", "hic"] + args + ["-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
+                                                                "-2", os.path.join(d, "read2.fq.gz"), "-o", out], stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".pairs.gz")).read()
