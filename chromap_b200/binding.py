@@ -26,13 +26,15 @@ class Params(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [("n_pairs", C.c_uint32), ("seq1", C.c_void_p), ("off1", C.c_void_p), ("seq2", C.c_void_p),
-                ("off2", C.c_void_p), ("first_read_id", C.c_uint32), ("on_device", C.c_int32)]
+                ("off2", C.c_void_p), ("first_read_id", C.c_uint32), ("on_device", C.c_int32),
+                ("bc_seq", C.c_void_p), ("bc_qual", C.c_void_p), ("bc_len", C.c_uint32)]
 
 
 class Records(C.Structure):
     _fields_ = [("records", C.c_void_p), ("capacity", C.c_uint64), ("n_records", C.c_uint64), ("on_device", C.c_int32),
                 ("n_mapped_pairs", C.c_uint64), ("n_uniquely_mapped_pairs", C.c_uint64), ("n_candidates", C.c_uint64),
-                ("n_overflow_pairs", C.c_uint64)]
+                ("n_overflow_pairs", C.c_uint64), ("barcode_keys", C.c_void_p), ("n_barcodes_in_whitelist", C.c_uint64),
+                ("n_barcodes_corrected", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -89,6 +91,9 @@ def load_library():
     L.cmx_download_index.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), vp, vp, vp, C.POINTER(u32), vp]
     L.cmx_index_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.cmx_map_batch_pe.argtypes = [vp, C.POINTER(Batch), C.POINTER(Records), vp]
+    L.cmx_upload_barcode_whitelist.argtypes = [vp, vp, vp, u64, u64, u32, i32, C.c_double, i32]
+    L.cmx_postprocess_bc.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.cmx_format_bed_bc.restype = i64; L.cmx_format_bed_bc.argtypes = [vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
     L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
@@ -204,22 +209,35 @@ class Mapper:
                                               C.byref(no), occ.ctypes.data if no.value else None), "cmx_download_index")
         return dict(n_buckets=nb.value, n_keys=nk.value, flags=flags, keys=keys, vals=vals, occ=occ)
 
-    def map_batch(self, seq1, off1, seq2, off2, first_read_id=0, on_device=False, n_pairs=None, out=None, out_on_device=False):
+    def upload_barcode_whitelist(self, keys, counts, num_sample, bc_len, err_threshold=1, prob_threshold=0.9, output_not_in_whitelist=False):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64); counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        self._check(self.L.cmx_upload_barcode_whitelist(self.h, keys.ctypes.data, counts.ctypes.data, len(keys), int(num_sample), bc_len,
+                                                        err_threshold, prob_threshold, int(output_not_in_whitelist)), "cmx_upload_barcode_whitelist")
+
+    def map_batch(self, seq1, off1, seq2, off2, first_read_id=0, on_device=False, n_pairs=None, out=None, out_on_device=False,
+                  barcodes=None, barcode_quals=None, bc_len=0):
         """Host numpy arrays (or device pointers / torch tensors when on_device).  Returns (records, stats)."""
         n = n_pairs if n_pairs is not None else len(off1) - 1
         if not on_device:
             seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
             off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
-        b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), first_read_id, 1 if on_device else 0)
+        if barcodes is not None and not on_device:
+            barcodes = np.ascontiguousarray(barcodes, dtype=np.uint8); barcode_quals = np.ascontiguousarray(barcode_quals, dtype=np.uint8)
+        b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), first_read_id, 1 if on_device else 0,
+                  _ptr(barcodes), _ptr(barcode_quals), bc_len if barcodes is not None else 0)
         mb = self.params.max_num_best_mappings
         if out is None:
             out = np.zeros(n * mb, dtype=PAIRS_RECORD if self.params.output_format == 5 else PE_RECORD)
         cap = (out.numel() * out.element_size() // 24) if hasattr(out, "data_ptr") else len(out)
-        r = Records(_ptr(out), cap, 0, 1 if out_on_device else 0, 0, 0, 0, 0)
+        bck = np.zeros(cap, dtype=np.uint64) if (barcodes is not None and not out_on_device) else None
+        r = Records(_ptr(out), cap, 0, 1 if out_on_device else 0, 0, 0, 0, 0, _ptr(bck), 0, 0)
         rc = self.L.cmx_map_batch_pe(self.h, C.byref(b), C.byref(r), None)
         self._check(rc, "cmx_map_batch_pe")
         stats = dict(n_records=r.n_records, n_mapped_pairs=r.n_mapped_pairs, n_uniquely_mapped_pairs=r.n_uniquely_mapped_pairs,
-                     n_candidates=r.n_candidates, n_overflow_pairs=r.n_overflow_pairs)
+                     n_candidates=r.n_candidates, n_overflow_pairs=r.n_overflow_pairs, n_barcodes_in_whitelist=r.n_barcodes_in_whitelist,
+                     n_barcodes_corrected=r.n_barcodes_corrected)
+        if bck is not None:
+            stats["barcode_keys"] = bck[:r.n_records]
         if out_on_device:
             return out, stats
         return out[:r.n_records], stats
@@ -255,6 +273,21 @@ class Mapper:
         n = self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, None, 0)
         buf = C.create_string_buffer(n + 1)
         self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, buf, n)
+        return buf.raw[:n]
+
+    def postprocess_bc(self, recs, bcs):
+        recs = np.ascontiguousarray(recs.copy()); bcs = np.ascontiguousarray(bcs.copy(), dtype=np.uint64)
+        n = C.c_uint64()
+        self._check(self.L.cmx_postprocess_bc(self.h, recs.ctypes.data, bcs.ctypes.data, len(recs), C.byref(n)), "cmx_postprocess_bc")
+        return recs[:n.value], bcs[:n.value]
+
+    def format_bed_bc(self, recs, bcs, bc_len, names=None):
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        recs = np.ascontiguousarray(recs); bcs = np.ascontiguousarray(bcs, dtype=np.uint64)
+        n = self.L.cmx_format_bed_bc(arr, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.cmx_format_bed_bc(arr, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, buf, n)
         return buf.raw[:n]
 
     def format_bed(self, recs, names=None):

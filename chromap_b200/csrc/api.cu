@@ -60,6 +60,14 @@ struct cmx_ctx {
   u32 n_occ = 0;
   u64 n_keys = 0;
   int k = 0, w = 0;
+  // scATAC barcode whitelist
+  ulonglong2 *wl_slots = nullptr;
+  u64 wl_n_slots = 0, wl_num_sample = 0;
+  double *wl_pow = nullptr;
+  u32 wl_bc_len = 0;
+  int wl_err = 1, wl_output_nw = 0, wl_active = 0;
+  double wl_prob = 0.9;
+  DevBuf bc_seq, bc_qual, bc_key, bc_ok, bc_out;
   // mapq tables
   double *inv_log = nullptr;
   int *pen_thr = nullptr;
@@ -70,6 +78,7 @@ struct cmx_ctx {
   Tier tiers[N_TIERS];
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
   std::vector<cudaEvent_t> ev_up;
+  cudaEvent_t ev_bc = nullptr;
   cudaEvent_t ev[10];
   cudaEvent_t ev_sub[2];
   float ms_minimizer = 0, ms_probe = 0, ms_cluster = 0;
@@ -184,7 +193,8 @@ void cmx_destroy(cmx_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
   cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr);
-  cudaFree(ctx->ctr); cudaFree(ctx->d_count);
+  cudaFree(ctx->ctr); cudaFree(ctx->d_count); cudaFree(ctx->wl_slots); cudaFree(ctx->wl_pow);
+  for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->bc_key, &ctx->bc_ok, &ctx->bc_out}) release(*b);
   for (DevBuf *b : {&ctx->rescue_list, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->nbest, &ctx->sel, &ctx->out_rec, &ctx->out_n, &ctx->offs,
                     &ctx->out_compact, &ctx->chunk_start, &ctx->cub_tmp, &ctx->trace})
     release(*b);
@@ -266,6 +276,36 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   CU(cudaMalloc(&ctx->occ, (size_t)std::max<u32>(n_occ, 1) * sizeof(u64)));
   if (n_occ) CU(cudaMemcpy(ctx->occ, occ, (size_t)n_occ * sizeof(u64), cudaMemcpyHostToDevice));
   ctx->n_occ = n_occ; ctx->k = k; ctx->w = w;
+  return CMX_OK;
+}
+
+int cmx_upload_barcode_whitelist(cmx_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint64_t num_sample, uint32_t bc_len,
+                                 int err_threshold, double prob_threshold, int output_not_in_whitelist) {
+  if (!ctx || (n && (!keys || !counts)) || bc_len == 0 || bc_len > 32) return CMX_ERR_INVALID;
+  if (err_threshold < 0 || err_threshold > 1) return fail(ctx, CMX_ERR_INVALID, "--bc-error-threshold %d is not on the GPU path (0 or 1)", err_threshold);
+  CU(cudaSetDevice(ctx->device));
+  cudaFree(ctx->wl_slots); ctx->wl_slots = nullptr;
+  u64 ns = 64;
+  while (ns < 2 * n) ns <<= 1;
+  CU(cudaMalloc(&ctx->wl_slots, ns * sizeof(ulonglong2)));
+  CU(cudaMemset(ctx->wl_slots, 0xFF, ns * sizeof(ulonglong2)));
+  if (n) {
+    u64 *dk; u32 *dc;
+    CU(cudaMalloc(&dk, n * 8)); CU(cudaMalloc(&dc, n * 4));
+    CU(cudaMemcpy(dk, keys, n * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dc, counts, n * 4, cudaMemcpyHostToDevice));
+    wl_insert_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dk, dc, n, ctx->wl_slots, ns - 1, table_shift(ns));
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    cudaFree(dk); cudaFree(dc);
+  }
+  if (!ctx->wl_pow) {
+    std::vector<double> pw(41);
+    for (int q = 0; q <= 40; ++q) pw[q] = pow(10.0, ((-q) / 10.0));  // host libm, chromap.cc:629-630
+    CU(cudaMalloc(&ctx->wl_pow, 41 * sizeof(double)));
+    CU(cudaMemcpy(ctx->wl_pow, pw.data(), 41 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  ctx->wl_n_slots = ns; ctx->wl_num_sample = num_sample; ctx->wl_bc_len = bc_len; ctx->wl_err = err_threshold; ctx->wl_prob = prob_threshold;
+  ctx->wl_output_nw = output_not_in_whitelist; ctx->wl_active = 1;
   return CMX_OK;
 }
 
@@ -428,7 +468,7 @@ static int upload_batch(cmx_ctx *ctx, const cmx_batch *in, DevBatch *B) {
     B->seq1 = (const u8 *)ctx->seq1.p; B->off1 = (const u32 *)ctx->off1.p;
     B->seq2 = (const u8 *)ctx->seq2.p; B->off2 = (const u32 *)ctx->off2.p;
   }
-  B->n_pairs = n; B->first_read_id = in->first_read_id;
+  B->n_pairs = n; B->first_read_id = in->first_read_id; B->bc_ok = nullptr;
   return CMX_OK;
 }
 
@@ -444,7 +484,8 @@ struct BatchAcc {  // per-call accumulators over sub-batches
 // The whole device pipeline over pairs already resident in HBM; records compacted in read order into `dst`
 // (device).  Synchronous on the context's stream.
 static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64 *total_out, BatchAcc &acc, u32 piece = 0,
-                            const std::vector<cudaEvent_t> *piece_ready = nullptr) {
+                            const std::vector<cudaEvent_t> *piece_ready = nullptr, const u8 *bc_dev_seq = nullptr, const u8 *bc_dev_qual = nullptr,
+                            u32 bc_len = 0, cudaEvent_t bc_ready = nullptr, u64 *bc_dst = nullptr) {
   const u32 n = B.n_pairs;
   const int mb = ctx->params.max_num_best_mappings;
   cudaStream_t st = ctx->stream;
@@ -461,6 +502,18 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
   CU(cudaMemsetAsync(ctx->nbest.p, 0, (size_t)n * 4, st));
   CU(cudaMemsetAsync(ctx->out_n.p, 0, (size_t)(n + 1) * 4, st));
   CU(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), st));
+  DevBatch Bx = B;  // with the barcode gate, when barcodes came with the batch
+  if (bc_dev_seq) {
+    DevWhitelist W;
+    W.slots = ctx->wl_slots; W.mask = ctx->wl_n_slots ? ctx->wl_n_slots - 1 : 0; W.shift = ctx->wl_n_slots ? table_shift(ctx->wl_n_slots) : 0;
+    W.num_sample = (double)ctx->wl_num_sample; W.pow_tab = ctx->wl_pow; W.err_threshold = ctx->wl_err; W.prob_threshold = ctx->wl_prob;
+    W.output_not_in_whitelist = ctx->wl_output_nw; W.active = ctx->wl_active;
+    CU(ensure(ctx->bc_key, (size_t)n * 8)); CU(ensure(ctx->bc_ok, (size_t)n));
+    if (bc_ready) CU(cudaStreamWaitEvent(st, bc_ready, 0));
+    barcode_kernel<<<(n + 127) / 128, 128, 0, st>>>(W, bc_dev_seq, bc_dev_qual, (int)bc_len, (int)n, (u64 *)ctx->bc_key.p, (u8 *)ctx->bc_ok.p, ctx->ctr);
+    acc.launches += 1;
+    Bx.bc_ok = (const u8 *)ctx->bc_ok.p;
+  }
   int n_slots = (int)n;
   const int *pair_list = nullptr;
   int tiers_used = 0;
@@ -481,14 +534,15 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
         Scratch V = S;
         V.n_slots = (int)np; V.rmeta += 2 * (size_t)p0; V.pmeta += p0;
         V.mm_hash += 2 * (size_t)p0 * S.caps.maxmm; V.mm_val += 2 * (size_t)p0 * S.caps.maxmm; V.mm_pos += 2 * (size_t)p0 * S.caps.maxmm;
-        DevBatch Bq = B;
+        DevBatch Bq = Bx;
+        if (Bq.bc_ok) Bq.bc_ok += p0;
         Bq.off1 += p0; Bq.off2 += p0; Bq.n_pairs = np;
         prep_kernel<<<(np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V);
         minimizer_kernel<<<(2 * np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V, ctx->ctr);
         acc.launches += 2;
       }
     } else {
-      prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
+      prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, Bx, S);
       if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, ctx->ctr);
     }
     if (t == 0) {
@@ -574,6 +628,10 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
   cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
   compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)ctx->out_rec.p, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, dst);
   acc.launches += 2;
+  if (bc_dst && bc_dev_seq) {
+    compact_bc_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, (const u64 *)ctx->bc_key.p, bc_dst);
+    acc.launches += 1;
+  }
   u64 total = 0;
   CU(cudaEventRecord(ctx->ev[4], st));
   CU(cudaMemcpyAsync(&total, (u64 *)ctx->offs.p + n, 8, cudaMemcpyDeviceToHost, st));
@@ -603,6 +661,9 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   const u32 n = in->n_pairs;
   const int mb = ctx->params.max_num_best_mappings;
   out->n_records = 0; out->n_mapped_pairs = out->n_uniquely_mapped_pairs = out->n_candidates = out->n_overflow_pairs = 0;
+  out->n_barcodes_in_whitelist = out->n_barcodes_corrected = 0;
+  if (in->bc_seq && (in->bc_len == 0 || in->bc_len > 32 || !in->bc_qual)) return fail(ctx, CMX_ERR_INVALID, "barcodes need bc_qual and 1 <= bc_len <= 32");
+  if (in->bc_seq && ctx->params.split_alignment) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with split alignment");
   if (n == 0) return CMX_OK;
   if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
   CU(cudaSetDevice(ctx->device));
@@ -615,18 +676,31 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   const u32 bs = (u32)ctx->params.batch_size;
   if (in->on_device || out->on_device || n <= bs) {
     // single pass: upload (if needed), map, download
-    DevBatch B;
+    DevBatch B{};
     int rc = upload_batch(ctx, in, &B);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], st));
     OutRecord *dst;
     if (out->on_device) dst = (OutRecord *)out->records;
     else { CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)ctx->out_compact.p; }
-    rc = run_device_batch(ctx, B, dst, &total, acc);
+    const u8 *bcs = nullptr, *bcq = nullptr;
+    u64 *bc_dst = nullptr;
+    if (in->bc_seq && in->bc_len) {
+      if (in->on_device) { bcs = (const u8 *)in->bc_seq; bcq = (const u8 *)in->bc_qual; }
+      else {
+        CU(ensure(ctx->bc_seq, (size_t)n * in->bc_len + 16)); CU(ensure(ctx->bc_qual, (size_t)n * in->bc_len + 16));
+        CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->bc_qual.p, in->bc_qual, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, st));
+        bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
+      }
+      if (out->barcode_keys) { CU(ensure(ctx->bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)ctx->bc_out.p; }
+    }
+    rc = run_device_batch(ctx, B, dst, &total, acc, 0, nullptr, bcs, bcq, in->bc_len, nullptr, bc_dst);
     if (rc) return rc;
     cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);
     CU(cudaEventRecord(ctx->ev[1], st));
     if (!out->on_device && total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
+    if (bc_dst && total) CU(cudaMemcpyAsync(out->barcode_keys, bc_dst, total * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev[5], st));
     CU(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
@@ -642,21 +716,35 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     while (ctx->ev_up.size() < n_sub) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
     CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
     CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
+    if (in->bc_seq && in->bc_len) {
+      CU(ensure(ctx->bc_seq, (size_t)n * in->bc_len + 16)); CU(ensure(ctx->bc_qual, (size_t)n * in->bc_len + 16));
+      CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, ctx->up_stream));
+      CU(cudaMemcpyAsync(ctx->bc_qual.p, in->bc_qual, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, ctx->up_stream));
+      if (!ctx->ev_bc) CU(cudaEventCreateWithFlags(&ctx->ev_bc, cudaEventDisableTiming));
+      CU(cudaEventRecord(ctx->ev_bc, ctx->up_stream));
+    }
     for (u32 s = 0; s < n_sub; ++s) {
       const u32 p0 = s * bs, p1 = std::min(n, p0 + bs);
       CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, ctx->up_stream));
       CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, ctx->up_stream));
       CU(cudaEventRecord(ctx->ev_up[s], ctx->up_stream));
     }
-    DevBatch B;
+    DevBatch B{};
     B.seq1 = (const u8 *)ctx->seq1.p; B.off1 = (const u32 *)ctx->off1.p;
     B.seq2 = (const u8 *)ctx->seq2.p; B.off2 = (const u32 *)ctx->off2.p;
     B.n_pairs = n; B.first_read_id = in->first_read_id;
     OutRecord *dst = (OutRecord *)ctx->out_compact.p;
-    const int rc = run_device_batch(ctx, B, dst, &total, acc, bs, &ctx->ev_up);
+    const u8 *bcs = nullptr, *bcq = nullptr;
+    u64 *bc_dst = nullptr;
+    if (in->bc_seq && in->bc_len) {
+      bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
+      if (out->barcode_keys) { CU(ensure(ctx->bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)ctx->bc_out.p; }
+    }
+    const int rc = run_device_batch(ctx, B, dst, &total, acc, bs, &ctx->ev_up, bcs, bcq, in->bc_len, bcs ? ctx->ev_bc : nullptr, bc_dst);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], st));
     if (total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
+    if (bc_dst && total) CU(cudaMemcpyAsync(out->barcode_keys, bc_dst, total * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev[5], st));
     CU(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
@@ -666,6 +754,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   out->n_records = total;
   out->n_mapped_pairs = acc.c.n_mapped; out->n_uniquely_mapped_pairs = acc.c.n_unique; out->n_candidates = acc.c.n_candidates;
   out->n_overflow_pairs = acc.n_overflow;
+  out->n_barcodes_in_whitelist = acc.c.n_bc_in_whitelist; out->n_barcodes_corrected = acc.c.n_bc_corrected;
   cmx_timing &tm = ctx->timing;
   memset(&tm, 0, sizeof(tm));
   tm.h2d_ms = ms_h2d; tm.d2h_ms = ms_d2h;
@@ -736,7 +825,7 @@ int cmx_stage_minimizers(cmx_ctx *ctx, const cmx_batch *in, uint64_t *out_hash, 
   if (!ctx || !in || !out_hash || !out_pos || !out_n) return CMX_ERR_INVALID;
   if (!ctx->k) return fail(ctx, CMX_ERR_STATE, "index (k, w) not set");
   CU(cudaSetDevice(ctx->device));
-  DevBatch B;
+  DevBatch B{};
   int rc = upload_batch(ctx, in, &B);
   if (rc) return rc;
   const size_t R = 2 * (size_t)in->n_pairs;
@@ -926,6 +1015,60 @@ int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint
     const std::string line = std::string(read_names[r.read_id - first_read_id]) + "\t" + names[r.rid1] + "\t" + std::to_string(r.pos1 + 1) + "\t" + names[r.rid2] +
                              "\t" + std::to_string(r.pos2 + 1) + "\t" + (r.strand1 ? "+" : "-") + "\t" + (r.strand2 ? "+" : "-") + "\tUU\t" +
                              std::to_string(r.mapq) + "\t" + std::to_string(r.mapq) + "\n";
+    if (buf && len + (int64_t)line.size() <= cap) memcpy(buf + len, line.data(), line.size());
+    len += (int64_t)line.size();
+  }
+  return len;
+}
+
+int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t *bcs, uint64_t n, uint64_t *n_out) {
+  if (!ctx || (n && (!recs || !bcs)) || !n_out) return CMX_ERR_INVALID;
+  const cmx_params &p = ctx->params;
+  *n_out = 0;
+  if (n == 0) return CMX_OK;
+  std::vector<cmx_pe_record> rr(recs, recs + n);
+  std::vector<uint64_t> bb(bcs, bcs + n);
+  if (!p.low_memory_mode && p.tn5_shift) for (auto &r : rr) tn5(r);
+  std::vector<uint64_t> ord(n);
+  for (uint64_t i = 0; i < n; ++i) ord[i] = i;
+  auto key = [&](uint64_t i) {  // bed_mapping.h:145-153 prefixed by rid
+    const cmx_pe_record &r = rr[i];
+    return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bb[i], r.mapq, r.direction, r.is_unique, r.read_id);
+  };
+  std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return key(a) < key(b); });
+  auto same = [&](uint64_t a, uint64_t b) {  // bed_mapping.h:154-159: cell-level duplicates
+    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && rr[a].fragment_length == rr[b].fragment_length && bb[a] == bb[b];
+  };
+  uint64_t o = 0, i = 0;
+  while (i < n) {
+    uint64_t j = i + 1, keep = ord[i];
+    uint32_t dups = 1;
+    if (p.remove_pcr_duplicates)
+      for (; j < n && same(ord[j], ord[i]); ++j) {
+        ++dups;
+        if (p.low_memory_mode) { if (rr[ord[j]].mapq > rr[keep].mapq) keep = ord[j]; }
+        else keep = ord[j];
+      }
+    cmx_pe_record k = rr[keep];
+    if (k.mapq >= p.mapq_threshold) {
+      if (p.remove_pcr_duplicates) k.num_dups = (uint8_t)std::min<uint32_t>(255, dups);
+      if (p.low_memory_mode && p.tn5_shift) tn5(k);
+      recs[o] = k; bcs[o] = bb[keep]; ++o;
+    }
+    i = j;
+  }
+  *n_out = o;
+  return CMX_OK;
+}
+
+int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *recs, const uint64_t *bcs, uint64_t n, uint32_t bc_len, char *buf, int64_t cap) {
+  int64_t len = 0;
+  static const char tab[4] = {'A', 'C', 'G', 'T'};
+  for (uint64_t i = 0; i < n; ++i) {  // mapping_writer.cc:127-137, barcode_translator.h:114-123
+    const cmx_pe_record &r = recs[i];
+    std::string line = std::string(names[r.rid]) + "\t" + std::to_string(r.fragment_start) + "\t" + std::to_string((uint32_t)(r.fragment_start + r.fragment_length)) + "\t";
+    for (uint32_t j = 0; j < bc_len; ++j) line.push_back(tab[(bcs[i] >> ((bc_len - 1 - j) * 2)) & 3]);
+    line += "\t" + std::to_string((uint32_t)r.num_dups) + "\n";
     if (buf && len + (int64_t)line.size() <= cap) memcpy(buf + len, line.data(), line.size());
     len += (int64_t)line.size();
   }

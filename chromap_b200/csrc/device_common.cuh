@@ -72,6 +72,7 @@ struct DevBatch {
   const u32 *off2;
   u32 n_pairs;
   u32 first_read_id;
+  const u8 *bc_ok;  // scATAC: 0 = barcode not in the whitelist -> the pair is not mapped (nullptr for bulk data)
 };
 
 // One scratch tier: arrays indexed by slot (pair slot s -> read slots 2s, 2s+1).

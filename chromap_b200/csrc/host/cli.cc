@@ -153,8 +153,10 @@ int main(int argc, char **argv) {
     cur.first_id = read_id;
     std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs); });
     recs.resize((size_t)cur.n * p.max_num_best_mappings);
-    cmx_batch in{cur.n, cur.s1.data(), cur.o1.data(), cur.s2.data(), cur.o2.data(), cur.first_id, 0};
-    cmx_records out{recs.data(), recs.size(), 0, 0, 0, 0, 0, 0};
+    cmx_batch in{};
+    in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = cur.s2.data(); in.off2 = cur.o2.data(); in.first_read_id = cur.first_id;
+    cmx_records out{};
+    out.records = recs.data(); out.capacity = recs.size();
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);

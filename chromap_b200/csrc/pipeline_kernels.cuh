@@ -12,6 +12,7 @@ struct MapqTables {
 
 struct Counters {  // device-side statistics (atomics)
   u64 n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_candidates, n_mapped, n_unique, n_overflow;
+  u64 n_bc_in_whitelist, n_bc_corrected;
   u64 ovf_reason[8];  // tier-0 escalations by cause: 0 read length, 1 #minimizers, 2 seed hits, 3 seed candidates, 4 rescue hits, 5 rescue/merge candidates, 6 draft mappings
 };
 
@@ -37,7 +38,8 @@ __global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
   PairMeta pm;
   pm.status = ST_OK; pm.sup = 0; pm.min_sum = 0; pm.second_min_sum = 0; pm.n_best = 0; pm.n_second_best = 0; pm.n_rec = 0; pm.pad = 0;
   int len1 = read_raw_len(B, pair, 0), len2 = read_raw_len(B, pair, 1);
-  if (len1 < P.min_read_len || len2 < P.min_read_len) pm.status = ST_DROP;
+  if (B.bc_ok && !B.bc_ok[pair]) pm.status = ST_DROP;  // chromap.h:908-909
+  else if (len1 < P.min_read_len || len2 < P.min_read_len) pm.status = ST_DROP;
   else if (len1 > S.caps.maxmm || len2 > S.caps.maxmm) pm.status = ST_OVERFLOW;  // longer than max_read_length
   else if (P.trim) {
     const u8 *raw1 = read_ptr(B, pair, 0), *raw2 = read_ptr(B, pair, 1);
@@ -2301,4 +2303,117 @@ __global__ void emit_split_kernel(DevParams P, DevRef R, DevBatch B, MapqTables 
   out_n[pair] = reported;
   pm.n_rec = reported;
   if (reported > 0) { atomicAdd(&ctr->n_mapped, 1ull); if (pm.n_best == 1) atomicAdd(&ctr->n_unique, 1ull); }
+}
+
+
+// =================================================================================================
+// scATAC cell barcodes: CorrectBarcodeAt (chromap.cc:572-799) for --bc-error-threshold <= 1.
+struct DevWhitelist {
+  const ulonglong2 *slots;  // {key, count}; empty key = ~0
+  u64 mask;                 // n_slots - 1
+  int shift;
+  double num_sample;
+  const double *pow_tab;    // [41]: pow(10.0, (-q) / 10.0) from the host libm
+  int err_threshold;
+  double prob_threshold;
+  int output_not_in_whitelist;
+  int active;               // whitelist uploaded
+};
+__device__ __forceinline__ bool wl_find(const DevWhitelist &W, u64 key, u64 *count) {
+  u64 s = (key * 0x9E3779B97F4A7C15ull) >> W.shift;
+  for (;;) {
+    const ulonglong2 kv = __ldg(&W.slots[s]);
+    if (kv.x == CMX_EMPTY_KEY) return false;
+    if (kv.x == key) { *count = kv.y; return true; }
+    s = (s + 1) & W.mask;
+  }
+}
+__global__ void wl_insert_kernel(const u64 *keys, const u32 *counts, u64 n, ulonglong2 *slots, u64 mask, int shift) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 key = keys[i];
+  u64 s = (key * 0x9E3779B97F4A7C15ull) >> shift;
+  for (;;) {
+    const u64 old = atomicCAS((unsigned long long *)&slots[s].x, (unsigned long long)CMX_EMPTY_KEY, (unsigned long long)key);
+    if (old == CMX_EMPTY_KEY || old == key) { slots[s].y = counts[i]; return; }
+    s = (s + 1) & mask;
+  }
+}
+// utils.h:107-126: 2 bits per base, ambiguous base -> A
+__device__ __forceinline__ u64 barcode_seed(const u8 *s, int len) {
+  u64 seed = 0;
+  for (int i = 0; i < len; ++i) { const u32 b = base_code(s[i]); seed = b < 4 ? (seed << 2) | b : seed << 2; }
+  return seed;
+}
+__global__ void barcode_kernel(DevWhitelist W, const u8 *bc_seq, const u8 *bc_qual, int bc_len, int n, u64 *bc_key, u8 *bc_ok, Counters *ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8 *bc = bc_seq + (size_t)i * bc_len, *qual = bc_qual + (size_t)i * bc_len;
+  const u64 key = barcode_seed(bc, bc_len);
+  if (!W.active) { bc_key[i] = key; bc_ok[i] = 1; return; }
+  int n_n = 0, first_n = 0;
+  for (int p = bc_len - 1; p >= 0; --p) if (bc[p] == 'N') { if (n_n == 0) first_n = bc_len - 1 - p; ++n_n; }
+  u64 cnt;
+  bool ok = false;
+  u64 out_key = key;
+  if (n_n > W.err_threshold) ok = false;
+  else if (n_n == 0 && wl_find(W, key, &cnt)) { ok = true; atomicAdd(&ctr->n_bc_in_whitelist, 1ull); }
+  else if (W.err_threshold > 0) {
+    double sc[128];
+    u8 ci[128], cb[128];
+    int nc = 0;
+    int i_start = 0, i_end = bc_len, ti_limit = 3;
+    if (n_n > 0) { i_start = first_n; i_end = first_n + 1; ti_limit = 4; }
+    for (int p = i_start; p < i_end; ++p) {
+      const u64 keep = ~(3ull << (2 * p)) & key;
+      u64 b1 = (key >> (2 * p)) & 3ull;
+      for (int ti = 0; ti < ti_limit; ++ti) {
+        b1 = (b1 + 1) & 3ull;
+        if (wl_find(W, keep | (b1 << (2 * p)), &cnt)) {
+          const double abundance = xdiv((double)cnt, W.num_sample);
+          int q = (int)(signed char)qual[bc_len - 1 - p] - 33;
+          q = q > 40 ? 40 : q; q = q < 3 ? 3 : q;
+          if (nc < 128) { sc[nc] = xmul(W.pow_tab[q], abundance); ci[nc] = (u8)(bc_len - 1 - p); cb[nc] = (u8)b1; }
+          ++nc;
+        }
+      }
+    }
+    if (nc >= 1) {
+      int best = 0;
+      bool accept = true;
+      if (nc > 1) {
+        // std::sort with std::greater<BarcodeWithQual> (utils.h:23-35): (score, index, base char) descending
+        for (int a = 1; a < nc; ++a) {
+          const double s_ = sc[a]; const u8 i_ = ci[a], b_ = cb[a];
+          int b = a - 1;
+          while (b >= 0 && (sc[b] < s_ || (sc[b] == s_ && (ci[b] < i_ || (ci[b] == i_ && cb[b] < b_))))) { sc[b + 1] = sc[b]; ci[b + 1] = ci[b]; cb[b + 1] = cb[b]; --b; }
+          sc[b + 1] = s_; ci[b + 1] = i_; cb[b + 1] = b_;
+        }
+        double sum = 0;
+        for (int a = 0; a < nc; ++a) sum = xadd(sum, sc[a]);
+        accept = xdiv(sc[0], sum) > W.prob_threshold;
+      }
+      if (accept) {
+        const int p = bc_len - 1 - (int)ci[best];  // bit position of the corrected base
+        out_key = (key & ~(3ull << (2 * p))) | ((u64)cb[best] << (2 * p));
+        ok = true;
+        atomicAdd(&ctr->n_bc_corrected, 1ull);
+      }
+    }
+  }
+  bc_key[i] = out_key;
+  bc_ok[i] = (ok || W.output_not_in_whitelist) ? 1 : 0;
+}
+
+__global__ void barcode_gate_kernel(Scratch S, const u8 *bc_ok) {  // chromap.h:908-909: pairs outside the whitelist are not mapped
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  if (!bc_ok[slot_pair(S, slot)] && S.pmeta[slot].status == ST_OK) S.pmeta[slot].status = ST_DROP;
+}
+
+__global__ void compact_bc_kernel(int n_pairs, const int *n_rec, const u64 *offs, const u64 *bc_key, u64 *out) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  const int n = n_rec[pair];
+  for (int j = 0; j < n; ++j) out[offs[pair] + j] = bc_key[pair];
 }

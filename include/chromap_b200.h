@@ -80,6 +80,13 @@ int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint
 int cmx_index_info(const cmx_ctx *ctx, int *k, int *w, uint64_t *n_keys, uint64_t *n_occ,
                    uint64_t *table_slots);
 
+/* scATAC barcode whitelist with the abundances of ComputeBarcodeAbundance (chromap.cc:388-548, a host pre-pass over the
+ * barcode file): n distinct 2-bit packed keys (GenerateSeedFromSequence, utils.h:107-126), their counts among the
+ * sampled barcodes and the sample size.  Enables CorrectBarcodeAt (chromap.cc:572-799) inside cmx_map_batch_pe.
+ * err_threshold = --bc-error-threshold (0 or 1 on the GPU path), prob_threshold = --bc-probability-threshold. */
+int cmx_upload_barcode_whitelist(cmx_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint64_t num_sample,
+                                 uint32_t bc_len, int err_threshold, double prob_threshold, int output_not_in_whitelist);
+
 /* One batch of read pairs = the inputs of the taskloop (read_batch1, read_batch2; chromap.h:892).
  * Bases are ASCII exactly as in the FASTQ; pair i's mates are seq1[off1[i]..off1[i+1]) and
  * seq2[off2[i]..off2[i+1]).  on_device != 0: all four pointers are device pointers. */
@@ -91,6 +98,11 @@ typedef struct {
   const uint32_t *off2;   /* n_pairs + 1 */
   uint32_t first_read_id; /* running read counter (sequence_batch.cc:38-39) */
   int32_t on_device;
+  /* scATAC (optional, NULL for bulk data): one cell barcode + its qualities per pair, bc_len bytes each
+   * (barcode_batch of chromap.h:892-909); host or device pointers like the reads. */
+  const char *bc_seq;
+  const char *bc_qual;
+  uint32_t bc_len;
 } cmx_batch;
 
 /* PairedEndMappingWithoutBarcode (bed_mapping.h:170-238) without the vptr, plus rid. 24 bytes. */
@@ -124,6 +136,10 @@ typedef struct {
   int32_t on_device;     /* records is a device pointer (n_records still returned on the host) */
   /* out: counters the reference prints (chromap.cc:808-823) */
   uint64_t n_mapped_pairs, n_uniquely_mapped_pairs, n_candidates, n_overflow_pairs;
+  /* scATAC: barcode key (2 bits per base, after correction) of every returned record, same capacity as `records`
+   * (host pointer; may be NULL), and the counters of chromap.cc:801-805 */
+  uint64_t *barcode_keys;
+  uint64_t n_barcodes_in_whitelist, n_barcodes_corrected;
 } cmx_records;
 
 /* Replaces the taskloop body over one batch, chromap.h:892-1143: trimming, minimizers, index probe,
@@ -141,6 +157,12 @@ int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *records, uint64_t n, uint64_t *
 int cmx_postprocess_pairs(cmx_ctx *ctx, cmx_pairs_record *records, uint64_t n, uint64_t *n_out);
 int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint32_t n_seq, const cmx_pairs_record *records, uint64_t n,
                          const char *const *read_names, uint32_t first_read_id, char *buf, int64_t cap);
+/* scATAC post-processing and BED text: records ordered / de-duplicated with the barcode in the key
+ * (PairedEndMappingWithBarcode, bed_mapping.h:116-167; cell-level dedup as the atac preset sets it) and written as
+ * `chrom start end barcode num_dups` (mapping_writer.cc:127-137). */
+int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out);
+int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys, uint64_t n, uint32_t bc_len,
+                          char *buf, int64_t cap);
 /* BED text (mapping_writer.cc:75-83); names = n_seq C strings.  Returns bytes (or needed size if buf NULL). */
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, uint64_t n, char *buf,
                        int64_t cap);

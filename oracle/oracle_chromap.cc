@@ -858,11 +858,104 @@ static void ref_span_split(const orc_params &P, const orc_reference &ref, const 
   end = vws + en - 1;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Cell barcodes: 2-bit packing (utils.h:107-126, N -> A), whitelist + abundance (chromap.cc:388-548),
+// correction (chromap.cc:572-799).
+static u64 barcode_seed(const char *s, u32 len) {
+  u64 seed = 0;
+  for (u32 i = 0; i < len; ++i) { const uint8_t b = code(s[i]); seed = b < 4 ? (seed << 2) | b : seed << 2; }
+  return seed;
+}
+struct orc_whitelist {
+  std::vector<u64> keys;    // sorted
+  std::vector<u32> counts;  // abundance in the sampled barcodes
+  u64 num_sample = 0;
+  u32 bc_len = 0;
+  int find(u64 k) const {
+    auto it = std::lower_bound(keys.begin(), keys.end(), k);
+    return (it != keys.end() && *it == k) ? (int)(it - keys.begin()) : -1;
+  }
+};
+struct BcCand {
+  u32 idx1; char b1; u32 idx2; char b2; double score;
+  bool operator>(const BcCand &o) const {  // utils.h:23-35
+    return std::tie(score, idx1, b1, idx2, b2) > std::tie(o.score, o.idx1, o.b1, o.idx2, o.b2);
+  }
+};
+// chromap.cc:572-799.  Returns true if the (possibly corrected, in place) barcode is in the whitelist.
+static bool correct_barcode(const orc_whitelist &wl, int err_threshold, double prob_threshold, char *bc, const char *qual, u32 len,
+                            u64 *n_in_whitelist, u64 *n_corrected) {
+  const u64 key = barcode_seed(bc, len);
+  std::vector<int> npos;  // little endian: from the right end (sequence_batch.h:85-104)
+  for (int i = (int)len - 1; i >= 0; --i) if (bc[i] == 'N') npos.push_back(len - 1 - i);
+  if (npos.size() > (size_t)err_threshold) return false;
+  if (npos.empty() && wl.find(key) >= 0) { ++*n_in_whitelist; return true; }
+  if (err_threshold <= 0) return false;
+  static const char tab[4] = {'A', 'C', 'G', 'T'};
+  std::vector<BcCand> cands;
+  const u64 mask = 3;
+  u32 i_start = 0, i_end = len, ti_limit = 3;
+  if (!npos.empty()) { i_start = npos[0]; i_end = npos[0] + 1; ti_limit = 4; }
+  for (u32 i = i_start; i < i_end; ++i) {
+    const u64 keep = ~(mask << (2 * i)) & key;
+    u64 b1 = (key >> (2 * i)) & mask;
+    for (u32 ti = 0; ti < ti_limit; ++ti) {
+      b1 = (b1 + 1) & mask;
+      const u64 k1 = keep | (b1 << (2 * i));
+      int f = wl.find(k1);
+      if (f >= 0) {
+        const double abundance = wl.counts[f] / (double)wl.num_sample;
+        int q = qual[len - 1 - i] - 33;
+        q = q > 40 ? 40 : q; q = q < 3 ? 3 : q;
+        cands.push_back({len - 1 - i, tab[b1], 0, 0, pow(10.0, ((-q) / 10.0)) * abundance});
+      }
+      if (err_threshold == 2) {
+        u32 j_start = i + 1, j_end = len, ti2_limit = 3;
+        if (npos.size() == 2) { j_start = npos[1]; j_end = npos[1] + 1; ti2_limit = 4; }
+        for (u32 j = j_start; j < j_end; ++j) {
+          const u64 keep2 = ~(mask << (2 * j)) & k1;
+          u64 b2 = (k1 >> (2 * j)) & mask;
+          for (u32 t2 = 0; t2 < ti2_limit; ++t2) {
+            b2 = (b2 + 1) & mask;
+            const u64 k2 = keep2 | (b2 << (2 * j));
+            f = wl.find(k2);
+            if (f >= 0) {
+              const double abundance = wl.counts[f] / (double)wl.num_sample;
+              int q = qual[len - 1 - j] - 33;
+              q = q > 40 ? 40 : q; q = q < 3 ? 3 : q;
+              int q1 = qual[len - 1 - i] - 33;
+              q1 = q1 > 40 ? 40 : q1; q1 = q1 < 3 ? 3 : q1;
+              q += q1;
+              cands.push_back({len - 1 - i, tab[b1], len - 1 - j, tab[b2], pow(10.0, ((-q) / 10.0)) * abundance});
+            }
+          }
+        }
+      }
+    }
+  }
+  if (cands.empty()) return false;
+  size_t best = 0;
+  if (cands.size() > 1) {
+    std::sort(cands.begin(), cands.end(), std::greater<BcCand>());
+    double sum = 0;
+    for (const BcCand &c : cands) sum += c.score;
+    if (!(cands[0].score / sum > prob_threshold)) return false;
+  }
+  bc[cands[best].idx1] = cands[best].b1;
+  if (cands[best].b2 != 0) bc[cands[best].idx2] = cands[best].b2;
+  ++*n_corrected;
+  return true;
+}
+
 static const bool g_debug = getenv("ORC_DEBUG") != nullptr;
 struct orc_mapper {
   orc_params P;
   const orc_index *ix;
   const orc_reference *ref;
+  const orc_whitelist *wl = nullptr;  // scATAC: barcode whitelist with abundances (may stay null: barcodes used as they are)
+  int bc_err_threshold = 1;           // --bc-error-threshold (mapping_parameters.h:43)
+  double bc_prob_threshold = 0.9;     // --bc-probability-threshold
+  int output_not_in_whitelist = 0;    // --output-mappings-not-in-whitelist
 };
 
 static void revcomp(const char *s, u32 L, std::string &out) {  // sequence_batch.h:123-134
@@ -1330,6 +1423,216 @@ int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint
   int64_t n_out = 0;
   for (u32 i = 0; i < n; ++i) for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) out[n_out++] = all[(size_t)i * per + j];
   return n_out;
+}
+
+static inline void tn5(orc_pe_record &r);
+void orc_mapper_set_barcodes(orc_mapper *m, const orc_whitelist *wl, int err_threshold, double prob_threshold, int output_not_in_whitelist) {
+  m->wl = wl; m->bc_err_threshold = err_threshold; m->bc_prob_threshold = prob_threshold; m->output_not_in_whitelist = output_not_in_whitelist;
+}
+
+orc_whitelist *orc_whitelist_load(const char *path, uint32_t bc_len) {  // chromap.cc:388-431
+  gzFile f = gzopen(path, "r");
+  if (!f) return nullptr;
+  orc_whitelist *wl = new orc_whitelist;
+  wl->bc_len = bc_len;
+  char buf[256];
+  while (gzgets(f, buf, sizeof(buf)) != NULL) {
+    size_t l = strlen(buf);
+    if (l && buf[l - 1] == '\n') buf[--l] = 0;
+    if (l != bc_len) { gzclose(f); delete wl; return nullptr; }
+    wl->keys.push_back(barcode_seed(buf, l));
+  }
+  gzclose(f);
+  std::sort(wl->keys.begin(), wl->keys.end());
+  wl->keys.erase(std::unique(wl->keys.begin(), wl->keys.end()), wl->keys.end());
+  wl->counts.assign(wl->keys.size(), 0);
+  return wl;
+}
+void orc_whitelist_free(orc_whitelist *wl) { delete wl; }
+// ComputeBarcodeAbundance (chromap.cc:492-548) over barcodes given in memory: n barcodes of bc_len bytes, in file
+// order; `batch` = reference batch size (500000); sampling stops after the batch in which num_sample reaches `max_sample`.
+void orc_whitelist_sample(orc_whitelist *wl, const char *bcs, uint64_t n, uint32_t bc_len, uint64_t max_sample, uint32_t batch) {
+  for (uint64_t b0 = 0; b0 < n; b0 += batch) {
+    const uint64_t b1 = std::min<uint64_t>(n, b0 + batch);
+    for (uint64_t i = b0; i < b1; ++i) {
+      const char *s = bcs + i * bc_len;
+      bool has_n = false;
+      for (u32 j = 0; j < bc_len; ++j) if (s[j] == 'N') has_n = true;
+      if (has_n) continue;
+      const int f = wl->find(barcode_seed(s, bc_len));
+      if (f >= 0) { wl->counts[f] += 1; ++wl->num_sample; }
+    }
+    if (wl->num_sample >= max_sample) break;
+  }
+}
+uint64_t orc_whitelist_arrays(const orc_whitelist *wl, const uint64_t **keys, const uint32_t **counts, uint64_t *num_sample) {
+  *keys = wl->keys.data(); *counts = wl->counts.data(); *num_sample = wl->num_sample;
+  return wl->keys.size();
+}
+
+// scATAC variant of the taskloop body: CorrectBarcodeAt first (chromap.h:897-909), the (corrected) barcode key
+// travels with every record (mapping_generator.h:566-573).  bcs / quals: n * bc_len bytes each; out_bc[i] = barcode key
+// of record i; bc_stats[0] += #barcodes in whitelist, bc_stats[1] += #corrected.
+int64_t orc_map_pairs_bc(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2, const uint32_t *off2,
+                         const char *bcs, const char *quals, uint32_t bc_len, uint32_t first_read_id, orc_pe_record *out, uint64_t *out_bc,
+                         int64_t cap_out, int n_threads, uint64_t *bc_stats) {
+  const int per = m->P.max_num_best_mappings;
+  std::vector<orc_pe_record> all((size_t)n * per);
+  std::vector<u64> keys(n, 0);
+  std::vector<int> cnt(n, 0);
+  const u32 max_tasks = n / 5000 + 2;
+  std::vector<u32> st(max_tasks), en(max_tasks);
+  const int nt = orc_ref_task_chunks(n, st.data(), en.data(), max_tasks);
+  u64 n_in = 0, n_cor = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1) reduction(+ : n_in, n_cor)
+  for (int t = 0; t < nt; ++t) {
+    std::mt19937 gen(11);
+    for (u32 i = st[t]; i < en[t]; ++i) {
+      std::string bc(bcs + (size_t)i * bc_len, bc_len);
+      bool ok = true;
+      if (m->wl) ok = correct_barcode(*m->wl, m->bc_err_threshold, m->bc_prob_threshold, &bc[0], quals + (size_t)i * bc_len, bc_len, &n_in, &n_cor);
+      keys[i] = barcode_seed(bc.data(), bc_len);
+      if (!(ok || m->output_not_in_whitelist)) continue;
+      cnt[i] = map_one_pair(m->P, *m->ix, *m->ref, gen, seq1 + off1[i], off1[i + 1] - off1[i], seq2 + off2[i], off2[i + 1] - off2[i],
+                            first_read_id + i, i, &all[(size_t)i * per], per, nullptr);
+    }
+  }
+  if (bc_stats) { bc_stats[0] += n_in; bc_stats[1] += n_cor; }
+  int64_t n_out = 0;
+  for (u32 i = 0; i < n; ++i)
+    for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) { out[n_out] = all[(size_t)i * per + j]; out_bc[n_out] = keys[i]; ++n_out; }
+  return n_out;
+}
+
+// Post-processing with cell barcodes (PairedEndMappingWithBarcode, bed_mapping.h:116-167: order (start, len, barcode,
+// mapq, ...), duplicates = same (barcode, start, len) — the atac preset dedups at cell level,
+// remove_pcr_duplicates_at_bulk_level = false, chromap_driver.cc:256).
+int64_t orc_postprocess_bc(const orc_params *p, orc_pe_record *recs, uint64_t *bcs, int64_t n) {
+  if (n == 0) return 0;
+  std::vector<int64_t> ord(n);
+  std::iota(ord.begin(), ord.end(), 0);
+  auto key = [&](int64_t i) {
+    const orc_pe_record &r = recs[i];
+    return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bcs[i], r.mapq, r.direction, r.is_unique, r.read_id);
+  };
+  std::vector<orc_pe_record> rr(recs, recs + n);
+  std::vector<u64> bb(bcs, bcs + n);
+  if (!p->low_memory_mode && p->tn5_shift) for (auto &r : rr) tn5(r);
+  auto key2 = [&](int64_t i) {
+    const orc_pe_record &r = rr[i];
+    return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bb[i], r.mapq, r.direction, r.is_unique, r.read_id);
+  };
+  (void)key;
+  std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return key2(a) < key2(b); });
+  auto same = [&](int64_t a, int64_t b) {
+    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && rr[a].fragment_length == rr[b].fragment_length && bb[a] == bb[b];
+  };
+  int64_t o = 0, i = 0;
+  while (i < n) {
+    int64_t j = i + 1;
+    int64_t keep = ord[i];
+    u32 dups = 1;
+    if (p->remove_pcr_duplicates)
+      for (; j < n && same(ord[j], ord[i]); ++j) {
+        ++dups;
+        if (p->low_memory_mode) { if (rr[ord[j]].mapq > rr[keep].mapq) keep = ord[j]; }
+        else keep = ord[j];  // in-memory dedup keeps the last of the run (mapping_processor.h:181-197)
+      }
+    orc_pe_record k = rr[keep];
+    if (k.mapq >= p->mapq_threshold) {
+      if (p->remove_pcr_duplicates) k.num_dups = std::min<u32>(255, dups);
+      if (p->low_memory_mode && p->tn5_shift) tn5(k);
+      recs[o] = k; bcs[o] = bb[keep]; ++o;
+    }
+    i = j;
+  }
+  return o;
+}
+
+int64_t orc_format_bed_bc(const orc_reference *ref, const orc_pe_record *recs, const uint64_t *bcs, int64_t n, uint32_t bc_len, char *buf, int64_t cap) {
+  int64_t len = 0;
+  static const char tab[4] = {'A', 'C', 'G', 'T'};
+  for (int64_t i = 0; i < n; ++i) {  // mapping_writer.cc:127-137, barcode_translator.h:114-123
+    const orc_pe_record &r = recs[i];
+    std::string line = ref->names[r.rid] + "\t" + std::to_string(r.fragment_start) + "\t" + std::to_string((u32)(r.fragment_start + r.fragment_length)) + "\t";
+    for (u32 j = 0; j < bc_len; ++j) line.push_back(tab[(bcs[i] >> ((bc_len - 1 - j) * 2)) & 3]);
+    line += "\t" + std::to_string((u32)r.num_dups) + "\n";
+    if (buf && len + (int64_t)line.size() <= cap) memcpy(buf + len, line.data(), line.size());
+    len += line.size();
+  }
+  return len;
+}
+
+// Whole-file scATAC driver: `chromap --preset atac -x idx -r ref -1 r1 -2 r2 -b bc [--barcode-whitelist wl] -o out`.
+int orc_run_files_bc(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                     const char *barcode_path, const char *whitelist_path, const char *out_path, int n_threads, uint64_t *bc_stats) {
+  orc_reference *ref = orc_reference_load(ref_path);
+  orc_index *ix = orc_index_load(index_path);
+  if (!ref || !ix) return -1;
+  orc_mapper *m = orc_mapper_create(p, ix, ref);
+  if (!m) return -2;
+  // barcode length from the first records (chromap.cc:364-386), whitelist + abundance pre-pass (chromap.h:755-761)
+  std::string allbc, allq;
+  u32 bc_len = 0;
+  {
+    SeqReader rb;
+    if (!rb.open(barcode_path)) return -3;
+    std::string n, s, q;
+    while (rb.next(n, s, q)) { if (s.empty()) continue; if (!bc_len) bc_len = s.size(); if (s.size() != bc_len) return -6; allbc += s; q.resize(bc_len, 'I'); allq += q; }
+    rb.close();
+  }
+  orc_whitelist *wl = nullptr;
+  if (whitelist_path && whitelist_path[0]) {
+    wl = orc_whitelist_load(whitelist_path, bc_len);
+    if (!wl) return -7;
+    orc_whitelist_sample(wl, allbc.data(), allbc.size() / bc_len, bc_len, 20000000, 500000);
+    orc_mapper_set_barcodes(m, wl, 1, 0.9, 0);
+  }
+  SeqReader r1, r2;
+  if (!r1.open(read1_path) || !r2.open(read2_path)) return -3;
+  std::vector<orc_pe_record> recs;
+  std::vector<u64> rbc;
+  const u32 batch = 500000;
+  u32 read_id = 0;
+  for (;;) {
+    std::string s1, s2;
+    std::vector<u32> o1{0}, o2{0};
+    std::string n, s, q;
+    u32 cnt = 0;
+    while (cnt < batch) {
+      bool a = r1.next(n, s, q);
+      while (a && s.empty()) a = r1.next(n, s, q);
+      if (!a) break;
+      s1 += s; o1.push_back(s1.size());
+      bool b = r2.next(n, s, q);
+      while (b && s.empty()) b = r2.next(n, s, q);
+      if (!b) return -4;
+      s2 += s; o2.push_back(s2.size());
+      ++cnt;
+    }
+    if (cnt == 0) break;
+    if ((size_t)(read_id + cnt) * bc_len > allbc.size()) return -4;
+    const size_t base = recs.size();
+    recs.resize(base + (size_t)cnt * p->max_num_best_mappings);
+    rbc.resize(recs.size());
+    const int64_t got = orc_map_pairs_bc(m, cnt, s1.data(), o1.data(), s2.data(), o2.data(), allbc.data() + (size_t)read_id * bc_len,
+                                         allq.data() + (size_t)read_id * bc_len, bc_len, read_id, recs.data() + base, rbc.data() + base,
+                                         recs.size() - base, n_threads, bc_stats);
+    recs.resize(base + got); rbc.resize(base + got);
+    read_id += cnt;
+  }
+  r1.close(); r2.close();
+  const int64_t keep = orc_postprocess_bc(p, recs.data(), rbc.data(), recs.size());
+  const int64_t bytes = orc_format_bed_bc(ref, recs.data(), rbc.data(), keep, bc_len, nullptr, 0);
+  std::vector<char> text(bytes + 1);
+  orc_format_bed_bc(ref, recs.data(), rbc.data(), keep, bc_len, text.data(), bytes);
+  FILE *f = fopen(out_path, "wb");
+  if (!f) return -5;
+  fwrite(text.data(), 1, bytes, f);
+  fclose(f);
+  orc_mapper_free(m); orc_index_free(ix); orc_reference_free(ref);
+  if (wl) orc_whitelist_free(wl);
+  return 0;
 }
 
 static inline auto rec_key(const orc_pe_record &r) {  // bed_mapping.h:208-215, prefixed by rid

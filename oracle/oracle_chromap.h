@@ -141,6 +141,21 @@ int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint
                          const char *seq2, const uint32_t *off2, uint32_t first_read_id,
                          orc_pe_record *out, int64_t cap_out, int n_threads, orc_pair_trace *trace);
 
+// ---- scATAC cell barcodes (chromap.cc:388-799): whitelist, abundance sampling, correction ------------------------
+typedef struct orc_whitelist orc_whitelist;
+orc_whitelist *orc_whitelist_load(const char *path, uint32_t bc_len);
+void orc_whitelist_free(orc_whitelist *wl);
+void orc_whitelist_sample(orc_whitelist *wl, const char *bcs, uint64_t n, uint32_t bc_len, uint64_t max_sample, uint32_t batch);
+uint64_t orc_whitelist_arrays(const orc_whitelist *wl, const uint64_t **keys, const uint32_t **counts, uint64_t *num_sample);
+void orc_mapper_set_barcodes(orc_mapper *m, const orc_whitelist *wl, int err_threshold, double prob_threshold, int output_not_in_whitelist);
+int64_t orc_map_pairs_bc(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2, const uint32_t *off2,
+                         const char *bcs, const char *quals, uint32_t bc_len, uint32_t first_read_id, orc_pe_record *out, uint64_t *out_bc,
+                         int64_t cap_out, int n_threads, uint64_t *bc_stats);
+int64_t orc_postprocess_bc(const orc_params *p, orc_pe_record *recs, uint64_t *bcs, int64_t n);
+int64_t orc_format_bed_bc(const orc_reference *ref, const orc_pe_record *recs, const uint64_t *bcs, int64_t n, uint32_t bc_len, char *buf, int64_t cap);
+int orc_run_files_bc(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                     const char *barcode_path, const char *whitelist_path, const char *out_path, int n_threads, uint64_t *bc_stats);
+
 // Post-processing (mapping_processor.h:100-202, mapping_writer.h:166-376, chromap.h:1305-1355):
 // sort / dedup / Tn5 / MAPQ filter, in place.  Returns the number of surviving records, sorted in
 // output order (rid, then record operator<).

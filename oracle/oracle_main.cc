@@ -12,7 +12,7 @@
 int main(int argc, char **argv) {
   orc_params p;
   orc_default_params(&p);
-  std::string idx, ref, r1, r2, out, preset;
+  std::string idx, ref, r1, r2, out, preset, bc, wl;
   int threads = 1, k = 17, w = 7;
   bool build = false;
   for (int i = 1; i < argc; ++i)
@@ -28,6 +28,8 @@ int main(int argc, char **argv) {
     else if (a == "-1") r1 = next();
     else if (a == "-2") r2 = next();
     else if (a == "-o") out = next();
+    else if (a == "-b") bc = next();
+    else if (a == "--barcode-whitelist") wl = next();
     else if (a == "-t") threads = atoi(next());
     else if (a == "-k") k = atoi(next());
     else if (a == "-w") w = atoi(next());
@@ -47,6 +49,13 @@ int main(int argc, char **argv) {
     if (!r) { fprintf(stderr, "Cannot find sequence file %s\n", ref.c_str()); return 255; }
     orc_index *ix = orc_index_build(r, k, w);
     return orc_index_save(ix, out.c_str()) == 0 ? 0 : 255;
+  }
+  if (!bc.empty()) {
+    uint64_t st[2] = {0, 0};
+    int rc = orc_run_files_bc(&p, idx.c_str(), ref.c_str(), r1.c_str(), r2.c_str(), bc.c_str(), wl.c_str(), out.c_str(), threads, st);
+    if (rc != 0) { fprintf(stderr, "oracle_map failed (%d)\n", rc); return 255; }
+    fprintf(stderr, "Number of barcodes in whitelist: %llu.\nNumber of corrected barcodes: %llu.\n", (unsigned long long)st[0], (unsigned long long)st[1]);
+    return 0;
   }
   double secs = 0;
   uint64_t n = 0;

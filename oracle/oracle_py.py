@@ -79,6 +79,16 @@ def lib():
         L.orc_ref_task_chunks.argtypes = [u32, vp, vp, i32]
         L.orc_postprocess.restype = i64; L.orc_postprocess.argtypes = [C.POINTER(Params), vp, i64]
         L.orc_format_bed.restype = i64; L.orc_format_bed.argtypes = [vp, vp, i64, vp, i64]
+        L.orc_whitelist_load.restype = vp; L.orc_whitelist_load.argtypes = [C.c_char_p, u32]
+        L.orc_whitelist_free.argtypes = [vp]
+        L.orc_whitelist_sample.argtypes = [vp, vp, u64, u32, u64, u32]
+        L.orc_whitelist_arrays.restype = u64; L.orc_whitelist_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+        L.orc_mapper_set_barcodes.argtypes = [vp, vp, i32, C.c_double, i32]
+        L.orc_map_pairs_bc.restype = i64
+        L.orc_map_pairs_bc.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, u32, vp, vp, i64, i32, vp]
+        L.orc_postprocess_bc.restype = i64; L.orc_postprocess_bc.argtypes = [C.POINTER(Params), vp, vp, i64]
+        L.orc_format_bed_bc.restype = i64; L.orc_format_bed_bc.argtypes = [vp, vp, vp, i64, u32, vp, i64]
+        L.orc_run_files_bc.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 7 + [i32, vp]
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
         _lib = L
     return _lib
@@ -196,3 +206,51 @@ def run_files(params, index_path, ref_path, r1, r2, out, n_threads=1):
     if rc != 0:
         raise RuntimeError("orc_run_files failed: %d" % rc)
     return secs.value, n.value
+
+
+class Whitelist:
+    """Barcode whitelist + abundances (chromap.cc:388-548)."""
+
+    def __init__(self, path, bc_len):
+        self.h = lib().orc_whitelist_load(path.encode(), bc_len)
+        if not self.h:
+            raise IOError("cannot load whitelist")
+        self.bc_len = bc_len
+
+    def sample(self, barcodes, max_sample=20000000, batch=500000):
+        barcodes = np.ascontiguousarray(barcodes, dtype=np.uint8)
+        lib().orc_whitelist_sample(self.h, barcodes.ctypes.data, len(barcodes) // self.bc_len, self.bc_len, max_sample, batch)
+
+    def arrays(self):
+        k, c, ns = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        n = lib().orc_whitelist_arrays(self.h, C.byref(k), C.byref(c), C.byref(ns))
+        keys = np.ctypeslib.as_array(C.cast(k, C.POINTER(C.c_uint64)), (n,)).copy()
+        counts = np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_uint32)), (n,)).copy()
+        return keys, counts, ns.value
+
+
+def map_pairs_bc(params, index, ref, seq1, off1, seq2, off2, barcodes, quals, bc_len, whitelist=None, first_read_id=0, n_threads=1):
+    L = lib()
+    m = L.orc_mapper_create(C.byref(params), index.h, ref.h)
+    if whitelist is not None:
+        L.orc_mapper_set_barcodes(m, whitelist.h, 1, 0.9, 0)
+    n = len(off1) - 1
+    out = np.zeros(n * params.max_num_best_mappings, dtype=PE_RECORD)
+    obc = np.zeros(len(out), dtype=np.uint64)
+    st = np.zeros(2, dtype=np.uint64)
+    seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
+    off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
+    barcodes = np.ascontiguousarray(barcodes, dtype=np.uint8); quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    got = L.orc_map_pairs_bc(m, n, seq1.ctypes.data, off1.ctypes.data, seq2.ctypes.data, off2.ctypes.data, barcodes.ctypes.data, quals.ctypes.data,
+                             bc_len, first_read_id, out.ctypes.data, obc.ctypes.data, len(out), n_threads, st.ctypes.data)
+    L.orc_mapper_free(m)
+    return out[:got], obc[:got], st
+
+
+def run_files_bc(params, index_path, ref_path, r1, r2, barcode_path, whitelist_path, out, n_threads=1):
+    st = np.zeros(2, dtype=np.uint64)
+    rc = lib().orc_run_files_bc(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), r2.encode(), barcode_path.encode(),
+                                (whitelist_path or "").encode(), out.encode(), n_threads, st.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("orc_run_files_bc failed: %d" % rc)
+    return st

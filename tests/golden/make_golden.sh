@@ -43,3 +43,16 @@ $REF --preset hic -q 0 -e 6 --remove-pcr-duplicates -x ref.index -r ref.fa -1 re
 md5sum *.pairs > md5.txt
 gzip -9 -n ref.fa read1.fq read2.fq *.pairs
 rm -f ref.index
+# scATAC (--preset atac with -b / --barcode-whitelist): barcodes with substitutions, Ns and near-neighbour whitelist entries
+cd .. && rm -rf synth_sc && mkdir -p synth_sc
+python $REPO/tools/gen_synth.py --out synth_sc --seed 13 --n-seq 3 --seq-len 250000 --n-pairs 5000 --short-frac 0.3 --barcodes \
+  --repeat-copies 15 --repeat-len 2000 --fam-copies 500
+python $REPO/tools/perturb_barcodes.py synth_sc
+cd synth_sc
+$REF -i -r ref.fa -o ref.index 2> /dev/null
+$REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -b barcode.fq --barcode-whitelist whitelist.txt -o sc_whitelist.bed -t 1 2> sc.log
+$REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -b barcode.fq -o sc_nowhitelist.bed -t 1 2> /dev/null
+grep -E "Number of (barcodes|corrected)" sc.log > sc_stats.txt; rm sc.log
+md5sum *.bed > md5.txt
+gzip -9 -n ref.fa read1.fq read2.fq barcode.fq *.bed
+rm -f ref.index

@@ -336,3 +336,44 @@ def test_hic_reference_quickstart_golden(golden_dir):
     rn = [l[1:].split()[0] for i, l in enumerate(open(os.path.join(d, "read1.fq"), "rb")) if i % 4 == 0]
     text = m.format_pairs(m.postprocess_pairs(recs), rn, [len(s) for s in seqs])
     assert hashlib.md5(text).hexdigest() == "fc844a251ebdcec0f641b59fef804d0f"
+
+
+def _read_barcodes(path):
+    import gzip as gz
+    seqs, quals = [], []
+    with gz.open(path, "rb") as f:
+        for i, line in enumerate(f):
+            if i % 4 == 1:
+                seqs.append(line.rstrip(b"\r\n"))
+            elif i % 4 == 3:
+                quals.append(line.rstrip(b"\r\n"))
+    return np.frombuffer(b"".join(seqs), dtype=np.uint8), np.frombuffer(b"".join(quals), dtype=np.uint8), len(seqs[0])
+
+
+@pytest.mark.parametrize("case,use_wl", [("sc_whitelist", True), ("sc_nowhitelist", False)])
+def test_scatac_barcodes_equal_oracle_and_golden(case, use_wl, golden_dir):
+    """BASELINE config 4 semantics: cell barcodes, whitelist correction on the device, cell-level duplicate removal."""
+    d = os.path.join(golden_dir, "synth_sc")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    bcs, quals, bc_len = _read_barcodes(os.path.join(d, "barcode.fq.gz"))
+    m = cb.Mapper(cb.make_params("atac", max_read_length=64))
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    wl = None
+    if use_wl:
+        wl = orc.Whitelist(os.path.join(d, "whitelist.txt"), bc_len)
+        wl.sample(bcs)   # host pre-pass of the reference (ComputeBarcodeAbundance); the product CLI has its own
+        keys, counts, ns = wl.arrays()
+        m.upload_barcode_whitelist(keys, counts, ns, bc_len)
+    recs, stats = m.map_batch(s1, o1, s2, o2, barcodes=bcs, barcode_quals=quals, bc_len=bc_len)
+    orecs, obc, ost = orc.map_pairs_bc(orc.make_params("atac"), oidx, oref, s1, o1, s2, o2, bcs, quals, bc_len, whitelist=wl)
+    assert_same_records(recs, orecs)
+    assert np.array_equal(stats["barcode_keys"], obc)
+    if use_wl:
+        assert (stats["n_barcodes_in_whitelist"], stats["n_barcodes_corrected"]) == (int(ost[0]), int(ost[1]))
+    r2, b2 = m.postprocess_bc(recs, stats["barcode_keys"])
+    assert m.format_bed_bc(r2, b2, bc_len) == gzip.open(os.path.join(d, case + ".bed.gz")).read()

@@ -125,3 +125,22 @@ def test_hic_reference_quickstart(golden_dir, tmp_path):
     orc.run_files(orc.make_params("hic"), os.path.join(d, "ref.index"), os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq"),
                   os.path.join(d, "read2.fq"), out)
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == "fc844a251ebdcec0f641b59fef804d0f"
+
+
+@pytest.mark.parametrize("case,use_wl", [("sc_whitelist", True), ("sc_nowhitelist", False)])
+def test_scatac_barcodes_match_reference_binary(case, use_wl, golden_dir, tmp_path):
+    """--preset atac with -b (and --barcode-whitelist): barcode correction, cell-level dedup, barcode BED column."""
+    d = os.path.join(golden_dir, "synth_sc")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    ip = str(tmp_path / "sc.index")
+    assert idx.save(ip) == 0
+    out = str(tmp_path / "o.bed")
+    st = orc.run_files_bc(orc.make_params("atac"), ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), os.path.join(d, "read2.fq.gz"),
+                          os.path.join(d, "barcode.fq.gz"), os.path.join(d, "whitelist.txt") if use_wl else "", out)
+    want = gzip.open(os.path.join(d, case + ".bed.gz")).read()
+    assert hashlib.md5(want).hexdigest() == _md5s(d)[case + ".bed"]
+    assert open(out, "rb").read() == want
+    if use_wl:
+        s = open(os.path.join(d, "sc_stats.txt")).read()
+        assert "whitelist: %d." % st[0] in s and "corrected barcodes: %d." % st[1] in s
