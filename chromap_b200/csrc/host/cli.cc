@@ -7,7 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/chromap_b200.h"
@@ -27,13 +29,24 @@ struct Batch {
   std::string s1, s2;
   std::vector<uint32_t> o1{0}, o2{0};
   std::vector<std::string> names1;  // read-1 names, kept for pairs output only
+  std::string bc, bq;               // cell barcodes + qualities, bc_len bytes per pair (scATAC)
   uint32_t n = 0, first_id = 0;
-  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); n = 0; }
+  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); bc.clear(); bq.clear(); n = 0; }
 };
 
 // LoadPairedEndReadsWithBarcodes (chromap.cc:93-174, non-barcode): empty reads are skipped per file
 // (sequence_batch.cc:28-31), the two files must run out together.
-static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names) {
+// utils.h:107-126
+static uint64_t BarcodeSeed(const std::string &s) {
+  uint64_t seed = 0;
+  for (char c : s) {
+    const int b = (c == 'A' || c == 'a') ? 0 : (c == 'C' || c == 'c') ? 1 : (c == 'G' || c == 'g') ? 2 : (c == 'T' || c == 't') ? 3 : 4;
+    seed = b < 4 ? (seed << 2) | (uint64_t)b : seed << 2;
+  }
+  return seed;
+}
+
+static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names, SeqReader *rb = nullptr, uint32_t bc_len = 0) {
   std::string n, s, q;
   b->Clear();
   while (b->n < max_pairs) {
@@ -43,8 +56,18 @@ static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batc
     bool c = r2.Next(&n, &s, &q);
     while (c && s.empty()) c = r2.Next(&n, &s, &q);
     if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
-    if (!a && !c) break;
-    if (a != c) Die("Numbers of reads and barcodes don't match!");
+    bool d = c;
+    if (rb) {
+      d = rb->Next(&n, &s, &q);
+      while (d && s.empty()) d = rb->Next(&n, &s, &q);
+      if (d) {
+        if (s.size() != bc_len) Die("ERROR: barcode lengths are not equal in the sample!");
+        q.resize(bc_len, 'I');
+        b->bc += s; b->bq += q;
+      }
+    }
+    if (!a && !c && !d) break;
+    if (a != c || c != d) Die("Numbers of reads and barcodes don't match!");
     ++b->n;
   }
   return b->n;
@@ -53,7 +76,10 @@ static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batc
 int main(int argc, char **argv) {
   cmx_params p;
   cmx_default_params(&p);
-  std::string preset, ref_path, index_path, r1_path, r2_path, out_path;
+  std::string preset, ref_path, index_path, r1_path, r2_path, out_path, bc_path, wl_path;
+  int bc_err = 1, out_nw = 0;
+  bool skip_bc_check = false;
+  double bc_prob = 0.9;
   bool build_index = false, bed = false, user_set_format = false;
   int k = 17, w = 7, threads = 1;
   (void)threads;
@@ -90,8 +116,13 @@ int main(int argc, char **argv) {
     else if (a == "--BED") { bed = true; user_set_format = true; }
     else if (a == "--split-alignment") p.split_alignment = 1;
     else if (a == "--pairs") p.output_format = 5;
-    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "-b" || a == "--barcode" ||
-             a == "--barcode-whitelist" || a == "-n" || a == "--summary")
+    else if (a == "-b" || a == "--barcode") bc_path = val();
+    else if (a == "--barcode-whitelist") wl_path = val();
+    else if (a == "--bc-error-threshold") bc_err = atoi(val().c_str());
+    else if (a == "--bc-probability-threshold") bc_prob = atof(val().c_str());
+    else if (a == "--output-mappings-not-in-whitelist") out_nw = 1;
+    else if (a == "--skip-barcode-check") skip_bc_check = true;
+    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "-n" || a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (paired-end BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
@@ -138,7 +169,52 @@ int main(int argc, char **argv) {
   if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
   if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags.data(), ix.keys.data(), ix.vals.data(), ix.occ.data(), (uint32_t)ix.occ.size())) Die(cmx_last_error(ctx));
   { IndexFile().flags.swap(ix.flags); std::vector<uint64_t>().swap(ix.keys); std::vector<uint64_t>().swap(ix.vals); std::vector<uint64_t>().swap(ix.occ); }
-  SeqReader r1, r2;
+  // scATAC pre-pass (chromap.h:755-761): barcode length from the first record, whitelist, abundance over the first >= 20 M
+  // whitelisted barcodes (chromap.cc:364-386, 388-548)
+  const bool sc = !bc_path.empty();
+  uint32_t bc_len = 0;
+  if (sc) {
+    if (pairs) Die("chromap-b200: barcodes with Hi-C pairs output are not on the GPU path");
+    SeqReader rb0;
+    if (!rb0.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
+    std::string n, s, q;
+    if (!rb0.Next(&n, &s, &q)) Die("Empty barcode file");
+    bc_len = (uint32_t)s.size();
+    if (bc_len > 32) Die("ERROR: barcode length is greater than 32!");
+    if (!wl_path.empty()) {
+      std::unordered_map<uint64_t, uint32_t> wl;
+      gzFile f = gzopen(wl_path.c_str(), "r");
+      if (!f) Die("ERROR: barcode whitelist file does not exist or is truncated!");
+      char buf[256];
+      while (gzgets(f, buf, sizeof(buf)) != NULL) {
+        size_t l = strlen(buf);
+        if (l && buf[l - 1] == '\n') buf[--l] = 0;
+        if (l != bc_len) Die(wl.empty() ? "ERROR: whitelist and input barcode lengths are not equal!" : "ERROR: barcode lengths are not equal in the whitelist!");
+        wl.emplace(BarcodeSeed(std::string(buf, l)), 0u);
+      }
+      gzclose(f);
+      fprintf(stderr, "Loaded %zu barcodes.\n", wl.size());
+      uint64_t num_sample = 0, in_batch = 0, loaded = 0;
+      bool more = true;
+      while (more) {  // one reference batch at a time; stop after the batch that reaches 20 M
+        if (s.find('N') == std::string::npos) { auto it = wl.find(BarcodeSeed(s)); if (it != wl.end()) { ++it->second; ++num_sample; } }
+        ++in_batch; ++loaded;
+        more = rb0.Next(&n, &s, &q);
+        while (more && s.empty()) more = rb0.Next(&n, &s, &q);
+        if (in_batch == (uint64_t)p.batch_size || !more) {
+          if (!skip_bc_check && num_sample * 20 < in_batch) Die("Less than 5% barcodes can be found or corrected based on the barcode whitelist.");
+          if (num_sample >= 20000000ull) break;
+          in_batch = 0;
+        }
+      }
+      fprintf(stderr, "Compute barcode abundance using %llu.\n", (unsigned long long)num_sample);
+      std::vector<uint64_t> keys; std::vector<uint32_t> counts;
+      for (const auto &kv : wl) { keys.push_back(kv.first); counts.push_back(kv.second); }
+      if (cmx_upload_barcode_whitelist(ctx, keys.data(), counts.data(), keys.size(), num_sample, bc_len, bc_err, bc_prob, out_nw)) Die(cmx_last_error(ctx));
+    }
+  }
+  SeqReader r1, r2, rb;
+  if (sc && !rb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
   if (!r1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
   if (!r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
   // double-buffered batch loop: the loader thread parses batch b+1 while the GPU maps batch b (chromap.h:871-877)
@@ -148,20 +224,24 @@ int main(int argc, char **argv) {
   const double t_map = Now();
   uint32_t read_id = 0;
   std::vector<std::string> all_names;
-  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs);
+  std::vector<uint64_t> all_bc, bc_keys;
+  uint64_t n_bc_in = 0, n_bc_cor = 0;
+  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs, sc ? &rb : nullptr, bc_len);
   while (cur.n > 0) {
     cur.first_id = read_id;
-    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs); });
+    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs, sc ? &rb : nullptr, bc_len); });
     recs.resize((size_t)cur.n * p.max_num_best_mappings);
     cmx_batch in{};
     in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = cur.s2.data(); in.off2 = cur.o2.data(); in.first_read_id = cur.first_id;
     cmx_records out{};
     out.records = recs.data(); out.capacity = recs.size();
+    if (sc) { in.bc_seq = cur.bc.data(); in.bc_qual = cur.bq.data(); in.bc_len = bc_len; bc_keys.resize(recs.size()); out.barcode_keys = bc_keys.data(); }
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
     all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
     if (pairs) all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
+    if (sc) { all_bc.insert(all_bc.end(), bc_keys.begin(), bc_keys.begin() + out.n_records); n_bc_in += out.n_barcodes_in_whitelist; n_bc_cor += out.n_barcodes_corrected; }
     n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
     read_id += cur.n;
     loader.join();
@@ -186,6 +266,12 @@ int main(int argc, char **argv) {
     bytes = cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, nullptr, 0);
     text.resize((size_t)bytes + 1);
     cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
+  } else if (sc) {
+    if (cmx_postprocess_bc(ctx, all.data(), all_bc.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+    bytes = cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);
+    text.resize((size_t)bytes + 1);
+    cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, text.data(), bytes);
+    fprintf(stderr, "Number of barcodes in whitelist: %llu.\nNumber of corrected barcodes: %llu.\n", (unsigned long long)n_bc_in, (unsigned long long)n_bc_cor);
   } else {
     if (cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
     bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);

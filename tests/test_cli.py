@@ -78,3 +78,20 @@ def test_cli_hic_preset_pairs_output(tmp_path, golden_dir):
         subprocess.check_call([cli, "--preset", "hic"] + args + ["-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
                                                                 "-2", os.path.join(d, "read2.fq.gz"), "-o", out], stderr=subprocess.DEVNULL)
         assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".pairs.gz")).read()
+
+
+@pytest.mark.gpu
+def test_cli_scatac_barcodes(tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_sc")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for case, extra in (("sc_whitelist", ["--barcode-whitelist", os.path.join(d, "whitelist.txt")]), ("sc_nowhitelist", [])):
+        out = str(tmp_path / (case + ".bed"))
+        r = subprocess.run([cli, "--preset", "atac", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
+                            "-2", os.path.join(d, "read2.fq.gz"), "-b", os.path.join(d, "barcode.fq.gz"), "-o", out] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+        if extra:
+            for line in open(os.path.join(d, "sc_stats.txt")):
+                assert line.strip() in r.stderr
