@@ -104,6 +104,7 @@ def load_library():
     L.cmx_stage_cta_sort.argtypes = [vp, vp, vp, u32, u32]
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.cmx_set_lanes.argtypes = [vp, i32]
     _lib = L
     return L
 
@@ -241,6 +242,9 @@ class Mapper:
         if out_on_device:
             return out, stats
         return out[:r.n_records], stats
+
+    def set_lanes(self, n):
+        self._check(self.L.cmx_set_lanes(self.h, int(n)), "cmx_set_lanes")
 
     def timing(self):
         t = Timing()

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -40,6 +41,25 @@ struct Tier {
   Scratch view;
 };
 
+// Per-lane state of the batch pipeline.  A call that carries several whole reference batches is cut into up to
+// CMX_MAX_LANES contiguous groups of batches; every group runs the full pipeline on its own stream (one host
+// thread each), so the latency-bound kernels of one lane (overflow tiers, candidate pairing) share the SMs with
+// the issue-bound kernels of another (minimizers, verification).
+#define CMX_MAX_LANES 4
+struct Lane {
+  DevBuf rescue_list, nbest, sel, out_rec, out_n, offs, chunk_start, cub_tmp, bc_key, bc_ok, out_compact, bc_out;
+  Counters *ctr = nullptr;
+  int *d_count = nullptr;
+  Tier tiers[N_TIERS];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10];
+  cudaEvent_t ev_sub[2];
+  cudaEvent_t ev_done = nullptr;
+  u32 p0 = 0, n = 0;  // pair range of the last call
+  int tiers_used = 0;
+  std::string err;
+};
+
 struct cmx_ctx {
   int device = 0;
   cmx_params params;
@@ -67,24 +87,21 @@ struct cmx_ctx {
   u32 wl_bc_len = 0;
   int wl_err = 1, wl_output_nw = 0, wl_active = 0;
   double wl_prob = 0.9;
-  DevBuf bc_seq, bc_qual, bc_key, bc_ok, bc_out;
+  DevBuf bc_seq, bc_qual;
   // mapq tables
   double *inv_log = nullptr;
   int *pen_thr = nullptr;
   // per-batch buffers
-  DevBuf rescue_list, seq1, off1, seq2, off2, nbest, sel, out_rec, out_n, offs, out_compact, chunk_start, cub_tmp, trace;
-  Counters *ctr = nullptr;
-  int *d_count = nullptr;
-  Tier tiers[N_TIERS];
+  DevBuf seq1, off1, seq2, off2, trace;
+  Lane lanes[CMX_MAX_LANES];
+  int n_lanes = CMX_MAX_LANES;  // lanes a multi-batch call is cut into (cmx_set_lanes; CMX_LANES overrides the default)
+  int last_lanes_used = 0;
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
   std::vector<cudaEvent_t> ev_up;
   cudaEvent_t ev_bc = nullptr;
-  cudaEvent_t ev[10];
-  cudaEvent_t ev_sub[2];
-  float ms_minimizer = 0, ms_probe = 0, ms_cluster = 0;
+  cudaEvent_t ev[4];
   cmx_timing timing;
   u32 last_n_pairs = 0;
-  int last_tiers_used = 0;
 };
 
 static int fail(cmx_ctx *c, int code, const char *fmt, ...) {
@@ -152,9 +169,15 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
-  for (auto &e : ctx->ev_sub) CU(cudaEventCreate(&e));
-  CU(cudaMalloc(&ctx->ctr, sizeof(Counters)));
-  CU(cudaMalloc(&ctx->d_count, sizeof(int) * 4));
+  if (const char *ev = getenv("CMX_LANES")) ctx->n_lanes = std::max(1, std::min(CMX_MAX_LANES, atoi(ev)));
+  for (Lane &L : ctx->lanes) {
+    CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    for (auto &e : L.ev) CU(cudaEventCreate(&e));
+    for (auto &e : L.ev_sub) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    CU(cudaMalloc(&L.ctr, sizeof(Counters)));
+    CU(cudaMalloc(&L.d_count, sizeof(int) * 4));
+  }
   // MAPQ tables from the host libm, so truncations match the reference bit for bit (mapping_generator.h:920-1022)
   {
     std::vector<double> il(65536, 0.0);
@@ -180,9 +203,11 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   CU(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
-  ctx->tiers[0].caps = {mrl, 64, 32, 32};
-  ctx->tiers[1].caps = {mrl * 2, 1024, 256, 256};
-  ctx->tiers[2].caps = {mrl * 4, 65536, 8192, 8192};
+  for (Lane &L : ctx->lanes) {
+    L.tiers[0].caps = {mrl, 64, 32, 32};
+    L.tiers[1].caps = {mrl * 2, 1024, 256, 256};
+    L.tiers[2].caps = {mrl * 4, 65536, 8192, 8192};
+  }
   memset(&ctx->timing, 0, sizeof(ctx->timing));
   *out = ctx;
   return CMX_OK;
@@ -193,12 +218,18 @@ void cmx_destroy(cmx_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
   cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr);
-  cudaFree(ctx->ctr); cudaFree(ctx->d_count); cudaFree(ctx->wl_slots); cudaFree(ctx->wl_pow);
-  for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->bc_key, &ctx->bc_ok, &ctx->bc_out}) release(*b);
-  for (DevBuf *b : {&ctx->rescue_list, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->nbest, &ctx->sel, &ctx->out_rec, &ctx->out_n, &ctx->offs,
-                    &ctx->out_compact, &ctx->chunk_start, &ctx->cub_tmp, &ctx->trace})
-    release(*b);
-  for (auto &t : ctx->tiers) { release(t.mem); release(t.ovf_list); }
+  cudaFree(ctx->wl_slots); cudaFree(ctx->wl_pow);
+  for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->trace}) release(*b);
+  for (Lane &L : ctx->lanes) {
+    cudaFree(L.ctr); cudaFree(L.d_count);
+    for (DevBuf *b : {&L.rescue_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
+      release(*b);
+    for (auto &t : L.tiers) { release(t.mem); release(t.ovf_list); }
+    for (auto &e : L.ev) cudaEventDestroy(e);
+    for (auto &e : L.ev_sub) cudaEventDestroy(e);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
   for (auto &e : ctx->ev) cudaEventDestroy(e);
   for (auto &e : ctx->ev_up) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -481,14 +512,42 @@ struct BatchAcc {  // per-call accumulators over sub-batches
   BatchAcc() { memset(&c, 0, sizeof(c)); }
 };
 
-// The whole device pipeline over pairs already resident in HBM; records compacted in read order into `dst`
-// (device).  Synchronous on the context's stream.
-static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64 *total_out, BatchAcc &acc, u32 piece = 0,
-                            const std::vector<cudaEvent_t> *piece_ready = nullptr, const u8 *bc_dev_seq = nullptr, const u8 *bc_dev_qual = nullptr,
-                            u32 bc_len = 0, cudaEvent_t bc_ready = nullptr, u64 *bc_dst = nullptr) {
-  const u32 n = B.n_pairs;
+#define CUL(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      L.err = b_;                                                                                  \
+      return CMX_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+struct LaneJob {  // what one lane maps in one call: pairs [p0, p0 + n) of the call's batch
+  u32 p0 = 0, n = 0;
+  u32 piece = 0, piece0 = 0;                       // reads arrive in pieces of `piece` pairs; this lane's first piece index
+  const std::vector<cudaEvent_t> *piece_ready = nullptr;
+  const u8 *bc_seq = nullptr, *bc_qual = nullptr;  // device, already offset to p0
+  u32 bc_len = 0;
+  cudaEvent_t bc_ready = nullptr;
+  bool want_bc = false;
+  OutRecord *dst = nullptr;                        // device: compacted records of this lane (nullptr = lane buffer)
+  u64 total = 0;
+  BatchAcc acc;
+  int rc = CMX_OK;
+};
+
+// The whole device pipeline over pairs already resident in HBM (or landing piece by piece); records compacted in
+// read order into the lane's buffer.  Synchronous on the lane's stream; safe to run one lane per host thread.
+static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
+  CUL(cudaSetDevice(ctx->device));
+  const u32 n = J.n;
+  BatchAcc &acc = J.acc;
+  DevBatch B = Bfull;  // view of this lane's pairs: pair index i of the lane = pair p0 + i of the call
+  B.off1 += J.p0; B.off2 += J.p0; B.n_pairs = n; B.first_read_id = Bfull.first_read_id + J.p0; B.bc_ok = nullptr;
+  L.p0 = J.p0; L.n = n;
   const int mb = ctx->params.max_num_best_mappings;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = L.stream;
   const DevParams P = make_dev_params(ctx);
   DevIndex ix;
   ix.slots = ctx->slots; ix.n_slots_mask = ctx->n_slots - 1; ix.shift = table_shift(ctx->n_slots); ix.occ = ctx->occ; ix.n_occ = ctx->n_occ; ix.k = ctx->k; ix.w = ctx->w;
@@ -496,23 +555,27 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
   R.seq = ctx->ref_seq; R.off = ctx->ref_off; R.len = ctx->ref_len; R.n_seq = ctx->n_seq;
   MapqTables T;
   T.inv_log = ctx->inv_log; T.pen_thr = ctx->pen_thr;
-  CU(ensure(ctx->nbest, (size_t)n * 4)); CU(ensure(ctx->sel, (size_t)n * mb * 4));
-  CU(ensure(ctx->out_rec, (size_t)n * mb * sizeof(OutRecord))); CU(ensure(ctx->out_n, (size_t)(n + 1) * 4));
-  CU(ensure(ctx->offs, (size_t)(n + 1) * 8));
-  CU(cudaMemsetAsync(ctx->nbest.p, 0, (size_t)n * 4, st));
-  CU(cudaMemsetAsync(ctx->out_n.p, 0, (size_t)(n + 1) * 4, st));
-  CU(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), st));
-  DevBatch Bx = B;  // with the barcode gate, when barcodes came with the batch
-  if (bc_dev_seq) {
+  CUL(ensure(L.nbest, (size_t)n * 4)); CUL(ensure(L.sel, (size_t)n * mb * 4));
+  CUL(ensure(L.out_rec, (size_t)n * mb * sizeof(OutRecord))); CUL(ensure(L.out_n, (size_t)(n + 1) * 4));
+  CUL(ensure(L.offs, (size_t)(n + 1) * 8));
+  OutRecord *dst = J.dst;
+  if (!dst) { CUL(ensure(L.out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)L.out_compact.p; }
+  J.dst = dst;
+  u64 *bc_dst = nullptr;
+  if (J.want_bc && J.bc_seq) { CUL(ensure(L.bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)L.bc_out.p; }
+  CUL(cudaMemsetAsync(L.nbest.p, 0, (size_t)n * 4, st));
+  CUL(cudaMemsetAsync(L.out_n.p, 0, (size_t)(n + 1) * 4, st));
+  CUL(cudaMemsetAsync(L.ctr, 0, sizeof(Counters), st));
+  if (J.bc_seq) {  // the barcode gate, when barcodes came with the batch
     DevWhitelist W;
     W.slots = ctx->wl_slots; W.mask = ctx->wl_n_slots ? ctx->wl_n_slots - 1 : 0; W.shift = ctx->wl_n_slots ? table_shift(ctx->wl_n_slots) : 0;
     W.num_sample = (double)ctx->wl_num_sample; W.pow_tab = ctx->wl_pow; W.err_threshold = ctx->wl_err; W.prob_threshold = ctx->wl_prob;
     W.output_not_in_whitelist = ctx->wl_output_nw; W.active = ctx->wl_active;
-    CU(ensure(ctx->bc_key, (size_t)n * 8)); CU(ensure(ctx->bc_ok, (size_t)n));
-    if (bc_ready) CU(cudaStreamWaitEvent(st, bc_ready, 0));
-    barcode_kernel<<<(n + 127) / 128, 128, 0, st>>>(W, bc_dev_seq, bc_dev_qual, (int)bc_len, (int)n, (u64 *)ctx->bc_key.p, (u8 *)ctx->bc_ok.p, ctx->ctr);
+    CUL(ensure(L.bc_key, (size_t)n * 8)); CUL(ensure(L.bc_ok, (size_t)n));
+    if (J.bc_ready) CUL(cudaStreamWaitEvent(st, J.bc_ready, 0));
+    barcode_kernel<<<(n + 127) / 128, 128, 0, st>>>(W, J.bc_seq, J.bc_qual, (int)J.bc_len, (int)n, (u64 *)L.bc_key.p, (u8 *)L.bc_ok.p, L.ctr);
     acc.launches += 1;
-    Bx.bc_ok = (const u8 *)ctx->bc_ok.p;
+    B.bc_ok = (const u8 *)L.bc_ok.p;
   }
   int n_slots = (int)n;
   const int *pair_list = nullptr;
@@ -520,74 +583,74 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
   u64 n_overflow_final = 0;
   const int TB = 128;
   for (int t = 0; t < N_TIERS && n_slots > 0; ++t) {
-    Tier &tier = ctx->tiers[t];
-    CU(tier_prepare(tier, n_slots, pair_list));
+    Tier &tier = L.tiers[t];
+    CUL(tier_prepare(tier, n_slots, pair_list));
     const Scratch S = tier.view;
-    cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6], e2 = ctx->ev[7], e3 = ctx->ev[8], e4 = ctx->ev[9];
-    CU(cudaEventRecord(e0, st));
-    if (t == 0 && piece_ready) {
+    cudaEvent_t e0 = L.ev[5], e1 = L.ev[6], e2 = L.ev[7], e3 = L.ev[8], e4 = L.ev[9];
+    CUL(cudaEventRecord(e0, st));
+    if (t == 0 && J.piece_ready) {
       // reads arrive in pieces on the upload stream: length filter / trimming and minimizers start on a piece as
       // soon as it has landed, the rest of the upload hides behind them
-      for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += piece) {
-        const u32 np = std::min(piece, n - p0);
-        CU(cudaStreamWaitEvent(st, (*piece_ready)[q], 0));
+      for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += J.piece) {
+        const u32 np = std::min(J.piece, n - p0);
+        CUL(cudaStreamWaitEvent(st, (*J.piece_ready)[J.piece0 + q], 0));
         Scratch V = S;
         V.n_slots = (int)np; V.rmeta += 2 * (size_t)p0; V.pmeta += p0;
         V.mm_hash += 2 * (size_t)p0 * S.caps.maxmm; V.mm_val += 2 * (size_t)p0 * S.caps.maxmm; V.mm_pos += 2 * (size_t)p0 * S.caps.maxmm;
-        DevBatch Bq = Bx;
+        DevBatch Bq = B;
         if (Bq.bc_ok) Bq.bc_ok += p0;
         Bq.off1 += p0; Bq.off2 += p0; Bq.n_pairs = np;
         prep_kernel<<<(np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V);
-        minimizer_kernel<<<(2 * np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V, ctx->ctr);
+        minimizer_kernel<<<(2 * np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V, L.ctr);
         acc.launches += 2;
       }
     } else {
-      prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, Bx, S);
-      if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, ctx->ctr);
+      prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
+      if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, L.ctr);
     }
     if (t == 0) {
-      CU(cudaEventRecord(ctx->ev_sub[0], st));
-      probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, ctx->ctr);  // persistent: 8 CTAs per SM
-      CU(cudaEventRecord(ctx->ev_sub[1], st));
-      cluster_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr);
-      CU(cudaEventRecord(e1, st));
-      CU(ensure(ctx->rescue_list, (size_t)n_slots * 4));
-      CU(cudaMemsetAsync(ctx->d_count + 1, 0, sizeof(int), st));
-      pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, ctx->ctr, 0, (int *)ctx->rescue_list.p, ctx->d_count + 1);
-      pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, ctx->ctr, 1, (int *)ctx->rescue_list.p, ctx->d_count + 1);
-      CU(cudaEventRecord(e2, st));
-      if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
-      else verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, ctx->ctr);
-      CU(cudaEventRecord(e3, st));
-      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
-      else pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
-      CU(cudaEventRecord(e4, st));
+      CUL(cudaEventRecord(L.ev_sub[0], st));
+      probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, L.ctr);  // persistent: 8 CTAs per SM
+      CUL(cudaEventRecord(L.ev_sub[1], st));
+      cluster_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr);
+      CUL(cudaEventRecord(e1, st));
+      CUL(ensure(L.rescue_list, (size_t)n_slots * 4));
+      CUL(cudaMemsetAsync(L.d_count + 1, 0, sizeof(int), st));
+      pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr, 0, (int *)L.rescue_list.p, L.d_count + 1);
+      pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, L.ctr, 1, (int *)L.rescue_list.p, L.d_count + 1);
+      CUL(cudaEventRecord(e2, st));
+      if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
+      else verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
+      CUL(cudaEventRecord(e3, st));
+      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
+      else pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
+      CUL(cudaEventRecord(e4, st));
     } else {  // overflow tiers: one CTA per read / pair; shared-memory sort buffers sized to the tier
       auto cap_of = [](int n) { int c = 1; while (c < n) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
       const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
-      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, ctx->ctr, c_seed);
-      CU(cudaEventRecord(e1, st));
-      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 11, st>>>(P, ix, S, ctx->ctr, c_pc);
-      CU(cudaEventRecord(e2, st));
-      if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
-      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, ctx->ctr, c_ver);
-      CU(cudaEventRecord(e3, st));
-      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)ctx->nbest.p);
-      else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)ctx->nbest.p, c_pair);
-      CU(cudaEventRecord(e4, st));
+      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, L.ctr, c_seed);
+      CUL(cudaEventRecord(e1, st));
+      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 11, st>>>(P, ix, S, L.ctr, c_pc);
+      CUL(cudaEventRecord(e2, st));
+      if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
+      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
+      CUL(cudaEventRecord(e3, st));
+      if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
+      else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)L.nbest.p, c_pair);
+      CUL(cudaEventRecord(e4, st));
     }
-    acc.launches += (t == 0 ? 8 : 6);
-    CU(ensure(tier.ovf_list, (size_t)n_slots * 4));
-    CU(cudaMemsetAsync(ctx->d_count, 0, sizeof(int), st));
-    collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, ctx->d_count);
+    acc.launches += (t == 0 ? (J.piece_ready ? 6 : 8) : 6);
+    CUL(ensure(tier.ovf_list, (size_t)n_slots * 4));
+    CUL(cudaMemsetAsync(L.d_count, 0, sizeof(int), st));
+    collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, L.d_count);
     acc.launches += 1;
     int n_ovf = 0;
-    CU(cudaMemcpyAsync(&n_ovf, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
+    CUL(cudaMemcpyAsync(&n_ovf, L.d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUL(cudaStreamSynchronize(st));
+    CUL(cudaGetLastError());
     float f;
     cudaEventElapsedTime(&f, e0, e1); acc.ms_seed += f;
-    if (t == 0) { cudaEventElapsedTime(&f, e0, ctx->ev_sub[0]); acc.ms_minimizer += f; cudaEventElapsedTime(&f, ctx->ev_sub[0], ctx->ev_sub[1]); acc.ms_probe += f; cudaEventElapsedTime(&f, ctx->ev_sub[1], e1); acc.ms_cluster += f; }
+    if (t == 0) { cudaEventElapsedTime(&f, e0, L.ev_sub[0]); acc.ms_minimizer += f; cudaEventElapsedTime(&f, L.ev_sub[0], L.ev_sub[1]); acc.ms_probe += f; cudaEventElapsedTime(&f, L.ev_sub[1], e1); acc.ms_cluster += f; }
     cudaEventElapsedTime(&f, e1, e2); acc.ms_pc += f;
     cudaEventElapsedTime(&f, e2, e3); acc.ms_ver += f;
     cudaEventElapsedTime(&f, e3, e4); acc.ms_pair += f;
@@ -595,63 +658,65 @@ static int run_device_batch(cmx_ctx *ctx, const DevBatch &B, OutRecord *dst, u64
     if (n_ovf > 0 && t + 1 < N_TIERS) {
       // deterministic order for the next tier: sort the pair list (atomic append order is arbitrary)
       std::vector<int> h(n_ovf);
-      CU(cudaMemcpy(h.data(), tier.ovf_list.p, (size_t)n_ovf * 4, cudaMemcpyDeviceToHost));
+      CUL(cudaMemcpyAsync(h.data(), tier.ovf_list.p, (size_t)n_ovf * 4, cudaMemcpyDeviceToHost, st));
+      CUL(cudaStreamSynchronize(st));
       std::sort(h.begin(), h.end());
-      CU(cudaMemcpy(tier.ovf_list.p, h.data(), (size_t)n_ovf * 4, cudaMemcpyHostToDevice));
+      CUL(cudaMemcpyAsync(tier.ovf_list.p, h.data(), (size_t)n_ovf * 4, cudaMemcpyHostToDevice, st));
+      CUL(cudaStreamSynchronize(st));
       pair_list = (const int *)tier.ovf_list.p;
     } else if (n_ovf > 0) {
       n_overflow_final = n_ovf;
     }
     n_slots = n_ovf;
   }
-  // multi-mapper sampling: one thread per taskloop chunk of every reference batch in this call
+  // multi-mapper sampling: one warp per taskloop chunk of every reference batch in this lane
   std::vector<int> chunks;
   for (u32 b0 = 0; b0 < n; b0 += (u32)ctx->params.batch_size) taskloop_chunks(b0, std::min<u32>((u32)ctx->params.batch_size, n - b0), chunks);
   const int n_chunks = (int)chunks.size();
   chunks.push_back((int)n);
-  CU(ensure(ctx->chunk_start, chunks.size() * 4));
-  CU(cudaEventRecord(ctx->ev[2], st));
-  CU(cudaMemcpyAsync(ctx->chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
-  select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)ctx->chunk_start.p, (const int *)ctx->nbest.p, (int *)ctx->sel.p);
-  CU(cudaEventRecord(ctx->ev[3], st));
+  CUL(ensure(L.chunk_start, chunks.size() * 4));
+  CUL(cudaEventRecord(L.ev[2], st));
+  CUL(cudaMemcpyAsync(L.chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
+  select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)L.chunk_start.p, (const int *)L.nbest.p, (int *)L.sel.p);
+  CUL(cudaEventRecord(L.ev[3], st));
   for (int t = 0; t < tiers_used; ++t) {
-    const Scratch S = ctx->tiers[t].view;
-    if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutPairs *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
-    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)ctx->sel.p, (OutRecord *)ctx->out_rec.p, (int *)ctx->out_n.p, ctx->ctr);
+    const Scratch S = L.tiers[t].view;
+    if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)L.sel.p, (OutPairs *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
   }
   acc.launches += 1 + tiers_used;
   // read-order compaction
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
-  CU(ensure(ctx->cub_tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const int *)L.out_n.p, (u64 *)L.offs.p, (int)n + 1, st);
+  CUL(ensure(L.cub_tmp, tmp_bytes));
   // out_n has n entries plus one trailing zero so that offs[n] = total
-  cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, (const int *)ctx->out_n.p, (u64 *)ctx->offs.p, (int)n + 1, st);
-  compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)ctx->out_rec.p, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, dst);
+  cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tmp_bytes, (const int *)L.out_n.p, (u64 *)L.offs.p, (int)n + 1, st);
+  compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)L.out_rec.p, (const int *)L.out_n.p, (const u64 *)L.offs.p, dst);
   acc.launches += 2;
-  if (bc_dst && bc_dev_seq) {
-    compact_bc_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, (const int *)ctx->out_n.p, (const u64 *)ctx->offs.p, (const u64 *)ctx->bc_key.p, bc_dst);
+  if (bc_dst) {
+    compact_bc_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, (const int *)L.out_n.p, (const u64 *)L.offs.p, (const u64 *)L.bc_key.p, bc_dst);
     acc.launches += 1;
   }
   u64 total = 0;
-  CU(cudaEventRecord(ctx->ev[4], st));
-  CU(cudaMemcpyAsync(&total, (u64 *)ctx->offs.p + n, 8, cudaMemcpyDeviceToHost, st));
+  CUL(cudaEventRecord(L.ev[4], st));
+  CUL(cudaMemcpyAsync(&total, (u64 *)L.offs.p + n, 8, cudaMemcpyDeviceToHost, st));
   Counters hc;
-  CU(cudaMemcpyAsync(&hc, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  CU(cudaGetLastError());
+  CUL(cudaMemcpyAsync(&hc, L.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CUL(cudaStreamSynchronize(st));
+  CUL(cudaGetLastError());
   float f;
-  cudaEventElapsedTime(&f, ctx->ev[2], ctx->ev[3]); acc.ms_select += f;
-  cudaEventElapsedTime(&f, ctx->ev[3], ctx->ev[4]); acc.ms_emit += f;
+  cudaEventElapsedTime(&f, L.ev[2], L.ev[3]); acc.ms_select += f;
+  cudaEventElapsedTime(&f, L.ev[3], L.ev[4]); acc.ms_emit += f;
   {
     u64 *a = (u64 *)&acc.c;
     const u64 *b = (const u64 *)&hc;
     for (size_t i = 0; i < sizeof(Counters) / 8; ++i) a[i] += b[i];
   }
-  for (int t = 0; t < N_TIERS; ++t) if (t < tiers_used) acc.tier_pairs[t] += (u64)ctx->tiers[t].n_slots;
+  for (int t = 0; t < N_TIERS; ++t) if (t < tiers_used) acc.tier_pairs[t] += (u64)L.tiers[t].n_slots;
   acc.tiers_used = std::max(acc.tiers_used, tiers_used);
   acc.n_overflow += n_overflow_final;
-  *total_out = total;
-  ctx->last_tiers_used = tiers_used;
+  J.total = total;
+  L.tiers_used = tiers_used;
   return CMX_OK;
 }
 
@@ -668,104 +733,118 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
   CU(cudaSetDevice(ctx->device));
   (void)user_stream;  // the context's own streams are used; the call is synchronous
-  cudaStream_t st = ctx->stream;
-  BatchAcc acc;
-  u64 total = 0;
-  float ms_h2d = 0, ms_d2h = 0;
-  CU(cudaEventRecord(ctx->ev[0], st));
+  cudaStream_t up = ctx->up_stream;
   const u32 bs = (u32)ctx->params.batch_size;
-  if (in->on_device || out->on_device || n <= bs) {
-    // single pass: upload (if needed), map, download
-    DevBatch B{};
-    int rc = upload_batch(ctx, in, &B);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[1], st));
-    OutRecord *dst;
-    if (out->on_device) dst = (OutRecord *)out->records;
-    else { CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)ctx->out_compact.p; }
-    const u8 *bcs = nullptr, *bcq = nullptr;
-    u64 *bc_dst = nullptr;
-    if (in->bc_seq && in->bc_len) {
-      if (in->on_device) { bcs = (const u8 *)in->bc_seq; bcq = (const u8 *)in->bc_qual; }
-      else {
-        CU(ensure(ctx->bc_seq, (size_t)n * in->bc_len + 16)); CU(ensure(ctx->bc_qual, (size_t)n * in->bc_len + 16));
-        CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->bc_qual.p, in->bc_qual, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, st));
-        bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
-      }
-      if (out->barcode_keys) { CU(ensure(ctx->bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)ctx->bc_out.p; }
-    }
-    rc = run_device_batch(ctx, B, dst, &total, acc, 0, nullptr, bcs, bcq, in->bc_len, nullptr, bc_dst);
-    if (rc) return rc;
-    cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);
-    CU(cudaEventRecord(ctx->ev[1], st));
-    if (!out->on_device && total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
-    if (bc_dst && total) CU(cudaMemcpyAsync(out->barcode_keys, bc_dst, total * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(ctx->ev[5], st));
-    CU(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
-    ctx->last_n_pairs = n;
+  const u32 n_sub = (n + bs - 1) / bs;  // reference batches in this call
+  const bool bc = in->bc_seq && in->bc_len;
+  CU(cudaEventRecord(ctx->ev[0], up));
+  // ---- inputs: device pointers as they are; host buffers go up in pieces (one per reference batch) on the upload
+  // stream, so the first kernels start on piece 0 while the other pieces are still in flight
+  DevBatch B{};
+  B.n_pairs = n; B.first_read_id = in->first_read_id;
+  const u8 *bcs = nullptr, *bcq = nullptr;
+  const bool pieces = !in->on_device;
+  if (in->on_device) {
+    B.seq1 = (const u8 *)in->seq1; B.off1 = in->off1; B.seq2 = (const u8 *)in->seq2; B.off2 = in->off2;
+    if (bc) { bcs = (const u8 *)in->bc_seq; bcq = (const u8 *)in->bc_qual; }
   } else {
-    // host buffers, several reference batches: reads are uploaded in pieces (one per reference batch) on the
-    // upload stream; the first kernels start on piece 0 while the other pieces are still in flight.
     const size_t b1 = in->off1[n], b2 = in->off2[n];
     CU(ensure(ctx->seq1, b1 + 64)); CU(ensure(ctx->seq2, b2 + 64));
     CU(ensure(ctx->off1, (size_t)(n + 1) * 4)); CU(ensure(ctx->off2, (size_t)(n + 1) * 4));
-    CU(ensure(ctx->out_compact, (size_t)n * mb * sizeof(OutRecord)));
-    const u32 n_sub = (n + bs - 1) / bs;
     while (ctx->ev_up.size() < n_sub) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
-    CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
-    CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->up_stream));
-    if (in->bc_seq && in->bc_len) {
+    CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
+    CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
+    if (bc) {
       CU(ensure(ctx->bc_seq, (size_t)n * in->bc_len + 16)); CU(ensure(ctx->bc_qual, (size_t)n * in->bc_len + 16));
-      CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, ctx->up_stream));
-      CU(cudaMemcpyAsync(ctx->bc_qual.p, in->bc_qual, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, ctx->up_stream));
+      CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, up));
+      CU(cudaMemcpyAsync(ctx->bc_qual.p, in->bc_qual, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, up));
       if (!ctx->ev_bc) CU(cudaEventCreateWithFlags(&ctx->ev_bc, cudaEventDisableTiming));
-      CU(cudaEventRecord(ctx->ev_bc, ctx->up_stream));
+      CU(cudaEventRecord(ctx->ev_bc, up));
+      bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
     }
     for (u32 s = 0; s < n_sub; ++s) {
       const u32 p0 = s * bs, p1 = std::min(n, p0 + bs);
-      CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, ctx->up_stream));
-      CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, ctx->up_stream));
-      CU(cudaEventRecord(ctx->ev_up[s], ctx->up_stream));
+      CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, up));
+      CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, up));
+      CU(cudaEventRecord(ctx->ev_up[s], up));
     }
-    DevBatch B{};
     B.seq1 = (const u8 *)ctx->seq1.p; B.off1 = (const u32 *)ctx->off1.p;
     B.seq2 = (const u8 *)ctx->seq2.p; B.off2 = (const u32 *)ctx->off2.p;
-    B.n_pairs = n; B.first_read_id = in->first_read_id;
-    OutRecord *dst = (OutRecord *)ctx->out_compact.p;
-    const u8 *bcs = nullptr, *bcq = nullptr;
-    u64 *bc_dst = nullptr;
-    if (in->bc_seq && in->bc_len) {
-      bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
-      if (out->barcode_keys) { CU(ensure(ctx->bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)ctx->bc_out.p; }
-    }
-    const int rc = run_device_batch(ctx, B, dst, &total, acc, bs, &ctx->ev_up, bcs, bcq, in->bc_len, bcs ? ctx->ev_bc : nullptr, bc_dst);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[1], st));
-    if (total) CU(cudaMemcpyAsync(out->records, dst, total * sizeof(OutRecord), cudaMemcpyDeviceToHost, st));
-    if (bc_dst && total) CU(cudaMemcpyAsync(out->barcode_keys, bc_dst, total * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(ctx->ev[5], st));
-    CU(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&ms_d2h, ctx->ev[1], ctx->ev[5]);
-    ctx->last_n_pairs = n;
   }
+  CU(cudaEventRecord(ctx->ev[1], up));
+  // ---- lanes: contiguous groups of whole reference batches (the sampling generator restarts per batch chunk,
+  // so a lane needs nothing from its neighbours)
+  const int n_lanes = (int)std::min<u32>((u32)ctx->n_lanes, n_sub);
+  LaneJob jobs[CMX_MAX_LANES];
+  for (int l = 0; l < n_lanes; ++l) {
+    const u32 s0 = (u32)((u64)n_sub * l / n_lanes), s1 = (u32)((u64)n_sub * (l + 1) / n_lanes);
+    LaneJob &J = jobs[l];
+    J.p0 = s0 * bs; J.n = std::min(n, s1 * bs) - J.p0;
+    if (pieces) { J.piece = bs; J.piece0 = s0; J.piece_ready = &ctx->ev_up; }
+    if (bc) { J.bc_seq = bcs + (size_t)J.p0 * in->bc_len; J.bc_qual = bcq + (size_t)J.p0 * in->bc_len; J.bc_len = in->bc_len; J.bc_ready = pieces ? ctx->ev_bc : nullptr; }
+    J.want_bc = bc && out->barcode_keys;
+    if (out->on_device && n_lanes == 1) J.dst = (OutRecord *)out->records;
+  }
+  {
+    std::vector<std::thread> th;
+    for (int l = 1; l < n_lanes; ++l) th.emplace_back([&, l]() { jobs[l].rc = run_lane(ctx, ctx->lanes[l], B, jobs[l]); });
+    jobs[0].rc = run_lane(ctx, ctx->lanes[0], B, jobs[0]);
+    for (auto &t : th) t.join();
+  }
+  ctx->last_lanes_used = n_lanes;
+  ctx->last_n_pairs = n;
+  for (int l = 0; l < n_lanes; ++l)
+    if (jobs[l].rc) { ctx->err = ctx->lanes[l].err; return jobs[l].rc; }
+  // ---- gather: records of the lanes, in lane order, into the caller's buffer
+  cudaStream_t dn = ctx->down_stream;
+  CU(cudaEventRecord(ctx->ev[2], dn));
+  u64 total = 0;
+  for (int l = 0; l < n_lanes; ++l) {
+    const LaneJob &J = jobs[l];
+    if (J.total && (void *)J.dst != (void *)out->records)
+      CU(cudaMemcpyAsync((OutRecord *)out->records + total, J.dst, J.total * sizeof(OutRecord), out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, dn));
+    if (J.want_bc && J.total) CU(cudaMemcpyAsync(out->barcode_keys + total, ctx->lanes[l].bc_out.p, J.total * 8, cudaMemcpyDeviceToHost, dn));
+    total += J.total;
+  }
+  CU(cudaEventRecord(ctx->ev[3], dn));
+  CU(cudaStreamSynchronize(dn));
   CU(cudaGetLastError());
+  float ms_h2d = 0, ms_d2h = 0;
+  cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ms_d2h, ctx->ev[2], ctx->ev[3]);
+  BatchAcc acc;
+  for (int l = 0; l < n_lanes; ++l) {
+    const BatchAcc &a = jobs[l].acc;
+    acc.ms_seed += a.ms_seed; acc.ms_pc += a.ms_pc; acc.ms_ver += a.ms_ver; acc.ms_pair += a.ms_pair; acc.ms_minimizer += a.ms_minimizer;
+    acc.ms_probe += a.ms_probe; acc.ms_cluster += a.ms_cluster; acc.ms_select += a.ms_select; acc.ms_emit += a.ms_emit;
+    acc.launches += a.launches; acc.n_overflow += a.n_overflow;
+    u64 *x = (u64 *)&acc.c;
+    const u64 *y = (const u64 *)&a.c;
+    for (size_t i = 0; i < sizeof(Counters) / 8; ++i) x[i] += y[i];
+    for (int t = 0; t < N_TIERS; ++t) acc.tier_pairs[t] += a.tier_pairs[t];
+  }
   out->n_records = total;
   out->n_mapped_pairs = acc.c.n_mapped; out->n_uniquely_mapped_pairs = acc.c.n_unique; out->n_candidates = acc.c.n_candidates;
   out->n_overflow_pairs = acc.n_overflow;
   out->n_barcodes_in_whitelist = acc.c.n_bc_in_whitelist; out->n_barcodes_corrected = acc.c.n_bc_corrected;
   cmx_timing &tm = ctx->timing;
   memset(&tm, 0, sizeof(tm));
+  // stage times are sums over the lanes' own streams; lanes overlap, so they add up to more than total_ms
   tm.h2d_ms = ms_h2d; tm.d2h_ms = ms_d2h;
   tm.seed_ms = acc.ms_seed; tm.minimizer_ms = acc.ms_minimizer; tm.probe_ms = acc.ms_probe; tm.cluster_ms = acc.ms_cluster;
   tm.pair_candidates_ms = acc.ms_pc; tm.verify_ms = acc.ms_ver; tm.pairing_ms = acc.ms_pair; tm.select_ms = acc.ms_select; tm.emit_ms = acc.ms_emit;
-  cudaEventElapsedTime(&tm.total_ms, ctx->ev[0], ctx->ev[5]);
+  tm.total_ms = 0;
   tm.n_minimizers = acc.c.n_minimizers; tm.n_probe_steps = acc.c.n_probe_steps; tm.n_found = acc.c.n_found; tm.n_occ_reads = acc.c.n_occ_reads;
   tm.n_verified = acc.c.n_verified; tm.n_launches = acc.launches;
   for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = acc.tier_pairs[t];
   for (int r = 0; r < 8; ++r) tm.escalations[r] = acc.c.ovf_reason[r];
   if (acc.n_overflow) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)acc.n_overflow);
+  return CMX_OK;
+}
+
+int cmx_set_lanes(cmx_ctx *ctx, int n_lanes) {
+  if (!ctx || n_lanes < 1 || n_lanes > CMX_MAX_LANES) return CMX_ERR_INVALID;
+  ctx->n_lanes = n_lanes;
   return CMX_OK;
 }
 
@@ -775,7 +854,7 @@ int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out) {
   return CMX_OK;
 }
 
-__global__ void trace_kernel(Scratch S, cmx_pair_trace *out) {
+__global__ void trace_kernel(Scratch S, cmx_pair_trace *out, u32 p0) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= S.n_slots) return;
   const PairMeta &pm = S.pmeta[slot];
@@ -796,7 +875,7 @@ __global__ void trace_kernel(Scratch S, cmx_pair_trace *out) {
   t.supplement_result = pm.sup;
   t.min_sum_errors = pm.min_sum; t.second_min_sum_errors = pm.second_min_sum; t.n_best_pairs = pm.n_best; t.n_second_best_pairs = pm.n_second_best;
   t.n_records = pm.n_rec;
-  out[slot_pair(S, slot)] = t;
+  out[p0 + slot_pair(S, slot)] = t;
 }
 
 int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs) {
@@ -804,9 +883,12 @@ int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs) {
   CU(cudaSetDevice(ctx->device));
   CU(ensure(ctx->trace, (size_t)n_pairs * sizeof(cmx_pair_trace)));
   CU(cudaMemset(ctx->trace.p, 0, (size_t)n_pairs * sizeof(cmx_pair_trace)));
-  for (int t = 0; t < ctx->last_tiers_used; ++t) {
-    const Scratch S = ctx->tiers[t].view;
-    trace_kernel<<<(S.n_slots + 255) / 256, 256>>>(S, (cmx_pair_trace *)ctx->trace.p);
+  for (int l = 0; l < ctx->last_lanes_used; ++l) {
+    const Lane &L = ctx->lanes[l];
+    for (int t = 0; t < L.tiers_used; ++t) {
+      const Scratch S = L.tiers[t].view;
+      trace_kernel<<<(S.n_slots + 255) / 256, 256>>>(S, (cmx_pair_trace *)ctx->trace.p, L.p0);
+    }
   }
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out, ctx->trace.p, (size_t)n_pairs * sizeof(cmx_pair_trace), cudaMemcpyDeviceToHost));

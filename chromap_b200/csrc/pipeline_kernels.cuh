@@ -29,6 +29,23 @@ __device__ __forceinline__ u32 neg_code(const u8 *read, int L, int i) {
 }
 __device__ __forceinline__ u8 code_char(u32 c) { return c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : c == 3 ? 'T' : 'N'; }
 
+// Counter updates: every lane adds to the same address, and same-address atomics serialise in L2 at about one
+// per clock, so the lanes that are here together add up first and one of them issues the atomic.
+__device__ __forceinline__ void agg_add(u64 *addr, u64 v) {
+  const unsigned m = __activemask();
+  const unsigned s_ = __reduce_add_sync(m, (unsigned)v);
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(addr, (u64)s_);
+}
+// Append to a list with one atomic per group of converged lanes; returns this lane's index.
+__device__ __forceinline__ int agg_append(int *count) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K0: per pair — length filter (chromap.h:911-916) and adapter trimming (chromap.cc:176-289).
 __global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
@@ -338,7 +355,7 @@ __global__ void cluster_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ct
       occ_reads += n;
     }
   }
-  if (occ_reads) atomicAdd(&ctr->n_occ_reads, (u64)occ_reads);
+  if (occ_reads) agg_add(&ctr->n_occ_reads, (u64)occ_reads);
   sort_u64(hp, np);
   sort_u64(hn, nn);
   rm.rep_len = st.len;
@@ -502,7 +519,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
     if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
     const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1], a2 = rm[1].n_cand[0] + rm[1].n_cand[1];
     if (!(a1 > 0 && a2 > 0)) { pm.status = ST_DROP; return; }
-    atomicAdd(&ctr->n_candidates, (u64)(a1 + a2));
+    agg_add(&ctr->n_candidates, (u64)(a1 + a2));
     return;
   }
   if (mode == 0) {
@@ -519,7 +536,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       // a rescue lookup only happens when the mate has candidates to guide it (candidate_processor.cc:163-181)
       if (a && rm[1 - mate].n_cand[0] + rm[1 - mate].n_cand[1] > 0) need = true;
     }
-    if (need) { list[atomicAdd(list_count, 1)] = slot; return; }
+    if (need) { list[agg_append(list_count)] = slot; return; }
     // no rescue: hits are cleared in the reference but nothing reads them afterwards; ret stays 0
   } else {
     int ret = 0;
@@ -594,7 +611,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
     nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
   }
   if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
-  atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
+  agg_add(&ctr->n_candidates, (u64)(nc1 + nc2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -742,7 +759,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
   if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
   rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
   rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
-  if (n_verified) atomicAdd(&ctr->n_verified, n_verified);
+  if (n_verified) agg_add(&ctr->n_verified, n_verified);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1078,7 +1095,7 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
   }
   out_n[pair] = reported;
   pm.n_rec = reported;
-  if (reported > 0) { atomicAdd(&ctr->n_mapped, 1ull); if (pm.n_best == 1) atomicAdd(&ctr->n_unique, 1ull); }
+  if (reported > 0) { agg_add(&ctr->n_mapped, 1ull); if (pm.n_best == 1) agg_add(&ctr->n_unique, 1ull); }
 }
 
 // compaction of per-pair records into read order
@@ -1093,7 +1110,7 @@ __global__ void compact_kernel(int n_pairs, int mb, const OutRecord *in, const i
 __global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= S.n_slots) return;
-  if (S.pmeta[slot].status == ST_OVERFLOW) list[atomicAdd(count, 1)] = slot_pair(S, slot);
+  if (S.pmeta[slot].status == ST_OVERFLOW) list[agg_append(count)] = slot_pair(S, slot);
 }
 
 // =================================================================================================
@@ -2048,7 +2065,7 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
   if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
   rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
   rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
-  if (n_verified) atomicAdd(&ctr->n_verified, n_verified);
+  if (n_verified) agg_add(&ctr->n_verified, n_verified);
 }
 
 // K3 (split, overflow tiers): every valid candidate verified by its own thread, thread 0 replays the pruning order.
@@ -2302,7 +2319,7 @@ __global__ void emit_split_kernel(DevParams P, DevRef R, DevBatch B, MapqTables 
   }
   out_n[pair] = reported;
   pm.n_rec = reported;
-  if (reported > 0) { atomicAdd(&ctr->n_mapped, 1ull); if (pm.n_best == 1) atomicAdd(&ctr->n_unique, 1ull); }
+  if (reported > 0) { agg_add(&ctr->n_mapped, 1ull); if (pm.n_best == 1) agg_add(&ctr->n_unique, 1ull); }
 }
 
 
@@ -2357,7 +2374,7 @@ __global__ void barcode_kernel(DevWhitelist W, const u8 *bc_seq, const u8 *bc_qu
   bool ok = false;
   u64 out_key = key;
   if (n_n > W.err_threshold) ok = false;
-  else if (n_n == 0 && wl_find(W, key, &cnt)) { ok = true; atomicAdd(&ctr->n_bc_in_whitelist, 1ull); }
+  else if (n_n == 0 && wl_find(W, key, &cnt)) { ok = true; agg_add(&ctr->n_bc_in_whitelist, 1ull); }
   else if (W.err_threshold > 0) {
     double sc[128];
     u8 ci[128], cb[128];

@@ -208,6 +208,13 @@ typedef struct {
 } cmx_timing;
 int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out);
 
+/* Concurrency of one cmx_map_batch_pe call (no counterpart in the reference, whose knob is -t): a call that carries
+ * several whole reference batches is cut into up to n_lanes (1..4, default 4) groups of batches that run the whole
+ * pipeline on their own streams, so the latency-bound kernels of one group overlap the issue-bound kernels of
+ * another.  Results do not depend on it.  With 1 lane the kernels of a call run back to back on one stream and
+ * cmx_timing's stage times are exclusive; with more lanes they are sums over overlapping streams. */
+int cmx_set_lanes(cmx_ctx *ctx, int n_lanes);
+
 #ifdef __cplusplus
 }
 #endif
