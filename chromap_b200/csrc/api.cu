@@ -91,6 +91,7 @@ struct cmx_ctx {
   // mapq tables
   double *inv_log = nullptr;
   int *pen_thr = nullptr;
+  u32 *mt_init = nullptr;  // std::mt19937(11) right after seeding
   // per-batch buffers
   DevBuf seq1, off1, seq2, off2, trace;
   Lane lanes[CMX_MAX_LANES];
@@ -196,6 +197,13 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
     CU(cudaMemcpy(ctx->inv_log, il.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->pen_thr, thr.data(), 96 * sizeof(int), cudaMemcpyHostToDevice));
   }
+  {
+    std::vector<u32> mt(624);
+    mt[0] = 11u;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (u32)i;
+    CU(cudaMalloc(&ctx->mt_init, 624 * sizeof(u32)));
+    CU(cudaMemcpy(ctx->mt_init, mt.data(), 624 * sizeof(u32), cudaMemcpyHostToDevice));
+  }
   // the overflow-tier kernels may use more than the default 48 KB of (static + dynamic) shared memory
   CU(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -217,7 +225,7 @@ void cmx_destroy(cmx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
-  cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr);
+  cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr); cudaFree(ctx->mt_init);
   cudaFree(ctx->wl_slots); cudaFree(ctx->wl_pow);
   for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->trace}) release(*b);
   for (Lane &L : ctx->lanes) {
@@ -677,7 +685,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   CUL(ensure(L.chunk_start, chunks.size() * 4));
   CUL(cudaEventRecord(L.ev[2], st));
   CUL(cudaMemcpyAsync(L.chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
-  select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)L.chunk_start.p, (const int *)L.nbest.p, (int *)L.sel.p);
+  select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)L.chunk_start.p, (const int *)L.nbest.p, (int *)L.sel.p, ctx->mt_init);
   CUL(cudaEventRecord(L.ev[3], st));
   for (int t = 0; t < tiers_used; ++t) {
     const Scratch S = L.tiers[t].view;

@@ -819,50 +819,84 @@ __global__ void pairing_kernel(DevParams P, Scratch S, int *pair_nbest) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: multi-mapper sampling (mapping_generator.h:199-214).  One thread per taskloop chunk: `generator`
+// K5: multi-mapper sampling (mapping_generator.h:199-214).  One warp per taskloop chunk: `generator`
 // (chromap.h:863) is firstprivate in each task the taskloop (chromap.h:892) generates, so every chunk
-// replays std::mt19937(11) from scratch, consumed by its pairs in index order.
-struct Mt19937 {
-  u32 mt[624];
-  int idx;
-  __device__ void seed(u32 s) {
-    mt[0] = s;
-    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (u32)i;
-    idx = 624;
-  }
-  __device__ u32 next() {
-    if (idx >= 624) {
-      for (int i = 0; i < 624; ++i) {
-        const u32 y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
-        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      idx = 0;
-    }
-    u32 y = mt[idx++];
-    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-    return y;
-  }
+// replays std::mt19937(11) from scratch, consumed by its pairs in index order.  The generator lives in shared
+// memory and is advanced by the whole warp: a twist produces 624 tempered outputs at once (three dependency
+// phases), and a run of reservoir draws uniform(0, i), uniform(0, i+1), ... consumes 32 outputs per step.
+#define MT_N 624
+struct WarpMt {
+  u32 *mt;   // [624] state
+  u32 *out;  // [624] tempered outputs of the current block
+  int pos;   // next unread output (warp-uniform); MT_N = block exhausted
 };
+__device__ __forceinline__ u32 mt_mix(u32 a, u32 b, u32 c) {  // a = mt[i], b = mt[i+1], c = mt[i+397]
+  const u32 y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ void mt_regen(WarpMt &g, int lane) {
+  u32 *mt = g.mt;
+  // new[i] = f(old[i], old[i+1], x[(i+397) % 624]) where x is already new for i >= 227
+  // phase 1: i in [0,227) reads old mt[i], mt[i+1] (mt[227] for i=226 still old) and old mt[i+397]
+  u32 v[8];
+  int n = 0;
+  for (int i = lane; i < 227; i += 32) v[n++] = mt_mix(mt[i], mt[i + 1], mt[i + 397]);
+  __syncwarp();
+  n = 0;
+  for (int i = lane; i < 227; i += 32) mt[i] = v[n++];
+  __syncwarp();
+  // phase 2: i in [227,454): old mt[i], old mt[i+1] (mt[454] old), new mt[i-227]
+  n = 0;
+  for (int i = 227 + lane; i < 454; i += 32) v[n++] = mt_mix(mt[i], mt[i + 1], mt[i - 227]);
+  __syncwarp();
+  n = 0;
+  for (int i = 227 + lane; i < 454; i += 32) mt[i] = v[n++];
+  __syncwarp();
+  // phase 3: i in [454,623): old mt[i], old mt[i+1], new mt[i-227]; i = 623 pairs with the NEW mt[0]
+  n = 0;
+  for (int i = 454 + lane; i < 623; i += 32) v[n++] = mt_mix(mt[i], mt[i + 1], mt[i - 227]);
+  __syncwarp();
+  n = 0;
+  for (int i = 454 + lane; i < 623; i += 32) mt[i] = v[n++];
+  __syncwarp();
+  if (lane == 0) mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+  __syncwarp();
+  for (int i = lane; i < MT_N; i += 32) {
+    u32 y = mt[i];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    g.out[i] = y;
+  }
+  __syncwarp();
+  g.pos = 0;
+}
+__device__ __forceinline__ u32 mt_next(WarpMt &g, int lane) {  // warp-uniform: every lane gets the same output
+  if (g.pos >= MT_N) mt_regen(g, lane);
+  return g.out[g.pos++];
+}
 // libstdc++ 13 std::uniform_int_distribution<int>(0, hi) on a 32-bit URNG: Lemire's nearly-divisionless
-// method (bits/uniform_int_dist.h, _S_nd).  hi < 2^31.
-__device__ __forceinline__ u32 uniform_0_hi(Mt19937 &g, u32 hi) {
+// method (bits/uniform_int_dist.h, _S_nd).  hi < 2^31.  Warp-uniform.
+__device__ __forceinline__ u32 uniform_0_hi(WarpMt &g, int lane, u32 hi) {
   const u32 range = hi + 1u;
-  u64 product = (u64)g.next() * (u64)range;
+  u64 product = (u64)mt_next(g, lane) * (u64)range;
   u32 low = (u32)product;
   if (low < range) {
     const u32 threshold = (0u - range) % range;
-    while (low < threshold) { product = (u64)g.next() * (u64)range; low = (u32)product; }
+    while (low < threshold) { product = (u64)mt_next(g, lane) * (u64)range; low = (u32)product; }
   }
   return (u32)(product >> 32);
 }
 
-// one warp per chunk: all lanes scan 32 pairs at a time and write the identity selection; lane 0 replays the
-// generator for the (rare) pairs with more best pairs than -n, in pair order.
-__global__ void select_kernel(DevParams P, int n_chunks, const int *chunk_start, const int *pair_nbest, int *pair_sel) {
+// one warp per chunk: all lanes scan 32 pairs at a time and write the identity selection; for the pairs with
+// more best pairs than -n the warp replays the reservoir sampling, 32 draws per step.  mt_init = the state of
+// std::mt19937(11) right after seeding (624 words, computed once on the host).
+__global__ void __launch_bounds__(128) select_kernel(DevParams P, int n_chunks, const int *chunk_start, const int *pair_nbest, int *pair_sel,
+                                                     const u32 *mt_init) {
+  __shared__ u32 s_mt[4][MT_N], s_out[4][MT_N];
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (ch >= n_chunks) return;
-  Mt19937 g;
+  WarpMt g;
+  g.mt = s_mt[wid]; g.out = s_out[wid]; g.pos = MT_N;
   bool seeded = false;
   const int mb = P.max_best;
   const int p0 = chunk_start[ch], p1 = chunk_start[ch + 1];
@@ -880,13 +914,44 @@ __global__ void select_kernel(DevParams P, int n_chunks, const int *chunk_start,
       const int l = __ffs(m) - 1;
       m &= m - 1;
       const int nbl = __shfl_sync(0xffffffffu, nb, l);
-      if (lane == 0) {
-        if (!seeded) { g.seed(11u); seeded = true; }
-        int *sel = pair_sel + (size_t)(base + l) * mb;
-        for (int i = mb; i < nbl; ++i) {
-          const int j = (int)uniform_0_hi(g, (u32)i);
-          if (j < mb) sel[j] = i;
+      if (!seeded) {
+        for (int i = lane; i < MT_N; i += 32) g.mt[i] = mt_init[i];
+        __syncwarp();
+        g.pos = MT_N;
+        seeded = true;
+      }
+      int *sel = pair_sel + (size_t)(base + l) * mb;
+      int i = mb;
+      while (i < nbl) {
+        if (g.pos >= MT_N) mt_regen(g, lane);
+        const int cnt = min(min(32, nbl - i), MT_N - g.pos);
+        // draw i + lane takes output pos + lane, unless an earlier draw of this step needs Lemire's rejection test
+        u64 product = 0;
+        bool slow = false;
+        if (lane < cnt) {
+          const u32 range = (u32)(i + lane) + 1u;
+          product = (u64)g.out[g.pos + lane] * (u64)range;
+          slow = (u32)product < range;
         }
+        const unsigned sm_ = __ballot_sync(0xffffffffu, slow);
+        const int ok = sm_ ? __ffs(sm_) - 1 : cnt;  // draws i .. i+ok-1 accept their first output
+        const int j = (int)(product >> 32);
+        unsigned hit = __ballot_sync(0xffffffffu, lane < ok && j < mb);
+        while (hit) {  // in draw order: a later draw overwrites an earlier one in the same reservoir slot
+          const int t = __ffs(hit) - 1;
+          hit &= hit - 1;
+          const int jt = __shfl_sync(0xffffffffu, j, t);
+          if (lane == 0) sel[jt] = i + t;
+        }
+        i += ok; g.pos += ok;
+        if (ok < cnt) {  // one draw through the full rejection loop
+          const int jj = (int)uniform_0_hi(g, lane, (u32)i);
+          if (jj < mb && lane == 0) sel[jj] = i;
+          ++i;
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
         for (int a = 1; a < mb; ++a) {  // std::sort of <= CMX_MAX_BEST ints
           const int v = sel[a];
           int b = a - 1;

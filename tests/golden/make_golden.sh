@@ -17,6 +17,7 @@ run default
 run q0dedup --remove-pcr-duplicates -q 0
 run e5 -e 5 -q 10 --Tn5-shift --remove-pcr-duplicates
 run e12l300 -e 12 -l 300 -q 0
+run n3q0 -n 3 -q 0
 md5sum *.bed > md5.txt
 gzip -9 -n ref.fa read1.fq read2.fq *.bed
 rm -f ref.index

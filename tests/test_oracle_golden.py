@@ -24,6 +24,7 @@ CASES = {
     "q0dedup": dict(preset="", remove_pcr_duplicates=1, mapq_threshold=0),
     "e5": dict(preset="", error_threshold=5, mapq_threshold=10, tn5_shift=1, remove_pcr_duplicates=1),
     "e12l300": dict(preset="", error_threshold=12, max_insert_size=300, mapq_threshold=0),
+    "n3q0": dict(preset="", max_num_best_mappings=3, mapq_threshold=0),
 }
 
 
