@@ -47,7 +47,7 @@ struct Tier {
 // the issue-bound kernels of another (minimizers, verification).
 #define CMX_MAX_LANES 4
 struct Lane {
-  DevBuf rescue_list, nbest, sel, out_rec, out_n, offs, chunk_start, cub_tmp, bc_key, bc_ok, out_compact, bc_out;
+  DevBuf rescue_list, verify_list, nbest, sel, out_rec, out_n, offs, chunk_start, cub_tmp, bc_key, bc_ok, out_compact, bc_out;
   Counters *ctr = nullptr;
   int *d_count = nullptr;
   Tier tiers[N_TIERS];
@@ -205,6 +205,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
     CU(cudaMemcpy(ctx->mt_init, mt.data(), 624 * sizeof(u32), cudaMemcpyHostToDevice));
   }
   // the overflow-tier kernels may use more than the default 48 KB of (static + dynamic) shared memory
+  CU(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * CLUSTER_NT * 8));  // tier-0 hc = 64
   CU(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -230,7 +231,7 @@ void cmx_destroy(cmx_ctx *ctx) {
   for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->trace}) release(*b);
   for (Lane &L : ctx->lanes) {
     cudaFree(L.ctr); cudaFree(L.d_count);
-    for (DevBuf *b : {&L.rescue_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
+    for (DevBuf *b : {&L.rescue_list, &L.verify_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
       release(*b);
     for (auto &t : L.tiers) { release(t.mem); release(t.ovf_list); }
     for (auto &e : L.ev) cudaEventDestroy(e);
@@ -617,18 +618,30 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, L.ctr);
     }
     if (t == 0) {
+      CUL(ensure(L.rescue_list, (size_t)n_slots * 4)); CUL(ensure(L.verify_list, (size_t)n_slots * 8));  // verify_list: cluster's, then verify's
+      CUL(cudaMemsetAsync(L.d_count + 1, 0, 3 * sizeof(int), st));
       CUL(cudaEventRecord(L.ev_sub[0], st));
       probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, L.ctr);  // persistent: 8 CTAs per SM
       CUL(cudaEventRecord(L.ev_sub[1], st));
-      cluster_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr);
+      {
+        // first-pass tile: enough rows for a typical read (about 2L/(w+1) minimizers, most of them single hits)
+        int rows0 = 16;
+        while (rows0 < S.caps.hc && rows0 * (ctx->w + 1) < 3 * ctx->params.max_read_length) rows0 <<= 1;
+        rows0 = std::min(rows0, S.caps.hc);
+        cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)rows0 * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 0, rows0, (int *)L.verify_list.p, L.d_count + 3);
+        if (rows0 < S.caps.hc)
+          cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)S.caps.hc * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 1, S.caps.hc, (int *)L.verify_list.p, L.d_count + 3);
+      }
       CUL(cudaEventRecord(e1, st));
-      CUL(ensure(L.rescue_list, (size_t)n_slots * 4));
-      CUL(cudaMemsetAsync(L.d_count + 1, 0, sizeof(int), st));
+
       pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr, 0, (int *)L.rescue_list.p, L.d_count + 1);
       pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, L.ctr, 1, (int *)L.rescue_list.p, L.d_count + 1);
       CUL(cudaEventRecord(e2, st));
       if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
-      else verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
+      else {
+        verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr, 0, (int *)L.verify_list.p, L.d_count + 2);
+        verify_kernel<<<(2 * n_slots + 63) / 64, 64, 0, st>>>(P, R, B, S, L.ctr, 1, (int *)L.verify_list.p, L.d_count + 2);
+      }
       CUL(cudaEventRecord(e3, st));
       if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
       else pairing_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);

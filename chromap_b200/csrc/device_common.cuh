@@ -140,8 +140,18 @@ __device__ __forceinline__ u64 hit_to_candidate(int k, u64 ref_hit, u32 read_pos
   return ((ref_hit >> 33) << 32) | start;
 }
 
+// a[i] view of every `stride`-th u64 starting at base (a per-thread column of an interleaved shared-memory tile;
+// a negative stride walks it backwards).
+struct StridedU64 {
+  u64 *base;
+  int stride;
+  __device__ __forceinline__ u64 &operator[](int i) const { return base[i * stride]; }
+};
+
 // In-place ascending sort of u64 keys by one thread: insertion for short lists, heapsort otherwise.
-__device__ inline void sort_u64(u64 *a, int n) {
+// A = u64* or StridedU64.
+template <typename A>
+__device__ inline void sort_u64(A a, int n) {
   if (n <= 24) {
     for (int i = 1; i < n; ++i) {
       const u64 v = a[i];

@@ -229,7 +229,8 @@ __device__ __forceinline__ void rep_update(int k, int w, u32 read_pos, RepStats 
 }
 
 // candidate_processor.cc:283-342 — clustering scan over sorted hits (sentinel handled implicitly).
-__device__ inline int cluster_hits(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap) {
+template <typename A>
+__device__ inline int cluster_hits(int e, int need, u32 n_mm, A hits, int nh, u64 *cpos, u8 *ccnt, int cap) {
   if (nh == 0) return 0;
   int n = 0, mcount = 1, eq = 1, best_eq = 1;
   u64 prev = hits[0], best = hits[0];
@@ -303,9 +304,21 @@ __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, Scratch S, Coun
 // K1c: per read — hit lists from the probed values, sort, clustering (candidate_processor.cc:12-71,
 // index.cc:237-349).  Tier 0 takes only "light" reads: as soon as the exact hit count (known from the table
 // values before any occurrence is read) exceeds the tier's capacity the pair is escalated to the CTA tier.
-__global__ void cluster_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr) {
-  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sr >= 2 * S.n_slots) return;
+// The hit lists never touch global memory: every thread owns one column of an interleaved shared-memory tile
+// [hc][CLUSTER_NT] (bank-conflict free: lane t reads word i*CLUSTER_NT + t), + strand hits growing from row 0,
+// - strand hits from row hc-1 downwards (their total is <= hc by the check above).
+#define CLUSTER_NT 128
+// Two launches: mode 0 with a `rows`-row tile (16: full occupancy) takes the reads with at most `rows` hits and
+// lists the others, mode 1 runs the list with an hc-row tile.
+__global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int mode, int rows, int *list,
+                                                             int *list_count) {
+  extern __shared__ u64 sh_hits[];
+  const int tid = blockIdx.x * CLUSTER_NT + threadIdx.x;
+  int sr = tid;
+  if (mode == 1) {
+    if (tid >= *list_count) return;
+    sr = list[tid];
+  } else if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1;
   if (S.pmeta[slot].status != ST_OK) return;
   ReadMeta &rm = S.rmeta[sr];
@@ -330,8 +343,10 @@ __global__ void cluster_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ct
   const bool round2 = cnt1 == 0;
   const long long total = round2 ? cnt2 : cnt1;
   if (total > c.hc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[2], 1ull); return; }  // per-strand lists can then never exceed hc
+  if (total > rows) { list[agg_append(list_count)] = sr; return; }  // mode 0 only: rows == hc in mode 1
   const u32 max_freq = round2 ? (u32)P.f1 : (u32)P.f0;
-  u64 *hp = S.hits + ((size_t)sr * 2 + 0) * c.hc, *hn = S.hits + ((size_t)sr * 2 + 1) * c.hc;
+  const StridedU64 hp = {sh_hits + threadIdx.x, CLUSTER_NT};
+  const StridedU64 hn = {sh_hits + (size_t)(rows - 1) * CLUSTER_NT + threadIdx.x, -CLUSTER_NT};
   int np = 0, nn = 0;
   u32 occ_reads = 0;
   for (int i = 0; i < n_mm; ++i) {
@@ -672,9 +687,16 @@ __device__ __forceinline__ void tally(Tally &t, int err) {
 
 // K3: per read — GenerateDraftMappings (draft_mapping_generator.cc:9-57; fast path :72-157; lane-group
 // driver :159-357 replayed with the scalar routine; per-candidate driver :359-557), non-split.
-__global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr) {
-  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sr >= 2 * S.n_slots) return;
+// Two launches: mode 0 settles the reads that take the zero-DP fast path (about 70 % at 2x50) and appends the
+// others to `list`; mode 1 runs the banded alignments over the list, densely packed, so a warp is not held up by
+// its few aligning lanes.
+__global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int mode, int *list, int *list_count) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int sr = tid;
+  if (mode == 1) {
+    if (tid >= *list_count) return;
+    sr = list[tid];
+  } else if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1, mate = sr & 1;
   if (S.pmeta[slot].status != ST_OK) return;
   const int pair = slot_pair(S, slot);
@@ -690,7 +712,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
   u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
   const int nc[2] = {rm.n_cand[0], rm.n_cand[1]};
   bool done = false;
-  if (nc[0] + nc[1] == 1) {
+  if (mode == 0 && nc[0] + nc[1] == 1) {
     int n_all = 0, idx = 0, strand = 0;
     for (int i = 0; i < nc[0]; ++i) if (cc[0][i] == rm.n_mm) { idx = i; ++n_all; }
     for (int i = 0; i < nc[1]; ++i) if (cc[1][i] == rm.n_mm) { idx = i; strand = 1; ++n_all; }
@@ -708,6 +730,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
     }
   }
   u64 n_verified = 0;
+  if (mode == 0 && !done && nc[0] + nc[1] > 0) { list[agg_append(list_count)] = sr; return; }
   if (!done) {
     auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };  // candidate.h:23-33
     sort_pairs<u8>(cp[0], cc[0], nc[0], cless);
