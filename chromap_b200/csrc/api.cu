@@ -626,7 +626,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       {
         // first-pass tile: enough rows for a typical read (about 2L/(w+1) minimizers, most of them single hits)
         int rows0 = 16;
-        while (rows0 < S.caps.hc && rows0 * (ctx->w + 1) < 3 * ctx->params.max_read_length) rows0 <<= 1;
+        while (rows0 < S.caps.hc && rows0 * (ctx->w + 1) < 2 * ctx->params.max_read_length) rows0 <<= 1;
         rows0 = std::min(rows0, S.caps.hc);
         cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)rows0 * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 0, rows0, (int *)L.verify_list.p, L.d_count + 3);
         if (rows0 < S.caps.hc)

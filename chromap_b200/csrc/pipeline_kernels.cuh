@@ -515,6 +515,8 @@ __device__ inline void pe_filter_dir(u32 dist, const u64 *p1, const u8 *c1, int 
 // Two launches: mode 0 handles every pair that needs no mate-guided rescue (the common case: a few loads
 // and two short sweeps) and appends the others to `list`; mode 1 runs the rescue pairs densely packed, so a
 // warp is no longer held up by its one rescuing pair.
+#define PC_SMALL 8          // lists of at most this many candidates take the local-memory path
+#define PC_RESCUE_HEAVY 48  // more (minimizer, window) searches than this: rescue in the CTA tier
 __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int mode, int *list, int *list_count) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int slot = tid;
@@ -539,20 +541,64 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   }
   if (mode == 0) {
     if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
+    // the common case -- a handful of candidates per list -- is staged in local memory (interleaved per lane by the
+    // hardware, i.e. coalesced), filtered from there straight into set 0: no round trip through the buffer set
+    const int nq[4] = {rm[0].n_cand[0], rm[0].n_cand[1], rm[1].n_cand[0], rm[1].n_cand[1]};
+    const bool small = nq[0] <= PC_SMALL && nq[1] <= PC_SMALL && nq[2] <= PC_SMALL && nq[3] <= PC_SMALL;
+    u64 lp[4][PC_SMALL];
+    u8 lc[4][PC_SMALL];
+    if (small) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const u64 *src = CP(q >> 1, 0, q & 1);
+        const u8 *srcc = CC(q >> 1, 0, q & 1);
+        for (int i = 0; i < nq[q]; ++i) { lp[q][i] = src[i]; lc[q][i] = srcc[i]; }
+      }
+    }
     bool need = false;
     for (int mate = 0; mate < 2; ++mate) {
       const u32 n_mm = rm[mate].n_mm;
       bool a = true;
       for (int s = 0; s < 2 && a; ++s) {
-        const u8 *cc = CC(mate, 0, s);
-        for (int i = 0; i < rm[mate].n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
+        const u8 *cc = small ? lc[mate * 2 + s] : CC(mate, 0, s);
+        for (int i = 0; i < nq[mate * 2 + s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
       }
       aug[mate] = a;
       // a rescue lookup only happens when the mate has candidates to guide it (candidate_processor.cc:163-181)
-      if (a && rm[1 - mate].n_cand[0] + rm[1 - mate].n_cand[1] > 0) need = true;
+      if (a && nq[(1 - mate) * 2] + nq[(1 - mate) * 2 + 1] > 0) need = true;
     }
-    if (need) { list[agg_append(list_count)] = slot; return; }
+    if (need) {
+      // one thread walks every (multi-occurrence minimizer, mate window) binary search of the rescue; when that
+      // product is large the pair goes to the CTA tier, which runs the searches in parallel (same results)
+      u32 searches = 0;
+      for (int mate = 0; mate < 2; ++mate) {
+        if (!aug[mate]) continue;
+        const u32 *mmp = S.mm_pos + (size_t)(2 * slot + mate) * c.maxmm;
+        u32 n_multi = 0;
+        for (int i = 0; i < rm[mate].n_mm; ++i) n_multi += (mmp[i] >> 30) == 2;
+        searches += n_multi * (u32)(nq[(1 - mate) * 2] + nq[(1 - mate) * 2 + 1]);
+      }
+      if (searches > PC_RESCUE_HEAVY) { pm.status = ST_OVERFLOW; agg_add(&ctr->ovf_reason[7], 1ull); return; }
+      list[agg_append(list_count)] = slot;
+      return;
+    }
     // no rescue: hits are cleared in the reference but nothing reads them afterwards; ret stays 0
+    if (small) {
+      int nc1 = nq[0] + nq[1], nc2 = nq[2] + nq[3];
+      if (nc1 > 0 && nc2 > 0) {
+        int a, b;
+        rm[0].n_buf[0] = nq[0]; rm[0].n_buf[1] = nq[1]; rm[1].n_buf[0] = nq[2]; rm[1].n_buf[1] = nq[3];
+        pe_filter_dir((u32)P.max_insert, lp[0], lc[0], nq[0], lp[3], lc[3], nq[3], CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
+        rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
+        nc1 = a; nc2 = b;
+        pe_filter_dir((u32)P.max_insert, lp[1], lc[1], nq[1], lp[2], lc[2], nq[2], CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
+        rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
+        nc1 += a; nc2 += b;
+      }
+      if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
+      agg_add(&ctr->n_candidates, (u64)(nc1 + nc2));
+      return;
+    }
   } else {
     int ret = 0;
     const u32 range = 2u * (u32)P.max_insert;
