@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,7 +52,8 @@ struct Lane {
   Counters *ctr = nullptr;
   int *d_count = nullptr;
   Tier tiers[N_TIERS];
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, aux[N_TIERS - 1] = {nullptr, nullptr};  // aux: emit of the overflow tiers, beside tier 0's
+  cudaEvent_t ev_fork = nullptr, ev_join[N_TIERS - 1] = {nullptr, nullptr};
   cudaEvent_t ev[10];
   cudaEvent_t ev_sub[2];
   cudaEvent_t ev_done = nullptr;
@@ -173,6 +175,9 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   if (const char *ev = getenv("CMX_LANES")) ctx->n_lanes = std::max(1, std::min(CMX_MAX_LANES, atoi(ev)));
   for (Lane &L : ctx->lanes) {
     CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    for (auto &a : L.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+    for (auto &e : L.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : L.ev) CU(cudaEventCreate(&e));
     for (auto &e : L.ev_sub) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
@@ -238,6 +243,9 @@ void cmx_destroy(cmx_ctx *ctx) {
     for (auto &e : L.ev_sub) cudaEventDestroy(e);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.stream) cudaStreamDestroy(L.stream);
+    for (auto &a : L.aux) if (a) cudaStreamDestroy(a);
+    if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+    for (auto &e : L.ev_join) if (e) cudaEventDestroy(e);
   }
   for (auto &e : ctx->ev) cudaEventDestroy(e);
   for (auto &e : ctx->ev_up) cudaEventDestroy(e);
@@ -700,11 +708,17 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   CUL(cudaMemcpyAsync(L.chunk_start.p, chunks.data(), chunks.size() * 4, cudaMemcpyHostToDevice, st));
   select_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(P, n_chunks, (const int *)L.chunk_start.p, (const int *)L.nbest.p, (int *)L.sel.p, ctx->mt_init);
   CUL(cudaEventRecord(L.ev[3], st));
-  for (int t = 0; t < tiers_used; ++t) {
+  // the overflow tiers' emits (few pairs, long per-thread sweeps) run beside tier 0's on their own streams
+  if (tiers_used > 1) CUL(cudaEventRecord(L.ev_fork, st));
+  for (int t = tiers_used - 1; t >= 0; --t) {
     const Scratch S = L.tiers[t].view;
-    if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)L.sel.p, (OutPairs *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
-    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    cudaStream_t es = t == 0 ? st : L.aux[t - 1];
+    if (t > 0) CUL(cudaStreamWaitEvent(es, L.ev_fork, 0));
+    if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutPairs *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    if (t > 0) CUL(cudaEventRecord(L.ev_join[t - 1], es));
   }
+  for (int t = 1; t < tiers_used; ++t) CUL(cudaStreamWaitEvent(st, L.ev_join[t - 1], 0));
   acc.launches += 1 + tiers_used;
   // read-order compaction
   size_t tmp_bytes = 0;
@@ -806,29 +820,44 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     J.want_bc = bc && out->barcode_keys;
     if (out->on_device && n_lanes == 1) J.dst = (OutRecord *)out->records;
   }
+  // every lane maps its pairs and then delivers its records itself, behind the records of the lanes before it (their
+  // counts are known as soon as those lanes have finished mapping), so the copies of early lanes overlap later lanes
+  std::atomic<int> mapped[CMX_MAX_LANES];
+  for (auto &f : mapped) f.store(0);
+  auto lane_main = [&](int l) {
+    LaneJob &J = jobs[l];
+    Lane &L = ctx->lanes[l];
+    J.rc = run_lane(ctx, L, B, J);
+    if (J.rc) J.total = 0;
+    mapped[l].store(1, std::memory_order_release);
+    u64 before = 0;
+    for (int k = 0; k < l; ++k) {
+      while (!mapped[k].load(std::memory_order_acquire)) std::this_thread::yield();
+      before += jobs[k].total;
+    }
+    if (J.rc || !J.total) return;
+    cudaError_t e = cudaSuccess;
+    if ((void *)J.dst != (void *)out->records)
+      e = cudaMemcpyAsync((OutRecord *)out->records + before, J.dst, J.total * sizeof(OutRecord), out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L.stream);
+    if (e == cudaSuccess && J.want_bc) e = cudaMemcpyAsync(out->barcode_keys + before, L.bc_out.p, J.total * 8, cudaMemcpyDeviceToHost, L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+    if (e != cudaSuccess) { L.err = std::string("record copy: ") + cudaGetErrorString(e); J.rc = CMX_ERR_CUDA; }
+  };
+  CU(cudaEventRecord(ctx->ev[2], ctx->down_stream));
   {
     std::vector<std::thread> th;
-    for (int l = 1; l < n_lanes; ++l) th.emplace_back([&, l]() { jobs[l].rc = run_lane(ctx, ctx->lanes[l], B, jobs[l]); });
-    jobs[0].rc = run_lane(ctx, ctx->lanes[0], B, jobs[0]);
+    for (int l = 1; l < n_lanes; ++l) th.emplace_back(lane_main, l);
+    lane_main(0);
     for (auto &t : th) t.join();
   }
+  CU(cudaEventRecord(ctx->ev[3], ctx->down_stream));
+  CU(cudaStreamSynchronize(ctx->down_stream));
   ctx->last_lanes_used = n_lanes;
   ctx->last_n_pairs = n;
   for (int l = 0; l < n_lanes; ++l)
     if (jobs[l].rc) { ctx->err = ctx->lanes[l].err; return jobs[l].rc; }
-  // ---- gather: records of the lanes, in lane order, into the caller's buffer
-  cudaStream_t dn = ctx->down_stream;
-  CU(cudaEventRecord(ctx->ev[2], dn));
   u64 total = 0;
-  for (int l = 0; l < n_lanes; ++l) {
-    const LaneJob &J = jobs[l];
-    if (J.total && (void *)J.dst != (void *)out->records)
-      CU(cudaMemcpyAsync((OutRecord *)out->records + total, J.dst, J.total * sizeof(OutRecord), out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, dn));
-    if (J.want_bc && J.total) CU(cudaMemcpyAsync(out->barcode_keys + total, ctx->lanes[l].bc_out.p, J.total * 8, cudaMemcpyDeviceToHost, dn));
-    total += J.total;
-  }
-  CU(cudaEventRecord(ctx->ev[3], dn));
-  CU(cudaStreamSynchronize(dn));
+  for (int l = 0; l < n_lanes; ++l) total += jobs[l].total;
   CU(cudaGetLastError());
   float ms_h2d = 0, ms_d2h = 0;
   cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);

@@ -852,6 +852,25 @@ __device__ __forceinline__ void pair_sweep(const DevParams &P, int s1, u32 L1, u
     }
   }
 }
+// same enumeration, VISIT returns true to stop it
+template <typename Visit>
+__device__ __forceinline__ void pair_sweep_until(const DevParams &P, int s1, u32 L1, u32 L2, const u64 *p1, const short *e1, int n1,
+                                                 const u64 *p2, const short *e2, int n2, Visit VISIT) {
+  int i1 = 0, i2 = 0;
+  const u64 ins = (u64)P.max_insert, ovl = (u64)(u32)P.min_read_len;
+  while (i1 < n1 && i2 < n2) {
+    if ((s1 == 1 && p1[i1] > p2[i2] + ins - L2) || (s1 == 0 && p1[i1] > p2[i2] + L1 - ovl)) ++i2;
+    else if ((s1 == 0 && p2[i2] > p1[i1] + ins - L1) || (s1 == 1 && p2[i2] > p1[i1] + L2 - ovl)) ++i1;
+    else {
+      int j = i2;
+      while (j < n2 && ((s1 == 0 && p2[j] <= p1[i1] + ins - L1) || (s1 == 1 && p2[j] <= p1[i1] + L2 - ovl))) {
+        if (VISIT(i1, j, (int)e1[i1] + (int)e2[j])) return;
+        ++j;
+      }
+      ++i1;
+    }
+  }
+}
 
 // K4: per pair — SortMappingsByPositions (mapping_metadata.h:70-78) + best-pair statistics
 // (mapping_generator.h:160-197).  pair_nbest[pair] = #best pairs if the pair reaches sampling/emit, else 0.
@@ -1203,8 +1222,8 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
     const int s1 = dir, s2 = 1 - dir;
     const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
     const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    pair_sweep(P, s1, (u32)L[0], (u32)L[1], p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) {
-      if (sum != pm.min_sum || reported == to_report) return;
+    pair_sweep_until(P, s1, (u32)L[0], (u32)L[1], p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) -> bool {
+      if (sum != pm.min_sum) return false;
       if (idx == sel[reported]) {
         u32 st1, en1, st2, en2;
         span(0, s1, p1[i1], e1[i1], &st1, &en1);
@@ -1225,6 +1244,7 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
         ++reported;
       }
       ++idx;
+      return reported == to_report;
     });
   }
   out_n[pair] = reported;
