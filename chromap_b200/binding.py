@@ -97,6 +97,7 @@ def load_library():
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
     L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.cmx_postprocess_gpu.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_pairs.restype = i64; L.cmx_format_pairs.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, i64]
     L.cmx_stage_minimizers.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, u32]
     L.cmx_stage_probe.argtypes = [vp, vp, u64, vp, vp, vp]
@@ -261,6 +262,16 @@ class Mapper:
         n = C.c_uint64()
         self._check(self.L.cmx_postprocess(self.h, recs.ctypes.data, len(recs), C.byref(n)), "cmx_postprocess")
         return recs[:n.value]
+
+    def postprocess_gpu(self, recs, bcs=None):
+        """Sort / dedup / filter on the device; same results as postprocess / postprocess_pairs / postprocess_bc."""
+        recs = np.ascontiguousarray(recs.copy())
+        n = C.c_uint64()
+        if bcs is not None:
+            bcs = np.ascontiguousarray(bcs.copy(), dtype=np.uint64)
+        self._check(self.L.cmx_postprocess_gpu(self.h, recs.ctypes.data, bcs.ctypes.data if bcs is not None else None, len(recs), C.byref(n)),
+                    "cmx_postprocess_gpu")
+        return recs[:n.value] if bcs is None else (recs[:n.value], bcs[:n.value])
 
     def postprocess_pairs(self, recs):
         recs = np.ascontiguousarray(recs.copy())

@@ -20,6 +20,7 @@
 #include "../../include/chromap_b200.h"
 #include "index_build.cuh"
 #include "pipeline_kernels.cuh"
+#include "postprocess.cuh"
 
 static_assert(sizeof(OutRecord) == sizeof(cmx_pe_record), "record layout");
 static_assert(sizeof(cmx_pe_record) == 24, "record size");
@@ -604,6 +605,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     CUL(tier_prepare(tier, n_slots, pair_list));
     const Scratch S = tier.view;
     cudaEvent_t e0 = L.ev[5], e1 = L.ev[6], e2 = L.ev[7], e3 = L.ev[8], e4 = L.ev[9];
+    int cluster_passes = 1;
     CUL(cudaEventRecord(e0, st));
     if (t == 0 && J.piece_ready) {
       // reads arrive in pieces on the upload stream: length filter / trimming and minimizers start on a piece as
@@ -637,6 +639,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
         while (rows0 < S.caps.hc && rows0 * (ctx->w + 1) < 2 * ctx->params.max_read_length) rows0 <<= 1;
         rows0 = std::min(rows0, S.caps.hc);
         cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)rows0 * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 0, rows0, (int *)L.verify_list.p, L.d_count + 3);
+        cluster_passes = rows0 < S.caps.hc ? 2 : 1;
         if (rows0 < S.caps.hc)
           cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)S.caps.hc * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 1, S.caps.hc, (int *)L.verify_list.p, L.d_count + 3);
       }
@@ -668,7 +671,10 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)L.nbest.p, c_pair);
       CUL(cudaEventRecord(e4, st));
     }
-    acc.launches += (t == 0 ? (J.piece_ready ? 6 : 8) : 6);
+    // kernels launched above: tier 0 = [prep + minimizer unless counted per piece] + probe + cluster (1 or 2 passes) +
+    // pair_candidates x2 + verify (x2 unless split) + pairing; overflow tiers = prep + four CTA kernels
+    if (t == 0) acc.launches += (J.piece_ready ? 0 : 2) + 1 + cluster_passes + 2 + (P.split ? 1 : 2) + 1;
+    else acc.launches += 5;
     CUL(ensure(tier.ovf_list, (size_t)n_slots * 4));
     CUL(cudaMemsetAsync(L.d_count, 0, sizeof(int), st));
     collect_overflow_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(S, (int *)tier.ovf_list.p, L.d_count);
@@ -779,6 +785,9 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   B.n_pairs = n; B.first_read_id = in->first_read_id;
   const u8 *bcs = nullptr, *bcq = nullptr;
   const bool pieces = !in->on_device;
+  // upload granularity: a quarter of a reference batch, so the first kernels start after a sixteenth of a 4-batch upload
+  const u32 ps = (bs % 4 == 0 && bs / 4 >= 32768) ? bs / 4 : bs;
+  u32 n_pieces = 0;
   if (in->on_device) {
     B.seq1 = (const u8 *)in->seq1; B.off1 = in->off1; B.seq2 = (const u8 *)in->seq2; B.off2 = in->off2;
     if (bc) { bcs = (const u8 *)in->bc_seq; bcq = (const u8 *)in->bc_qual; }
@@ -786,7 +795,8 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     const size_t b1 = in->off1[n], b2 = in->off2[n];
     CU(ensure(ctx->seq1, b1 + 64)); CU(ensure(ctx->seq2, b2 + 64));
     CU(ensure(ctx->off1, (size_t)(n + 1) * 4)); CU(ensure(ctx->off2, (size_t)(n + 1) * 4));
-    while (ctx->ev_up.size() < n_sub) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
+    n_pieces = (n + ps - 1) / ps;
+    while (ctx->ev_up.size() < n_pieces) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
     CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
     CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
     if (bc) {
@@ -797,8 +807,8 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
       CU(cudaEventRecord(ctx->ev_bc, up));
       bcs = (const u8 *)ctx->bc_seq.p; bcq = (const u8 *)ctx->bc_qual.p;
     }
-    for (u32 s = 0; s < n_sub; ++s) {
-      const u32 p0 = s * bs, p1 = std::min(n, p0 + bs);
+    for (u32 s = 0; s < n_pieces; ++s) {
+      const u32 p0 = s * ps, p1 = std::min(n, p0 + ps);
       CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, up));
       CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, up));
       CU(cudaEventRecord(ctx->ev_up[s], up));
@@ -815,7 +825,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     const u32 s0 = (u32)((u64)n_sub * l / n_lanes), s1 = (u32)((u64)n_sub * (l + 1) / n_lanes);
     LaneJob &J = jobs[l];
     J.p0 = s0 * bs; J.n = std::min(n, s1 * bs) - J.p0;
-    if (pieces) { J.piece = bs; J.piece0 = s0; J.piece_ready = &ctx->ev_up; }
+    if (pieces) { J.piece = ps; J.piece0 = s0 * (bs / ps); J.piece_ready = &ctx->ev_up; }
     if (bc) { J.bc_seq = bcs + (size_t)J.p0 * in->bc_len; J.bc_qual = bcq + (size_t)J.p0 * in->bc_len; J.bc_len = in->bc_len; J.bc_ready = pieces ? ctx->ev_bc : nullptr; }
     J.want_bc = bc && out->barcode_keys;
     if (out->on_device && n_lanes == 1) J.dst = (OutRecord *)out->records;
@@ -1205,6 +1215,72 @@ int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *recs, c
     len += (int64_t)line.size();
   }
   return len;
+}
+
+// Sort + duplicate removal + MAPQ filter (+ Tn5 shift) on the device, in place on host buffers: same results as
+// cmx_postprocess / cmx_postprocess_bc / cmx_postprocess_pairs (postprocess.cuh).  The record kind follows the
+// context: pairs when output_format == 5, barcoded BED when barcode_keys != NULL, else bulk BED.
+int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out) {
+  if (!ctx || (!records && n) || !n_out) return CMX_ERR_INVALID;
+  *n_out = 0;
+  if (n == 0) return CMX_OK;
+  if (n > 0x7FFFFFFFull) return fail(ctx, CMX_ERR_INVALID, "cmx_postprocess_gpu: more than 2^31-1 records in one call");
+  CU(cudaSetDevice(ctx->device));
+  const cmx_params &p = ctx->params;
+  PpParams P;
+  P.kind = p.output_format == 5 ? PP_PAIRS : (barcode_keys ? PP_BED_BC : PP_BED);
+  P.low_mem = p.low_memory_mode; P.dedup = p.remove_pcr_duplicates; P.tn5 = p.tn5_shift; P.mapq_threshold = p.mapq_threshold;
+  if (P.kind == PP_PAIRS && barcode_keys) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with pairs output");
+  const bool bc = P.kind == PP_BED_BC;
+  cudaStream_t st = ctx->stream;
+  PpRecord *d_a = nullptr, *d_b = nullptr;
+  u64 *d_bca = nullptr, *d_bcb = nullptr, *d_k0 = nullptr, *d_k1 = nullptr, *d_nsel = nullptr;
+  u32 *d_i0 = nullptr, *d_i1 = nullptr;
+  u8 *d_head = nullptr, *d_keep = nullptr;
+  void *d_tmp = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_bca); cudaFree(d_bcb); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_nsel);
+    cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_head); cudaFree(d_keep); cudaFree(d_tmp);
+  };
+#define PPCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+  PPCU(cudaMalloc(&d_a, n * sizeof(PpRecord))); PPCU(cudaMalloc(&d_b, n * sizeof(PpRecord)));
+  if (bc) { PPCU(cudaMalloc(&d_bca, n * 8)); PPCU(cudaMalloc(&d_bcb, n * 8)); }
+  PPCU(cudaMalloc(&d_k0, n * 8)); PPCU(cudaMalloc(&d_k1, n * 8)); PPCU(cudaMalloc(&d_i0, n * 4)); PPCU(cudaMalloc(&d_i1, n * 4));
+  PPCU(cudaMalloc(&d_head, n)); PPCU(cudaMalloc(&d_keep, n)); PPCU(cudaMalloc(&d_nsel, 16));
+  PPCU(cudaMemcpyAsync(d_a, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
+  if (bc) PPCU(cudaMemcpyAsync(d_bca, barcode_keys, n * 8, cudaMemcpyHostToDevice, st));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(d_a, n);  // chromap.h:1322-1355: before the sort
+  pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n);
+  cub::DoubleBuffer<u64> dk(d_k0, d_k1);
+  cub::DoubleBuffer<u32> di(d_i0, d_i1);
+  size_t tmp_bytes = 0, need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, (int)n, 0, 64, st);
+  cub::DeviceSelect::Flagged(nullptr, need, d_a, d_keep, d_b, d_nsel, (int)n, st);
+  tmp_bytes = std::max(tmp_bytes, need);
+  cub::DeviceSelect::Flagged(nullptr, need, d_bca, d_keep, d_bcb, d_nsel, (int)n, st);
+  tmp_bytes = std::max(tmp_bytes, need);
+  PPCU(cudaMalloc(&d_tmp, tmp_bytes));
+  for (int w = pp_n_words(P.kind) - 1; w >= 0; --w) {  // least significant word first; every pass is stable
+    pp_key_kernel<<<nb, 256, 0, st>>>(P.kind, w, d_a, bc ? d_bca : nullptr, di.Current(), n, dk.Current());
+    PPCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dk, di, (int)n, 0, 64, st));
+  }
+  pp_gather_kernel<<<nb, 256, 0, st>>>(d_a, bc ? d_bca : nullptr, di.Current(), n, d_b, d_bcb);
+  pp_head_kernel<<<nb, 256, 0, st>>>(P.kind, P.dedup, d_b, bc ? d_bcb : nullptr, n, d_head);
+  pp_resolve_kernel<<<nb, 256, 0, st>>>(P, d_b, bc ? d_bcb : nullptr, d_head, n, d_a, bc ? d_bca : nullptr, d_keep);
+  PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_a, d_keep, d_b, d_nsel, (int)n, st));
+  if (bc) PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_bca, d_keep, d_bcb, d_nsel + 1, (int)n, st));
+  u64 nsel = 0;
+  PPCU(cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, st));
+  PPCU(cudaStreamSynchronize(st));
+  PPCU(cudaGetLastError());
+  if (nsel) PPCU(cudaMemcpyAsync(records, d_b, nsel * sizeof(PpRecord), cudaMemcpyDeviceToHost, st));
+  if (bc && nsel) PPCU(cudaMemcpyAsync(barcode_keys, d_bcb, nsel * 8, cudaMemcpyDeviceToHost, st));
+  PPCU(cudaStreamSynchronize(st));
+#undef PPCU
+  cleanup();
+  *n_out = nsel;
+  return CMX_OK;
 }
 
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {

@@ -258,7 +258,7 @@ int main(int argc, char **argv) {
   int64_t bytes = 0;
   if (pairs) {
     cmx_pairs_record *pr = reinterpret_cast<cmx_pairs_record *>(all.data());
-    if (cmx_postprocess_pairs(ctx, pr, all.size(), &keep)) Die(cmx_last_error(ctx));
+    if (cmx_postprocess_gpu(ctx, pr, nullptr, all.size(), &keep) && cmx_postprocess_pairs(ctx, pr, all.size(), &keep)) Die(cmx_last_error(ctx));
     std::vector<const char *> rn;
     for (const auto &s : all_names) rn.push_back(s.c_str());
     std::vector<uint32_t> lens;
@@ -267,13 +267,14 @@ int main(int argc, char **argv) {
     text.resize((size_t)bytes + 1);
     cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
   } else if (sc) {
-    if (cmx_postprocess_bc(ctx, all.data(), all_bc.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+    if (cmx_postprocess_gpu(ctx, all.data(), all_bc.data(), all.size(), &keep) && cmx_postprocess_bc(ctx, all.data(), all_bc.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
     bytes = cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);
     text.resize((size_t)bytes + 1);
     cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, text.data(), bytes);
     fprintf(stderr, "Number of barcodes in whitelist: %llu.\nNumber of corrected barcodes: %llu.\n", (unsigned long long)n_bc_in, (unsigned long long)n_bc_cor);
   } else {
-    if (cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+    // sort / dedup / filter on the device; the host routine only if the records do not fit beside the index
+    if (cmx_postprocess_gpu(ctx, all.data(), nullptr, all.size(), &keep) && cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
     bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
     text.resize((size_t)bytes + 1);
     cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);

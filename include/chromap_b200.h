@@ -161,6 +161,11 @@ int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint
  * (PairedEndMappingWithBarcode, bed_mapping.h:116-167; cell-level dedup as the atac preset sets it) and written as
  * `chrom start end barcode num_dups` (mapping_writer.cc:127-137). */
 int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out);
+/* The same three routines on the device (LSD radix sort over the reference's record order + run resolution), in place on
+ * host buffers: `records` is cmx_pairs_record[] when the context emits pairs, cmx_pe_record[] otherwise; barcode_keys
+ * is NULL for bulk data.  Replaces the sort / merge of mapping_processor.h:100-202 and mapping_writer.h:166-376 the
+ * same way; results are identical to the host routines.  n < 2^31 per call. */
+int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out);
 int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys, uint64_t n, uint32_t bc_len,
                           char *buf, int64_t cap);
 /* BED text (mapping_writer.cc:75-83); names = n_seq C strings.  Returns bytes (or needed size if buf NULL). */

@@ -378,3 +378,53 @@ def test_scatac_barcodes_equal_oracle_and_golden(case, use_wl, golden_dir):
         assert (stats["n_barcodes_in_whitelist"], stats["n_barcodes_corrected"]) == (int(ost[0]), int(ost[1]))
     r2, b2 = m.postprocess_bc(recs, stats["barcode_keys"])
     assert m.format_bed_bc(r2, b2, bc_len) == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+
+
+def _random_records(rng, n, pairs):
+    """Records with many equal fragments, equal MAPQs and ties down to the last key field."""
+    if pairs:
+        r = np.zeros(n, dtype=cb.PAIRS_RECORD)
+        r["read_id"] = rng.permutation(n).astype(np.uint32)
+        r["rid1"] = rng.integers(0, 3, n); r["rid2"] = np.maximum(r["rid1"], rng.integers(0, 3, n))
+        r["pos1"] = rng.integers(0, 40, n) * 7; r["pos2"] = rng.integers(0, 40, n) * 7
+        r["strand1"] = rng.integers(0, 2, n); r["strand2"] = rng.integers(0, 2, n)
+        r["mapq"] = rng.choice([0, 1, 13, 60], n); r["is_unique"] = rng.integers(0, 2, n)
+        return r
+    r = np.zeros(n, dtype=cb.PE_RECORD)
+    r["read_id"] = rng.permutation(n).astype(np.uint32)
+    r["rid"] = rng.integers(0, 3, n)
+    r["fragment_start"] = rng.integers(0, 60, n) * 11
+    r["fragment_length"] = rng.choice([60, 61, 200, 65535], n)
+    r["mapq"] = rng.choice([0, 3, 30, 60], n); r["direction"] = rng.integers(0, 2, n); r["is_unique"] = rng.integers(0, 2, n)
+    r["num_dups"] = 1
+    r["positive_alignment_length"] = rng.choice([48, 50, 51], n); r["negative_alignment_length"] = rng.choice([49, 50], n)
+    return r
+
+
+@pytest.mark.parametrize("kind", ["bed", "bed_bc", "pairs"])
+@pytest.mark.parametrize("low_mem,dedup,tn5,q", [(1, 1, 0, 30), (1, 1, 1, 0), (1, 0, 1, 3), (0, 1, 1, 0), (0, 1, 0, 30), (0, 0, 0, 1)])
+def test_postprocess_on_device_equals_host(kind, low_mem, dedup, tn5, q):
+    rng = np.random.default_rng(7 + low_mem * 8 + dedup * 4 + tn5 * 2 + q)
+    pairs = kind == "pairs"
+    kw = dict(low_memory_mode=low_mem, remove_pcr_duplicates=dedup, mapq_threshold=q)
+    if pairs:
+        p = cb.make_params("hic", max_read_length=64, **kw)
+    else:
+        p = cb.make_params("", max_read_length=64, tn5_shift=tn5, **kw)
+    m = cb.Mapper(p)
+    for n in (1, 2, 1000, 200000):
+        recs = _random_records(rng, n, pairs)
+        if n >= 1000:  # a long run of duplicates (num_dups saturates at 255)
+            recs[: n // 3] = recs[0]
+            recs["read_id"][: n // 3] = np.arange(n // 3, dtype=np.uint32) + 7 * n
+            recs["mapq"][: n // 3] = rng.choice([0, 30, 60], n // 3)
+        if kind == "bed_bc":
+            bcs = rng.integers(0, 5, n).astype(np.uint64) * 0x123456789
+            want, wbc = m.postprocess_bc(recs, bcs)
+            got, gbc = m.postprocess_gpu(recs, bcs)
+            assert np.array_equal(wbc, gbc)
+        elif pairs:
+            want, got = m.postprocess_pairs(recs), m.postprocess_gpu(recs)
+        else:
+            want, got = m.postprocess(recs), m.postprocess_gpu(recs)
+        assert_same_records(got, want)
