@@ -323,7 +323,7 @@ def run_ours(a):
         "lanes": a.lanes,
         "mapped_fraction": dv["n_map"] / (a.steps * n),
         "tier_pairs_per_step": [x / ks for x in st["tier_pairs"]],
-        "roofline": {"kernel": "probe_kernel (minimizer-index probe + occurrence expansion)", "bound": "hbm",
+        "roofline": {"kernel": "probe_kernel (minimizer-index probe)", "bound": "hbm",
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": probe_bytes,
                      "kernel_ms": kern["probe_ms"], "kernel_share_of_step": kern["probe_ms"] / (sr["dt"] / ks * 1e3), "top_stage": top,
