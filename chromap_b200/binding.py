@@ -96,6 +96,7 @@ def load_library():
     L.cmx_format_bed_bc.restype = i64; L.cmx_format_bed_bc.argtypes = [vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
+    L.cmx_format_bed_gpu.restype = i64; L.cmx_format_bed_gpu.argtypes = [vp, vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_postprocess_gpu.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_pairs.restype = i64; L.cmx_format_pairs.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, i64]
@@ -303,6 +304,23 @@ class Mapper:
         n = self.L.cmx_format_bed_bc(arr, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, None, 0)
         buf = C.create_string_buffer(n + 1)
         self.L.cmx_format_bed_bc(arr, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, buf, n)
+        return buf.raw[:n]
+
+    def format_bed_gpu(self, recs, bcs=None, bc_len=0, names=None):
+        """BED text written on the device; byte-identical to format_bed / format_bed_bc."""
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        recs = np.ascontiguousarray(recs)
+        bp = None
+        if bcs is not None:
+            bcs = np.ascontiguousarray(bcs, dtype=np.uint64)
+            bp = bcs.ctypes.data
+        n = self.L.cmx_format_bed_gpu(self.h, arr, recs.ctypes.data, bp, len(recs), bc_len, None, 0)
+        if n < 0:
+            raise RuntimeError("cmx_format_bed_gpu: " + self.L.cmx_last_error(self.h).decode())
+        buf = C.create_string_buffer(n + 1)
+        m = self.L.cmx_format_bed_gpu(self.h, arr, recs.ctypes.data, bp, len(recs), bc_len, buf, n)
+        assert m == n
         return buf.raw[:n]
 
     def format_bed(self, recs, names=None):

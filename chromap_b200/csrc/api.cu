@@ -1283,6 +1283,60 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   return CMX_OK;
 }
 
+// BED text on the device (bed_len_kernel / bed_write_kernel), byte-identical to cmx_format_bed / cmx_format_bed_bc.
+// Records (and barcode keys, NULL for bulk data) and the output buffer are host memory; work goes through the device in
+// chunks of 8 M records.  buf == NULL: returns the text length only.  Returns < 0 on error.
+int64_t cmx_format_bed_gpu(cmx_ctx *ctx, const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys, uint64_t n,
+                           uint32_t bc_len, char *buf, int64_t cap) {
+  if (!ctx || !names || (!records && n) || (barcode_keys && (bc_len == 0 || bc_len > 32))) return -1;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+  const u32 n_seq = ctx->n_seq;
+  std::string cat;
+  std::vector<u32> noff(n_seq + 1, 0);
+  for (u32 i = 0; i < n_seq; ++i) { cat += names[i]; noff[i + 1] = (u32)cat.size(); }
+  const u64 CH = 8u << 20;
+  const u64 nc = std::min<u64>(n, CH);
+  char *d_names = nullptr, *d_out = nullptr;
+  u32 *d_noff = nullptr, *d_len = nullptr;
+  PpRecord *d_rec = nullptr;
+  u64 *d_bc = nullptr, *d_off = nullptr;
+  void *d_tmp = nullptr;
+  size_t out_cap = 0, tmp_bytes = 0;
+  int64_t total = 0;
+  bool ok = true;
+  auto CK = [&](cudaError_t e) { if (e != cudaSuccess) { ok = false; ctx->err = std::string("cmx_format_bed_gpu: ") + cudaGetErrorString(e); } return ok; };
+  cudaStream_t st = ctx->stream;
+  do {
+    if (!CK(cudaMalloc(&d_names, cat.size() + 1)) || !CK(cudaMalloc(&d_noff, (n_seq + 1) * 4))) break;
+    if (!CK(cudaMemcpyAsync(d_names, cat.data(), cat.size(), cudaMemcpyHostToDevice, st)) || !CK(cudaMemcpyAsync(d_noff, noff.data(), (n_seq + 1) * 4, cudaMemcpyHostToDevice, st))) break;
+    if (nc == 0) break;
+    if (!CK(cudaMalloc(&d_rec, nc * sizeof(PpRecord))) || !CK(cudaMalloc(&d_len, (nc + 1) * 4)) || !CK(cudaMalloc(&d_off, (nc + 1) * 8))) break;
+    if (barcode_keys && !CK(cudaMalloc(&d_bc, nc * 8))) break;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_off, (int)nc + 1, st);
+    if (!CK(cudaMalloc(&d_tmp, tmp_bytes))) break;
+    for (u64 c0 = 0; c0 < n && ok; c0 += CH) {
+      const u64 m = std::min(CH, n - c0);
+      const unsigned nb = (unsigned)((m + 255) / 256);
+      if (!CK(cudaMemcpyAsync(d_rec, records + c0, m * sizeof(PpRecord), cudaMemcpyHostToDevice, st))) break;
+      if (barcode_keys && !CK(cudaMemcpyAsync(d_bc, barcode_keys + c0, m * 8, cudaMemcpyHostToDevice, st))) break;
+      if (!CK(cudaMemsetAsync(d_len + m, 0, 4, st))) break;
+      bed_len_kernel<<<nb, 256, 0, st>>>(d_rec, m, d_noff, barcode_keys ? (int)bc_len : 0, d_len);
+      if (!CK(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len, d_off, (int)m + 1, st))) break;
+      u64 bytes = 0;
+      if (!CK(cudaMemcpyAsync(&bytes, d_off + m, 8, cudaMemcpyDeviceToHost, st)) || !CK(cudaStreamSynchronize(st))) break;
+      if (buf && total + (int64_t)bytes <= cap) {
+        if (bytes > out_cap) { cudaFree(d_out); d_out = nullptr; out_cap = bytes + bytes / 8; if (!CK(cudaMalloc(&d_out, out_cap))) break; }
+        bed_write_kernel<<<nb, 256, 0, st>>>(d_rec, d_bc, m, d_names, d_noff, barcode_keys ? (int)bc_len : 0, d_off, 0, d_out);
+        if (!CK(cudaMemcpyAsync(buf + total, d_out, bytes, cudaMemcpyDeviceToHost, st)) || !CK(cudaStreamSynchronize(st))) break;
+      }
+      total += (int64_t)bytes;
+    }
+  } while (0);
+  if (ok) CK(cudaGetLastError());
+  cudaFree(d_names); cudaFree(d_noff); cudaFree(d_rec); cudaFree(d_len); cudaFree(d_off); cudaFree(d_bc); cudaFree(d_tmp); cudaFree(d_out);
+  return ok ? total : -1;
+}
+
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {
   int64_t len = 0;
   char line[1100];

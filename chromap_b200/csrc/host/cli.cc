@@ -268,16 +268,24 @@ int main(int argc, char **argv) {
     cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
   } else if (sc) {
     if (cmx_postprocess_gpu(ctx, all.data(), all_bc.data(), all.size(), &keep) && cmx_postprocess_bc(ctx, all.data(), all_bc.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
-    bytes = cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);
-    text.resize((size_t)bytes + 1);
-    cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, text.data(), bytes);
+    bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);  // text written on the device
+    if (bytes >= 0) { text.resize((size_t)bytes + 1); bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), all_bc.data(), keep, bc_len, text.data(), bytes); }
+    if (bytes < 0) {
+      bytes = cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);
+      text.resize((size_t)bytes + 1);
+      cmx_format_bed_bc(names.data(), all.data(), all_bc.data(), keep, bc_len, text.data(), bytes);
+    }
     fprintf(stderr, "Number of barcodes in whitelist: %llu.\nNumber of corrected barcodes: %llu.\n", (unsigned long long)n_bc_in, (unsigned long long)n_bc_cor);
   } else {
     // sort / dedup / filter on the device; the host routine only if the records do not fit beside the index
     if (cmx_postprocess_gpu(ctx, all.data(), nullptr, all.size(), &keep) && cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
-    bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
-    text.resize((size_t)bytes + 1);
-    cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);
+    bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), nullptr, keep, 0, nullptr, 0);  // text written on the device
+    if (bytes >= 0) { text.resize((size_t)bytes + 1); bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), nullptr, keep, 0, text.data(), bytes); }
+    if (bytes < 0) {
+      bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
+      text.resize((size_t)bytes + 1);
+      cmx_format_bed(names.data(), all.data(), keep, text.data(), bytes);
+    }
   }
   FILE *fo = fopen(out_path.c_str(), "wb");
   if (!fo) Die("Cannot open output file " + out_path);

@@ -124,3 +124,54 @@ __global__ void pp_resolve_kernel(PpParams P, const PpRecord *recs, const u64 *b
   }
   keep_flag[i] = k;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Text writer on the device: BED lines of mapping_writer.cc:75-83 (bulk: chrom start end N mapq
+// strand dups) and :127-137 (barcoded: chrom start end barcode dups), byte-identical to cmx_format_bed[_bc].
+// Pass 1 computes every line's length, an exclusive scan places the lines, pass 2 writes them.
+__device__ __forceinline__ int dec_digits(u32 v) {
+  int d = 1;
+  while (v >= 10u) { v /= 10u; ++d; }
+  return d;
+}
+__device__ __forceinline__ char *put_dec(char *p, u32 v) {  // writes v, returns the position after it
+  const int d = dec_digits(v);
+  for (int i = d - 1; i >= 0; --i) { p[i] = (char)('0' + v % 10u); v /= 10u; }
+  return p + d;
+}
+__global__ void bed_len_kernel(const PpRecord *recs, u64 n, const u32 *name_off, int bc_len, u32 *len) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PpRecord r = recs[i];
+  const u32 start = r.w[2], end = start + pe_len(r);
+  const u32 nm = name_off[r.w[1] + 1] - name_off[r.w[1]];
+  const u32 dups = (r.w[4] >> 8) & 0xFFu;
+  u32 l = nm + 1 + dec_digits(start) + 1 + dec_digits(end) + 1;
+  if (bc_len > 0) l += (u32)bc_len + 1 + dec_digits(dups) + 1;
+  else l += 1 + 1 + dec_digits(pe_mapq(r)) + 1 + 1 + 1 + dec_digits(dups) + 1;
+  len[i] = l;
+}
+__global__ void bed_write_kernel(const PpRecord *recs, const u64 *bcs, u64 n, const char *names, const u32 *name_off, int bc_len,
+                                 const u64 *off, u64 base, char *out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PpRecord r = recs[i];
+  char *p = out + (off[i] - base);
+  const u32 a = name_off[r.w[1]], b = name_off[r.w[1] + 1];
+  for (u32 k = a; k < b; ++k) *p++ = names[k];
+  *p++ = '\t';
+  p = put_dec(p, r.w[2]); *p++ = '\t';
+  p = put_dec(p, r.w[2] + pe_len(r)); *p++ = '\t';
+  const u32 dups = (r.w[4] >> 8) & 0xFFu;
+  if (bc_len > 0) {
+    const u64 bc = bcs[i];
+    for (int j = 0; j < bc_len; ++j) *p++ = "ACGT"[(bc >> ((bc_len - 1 - j) * 2)) & 3];  // barcode_translator.h:114-123
+    *p++ = '\t';
+  } else {
+    *p++ = 'N'; *p++ = '\t';
+    p = put_dec(p, pe_mapq(r)); *p++ = '\t';
+    *p++ = pe_dir(r) ? '+' : '-'; *p++ = '\t';
+  }
+  p = put_dec(p, dups);
+  *p++ = '\n';
+}

@@ -171,6 +171,11 @@ int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *records
 /* BED text (mapping_writer.cc:75-83); names = n_seq C strings.  Returns bytes (or needed size if buf NULL). */
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, uint64_t n, char *buf,
                        int64_t cap);
+/* The same text written on the device (also the barcoded form when barcode_keys != NULL): per-line lengths, exclusive
+ * scan, one thread per line; host buffers in and out, byte-identical to cmx_format_bed / cmx_format_bed_bc.
+ * buf == NULL returns the length only; < 0 on error. */
+int64_t cmx_format_bed_gpu(cmx_ctx *ctx, const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys,
+                           uint64_t n, uint32_t bc_len, char *buf, int64_t cap);
 
 /* ---- stage-level entry points: fixture-level parity tests and ncu isolation ------------------- */
 /* MinimizerGenerator::GenerateMinimizers (minimizer_generator.cc:7-139) for every read of a host batch.

@@ -428,3 +428,20 @@ def test_postprocess_on_device_equals_host(kind, low_mem, dedup, tn5, q):
         else:
             want, got = m.postprocess(recs), m.postprocess_gpu(recs)
         assert_same_records(got, want)
+
+
+@pytest.mark.parametrize("bc", [False, True])
+def test_bed_text_on_device_equals_host(synth, bc):
+    m = _mapper(synth, CASES["default"])
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 999, 300000):
+        recs = _random_records(rng, n, False)
+        recs["rid"] = rng.integers(0, len(synth["names"]), n)
+        recs["fragment_start"] = rng.choice([0, 9, 10, 99999, 4294967295, 1000000000], n)
+        recs["num_dups"] = rng.choice([1, 9, 10, 255], n)
+        recs["mapq"] = rng.choice([0, 9, 10, 60], n)
+        if bc:
+            bcs = rng.integers(0, 1 << 32, n).astype(np.uint64)
+            assert m.format_bed_gpu(recs, bcs, 16) == m.format_bed_bc(recs, bcs, 16)
+        else:
+            assert m.format_bed_gpu(recs) == m.format_bed(recs)
