@@ -1150,6 +1150,58 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
   return reported;
 }
 
+// Single-end: the taskloop body of MapSingleEndReads (chromap.h:383-470) + GenerateBestMappingsForSingleEndRead /
+// ProcessBestMappingsForSingleEndRead (mapping_generator.h:115-157,256-343) + EmplaceBackSingleEndMappingRecord
+// (mapping_generator.cc:7-16).  No mate: no supplementation, no paired-end filter, mappings stay in verification
+// order; the sampling generator is a fresh mt19937(11) per read (mapping_generator.h:128).
+static int map_one_read_se(const orc_params &P, const orc_index &ix, const orc_reference &ref, const char *s, u32 len, u32 read_id,
+                           u32 read_index, orc_pe_record *out, int cap) {
+  if (len < (u32)P.min_read_length) return 0;
+  std::string r(s, len), neg;
+  revcomp(r.data(), len, neg);
+  ReadState rs;
+  rs.reset();
+  gen_minimizers(r.data(), len, read_index, ix.k, ix.w, rs.mm);
+  if (rs.mm.empty()) return 0;
+  gen_candidates(P, ix, rs);
+  if (rs.cand[0].size() + rs.cand[1].size() == 0) return 0;
+  verify_read(P, ref, r.data(), neg, len, rs);
+  if (rs.map[0].size() + rs.map[1].size() == 0) return 0;
+  std::vector<int> sel(P.max_num_best_mappings);
+  std::iota(sel.begin(), sel.end(), 0);
+  if (rs.n_best > P.max_num_best_mappings) {
+    std::mt19937 gen(11);
+    for (int i = P.max_num_best_mappings; i < rs.n_best; ++i) {
+      std::uniform_int_distribution<int> dist(0, i);
+      const int j = dist(gen);
+      if (j < P.max_num_best_mappings) sel[j] = i;
+    }
+    std::sort(sel.begin(), sel.end());
+  }
+  int idx = 0, reported = 0;
+  const int to_report = std::min(rs.n_best, P.max_num_best_mappings);
+  for (int st = 0; st < 2 && reported != to_report; ++st) {
+    for (const Draft &d : rs.map[st]) {
+      if (d.err > rs.min_err) continue;
+      if (idx == sel[reported]) {
+        u32 a, b;
+        ref_span(P, ref, d, st == 0 ? r.data() : neg.data(), len, a, b);
+        const uint16_t al = b - a + 1;
+        if (reported < cap) {
+          orc_pe_record &o = out[reported];
+          memset(&o, 0, sizeof(o));
+          o.read_id = read_id; o.rid = (u32)(d.pos >> 32); o.fragment_start = a; o.fragment_length = al;
+          o.mapq = mapq_se(d.err, al, (int)len, P.error_threshold, rs);
+          o.direction = st == 0 ? 1 : 0; o.is_unique = rs.n_best == 1 ? 1 : 0; o.num_dups = 1;
+        }
+        if (++reported == to_report) break;
+      }
+      ++idx;
+    }
+  }
+  return reported;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Host-side pieces: FASTA/FASTQ reader (kseq.h semantics: name = first token, multi-line sequence),
 // index file I/O, post-processing, BED text.
@@ -1808,6 +1860,111 @@ int orc_run_files(const orc_params *p, const char *index_path, const char *ref_p
   fclose(f);
   if (mapping_seconds) *mapping_seconds = secs;
   if (n_pairs_out) *n_pairs_out = total;
+  orc_mapper_free(m); orc_index_free(ix); orc_reference_free(ref);
+  return 0;
+}
+
+
+// ---- single-end (MappingWithoutBarcode, bed_mapping.h:61-113) -----------------------------------------------
+int64_t orc_map_reads_se(orc_mapper *m, uint32_t n, const char *seq, const uint32_t *off, uint32_t first_read_id, orc_pe_record *out,
+                         int64_t cap_out, int n_threads) {
+  const int per = m->P.max_num_best_mappings;
+  std::vector<orc_pe_record> all((size_t)n * per);
+  std::vector<int> cnt(n, 0);
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int64_t i = 0; i < (int64_t)n; ++i)
+    cnt[i] = map_one_read_se(m->P, *m->ix, *m->ref, seq + off[i], off[i + 1] - off[i], first_read_id + (u32)i, (u32)i, &all[(size_t)i * per], per);
+  int64_t n_out = 0;
+  for (u32 i = 0; i < n; ++i) for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) out[n_out++] = all[(size_t)i * per + j];
+  return n_out;
+}
+
+static inline void tn5_se(orc_pe_record &r) {  // bed_mapping.h:97-103
+  if (r.direction == 1) r.fragment_start += 4; else r.fragment_length -= 5;
+}
+
+// Order bed_mapping.h:83-88 (prefixed by rid), duplicates = same start on the same sequence (:89-92).
+int64_t orc_postprocess_se(const orc_params *p, orc_pe_record *recs, int64_t n) {
+  if (n == 0) return 0;
+  auto key = [](const orc_pe_record &r) { return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, r.mapq, r.direction, r.is_unique, r.read_id); };
+  auto less = [&](const orc_pe_record &a, const orc_pe_record &b) { return key(a) < key(b); };
+  auto same = [](const orc_pe_record &a, const orc_pe_record &b) { return a.rid == b.rid && a.fragment_start == b.fragment_start; };
+  int64_t o = 0;
+  if (p->low_memory_mode) {  // mapping_writer.h:166-376
+    std::sort(recs, recs + n, less);
+    int64_t i = 0;
+    while (i < n) {
+      orc_pe_record keep = recs[i];
+      u32 dups = 1;
+      int64_t j = i + 1;
+      if (p->remove_pcr_duplicates)
+        for (; j < n && same(recs[j], recs[i]); ++j) { ++dups; if (recs[j].mapq > keep.mapq) keep = recs[j]; }
+      if (keep.mapq >= p->mapq_threshold) {
+        keep.num_dups = std::min<u32>(255, dups);
+        if (p->tn5_shift) tn5_se(keep);
+        recs[o++] = keep;
+      }
+      i = j;
+    }
+    return o;
+  }
+  if (p->tn5_shift) for (int64_t i = 0; i < n; ++i) tn5_se(recs[i]);  // chromap.h:594-597
+  std::sort(recs, recs + n, less);
+  if (p->remove_pcr_duplicates) {  // mapping_processor.h:161-202
+    int64_t i = 0, w = 0;
+    while (i < n) {
+      int64_t j = i + 1;
+      while (j < n && same(recs[j], recs[j - 1])) ++j;
+      orc_pe_record keep = recs[j - 1];
+      keep.num_dups = std::min<u32>(255, (u32)(j - i));
+      recs[w++] = keep;
+      i = j;
+    }
+    n = w;
+  }
+  for (int64_t i = 0; i < n; ++i) if (recs[i].mapq >= p->mapq_threshold) recs[o++] = recs[i];
+  return o;
+}
+
+int orc_run_files_se(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *out_path,
+                     int n_threads) {
+  orc_reference *ref = orc_reference_load(ref_path);
+  orc_index *ix = orc_index_load(index_path);
+  if (!ref || !ix) return -1;
+  orc_mapper *m = orc_mapper_create(p, ix, ref);
+  if (!m) return -2;
+  SeqReader r1;
+  if (!r1.open(read1_path)) return -3;
+  std::vector<orc_pe_record> recs;
+  const u32 batch = 500000;
+  u32 read_id = 0;
+  for (;;) {
+    std::string s1, n, s, q;
+    std::vector<u32> o1{0};
+    u32 cnt = 0;
+    while (cnt < batch) {
+      bool a = r1.next(n, s, q);
+      while (a && s.empty()) a = r1.next(n, s, q);
+      if (!a) break;
+      s1 += s; o1.push_back(s1.size());
+      ++cnt;
+    }
+    if (cnt == 0) break;
+    const size_t base = recs.size();
+    recs.resize(base + (size_t)cnt * p->max_num_best_mappings);
+    const int64_t got = orc_map_reads_se(m, cnt, s1.data(), o1.data(), read_id, recs.data() + base, recs.size() - base, n_threads);
+    recs.resize(base + got);
+    read_id += cnt;
+  }
+  r1.close();
+  const int64_t keep = orc_postprocess_se(p, recs.data(), recs.size());
+  const int64_t bytes = orc_format_bed(ref, recs.data(), keep, nullptr, 0);
+  std::vector<char> text(bytes + 1);
+  orc_format_bed(ref, recs.data(), keep, text.data(), bytes);
+  FILE *f = fopen(out_path, "wb");
+  if (!f) return -5;
+  fwrite(text.data(), 1, bytes, f);
+  fclose(f);
   orc_mapper_free(m); orc_index_free(ix); orc_reference_free(ref);
   return 0;
 }

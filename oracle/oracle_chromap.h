@@ -174,6 +174,14 @@ int orc_run_files(const orc_params *p, const char *index_path, const char *ref_p
                   const char *read1_path, const char *read2_path, const char *out_path,
                   int n_threads, double *mapping_seconds, uint64_t *n_pairs);
 
+
+// Single-end (chromap.h:218-634 with MappingWithoutBarcode): records use orc_pe_record with both alignment lengths 0.
+int64_t orc_map_reads_se(orc_mapper *m, uint32_t n, const char *seq, const uint32_t *off, uint32_t first_read_id, orc_pe_record *out,
+                         int64_t cap_out, int n_threads);
+int64_t orc_postprocess_se(const orc_params *p, orc_pe_record *recs, int64_t n);
+int orc_run_files_se(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *out_path,
+                     int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,9 @@ def lib():
         L.orc_format_bed_bc.restype = i64; L.orc_format_bed_bc.argtypes = [vp, vp, vp, i64, u32, vp, i64]
         L.orc_run_files_bc.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 7 + [i32, vp]
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.orc_map_reads_se.restype = i64; L.orc_map_reads_se.argtypes = [vp, u32, vp, vp, u32, vp, i64, i32]
+        L.orc_postprocess_se.restype = i64; L.orc_postprocess_se.argtypes = [C.POINTER(Params), vp, i64]
+        L.orc_run_files_se.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 4 + [i32]
         _lib = L
     return _lib
 
@@ -206,6 +209,32 @@ def run_files(params, index_path, ref_path, r1, r2, out, n_threads=1):
     if rc != 0:
         raise RuntimeError("orc_run_files failed: %d" % rc)
     return secs.value, n.value
+
+
+def map_reads_se(params, index, ref, seq, off, first_read_id=0, n_threads=1):
+    """Single-end: one batch of reads -> records (alignment lengths unused)."""
+    L = lib()
+    m = L.orc_mapper_create(C.byref(params), index.h, ref.h)
+    if not m:
+        raise ValueError("unsupported parameters for the oracle")
+    n = len(off) - 1
+    out = np.zeros(n * params.max_num_best_mappings, dtype=PE_RECORD)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.uint32)
+    got = L.orc_map_reads_se(m, n, seq.ctypes.data, off.ctypes.data, first_read_id, out.ctypes.data, len(out), n_threads)
+    L.orc_mapper_free(m)
+    return out[:got]
+
+
+def postprocess_se(params, recs):
+    recs = np.ascontiguousarray(recs.copy())
+    n = lib().orc_postprocess_se(C.byref(params), recs.ctypes.data, len(recs))
+    return recs[:n]
+
+
+def run_files_se(params, index_path, ref_path, r1, out, n_threads=1):
+    rc = lib().orc_run_files_se(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), out.encode(), n_threads)
+    if rc != 0:
+        raise RuntimeError("orc_run_files_se failed: %d" % rc)
 
 
 class Whitelist:

@@ -145,3 +145,27 @@ def test_scatac_barcodes_match_reference_binary(case, use_wl, golden_dir, tmp_pa
     if use_wl:
         s = open(os.path.join(d, "sc_stats.txt")).read()
         assert "whitelist: %d." % st[0] in s and "corrected barcodes: %d." % st[1] in s
+
+
+SE_CASES = {
+    "se_default": dict(preset=""),
+    "se_chip": dict(preset="chip"),
+    "se_q0dedup_tn5": dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1),
+    "se_n3q0": dict(preset="", max_num_best_mappings=3, mapq_threshold=0),
+    "se_lowmem_q0": dict(preset="", low_memory_mode=1, mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SE_CASES))
+def test_single_end_oracle_reproduces_reference_bed(golden_dir, tmp_path, case):
+    """chromap -1 read1.fq (single-end, MappingWithoutBarcode): oracle output == the reference binary's BED."""
+    d = os.path.join(golden_dir, "synth_small")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    ip = str(tmp_path / "ref.index")
+    idx.save(ip)
+    kw = dict(SE_CASES[case])
+    p = orc.make_params(kw.pop("preset"), **kw)
+    out = str(tmp_path / "out.bed")
+    orc.run_files_se(p, ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), out, 2)
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
