@@ -21,7 +21,7 @@ class Params(C.Structure):
         "error_threshold", "min_num_seeds", "max_seed_freq0", "max_seed_freq1", "max_num_best_mappings",
         "max_insert_size", "mapq_threshold", "min_read_length", "drop_repetitive_reads", "trim_adapters",
         "remove_pcr_duplicates", "tn5_shift", "split_alignment", "low_memory_mode", "output_format",
-        "batch_size", "max_read_length")]
+        "batch_size", "max_read_length", "single_end")]
 
 
 class Batch(C.Structure):
@@ -222,8 +222,9 @@ class Mapper:
         """Host numpy arrays (or device pointers / torch tensors when on_device).  Returns (records, stats)."""
         n = n_pairs if n_pairs is not None else len(off1) - 1
         if not on_device:
-            seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
-            off1 = np.ascontiguousarray(off1, dtype=np.uint32); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
+            seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); off1 = np.ascontiguousarray(off1, dtype=np.uint32)
+            if seq2 is not None:  # None: single-end (params.single_end)
+                seq2 = np.ascontiguousarray(seq2, dtype=np.uint8); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
         if barcodes is not None and not on_device:
             barcodes = np.ascontiguousarray(barcodes, dtype=np.uint8); barcode_quals = np.ascontiguousarray(barcode_quals, dtype=np.uint8)
         b = Batch(n, _ptr(seq1), _ptr(off1), _ptr(seq2), _ptr(off2), first_read_id, 1 if on_device else 0,

@@ -142,6 +142,7 @@ void cmx_default_params(cmx_params *p) {
   p->max_num_best_mappings = 1; p->max_insert_size = 1000; p->mapq_threshold = 30; p->min_read_length = 30;
   p->drop_repetitive_reads = 500000; p->trim_adapters = 0; p->remove_pcr_duplicates = 0; p->tn5_shift = 0;
   p->split_alignment = 0; p->low_memory_mode = 0; p->output_format = 1; p->batch_size = 500000; p->max_read_length = 160;
+  p->single_end = 0;
 }
 
 int cmx_apply_preset(cmx_params *p, const char *preset) {  // chromap_driver.cc:247-275
@@ -165,6 +166,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   if (params->error_threshold < 1 || params->error_threshold >= 16) return CMX_ERR_INVALID;  // mapping_parameters.h:80-88
   if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
   if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
+  if (params->single_end && (params->split_alignment || params->output_format != 1)) return CMX_ERR_INVALID;  // single-end: BED only
   cmx_ctx *ctx = new cmx_ctx;
   ctx->device = device;
   ctx->params = *params;
@@ -499,6 +501,7 @@ static DevParams make_dev_params(const cmx_ctx *ctx) {
   d.drop_rep = p.drop_repetitive_reads; d.trim = p.trim_adapters; d.k = ctx->k; d.w = ctx->w;
   d.lanes = p.error_threshold < 8 ? 8 : 4;  // mapping_parameters.h:80-88
   d.split = p.split_alignment;
+  d.se = p.single_end;
   return d;
 }
 
@@ -721,6 +724,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     cudaStream_t es = t == 0 ? st : L.aux[t - 1];
     if (t > 0) CUL(cudaStreamWaitEvent(es, L.ev_fork, 0));
     if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutPairs *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else if (P.se) emit_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     if (t > 0) CUL(cudaEventRecord(L.ev_join[t - 1], es));
   }
@@ -770,6 +774,8 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   out->n_barcodes_in_whitelist = out->n_barcodes_corrected = 0;
   if (in->bc_seq && (in->bc_len == 0 || in->bc_len > 32 || !in->bc_qual)) return fail(ctx, CMX_ERR_INVALID, "barcodes need bc_qual and 1 <= bc_len <= 32");
   if (in->bc_seq && ctx->params.split_alignment) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with split alignment");
+  const bool se = ctx->params.single_end != 0;
+  if (!in->seq1 || !in->off1 || (!se && (!in->seq2 || !in->off2))) return fail(ctx, CMX_ERR_INVALID, "cmx_batch: read pointers missing");
   if (n == 0) return CMX_OK;
   if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
   CU(cudaSetDevice(ctx->device));
@@ -792,13 +798,13 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     B.seq1 = (const u8 *)in->seq1; B.off1 = in->off1; B.seq2 = (const u8 *)in->seq2; B.off2 = in->off2;
     if (bc) { bcs = (const u8 *)in->bc_seq; bcq = (const u8 *)in->bc_qual; }
   } else {
-    const size_t b1 = in->off1[n], b2 = in->off2[n];
+    const size_t b1 = in->off1[n], b2 = se ? 0 : in->off2[n];
     CU(ensure(ctx->seq1, b1 + 64)); CU(ensure(ctx->seq2, b2 + 64));
     CU(ensure(ctx->off1, (size_t)(n + 1) * 4)); CU(ensure(ctx->off2, (size_t)(n + 1) * 4));
     n_pieces = (n + ps - 1) / ps;
     while (ctx->ev_up.size() < n_pieces) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
     CU(cudaMemcpyAsync(ctx->off1.p, in->off1, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
-    CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
+    if (!se) CU(cudaMemcpyAsync(ctx->off2.p, in->off2, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, up));
     if (bc) {
       CU(ensure(ctx->bc_seq, (size_t)n * in->bc_len + 16)); CU(ensure(ctx->bc_qual, (size_t)n * in->bc_len + 16));
       CU(cudaMemcpyAsync(ctx->bc_seq.p, in->bc_seq, (size_t)n * in->bc_len, cudaMemcpyHostToDevice, up));
@@ -810,7 +816,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     for (u32 s = 0; s < n_pieces; ++s) {
       const u32 p0 = s * ps, p1 = std::min(n, p0 + ps);
       CU(cudaMemcpyAsync((char *)ctx->seq1.p + in->off1[p0], in->seq1 + in->off1[p0], in->off1[p1] - in->off1[p0], cudaMemcpyHostToDevice, up));
-      CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, up));
+      if (!se) CU(cudaMemcpyAsync((char *)ctx->seq2.p + in->off2[p0], in->seq2 + in->off2[p0], in->off2[p1] - in->off2[p0], cudaMemcpyHostToDevice, up));
       CU(cudaEventRecord(ctx->ev_up[s], up));
     }
     B.seq1 = (const u8 *)ctx->seq1.p; B.off1 = (const u32 *)ctx->off1.p;
@@ -1072,6 +1078,9 @@ static inline auto rec_key(const cmx_pe_record &r) {  // bed_mapping.h:208-215 p
 static inline void tn5(cmx_pe_record &r) {  // bed_mapping.h:225-230
   r.fragment_start += 4; r.positive_alignment_length -= 4; r.fragment_length -= 9; r.negative_alignment_length -= 5;
 }
+static inline void tn5_se(cmx_pe_record &r) {  // single-end, bed_mapping.h:97-103
+  if (r.direction == 1) r.fragment_start += 4; else r.fragment_length -= 5;
+}
 
 int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t n, uint64_t *n_out) {
   if (!ctx || (!recs && n) || !n_out) return CMX_ERR_INVALID;
@@ -1079,7 +1088,11 @@ int cmx_postprocess(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t n, uint64_t *n_o
   *n_out = 0;
   if (n == 0) return CMX_OK;
   auto less = [](const cmx_pe_record &a, const cmx_pe_record &b) { return rec_key(a) < rec_key(b); };
-  auto same = [](const cmx_pe_record &a, const cmx_pe_record &b) { return a.rid == b.rid && a.fragment_start == b.fragment_start && a.fragment_length == b.fragment_length; };
+  const bool se = p.single_end != 0;  // single-end duplicates: same start on the same sequence (bed_mapping.h:89-92)
+  auto same = [se](const cmx_pe_record &a, const cmx_pe_record &b) {
+    return a.rid == b.rid && a.fragment_start == b.fragment_start && (se || a.fragment_length == b.fragment_length);
+  };
+  auto tn5 = [se](cmx_pe_record &r) { if (se) tn5_se(r); else ::tn5(r); };
   uint64_t o = 0;
   if (p.low_memory_mode) {  // mapping_writer.h:166-376
     std::sort(recs, recs + n, less);
@@ -1228,7 +1241,7 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   CU(cudaSetDevice(ctx->device));
   const cmx_params &p = ctx->params;
   PpParams P;
-  P.kind = p.output_format == 5 ? PP_PAIRS : (barcode_keys ? PP_BED_BC : PP_BED);
+  P.kind = p.output_format == 5 ? PP_PAIRS : (barcode_keys ? PP_BED_BC : (p.single_end ? PP_BED_SE : PP_BED));
   P.low_mem = p.low_memory_mode; P.dedup = p.remove_pcr_duplicates; P.tn5 = p.tn5_shift; P.mapq_threshold = p.mapq_threshold;
   if (P.kind == PP_PAIRS && barcode_keys) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with pairs output");
   const bool bc = P.kind == PP_BED_BC;
@@ -1250,7 +1263,7 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   PPCU(cudaMemcpyAsync(d_a, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
   if (bc) PPCU(cudaMemcpyAsync(d_bca, barcode_keys, n * 8, cudaMemcpyHostToDevice, st));
   const unsigned nb = (unsigned)((n + 255) / 256);
-  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(d_a, n);  // chromap.h:1322-1355: before the sort
+  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(P.kind, d_a, n);  // chromap.h:1322-1355: before the sort
   pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n);
   cub::DoubleBuffer<u64> dk(d_k0, d_k1);
   cub::DoubleBuffer<u32> di(d_i0, d_i1);

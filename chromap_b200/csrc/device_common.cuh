@@ -14,6 +14,7 @@ typedef unsigned char u8;
 // Parameters the kernels read (subset of cmx_params + index k/w).
 struct DevParams {
   int e, min_seeds, f0, f1, max_best, max_insert, min_read_len, drop_rep, trim, k, w, lanes, split;
+  int se;  // single-end: a slot holds one read (mate 0), mate 1 stays empty
 };
 
 struct Caps {  // per-read (per-strand where applicable) scratch capacities of one tier

@@ -54,11 +54,11 @@ __global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
   const int pair = slot_pair(S, slot);
   PairMeta pm;
   pm.status = ST_OK; pm.sup = 0; pm.min_sum = 0; pm.second_min_sum = 0; pm.n_best = 0; pm.n_second_best = 0; pm.n_rec = 0; pm.pad = 0;
-  int len1 = read_raw_len(B, pair, 0), len2 = read_raw_len(B, pair, 1);
+  int len1 = read_raw_len(B, pair, 0), len2 = P.se ? 0 : read_raw_len(B, pair, 1);
   if (B.bc_ok && !B.bc_ok[pair]) pm.status = ST_DROP;  // chromap.h:908-909
-  else if (len1 < P.min_read_len || len2 < P.min_read_len) pm.status = ST_DROP;
+  else if (len1 < P.min_read_len || (!P.se && len2 < P.min_read_len)) pm.status = ST_DROP;  // single-end: chromap.h:411-414
   else if (len1 > S.caps.maxmm || len2 > S.caps.maxmm) pm.status = ST_OVERFLOW;  // longer than max_read_length
-  else if (P.trim) {
+  else if (P.trim && !P.se) {
     const u8 *raw1 = read_ptr(B, pair, 0), *raw2 = read_ptr(B, pair, 1);
     const bool swp = !(len1 <= len2);
     const u8 *r1 = swp ? raw2 : raw1;   // the shorter read
@@ -257,7 +257,7 @@ __global__ void minimizer_kernel(DevParams P, DevBatch B, Scratch S, Counters *c
   const int sr = blockIdx.x * blockDim.x + threadIdx.x;
   if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1, mate = sr & 1;
-  if (S.pmeta[slot].status != ST_OK) return;
+  if (S.pmeta[slot].status != ST_OK || (P.se && mate == 1)) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
   const Caps c = S.caps;
@@ -531,6 +531,13 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   bool aug[2];
+  if (P.se) {  // single-end (chromap.h:449-453): a read goes on iff it has minimizers and candidates
+    if (mode != 0) return;
+    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1];
+    if (rm[0].n_mm == 0 || a1 == 0) { pm.status = ST_DROP; return; }
+    agg_add(&ctr->n_candidates, (u64)a1);
+    return;
+  }
   if (P.split) {  // chromap.h:1021,1036-1038: no mate supplementation and no paired-end filter under split alignment
     if (mode != 0) return;
     if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { pm.status = ST_DROP; return; }
@@ -744,7 +751,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
     sr = list[tid];
   } else if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1, mate = sr & 1;
-  if (S.pmeta[slot].status != ST_OK) return;
+  if (S.pmeta[slot].status != ST_OK || (P.se && mate == 1)) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
   const Caps c = S.caps;
@@ -882,6 +889,12 @@ __global__ void pairing_kernel(DevParams P, Scratch S, int *pair_nbest) {
   if (pm.status != ST_OK) { if (pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
   const Caps c = S.caps;
   ReadMeta *rm = S.rmeta + 2 * slot;
+  if (P.se) {  // single-end: the read's own best / second-best tallies; mappings stay in verification order
+    if (rm[0].n_map[0] + rm[0].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; return; }
+    pm.min_sum = rm[0].min_err; pm.second_min_sum = rm[0].second_min_err; pm.n_best = rm[0].n_best; pm.n_second_best = rm[0].n_second_best;
+    pair_nbest[pair] = rm[0].n_best;
+    return;
+  }
   if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; return; }
   // equal positions are interchangeable for the output; (pos, err) makes the order canonical
   auto mless = [](u64 pa, short ea, u64 pb, short eb) { return pa != pb ? pa < pb : ea < eb; };
@@ -1002,7 +1015,8 @@ __global__ void __launch_bounds__(128) select_kernel(DevParams P, int n_chunks, 
       const int l = __ffs(m) - 1;
       m &= m - 1;
       const int nbl = __shfl_sync(0xffffffffu, nb, l);
-      if (!seeded) {
+      if (!seeded || P.se) {  // single-end: a fresh generator per read (mapping_generator.h:128)
+        __syncwarp();
         for (int i = lane; i < MT_N; i += 32) g.mt[i] = mt_init[i];
         __syncwarp();
         g.pos = MT_N;
@@ -1253,6 +1267,61 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
 }
 
 // compaction of per-pair records into read order
+// Single-end emit: ProcessBestMappingsForSingleEndRead (mapping_generator.h:256-343) + EmplaceBackSingleEndMappingRecord
+// (mapping_generator.cc:7-16).  + strand mappings first, then - strand, in verification order.
+__global__ void emit_se_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, const int *pair_sel, OutRecord *out, int *out_n,
+                               Counters *ctr) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= S.n_slots) return;
+  PairMeta &pm = S.pmeta[slot];
+  const int pair = slot_pair(S, slot);
+  if (pm.status == ST_OVERFLOW) return;
+  if (pm.status != ST_OK || pm.n_best == 0) { out_n[pair] = 0; return; }
+  const Caps c = S.caps;
+  const ReadMeta &rm = S.rmeta[2 * slot];
+  const int mb = P.max_best, e = P.e, L = rm.len;
+  const int to_report = mb < rm.n_best ? mb : rm.n_best;
+  const int *sel = pair_sel + (size_t)pair * mb;
+  const u8 *r = read_ptr(B, pair, 0);
+  int idx = 0, reported = 0;
+  for (int s = 0; s < 2 && reported != to_report; ++s) {
+    const u64 *mp = S.map_pos + ((size_t)(2 * slot) * 2 + s) * c.mc;
+    const short *me = S.map_err + ((size_t)(2 * slot) * 2 + s) * c.mc;
+    for (int mi = 0; mi < rm.n_map[s]; ++mi) {
+      if ((int)me[mi] > rm.min_err) continue;
+      if (idx == sel[reported]) {
+        const u64 dpos = mp[mi];
+        const u32 rid = (u32)(dpos >> 32), rp = (u32)dpos;
+        u32 vws = rp + 1u > (u32)(L + e) ? rp + 1u - (u32)L - (u32)e : 0u;
+        if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)L;
+        const u8 *win = R.seq + R.off[rid] + vws;
+        int s0;
+        if (s == 0) s0 = banded_traceback(e, (int)me[mi], L, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[i]; });
+        else s0 = banded_traceback(e, (int)me[mi], L, [&](int i) { return __ldg(win + i); }, [&](int i) { return code_char(neg_code(r, L, i)); });
+        const u32 st = vws + (u32)s0;
+        const unsigned short al = (unsigned short)(rp - st + 1u);
+        OutRecord o;
+        o.read_id = B.first_read_id + (u32)pair;
+        o.rid = rid;
+        o.fragment_start = st;
+        o.fragment_length = al;
+        o.mapq = mapq_se(T, (int)me[mi], al, L, e, rm);
+        o.direction = s == 0 ? 1 : 0;
+        o.is_unique = rm.n_best == 1 ? 1 : 0;
+        o.num_dups = 1;
+        o.positive_alignment_length = 0;
+        o.negative_alignment_length = 0;
+        out[(size_t)pair * mb + reported] = o;
+        if (++reported == to_report) break;
+      }
+      ++idx;
+    }
+  }
+  out_n[pair] = reported;
+  pm.n_rec = reported;
+  if (reported > 0) { agg_add(&ctr->n_mapped, 1ull); if (rm.n_best == 1) agg_add(&ctr->n_unique, 1ull); }
+}
+
 __global__ void compact_kernel(int n_pairs, int mb, const OutRecord *in, const int *n_rec, const u64 *offs, OutRecord *out) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= n_pairs) return;
@@ -1611,7 +1680,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   // the mate's CTA may flag the pair concurrently: read the status once, uniformly
   if (tid == 0) s_i[7] = S.pmeta[slot].status;
   __syncthreads();
-  if (s_i[7] != ST_OK) return;
+  if (s_i[7] != ST_OK || (P.se && mate == 1)) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
   const Caps c = S.caps;
@@ -1845,6 +1914,12 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
   ReadMeta *rm = S.rmeta + 2 * slot;
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
+  if (P.se) {
+    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1];
+    __syncthreads();
+    if (tid == 0) { if (rm[0].n_mm == 0 || a1 == 0) pm.status = ST_DROP; else atomicAdd(&ctr->n_candidates, (u64)a1); }
+    return;
+  }
   if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { __syncthreads(); if (tid == 0) pm.status = ST_DROP; return; }
   if (P.split) {
     const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1], a2 = rm[1].n_cand[0] + rm[1].n_cand[1];
@@ -1949,7 +2024,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
   const int slot = sr >> 1, mate = sr & 1;
   if (tid == 0) s_status = S.pmeta[slot].status;  // the mate's CTA may flag the pair concurrently
   __syncthreads();
-  if (s_status != ST_OK) return;
+  if (s_status != ST_OK || (P.se && mate == 1)) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
   const Caps c = S.caps;
@@ -2056,6 +2131,17 @@ __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratc
   if (pm.status != ST_OK) { if (tid == 0 && pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
   const Caps c = S.caps;
   ReadMeta *rm = S.rmeta + 2 * slot;
+  if (P.se) {
+    __syncthreads();
+    if (tid == 0) {
+      if (rm[0].n_map[0] + rm[0].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
+      else {
+        pm.min_sum = rm[0].min_err; pm.second_min_sum = rm[0].second_min_err; pm.n_best = rm[0].n_best; pm.n_second_best = rm[0].n_second_best;
+        pair_nbest[pair] = rm[0].n_best;
+      }
+    }
+    return;
+  }
   if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) {
     __syncthreads();
     if (tid == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
@@ -2173,7 +2259,7 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
   const int sr = blockIdx.x * blockDim.x + threadIdx.x;
   if (sr >= 2 * S.n_slots) return;
   const int slot = sr >> 1, mate = sr & 1;
-  if (S.pmeta[slot].status != ST_OK) return;
+  if (S.pmeta[slot].status != ST_OK || (P.se && mate == 1)) return;
   const int pair = slot_pair(S, slot);
   ReadMeta &rm = S.rmeta[sr];
   const Caps c = S.caps;

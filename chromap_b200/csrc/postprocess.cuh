@@ -13,7 +13,7 @@
 
 #include "device_common.cuh"
 
-enum { PP_BED = 0, PP_BED_BC = 1, PP_PAIRS = 2 };
+enum { PP_BED = 0, PP_BED_BC = 1, PP_PAIRS = 2, PP_BED_SE = 3 };  // PP_BED_SE: single-end records (MappingWithoutBarcode)
 
 struct PpRecord {  // 24 bytes, viewed as cmx_pe_record or cmx_pairs_record
   u32 w[6];
@@ -56,6 +56,7 @@ static inline int pp_n_words(int kind) { return kind == PP_BED_BC ? 4 : 3; }
 
 __device__ __forceinline__ bool pp_same_fragment(int kind, const PpRecord &a, u64 bca, const PpRecord &b, u64 bcb) {
   if (kind == PP_PAIRS) return a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3] && a.w[4] == b.w[4];
+  if (kind == PP_BED_SE) return a.w[1] == b.w[1] && a.w[2] == b.w[2];  // bed_mapping.h:89-92
   const bool s = a.w[1] == b.w[1] && a.w[2] == b.w[2] && pe_len(a) == pe_len(b);
   return kind == PP_BED_BC ? (s && bca == bcb) : s;
 }
@@ -68,9 +69,14 @@ __device__ __forceinline__ void pp_tn5(PpRecord &r) {  // bed_mapping.h:225-230
   r.w[5] = (r.w[5] & 0xFFFF0000u) | nal;
 }
 
-__global__ void pp_tn5_kernel(PpRecord *recs, u64 n) {
+__device__ __forceinline__ void pp_tn5_se(PpRecord &r) {  // bed_mapping.h:97-103
+  if (pe_dir(r) == 1u) r.w[2] += 4u;
+  else r.w[3] = (r.w[3] & 0xFFFF0000u) | ((pe_len(r) - 5u) & 0xFFFFu);
+}
+__device__ __forceinline__ void pp_tn5_any(int kind, PpRecord &r) { if (kind == PP_BED_SE) pp_tn5_se(r); else pp_tn5(r); }
+__global__ void pp_tn5_kernel(int kind, PpRecord *recs, u64 n) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) pp_tn5(recs[i]);
+  if (i < n) pp_tn5_any(kind, recs[i]);
 }
 __global__ void pp_iota_kernel(u32 *idx, u64 n) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +123,7 @@ __global__ void pp_resolve_kernel(PpParams P, const PpRecord *recs, const u64 *b
   if (k) {
     if (kind != PP_PAIRS) {
       if (P.dedup) keep.w[4] = (keep.w[4] & 0xFFFF00FFu) | ((dups > 255u ? 255u : dups) << 8);  // num_dups saturates (mapping_writer.h:282-284)
-      if (P.low_mem && P.tn5) pp_tn5(keep);
+      if (P.low_mem && P.tn5) pp_tn5_any(kind, keep);
     }
     res[i] = keep;
     if (res_bc) res_bc[i] = keep_bc;

@@ -49,6 +49,8 @@ typedef struct {
   int32_t batch_size;             /* pairs per reference batch (chromap.h:182: 500000); fixes the
                                      taskloop chunking that seeds multi-mapper sampling */
   int32_t max_read_length;        /* upper bound on read length in any batch (sizing), default 160 */
+  int32_t single_end;             /* 1 = single-end reads (chromap -1 only; MapSingleEndReads, chromap.h:218-634): cmx_batch.seq2/off2
+                                     are NULL, records are MappingWithoutBarcode (both alignment lengths 0). BED, non-split only */
 } cmx_params;
 
 void cmx_default_params(cmx_params *p);

@@ -445,3 +445,55 @@ def test_bed_text_on_device_equals_host(synth, bc):
             assert m.format_bed_gpu(recs, bcs, 16) == m.format_bed_bc(recs, bcs, 16)
         else:
             assert m.format_bed_gpu(recs) == m.format_bed(recs)
+
+
+SE_CASES = {
+    "se_default": dict(preset=""),
+    "se_chip": dict(preset="chip"),
+    "se_q0dedup_tn5": dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1),
+    "se_n3q0": dict(preset="", max_num_best_mappings=3, mapq_threshold=0),
+    "se_lowmem_q0": dict(preset="", low_memory_mode=1, mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SE_CASES))
+def test_single_end_records_equal_oracle_and_golden(synth, case):
+    """chromap -1 only (MapSingleEndReads): records == oracle, BED == the reference binary's, host and device post-processing."""
+    kw = dict(SE_CASES[case])
+    m = _mapper(synth, dict(kw, single_end=1))
+    s1, o1, _, _ = synth["pairs"]
+    recs, stats = m.map_batch(s1, o1, None, None)
+    orecs = orc.map_reads_se(_oparams(kw), synth["oidx"], synth["oref"], s1, o1)
+    assert len(recs) == len(orecs)
+    assert_same_records(recs, orecs)
+    assert stats["n_overflow_pairs"] == 0
+    want = gzip.open(os.path.join(synth["d"], case + ".bed.gz")).read()
+    assert m.format_bed(m.postprocess(recs)) == want
+    assert m.format_bed_gpu(m.postprocess_gpu(recs)) == want
+
+
+def test_single_end_heavy_repeats_through_all_tiers(tmp_path):
+    """Reads from repeat families (hundreds to thousands of hits): single-end through the CTA tiers == oracle."""
+    import subprocess
+    import sys
+    d = str(tmp_path)
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "gen_synth.py"),
+                           "--out", d, "--seed", "23", "--n-seq", "2", "--seq-len", "400000", "--n-pairs", "20000", "--repeat-copies", "60",
+                           "--repeat-len", "3000", "--fam-copies", "3000"])
+    names, seqs = read_fasta(os.path.join(d, "ref.fa"))
+    oref = orc.Reference(os.path.join(d, "ref.fa"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    kw = dict(preset="", mapq_threshold=0, max_num_best_mappings=2)
+    p = cb.make_params("", max_read_length=64, single_end=1, mapq_threshold=0, max_num_best_mappings=2)
+    m = cb.Mapper(p)
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    s1, o1, _, _ = load_pairs(d, "read1.fq", "read2.fq")
+    recs, stats = m.map_batch(s1, o1, None, None)
+    orecs = orc.map_reads_se(_oparams(kw), oidx, oref, s1, o1, n_threads=8)
+    assert stats["n_overflow_pairs"] == 0
+    tm = m.timing()
+    assert tm["tier_pairs"][1] > 0
+    assert len(recs) == len(orecs)
+    assert_same_records(recs, orecs)
