@@ -776,6 +776,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   if (in->bc_seq && ctx->params.split_alignment) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with split alignment");
   const bool se = ctx->params.single_end != 0;
   if (!in->seq1 || !in->off1 || (!se && (!in->seq2 || !in->off2))) return fail(ctx, CMX_ERR_INVALID, "cmx_batch: read pointers missing");
+  if (se && in->bc_seq) return fail(ctx, CMX_ERR_INVALID, "barcodes with single-end reads are not on the GPU path");
   if (n == 0) return CMX_OK;
   if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
   CU(cudaSetDevice(ctx->device));

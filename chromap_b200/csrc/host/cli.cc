@@ -46,16 +46,20 @@ static uint64_t BarcodeSeed(const std::string &s) {
   return seed;
 }
 
-static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names, SeqReader *rb = nullptr, uint32_t bc_len = 0) {
+static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names, SeqReader *rb = nullptr, uint32_t bc_len = 0,
+                          bool se = false) {
   std::string n, s, q;
   b->Clear();
   while (b->n < max_pairs) {
     bool a = r1.Next(&n, &s, &q);
     while (a && s.empty()) a = r1.Next(&n, &s, &q);
     if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); if (keep_names) b->names1.push_back(n); }
-    bool c = r2.Next(&n, &s, &q);
-    while (c && s.empty()) c = r2.Next(&n, &s, &q);
-    if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
+    bool c = a;  // single-end: no second file
+    if (!se) {
+      c = r2.Next(&n, &s, &q);
+      while (c && s.empty()) c = r2.Next(&n, &s, &q);
+      if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
+    }
     bool d = c;
     if (rb) {
       d = rb->Next(&n, &s, &q);
@@ -122,8 +126,9 @@ int main(int argc, char **argv) {
     else if (a == "--bc-probability-threshold") bc_prob = atof(val().c_str());
     else if (a == "--output-mappings-not-in-whitelist") out_nw = 1;
     else if (a == "--skip-barcode-check") skip_bc_check = true;
-    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "-n" || a == "--summary")
-      Die("chromap-b200: option " + a + " is not on the GPU path yet (paired-end BED and Hi-C pairs only); use the reference chromap for it");
+    else if (a == "-n" || a == "--max-num-best-mappings") p.max_num_best_mappings = atoi(val().c_str());
+    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "--summary")
+      Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
   (void)bed; (void)user_set_format;
@@ -156,7 +161,9 @@ int main(int argc, char **argv) {
   }
   if (ref_path.empty()) Die("No reference specified!");
   if (index_path.empty()) Die("No index specified!");
-  if (r1_path.empty() || r2_path.empty()) Die("chromap-b200 maps paired-end reads: give -1 and -2");
+  if (r1_path.empty()) Die("No read file specified!");
+  const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
+  if (se && (pairs || !bc_path.empty())) Die("chromap-b200: single-end mapping writes bulk BED only");
   if (out_path.empty()) Die("No output file specified!");
   Reference ref;
   if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);
@@ -164,6 +171,7 @@ int main(int argc, char **argv) {
   IndexFile ix;
   if (!ix.Load(index_path)) Die("Cannot load index file " + index_path);
   fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %zu.\n", ix.k, ix.w, ix.size, ix.occ.size());
+  p.single_end = se ? 1 : 0;
   int rc = cmx_create(&ctx, 0, &p);
   if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: unsupported parameter combination");
   if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
@@ -216,7 +224,7 @@ int main(int argc, char **argv) {
   SeqReader r1, r2, rb;
   if (sc && !rb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
   if (!r1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
-  if (!r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
+  if (!se && !r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
   // double-buffered batch loop: the loader thread parses batch b+1 while the GPU maps batch b (chromap.h:871-877)
   Batch cur, next;
   std::vector<cmx_pe_record> all, recs;
@@ -226,19 +234,19 @@ int main(int argc, char **argv) {
   std::vector<std::string> all_names;
   std::vector<uint64_t> all_bc, bc_keys;
   uint64_t n_bc_in = 0, n_bc_cor = 0;
-  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs, sc ? &rb : nullptr, bc_len);
+  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs, sc ? &rb : nullptr, bc_len, se);
   while (cur.n > 0) {
     cur.first_id = read_id;
-    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs, sc ? &rb : nullptr, bc_len); });
+    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs, sc ? &rb : nullptr, bc_len, se); });
     recs.resize((size_t)cur.n * p.max_num_best_mappings);
     cmx_batch in{};
-    in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = cur.s2.data(); in.off2 = cur.o2.data(); in.first_read_id = cur.first_id;
+    in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = se ? nullptr : cur.s2.data(); in.off2 = se ? nullptr : cur.o2.data(); in.first_read_id = cur.first_id;
     cmx_records out{};
     out.records = recs.data(); out.capacity = recs.size();
     if (sc) { in.bc_seq = cur.bc.data(); in.bc_qual = cur.bq.data(); in.bc_len = bc_len; bc_keys.resize(recs.size()); out.barcode_keys = bc_keys.data(); }
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
-    fprintf(stderr, "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
+    fprintf(stderr, se ? "Mapped %u reads in %.2fs.\n" : "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
     all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
     if (pairs) all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
     if (sc) { all_bc.insert(all_bc.end(), bc_keys.begin(), bc_keys.begin() + out.n_records); n_bc_in += out.n_barcodes_in_whitelist; n_bc_cor += out.n_barcodes_corrected; }
@@ -249,7 +257,8 @@ int main(int argc, char **argv) {
   }
   fprintf(stderr, "Mapped all reads in %.2fs.\n", Now() - t_map);
   fprintf(stderr, "Number of reads: %llu.\nNumber of mapped reads: %llu.\nNumber of uniquely mapped reads: %llu.\nNumber of candidates: %llu.\n",
-          (unsigned long long)(2 * n_pairs), (unsigned long long)(2 * n_mapped), (unsigned long long)(2 * n_unique), (unsigned long long)n_cand);
+          (unsigned long long)((se ? 1 : 2) * n_pairs), (unsigned long long)((se ? 1 : 2) * n_mapped), (unsigned long long)((se ? 1 : 2) * n_unique),
+          (unsigned long long)n_cand);
   uint64_t keep = 0;
   const double t_pp = Now();
   std::vector<const char *> names;

@@ -95,3 +95,18 @@ def test_cli_scatac_barcodes(tmp_path, golden_dir):
         if extra:
             for line in open(os.path.join(d, "sc_stats.txt")):
                 assert line.strip() in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_single_end(tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for case, extra in (("se_chip", ["--preset", "chip"]), ("se_q0dedup_tn5", ["-q", "0", "--remove-pcr-duplicates", "--Tn5-shift"]),
+                        ("se_n3q0", ["-n", "3", "-q", "0"])):
+        out = str(tmp_path / (case + ".bed"))
+        r = subprocess.run([cli, "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"), "-o", out] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
