@@ -24,6 +24,10 @@ class Params(C.Structure):
         "batch_size", "max_read_length", "single_end")]
 
 
+class Ingested(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("seq", C.c_void_p), ("off", C.c_void_p), ("qual", C.c_void_p), ("min_len", C.c_uint32), ("max_len", C.c_uint32)]
+
+
 class Batch(C.Structure):
     _fields_ = [("n_pairs", C.c_uint32), ("seq1", C.c_void_p), ("off1", C.c_void_p), ("seq2", C.c_void_p),
                 ("off2", C.c_void_p), ("first_read_id", C.c_uint32), ("on_device", C.c_int32),
@@ -107,6 +111,8 @@ def load_library():
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
     L.cmx_set_lanes.argtypes = [vp, i32]
+    L.cmx_fastq_cut.restype = u64; L.cmx_fastq_cut.argtypes = [vp, u64, u32, C.POINTER(u32)]
+    L.cmx_ingest_fastq.argtypes = [vp, i32, vp, u64, i32, vp, C.POINTER(Ingested)]
     _lib = L
     return L
 
@@ -245,6 +251,22 @@ class Mapper:
         if out_on_device:
             return out, stats
         return out[:r.n_records], stats
+
+    def fastq_cut(self, text, max_records):
+        """(bytes, records) of the first min(max_records, complete) 4-line records of `text` (bytes / uint8 array)."""
+        a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        n = C.c_uint32()
+        b = self.L.cmx_fastq_cut(a.ctypes.data, len(a), max_records, C.byref(n))
+        return b, n.value
+
+    def ingest_fastq(self, slot, text, want_qual=False, want_names=False):
+        """FASTQ text (whole records) -> packed reads on the device.  Returns (Ingested, name_spans | None)."""
+        a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        spans = np.zeros(2 * (len(a) // 8 + 1), dtype=np.uint32) if want_names else None
+        g = Ingested()
+        self._check(self.L.cmx_ingest_fastq(self.h, slot, a.ctypes.data, len(a), 1 if want_qual else 0, spans.ctypes.data if want_names else None, C.byref(g)),
+                    "cmx_ingest_fastq")
+        return g, (spans[:2 * g.n_reads].reshape(-1, 2) if want_names else None)
 
     def set_lanes(self, n):
         self._check(self.L.cmx_set_lanes(self.h, int(n)), "cmx_set_lanes")

@@ -21,6 +21,7 @@
 #include "index_build.cuh"
 #include "pipeline_kernels.cuh"
 #include "postprocess.cuh"
+#include "ingest.cuh"
 
 static_assert(sizeof(OutRecord) == sizeof(cmx_pe_record), "record layout");
 static_assert(sizeof(cmx_pe_record) == 24, "record size");
@@ -63,6 +64,12 @@ struct Lane {
   std::string err;
 };
 
+#define CMX_INGEST_SLOTS 6
+struct IngestSlot {  // buffers of one cmx_ingest_fastq stream (text in, packed reads out)
+  DevBuf text, nl, seq_start, qual_start, len, off, seq, qual, spans, tmp, stats, count;
+  cudaStream_t stream = nullptr;
+};
+
 struct cmx_ctx {
   int device = 0;
   cmx_params params;
@@ -98,6 +105,7 @@ struct cmx_ctx {
   // per-batch buffers
   DevBuf seq1, off1, seq2, off2, trace;
   Lane lanes[CMX_MAX_LANES];
+  IngestSlot ingest[CMX_INGEST_SLOTS];
   int n_lanes = CMX_MAX_LANES;  // lanes a multi-batch call is cut into (cmx_set_lanes; CMX_LANES overrides the default)
   int last_lanes_used = 0;
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
@@ -249,6 +257,10 @@ void cmx_destroy(cmx_ctx *ctx) {
     for (auto &a : L.aux) if (a) cudaStreamDestroy(a);
     if (L.ev_fork) cudaEventDestroy(L.ev_fork);
     for (auto &e : L.ev_join) if (e) cudaEventDestroy(e);
+  }
+  for (IngestSlot &g : ctx->ingest) {
+    for (DevBuf *b : {&g.text, &g.nl, &g.seq_start, &g.qual_start, &g.len, &g.off, &g.seq, &g.qual, &g.spans, &g.tmp, &g.stats, &g.count}) release(*b);
+    if (g.stream) cudaStreamDestroy(g.stream);
   }
   for (auto &e : ctx->ev) cudaEventDestroy(e);
   for (auto &e : ctx->ev_up) cudaEventDestroy(e);
@@ -906,6 +918,72 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = acc.tier_pairs[t];
   for (int r = 0; r < 8; ++r) tm.escalations[r] = acc.c.ovf_reason[r];
   if (acc.n_overflow) return fail(ctx, CMX_ERR_OVERFLOW, "%llu pair(s) exceeded the largest scratch tier", (unsigned long long)acc.n_overflow);
+  return CMX_OK;
+}
+
+// Host helper: bytes taken by the first min(max_records, complete) 4-line records of `text` (a record is complete when
+// its fourth newline is present).
+uint64_t cmx_fastq_cut(const char *text, uint64_t n_bytes, uint32_t max_records, uint32_t *n_records) {
+  uint64_t pos = 0, end_of_last = 0;
+  uint32_t lines = 0, recs = 0;
+  while (recs < max_records) {
+    const void *q = memchr(text + pos, '\n', n_bytes - pos);
+    if (!q) break;
+    pos = (uint64_t)((const char *)q - text) + 1;
+    if (++lines == 4) { lines = 0; ++recs; end_of_last = pos; }
+  }
+  if (n_records) *n_records = recs;
+  return end_of_last;
+}
+
+int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes, int want_qual, uint32_t *name_spans, cmx_ingested *out) {
+  if (!ctx || !out || slot < 0 || slot >= CMX_INGEST_SLOTS || (!text && n_bytes)) return CMX_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  if (n_bytes == 0) return CMX_OK;
+  if (n_bytes >= 0xFFFFFFF0ull) return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: chunk of 4 GiB or more");
+  if (text[n_bytes - 1] != '\n') return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: the chunk must end at a record boundary (cmx_fastq_cut)");
+  CU(cudaSetDevice(ctx->device));
+  IngestSlot &g = ctx->ingest[slot];
+  if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  cudaStream_t st = g.stream;
+  const u32 nb = (u32)n_bytes;
+  CU(ensure(g.text, n_bytes + 16)); CU(ensure(g.nl, ((size_t)nb + 16) * 4)); CU(ensure(g.count, 16)); CU(ensure(g.stats, sizeof(IngestStats)));
+  CU(cudaMemcpyAsync(g.text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
+  // newline positions: select the indices whose byte is '\n'
+  cub::CountingInputIterator<u32> idx(0);
+  cub::TransformInputIterator<u8, IsNewline, cub::CountingInputIterator<u32>> flags(idx, IsNewline{(const char *)g.text.p});
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, idx, flags, (u32 *)g.nl.p, (u32 *)g.count.p, (int)nb, st);
+  CU(ensure(g.tmp, tb));
+  CU(cub::DeviceSelect::Flagged(g.tmp.p, tb, idx, flags, (u32 *)g.nl.p, (u32 *)g.count.p, (int)nb, st));
+  u32 n_nl = 0;
+  CU(cudaMemcpyAsync(&n_nl, g.count.p, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_nl % 4 != 0) return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: %u lines is not a whole number of 4-line records", n_nl);
+  const u32 n = n_nl / 4;
+  CU(ensure(g.seq_start, (size_t)n * 4)); CU(ensure(g.qual_start, (size_t)n * 4)); CU(ensure(g.len, (size_t)(n + 1) * 4)); CU(ensure(g.off, (size_t)(n + 1) * 4));
+  if (name_spans) CU(ensure(g.spans, (size_t)n * 8));
+  IngestStats hs = {0, 0, 0, 0, 0xFFFFFFFFu, 0};
+  CU(cudaMemcpyAsync(g.stats.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync((u32 *)g.len.p + n, 0, 4, st));
+  ingest_record_kernel<<<(n + 255) / 256, 256, 0, st>>>((const char *)g.text.p, (const u32 *)g.nl.p, n, (u32 *)g.seq_start.p, (u32 *)g.qual_start.p, (u32 *)g.len.p,
+                                                        name_spans ? (u32 *)g.spans.p : nullptr, (IngestStats *)g.stats.p);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (const u32 *)g.len.p, (u32 *)g.off.p, (int)n + 1, st);
+  CU(ensure(g.tmp, tb));
+  CU(cub::DeviceScan::ExclusiveSum(g.tmp.p, tb, (const u32 *)g.len.p, (u32 *)g.off.p, (int)n + 1, st));
+  CU(ensure(g.seq, n_bytes / 2 + 64));  // bases are less than half of a 4-line record
+  if (want_qual) CU(ensure(g.qual, n_bytes / 2 + 64));
+  ingest_pack_kernel<<<(unsigned)(((u64)n * 32 + 255) / 256), 256, 0, st>>>((const char *)g.text.p, (const u32 *)g.seq_start.p, (const u32 *)g.qual_start.p,
+                                                                           (const u32 *)g.off.p, n, (char *)g.seq.p, want_qual ? (char *)g.qual.p : nullptr);
+  CU(cudaMemcpyAsync(&hs, g.stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  if (name_spans) CU(cudaMemcpyAsync(name_spans, g.spans.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (hs.bad_header || hs.bad_plus) return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: not 4-line FASTQ (%u headers without '@', %u separator lines without '+')", hs.bad_header, hs.bad_plus);
+  if (hs.empty_reads) return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: %u empty reads (the reference skips them per file; use the host reader)", hs.empty_reads);
+  if (hs.qual_mismatch) return fail(ctx, CMX_ERR_INVALID, "cmx_ingest_fastq: %u records whose quality and sequence lengths differ", hs.qual_mismatch);
+  out->n_reads = n; out->seq = (const char *)g.seq.p; out->off = (const uint32_t *)g.off.p; out->qual = want_qual ? (const char *)g.qual.p : nullptr;
+  out->min_len = n ? hs.min_len : 0; out->max_len = hs.max_len;
   return CMX_OK;
 }
 

@@ -220,6 +220,23 @@ typedef struct {
 } cmx_timing;
 int cmx_last_batch_timing(cmx_ctx *ctx, cmx_timing *out);
 
+/* FASTQ text -> packed reads on the device (the loader's side of the path: SequenceBatch::LoadBatch + kseq_read,
+ * sequence_batch.cc:9-60, kseq.h:177-222, for 4-line FASTQ).  `text` (host) must hold whole records: cmx_fastq_cut returns
+ * how many bytes the first min(max_records, complete) records take.  The result lives in the context's ingest buffers of
+ * `slot` (0..5, independent sets so that three files can be double-buffered) until the next call on that slot, in the layout
+ * cmx_batch takes with on_device = 1.  name_spans (optional, host, 2 x n_reads u32): start and length of each read name
+ * in `text`.  Anything that is not plain 4-line FASTQ (multi-line records, FASTA, empty reads) returns CMX_ERR_INVALID:
+ * the caller falls back to its own reader. */
+typedef struct {
+  uint32_t n_reads;
+  const char *seq;      /* device: bases of all reads, concatenated */
+  const uint32_t *off;  /* device: n_reads + 1 offsets into seq */
+  const char *qual;     /* device: qualities in the same layout (NULL unless want_qual) */
+  uint32_t min_len, max_len;
+} cmx_ingested;
+uint64_t cmx_fastq_cut(const char *text, uint64_t n_bytes, uint32_t max_records, uint32_t *n_records);
+int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes, int want_qual, uint32_t *name_spans, cmx_ingested *out);
+
 /* Concurrency of one cmx_map_batch_pe call (no counterpart in the reference, whose knob is -t): a call that carries
  * several whole reference batches is cut into up to n_lanes (1..4, default 4) groups of batches that run the whole
  * pipeline on their own streams, so the latency-bound kernels of one group overlap the issue-bound kernels of

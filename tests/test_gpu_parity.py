@@ -8,7 +8,9 @@ import pytest
 
 import chromap_b200 as cb
 from oracle import oracle_py as orc
-from tests.util import load_pairs, read_fasta
+import ctypes as C
+
+from tests.util import load_pairs, read_fasta, read_fastq_records
 
 pytestmark = pytest.mark.gpu
 
@@ -497,3 +499,48 @@ def test_single_end_heavy_repeats_through_all_tiers(tmp_path):
     assert tm["tier_pairs"][1] > 0
     assert len(recs) == len(orecs)
     assert_same_records(recs, orecs)
+
+
+def _d2h(ptr, nbytes):
+    rt = C.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    out = np.empty(nbytes, dtype=np.uint8)
+    assert rt.cudaMemcpy(out.ctypes.data, ptr, nbytes, 2) == 0
+    return out
+
+
+def test_fastq_ingest_on_device_equals_host_reader(synth):
+    """cmx_fastq_cut + cmx_ingest_fastq: packed bases / qualities / name spans == the host FASTQ reader; mapping the
+    device-resident batch gives the same records as mapping the host batch."""
+    m = _mapper(synth, CASES["default"])
+    d = synth["d"]
+    t1 = gzip.open(os.path.join(d, "read1.fq.gz")).read()
+    t2 = gzip.open(os.path.join(d, "read2.fq.gz")).read()
+    s1, o1, s2, o2 = synth["pairs"]
+    n = len(o1) - 1
+    # record-boundary cuts
+    b, k = m.fastq_cut(t1, 1000)
+    assert k == 1000 and t1[:b].count(b"\n") == 4000 and t1[b - 1:b] == b"\n"
+    b_all, k_all = m.fastq_cut(t1 + b"@partial\nACGT\n+", 10 ** 9)
+    assert k_all == n and b_all == len(t1)
+    g1, spans = m.ingest_fastq(0, t1, want_qual=True, want_names=True)
+    g2, _ = m.ingest_fastq(1, t2)
+    assert g1.n_reads == n and g2.n_reads == n
+    off = _d2h(g1.off, 4 * (n + 1)).view(np.uint32)
+    assert np.array_equal(off, o1)
+    assert np.array_equal(_d2h(g1.seq, int(off[-1])), s1)
+    recs = read_fastq_records(os.path.join(d, "read1.fq.gz"))
+    assert _d2h(g1.qual, int(off[-1])).tobytes() == b"".join(q for _, _, q in recs)
+    names = [t1[a:a + l] for a, l in spans]
+    assert names == [nm for nm, _, _ in recs]
+    assert g1.min_len == min(len(s) for _, s, _ in recs) and g1.max_len == max(len(s) for _, s, _ in recs)
+    want, _ = m.map_batch(s1, o1, s2, o2)
+    got, _ = m.map_batch(g1.seq, g1.off, g2.seq, g2.off, on_device=True, n_pairs=n)
+    assert_same_records(got, want)
+    # CRLF line ends and a final chunk are handled like kseq does; anything else is refused, not guessed at
+    crlf = t1[:b].replace(b"\n", b"\r\n")
+    gc, _ = m.ingest_fastq(2, crlf)
+    assert gc.n_reads == 1000 and np.array_equal(_d2h(gc.off, 4 * 1001).view(np.uint32), o1[:1001])
+    for bad in (b">r\nACGT\n+\nIIII\n", b"@r\nACGT\nIIII\nIIII\n", b"@r\n\n+\n\n", b"@r\nACGT\n+\nIII\n"):
+        with pytest.raises(cb.CmxError):
+            m.ingest_fastq(2, bad)

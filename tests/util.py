@@ -38,6 +38,16 @@ def read_fastq(path):
     return seqs
 
 
+def read_fastq_records(path):
+    """[(name, sequence, quality)] of a 4-line FASTQ; name = header up to the first whitespace (kseq)."""
+    out = []
+    with _open(path) as f:
+        lines = [l.rstrip(b"\r\n") for l in f]
+    for i in range(0, len(lines) - 3, 4):
+        out.append((lines[i][1:].split()[0] if lines[i][1:].split() else b"", lines[i + 1], lines[i + 3]))
+    return out
+
+
 def pack(reads):
     off = np.zeros(len(reads) + 1, dtype=np.uint32)
     off[1:] = np.cumsum([len(r) for r in reads])
