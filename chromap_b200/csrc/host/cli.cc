@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "../../../include/chromap_b200.h"
+#include <zlib.h>
+
 #include "seqio.h"
 
 using cmxhost::IndexFile;
@@ -31,8 +33,69 @@ struct Batch {
   std::vector<std::string> names1;  // read-1 names, kept for pairs output only
   std::string bc, bq;               // cell barcodes + qualities, bc_len bytes per pair (scATAC)
   uint32_t n = 0, first_id = 0;
-  void Clear() { s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); bc.clear(); bq.clear(); n = 0; }
+  bool dev = false;      // reads were packed on the device (cmx_ingest_fastq): dev_in holds device pointers
+  cmx_batch dev_in{};
+  void Clear() { dev = false; s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); bc.clear(); bq.clear(); n = 0; }
 };
+
+// Raw text of one read file for the device-side FASTQ parser: gzread() (plain or gzip) into a growing buffer; whole
+// 4-line records are cut off its front with cmx_fastq_cut, the rest stays for the next batch.
+struct RawFile {
+  gzFile f = nullptr;
+  std::vector<char> buf;
+  size_t have = 0;
+  bool eof = false;
+  bool Open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); have = 0; eof = false; return f != nullptr; }
+  void Close() { if (f) gzclose(f); f = nullptr; }
+  // bytes of up to max_records whole records now in the buffer (reading more as needed); *n = their number
+  uint64_t Fill(uint32_t max_records, uint32_t *n) {
+    for (;;) {
+      const uint64_t cut = cmx_fastq_cut(buf.data(), have, max_records, n);
+      if (*n == max_records || eof) return cut;
+      const size_t want = 64u << 20;
+      if (buf.size() < have + want + 1) buf.resize(have + want + 1);
+      const int got = gzread(f, buf.data() + have, (unsigned)want);
+      if (got <= 0) {
+        eof = true;
+        if (have > 0 && buf[have - 1] != '\n') buf[have++] = '\n';  // a last line without its newline
+      } else have += (size_t)got;
+    }
+  }
+  void Consume(uint64_t bytes) { memmove(buf.data(), buf.data() + bytes, have - bytes); have -= bytes; }
+};
+
+// One batch through the device-side parser.  Returns false if a file is not plain 4-line FASTQ (the caller then uses the
+// host reader); dies on real input errors, like LoadBatch.
+static bool LoadBatchGpu(cmx_ctx *ctx, RawFile *f1, RawFile *f2, RawFile *fb, int parity, uint32_t max_pairs, Batch *b, bool keep_names, uint32_t bc_len) {
+  b->Clear();
+  uint32_t n1 = 0, n2 = 0, nb = 0;
+  const uint64_t c1 = f1->Fill(max_pairs, &n1);
+  const uint64_t c2 = f2 ? f2->Fill(max_pairs, &n2) : 0;
+  const uint64_t cb = fb ? fb->Fill(max_pairs, &nb) : 0;
+  if ((f2 && n2 != n1) || (fb && nb != n1)) Die("Numbers of reads and barcodes don't match!");
+  if (n1 == 0) {
+    if (f1->have || (f2 && f2->have) || (fb && fb->have)) return false;  // trailing bytes that are no whole record: not 4-line FASTQ
+    return true;
+  }
+  cmx_ingested g1{}, g2{}, gb{};
+  std::vector<uint32_t> spans;
+  if (keep_names) spans.resize(2 * (size_t)n1);
+  if (cmx_ingest_fastq(ctx, parity * 3 + 0, f1->buf.data(), c1, 0, keep_names ? spans.data() : nullptr, &g1)) return false;
+  if (f2 && cmx_ingest_fastq(ctx, parity * 3 + 1, f2->buf.data(), c2, 0, nullptr, &g2)) return false;
+  if (fb) {
+    if (cmx_ingest_fastq(ctx, parity * 3 + 2, fb->buf.data(), cb, 1, nullptr, &gb)) return false;
+    if (gb.min_len != bc_len || gb.max_len != bc_len) Die("ERROR: barcode lengths are not equal in the sample!");
+  }
+  if (keep_names) for (uint32_t i = 0; i < n1; ++i) b->names1.emplace_back(f1->buf.data() + spans[2 * i], spans[2 * i + 1]);
+  f1->Consume(c1);
+  if (f2) f2->Consume(c2);
+  if (fb) fb->Consume(cb);
+  b->n = n1; b->dev = true;
+  b->dev_in.n_pairs = n1; b->dev_in.seq1 = g1.seq; b->dev_in.off1 = g1.off; b->dev_in.on_device = 1;
+  if (f2) { b->dev_in.seq2 = g2.seq; b->dev_in.off2 = g2.off; }
+  if (fb) { b->dev_in.bc_seq = gb.seq; b->dev_in.bc_qual = gb.qual; b->dev_in.bc_len = bc_len; }
+  return true;
+}
 
 // LoadPairedEndReadsWithBarcodes (chromap.cc:93-174, non-barcode): empty reads are skipped per file
 // (sequence_batch.cc:28-31), the two files must run out together.
@@ -82,7 +145,7 @@ int main(int argc, char **argv) {
   cmx_default_params(&p);
   std::string preset, ref_path, index_path, r1_path, r2_path, out_path, bc_path, wl_path;
   int bc_err = 1, out_nw = 0;
-  bool skip_bc_check = false;
+  bool skip_bc_check = false, host_reader = false;
   double bc_prob = 0.9;
   bool build_index = false, bed = false, user_set_format = false;
   int k = 17, w = 7, threads = 1;
@@ -126,6 +189,7 @@ int main(int argc, char **argv) {
     else if (a == "--bc-probability-threshold") bc_prob = atof(val().c_str());
     else if (a == "--output-mappings-not-in-whitelist") out_nw = 1;
     else if (a == "--skip-barcode-check") skip_bc_check = true;
+    else if (a == "--host-reader") host_reader = true;  // parse FASTQ on the host (multi-line records, FASTA reads)
     else if (a == "-n" || a == "--max-num-best-mappings") p.max_num_best_mappings = atoi(val().c_str());
     else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
@@ -221,12 +285,37 @@ int main(int argc, char **argv) {
       if (cmx_upload_barcode_whitelist(ctx, keys.data(), counts.data(), keys.size(), num_sample, bc_len, bc_err, bc_prob, out_nw)) Die(cmx_last_error(ctx));
     }
   }
+  // double-buffered batch loop: the loader thread prepares batch b+1 while the GPU maps batch b (chromap.h:871-877).
+  // Reads are parsed on the device (cmx_ingest_fastq) when the files are plain 4-line FASTQ, else by the host reader.
   SeqReader r1, r2, rb;
-  if (sc && !rb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
-  if (!r1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
-  if (!se && !r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
-  // double-buffered batch loop: the loader thread parses batch b+1 while the GPU maps batch b (chromap.h:871-877)
+  RawFile g1, g2, gb;
   Batch cur, next;
+  bool gpu_reader = !host_reader;
+  auto open_all = [&](bool raw) {
+    if (raw) {
+      if (!g1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
+      if (!se && !g2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
+      if (sc && !gb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
+    } else {
+      if (sc && !rb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
+      if (!r1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
+      if (!se && !r2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
+    }
+  };
+  int parity = 0;
+  auto load = [&](Batch *b, int par) {
+    if (gpu_reader) {
+      if (!LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, par, (uint32_t)p.batch_size, b, pairs, bc_len))
+        Die(std::string("chromap-b200: the read files are not plain 4-line FASTQ (") + cmx_last_error(ctx) + "); rerun with --host-reader");
+    } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs, sc ? &rb : nullptr, bc_len, se);
+  };
+  open_all(gpu_reader);
+  if (gpu_reader && !LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, parity, (uint32_t)p.batch_size, &cur, pairs, bc_len)) {
+    fprintf(stderr, "Read files are not plain 4-line FASTQ (%s): using the host reader.\n", cmx_last_error(ctx));
+    g1.Close(); g2.Close(); gb.Close();
+    gpu_reader = false;
+    open_all(false);
+  }
   std::vector<cmx_pe_record> all, recs;
   uint64_t n_pairs = 0, n_mapped = 0, n_unique = 0, n_cand = 0;
   const double t_map = Now();
@@ -234,16 +323,22 @@ int main(int argc, char **argv) {
   std::vector<std::string> all_names;
   std::vector<uint64_t> all_bc, bc_keys;
   uint64_t n_bc_in = 0, n_bc_cor = 0;
-  LoadBatch(r1, r2, (uint32_t)p.batch_size, &cur, pairs, sc ? &rb : nullptr, bc_len, se);
+  if (!gpu_reader) load(&cur, parity);
   while (cur.n > 0) {
     cur.first_id = read_id;
-    std::thread loader([&]() { LoadBatch(r1, r2, (uint32_t)p.batch_size, &next, pairs, sc ? &rb : nullptr, bc_len, se); });
+    parity ^= 1;
+    std::thread loader([&]() { load(&next, parity); });
     recs.resize((size_t)cur.n * p.max_num_best_mappings);
     cmx_batch in{};
-    in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = se ? nullptr : cur.s2.data(); in.off2 = se ? nullptr : cur.o2.data(); in.first_read_id = cur.first_id;
+    if (cur.dev) in = cur.dev_in;
+    else {
+      in.n_pairs = cur.n; in.seq1 = cur.s1.data(); in.off1 = cur.o1.data(); in.seq2 = se ? nullptr : cur.s2.data(); in.off2 = se ? nullptr : cur.o2.data();
+      if (sc) { in.bc_seq = cur.bc.data(); in.bc_qual = cur.bq.data(); in.bc_len = bc_len; }
+    }
+    in.first_read_id = cur.first_id;
     cmx_records out{};
     out.records = recs.data(); out.capacity = recs.size();
-    if (sc) { in.bc_seq = cur.bc.data(); in.bc_qual = cur.bq.data(); in.bc_len = bc_len; bc_keys.resize(recs.size()); out.barcode_keys = bc_keys.data(); }
+    if (sc) { bc_keys.resize(recs.size()); out.barcode_keys = bc_keys.data(); }
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, se ? "Mapped %u reads in %.2fs.\n" : "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);

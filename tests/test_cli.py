@@ -110,3 +110,28 @@ def test_cli_single_end(tmp_path, golden_dir):
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+
+
+@pytest.mark.gpu
+def test_cli_falls_back_to_the_host_reader_for_fasta_reads(tmp_path, golden_dir):
+    """Reads given as FASTA (kseq accepts them) are not 4-line FASTQ: the device-side parser refuses them and the CLI
+    switches to its host reader; --host-reader forces that path.  Same BED either way."""
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for which in ("read1", "read2"):
+        lines = gzip.open(os.path.join(d, which + ".fq.gz")).read().split(b"\n")
+        with open(str(tmp_path / (which + ".fa")), "wb") as f:
+            for i in range(0, len(lines) - 3, 4):
+                f.write(b">" + lines[i][1:] + b"\n" + lines[i + 1] + b"\n")
+    want = gzip.open(os.path.join(d, "chip.bed.gz")).read()
+    for reads, extra, note in (((str(tmp_path / "read1.fa"), str(tmp_path / "read2.fa")), [], "using the host reader"),
+                               ((os.path.join(d, "read1.fq.gz"), os.path.join(d, "read2.fq.gz")), ["--host-reader"], None)):
+        out = str(tmp_path / "out.bed")
+        r = subprocess.run([cli, "--preset", "chip", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", reads[0], "-2", reads[1], "-o", out] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == want
+        if note:
+            assert note in r.stderr
