@@ -316,25 +316,33 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   if (!ctx || !flags || !keys || !vals || (n_occ && !occ)) return CMX_ERR_INVALID;
   if (k < 2 || k > 28 || w < 1 || w > CMX_W_MAX) return fail(ctx, CMX_ERR_INVALID, "unsupported k=%d w=%d", k, w);
   CU(cudaSetDevice(ctx->device));
-  // occupied buckets (khash.h:165: 2 flag bits per bucket: 10 empty, 01 deleted, 00 occupied)
-  std::vector<ulonglong2> kv;
-  kv.reserve(n_buckets / 2);
-  for (u64 i = 0; i < n_buckets; ++i)
-    if (((flags[i >> 4] >> ((i & 0xfU) << 1)) & 3) == 0) kv.push_back(make_ulonglong2(keys[i], vals[i]));
-  ctx->n_keys = kv.size();
-  int rc = alloc_table(ctx, kv.size());
+  // occupied buckets (khash.h:165: 2 flag bits per bucket: 10 empty, 01 deleted, 00 occupied) are counted and inserted on
+  // the device, straight from the reference's arrays: no host-side compaction pass over a billion buckets
+  const u64 nbk = n_buckets;
+  const size_t nfw = (size_t)((nbk + 15) / 16);
+  u32 *d_flags = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  u64 *d_k = nullptr, *d_v = nullptr;
+  CU(cudaMalloc(&d_flags, nfw * 4)); CU(cudaMalloc(&d_cnt, 8));
+  CU(cudaMemcpy(d_flags, flags, nfw * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemset(d_cnt, 0, 8));
+  khash_count_kernel<<<(unsigned)((nfw + 255) / 256), 256>>>(d_flags, nbk, d_cnt);
+  unsigned long long n_keys = 0;
+  CU(cudaMemcpy(&n_keys, d_cnt, 8, cudaMemcpyDeviceToHost));
+  ctx->n_keys = n_keys;
+  int rc = alloc_table(ctx, n_keys);
   if (rc) return rc;
-  ulonglong2 *d_kv = nullptr;
-  const size_t CH = 1u << 24;
-  CU(cudaMalloc(&d_kv, std::min(kv.size(), CH) * sizeof(ulonglong2) + 16));
-  for (size_t o = 0; o < kv.size(); o += CH) {
-    const size_t n = std::min(CH, kv.size() - o);
-    CU(cudaMemcpy(d_kv, kv.data() + o, n * sizeof(ulonglong2), cudaMemcpyHostToDevice));
-    table_insert_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_kv, n, ctx->slots, ctx->n_slots - 1, table_shift(ctx->n_slots));
+  const size_t CH = 1u << 25;  // buckets per chunk: 2 x 256 MB in flight
+  CU(cudaMalloc(&d_k, std::min<size_t>(nbk, CH) * 8 + 16)); CU(cudaMalloc(&d_v, std::min<size_t>(nbk, CH) * 8 + 16));
+  for (u64 b0 = 0; b0 < nbk; b0 += CH) {
+    const u64 n = std::min<u64>(CH, nbk - b0);
+    CU(cudaMemcpy(d_k, keys + b0, n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_v, vals + b0, n * 8, cudaMemcpyHostToDevice));
+    khash_insert_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_flags, d_k, d_v, b0, n, ctx->slots, ctx->n_slots - 1, table_shift(ctx->n_slots));
     CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
   }
-  cudaFree(d_kv);
+  CU(cudaDeviceSynchronize());
+  cudaFree(d_flags); cudaFree(d_cnt); cudaFree(d_k); cudaFree(d_v);
   cudaFree(ctx->occ); ctx->occ = nullptr;
   CU(cudaMalloc(&ctx->occ, (size_t)std::max<u32>(n_occ, 1) * sizeof(u64)));
   if (n_occ) CU(cudaMemcpy(ctx->occ, occ, (size_t)n_occ * sizeof(u64), cudaMemcpyHostToDevice));

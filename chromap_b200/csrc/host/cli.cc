@@ -69,9 +69,13 @@ struct RawFile {
 static bool LoadBatchGpu(cmx_ctx *ctx, RawFile *f1, RawFile *f2, RawFile *fb, int parity, uint32_t max_pairs, Batch *b, bool keep_names, uint32_t bc_len) {
   b->Clear();
   uint32_t n1 = 0, n2 = 0, nb = 0;
-  const uint64_t c1 = f1->Fill(max_pairs, &n1);
-  const uint64_t c2 = f2 ? f2->Fill(max_pairs, &n2) : 0;
-  const uint64_t cb = fb ? fb->Fill(max_pairs, &nb) : 0;
+  uint64_t c1 = 0, c2 = 0, cb = 0;  // the files are read (and inflated) side by side
+  std::thread t2, tb;
+  if (f2) t2 = std::thread([&]() { c2 = f2->Fill(max_pairs, &n2); });
+  if (fb) tb = std::thread([&]() { cb = fb->Fill(max_pairs, &nb); });
+  c1 = f1->Fill(max_pairs, &n1);
+  if (f2) t2.join();
+  if (fb) tb.join();
   if ((f2 && n2 != n1) || (fb && nb != n1)) Die("Numbers of reads and barcodes don't match!");
   if (n1 == 0) {
     if (f1->have || (f2 && f2->have) || (fb && fb->have)) return false;  // trailing bytes that are no whole record: not 4-line FASTQ

@@ -1,5 +1,7 @@
 #include "seqio.h"
 
+#include <cstring>
+
 #include <cctype>
 #include <cstdio>
 
@@ -45,8 +47,8 @@ bool SeqReader::GetLine(std::string *s) {
       end_ = (size_t)n;
     }
     any = true;
-    size_t i = pos_;
-    while (i < end_ && buf_[i] != '\n') ++i;
+    const void *nlp = memchr(buf_.data() + pos_, '\n', end_ - pos_);
+    const size_t i = nlp ? (size_t)((const unsigned char *)nlp - buf_.data()) : end_;
     s->append((const char *)buf_.data() + pos_, i - pos_);
     if (i < end_) { pos_ = i + 1; break; }
     pos_ = end_;

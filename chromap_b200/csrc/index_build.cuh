@@ -23,6 +23,33 @@ __global__ void table_insert_kernel(const ulonglong2 *kv, size_t n, ulonglong2 *
   }
 }
 
+// khash arrays as the reference stores them (khash.h:165: 2 flag bits per bucket, 00 = occupied): count / insert the
+// occupied buckets of [b0, b0 + n) without compacting them on the host first.
+__global__ void khash_count_kernel(const u32 *flags, u64 n_buckets, unsigned long long *count) {
+  const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // one flag word = 16 buckets
+  const u64 nw = (n_buckets + 15) / 16;
+  u32 c = 0;
+  if (w < nw) {
+    const u32 f = flags[w];
+    for (u32 j = 0; j < 16; ++j) if (w * 16 + j < n_buckets && ((f >> (2 * j)) & 3u) == 0u) ++c;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+__global__ void khash_insert_kernel(const u32 *flags, const u64 *keys, const u64 *vals, u64 b0, u64 n, ulonglong2 *slots, u64 mask, int shift) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 b = b0 + i;
+  if (((flags[b >> 4] >> ((b & 0xfu) << 1)) & 3u) != 0u) return;
+  const u64 key = keys[i], val = vals[i];
+  u64 s = ((key >> 1) * 0x9E3779B97F4A7C15ull) >> shift;
+  for (;;) {
+    const u64 old = atomicCAS((unsigned long long *)&slots[s].x, (unsigned long long)CMX_EMPTY_KEY, (unsigned long long)key);
+    if (old == CMX_EMPTY_KEY) { slots[s].y = val; return; }
+    s = (s + 1) & mask;
+  }
+}
+
 struct IndexBuildResult {
   ulonglong2 *slots = nullptr;
   u64 n_slots = 0;
