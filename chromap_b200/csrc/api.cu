@@ -958,8 +958,10 @@ int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes,
   CU(ensure(g.text, n_bytes + 16)); CU(ensure(g.nl, ((size_t)nb + 16) * 4)); CU(ensure(g.count, 16)); CU(ensure(g.stats, sizeof(IngestStats)));
   CU(cudaMemcpyAsync(g.text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
   // newline positions: select the indices whose byte is '\n'
-  cub::CountingInputIterator<u32> idx(0);
-  cub::TransformInputIterator<u8, IsNewline, cub::CountingInputIterator<u32>> flags(idx, IsNewline{(const char *)g.text.p});
+  thrust::counting_iterator<u32> idx(0);
+  CU(ensure(g.qual_start, (size_t)nb));  // newline flags live here until the per-record arrays are sized (same buffer, reused)
+  u8 *flags = (u8 *)g.qual_start.p;
+  newline_flag_kernel<<<(nb + 255) / 256, 256, 0, st>>>((const char *)g.text.p, nb, flags);
   size_t tb = 0;
   cub::DeviceSelect::Flagged(nullptr, tb, idx, flags, (u32 *)g.nl.p, (u32 *)g.count.p, (int)nb, st);
   CU(ensure(g.tmp, tb));
@@ -1129,13 +1131,13 @@ int cmx_stage_banded_align(cmx_ctx *ctx, int e, int read_len, const char *patter
 }
 
 __global__ void __launch_bounds__(CTA_NT) stage_cta_sort_kernel(u64 *keys, u8 *tags, int n, int sm_cap, int with_tags) {
-  extern __shared__ u64 smk[];
-  u8 *smt = (u8 *)(smk + sm_cap);
+  extern __shared__ u64 smk_stage[];
+  u8 *smt = (u8 *)(smk_stage + sm_cap);
   if (with_tags) {
     auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };  // candidate order
-    cta_sort_pairs<u8>(keys, tags, n, ~0ull, (u8)0, cless, smk, smt, sm_cap);
+    cta_sort_pairs<u8>(keys, tags, n, ~0ull, (u8)0, cless, smk_stage, smt, sm_cap);
   } else {
-    cta_sort_keys(keys, n, smk, sm_cap);
+    cta_sort_keys(keys, n, smk_stage, sm_cap);
   }
 }
 

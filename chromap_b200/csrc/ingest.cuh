@@ -6,15 +6,14 @@
 #pragma once
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "device_common.cuh"
 
-struct IsNewline {
-  const char *text;
-  __host__ __device__ __forceinline__ u8 operator()(u32 i) const { return text[i] == '\n' ? 1 : 0; }
-};
+__global__ void newline_flag_kernel(const char *text, u32 n, u8 *flag) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = text[i] == '\n' ? 1 : 0;
+}
 
 struct IngestStats {  // device-side summary of one chunk
   u32 bad_header, bad_plus, empty_reads, qual_mismatch, min_len, max_len;
