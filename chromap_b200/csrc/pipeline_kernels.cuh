@@ -1975,39 +1975,52 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
     if (tid == 0 && ((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) s_flag[2] = 1;
     __syncthreads();
   }
-  if (tid != 0) return;
-  // merges + PE filter: linear passes, thread 0
-  for (int mate = 0; mate < 2; ++mate)
-    for (int s = 0; s < 2; ++s) {
-      ReadMeta &me = rm[mate];
-      if (me.n_aug[s] > 0) {
-        const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
-                                  CP(mate, 1, s), CC(mate, 1, s), c.cc);
-        if (n > c.cc) { pm.status = ST_OVERFLOW; return; }
-        me.n_cand[s] = n;
-      }
+  // merges, buffer copy and paired-end filter: the four (mate, strand) merges and the two filter directions touch
+  // disjoint lists, so each runs on its own warp's lane 0; the copy is done by everyone
+  const int wid = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_flag[3] = 0;
+  __syncthreads();
+  if (lane == 0 && wid < 4) {
+    const int mate = wid >> 1, s = wid & 1;
+    ReadMeta &me = rm[mate];
+    if (me.n_aug[s] > 0) {
+      const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
+                                CP(mate, 1, s), CC(mate, 1, s), c.cc);
+      if (n > c.cc) s_flag[3] = 1; else me.n_cand[s] = n;
     }
-  pm.sup = s_flag[2];
-  int nc1 = rm[0].n_cand[0] + rm[0].n_cand[1], nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
-  if (nc1 > 0 && nc2 > 0) {
-    for (int mate = 0; mate < 2; ++mate)
-      for (int s = 0; s < 2; ++s) {
-        const int n = rm[mate].n_cand[s];
-        u64 *src = CP(mate, 0, s), *dst = CP(mate, 1, s);
-        u8 *srcc = CC(mate, 0, s), *dstc = CC(mate, 1, s);
-        for (int i = 0; i < n; ++i) { dst[i] = src[i]; dstc[i] = srcc[i]; }
-        rm[mate].n_buf[s] = n;
-      }
-    int a, b;
-    pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), rm[0].n_buf[0], CP(1, 1, 1), CC(1, 1, 1), rm[1].n_buf[1],
-                  CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
-    rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
-    pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), rm[0].n_buf[1], CP(1, 1, 0), CC(1, 1, 0), rm[1].n_buf[0],
-                  CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
-    rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
-    nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
-    nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
   }
+  __syncthreads();
+  if (s_flag[3]) { if (tid == 0) pm.status = ST_OVERFLOW; return; }
+  const int nq[4] = {rm[0].n_cand[0], rm[0].n_cand[1], rm[1].n_cand[0], rm[1].n_cand[1]};
+  int nc1 = nq[0] + nq[1], nc2 = nq[2] + nq[3];
+  const bool both = nc1 > 0 && nc2 > 0;
+  if (both) {
+    for (int q = 0; q < 4; ++q) {
+      const u64 *src = CP(q >> 1, 0, q & 1);
+      const u8 *srcc = CC(q >> 1, 0, q & 1);
+      u64 *dst = CP(q >> 1, 1, q & 1);
+      u8 *dstc = CC(q >> 1, 1, q & 1);
+      for (int i = tid; i < nq[q]; i += CTA_NT) { dst[i] = src[i]; dstc[i] = srcc[i]; }
+    }
+  }
+  __syncthreads();
+  if (both && lane == 0 && wid < 2) {
+    int a, b;
+    if (wid == 0) {
+      pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), nq[0], CP(1, 1, 1), CC(1, 1, 1), nq[3], CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
+      rm[0].n_buf[0] = nq[0]; rm[1].n_buf[1] = nq[3];
+      rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
+    } else {
+      pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), nq[1], CP(1, 1, 0), CC(1, 1, 0), nq[2], CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
+      rm[0].n_buf[1] = nq[1]; rm[1].n_buf[0] = nq[2];
+      rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
+    }
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  pm.sup = s_flag[2];
+  nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
+  nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
   if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
   atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
 }
