@@ -544,3 +544,47 @@ def test_fastq_ingest_on_device_equals_host_reader(synth):
     for bad in (b">r\nACGT\n+\nIIII\n", b"@r\nACGT\nIIII\nIIII\n", b"@r\n\n+\n\n", b"@r\nACGT\n+\nIII\n"):
         with pytest.raises(cb.CmxError):
             m.ingest_fastq(2, bad)
+
+
+def test_scatac_large_whitelist_equals_oracle(golden_dir, tmp_path):
+    """A 300 000-entry whitelist (BASELINE config 4 uses 737 k): device hash table and 1-substitution correction == oracle."""
+    d = os.path.join(golden_dir, "synth_sc")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    n, bc_len = len(o1) - 1, 16
+    rng = np.random.default_rng(99)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    wl_codes = np.unique(rng.integers(0, 1 << 32, 300000, dtype=np.uint64))
+    wl_seq = acgt[(wl_codes[:, None] >> (2 * np.arange(bc_len - 1, -1, -1, dtype=np.uint64))[None, :]) & np.uint64(3)]
+    wl_path = str(tmp_path / "wl.txt")
+    with open(wl_path, "wb") as f:
+        f.write(b"\n".join(r.tobytes() for r in wl_seq) + b"\n")
+    cells = wl_seq[rng.integers(0, len(wl_seq), 800)]
+    bcs = cells[rng.integers(0, len(cells), n)].copy()
+    sub = rng.random(n) < 0.08
+    pos = rng.integers(0, bc_len, n)
+    bcs[sub, pos[sub]] = acgt[rng.integers(0, 4, int(sub.sum()))]
+    bcs[rng.random(n) < 0.02, rng.integers(0, bc_len)] = ord("N")
+    junk = rng.random(n) < 0.03
+    bcs[junk] = acgt[rng.integers(0, 4, (int(junk.sum()), bc_len))]
+    quals = (rng.integers(2, 41, (n, bc_len)) + 33).astype(np.uint8)
+    bcs, quals = bcs.reshape(-1), quals.reshape(-1)
+    m = cb.Mapper(cb.make_params("atac", max_read_length=64))
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    wl = orc.Whitelist(wl_path, bc_len)
+    wl.sample(bcs)
+    keys, counts, ns = wl.arrays()
+    m.upload_barcode_whitelist(keys, counts, ns, bc_len)
+    recs, stats = m.map_batch(s1, o1, s2, o2, barcodes=bcs, barcode_quals=quals, bc_len=bc_len)
+    orecs, obc, ost = orc.map_pairs_bc(orc.make_params("atac"), oidx, oref, s1, o1, s2, o2, bcs, quals, bc_len, whitelist=wl)
+    assert int(ost[1]) > 50  # corrections did happen
+    assert_same_records(recs, orecs)
+    assert np.array_equal(stats["barcode_keys"], obc)
+    assert (stats["n_barcodes_in_whitelist"], stats["n_barcodes_corrected"]) == (int(ost[0]), int(ost[1]))
+    r2, b2 = m.postprocess_gpu(recs, stats["barcode_keys"])
+    w2, wb2 = m.postprocess_bc(recs, stats["barcode_keys"])
+    assert_same_records(r2, w2) and np.array_equal(b2, wb2)
