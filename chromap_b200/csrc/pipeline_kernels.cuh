@@ -682,29 +682,33 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   agg_add(&ctr->n_candidates, (u64)(nc1 + nc2));
 }
 
+// The pattern window of the banded aligners as three bit planes (bit i of plane b = bit b of the base code at window
+// position i) instead of the reference's five Peq words: the match vector against a text base is three XORs, and a
+// new pattern base costs three ORs.  Same X as `Peq[code(text)]` (code 4 matches code 4), masked to the band.
+struct PatPlanes { u32 p0, p1, p2; };
+__device__ __forceinline__ void planes_or(PatPlanes &w, u32 code, u32 bit) {
+  w.p0 |= (0u - (code & 1u)) & bit;
+  w.p1 |= (0u - ((code >> 1) & 1u)) & bit;
+  w.p2 |= (0u - (code >> 2)) & bit;
+}
+__device__ __forceinline__ u32 planes_match(const PatPlanes &w, u32 code, u32 band_mask) {
+  return ~((w.p0 ^ (0u - (code & 1u))) | (w.p1 ^ (0u - ((code >> 1) & 1u))) | (w.p2 ^ (0u - (code >> 2)))) & band_mask;
+}
+__device__ __forceinline__ void planes_shift(PatPlanes &w) { w.p0 >>= 1; w.p1 >>= 1; w.p2 >>= 1; }
+
 // ------------------------------------------------------------------------------------------------
 // alignment.cc:141-192 — banded Myers/Hyyro bit-vector edit distance, band 2e+1, u32 words.
 // PAT(i) -> base code of the reference window at i; TXT(i) -> base code of the read at i.
 template <typename PatF, typename TxtF>
 __device__ __forceinline__ int banded_align(int e, int L, PatF PAT, TxtF TXT, int *end_pos) {
-  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
-  for (int i = 0; i < 2 * e; ++i) {
-    const u32 b = PAT(i);
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
-  }
-  const u32 hi = 1u << (2 * e);
+  PatPlanes W = {0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) planes_or(W, PAT(i), 1u << i);
+  const u32 hi = 1u << (2 * e), band = (hi << 1) - 1u;
   u32 VP = 0, VN = 0;
   int err = 0;
   for (int i = 0; i < L; ++i) {
-    const u32 pb = PAT(i + 2 * e);
-    const u32 tb = TXT(i);
-    u32 X = VN;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      Peq[a] |= (pb == (u32)a) ? hi : 0u;
-      X |= (tb == (u32)a) ? Peq[a] : 0u;
-    }
+    planes_or(W, PAT(i + 2 * e), hi);
+    u32 X = VN | planes_match(W, TXT(i), band);
     const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
     const u32 HN = VP & D0;
     const u32 HP = VN | ~(VP | D0);
@@ -713,8 +717,7 @@ __device__ __forceinline__ int banded_align(int e, int L, PatF PAT, TxtF TXT, in
     VP = HN | ~(X | HP);
     err += 1 - (int)(D0 & 1u);
     if (err > 3 * e) return e + 1;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+    planes_shift(W);
   }
   int best = err;
   *end_pos = L - 1;
@@ -1075,24 +1078,14 @@ __device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC 
   int ham = 0;
   for (int i = 0; i < L; ++i) if (PATC(i + e) != TXTC(i)) ++ham;
   if (ham == min_err) return e;
-  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
-  for (int i = 0; i < 2 * e; ++i) {
-    const u32 b = base_code(PATC(L - 1 + 2 * e - i));
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
-  }
-  const u32 hi = 1u << (2 * e);
+  PatPlanes W = {0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) planes_or(W, base_code(PATC(L - 1 + 2 * e - i)), 1u << i);
+  const u32 hi = 1u << (2 * e), band = (hi << 1) - 1u;
   u32 VP = 0, VN = 0;
   int err = 0;
   for (int i = 0; i < L; ++i) {
-    const u32 pb = base_code(PATC(L - 1 - i));
-    const u32 tb = base_code(TXTC(L - 1 - i));
-    u32 X = VN;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      Peq[a] |= (pb == (u32)a) ? hi : 0u;
-      X |= (tb == (u32)a) ? Peq[a] : 0u;
-    }
+    planes_or(W, base_code(PATC(L - 1 - i)), hi);
+    u32 X = VN | planes_match(W, base_code(TXTC(L - 1 - i)), band);
     const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
     const u32 HN = VP & D0;
     const u32 HP = VN | ~(VP | D0);
@@ -1100,8 +1093,7 @@ __device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC 
     VN = X & HP;
     VP = HN | ~(X | HP);
     err += 1 - (int)(D0 & 1u);
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+    planes_shift(W);
   }
   int start = 2 * e;
   for (int i = 0; i < 2 * e; ++i) {
@@ -2191,24 +2183,14 @@ __global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratc
 // alignment.cc:197-283 (from3 = false) and :285-376 (from3 = true).  PAT(i) / TXT(i): base codes at logical index i.
 template <typename PatF, typename TxtF>
 __device__ __forceinline__ int banded_align_dropoff(int e, int L, bool from3, PatF PAT, TxtF TXT, int *end_pos, int *read_len_out) {
-  u32 Peq[5] = {0u, 0u, 0u, 0u, 0u};
-  for (int i = 0; i < 2 * e; ++i) {
-    const u32 b = from3 ? PAT(L + 2 * e - 1 - i) : PAT(i);
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] |= (b == (u32)a) ? (1u << i) : 0u;
-  }
-  const u32 hi = 1u << (2 * e);
+  PatPlanes W = {0u, 0u, 0u};
+  for (int i = 0; i < 2 * e; ++i) planes_or(W, from3 ? PAT(L + 2 * e - 1 - i) : PAT(i), 1u << i);
+  const u32 hi = 1u << (2 * e), band = (hi << 1) - 1u;
   u32 VP = 0, VN = 0, pVP = 0, pVN = 0;
   int err = 0, perr = 0, i = 0, fail_beginning = 0;
   for (; i < L; ++i) {
-    const u32 pb = from3 ? PAT(L - 1 - i) : PAT(i + 2 * e);
-    const u32 tb = from3 ? TXT(L - 1 - i) : TXT(i);
-    u32 X = VN;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      Peq[a] |= (pb == (u32)a) ? hi : 0u;
-      X |= (tb == (u32)a) ? Peq[a] : 0u;
-    }
+    planes_or(W, from3 ? PAT(L - 1 - i) : PAT(i + 2 * e), hi);
+    u32 X = VN | planes_match(W, from3 ? TXT(L - 1 - i) : TXT(i), band);
     const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
     const u32 HN = VP & D0;
     const u32 HP = VN | ~(VP | D0);
@@ -2219,8 +2201,7 @@ __device__ __forceinline__ int banded_align_dropoff(int e, int L, bool from3, Pa
     perr = err;
     err += 1 - (int)(D0 & 1u);
     if (err > 2 * e) { if (i < 4 * e && i < L / 2) fail_beginning = 1; break; }
-#pragma unroll
-    for (int a = 0; a < 5; ++a) Peq[a] >>= 1;
+    planes_shift(W);
   }
   if (i < L) { err = perr; VN = pVN; VP = pVP; }
   const int band_start = i - 1;
