@@ -155,7 +155,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
@@ -469,7 +469,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preset", default="chip")
