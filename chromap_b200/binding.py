@@ -100,6 +100,7 @@ def load_library():
     L.cmx_format_bed_bc.restype = i64; L.cmx_format_bed_bc.argtypes = [vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
+    L.cmx_format_pairs_gpu.restype = i64; L.cmx_format_pairs_gpu.argtypes = [vp, vp, vp, u32, vp, u64, vp, u64, u32, vp, i64]
     L.cmx_format_bed_gpu.restype = i64; L.cmx_format_bed_gpu.argtypes = [vp, vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_postprocess_gpu.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
@@ -312,6 +313,20 @@ class Mapper:
         n = self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, None, 0)
         buf = C.create_string_buffer(n + 1)
         self.L.cmx_format_pairs(arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, first_read_id, buf, n)
+        return buf.raw[:n]
+
+    def format_pairs_gpu(self, recs, read_names, lengths, first_read_id=0, names=None):
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        rn = (C.c_char_p * len(read_names))(*[s if isinstance(s, bytes) else s.encode() for s in read_names])
+        lens = np.ascontiguousarray(lengths, dtype=np.uint32)
+        recs = np.ascontiguousarray(recs)
+        args = (self.h, arr, lens.ctypes.data, len(names), recs.ctypes.data, len(recs), rn, len(read_names), first_read_id)
+        n = self.L.cmx_format_pairs_gpu(*args, None, 0)
+        if n < 0:
+            raise RuntimeError("cmx_format_pairs_gpu: " + self.L.cmx_last_error(self.h).decode())
+        buf = C.create_string_buffer(n + 1)
+        assert self.L.cmx_format_pairs_gpu(*args, buf, n) == n
         return buf.raw[:n]
 
     def postprocess_bc(self, recs, bcs):

@@ -1439,6 +1439,69 @@ int64_t cmx_format_bed_gpu(cmx_ctx *ctx, const char *const *names, const cmx_pe_
   return ok ? total : -1;
 }
 
+// Pairs text on the device (pairs_len_kernel / pairs_write_kernel), byte-identical to cmx_format_pairs: the header is
+// written by the host, the lines by one thread each.  Read names travel as one concatenation + offsets.
+int64_t cmx_format_pairs_gpu(cmx_ctx *ctx, const char *const *names, const uint32_t *lengths, uint32_t n_seq, const cmx_pairs_record *records, uint64_t n,
+                             const char *const *read_names, uint64_t n_read_names, uint32_t first_read_id, char *buf, int64_t cap) {
+  if (!ctx || !names || !lengths || (!records && n) || (!read_names && n)) return -1;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+  std::string hdr = "## pairs format v1.0.0\n#shape: upper triangle\n";  // mapping_writer.cc:383-402
+  for (uint32_t i = 0; i < n_seq; ++i) hdr += std::string("#chromsize: ") + names[i] + " " + std::to_string(lengths[i]) + "\n";
+  hdr += "#columns: readID chrom1 pos1 chrom2 pos2 strand1 strand2 pair_type mapq1 mapq2\n";
+  int64_t total = (int64_t)hdr.size();
+  if (buf && total <= cap) memcpy(buf, hdr.data(), hdr.size());
+  if (n == 0) return total;
+  std::string cat;
+  std::vector<u32> noff(n_seq + 1, 0);
+  for (u32 i = 0; i < n_seq; ++i) { cat += names[i]; noff[i + 1] = (u32)cat.size(); }
+  std::vector<u64> roff(n_read_names + 1, 0);
+  for (u64 i = 0; i < n_read_names; ++i) roff[i + 1] = roff[i] + strlen(read_names[i]);
+  std::string rcat;
+  rcat.resize(roff[n_read_names]);
+  for (u64 i = 0; i < n_read_names; ++i) memcpy(&rcat[roff[i]], read_names[i], roff[i + 1] - roff[i]);
+  char *d_names = nullptr, *d_rn = nullptr, *d_out = nullptr;
+  u32 *d_noff = nullptr, *d_len = nullptr;
+  u64 *d_roff = nullptr, *d_off = nullptr;
+  PpRecord *d_rec = nullptr;
+  void *d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  bool ok = true;
+  auto CK = [&](cudaError_t e) { if (e != cudaSuccess) { ok = false; ctx->err = std::string("cmx_format_pairs_gpu: ") + cudaGetErrorString(e); } return ok; };
+  cudaStream_t st = ctx->stream;
+  const u64 CH = 8u << 20;
+  const u64 nc = std::min<u64>(n, CH);
+  do {
+    if (!CK(cudaMalloc(&d_names, cat.size() + 1)) || !CK(cudaMalloc(&d_noff, (n_seq + 1) * 4)) || !CK(cudaMalloc(&d_rn, rcat.size() + 1)) ||
+        !CK(cudaMalloc(&d_roff, (n_read_names + 1) * 8)) || !CK(cudaMalloc(&d_rec, nc * sizeof(PpRecord))) || !CK(cudaMalloc(&d_len, (nc + 1) * 4)) ||
+        !CK(cudaMalloc(&d_off, (nc + 1) * 8)))
+      break;
+    if (!CK(cudaMemcpyAsync(d_names, cat.data(), cat.size(), cudaMemcpyHostToDevice, st)) || !CK(cudaMemcpyAsync(d_noff, noff.data(), (n_seq + 1) * 4, cudaMemcpyHostToDevice, st)) ||
+        !CK(cudaMemcpyAsync(d_rn, rcat.data(), rcat.size(), cudaMemcpyHostToDevice, st)) || !CK(cudaMemcpyAsync(d_roff, roff.data(), (n_read_names + 1) * 8, cudaMemcpyHostToDevice, st)))
+      break;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_off, (int)nc + 1, st);
+    if (!CK(cudaMalloc(&d_tmp, tmp_bytes))) break;
+    size_t out_cap = 0;
+    for (u64 c0 = 0; c0 < n && ok; c0 += CH) {
+      const u64 m = std::min(CH, n - c0);
+      const unsigned nb = (unsigned)((m + 255) / 256);
+      if (!CK(cudaMemcpyAsync(d_rec, records + c0, m * sizeof(PpRecord), cudaMemcpyHostToDevice, st)) || !CK(cudaMemsetAsync(d_len + m, 0, 4, st))) break;
+      pairs_len_kernel<<<nb, 256, 0, st>>>(d_rec, m, d_noff, d_roff, first_read_id, d_len);
+      if (!CK(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len, d_off, (int)m + 1, st))) break;
+      u64 bytes = 0;
+      if (!CK(cudaMemcpyAsync(&bytes, d_off + m, 8, cudaMemcpyDeviceToHost, st)) || !CK(cudaStreamSynchronize(st))) break;
+      if (buf && total + (int64_t)bytes <= cap) {
+        if (bytes > out_cap) { cudaFree(d_out); d_out = nullptr; out_cap = bytes + bytes / 8; if (!CK(cudaMalloc(&d_out, out_cap))) break; }
+        pairs_write_kernel<<<nb, 256, 0, st>>>(d_rec, m, d_names, d_noff, d_rn, d_roff, first_read_id, d_off, d_out);
+        if (!CK(cudaMemcpyAsync(buf + total, d_out, bytes, cudaMemcpyDeviceToHost, st)) || !CK(cudaStreamSynchronize(st))) break;
+      }
+      total += (int64_t)bytes;
+    }
+  } while (0);
+  if (ok) CK(cudaGetLastError());
+  cudaFree(d_names); cudaFree(d_noff); cudaFree(d_rn); cudaFree(d_roff); cudaFree(d_rec); cudaFree(d_len); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_out);
+  return ok ? total : -1;
+}
+
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {
   int64_t len = 0;
   char line[1100];

@@ -371,9 +371,13 @@ int main(int argc, char **argv) {
     for (const auto &s : all_names) rn.push_back(s.c_str());
     std::vector<uint32_t> lens;
     for (size_t i = 0; i + 1 < ref.offsets.size(); ++i) lens.push_back((uint32_t)(ref.offsets[i + 1] - ref.offsets[i]));
-    bytes = cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, nullptr, 0);
-    text.resize((size_t)bytes + 1);
-    cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
+    bytes = cmx_format_pairs_gpu(ctx, names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), rn.size(), 0, nullptr, 0);
+    if (bytes >= 0) { text.resize((size_t)bytes + 1); bytes = cmx_format_pairs_gpu(ctx, names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), rn.size(), 0, text.data(), bytes); }
+    if (bytes < 0) {
+      bytes = cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, nullptr, 0);
+      text.resize((size_t)bytes + 1);
+      cmx_format_pairs(names.data(), lens.data(), (uint32_t)names.size(), pr, keep, rn.data(), 0, text.data(), bytes);
+    }
   } else if (sc) {
     if (cmx_postprocess_gpu(ctx, all.data(), all_bc.data(), all.size(), &keep) && cmx_postprocess_bc(ctx, all.data(), all_bc.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
     bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), all_bc.data(), keep, bc_len, nullptr, 0);  // text written on the device

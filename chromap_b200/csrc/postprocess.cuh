@@ -181,3 +181,36 @@ __global__ void bed_write_kernel(const PpRecord *recs, const u64 *bcs, u64 n, co
   p = put_dec(p, dups);
   *p++ = '\n';
 }
+
+// pairs lines of mapping_writer.cc:405-421: readID chrom1 pos1 chrom2 pos2 strand1 strand2 UU mapq mapq (1-based positions)
+__global__ void pairs_len_kernel(const PpRecord *recs, u64 n, const u32 *name_off, const u64 *rname_off, u32 first_read_id, u32 *len) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PpRecord r = recs[i];
+  const u32 ri = r.w[0] - first_read_id;
+  const u32 mq = pr_mapq(r);
+  len[i] = (u32)(rname_off[ri + 1] - rname_off[ri]) + 1 + (name_off[r.w[1] + 1] - name_off[r.w[1]]) + 1 + dec_digits(r.w[3] + 1u) + 1 +
+           (name_off[r.w[2] + 1] - name_off[r.w[2]]) + 1 + dec_digits(r.w[4] + 1u) + 1 + 2 + 2 + 3 + dec_digits(mq) + 1 + dec_digits(mq) + 1;
+}
+__global__ void pairs_write_kernel(const PpRecord *recs, u64 n, const char *names, const u32 *name_off, const char *rnames, const u64 *rname_off,
+                                   u32 first_read_id, const u64 *off, char *out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PpRecord r = recs[i];
+  char *p = out + off[i];
+  const u32 ri = r.w[0] - first_read_id;
+  for (u64 k = rname_off[ri]; k < rname_off[ri + 1]; ++k) *p++ = rnames[k];
+  *p++ = '\t';
+  for (u32 k = name_off[r.w[1]]; k < name_off[r.w[1] + 1]; ++k) *p++ = names[k];
+  *p++ = '\t';
+  p = put_dec(p, r.w[3] + 1u); *p++ = '\t';
+  for (u32 k = name_off[r.w[2]]; k < name_off[r.w[2] + 1]; ++k) *p++ = names[k];
+  *p++ = '\t';
+  p = put_dec(p, r.w[4] + 1u); *p++ = '\t';
+  *p++ = (r.w[5] & 0xFFu) ? '+' : '-'; *p++ = '\t';
+  *p++ = ((r.w[5] >> 8) & 0xFFu) ? '+' : '-'; *p++ = '\t';
+  *p++ = 'U'; *p++ = 'U'; *p++ = '\t';
+  const u32 mq = pr_mapq(r);
+  p = put_dec(p, mq); *p++ = '\t';
+  p = put_dec(p, mq); *p++ = '\n';
+}

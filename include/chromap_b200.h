@@ -178,6 +178,10 @@ int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, u
  * buf == NULL returns the length only; < 0 on error. */
 int64_t cmx_format_bed_gpu(cmx_ctx *ctx, const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys,
                            uint64_t n, uint32_t bc_len, char *buf, int64_t cap);
+/* Pairs text (header + lines of cmx_format_pairs) with the lines written on the device.  read_names[i] is the name of read
+ * first_read_id + i (n_read_names of them). */
+int64_t cmx_format_pairs_gpu(cmx_ctx *ctx, const char *const *names, const uint32_t *lengths, uint32_t n_seq, const cmx_pairs_record *records,
+                             uint64_t n, const char *const *read_names, uint64_t n_read_names, uint32_t first_read_id, char *buf, int64_t cap);
 
 /* ---- stage-level entry points: fixture-level parity tests and ncu isolation ------------------- */
 /* MinimizerGenerator::GenerateMinimizers (minimizer_generator.cc:7-139) for every read of a host batch.

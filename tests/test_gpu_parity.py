@@ -321,8 +321,10 @@ def test_hic_split_alignment_equals_oracle_and_golden(case, golden_dir):
         assert len(bad) == 0, (f, np.nonzero(alive)[0][bad[:5]], tr[f][alive][bad[:5]], otrace[f][alive][bad[:5]])
     assert_same_records(recs, orecs)
     assert stats["n_overflow_pairs"] == 0
-    text = m.format_pairs(m.postprocess_pairs(recs), _read_names(os.path.join(d, "read1.fq.gz")), [len(s) for s in seqs])
+    rn = _read_names(os.path.join(d, "read1.fq.gz"))
+    text = m.format_pairs(m.postprocess_pairs(recs), rn, [len(s) for s in seqs])
     assert text == gzip.open(os.path.join(d, case + ".pairs.gz")).read()
+    assert m.format_pairs_gpu(m.postprocess_gpu(recs), rn, [len(s) for s in seqs]) == text  # sort / dedup and text on the device
 
 
 def test_hic_reference_quickstart_golden(golden_dir):
