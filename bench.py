@@ -69,6 +69,11 @@ def gen_reference(torch, dev, total_bp, n_seq, seed):
         fam = lut[torch.randint(0, 4, (fam_len,), device=dev, generator=g)]
         sid = torch.randint(0, n_seq, (fam_copies,), device=dev, generator=g)
         st = sid * seq_len + torch.randint(0, seq_len - fam_len, (fam_copies,), device=dev, generator=g)
+        st = torch.sort(st).values
+        keep = torch.ones_like(st, dtype=torch.bool)
+        keep[1:] = (st[1:] - st[:-1]) >= fam_len  # a copy that would overlap its predecessor is dropped: the scatter below writes every base once (deterministic)
+        st = st[keep]
+        fam_copies = int(st.numel())
         idx = st[:, None] + torch.arange(fam_len, device=dev)[None, :]
         vals = fam[None, :].repeat(fam_copies, 1)
         m = torch.rand(fam_copies, fam_len, device=dev, generator=g) < 0.005
