@@ -52,3 +52,16 @@ def test_taskloop_chunks_match_libgomp_probe():
     assert cb.taskloop_chunks(9999) == [0]
     assert cb.taskloop_chunks(10001) == [0, 5001]
     assert len(cb.taskloop_chunks(500000)) == 100
+
+
+def test_fastq_cut_finds_record_boundaries():
+    """cmx_fastq_cut is host code: whole 4-line records only, at most max_records of them."""
+    import ctypes as C
+    import chromap_b200 as cb
+    L = cb.load_library()
+    text = b"@a 1\nACGT\n+\nIIII\n@b\nAC\n+\nII\n@c\nA"
+    n = C.c_uint32()
+    assert L.cmx_fastq_cut(text, len(text), 10, C.byref(n)) == len(b"@a 1\nACGT\n+\nIIII\n@b\nAC\n+\nII\n") and n.value == 2
+    assert L.cmx_fastq_cut(text, len(text), 1, C.byref(n)) == len(b"@a 1\nACGT\n+\nIIII\n") and n.value == 1
+    assert L.cmx_fastq_cut(text, 5, 10, C.byref(n)) == 0 and n.value == 0
+    assert L.cmx_fastq_cut(b"", 0, 10, C.byref(n)) == 0 and n.value == 0

@@ -590,3 +590,43 @@ def test_scatac_large_whitelist_equals_oracle(golden_dir, tmp_path):
     r2, b2 = m.postprocess_gpu(recs, stats["barcode_keys"])
     w2, wb2 = m.postprocess_bc(recs, stats["barcode_keys"])
     assert_same_records(r2, w2) and np.array_equal(b2, wb2)
+
+
+def test_reads_longer_than_max_read_length_escalate_and_ragged_lengths(golden_dir):
+    """2x150 bp reads, randomly cut to 20..150 bases, through a context sized for 64-base reads: too-short reads are
+    dropped, long ones climb the scratch tiers (their minimizer capacity grows 2x / 4x); records == oracle.  Reads
+    beyond the largest tier are reported (CMX_ERR_OVERFLOW), never mapped wrongly."""
+    d = os.path.join(golden_dir, "synth_hic")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    rng = np.random.default_rng(3)
+
+    def cut(s, o):
+        lens = np.minimum(np.diff(o.astype(np.int64)), rng.integers(20, 151, len(o) - 1))
+        parts = [s[o[i]:o[i] + lens[i]] for i in range(len(lens))]
+        off = np.zeros(len(o), dtype=np.uint32)
+        off[1:] = np.cumsum(lens)
+        return np.concatenate(parts), off
+
+    s1, o1 = cut(s1, o1)
+    s2, o2 = cut(s2, o2)
+    kw = dict(preset="", mapq_threshold=0)
+    m = cb.Mapper(cb.make_params("", max_read_length=64, mapq_threshold=0))
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    recs, stats = m.map_batch(s1, o1, s2, o2)
+    orecs, _ = orc.map_pairs(_oparams(kw), oidx, oref, s1, o1, s2, o2)
+    assert stats["n_overflow_pairs"] == 0
+    tm = m.timing()
+    assert tm["tier_pairs"][1] > 0 and tm["tier_pairs"][2] > 0
+    assert len(recs) == len(orecs) and len(recs) > 500
+    assert_same_records(recs, orecs)
+    m2 = cb.Mapper(cb.make_params("", max_read_length=32, mapq_threshold=0, min_read_length=20))  # largest tier: 128 bases
+    m2.upload_reference(seqs, names)
+    m2.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    with pytest.raises(cb.CmxError) as ei:
+        m2.map_batch(s1, o1, s2, o2)
+    assert "scratch tier" in str(ei.value)
