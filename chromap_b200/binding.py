@@ -100,6 +100,7 @@ def load_library():
     L.cmx_format_bed_bc.restype = i64; L.cmx_format_bed_bc.argtypes = [vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.cmx_format_bed.restype = i64; L.cmx_format_bed.argtypes = [vp, vp, u64, vp, i64]
+    L.cmx_format_tagalign.restype = i64; L.cmx_format_tagalign.argtypes = [vp, vp, u64, vp, i64]
     L.cmx_format_pairs_gpu.restype = i64; L.cmx_format_pairs_gpu.argtypes = [vp, vp, vp, u32, vp, u64, vp, u64, u32, vp, i64]
     L.cmx_format_bed_gpu.restype = i64; L.cmx_format_bed_gpu.argtypes = [vp, vp, vp, vp, u64, u32, vp, i64]
     L.cmx_postprocess_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
@@ -359,6 +360,15 @@ class Mapper:
         buf = C.create_string_buffer(n + 1)
         m = self.L.cmx_format_bed_gpu(self.h, arr, recs.ctypes.data, bp, len(recs), bc_len, buf, n)
         assert m == n
+        return buf.raw[:n]
+
+    def format_tagalign(self, recs, names=None):
+        names = names or self.names
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        recs = np.ascontiguousarray(recs)
+        n = self.L.cmx_format_tagalign(arr, recs.ctypes.data, len(recs), None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.cmx_format_tagalign(arr, recs.ctypes.data, len(recs), buf, n)
         return buf.raw[:n]
 
     def format_bed(self, recs, names=None):

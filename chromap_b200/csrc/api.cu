@@ -169,12 +169,12 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   *out = nullptr;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device >= n_dev) return CMX_ERR_NO_DEVICE;
-  if (!((params->output_format == 1 && !params->split_alignment) || (params->output_format == 5 && params->split_alignment)))
-    return CMX_ERR_INVALID;  // paired-end BED, or Hi-C pairs with split alignment
+  if (!(((params->output_format == 1 || params->output_format == 2) && !params->split_alignment) || (params->output_format == 5 && params->split_alignment)))
+    return CMX_ERR_INVALID;  // BED / TagAlign (same records), or Hi-C pairs with split alignment
   if (params->error_threshold < 1 || params->error_threshold >= 16) return CMX_ERR_INVALID;  // mapping_parameters.h:80-88
   if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
   if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
-  if (params->single_end && (params->split_alignment || params->output_format != 1)) return CMX_ERR_INVALID;  // single-end: BED only
+  if (params->single_end && (params->split_alignment || params->output_format == 5)) return CMX_ERR_INVALID;  // single-end: BED / TagAlign only
   cmx_ctx *ctx = new cmx_ctx;
   ctx->device = device;
   ctx->params = *params;
@@ -1500,6 +1500,29 @@ int64_t cmx_format_pairs_gpu(cmx_ctx *ctx, const char *const *names, const uint3
   if (ok) CK(cudaGetLastError());
   cudaFree(d_names); cudaFree(d_noff); cudaFree(d_rn); cudaFree(d_roff); cudaFree(d_rec); cudaFree(d_len); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_out);
   return ok ? total : -1;
+}
+
+// --TagAlign for paired-end records (mapping_writer.cc:84-110): one line per mate, the duplicate count on the second.
+// (Single-end TagAlign lines are the BED lines, mapping_writer.cc:55-62.)
+int64_t cmx_format_tagalign(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {
+  int64_t len = 0;
+  char line[2200];
+  for (uint64_t i = 0; i < n; ++i) {
+    const cmx_pe_record &r = recs[i];
+    const uint32_t pos_end = r.fragment_start + r.positive_alignment_length, neg_end = r.fragment_start + r.fragment_length;
+    const uint32_t neg_start = neg_end - r.negative_alignment_length;
+    const char *nm = names[r.rid];
+    int l;
+    if (r.direction)
+      l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t+\n%s\t%u\t%u\tN\t%u\t-\t%u\n", nm, r.fragment_start, pos_end, (uint32_t)r.mapq, nm, neg_start, neg_end,
+                   (uint32_t)r.mapq, (uint32_t)r.num_dups);
+    else
+      l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t-\n%s\t%u\t%u\tN\t%u\t+\t%u\n", nm, neg_start, neg_end, (uint32_t)r.mapq, nm, r.fragment_start, pos_end,
+                   (uint32_t)r.mapq, (uint32_t)r.num_dups);
+    if (buf && len + l <= cap) memcpy(buf + len, line, l);
+    len += l;
+  }
+  return len;
 }
 
 int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *recs, uint64_t n, char *buf, int64_t cap) {

@@ -195,13 +195,15 @@ int main(int argc, char **argv) {
     else if (a == "--skip-barcode-check") skip_bc_check = true;
     else if (a == "--host-reader") host_reader = true;  // parse FASTQ on the host (multi-line records, FASTA reads)
     else if (a == "-n" || a == "--max-num-best-mappings") p.max_num_best_mappings = atoi(val().c_str());
-    else if (a == "--SAM" || a == "--TagAlign" || a == "--PAF" || a == "--summary")
+    else if (a == "--TagAlign") p.output_format = 2;  // same records as BED, TagAlign / PairedTagAlign text (chromap_driver.cc:417-418)
+    else if (a == "--SAM" || a == "--PAF" || a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
   (void)bed; (void)user_set_format;
-  if (!((p.output_format == 1 && !p.split_alignment) || (p.output_format == 5 && p.split_alignment)))
-    Die("chromap-b200: supported outputs are paired-end BED (no split alignment) and Hi-C pairs (--split-alignment --pairs / --preset hic)");
+  if (!(((p.output_format == 1 || p.output_format == 2) && !p.split_alignment) || (p.output_format == 5 && p.split_alignment)))
+    Die("chromap-b200: supported outputs are BED / TagAlign (no split alignment) and Hi-C pairs (--split-alignment --pairs / --preset hic)");
+  const bool tagalign = p.output_format == 2;
   const bool pairs = p.output_format == 5;
   cmx_ctx *ctx = nullptr;
   const double t_start = Now();
@@ -231,7 +233,8 @@ int main(int argc, char **argv) {
   if (index_path.empty()) Die("No index specified!");
   if (r1_path.empty()) Die("No read file specified!");
   const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
-  if (se && (pairs || !bc_path.empty())) Die("chromap-b200: single-end mapping writes bulk BED only");
+  if (se && (pairs || !bc_path.empty())) Die("chromap-b200: single-end mapping writes bulk BED / TagAlign only");
+  if (tagalign && !bc_path.empty()) Die("chromap-b200: --TagAlign with barcodes is not on the GPU path");
   if (out_path.empty()) Die("No output file specified!");
   Reference ref;
   if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);
@@ -391,8 +394,13 @@ int main(int argc, char **argv) {
   } else {
     // sort / dedup / filter on the device; the host routine only if the records do not fit beside the index
     if (cmx_postprocess_gpu(ctx, all.data(), nullptr, all.size(), &keep) && cmx_postprocess(ctx, all.data(), all.size(), &keep)) Die(cmx_last_error(ctx));
+    if (tagalign && !se) {  // PairedTagAlign: two lines per pair (host formatter); single-end TagAlign is the BED text
+      bytes = cmx_format_tagalign(names.data(), all.data(), keep, nullptr, 0);
+      text.resize((size_t)bytes + 1);
+      cmx_format_tagalign(names.data(), all.data(), keep, text.data(), bytes);
+    } else
     bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), nullptr, keep, 0, nullptr, 0);  // text written on the device
-    if (bytes >= 0) { text.resize((size_t)bytes + 1); bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), nullptr, keep, 0, text.data(), bytes); }
+    if (!(tagalign && !se) && bytes >= 0) { text.resize((size_t)bytes + 1); bytes = cmx_format_bed_gpu(ctx, names.data(), all.data(), nullptr, keep, 0, text.data(), bytes); }
     if (bytes < 0) {
       bytes = cmx_format_bed(names.data(), all.data(), keep, nullptr, 0);
       text.resize((size_t)bytes + 1);

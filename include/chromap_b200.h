@@ -45,7 +45,7 @@ typedef struct {
   int32_t tn5_shift;
   int32_t split_alignment;        /* --split-alignment (Hi-C); requires output_format == 5 */
   int32_t low_memory_mode;
-  int32_t output_format;          /* 1 = BED, 5 = pairs (MAPPINGFORMAT_PAIRS, mapping_parameters.h:9-16) */
+  int32_t output_format;          /* 1 = BED, 2 = TagAlign (same records, other text), 5 = pairs (mapping_parameters.h:9-16) */
   int32_t batch_size;             /* pairs per reference batch (chromap.h:182: 500000); fixes the
                                      taskloop chunking that seeds multi-mapper sampling */
   int32_t max_read_length;        /* upper bound on read length in any batch (sizing), default 160 */
@@ -176,6 +176,9 @@ int64_t cmx_format_bed(const char *const *names, const cmx_pe_record *records, u
 /* The same text written on the device (also the barcoded form when barcode_keys != NULL): per-line lengths, exclusive
  * scan, one thread per line; host buffers in and out, byte-identical to cmx_format_bed / cmx_format_bed_bc.
  * buf == NULL returns the length only; < 0 on error. */
+/* --TagAlign (MAPPINGFORMAT_TAGALIGN = 2, mapping_writer.cc:84-110) for paired-end records: the same records as BED, one line
+ * per mate.  Single-end TagAlign is the BED text. */
+int64_t cmx_format_tagalign(const char *const *names, const cmx_pe_record *records, uint64_t n, char *buf, int64_t cap);
 int64_t cmx_format_bed_gpu(cmx_ctx *ctx, const char *const *names, const cmx_pe_record *records, const uint64_t *barcode_keys,
                            uint64_t n, uint32_t bc_len, char *buf, int64_t cap);
 /* Pairs text (header + lines of cmx_format_pairs) with the lines written on the device.  read_names[i] is the name of read

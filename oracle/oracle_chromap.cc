@@ -1793,6 +1793,28 @@ int64_t orc_format_pairs(const orc_reference *ref, const orc_pairs_record *recs,
   return len;
 }
 
+// --TagAlign for paired-end records (mapping_writer.cc:84-110): one line per mate, the duplicate count on the second
+int64_t orc_format_tagalign(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf, int64_t cap) {
+  int64_t len = 0;
+  char line[1100];
+  for (int64_t i = 0; i < n; ++i) {
+    const orc_pe_record &r = recs[i];
+    const u32 pos_end = r.fragment_start + r.positive_alignment_length, neg_end = r.fragment_start + r.fragment_length;
+    const u32 neg_start = neg_end - r.negative_alignment_length;
+    const char *nm = ref->names[r.rid].c_str();
+    int l;
+    if (r.direction)
+      l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t+\n%s\t%u\t%u\tN\t%u\t-\t%u\n", nm, r.fragment_start, pos_end, (u32)r.mapq, nm, neg_start, neg_end,
+                   (u32)r.mapq, (u32)r.num_dups);
+    else
+      l = snprintf(line, sizeof(line), "%s\t%u\t%u\tN\t%u\t-\n%s\t%u\t%u\tN\t%u\t+\t%u\n", nm, neg_start, neg_end, (u32)r.mapq, nm, r.fragment_start, pos_end,
+                   (u32)r.mapq, (u32)r.num_dups);
+    if (buf && len + l <= cap) memcpy(buf + len, line, l);
+    len += l;
+  }
+  return len;
+}
+
 int orc_run_files(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path,
                   const char *read2_path, const char *out_path, int n_threads, double *mapping_seconds, uint64_t *n_pairs_out) {
   orc_reference *ref = orc_reference_load(ref_path);

@@ -182,6 +182,8 @@ int64_t orc_postprocess_se(const orc_params *p, orc_pe_record *recs, int64_t n);
 int orc_run_files_se(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *out_path,
                      int n_threads);
 
+int64_t orc_format_tagalign(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,7 @@ def lib():
         L.orc_ref_task_chunks.argtypes = [u32, vp, vp, i32]
         L.orc_postprocess.restype = i64; L.orc_postprocess.argtypes = [C.POINTER(Params), vp, i64]
         L.orc_format_bed.restype = i64; L.orc_format_bed.argtypes = [vp, vp, i64, vp, i64]
+        L.orc_format_tagalign.restype = i64; L.orc_format_tagalign.argtypes = [vp, vp, i64, vp, i64]
         L.orc_whitelist_load.restype = vp; L.orc_whitelist_load.argtypes = [C.c_char_p, u32]
         L.orc_whitelist_free.argtypes = [vp]
         L.orc_whitelist_sample.argtypes = [vp, vp, u64, u32, u64, u32]
@@ -198,6 +199,14 @@ def format_bed(ref, recs):
     n = lib().orc_format_bed(ref.h, recs.ctypes.data, len(recs), None, 0)
     buf = C.create_string_buffer(n + 1)
     lib().orc_format_bed(ref.h, recs.ctypes.data, len(recs), buf, n)
+    return buf.raw[:n]
+
+
+def format_tagalign(ref, recs):
+    recs = np.ascontiguousarray(recs)
+    n = lib().orc_format_tagalign(ref.h, recs.ctypes.data, len(recs), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().orc_format_tagalign(ref.h, recs.ctypes.data, len(recs), buf, n)
     return buf.raw[:n]
 
 

@@ -18,6 +18,7 @@ run q0dedup --remove-pcr-duplicates -q 0
 run e5 -e 5 -q 10 --Tn5-shift --remove-pcr-duplicates
 run e12l300 -e 12 -l 300 -q 0
 run n3q0 -n 3 -q 0
+$REF --preset chip --TagAlign -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o chip.tagalign -t 1 2> /dev/null
 # single-end (read 1 only)
 runse() { name=$1; shift; $REF "$@" -x ref.index -r ref.fa -1 read1.fq -o $name.bed -t 1 2> /dev/null; }
 runse se_default
@@ -26,7 +27,7 @@ runse se_q0dedup_tn5 -q 0 --remove-pcr-duplicates --Tn5-shift
 runse se_n3q0 -n 3 -q 0
 runse se_lowmem_q0 --low-mem -q 0 --remove-pcr-duplicates --Tn5-shift
 md5sum *.bed > md5.txt
-gzip -9 -n ref.fa read1.fq read2.fq *.bed
+gzip -9 -n ref.fa read1.fq read2.fq *.bed chip.tagalign
 rm -f ref.index
 # the reference's own test data (README quick start): golden BEDs for SURVEY.md §4's md5s
 cd .. && rm -rf ref_test && mkdir ref_test && cd ref_test

@@ -135,3 +135,17 @@ def test_cli_falls_back_to_the_host_reader_for_fasta_reads(tmp_path, golden_dir)
         assert open(out, "rb").read() == want
         if note:
             assert note in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_tagalign(tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for reads, want in ((["-1", os.path.join(d, "read1.fq.gz"), "-2", os.path.join(d, "read2.fq.gz")], "chip.tagalign.gz"),
+                        (["-1", os.path.join(d, "read1.fq.gz")], "se_chip.bed.gz")):  # single-end TagAlign text == BED text
+        out = str(tmp_path / "out.txt")
+        r = subprocess.run([cli, "--preset", "chip", "--TagAlign", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-o", out] + reads, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == gzip.open(os.path.join(d, want)).read()

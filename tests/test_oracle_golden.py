@@ -7,6 +7,7 @@ import os
 import pytest
 
 from oracle import oracle_py as orc
+from tests.util import load_pairs
 
 
 def _md5s(d):
@@ -169,3 +170,14 @@ def test_single_end_oracle_reproduces_reference_bed(golden_dir, tmp_path, case):
     out = str(tmp_path / "out.bed")
     orc.run_files_se(p, ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), out, 2)
     assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+
+
+def test_tagalign_text_equals_reference(golden_dir):
+    """--preset chip --TagAlign: same records as BED, PairedTagAlign text (mapping_writer.cc:84-110)."""
+    d = os.path.join(golden_dir, "synth_small")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    p = orc.make_params("chip")
+    recs, _ = orc.map_pairs(p, idx, ref, s1, o1, s2, o2)
+    assert orc.format_tagalign(ref, orc.postprocess(p, recs)) == gzip.open(os.path.join(d, "chip.tagalign.gz")).read()
