@@ -150,6 +150,7 @@ int main(int argc, char **argv) {
   std::string preset, ref_path, index_path, r1_path, r2_path, out_path, bc_path, wl_path;
   int bc_err = 1, out_nw = 0;
   bool skip_bc_check = false, host_reader = false;
+  bool cell_level_dedup = false;  // remove_pcr_duplicates_at_bulk_level == false (mapping_parameters.h:49; --preset atac clears it)
   double bc_prob = 0.9;
   bool build_index = false, bed = false, user_set_format = false;
   int k = 17, w = 7, threads = 1;
@@ -157,6 +158,7 @@ int main(int argc, char **argv) {
   for (int i = 1; i < argc; ++i)
     if (!strcmp(argv[i], "--preset") && i + 1 < argc) preset = argv[i + 1];
   if (cmx_apply_preset(&p, preset.c_str()) != 0) Die("Unrecognized preset parameters " + preset + "\n");
+  if (preset == "atac") cell_level_dedup = true;  // chromap_driver.cc:254
   if (!preset.empty()) fprintf(stderr, "Preset parameters for %s are used.\n", preset.c_str());
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -195,6 +197,16 @@ int main(int argc, char **argv) {
     else if (a == "--skip-barcode-check") skip_bc_check = true;
     else if (a == "--host-reader") host_reader = true;  // parse FASTQ on the host (multi-line records, FASTA reads)
     else if (a == "-n" || a == "--max-num-best-mappings") p.max_num_best_mappings = atoi(val().c_str());
+    else if (a == "--drop-repetitive-reads") p.drop_repetitive_reads = atoi(val().c_str());
+    else if (a == "--remove-pcr-duplicates-at-cell-level") cell_level_dedup = true;   // chromap_driver.cc:395-400: the level only
+    else if (a == "--remove-pcr-duplicates-at-bulk-level") cell_level_dedup = false;
+    // options that cannot change BED / TagAlign / pairs output: the candidate cache (result-transparent), SAM scoring, QC estimators
+    else if (a == "--cache-size" || a == "--cache-update-param" || a == "--frip-est-params" || a == "--k-for-minhash" || a == "-A" || a == "--match-score" ||
+             a == "-B" || a == "--mismatch-penalty" || a == "-O" || a == "--gap-open-penalties" || a == "-E" || a == "--gap-extension-penalties") val();
+    else if (a == "--debug-cache" || a == "--turn-off-num-uniq-cache-slots") {}
+    else if (a == "--chr-order" || a == "--pairs-natural-chr-order" || a == "--read-format" || a == "--barcode-translate" || a == "--allocate-multi-mappings" ||
+             a == "-p" || a == "--matrix-output-prefix")
+      Die("chromap-b200: option " + a + " changes the output in ways that are not on the GPU path; use the reference chromap for it");
     else if (a == "--TagAlign") p.output_format = 2;  // same records as BED, TagAlign / PairedTagAlign text (chromap_driver.cc:417-418)
     else if (a == "--SAM" || a == "--PAF" || a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
@@ -235,6 +247,8 @@ int main(int argc, char **argv) {
   const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
   if (se && (pairs || !bc_path.empty())) Die("chromap-b200: single-end mapping writes bulk BED / TagAlign only");
   if (tagalign && !bc_path.empty()) Die("chromap-b200: --TagAlign with barcodes is not on the GPU path");
+  if (!bc_path.empty() && p.remove_pcr_duplicates && !cell_level_dedup)
+    Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");
   Reference ref;
   if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);

@@ -86,7 +86,8 @@ def test_cli_scatac_barcodes(tmp_path, golden_dir):
     d = os.path.join(golden_dir, "synth_sc")
     idx = str(tmp_path / "ref.index")
     subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
-    for case, extra in (("sc_whitelist", ["--barcode-whitelist", os.path.join(d, "whitelist.txt")]), ("sc_nowhitelist", [])):
+    for case, extra in (("sc_whitelist", ["--barcode-whitelist", os.path.join(d, "whitelist.txt"), "--cache-size", "1000", "--debug-cache", "-A", "1"]),
+                        ("sc_nowhitelist", [])):
         out = str(tmp_path / (case + ".bed"))
         r = subprocess.run([cli, "--preset", "atac", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
                             "-2", os.path.join(d, "read2.fq.gz"), "-b", os.path.join(d, "barcode.fq.gz"), "-o", out] + extra, capture_output=True, text=True)
