@@ -658,9 +658,8 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       CUL(cudaEventRecord(L.ev_sub[1], st));
       {
         // first-pass tile: enough rows for a typical read (about 2L/(w+1) minimizers, most of them single hits)
-        int rows0 = 16;
-        while (rows0 < S.caps.hc && rows0 * (ctx->w + 1) < 2 * ctx->params.max_read_length) rows0 <<= 1;
-        rows0 = std::min(rows0, S.caps.hc);
+        int rows0 = (2 * ctx->params.max_read_length / (ctx->w + 1) + 15) / 16 * 16;  // 16 rows at 2x50, 48 at 2x150
+        rows0 = std::max(16, std::min(rows0, S.caps.hc));
         cluster_kernel<<<(2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)rows0 * CLUSTER_NT * 8, st>>>(P, ix, S, L.ctr, 0, rows0, (int *)L.verify_list.p, L.d_count + 3);
         cluster_passes = rows0 < S.caps.hc ? 2 : 1;
         if (rows0 < S.caps.hc)
