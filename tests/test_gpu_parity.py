@@ -630,3 +630,58 @@ def test_reads_longer_than_max_read_length_escalate_and_ragged_lengths(golden_di
     with pytest.raises(cb.CmxError) as ei:
         m2.map_batch(s1, o1, s2, o2)
     assert "scratch tier" in str(ei.value)
+
+
+def test_bench_sized_batch_properties_and_sampled_oracle():
+    """One bench-sized step (2 M pairs, four reference batches) on a 300 Mbp synthetic reference: size-independent
+    properties of the whole path, plus the oracle on a contiguous sample that includes a taskloop-chunk boundary."""
+    torch = pytest.importorskip("torch")
+    import bench
+    dev = torch.device("cuda", 0)
+    n_seq, n, L = 6, 2000000, 50
+    ref, offsets, seq_len = bench.gen_reference(torch, dev, 300000000, n_seq, 11)
+    p = cb.make_params("", max_read_length=64, mapq_threshold=0, remove_pcr_duplicates=1, low_memory_mode=1)
+    m = cb.Mapper(p, device=0)
+    m.upload_reference_ptr(ref.data_ptr(), offsets)
+    m.names = ["chr%d" % (i + 1) for i in range(n_seq)]
+    m.build_index(17, 7)
+    r1, r2, off = bench.gen_pairs(torch, ref, n_seq, seq_len, n, L, 424242, dev)
+    h1, h2, ho = r1.cpu().numpy(), r2.cpu().numpy(), off.cpu().numpy().view(np.uint32)
+    out_dev = torch.empty(n * 24, dtype=torch.uint8, device=dev)
+    # (a) the same records whatever the path: device-resident input with 4 lanes / 1 lane, host input (piecewise upload)
+    m.set_lanes(4)
+    _, st4 = m.map_batch(r1, off, r2, off, on_device=True, n_pairs=n, out=out_dev, out_on_device=True)
+    rec4 = out_dev.cpu().numpy()[:st4["n_records"] * 24].view(cb.PE_RECORD).copy()
+    m.set_lanes(1)
+    _, st1 = m.map_batch(r1, off, r2, off, on_device=True, n_pairs=n, out=out_dev, out_on_device=True)
+    rec1 = out_dev.cpu().numpy()[:st1["n_records"] * 24].view(cb.PE_RECORD).copy()
+    m.set_lanes(4)
+    rech, sth = m.map_batch(h1, ho, h2, ho)
+    assert st4["n_overflow_pairs"] == 0 and st4["n_records"] == st1["n_records"] == sth["n_records"] > 0.9 * n
+    assert_same_records(rec4, rec1)
+    assert_same_records(rec4, rech)
+    # (b) records come back in read order, one per mapped pair, inside their sequences
+    assert np.all(np.diff(rec4["read_id"].astype(np.int64)) > 0)
+    assert np.all(rec4["rid"] < n_seq) and np.all(rec4["fragment_start"].astype(np.int64) + rec4["fragment_length"] <= seq_len)
+    assert np.all(rec4["mapq"] <= 60)
+    # (c) post-processing: device == host; output sorted by the reference's key, no duplicate fragment left, counts add up
+    pg, ph = m.postprocess_gpu(rec4), m.postprocess(rec4)
+    assert_same_records(pg, ph)
+    key = (pg["rid"].astype(np.uint64) << np.uint64(48)) | (pg["fragment_start"].astype(np.uint64) << np.uint64(16)) | pg["fragment_length"].astype(np.uint64)
+    assert np.all(np.diff(key.astype(np.int64)) > 0)
+    assert int(pg["num_dups"].astype(np.int64).sum()) == len(rec4)  # no run longer than 255 here, MAPQ threshold 0
+    assert m.format_bed_gpu(pg) == m.format_bed(pg)
+    # (d) the oracle on pairs [495000, 505000): the end of reference batch 0 and the start of batch 1
+    idx = m.download_index()
+    oidx = orc.Index(arrays=idx, k=17, w=7)
+    href = ref.cpu().numpy()
+    oref = orc.Reference(seqs=[href[int(offsets[i]):int(offsets[i + 1])] for i in range(n_seq)])
+    op = orc.make_params("", mapq_threshold=0, remove_pcr_duplicates=1, low_memory_mode=1)
+    for b0, lo, hi in ((0, 495000, 500000), (500000, 500000, 505000)):
+        # the sampling generator restarts per taskloop chunk of a batch: map whole chunks -> the batch's last / first 5000 pairs
+        s1, s2 = h1[lo * L:hi * L], h2[lo * L:hi * L]
+        o = (np.arange(hi - lo + 1, dtype=np.uint32) * L)
+        orecs, _ = orc.map_pairs(op, oidx, oref, s1, o, s2, o, first_read_id=lo, n_threads=8)
+        got = rec4[(rec4["read_id"] >= lo) & (rec4["read_id"] < hi)]
+        assert len(got) == len(orecs) > 4000
+        assert_same_records(got, orecs)
