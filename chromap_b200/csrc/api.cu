@@ -795,7 +795,6 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   if (in->bc_seq && ctx->params.split_alignment) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with split alignment");
   const bool se = ctx->params.single_end != 0;
   if (!in->seq1 || !in->off1 || (!se && (!in->seq2 || !in->off2))) return fail(ctx, CMX_ERR_INVALID, "cmx_batch: read pointers missing");
-  if (se && in->bc_seq) return fail(ctx, CMX_ERR_INVALID, "barcodes with single-end reads are not on the GPU path");
   if (n == 0) return CMX_OK;
   if (out->capacity < (u64)n * mb) return fail(ctx, CMX_ERR_INVALID, "records capacity %llu < n_pairs*max_num_best_mappings", (unsigned long long)out->capacity);
   CU(cudaSetDevice(ctx->device));
@@ -1271,7 +1270,7 @@ int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t *bcs, uint64_
   if (n == 0) return CMX_OK;
   std::vector<cmx_pe_record> rr(recs, recs + n);
   std::vector<uint64_t> bb(bcs, bcs + n);
-  if (!p.low_memory_mode && p.tn5_shift) for (auto &r : rr) tn5(r);
+  if (!p.low_memory_mode && p.tn5_shift) for (auto &r : rr) { if (p.single_end) tn5_se(r); else tn5(r); }
   std::vector<uint64_t> ord(n);
   for (uint64_t i = 0; i < n; ++i) ord[i] = i;
   auto key = [&](uint64_t i) {  // bed_mapping.h:145-153 prefixed by rid
@@ -1279,15 +1278,16 @@ int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t *bcs, uint64_
     return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bb[i], r.mapq, r.direction, r.is_unique, r.read_id);
   };
   std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return key(a) < key(b); });
-  auto same = [&](uint64_t a, uint64_t b) {  // bed_mapping.h:154-159: cell-level duplicates
-    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && rr[a].fragment_length == rr[b].fragment_length && bb[a] == bb[b];
+  const bool se = p.single_end != 0;
+  auto same = [&](uint64_t a, uint64_t b) {  // cell-level duplicates: bed_mapping.h:154-159 (paired-end), :36-39 (single-end: barcode + start)
+    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && (se || rr[a].fragment_length == rr[b].fragment_length) && bb[a] == bb[b];
   };
   uint64_t o = 0, i = 0;
   while (i < n) {
     uint64_t j = i + 1, keep = ord[i];
     uint32_t dups = 1;
     if (p.remove_pcr_duplicates)
-      for (; j < n && same(ord[j], ord[i]); ++j) {
+      for (; j < n && same(ord[j], ord[j - 1]); ++j) {  // consecutive equality (single-end: the key is not a prefix of the order)
         ++dups;
         if (p.low_memory_mode) { if (rr[ord[j]].mapq > rr[keep].mapq) keep = ord[j]; }
         else keep = ord[j];
@@ -1295,7 +1295,7 @@ int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *recs, uint64_t *bcs, uint64_
     cmx_pe_record k = rr[keep];
     if (k.mapq >= p.mapq_threshold) {
       if (p.remove_pcr_duplicates) k.num_dups = (uint8_t)std::min<uint32_t>(255, dups);
-      if (p.low_memory_mode && p.tn5_shift) tn5(k);
+      if (p.low_memory_mode && p.tn5_shift) { if (se) tn5_se(k); else tn5(k); }
       recs[o] = k; bcs[o] = bb[keep]; ++o;
     }
     i = j;
@@ -1330,7 +1330,7 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   const cmx_params &p = ctx->params;
   PpParams P;
   P.kind = p.output_format == 5 ? PP_PAIRS : (barcode_keys ? PP_BED_BC : (p.single_end ? PP_BED_SE : PP_BED));
-  P.low_mem = p.low_memory_mode; P.dedup = p.remove_pcr_duplicates; P.tn5 = p.tn5_shift; P.mapq_threshold = p.mapq_threshold;
+  P.low_mem = p.low_memory_mode; P.dedup = p.remove_pcr_duplicates; P.tn5 = p.tn5_shift; P.mapq_threshold = p.mapq_threshold; P.se = p.single_end;
   if (P.kind == PP_PAIRS && barcode_keys) return fail(ctx, CMX_ERR_INVALID, "barcodes are not supported with pairs output");
   const bool bc = P.kind == PP_BED_BC;
   cudaStream_t st = ctx->stream;
@@ -1351,7 +1351,7 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   PPCU(cudaMemcpyAsync(d_a, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
   if (bc) PPCU(cudaMemcpyAsync(d_bca, barcode_keys, n * 8, cudaMemcpyHostToDevice, st));
   const unsigned nb = (unsigned)((n + 255) / 256);
-  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(P.kind, d_a, n);  // chromap.h:1322-1355: before the sort
+  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, d_a, n);  // chromap.h:1322-1355: before the sort
   pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n);
   cub::DoubleBuffer<u64> dk(d_k0, d_k1);
   cub::DoubleBuffer<u32> di(d_i0, d_i1);
@@ -1367,7 +1367,7 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
     PPCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dk, di, (int)n, 0, 64, st));
   }
   pp_gather_kernel<<<nb, 256, 0, st>>>(d_a, bc ? d_bca : nullptr, di.Current(), n, d_b, d_bcb);
-  pp_head_kernel<<<nb, 256, 0, st>>>(P.kind, P.dedup, d_b, bc ? d_bcb : nullptr, n, d_head);
+  pp_head_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, P.dedup, d_b, bc ? d_bcb : nullptr, n, d_head);
   pp_resolve_kernel<<<nb, 256, 0, st>>>(P, d_b, bc ? d_bcb : nullptr, d_head, n, d_a, bc ? d_bca : nullptr, d_keep);
   PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_a, d_keep, d_b, d_nsel, (int)n, st));
   if (bc) PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_bca, d_keep, d_bcb, d_nsel + 1, (int)n, st));

@@ -245,9 +245,9 @@ int main(int argc, char **argv) {
   if (index_path.empty()) Die("No index specified!");
   if (r1_path.empty()) Die("No read file specified!");
   const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
-  if (se && (pairs || !bc_path.empty())) Die("chromap-b200: single-end mapping writes bulk BED / TagAlign only");
+  if (se && pairs) Die("chromap-b200: pairs output needs paired-end reads");
   if (tagalign && !bc_path.empty()) Die("chromap-b200: --TagAlign with barcodes is not on the GPU path");
-  if (!bc_path.empty() && p.remove_pcr_duplicates && !cell_level_dedup)
+  if (!bc_path.empty() && p.remove_pcr_duplicates && p.low_memory_mode && !cell_level_dedup)  // mapping_writer.h:254-262: only the low-memory merge has the bulk-level variant
     Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");
   Reference ref;

@@ -20,7 +20,7 @@ struct PpRecord {  // 24 bytes, viewed as cmx_pe_record or cmx_pairs_record
 };
 
 struct PpParams {
-  int kind, low_mem, dedup, tn5, mapq_threshold;
+  int kind, low_mem, dedup, tn5, mapq_threshold, se;
 };
 
 // cmx_pe_record: w0 read_id, w1 rid, w2 fragment_start, w3 = fragment_length | mapq<<16 | direction<<24,
@@ -54,9 +54,10 @@ __device__ __forceinline__ u64 pp_key_word(int kind, int word, const PpRecord &r
 }
 static inline int pp_n_words(int kind) { return kind == PP_BED_BC ? 4 : 3; }
 
-__device__ __forceinline__ bool pp_same_fragment(int kind, const PpRecord &a, u64 bca, const PpRecord &b, u64 bcb) {
+__device__ __forceinline__ bool pp_same_fragment(int kind, int se, const PpRecord &a, u64 bca, const PpRecord &b, u64 bcb) {
   if (kind == PP_PAIRS) return a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3] && a.w[4] == b.w[4];
   if (kind == PP_BED_SE) return a.w[1] == b.w[1] && a.w[2] == b.w[2];  // bed_mapping.h:89-92
+  if (kind == PP_BED_BC && se) return a.w[1] == b.w[1] && a.w[2] == b.w[2] && bca == bcb;  // bed_mapping.h:36-39
   const bool s = a.w[1] == b.w[1] && a.w[2] == b.w[2] && pe_len(a) == pe_len(b);
   return kind == PP_BED_BC ? (s && bca == bcb) : s;
 }
@@ -73,10 +74,10 @@ __device__ __forceinline__ void pp_tn5_se(PpRecord &r) {  // bed_mapping.h:97-10
   if (pe_dir(r) == 1u) r.w[2] += 4u;
   else r.w[3] = (r.w[3] & 0xFFFF0000u) | ((pe_len(r) - 5u) & 0xFFFFu);
 }
-__device__ __forceinline__ void pp_tn5_any(int kind, PpRecord &r) { if (kind == PP_BED_SE) pp_tn5_se(r); else pp_tn5(r); }
-__global__ void pp_tn5_kernel(int kind, PpRecord *recs, u64 n) {
+__device__ __forceinline__ void pp_tn5_any(int kind, int se, PpRecord &r) { if (kind == PP_BED_SE || se) pp_tn5_se(r); else pp_tn5(r); }
+__global__ void pp_tn5_kernel(int kind, int se, PpRecord *recs, u64 n) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) pp_tn5_any(kind, recs[i]);
+  if (i < n) pp_tn5_any(kind, se, recs[i]);
 }
 __global__ void pp_iota_kernel(u32 *idx, u64 n) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,10 +96,10 @@ __global__ void pp_gather_kernel(const PpRecord *recs, const u64 *bcs, const u32
   out[i] = recs[j];
   if (bcs) out_bc[i] = bcs[j];
 }
-__global__ void pp_head_kernel(int kind, int dedup, const PpRecord *recs, const u64 *bcs, u64 n, u8 *head) {
+__global__ void pp_head_kernel(int kind, int se, int dedup, const PpRecord *recs, const u64 *bcs, u64 n, u8 *head) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  head[i] = (!dedup || i == 0 || !pp_same_fragment(kind, recs[i - 1], bcs ? bcs[i - 1] : 0ull, recs[i], bcs ? bcs[i] : 0ull)) ? 1 : 0;
+  head[i] = (!dedup || i == 0 || !pp_same_fragment(kind, se, recs[i - 1], bcs ? bcs[i - 1] : 0ull, recs[i], bcs ? bcs[i] : 0ull)) ? 1 : 0;
 }
 // One thread per run head: walks its run of equal fragments (runs are short: PCR duplicates), picks the survivor
 // with the reference's rule, sets the duplicate count, applies the MAPQ filter and the deferred Tn5 shift.
@@ -123,7 +124,7 @@ __global__ void pp_resolve_kernel(PpParams P, const PpRecord *recs, const u64 *b
   if (k) {
     if (kind != PP_PAIRS) {
       if (P.dedup) keep.w[4] = (keep.w[4] & 0xFFFF00FFu) | ((dups > 255u ? 255u : dups) << 8);  // num_dups saturates (mapping_writer.h:282-284)
-      if (P.low_mem && P.tn5) pp_tn5_any(kind, keep);
+      if (P.low_mem && P.tn5) pp_tn5_any(kind, P.se, keep);
     }
     res[i] = keep;
     if (res_bc) res_bc[i] = keep_bc;

@@ -1274,6 +1274,7 @@ void orc_default_params(orc_params *p) {
   p->max_num_best_mappings = 1; p->max_insert_size = 1000; p->mapq_threshold = 30; p->min_read_length = 30;
   p->drop_repetitive_reads = 500000; p->trim_adapters = 0; p->remove_pcr_duplicates = 0; p->tn5_shift = 0;
   p->split_alignment = 0; p->low_memory_mode = 0; p->output_format = 1;
+  p->single_end = 0;
 }
 
 int orc_apply_preset(orc_params *p, const char *preset) {  // chromap_driver.cc:247-275
@@ -1478,6 +1479,7 @@ int64_t orc_map_pairs_mt(orc_mapper *m, uint32_t n, const char *seq1, const uint
 }
 
 static inline void tn5(orc_pe_record &r);
+static inline void tn5_se(orc_pe_record &r);
 void orc_mapper_set_barcodes(orc_mapper *m, const orc_whitelist *wl, int err_threshold, double prob_threshold, int output_not_in_whitelist) {
   m->wl = wl; m->bc_err_threshold = err_threshold; m->bc_prob_threshold = prob_threshold; m->output_not_in_whitelist = output_not_in_whitelist;
 }
@@ -1569,15 +1571,16 @@ int64_t orc_postprocess_bc(const orc_params *p, orc_pe_record *recs, uint64_t *b
   };
   std::vector<orc_pe_record> rr(recs, recs + n);
   std::vector<u64> bb(bcs, bcs + n);
-  if (!p->low_memory_mode && p->tn5_shift) for (auto &r : rr) tn5(r);
+  if (!p->low_memory_mode && p->tn5_shift) for (auto &r : rr) { if (p->single_end) tn5_se(r); else tn5(r); }
   auto key2 = [&](int64_t i) {
     const orc_pe_record &r = rr[i];
     return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bb[i], r.mapq, r.direction, r.is_unique, r.read_id);
   };
   (void)key;
   std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return key2(a) < key2(b); });
+  const bool se = p->single_end != 0;  // MappingWithBarcode::operator== is (barcode, start) (bed_mapping.h:36-39)
   auto same = [&](int64_t a, int64_t b) {
-    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && rr[a].fragment_length == rr[b].fragment_length && bb[a] == bb[b];
+    return rr[a].rid == rr[b].rid && rr[a].fragment_start == rr[b].fragment_start && (se || rr[a].fragment_length == rr[b].fragment_length) && bb[a] == bb[b];
   };
   int64_t o = 0, i = 0;
   while (i < n) {
@@ -1585,7 +1588,7 @@ int64_t orc_postprocess_bc(const orc_params *p, orc_pe_record *recs, uint64_t *b
     int64_t keep = ord[i];
     u32 dups = 1;
     if (p->remove_pcr_duplicates)
-      for (; j < n && same(ord[j], ord[i]); ++j) {
+      for (; j < n && same(ord[j], ord[j - 1]); ++j) {  // consecutive equality, as the merge / the in-memory pass compare
         ++dups;
         if (p->low_memory_mode) { if (rr[ord[j]].mapq > rr[keep].mapq) keep = ord[j]; }
         else keep = ord[j];  // in-memory dedup keeps the last of the run (mapping_processor.h:181-197)
@@ -1593,7 +1596,7 @@ int64_t orc_postprocess_bc(const orc_params *p, orc_pe_record *recs, uint64_t *b
     orc_pe_record k = rr[keep];
     if (k.mapq >= p->mapq_threshold) {
       if (p->remove_pcr_duplicates) k.num_dups = std::min<u32>(255, dups);
-      if (p->low_memory_mode && p->tn5_shift) tn5(k);
+      if (p->low_memory_mode && p->tn5_shift) { if (se) tn5_se(k); else tn5(k); }
       recs[o] = k; bcs[o] = bb[keep]; ++o;
     }
     i = j;
@@ -1898,6 +1901,29 @@ int64_t orc_map_reads_se(orc_mapper *m, uint32_t n, const char *seq, const uint3
     cnt[i] = map_one_read_se(m->P, *m->ix, *m->ref, seq + off[i], off[i + 1] - off[i], first_read_id + (u32)i, (u32)i, &all[(size_t)i * per], per);
   int64_t n_out = 0;
   for (u32 i = 0; i < n; ++i) for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) out[n_out++] = all[(size_t)i * per + j];
+  return n_out;
+}
+
+int64_t orc_map_reads_se_bc(orc_mapper *m, uint32_t n, const char *seq, const uint32_t *off, const char *bcs, const char *quals, uint32_t bc_len,
+                            uint32_t first_read_id, orc_pe_record *out, uint64_t *out_bc, int64_t cap_out, int n_threads, uint64_t *bc_stats) {
+  const int per = m->P.max_num_best_mappings;
+  std::vector<orc_pe_record> all((size_t)n * per);
+  std::vector<u64> keys(n, 0);
+  std::vector<int> cnt(n, 0);
+  u64 n_in = 0, n_cor = 0;
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(n_threads > 0 ? n_threads : 1) reduction(+ : n_in, n_cor)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {  // chromap.h:392-409: barcode gate first
+    std::string bc(bcs + (size_t)i * bc_len, bc_len);
+    bool ok = true;
+    if (m->wl) ok = correct_barcode(*m->wl, m->bc_err_threshold, m->bc_prob_threshold, &bc[0], quals + (size_t)i * bc_len, bc_len, &n_in, &n_cor);
+    keys[i] = barcode_seed(bc.data(), bc_len);
+    if (!(ok || m->output_not_in_whitelist)) continue;
+    cnt[i] = map_one_read_se(m->P, *m->ix, *m->ref, seq + off[i], off[i + 1] - off[i], first_read_id + (u32)i, (u32)i, &all[(size_t)i * per], per);
+  }
+  if (bc_stats) { bc_stats[0] += n_in; bc_stats[1] += n_cor; }
+  int64_t n_out = 0;
+  for (u32 i = 0; i < n; ++i)
+    for (int j = 0; j < cnt[i] && n_out < cap_out; ++j) { out[n_out] = all[(size_t)i * per + j]; out_bc[n_out] = keys[i]; ++n_out; }
   return n_out;
 }
 

@@ -37,6 +37,7 @@ typedef struct {
   int32_t split_alignment;
   int32_t low_memory_mode;
   int32_t output_format;  // 1 = BED, 5 = pairs (Hi-C, with split_alignment)
+  int32_t single_end;     // records are single-end (MappingWithoutBarcode / MappingWithBarcode): changes duplicate equality and Tn5
 } orc_params;
 
 void orc_default_params(orc_params *p);
@@ -183,6 +184,10 @@ int orc_run_files_se(const orc_params *p, const char *index_path, const char *re
                      int n_threads);
 
 int64_t orc_format_tagalign(const orc_reference *ref, const orc_pe_record *recs, int64_t n, char *buf, int64_t cap);
+
+// Single-end reads with cell barcodes (MappingWithBarcode, bed_mapping.h:8-60); post-process with orc_postprocess_bc and single_end = 1.
+int64_t orc_map_reads_se_bc(orc_mapper *m, uint32_t n, const char *seq, const uint32_t *off, const char *bcs, const char *quals, uint32_t bc_len,
+                            uint32_t first_read_id, orc_pe_record *out, uint64_t *out_bc, int64_t cap_out, int n_threads, uint64_t *bc_stats);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "error_threshold", "min_num_seeds", "max_seed_freq0", "max_seed_freq1", "max_num_best_mappings",
         "max_insert_size", "mapq_threshold", "min_read_length", "drop_repetitive_reads", "trim_adapters",
-        "remove_pcr_duplicates", "tn5_shift", "split_alignment", "low_memory_mode", "output_format")]
+        "remove_pcr_duplicates", "tn5_shift", "split_alignment", "low_memory_mode", "output_format", "single_end")]
 
 
 PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u4"), ("fragment_length", "<u2"),
@@ -91,6 +91,7 @@ def lib():
         L.orc_format_bed_bc.restype = i64; L.orc_format_bed_bc.argtypes = [vp, vp, vp, i64, u32, vp, i64]
         L.orc_run_files_bc.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 7 + [i32, vp]
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.orc_map_reads_se_bc.restype = i64; L.orc_map_reads_se_bc.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32, vp, vp, i64, i32, vp]
         L.orc_map_reads_se.restype = i64; L.orc_map_reads_se.argtypes = [vp, u32, vp, vp, u32, vp, i64, i32]
         L.orc_postprocess_se.restype = i64; L.orc_postprocess_se.argtypes = [C.POINTER(Params), vp, i64]
         L.orc_run_files_se.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 4 + [i32]
@@ -232,6 +233,37 @@ def map_reads_se(params, index, ref, seq, off, first_read_id=0, n_threads=1):
     got = L.orc_map_reads_se(m, n, seq.ctypes.data, off.ctypes.data, first_read_id, out.ctypes.data, len(out), n_threads)
     L.orc_mapper_free(m)
     return out[:got]
+
+
+def map_reads_se_bc(params, index, ref, seq, off, barcodes, quals, bc_len, whitelist=None, first_read_id=0, n_threads=1):
+    L = lib()
+    m = L.orc_mapper_create(C.byref(params), index.h, ref.h)
+    if whitelist is not None:
+        L.orc_mapper_set_barcodes(m, whitelist.h, 1, 0.9, 0)
+    n = len(off) - 1
+    out = np.zeros(n * params.max_num_best_mappings, dtype=PE_RECORD)
+    obc = np.zeros(len(out), dtype=np.uint64)
+    st = np.zeros(2, dtype=np.uint64)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.uint32)
+    barcodes = np.ascontiguousarray(barcodes, dtype=np.uint8); quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    got = L.orc_map_reads_se_bc(m, n, seq.ctypes.data, off.ctypes.data, barcodes.ctypes.data, quals.ctypes.data, bc_len, first_read_id,
+                                out.ctypes.data, obc.ctypes.data, len(out), n_threads, st.ctypes.data)
+    L.orc_mapper_free(m)
+    return out[:got], obc[:got], st
+
+
+def postprocess_bc(params, recs, bcs):
+    recs = np.ascontiguousarray(recs.copy()); bcs = np.ascontiguousarray(bcs.copy(), dtype=np.uint64)
+    n = lib().orc_postprocess_bc(C.byref(params), recs.ctypes.data, bcs.ctypes.data, len(recs))
+    return recs[:n], bcs[:n]
+
+
+def format_bed_bc(ref, recs, bcs, bc_len):
+    recs = np.ascontiguousarray(recs); bcs = np.ascontiguousarray(bcs, dtype=np.uint64)
+    n = lib().orc_format_bed_bc(ref.h, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().orc_format_bed_bc(ref.h, recs.ctypes.data, bcs.ctypes.data, len(recs), bc_len, buf, n)
+    return buf.raw[:n]
 
 
 def postprocess_se(params, recs):

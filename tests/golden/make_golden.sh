@@ -62,6 +62,10 @@ $REF -i -r ref.fa -o ref.index 2> /dev/null
 $REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -b barcode.fq --barcode-whitelist whitelist.txt -o sc_whitelist.bed -t 1 2> sc.log
 $REF --preset atac -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -b barcode.fq -o sc_nowhitelist.bed -t 1 2> /dev/null
 grep -E "Number of (barcodes|corrected)" sc.log > sc_stats.txt; rm sc.log
+# single-end reads with barcodes (MappingWithBarcode)
+$REF --preset atac -x ref.index -r ref.fa -1 read1.fq -b barcode.fq --barcode-whitelist whitelist.txt -o se_sc_whitelist.bed -t 1 2> /dev/null
+$REF --preset atac -x ref.index -r ref.fa -1 read1.fq -b barcode.fq -o se_sc_nowhitelist.bed -t 1 2> /dev/null
+$REF -q 0 --remove-pcr-duplicates --Tn5-shift -x ref.index -r ref.fa -1 read1.fq -b barcode.fq --barcode-whitelist whitelist.txt -o se_sc_inmem.bed -t 1 2> /dev/null
 md5sum *.bed > md5.txt
 gzip -9 -n ref.fa read1.fq read2.fq barcode.fq *.bed
 rm -f ref.index

@@ -96,6 +96,12 @@ def test_cli_scatac_barcodes(tmp_path, golden_dir):
         if extra:
             for line in open(os.path.join(d, "sc_stats.txt")):
                 assert line.strip() in r.stderr
+    # single-end reads with barcodes (MappingWithBarcode)
+    out = str(tmp_path / "se_sc.bed")
+    r = subprocess.run([cli, "--preset", "atac", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq.gz"),
+                        "-b", os.path.join(d, "barcode.fq.gz"), "--barcode-whitelist", os.path.join(d, "whitelist.txt"), "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, "se_sc_whitelist.bed.gz")).read()
 
 
 @pytest.mark.gpu

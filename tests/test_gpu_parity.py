@@ -685,3 +685,37 @@ def test_bench_sized_batch_properties_and_sampled_oracle():
         got = rec4[(rec4["read_id"] >= lo) & (rec4["read_id"] < hi)]
         assert len(got) == len(orecs) > 4000
         assert_same_records(got, orecs)
+
+
+@pytest.mark.parametrize("case,kw,use_wl", [("se_sc_whitelist", dict(preset="atac"), True), ("se_sc_nowhitelist", dict(preset="atac"), False),
+                                            ("se_sc_inmem", dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1), True)])
+def test_single_end_barcoded_equals_oracle_and_golden(case, kw, use_wl, golden_dir):
+    """Single-end reads with cell barcodes (MappingWithBarcode): device correction + mapping == oracle; post-processing on the
+    host and on the device reproduce the reference binary's BED (duplicates = same barcode and start, consecutive in order)."""
+    d = os.path.join(golden_dir, "synth_sc")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    oref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    oidx = orc.Index(ref=oref, k=17, w=7)
+    s1, o1, _, _ = load_pairs(d)
+    bcs, quals, bc_len = _read_barcodes(os.path.join(d, "barcode.fq.gz"))
+    kw = dict(kw)
+    preset = kw.pop("preset")
+    m = cb.Mapper(cb.make_params(preset, max_read_length=64, single_end=1, **kw))
+    m.upload_reference(seqs, names)
+    a = oidx.arrays()
+    m.upload_index(17, 7, a["n_buckets"], a["flags"], a["keys"], a["vals"], a["occ"])
+    wl = None
+    if use_wl:
+        wl = orc.Whitelist(os.path.join(d, "whitelist.txt"), bc_len)
+        wl.sample(bcs)
+        keys, counts, ns = wl.arrays()
+        m.upload_barcode_whitelist(keys, counts, ns, bc_len)
+    recs, stats = m.map_batch(s1, o1, None, None, barcodes=bcs, barcode_quals=quals, bc_len=bc_len)
+    orecs, obc, ost = orc.map_reads_se_bc(orc.make_params(preset, single_end=1, **kw), oidx, oref, s1, o1, bcs, quals, bc_len, whitelist=wl)
+    assert_same_records(recs, orecs)
+    assert np.array_equal(stats["barcode_keys"], obc)
+    want = gzip.open(os.path.join(d, case + ".bed.gz")).read()
+    r2, b2 = m.postprocess_bc(recs, stats["barcode_keys"])
+    assert m.format_bed_bc(r2, b2, bc_len) == want
+    r3, b3 = m.postprocess_gpu(recs, stats["barcode_keys"])
+    assert m.format_bed_gpu(r3, b3, bc_len) == want

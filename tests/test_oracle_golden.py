@@ -181,3 +181,36 @@ def test_tagalign_text_equals_reference(golden_dir):
     p = orc.make_params("chip")
     recs, _ = orc.map_pairs(p, idx, ref, s1, o1, s2, o2)
     assert orc.format_tagalign(ref, orc.postprocess(p, recs)) == gzip.open(os.path.join(d, "chip.tagalign.gz")).read()
+
+
+SE_SC_CASES = {
+    "se_sc_whitelist": (dict(preset="atac"), True),
+    "se_sc_nowhitelist": (dict(preset="atac"), False),
+    "se_sc_inmem": (dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1), True),
+}
+
+
+def _barcodes(path):
+    lines = gzip.open(path).read().split(b"\n")
+    import numpy as np
+    return np.frombuffer(b"".join(lines[1::4]), dtype=np.uint8), np.frombuffer(b"".join(lines[3::4]), dtype=np.uint8), len(lines[1])
+
+
+@pytest.mark.parametrize("case", sorted(SE_SC_CASES))
+def test_single_end_barcoded_oracle_reproduces_reference_bed(golden_dir, case):
+    """chromap -1 r1 -b barcodes [--barcode-whitelist]: MappingWithBarcode records, duplicates = same (barcode, start)."""
+    d = os.path.join(golden_dir, "synth_sc")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    s1, o1, _, _ = load_pairs(d)
+    bcs, quals, bc_len = _barcodes(os.path.join(d, "barcode.fq.gz"))
+    kw, use_wl = SE_SC_CASES[case]
+    kw = dict(kw)
+    p = orc.make_params(kw.pop("preset"), single_end=1, **kw)
+    wl = None
+    if use_wl:
+        wl = orc.Whitelist(os.path.join(d, "whitelist.txt"), bc_len)
+        wl.sample(bcs)
+    recs, obc, _ = orc.map_reads_se_bc(p, idx, ref, s1, o1, bcs, quals, bc_len, whitelist=wl, n_threads=2)
+    r2, b2 = orc.postprocess_bc(p, recs, obc)
+    assert orc.format_bed_bc(ref, r2, b2, bc_len) == gzip.open(os.path.join(d, case + ".bed.gz")).read()
