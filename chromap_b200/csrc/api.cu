@@ -894,9 +894,9 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   u64 total = 0;
   for (int l = 0; l < n_lanes; ++l) total += jobs[l].total;
   CU(cudaGetLastError());
-  float ms_h2d = 0, ms_d2h = 0;
+  float ms_h2d = 0, ms_call = 0;
   cudaEventElapsedTime(&ms_h2d, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&ms_d2h, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ms_call, ctx->ev[2], ctx->ev[3]);  // lanes launched .. last record delivered (events on an idle stream)
   BatchAcc acc;
   for (int l = 0; l < n_lanes; ++l) {
     const BatchAcc &a = jobs[l].acc;
@@ -915,10 +915,10 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   cmx_timing &tm = ctx->timing;
   memset(&tm, 0, sizeof(tm));
   // stage times are sums over the lanes' own streams; lanes overlap, so they add up to more than total_ms
-  tm.h2d_ms = ms_h2d; tm.d2h_ms = ms_d2h;
+  tm.h2d_ms = ms_h2d; tm.d2h_ms = 0;  // record copies run on the lanes' own streams, overlapped with other lanes' kernels
   tm.seed_ms = acc.ms_seed; tm.minimizer_ms = acc.ms_minimizer; tm.probe_ms = acc.ms_probe; tm.cluster_ms = acc.ms_cluster;
   tm.pair_candidates_ms = acc.ms_pc; tm.verify_ms = acc.ms_ver; tm.pairing_ms = acc.ms_pair; tm.select_ms = acc.ms_select; tm.emit_ms = acc.ms_emit;
-  tm.total_ms = 0;
+  tm.total_ms = ms_call;
   tm.n_minimizers = acc.c.n_minimizers; tm.n_probe_steps = acc.c.n_probe_steps; tm.n_found = acc.c.n_found; tm.n_occ_reads = acc.c.n_occ_reads;
   tm.n_verified = acc.c.n_verified; tm.n_launches = acc.launches;
   for (int t = 0; t < 3; ++t) tm.tier_pairs[t] = acc.tier_pairs[t];
