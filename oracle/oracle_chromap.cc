@@ -1007,9 +1007,105 @@ static void trim_adapters(const orc_params &P, std::string &r1, std::string &r2,
 }
 
 // One iteration of the taskloop, chromap.h:892-1143 (bulk data, BED, non-split).
+// ---- SAM output (round-2 groundwork: the oracle side of SURVEY.md 8f rank 3; the CUDA path does not emit SAM yet) ------
+// Semi-global affine alignment of the read (outer loop) against a reference window (banded, band w, one direction byte
+// per cell, traceback to a CIGAR) with the arithmetic and tie rules of ksw_semi_global3 (ksw.cc:505-626): the read may
+// start anywhere in the first w window positions for free and end at the best of the last w.
+struct SamAln { std::vector<u32> cigar; int start = 0, end = 0, score = 0; };
+static void sg_align(const char *win, int wlen, const char *read, int rlen, int match, int mismatch, int o_del, int e_del, int o_ins, int e_ins, int w,
+                     SamAln &out) {
+  const int NEG = -0x40000000;
+  auto sc = [&](char a, char b) { const int x = code(a), y = code(b); return (x < 4 && y < 4) ? (x == y ? match : -mismatch) : 0; };  // mapping_generator.h:661-670
+  const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+  const int n_col = wlen < 2 * w + 1 ? wlen : 2 * w + 1;
+  std::vector<uint8_t> z((size_t)n_col * rlen, 0);
+  std::vector<int> H(wlen + 1), E(wlen + 1);
+  H[0] = 0; E[0] = NEG;
+  int j = 1;
+  for (; j <= wlen && j <= w; ++j) { H[j] = 0; E[j] = NEG; }
+  for (; j <= wlen; ++j) H[j] = E[j] = NEG;
+  for (int i = 0; i < rlen; ++i) {
+    int f = NEG;
+    const int beg = i, end = i + w + 1 < wlen ? i + w + 1 : wlen;
+    int h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : NEG;
+    uint8_t *zi = &z[(size_t)i * n_col];
+    for (j = beg; j < end; ++j) {
+      int m = H[j], e = E[j];
+      H[j] = h1;
+      m += sc(read[i], win[j]);
+      uint8_t d = m >= e ? 0 : 1;
+      int h = m >= e ? m : e;
+      d = h >= f ? d : 2;
+      h = h >= f ? h : f;
+      h1 = h;
+      int t = m - oe_del;
+      e -= e_del;
+      if (e > t) d |= 1 << 2; else e = t;
+      E[j] = e;
+      t = m - oe_ins;
+      f -= e_ins;
+      if (f > t) d |= 2 << 4; else f = t;
+      zi[j - beg] = d;
+    }
+    H[end] = h1; E[end] = NEG;
+  }
+  int score = H[wlen], best = wlen;
+  for (j = 1; j < w; ++j) if (H[wlen - j] > score) { score = H[wlen - j]; best = wlen - j; }
+  out.score = score; out.end = best;
+  std::vector<std::pair<int, int>> ops;  // (op, len) from the end
+  auto push = [&](int op, int len) { if (!ops.empty() && ops.back().first == op) ops.back().second += len; else ops.push_back({op, len}); };
+  int i = rlen - 1, k = best - 1, which = 0;
+  while (i >= 0 && k >= 0) {
+    which = z[(size_t)i * n_col + (k - i)] >> (which << 1) & 3;
+    if (which == 0) { push(0, 1); --i; --k; }
+    else if (which == 1) { push(1, 1); --i; }
+    else { push(2, 1); --k; }
+  }
+  if (i >= 0) push(1, i + 1);
+  out.start = k + 1;
+  out.cigar.clear();
+  for (size_t q = ops.size(); q-- > 0;) out.cigar.push_back((u32)ops[q].second << 4 | (u32)ops[q].first);
+}
+
+struct SamRec {  // SAMMapping (sam_mapping.h), bulk data
+  u32 read_id; std::string name; int64_t pos; int rid; int64_t mpos; int mrid; int tlen; int flag; int strand_pos; int is_unique; int mapq; int nm;
+  std::vector<u32> cigar; std::string md, seq, qual;
+};
+
+// GetRefStartEndPositionForReadFromMapping, SAM branch, non-split (mapping_generator.h:696-760,807-855) + GenerateNMAndMDTag
+// (alignment.cc:85-139).  read_seq is the strand's sequence (the reverse complement for the - strand).
+static void ref_span_sam(const orc_params &P, const orc_reference &ref, const Draft &d, const char *read_seq, int L, u32 &start, u32 &end, SamRec &r) {
+  const int e = P.error_threshold;
+  const u32 rid = (u32)(d.pos >> 32), rp = (u32)d.pos;
+  u32 vws = rp + 1 > (u32)(L + e) ? rp + 1 - L - e : 0;
+  if (rp + e >= ref.lens[rid]) vws = ref.lens[rid] - e - L;
+  const char *rseq = ref.seqs[rid].data();
+  SamAln a;
+  sg_align(rseq + vws, L + 2 * e, read_seq, L, 1, 4, 6, 1, 6, 1, 2 * e + 1, a);  // mapping_parameters.h:20-23 defaults
+  start = vws + a.start;
+  end = vws + a.end - 1;
+  r.cigar = a.cigar;
+  r.nm = 0; r.md.clear();
+  int nmatch = 0, rpos = 0, gpos = 0;
+  const char *g = rseq + start;
+  for (u32 c : a.cigar) {
+    const int op = c & 0xf, len = c >> 4;
+    if (op == 0) {
+      for (int q = 0; q < len; ++q, ++rpos, ++gpos) {
+        if (g[gpos] == read_seq[rpos] || g[gpos] - 'a' + 'A' == read_seq[rpos]) ++nmatch;
+        else { ++r.nm; r.md += std::to_string(nmatch); nmatch = 0; r.md.push_back(g[gpos]); }
+      }
+    } else if (op == 1) { r.nm += len; rpos += len; }
+    else { r.nm += len; r.md += std::to_string(nmatch); nmatch = 0; r.md.push_back('^'); for (int q = 0; q < len; ++q) r.md.push_back(g[gpos++]); }
+  }
+  r.md += std::to_string(nmatch);
+}
+
+struct SamSink { std::vector<SamRec> *recs; const char *name1, *qual1, *name2, *qual2; };
+
 static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_reference &ref, std::mt19937 &gen,
                         const char *s1, u32 len1, const char *s2, u32 len2, u32 read_id, u32 pair_index,
-                        orc_pe_record *out, int cap, orc_pair_trace *tr) {
+                        orc_pe_record *out, int cap, orc_pair_trace *tr, const SamSink *sam = nullptr) {
   if (tr) memset(tr, 0, sizeof(*tr));
   if (len1 < (u32)P.min_read_length || len2 < (u32)P.min_read_length) return 0;
   std::string r[2] = {std::string(s1, len1), std::string(s2, len2)}, neg[2];
@@ -1124,6 +1220,33 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
           ++idx;
           continue;
         }
+        if (sam) {  // mapping_generator.h:575-640 with MAPPINGFORMAT_SAM, mapping_generator.cc:84-107
+          SamRec a, b;
+          ref_span_sam(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1, a);
+          ref_span_sam(P, ref, d2, s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2, b);
+          const uint16_t sal1 = en1 - st1 + 1, sal2 = en2 - st2 + 1;
+          q = mapq_pe(d1.err, d2.err, sal1, sal2, L[0], L[1], force, ps, rs);
+          const int tlen = s1 == 0 ? (int)(en2 - st1 + 1) : (int)(en1 - st2 + 1);
+          int f1 = 3 | 64, f2 = 3 | 128;
+          if (s1 == 1) { f1 |= 16; f2 |= 32; }
+          if (s2 == 1) { f1 |= 32; f2 |= 16; }
+          if (reported >= 1) { f1 |= 256; f2 |= 256; }
+          a.read_id = b.read_id = read_id; a.name = sam->name1; b.name = sam->name2;
+          a.pos = st1; a.rid = (int)(u32)(d1.pos >> 32); b.pos = st2; b.rid = (int)(u32)(d2.pos >> 32);
+          a.mpos = b.pos; a.mrid = b.rid; b.mpos = a.pos; b.mrid = a.rid;
+          a.strand_pos = s1 == 0; b.strand_pos = s2 == 0;
+          a.tlen = a.strand_pos ? tlen : -tlen; b.tlen = b.strand_pos ? tlen : -tlen;
+          a.flag = f1; b.flag = f2; a.is_unique = b.is_unique = uniq; a.mapq = b.mapq = q;
+          a.seq = s1 == 0 ? r[0] : neg[0]; b.seq = s2 == 0 ? r[1] : neg[1];
+          a.qual = sam->qual1; b.qual = sam->qual2;
+          if (s1 != 0) std::reverse(a.qual.begin(), a.qual.end());
+          if (s2 != 0) std::reverse(b.qual.begin(), b.qual.end());
+          a.qual.resize(a.seq.size(), 'I'); b.qual.resize(b.seq.size(), 'I');
+          sam->recs->push_back(a); sam->recs->push_back(b);
+          if (++reported == to_report) break;
+          ++idx;
+          continue;
+        }
         ref_span(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1);
         ref_span(P, ref, d2, s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2);
         const uint16_t al1 = en1 - st1 + 1, al2 = en2 - st2 + 1;
@@ -1155,7 +1278,7 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
 // (mapping_generator.cc:7-16).  No mate: no supplementation, no paired-end filter, mappings stay in verification
 // order; the sampling generator is a fresh mt19937(11) per read (mapping_generator.h:128).
 static int map_one_read_se(const orc_params &P, const orc_index &ix, const orc_reference &ref, const char *s, u32 len, u32 read_id,
-                           u32 read_index, orc_pe_record *out, int cap) {
+                           u32 read_index, orc_pe_record *out, int cap, const SamSink *sam = nullptr) {
   if (len < (u32)P.min_read_length) return 0;
   std::string r(s, len), neg;
   revcomp(r.data(), len, neg);
@@ -1185,6 +1308,21 @@ static int map_one_read_se(const orc_params &P, const orc_index &ix, const orc_r
       if (d.err > rs.min_err) continue;
       if (idx == sel[reported]) {
         u32 a, b;
+        if (sam) {  // mapping_generator.h:302-331 with MAPPINGFORMAT_SAM
+          SamRec sr;
+          ref_span_sam(P, ref, d, st == 0 ? r.data() : neg.data(), len, a, b, sr);
+          const uint16_t al = b - a + 1;
+          sr.read_id = read_id; sr.name = sam->name1; sr.pos = a; sr.rid = (int)(u32)(d.pos >> 32); sr.mpos = 0; sr.mrid = -1; sr.tlen = 0;
+          sr.flag = (st == 0 ? 0 : 16) | (reported >= 1 ? 256 : 0);
+          sr.strand_pos = st == 0; sr.is_unique = rs.n_best == 1; sr.mapq = mapq_se(d.err, al, (int)len, P.error_threshold, rs);
+          sr.seq = st == 0 ? r : neg;
+          sr.qual = sam->qual1;
+          if (st != 0) std::reverse(sr.qual.begin(), sr.qual.end());
+          sam->recs->push_back(sr);
+          if (++reported == to_report) break;
+          ++idx;
+          continue;
+        }
         ref_span(P, ref, d, st == 0 ? r.data() : neg.data(), len, a, b);
         const uint16_t al = b - a + 1;
         if (reported < cap) {
@@ -2014,6 +2152,83 @@ int orc_run_files_se(const orc_params *p, const char *index_path, const char *re
   fwrite(text.data(), 1, bytes, f);
   fclose(f);
   orc_mapper_free(m); orc_index_free(ix); orc_reference_free(ref);
+  return 0;
+}
+
+
+// ---- SAM (oracle only, groundwork): chromap --SAM for bulk single-end / paired-end reads, non-split --------------------
+int orc_run_files_sam(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                      const char *out_path) {
+  orc_reference *ref = orc_reference_load(ref_path);
+  orc_index *ix = orc_index_load(index_path);
+  if (!ref || !ix || p->split_alignment) return -1;
+  const bool se = !read2_path || !*read2_path;
+  SeqReader r1, r2;
+  if (!r1.open(read1_path) || (!se && !r2.open(read2_path))) return -3;
+  std::vector<SamRec> recs;
+  const u32 batch = 500000;
+  u32 read_id = 0;
+  for (;;) {
+    std::vector<std::string> n1, s1, q1, n2, s2, q2;
+    std::string n, s, q;
+    while (n1.size() < batch) {
+      bool a = r1.next(n, s, q);
+      while (a && s.empty()) a = r1.next(n, s, q);
+      if (!a) break;
+      n1.push_back(n); s1.push_back(s); q1.push_back(q);
+      if (!se) {
+        bool b = r2.next(n, s, q);
+        while (b && s.empty()) b = r2.next(n, s, q);
+        if (!b) return -4;
+        n2.push_back(n); s2.push_back(s); q2.push_back(q);
+      }
+    }
+    const u32 cnt = (u32)n1.size();
+    if (cnt == 0) break;
+    std::vector<u32> st(cnt / 5000 + 2), en(cnt / 5000 + 2);
+    const int nt = orc_ref_task_chunks(cnt, st.data(), en.data(), (int)st.size());
+    orc_pe_record dummy[8];
+    for (int t = 0; t < nt; ++t) {
+      std::mt19937 gen(11);
+      for (u32 i = st[t]; i < en[t]; ++i) {
+        SamSink sink{&recs, n1[i].c_str(), q1[i].c_str(), se ? nullptr : n2[i].c_str(), se ? nullptr : q2[i].c_str()};
+        if (se) map_one_read_se(*p, *ix, *ref, s1[i].data(), (u32)s1[i].size(), read_id + i, i, dummy, 8, &sink);
+        else map_one_pair(*p, *ix, *ref, gen, s1[i].data(), (u32)s1[i].size(), s2[i].data(), (u32)s2[i].size(), read_id + i, i, dummy, 8, nullptr, &sink);
+      }
+    }
+    read_id += cnt;
+  }
+  r1.close(); if (!se) r2.close();
+  // SAMMapping::operator< (sam_mapping.h:188-193) prefixed by the bucket (= rid); operator== (:194-199)
+  auto key = [](const SamRec &r) { return std::make_tuple(r.rid, r.pos, (u64)0, r.mrid, r.mpos, r.flag & 64, r.mapq, r.read_id); };
+  std::stable_sort(recs.begin(), recs.end(), [&](const SamRec &a, const SamRec &b) { return key(a) < key(b); });
+  auto same = [](const SamRec &a, const SamRec &b) { return a.rid == b.rid && a.pos == b.pos && (a.flag & 64) == (b.flag & 64) && a.mrid == b.mrid && a.mpos == b.mpos; };
+  std::vector<const SamRec *> keep;
+  if (p->remove_pcr_duplicates) {
+    size_t i = 0;
+    while (i < recs.size()) {
+      size_t j = i + 1, k = i;
+      for (; j < recs.size() && same(recs[j], recs[j - 1]); ++j) {
+        if (p->low_memory_mode) { if (recs[j].mapq > recs[k].mapq) k = j; } else k = j;
+      }
+      keep.push_back(&recs[k]);
+      i = j;
+    }
+  } else for (const auto &r : recs) keep.push_back(&r);
+  FILE *f = fopen(out_path, "wb");
+  if (!f) return -5;
+  for (size_t i = 0; i < ref->names.size(); ++i) fprintf(f, "@SQ\tSN:%s\tLN:%u\n", ref->names[i].c_str(), ref->lens[i]);  // mapping_writer.cc:312-321
+  for (const SamRec *r : keep) {  // mapping_writer.cc:324-356
+    if (r->mapq < p->mapq_threshold) continue;
+    std::string cig;
+    for (u32 c : r->cigar) { cig += std::to_string(c >> 4); cig.push_back("MIDNSHP=XB"[c & 0xf]); }
+    if (cig.empty()) cig = "*";
+    const std::string mate = r->mrid < 0 ? "*" : (r->mrid == r->rid ? "=" : ref->names[r->mrid]);
+    fprintf(f, "%s\t%d\t%s\t%lld\t%d\t%s\t%s\t%lld\t%d\t%s\t%s\tNM:i:%d\tMD:Z:%s\n", r->name.c_str(), r->flag, ref->names[r->rid].c_str(), (long long)r->pos + 1,
+            r->mapq, cig.c_str(), mate.c_str(), r->mrid < 0 ? 0LL : (long long)r->mpos + 1, r->tlen, r->seq.c_str(), r->qual.c_str(), r->nm, r->md.c_str());
+  }
+  fclose(f);
+  orc_index_free(ix); orc_reference_free(ref);
   return 0;
 }
 

@@ -189,6 +189,10 @@ int64_t orc_format_tagalign(const orc_reference *ref, const orc_pe_record *recs,
 int64_t orc_map_reads_se_bc(orc_mapper *m, uint32_t n, const char *seq, const uint32_t *off, const char *bcs, const char *quals, uint32_t bc_len,
                             uint32_t first_read_id, orc_pe_record *out, uint64_t *out_bc, int64_t cap_out, int n_threads, uint64_t *bc_stats);
 
+// chromap --SAM for bulk reads, non-split (oracle only: groundwork for SURVEY.md 8f rank 3; read2_path NULL/"" = single-end).
+int orc_run_files_sam(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                      const char *out_path);
+
 #ifdef __cplusplus
 }
 #endif

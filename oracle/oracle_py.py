@@ -91,6 +91,7 @@ def lib():
         L.orc_format_bed_bc.restype = i64; L.orc_format_bed_bc.argtypes = [vp, vp, vp, i64, u32, vp, i64]
         L.orc_run_files_bc.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 7 + [i32, vp]
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.orc_run_files_sam.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5
         L.orc_map_reads_se_bc.restype = i64; L.orc_map_reads_se_bc.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32, vp, vp, i64, i32, vp]
         L.orc_map_reads_se.restype = i64; L.orc_map_reads_se.argtypes = [vp, u32, vp, vp, u32, vp, i64, i32]
         L.orc_postprocess_se.restype = i64; L.orc_postprocess_se.argtypes = [C.POINTER(Params), vp, i64]
@@ -276,6 +277,12 @@ def run_files_se(params, index_path, ref_path, r1, out, n_threads=1):
     rc = lib().orc_run_files_se(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), out.encode(), n_threads)
     if rc != 0:
         raise RuntimeError("orc_run_files_se failed: %d" % rc)
+
+
+def run_files_sam(params, index_path, ref_path, r1, r2, out):
+    rc = lib().orc_run_files_sam(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), (r2 or "").encode(), out.encode())
+    if rc != 0:
+        raise RuntimeError("orc_run_files_sam failed: %d" % rc)
 
 
 class Whitelist:

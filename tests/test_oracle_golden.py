@@ -214,3 +214,27 @@ def test_single_end_barcoded_oracle_reproduces_reference_bed(golden_dir, case):
     recs, obc, _ = orc.map_reads_se_bc(p, idx, ref, s1, o1, bcs, quals, bc_len, whitelist=wl, n_threads=2)
     r2, b2 = orc.postprocess_bc(p, recs, obc)
     assert orc.format_bed_bc(ref, r2, b2, bc_len) == gzip.open(os.path.join(d, case + ".bed.gz")).read()
+
+
+SAM_CASES = {
+    "pe_chip": (dict(preset="chip"), True),
+    "pe_q0d": (dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1), True),
+    "se_n3": (dict(preset="", max_num_best_mappings=3, mapq_threshold=0), False),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SAM_CASES))
+def test_sam_oracle_reproduces_reference(golden_dir, tmp_path, case):
+    """chromap --SAM (ksw_semi_global3 CIGARs, NM / MD, flags, mate fields): groundwork for the round-2 CUDA path; the
+    oracle's text equals the reference binary's, header included."""
+    d = os.path.join(golden_dir, "synth_small")
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    ip = str(tmp_path / "ref.index")
+    idx.save(ip)
+    kw, paired = SAM_CASES[case]
+    kw = dict(kw)
+    p = orc.make_params(kw.pop("preset"), **kw)
+    out = str(tmp_path / "out.sam")
+    orc.run_files_sam(p, ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), os.path.join(d, "read2.fq.gz") if paired else None, out)
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".sam.gz")).read()
