@@ -4,8 +4,8 @@ Thin ctypes view of the C ABI in include/chromap_b200.h (chromap_b200/libchromap
 `__graft_entry__.build()` / chromap_b200/csrc/Makefile).  There is no CPU fallback: importing works
 anywhere, but creating a Mapper without the CUDA library or without a GPU raises.
 """
-from .binding import (Mapper, Params, PE_RECORD, PAIRS_RECORD, PAIR_TRACE, Timing, CmxError, lib_path, load_library,
-                      make_params, taskloop_chunks)
+from .binding import (Mapper, Params, PE_RECORD, PAIRS_RECORD, PAIR_TRACE, SAM_RECORD, Timing, CmxError, lib_path, load_library,
+                      make_params, taskloop_chunks, format_sam)
 
-__all__ = ["Mapper", "Params", "PE_RECORD", "PAIRS_RECORD", "PAIR_TRACE", "Timing", "CmxError", "lib_path", "load_library",
+__all__ = ["format_sam", "Mapper", "Params", "PE_RECORD", "PAIRS_RECORD", "PAIR_TRACE", "SAM_RECORD", "Timing", "CmxError", "lib_path", "load_library",
            "make_params", "taskloop_chunks"]

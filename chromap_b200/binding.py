@@ -24,6 +24,48 @@ class Params(C.Structure):
         "batch_size", "max_read_length", "single_end")]
 
 
+SAM_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("pos", "<u4", 2), ("end", "<u4", 2), ("strand", "u1", 2), ("mapq", "u1"), ("is_unique", "u1"),
+                       ("secondary", "u1"), ("n_cigar", "u1", 2), ("overflow", "u1"), ("cigar", "<u4", (2, 24))], align=True)
+
+
+class ReadSet(C.Structure):
+    _fields_ = [("names", C.c_void_p), ("seq", C.c_void_p), ("off", C.c_void_p), ("qual", C.c_void_p)]
+
+
+def format_sam(params, ref_names, ref_seqs, records, reads1, reads2=None, first_read_id=0):
+    """SAM text from SAM cores (host only).  ref_seqs: list of uint8 arrays; reads*: (names, seqs, quals) lists of bytes."""
+    L = load_library()
+    names = (C.c_char_p * len(ref_names))(*[s.encode() if isinstance(s, str) else s for s in ref_names])
+    lens = np.array([len(s) for s in ref_seqs], dtype=np.uint32)
+    concat = np.concatenate(ref_seqs).astype(np.uint8)
+    roff = np.zeros(len(ref_seqs) + 1, dtype=np.uint64)
+    roff[1:] = np.cumsum(lens.astype(np.uint64))
+    keep = []
+
+    def read_set(r):
+        if r is None:
+            return None
+        nm, sq, ql = r
+        arr = (C.c_char_p * len(nm))(*nm)
+        seq = np.frombuffer(b"".join(sq), dtype=np.uint8)
+        off = np.zeros(len(sq) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in sq])
+        qual = np.frombuffer(b"".join(ql), dtype=np.uint8) if ql is not None else None
+        keep.extend([arr, seq, off, qual])
+        return ReadSet(C.cast(arr, C.c_void_p), seq.ctypes.data, off.ctypes.data, qual.ctypes.data if qual is not None else None)
+
+    r1, r2 = read_set(reads1), read_set(reads2)
+    recs = np.ascontiguousarray(records)
+    args = (C.byref(params), names, lens.ctypes.data, len(ref_names), concat.ctypes.data, roff.ctypes.data, recs.ctypes.data, len(recs), C.byref(r1),
+            C.byref(r2) if r2 is not None else None, first_read_id)
+    n = L.cmx_format_sam(*args, None, 0)
+    if n < 0:
+        raise CmxError("cmx_format_sam failed (%d)" % n)
+    buf = C.create_string_buffer(n + 1)
+    assert L.cmx_format_sam(*args, buf, n) == n
+    return buf.raw[:n]
+
+
 class Ingested(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("seq", C.c_void_p), ("off", C.c_void_p), ("qual", C.c_void_p), ("min_len", C.c_uint32), ("max_len", C.c_uint32)]
 
@@ -113,6 +155,8 @@ def load_library():
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
     L.cmx_set_lanes.argtypes = [vp, i32]
+    L.cmx_format_sam.restype = i64
+    L.cmx_format_sam.argtypes = [C.POINTER(Params), vp, vp, u32, vp, vp, vp, u64, C.POINTER(ReadSet), C.POINTER(ReadSet), u32, vp, i64]
     L.cmx_fastq_cut.restype = u64; L.cmx_fastq_cut.argtypes = [vp, u64, u32, C.POINTER(u32)]
     L.cmx_ingest_fastq.argtypes = [vp, i32, vp, u64, i32, vp, C.POINTER(Ingested)]
     _lib = L
@@ -239,7 +283,7 @@ class Mapper:
                   _ptr(barcodes), _ptr(barcode_quals), bc_len if barcodes is not None else 0)
         mb = self.params.max_num_best_mappings
         if out is None:
-            out = np.zeros(n * mb, dtype=PAIRS_RECORD if self.params.output_format == 5 else PE_RECORD)
+            out = np.zeros(n * mb, dtype=PAIRS_RECORD if self.params.output_format == 5 else SAM_RECORD if self.params.output_format == 4 else PE_RECORD)
         cap = (out.numel() * out.element_size() // 24) if hasattr(out, "data_ptr") else len(out)
         bck = np.zeros(cap, dtype=np.uint64) if (barcodes is not None and not out_on_device) else None
         r = Records(_ptr(out), cap, 0, 1 if out_on_device else 0, 0, 0, 0, 0, _ptr(bck), 0, 0)

@@ -21,11 +21,13 @@
 #include "index_build.cuh"
 #include "pipeline_kernels.cuh"
 #include "postprocess.cuh"
+#include "sam_kernels.cuh"
 #include "ingest.cuh"
 
 static_assert(sizeof(OutRecord) == sizeof(cmx_pe_record), "record layout");
 static_assert(sizeof(cmx_pe_record) == 24, "record size");
 static_assert(sizeof(OutPairs) == 24 && sizeof(cmx_pairs_record) == 24, "pairs record size");
+static_assert(sizeof(OutSam) == sizeof(cmx_sam_record) && sizeof(OutSam) % 4 == 0 && SAM_MAX_CIGAR == CMX_SAM_MAX_CIGAR, "SAM record layout");
 
 #define N_TIERS 3
 
@@ -169,8 +171,10 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   *out = nullptr;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device >= n_dev) return CMX_ERR_NO_DEVICE;
-  if (!(((params->output_format == 1 || params->output_format == 2) && !params->split_alignment) || (params->output_format == 5 && params->split_alignment)))
-    return CMX_ERR_INVALID;  // BED / TagAlign (same records), or Hi-C pairs with split alignment
+  if (!(((params->output_format == 1 || params->output_format == 2 || params->output_format == 4) && !params->split_alignment) ||
+        (params->output_format == 5 && params->split_alignment)))
+    return CMX_ERR_INVALID;  // BED / TagAlign (same records), SAM cores, or Hi-C pairs with split alignment
+  if (params->output_format == 4 && (params->max_read_length > SAM_MAX_L || params->error_threshold > SAM_MAX_E)) return CMX_ERR_INVALID;
   if (params->error_threshold < 1 || params->error_threshold >= 16) return CMX_ERR_INVALID;  // mapping_parameters.h:80-88
   if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
   if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
@@ -597,10 +601,12 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   MapqTables T;
   T.inv_log = ctx->inv_log; T.pen_thr = ctx->pen_thr;
   CUL(ensure(L.nbest, (size_t)n * 4)); CUL(ensure(L.sel, (size_t)n * mb * 4));
-  CUL(ensure(L.out_rec, (size_t)n * mb * sizeof(OutRecord))); CUL(ensure(L.out_n, (size_t)(n + 1) * 4));
+  const bool sam = ctx->params.output_format == 4;
+  const size_t rec_bytes = sam ? sizeof(OutSam) : sizeof(OutRecord);
+  CUL(ensure(L.out_rec, (size_t)n * mb * rec_bytes)); CUL(ensure(L.out_n, (size_t)(n + 1) * 4));
   CUL(ensure(L.offs, (size_t)(n + 1) * 8));
   OutRecord *dst = J.dst;
-  if (!dst) { CUL(ensure(L.out_compact, (size_t)n * mb * sizeof(OutRecord))); dst = (OutRecord *)L.out_compact.p; }
+  if (!dst) { CUL(ensure(L.out_compact, (size_t)n * mb * rec_bytes)); dst = (OutRecord *)L.out_compact.p; }
   J.dst = dst;
   u64 *bc_dst = nullptr;
   if (J.want_bc && J.bc_seq) { CUL(ensure(L.bc_out, (size_t)n * mb * 8)); bc_dst = (u64 *)L.bc_out.p; }
@@ -743,6 +749,8 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     cudaStream_t es = t == 0 ? st : L.aux[t - 1];
     if (t > 0) CUL(cudaStreamWaitEvent(es, L.ev_fork, 0));
     if (P.split) emit_split_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutPairs *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else if (sam && P.se) emit_sam_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutSam *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else if (sam) emit_sam_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutSam *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else if (P.se) emit_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     if (t > 0) CUL(cudaEventRecord(L.ev_join[t - 1], es));
@@ -755,7 +763,8 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   CUL(ensure(L.cub_tmp, tmp_bytes));
   // out_n has n entries plus one trailing zero so that offs[n] = total
   cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tmp_bytes, (const int *)L.out_n.p, (u64 *)L.offs.p, (int)n + 1, st);
-  compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)L.out_rec.p, (const int *)L.out_n.p, (const u64 *)L.offs.p, dst);
+  if (sam) compact_words_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (int)(rec_bytes / 4), (const u32 *)L.out_rec.p, (const int *)L.out_n.p, (const u64 *)L.offs.p, (u32 *)dst);
+  else compact_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, mb, (const OutRecord *)L.out_rec.p, (const int *)L.out_n.p, (const u64 *)L.offs.p, dst);
   acc.launches += 2;
   if (bc_dst) {
     compact_bc_kernel<<<(n + 255) / 256, 256, 0, st>>>((int)n, (const int *)L.out_n.p, (const u64 *)L.offs.p, (const u64 *)L.bc_key.p, bc_dst);
@@ -778,7 +787,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   }
   for (int t = 0; t < N_TIERS; ++t) if (t < tiers_used) acc.tier_pairs[t] += (u64)L.tiers[t].n_slots;
   acc.tiers_used = std::max(acc.tiers_used, tiers_used);
-  acc.n_overflow += n_overflow_final;
+  acc.n_overflow += n_overflow_final + (sam ? hc.n_overflow : 0);  // SAM: reads / CIGARs beyond the fixed record
   J.total = total;
   L.tiers_used = tiers_used;
   return CMX_OK;
@@ -859,6 +868,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   // counts are known as soon as those lanes have finished mapping), so the copies of early lanes overlap later lanes
   std::atomic<int> mapped[CMX_MAX_LANES];
   for (auto &f : mapped) f.store(0);
+  const size_t rec_bytes = ctx->params.output_format == 4 ? sizeof(OutSam) : sizeof(OutRecord);
   auto lane_main = [&](int l) {
     LaneJob &J = jobs[l];
     Lane &L = ctx->lanes[l];
@@ -873,7 +883,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
     if (J.rc || !J.total) return;
     cudaError_t e = cudaSuccess;
     if ((void *)J.dst != (void *)out->records)
-      e = cudaMemcpyAsync((OutRecord *)out->records + before, J.dst, J.total * sizeof(OutRecord), out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L.stream);
+      e = cudaMemcpyAsync((char *)out->records + before * rec_bytes, J.dst, J.total * rec_bytes, out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L.stream);
     if (e == cudaSuccess && J.want_bc) e = cudaMemcpyAsync(out->barcode_keys + before, L.bc_out.p, J.total * 8, cudaMemcpyDeviceToHost, L.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
     if (e != cudaSuccess) { L.err = std::string("record copy: ") + cudaGetErrorString(e); J.rc = CMX_ERR_CUDA; }

@@ -30,12 +30,14 @@ static double Now() { return std::chrono::duration<double>(std::chrono::steady_c
 struct Batch {
   std::string s1, s2;
   std::vector<uint32_t> o1{0}, o2{0};
-  std::vector<std::string> names1;  // read-1 names, kept for pairs output only
+  std::vector<std::string> names1;  // read-1 names, kept for pairs / SAM output only
+  std::vector<std::string> names2;  // SAM only
+  std::string q1, q2;               // qualities in the layout of s1 / s2 (SAM only)
   std::string bc, bq;               // cell barcodes + qualities, bc_len bytes per pair (scATAC)
   uint32_t n = 0, first_id = 0;
   bool dev = false;      // reads were packed on the device (cmx_ingest_fastq): dev_in holds device pointers
   cmx_batch dev_in{};
-  void Clear() { dev = false; s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); bc.clear(); bq.clear(); n = 0; }
+  void Clear() { dev = false; s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); names2.clear(); q1.clear(); q2.clear(); bc.clear(); bq.clear(); n = 0; }
 };
 
 // Raw text of one read file for the device-side FASTQ parser: gzread() (plain or gzip) into a growing buffer; whole
@@ -114,18 +116,18 @@ static uint64_t BarcodeSeed(const std::string &s) {
 }
 
 static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batch *b, bool keep_names, SeqReader *rb = nullptr, uint32_t bc_len = 0,
-                          bool se = false) {
+                          bool se = false, bool keep_sam = false) {
   std::string n, s, q;
   b->Clear();
   while (b->n < max_pairs) {
     bool a = r1.Next(&n, &s, &q);
     while (a && s.empty()) a = r1.Next(&n, &s, &q);
-    if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); if (keep_names) b->names1.push_back(n); }
+    if (a) { b->s1 += s; b->o1.push_back((uint32_t)b->s1.size()); if (keep_names) b->names1.push_back(n); if (keep_sam) { q.resize(s.size(), 'I'); b->q1 += q; } }
     bool c = a;  // single-end: no second file
     if (!se) {
       c = r2.Next(&n, &s, &q);
       while (c && s.empty()) c = r2.Next(&n, &s, &q);
-      if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); }
+      if (c) { b->s2 += s; b->o2.push_back((uint32_t)b->s2.size()); if (keep_sam) { b->names2.push_back(n); q.resize(s.size(), 'I'); b->q2 += q; } }
     }
     bool d = c;
     if (rb) {
@@ -208,14 +210,16 @@ int main(int argc, char **argv) {
              a == "-p" || a == "--matrix-output-prefix")
       Die("chromap-b200: option " + a + " changes the output in ways that are not on the GPU path; use the reference chromap for it");
     else if (a == "--TagAlign") p.output_format = 2;  // same records as BED, TagAlign / PairedTagAlign text (chromap_driver.cc:417-418)
-    else if (a == "--SAM" || a == "--PAF" || a == "--summary")
+    else if (a == "--SAM") p.output_format = 4;  // device: ksw spans, CIGARs, MAPQ; host: flags, NM / MD, order, text (cmx_format_sam)
+    else if (a == "--PAF" || a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
   (void)bed; (void)user_set_format;
-  if (!(((p.output_format == 1 || p.output_format == 2) && !p.split_alignment) || (p.output_format == 5 && p.split_alignment)))
+  if (!(((p.output_format == 1 || p.output_format == 2 || p.output_format == 4) && !p.split_alignment) || (p.output_format == 5 && p.split_alignment)))
     Die("chromap-b200: supported outputs are BED / TagAlign (no split alignment) and Hi-C pairs (--split-alignment --pairs / --preset hic)");
   const bool tagalign = p.output_format == 2;
+  const bool sam = p.output_format == 4;
   const bool pairs = p.output_format == 5;
   cmx_ctx *ctx = nullptr;
   const double t_start = Now();
@@ -246,7 +250,7 @@ int main(int argc, char **argv) {
   if (r1_path.empty()) Die("No read file specified!");
   const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
   if (se && pairs) Die("chromap-b200: pairs output needs paired-end reads");
-  if (tagalign && !bc_path.empty()) Die("chromap-b200: --TagAlign with barcodes is not on the GPU path");
+  if ((tagalign || sam) && !bc_path.empty()) Die("chromap-b200: --TagAlign / --SAM with barcodes is not on the GPU path");
   if (!bc_path.empty() && p.remove_pcr_duplicates && p.low_memory_mode && !cell_level_dedup)  // mapping_writer.h:254-262: only the low-memory merge has the bulk-level variant
     Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");
@@ -311,7 +315,7 @@ int main(int argc, char **argv) {
   SeqReader r1, r2, rb;
   RawFile g1, g2, gb;
   Batch cur, next;
-  bool gpu_reader = !host_reader;
+  bool gpu_reader = !host_reader && !sam;  // SAM keeps names, bases and qualities of every read on the host
   auto open_all = [&](bool raw) {
     if (raw) {
       if (!g1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
@@ -328,7 +332,7 @@ int main(int argc, char **argv) {
     if (gpu_reader) {
       if (!LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, par, (uint32_t)p.batch_size, b, pairs, bc_len))
         Die(std::string("chromap-b200: the read files are not plain 4-line FASTQ (") + cmx_last_error(ctx) + "); rerun with --host-reader");
-    } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs, sc ? &rb : nullptr, bc_len, se);
+    } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs || sam, sc ? &rb : nullptr, bc_len, se, sam);
   };
   open_all(gpu_reader);
   if (gpu_reader && !LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, parity, (uint32_t)p.batch_size, &cur, pairs, bc_len)) {
@@ -341,7 +345,10 @@ int main(int argc, char **argv) {
   uint64_t n_pairs = 0, n_mapped = 0, n_unique = 0, n_cand = 0;
   const double t_map = Now();
   uint32_t read_id = 0;
-  std::vector<std::string> all_names;
+  std::vector<std::string> all_names, all_names2;
+  std::vector<cmx_sam_record> sam_recs, all_sam;
+  std::string sam_s1, sam_q1, sam_s2, sam_q2;
+  std::vector<uint64_t> sam_off1{0}, sam_off2{0};
   std::vector<uint64_t> all_bc, bc_keys;
   uint64_t n_bc_in = 0, n_bc_cor = 0;
   if (!gpu_reader) load(&cur, parity);
@@ -359,11 +366,18 @@ int main(int argc, char **argv) {
     in.first_read_id = cur.first_id;
     cmx_records out{};
     out.records = recs.data(); out.capacity = recs.size();
+    if (sam) { sam_recs.resize(recs.size()); out.records = reinterpret_cast<cmx_pe_record *>(sam_recs.data()); }
     if (sc) { bc_keys.resize(recs.size()); out.barcode_keys = bc_keys.data(); }
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, se ? "Mapped %u reads in %.2fs.\n" : "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
-    all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
+    if (sam) {
+      all_sam.insert(all_sam.end(), sam_recs.begin(), sam_recs.begin() + out.n_records);
+      for (uint32_t i = 0; i < cur.n; ++i) { sam_off1.push_back(sam_off1.back() + (cur.o1[i + 1] - cur.o1[i])); if (!se) sam_off2.push_back(sam_off2.back() + (cur.o2[i + 1] - cur.o2[i])); }
+      sam_s1 += cur.s1; sam_q1 += cur.q1; sam_s2 += cur.s2; sam_q2 += cur.q2;
+      all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
+      all_names2.insert(all_names2.end(), cur.names2.begin(), cur.names2.end());
+    } else all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
     if (pairs) all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
     if (sc) { all_bc.insert(all_bc.end(), bc_keys.begin(), bc_keys.begin() + out.n_records); n_bc_in += out.n_barcodes_in_whitelist; n_bc_cor += out.n_barcodes_corrected; }
     n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
@@ -381,7 +395,23 @@ int main(int argc, char **argv) {
   for (const auto &s : ref.names) names.push_back(s.c_str());
   std::vector<char> text;
   int64_t bytes = 0;
-  if (pairs) {
+  if (sam) {
+    std::vector<const char *> n1, n2;
+    for (const auto &x : all_names) n1.push_back(x.c_str());
+    for (const auto &x : all_names2) n2.push_back(x.c_str());
+    std::vector<uint32_t> lens;
+    for (size_t i = 0; i + 1 < ref.offsets.size(); ++i) lens.push_back((uint32_t)(ref.offsets[i + 1] - ref.offsets[i]));
+    cmx_read_set rs1{n1.data(), sam_s1.data(), sam_off1.data(), sam_q1.data()}, rs2{n2.data(), sam_s2.data(), sam_off2.data(), sam_q2.data()};
+    bytes = cmx_format_sam(&p, names.data(), lens.data(), (uint32_t)names.size(), ref.concat.data(), ref.offsets.data(), all_sam.data(), all_sam.size(), &rs1,
+                           se ? nullptr : &rs2, 0, nullptr, 0);
+    if (bytes < 0) Die("chromap-b200: cmx_format_sam failed");
+    text.resize((size_t)bytes + 1);
+    cmx_format_sam(&p, names.data(), lens.data(), (uint32_t)names.size(), ref.concat.data(), ref.offsets.data(), all_sam.data(), all_sam.size(), &rs1,
+                   se ? nullptr : &rs2, 0, text.data(), bytes);
+    keep = 0;
+    for (int64_t i = 0; i < bytes; ++i) keep += text[(size_t)i] == '\n';
+    keep -= names.size();
+  } else if (pairs) {
     cmx_pairs_record *pr = reinterpret_cast<cmx_pairs_record *>(all.data());
     if (cmx_postprocess_gpu(ctx, pr, nullptr, all.size(), &keep) && cmx_postprocess_pairs(ctx, pr, all.size(), &keep)) Die(cmx_last_error(ctx));
     std::vector<const char *> rn;

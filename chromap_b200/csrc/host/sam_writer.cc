@@ -1,0 +1,110 @@
+// chromap_b200 host side — SAM text from the device's SAM cores (cmx_sam_record): flags, mate fields and TLEN
+// (mapping_generator.h:613-640, mapping_generator.cc:84-107), NM / MD (alignment.cc:85-139), record order, duplicate
+// removal and MAPQ filter (sam_mapping.h:188-199, mapping_processor.h:161-202, mapping_writer.h:166-376, :405-437) and the
+// lines themselves (mapping_writer.cc:312-356).  No device needed.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../../include/chromap_b200.h"
+
+namespace {
+struct Line {
+  const cmx_sam_record *core;
+  int mate;  // 0 / 1: which span of the core
+  int64_t pos, mpos;
+  int rid, mrid, flag, tlen, mapq;
+  uint32_t read_id;
+};
+inline int BaseCode(char c) {  // utils.h:87-104
+  switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+}  // namespace
+
+extern "C" int64_t cmx_format_sam(const cmx_params *p, const char *const *ref_names, const uint32_t *ref_lengths, uint32_t n_seq, const char *ref_concat,
+                                  const uint64_t *ref_offsets, const cmx_sam_record *records, uint64_t n, const cmx_read_set *reads1,
+                                  const cmx_read_set *reads2, uint32_t first_read_id, char *buf, int64_t cap) {
+  if (!p || !ref_names || !ref_lengths || !ref_concat || !ref_offsets || (!records && n) || !reads1) return -1;
+  const bool pe = reads2 != nullptr;
+  std::vector<Line> lines;
+  lines.reserve(n * (pe ? 2 : 1));
+  for (uint64_t i = 0; i < n; ++i) {
+    const cmx_sam_record &c = records[i];
+    if (c.overflow) return -2;
+    if (!pe) {
+      lines.push_back({&c, 0, (int64_t)c.pos[0], 0, (int)c.rid, -1, (c.strand[0] ? 0 : 16) | (c.secondary ? 256 : 0), 0, (int)c.mapq, c.read_id});
+      continue;
+    }
+    int f1 = 3 | 64, f2 = 3 | 128;
+    if (!c.strand[0]) { f1 |= 16; f2 |= 32; }
+    if (!c.strand[1]) { f1 |= 32; f2 |= 16; }
+    if (c.secondary) { f1 |= 256; f2 |= 256; }
+    const int tlen = c.strand[0] ? (int)(c.end[1] - c.pos[0] + 1u) : (int)(c.end[0] - c.pos[1] + 1u);  // PairedEndMappingInMemory::GetFragmentLength
+    lines.push_back({&c, 0, (int64_t)c.pos[0], (int64_t)c.pos[1], (int)c.rid, (int)c.rid, f1, c.strand[0] ? tlen : -tlen, (int)c.mapq, c.read_id});
+    lines.push_back({&c, 1, (int64_t)c.pos[1], (int64_t)c.pos[0], (int)c.rid, (int)c.rid, f2, c.strand[1] ? tlen : -tlen, (int)c.mapq, c.read_id});
+  }
+  auto key = [](const Line &l) { return std::make_tuple(l.rid, l.pos, l.mrid, l.mpos, l.flag & 64, l.mapq, l.read_id); };
+  std::stable_sort(lines.begin(), lines.end(), [&](const Line &a, const Line &b) { return key(a) < key(b); });
+  auto same = [](const Line &a, const Line &b) { return a.rid == b.rid && a.pos == b.pos && (a.flag & 64) == (b.flag & 64) && a.mrid == b.mrid && a.mpos == b.mpos; };
+  std::vector<const Line *> keep;
+  if (p->remove_pcr_duplicates) {
+    size_t i = 0;
+    while (i < lines.size()) {
+      size_t j = i + 1, k = i;
+      for (; j < lines.size() && same(lines[j], lines[j - 1]); ++j) {
+        if (p->low_memory_mode) { if (lines[j].mapq > lines[k].mapq) k = j; } else k = j;
+      }
+      keep.push_back(&lines[k]);
+      i = j;
+    }
+  } else for (const Line &l : lines) keep.push_back(&l);
+  int64_t len = 0;
+  auto put = [&](const std::string &s) {
+    if (buf && len + (int64_t)s.size() <= cap) memcpy(buf + len, s.data(), s.size());
+    len += (int64_t)s.size();
+  };
+  for (uint32_t i = 0; i < n_seq; ++i) put(std::string("@SQ\tSN:") + ref_names[i] + "\tLN:" + std::to_string(ref_lengths[i]) + "\n");
+  std::string seq, qual, cig, md, out;
+  for (const Line *l : keep) {
+    if (l->mapq < p->mapq_threshold) continue;
+    const cmx_sam_record &c = *l->core;
+    const cmx_read_set &rs = l->mate == 0 ? *reads1 : *reads2;
+    const uint32_t ri = c.read_id - first_read_id;
+    const char *rseq = rs.seq + rs.off[ri];
+    const size_t rl = (size_t)(rs.off[ri + 1] - rs.off[ri]);
+    const bool plus = c.strand[l->mate] != 0;
+    if (plus) seq.assign(rseq, rl);
+    else {  // PrepareNegativeSequenceAt (sequence_batch.h:123-134)
+      seq.resize(rl);
+      for (size_t q = 0; q < rl; ++q) { const int b = BaseCode(rseq[rl - 1 - q]); seq[q] = b < 4 ? "ACGT"[3 - b] : 'N'; }
+    }
+    qual.clear();
+    if (rs.qual) { qual.assign(rs.qual + rs.off[ri], rl); if (!plus) std::reverse(qual.begin(), qual.end()); }
+    cig.clear(); md.clear();
+    int nm = 0, nmatch = 0;
+    size_t rpos = 0, gpos = 0;
+    const char *g = ref_concat + ref_offsets[c.rid] + c.pos[l->mate];
+    for (int q = 0; q < c.n_cigar[l->mate]; ++q) {  // GenerateNMAndMDTag
+      const uint32_t op = c.cigar[l->mate][q] & 0xf, ol = c.cigar[l->mate][q] >> 4;
+      cig += std::to_string(ol); cig.push_back("MIDNSHP=XB"[op]);
+      if (op == 0) {
+        for (uint32_t t = 0; t < ol; ++t, ++rpos, ++gpos) {
+          if (g[gpos] == seq[rpos] || g[gpos] - 'a' + 'A' == seq[rpos]) ++nmatch;
+          else { ++nm; md += std::to_string(nmatch); nmatch = 0; md.push_back(g[gpos]); }
+        }
+      } else if (op == 1) { nm += (int)ol; rpos += ol; }
+      else { nm += (int)ol; md += std::to_string(nmatch); nmatch = 0; md.push_back('^'); for (uint32_t t = 0; t < ol; ++t) md.push_back(g[gpos++]); }
+    }
+    md += std::to_string(nmatch);
+    if (cig.empty()) cig = "*";
+    out.assign(rs.names[ri]);
+    out += "\t" + std::to_string(l->flag) + "\t" + ref_names[l->rid] + "\t" + std::to_string(l->pos + 1) + "\t" + std::to_string(l->mapq) + "\t" + cig + "\t";
+    out += l->mrid < 0 ? "*" : (l->mrid == l->rid ? "=" : ref_names[l->mrid]);
+    out += "\t" + std::to_string(l->mrid < 0 ? 0 : l->mpos + 1) + "\t" + std::to_string(l->tlen) + "\t" + seq + "\t" + qual + "\tNM:i:" + std::to_string(nm) + "\tMD:Z:" + md + "\n";
+    put(out);
+  }
+  return len;
+}

@@ -45,7 +45,7 @@ typedef struct {
   int32_t tn5_shift;
   int32_t split_alignment;        /* --split-alignment (Hi-C); requires output_format == 5 */
   int32_t low_memory_mode;
-  int32_t output_format;          /* 1 = BED, 2 = TagAlign (same records, other text), 5 = pairs (mapping_parameters.h:9-16) */
+  int32_t output_format;          /* 1 = BED, 2 = TagAlign (same records), 4 = SAM cores (cmx_sam_record), 5 = pairs (mapping_parameters.h:9-16) */
   int32_t batch_size;             /* pairs per reference batch (chromap.h:182: 500000); fixes the
                                      taskloop chunking that seeds multi-mapper sampling */
   int32_t max_read_length;        /* upper bound on read length in any batch (sizing), default 160 */
@@ -130,6 +130,23 @@ typedef struct {
   uint8_t strand1, strand2; /* 1 = + */
   uint8_t mapq, is_unique;
 } cmx_pairs_record;
+
+/* output_format == 4 (MAPPINGFORMAT_SAM): what the SAM writer needs from the device for one reported pair (paired-end) or
+ * read (single-end, index 0 only): the spans and CIGARs ksw_semi_global3 gives (ksw.cc:505-626 through
+ * mapping_generator.h:723-760,807-855), MAPQ computed from those spans, strands.  Flags, TLEN, NM / MD and the text follow on
+ * the host from these fields (mapping_generator.h:613-640, mapping_generator.cc:84-107, alignment.cc:85-139).  Written into
+ * the records buffer, which must then hold capacity * sizeof(cmx_sam_record) bytes.  Non-split, reads <= 160 bases. */
+#define CMX_SAM_MAX_CIGAR 24
+typedef struct {
+  uint32_t read_id, rid;
+  uint32_t pos[2], end[2]; /* 0-based inclusive reference span of mate 1 / mate 2 */
+  uint8_t strand[2];       /* 1 = + */
+  uint8_t mapq, is_unique;
+  uint8_t secondary;       /* not the first reported mapping of this read (BAM_FSECONDARY) */
+  uint8_t n_cigar[2];
+  uint8_t overflow;        /* the call also returns CMX_ERR_OVERFLOW: read or CIGAR beyond the fixed record */
+  uint32_t cigar[2][CMX_SAM_MAX_CIGAR]; /* BAM encoding: length << 4 | op, M = 0, I = 1, D = 2 */
+} cmx_sam_record;
 
 typedef struct {
   cmx_pe_record *records; /* caller-owned, capacity >= n_pairs * max_num_best_mappings (cmx_pairs_record when pairs) */
@@ -243,6 +260,21 @@ typedef struct {
 } cmx_ingested;
 uint64_t cmx_fastq_cut(const char *text, uint64_t n_bytes, uint32_t max_records, uint32_t *n_records);
 int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes, int want_qual, uint32_t *name_spans, cmx_ingested *out);
+
+/* SAM text from the cores (host only, no device): expands them to one line per mate, puts them in SAMMapping's order,
+ * removes duplicates / filters by MAPQ as the context's parameters say (sam_mapping.h:188-199, mapping_processor.h:161-202,
+ * mapping_writer.h:166-376,405-437) and writes the @SQ header + lines of mapping_writer.cc:312-356 (flags, mate fields, TLEN,
+ * SEQ / QUAL of the mapped strand, NM / MD from the CIGAR).  reads1 / reads2: names, bases and qualities (qual may be NULL)
+ * of reads first_read_id .. ; reads2 == NULL for single-end.  buf == NULL returns the length; < 0 on error. */
+typedef struct {
+  const char *const *names; /* [n_reads] */
+  const char *seq;          /* bases, concatenated */
+  const uint64_t *off;      /* [n_reads + 1] */
+  const char *qual;         /* qualities in the same layout, or NULL */
+} cmx_read_set;
+int64_t cmx_format_sam(const cmx_params *p, const char *const *ref_names, const uint32_t *ref_lengths, uint32_t n_seq, const char *ref_concat,
+                       const uint64_t *ref_offsets, const cmx_sam_record *records, uint64_t n, const cmx_read_set *reads1,
+                       const cmx_read_set *reads2, uint32_t first_read_id, char *buf, int64_t cap);
 
 /* Concurrency of one cmx_map_batch_pe call (no counterpart in the reference, whose knob is -t): a call that carries
  * several whole reference batches is cut into up to n_lanes (1..4, default 4) groups of batches that run the whole

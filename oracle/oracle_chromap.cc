@@ -2232,4 +2232,52 @@ int orc_run_files_sam(const orc_params *p, const char *index_path, const char *r
   return 0;
 }
 
+
+// test hook: the oracle's sg_align on raw buffers (checks the device-side restatement compiled for the host)
+int orc_sg_align_test(const char *win, int wlen, const char *read, int rlen, int w, unsigned *cigar, int cap, int *start, int *end) {
+  SamAln a;
+  sg_align(win, wlen, read, rlen, 1, 4, 6, 1, 6, 1, w, a);
+  *start = a.start; *end = a.end;
+  int n = 0;
+  for (u32 c : a.cigar) if (n < cap) cigar[n++] = c;
+  return (int)a.cigar.size();
+}
+
+
+// SAM cores in the layout of cmx_sam_record (include/chromap_b200.h) for the device parity tests: one per reported pair
+// (paired-end: seq2 != NULL) or read.
+int64_t orc_map_sam_cores(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2, const uint32_t *off2, uint32_t first_read_id,
+                          orc_sam_record *out, int64_t cap_out) {
+  std::vector<u32> st(n / 5000 + 2), en(n / 5000 + 2);
+  const int nt = orc_ref_task_chunks(n, st.data(), en.data(), (int)st.size());
+  const bool se = seq2 == nullptr;
+  int64_t n_out = 0;
+  orc_pe_record dummy[8];
+  for (int t = 0; t < nt; ++t) {
+    std::mt19937 gen(11);
+    for (u32 i = st[t]; i < en[t]; ++i) {
+      std::vector<SamRec> recs;
+      SamSink sink{&recs, "", "", "", ""};
+      if (se) map_one_read_se(m->P, *m->ix, *m->ref, seq1 + off1[i], off1[i + 1] - off1[i], first_read_id + i, i, dummy, 8, &sink);
+      else map_one_pair(m->P, *m->ix, *m->ref, gen, seq1 + off1[i], off1[i + 1] - off1[i], seq2 + off2[i], off2[i + 1] - off2[i], first_read_id + i, i, dummy, 8, nullptr, &sink);
+      const size_t per = se ? 1 : 2;
+      for (size_t k = 0; k + per <= recs.size() && n_out < cap_out; k += per) {
+        orc_sam_record &o = out[n_out++];
+        memset(&o, 0, sizeof(o));
+        o.read_id = recs[k].read_id; o.rid = (u32)recs[k].rid; o.mapq = (uint8_t)recs[k].mapq; o.is_unique = (uint8_t)recs[k].is_unique;
+        o.secondary = (recs[k].flag & 256) ? 1 : 0;
+        for (size_t q = 0; q < per; ++q) {
+          const SamRec &r = recs[k + q];
+          int ref_len = 0;
+          for (u32 c : r.cigar) if ((c & 0xf) != 1) ref_len += c >> 4;
+          o.pos[q] = (u32)r.pos; o.end[q] = (u32)r.pos + ref_len - 1; o.strand[q] = (uint8_t)r.strand_pos;
+          o.n_cigar[q] = (uint8_t)std::min<size_t>(r.cigar.size(), ORC_SAM_MAX_CIGAR);
+          for (size_t c = 0; c < o.n_cigar[q]; ++c) o.cigar[q][c] = r.cigar[c];
+        }
+      }
+    }
+  }
+  return n_out;
+}
+
 }  // extern "C"

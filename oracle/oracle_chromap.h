@@ -193,6 +193,21 @@ int64_t orc_map_reads_se_bc(orc_mapper *m, uint32_t n, const char *seq, const ui
 int orc_run_files_sam(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
                       const char *out_path);
 
+// == cmx_sam_record
+#define ORC_SAM_MAX_CIGAR 24
+typedef struct {
+  uint32_t read_id, rid;
+  uint32_t pos[2], end[2];
+  uint8_t strand[2];
+  uint8_t mapq, is_unique, secondary;
+  uint8_t n_cigar[2];
+  uint8_t overflow;
+  uint32_t cigar[2][ORC_SAM_MAX_CIGAR];
+} orc_sam_record;
+int64_t orc_map_sam_cores(orc_mapper *m, uint32_t n, const char *seq1, const uint32_t *off1, const char *seq2, const uint32_t *off2, uint32_t first_read_id,
+                          orc_sam_record *out, int64_t cap_out);
+int orc_sg_align_test(const char *win, int wlen, const char *read, int rlen, int w, unsigned *cigar, int cap, int *start, int *end);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,7 @@ def lib():
         L.orc_format_bed_bc.restype = i64; L.orc_format_bed_bc.argtypes = [vp, vp, vp, i64, u32, vp, i64]
         L.orc_run_files_bc.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 7 + [i32, vp]
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.orc_map_sam_cores.restype = i64; L.orc_map_sam_cores.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, i64]
         L.orc_run_files_sam.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5
         L.orc_map_reads_se_bc.restype = i64; L.orc_map_reads_se_bc.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32, vp, vp, i64, i32, vp]
         L.orc_map_reads_se.restype = i64; L.orc_map_reads_se.argtypes = [vp, u32, vp, vp, u32, vp, i64, i32]
@@ -277,6 +278,25 @@ def run_files_se(params, index_path, ref_path, r1, out, n_threads=1):
     rc = lib().orc_run_files_se(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), out.encode(), n_threads)
     if rc != 0:
         raise RuntimeError("orc_run_files_se failed: %d" % rc)
+
+
+SAM_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("pos", "<u4", 2), ("end", "<u4", 2), ("strand", "u1", 2), ("mapq", "u1"), ("is_unique", "u1"),
+                       ("secondary", "u1"), ("n_cigar", "u1", 2), ("overflow", "u1"), ("cigar", "<u4", (2, 24))], align=True)
+
+
+def map_sam_cores(params, index, ref, seq1, off1, seq2=None, off2=None, first_read_id=0):
+    """SAM cores (spans, strands, MAPQ, CIGARs) per reported pair / read, in the layout of cmx_sam_record."""
+    L = lib()
+    m = L.orc_mapper_create(C.byref(params), index.h, ref.h)
+    n = len(off1) - 1
+    out = np.zeros(n * params.max_num_best_mappings, dtype=SAM_RECORD)
+    seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); off1 = np.ascontiguousarray(off1, dtype=np.uint32)
+    if seq2 is not None:
+        seq2 = np.ascontiguousarray(seq2, dtype=np.uint8); off2 = np.ascontiguousarray(off2, dtype=np.uint32)
+    got = L.orc_map_sam_cores(m, n, seq1.ctypes.data, off1.ctypes.data, seq2.ctypes.data if seq2 is not None else None,
+                              off2.ctypes.data if seq2 is not None else None, first_read_id, out.ctypes.data, len(out))
+    L.orc_mapper_free(m)
+    return out[:got]
 
 
 def run_files_sam(params, index_path, ref_path, r1, r2, out):

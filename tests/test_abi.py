@@ -65,3 +65,29 @@ def test_fastq_cut_finds_record_boundaries():
     assert L.cmx_fastq_cut(text, len(text), 1, C.byref(n)) == len(b"@a 1\nACGT\n+\nIIII\n") and n.value == 1
     assert L.cmx_fastq_cut(text, 5, 10, C.byref(n)) == 0 and n.value == 0
     assert L.cmx_fastq_cut(b"", 0, 10, C.byref(n)) == 0 and n.value == 0
+
+
+@pytest.mark.parametrize("case,kw,paired", [("pe_chip", dict(preset="chip"), True), ("pe_q0d", dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1), True),
+                                            ("se_n3", dict(preset="", max_num_best_mappings=3, mapq_threshold=0), False)])
+def test_host_sam_writer_reproduces_reference_text(golden_dir, case, kw, paired):
+    """cmx_format_sam is host code: fed with the oracle's SAM cores (the device emits the same cores, checked in the gpu
+    tests) it writes the reference binary's SAM file byte for byte - flags, mate fields, TLEN, order, dedup, NM / MD."""
+    import gzip
+    import os
+    import chromap_b200 as cb
+    from oracle import oracle_py as orc
+    from tests.util import load_pairs, read_fasta, read_fastq_records
+    d = os.path.join(golden_dir, "synth_small")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    kw = dict(kw)
+    preset = kw.pop("preset")
+    cores = orc.map_sam_cores(orc.make_params(preset, **kw), idx, ref, s1, o1, s2 if paired else None, o2 if paired else None)
+    r1 = read_fastq_records(os.path.join(d, "read1.fq.gz"))
+    r2 = read_fastq_records(os.path.join(d, "read2.fq.gz")) if paired else None
+    split = lambda r: ([a for a, _, _ in r], [b for _, b, _ in r], [c for _, _, c in r])
+    p = cb.make_params(preset, max_read_length=64, output_format=4, single_end=0 if paired else 1, **kw)
+    text = cb.format_sam(p, names, seqs, cores.view(cb.SAM_RECORD), split(r1), split(r2) if paired else None)
+    assert text == gzip.open(os.path.join(d, case + ".sam.gz")).read()

@@ -22,7 +22,7 @@ def test_cli_rejects_unsupported_and_missing_gpu():
     cli = _ensure_cli()
     r = subprocess.run([cli, "--preset", "nope"], capture_output=True, text=True)
     assert r.returncode != 0 and "Unrecognized preset" in r.stderr
-    r = subprocess.run([cli, "--SAM", "-x", "a", "-r", "b"], capture_output=True, text=True)
+    r = subprocess.run([cli, "--PAF", "-x", "a", "-r", "b"], capture_output=True, text=True)
     assert r.returncode != 0 and "not on the GPU path" in r.stderr
     import torch
     if not torch.cuda.is_available():
@@ -154,5 +154,19 @@ def test_cli_tagalign(tmp_path, golden_dir):
                         (["-1", os.path.join(d, "read1.fq.gz")], "se_chip.bed.gz")):  # single-end TagAlign text == BED text
         out = str(tmp_path / "out.txt")
         r = subprocess.run([cli, "--preset", "chip", "--TagAlign", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-o", out] + reads, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == gzip.open(os.path.join(d, want)).read()
+
+
+@pytest.mark.gpu
+def test_cli_sam(tmp_path, golden_dir):
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    for reads, extra, want in ((["-1", os.path.join(d, "read1.fq.gz"), "-2", os.path.join(d, "read2.fq.gz")], ["--preset", "chip"], "pe_chip.sam.gz"),
+                               (["-1", os.path.join(d, "read1.fq.gz")], ["-n", "3", "-q", "0"], "se_n3.sam.gz")):
+        out = str(tmp_path / "out.sam")
+        r = subprocess.run([cli, "--SAM", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-o", out] + extra + reads, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == gzip.open(os.path.join(d, want)).read()

@@ -719,3 +719,35 @@ def test_single_end_barcoded_equals_oracle_and_golden(case, kw, use_wl, golden_d
     assert m.format_bed_bc(r2, b2, bc_len) == want
     r3, b3 = m.postprocess_gpu(recs, stats["barcode_keys"])
     assert m.format_bed_gpu(r3, b3, bc_len) == want
+
+
+@pytest.mark.parametrize("case,kw,paired", [("pe_chip", dict(preset="chip"), True), ("pe_q0d", dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1), True),
+                                            ("pe_n3", dict(preset="", max_num_best_mappings=3, mapq_threshold=0), True),
+                                            ("se_n3", dict(preset="", max_num_best_mappings=3, mapq_threshold=0), False)])
+def test_sam_cores_equal_oracle_and_text_equals_reference(synth, case, kw, paired):
+    """output_format 4: the device computes, per reported mapping, the ksw_semi_global3 span and CIGAR (sam_kernels.cuh) and
+    MAPQ from those spans; cores == oracle, and the host writer turns them into the reference binary's SAM file."""
+    from tests.util import read_fastq_records
+    extra = dict(output_format=4) if paired else dict(output_format=4, single_end=1)
+    m = _mapper(synth, dict(kw, **extra))
+    s1, o1, s2, o2 = synth["pairs"]
+    recs, stats = m.map_batch(s1, o1, s2 if paired else None, o2 if paired else None)
+    assert recs.dtype == cb.SAM_RECORD and stats["n_overflow_pairs"] == 0
+    cores = orc.map_sam_cores(_oparams(kw), synth["oidx"], synth["oref"], s1, o1, s2 if paired else None, o2 if paired else None)
+    assert len(recs) == len(cores) > 1000
+    for f in ("read_id", "rid", "mapq", "is_unique", "secondary", "overflow"):
+        assert np.array_equal(recs[f], cores[f]), f
+    for q in range(2 if paired else 1):
+        for f in ("pos", "end", "strand", "n_cigar"):
+            bad = np.nonzero(recs[f][:, q] != cores[f][:, q])[0]
+            assert len(bad) == 0, (f, q, bad[:5], recs[f][bad[:5], q], cores[f][bad[:5], q])
+        for i in range(len(recs)):
+            k = recs["n_cigar"][i, q]
+            assert np.array_equal(recs["cigar"][i, q, :k], cores["cigar"][i, q, :k]), (i, q)
+    if case in ("pe_chip", "pe_q0d", "se_n3"):
+        d = synth["d"]
+        split = lambda r: ([a for a, _, _ in r], [b for _, b, _ in r], [c for _, _, c in r])
+        r1 = split(read_fastq_records(os.path.join(d, "read1.fq.gz")))
+        r2 = split(read_fastq_records(os.path.join(d, "read2.fq.gz"))) if paired else None
+        text = cb.format_sam(m.params, synth["names"], synth["seqs"], recs, r1, r2)
+        assert text == gzip.open(os.path.join(d, case + ".sam.gz")).read()
