@@ -91,3 +91,19 @@ def test_host_sam_writer_reproduces_reference_text(golden_dir, case, kw, paired)
     p = cb.make_params(preset, max_read_length=64, output_format=4, single_end=0 if paired else 1, **kw)
     text = cb.format_sam(p, names, seqs, cores.view(cb.SAM_RECORD), split(r1), split(r2) if paired else None)
     assert text == gzip.open(os.path.join(d, case + ".sam.gz")).read()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference headers (build container only)")
+def test_integration_stub_compiles_against_the_reference_headers(tmp_path):
+    """The bridge shown in INTEGRATION.md is real code: it type-checks against the reference's own headers."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    a = md.index("```cpp") + 6
+    code = md[a:md.index("```", a)].replace('#include "chromap_b200.h"', "")
+    src = tmp_path / "bridge.cc"
+    src.write_text("#include <cstdint>\n#include <string>\n#include <vector>\n#include \"mapping_parameters.h\"\n#include \"sequence_batch.h\"\n"
+                   "#include \"bed_mapping.h\"\n#include \"utils.h\"\n#include \"chromap_b200.h\"\nnamespace chromap {\n" + code + "\n}\nint main() { return 0; }\n")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-I/root/reference/src", "-I" + os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]
