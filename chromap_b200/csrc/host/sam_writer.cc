@@ -74,15 +74,23 @@ extern "C" int64_t cmx_format_sam(const cmx_params *p, const char *const *ref_na
     const cmx_read_set &rs = l->mate == 0 ? *reads1 : *reads2;
     const uint32_t ri = c.read_id - first_read_id;
     const char *rseq = rs.seq + rs.off[ri];
-    const size_t rl = (size_t)(rs.off[ri + 1] - rs.off[ri]);
+    const size_t full = (size_t)(rs.off[ri + 1] - rs.off[ri]);
+    // the mapped read may be shorter than the record (adapter trimming keeps a prefix): its length is what the CIGAR consumes
+    size_t rl = 0;
+    for (int q = 0; q < c.n_cigar[l->mate]; ++q) if ((c.cigar[l->mate][q] & 0xf) != 2) rl += c.cigar[l->mate][q] >> 4;
+    if (rl > full) return -3;
     const bool plus = c.strand[l->mate] != 0;
     if (plus) seq.assign(rseq, rl);
-    else {  // PrepareNegativeSequenceAt (sequence_batch.h:123-134)
+    else {  // PrepareNegativeSequenceAt on the kept prefix (sequence_batch.h:123-151)
       seq.resize(rl);
       for (size_t q = 0; q < rl; ++q) { const int b = BaseCode(rseq[rl - 1 - q]); seq[q] = b < 4 ? "ACGT"[3 - b] : 'N'; }
     }
     qual.clear();
-    if (rs.qual) { qual.assign(rs.qual + rs.off[ri], rl); if (!plus) std::reverse(qual.begin(), qual.end()); }
+    if (rs.qual) {  // SAMMapping's constructor: reverse the whole quality string for the - strand, then cut to the sequence length
+      qual.assign(rs.qual + rs.off[ri], full);
+      if (!plus) std::reverse(qual.begin(), qual.end());
+      qual.resize(rl);
+    }
     cig.clear(); md.clear();
     int nm = 0, nmatch = 0;
     size_t rpos = 0, gpos = 0;

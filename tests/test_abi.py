@@ -107,3 +107,32 @@ def test_integration_stub_compiles_against_the_reference_headers(tmp_path):
     r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-I/root/reference/src", "-I" + os.path.join(root, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[:2000]
+
+
+@pytest.mark.parametrize("kw,paired", [(dict(preset="", max_num_best_mappings=3, mapq_threshold=0), True), (dict(preset="atac"), True),
+                                       (dict(preset="", low_memory_mode=1, mapq_threshold=0, remove_pcr_duplicates=1), True),
+                                       (dict(preset="", low_memory_mode=1, mapq_threshold=0, remove_pcr_duplicates=1), False), (dict(preset="chip"), False)])
+def test_host_sam_writer_equals_oracle_writer_on_more_parameter_sets(golden_dir, tmp_path, kw, paired):
+    """More parameter sets than there are committed SAM files: the library's writer against the oracle's (which reproduced the
+    reference binary on all of them): secondary flags (-n 3), trimmed reads (atac), both duplicate rules."""
+    import chromap_b200 as cb
+    from oracle import oracle_py as orc
+    from tests.util import load_pairs, read_fasta, read_fastq_records
+    d = os.path.join(golden_dir, "synth_small")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    ip = str(tmp_path / "ref.index")
+    idx.save(ip)
+    s1, o1, s2, o2 = load_pairs(d)
+    kw = dict(kw)
+    preset = kw.pop("preset")
+    op = orc.make_params(preset, **kw)
+    out = str(tmp_path / "o.sam")
+    orc.run_files_sam(op, ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), os.path.join(d, "read2.fq.gz") if paired else None, out)
+    cores = orc.map_sam_cores(op, idx, ref, s1, o1, s2 if paired else None, o2 if paired else None)
+    split = lambda r: ([a for a, _, _ in r], [b for _, b, _ in r], [c for _, _, c in r])
+    r1 = split(read_fastq_records(os.path.join(d, "read1.fq.gz")))
+    r2 = split(read_fastq_records(os.path.join(d, "read2.fq.gz"))) if paired else None
+    p = cb.make_params(preset, max_read_length=64, output_format=4, single_end=0 if paired else 1, **kw)
+    assert cb.format_sam(p, names, seqs, cores.view(cb.SAM_RECORD), r1, r2) == open(out, "rb").read()
