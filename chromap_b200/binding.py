@@ -66,6 +66,25 @@ def format_sam(params, ref_names, ref_seqs, records, reads1, reads2=None, first_
     return buf.raw[:n]
 
 
+def format_paf(params, ref_names, ref_lengths, records, names1, lengths1, names2=None, lengths2=None, first_read_id=0):
+    """PAF text from BED-path records as map_batch returned them (host only; orders / dedups / filters itself)."""
+    L = load_library()
+    rn = (C.c_char_p * len(ref_names))(*[s.encode() if isinstance(s, str) else s for s in ref_names])
+    rl = np.ascontiguousarray(ref_lengths, dtype=np.uint32)
+    n1 = (C.c_char_p * len(names1))(*names1)
+    l1 = np.ascontiguousarray(lengths1, dtype=np.uint16)
+    n2 = (C.c_char_p * len(names2))(*names2) if names2 is not None else None
+    l2 = np.ascontiguousarray(lengths2, dtype=np.uint16) if lengths2 is not None else None
+    recs = np.ascontiguousarray(records)
+    args = (C.byref(params), rn, rl.ctypes.data, recs.ctypes.data, len(recs), n1, l1.ctypes.data, n2, l2.ctypes.data if l2 is not None else None, first_read_id)
+    n = L.cmx_format_paf(*args, None, 0)
+    if n < 0:
+        raise CmxError("cmx_format_paf failed (%d)" % n)
+    buf = C.create_string_buffer(n + 1)
+    assert L.cmx_format_paf(*args, buf, n) == n
+    return buf.raw[:n]
+
+
 class Ingested(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("seq", C.c_void_p), ("off", C.c_void_p), ("qual", C.c_void_p), ("min_len", C.c_uint32), ("max_len", C.c_uint32)]
 
@@ -155,6 +174,8 @@ def load_library():
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
     L.cmx_set_lanes.argtypes = [vp, i32]
+    L.cmx_format_paf.restype = i64
+    L.cmx_format_paf.argtypes = [C.POINTER(Params), vp, vp, vp, u64, vp, vp, vp, vp, u32, vp, i64]
     L.cmx_format_sam.restype = i64
     L.cmx_format_sam.argtypes = [C.POINTER(Params), vp, vp, u32, vp, vp, vp, u64, C.POINTER(ReadSet), C.POINTER(ReadSet), u32, vp, i64]
     L.cmx_fastq_cut.restype = u64; L.cmx_fastq_cut.argtypes = [vp, u64, u32, C.POINTER(u32)]

@@ -151,7 +151,7 @@ int main(int argc, char **argv) {
   cmx_default_params(&p);
   std::string preset, ref_path, index_path, r1_path, r2_path, out_path, bc_path, wl_path;
   int bc_err = 1, out_nw = 0;
-  bool skip_bc_check = false, host_reader = false;
+  bool skip_bc_check = false, host_reader = false, paf = false;
   bool cell_level_dedup = false;  // remove_pcr_duplicates_at_bulk_level == false (mapping_parameters.h:49; --preset atac clears it)
   double bc_prob = 0.9;
   bool build_index = false, bed = false, user_set_format = false;
@@ -211,7 +211,8 @@ int main(int argc, char **argv) {
       Die("chromap-b200: option " + a + " changes the output in ways that are not on the GPU path; use the reference chromap for it");
     else if (a == "--TagAlign") p.output_format = 2;  // same records as BED, TagAlign / PairedTagAlign text (chromap_driver.cc:417-418)
     else if (a == "--SAM") p.output_format = 4;  // device: ksw spans, CIGARs, MAPQ; host: flags, NM / MD, order, text (cmx_format_sam)
-    else if (a == "--PAF" || a == "--summary")
+    else if (a == "--PAF") paf = true;  // BED-path records, PAF text and order on the host (cmx_format_paf)
+    else if (a == "--summary")
       Die("chromap-b200: option " + a + " is not on the GPU path yet (BED and Hi-C pairs only); use the reference chromap for it");
     else Die("Unknown option " + a);
   }
@@ -250,7 +251,8 @@ int main(int argc, char **argv) {
   if (r1_path.empty()) Die("No read file specified!");
   const bool se = r2_path.empty();  // chromap_driver.cc:704-761: -1 alone = single-end
   if (se && pairs) Die("chromap-b200: pairs output needs paired-end reads");
-  if ((tagalign || sam) && !bc_path.empty()) Die("chromap-b200: --TagAlign / --SAM with barcodes is not on the GPU path");
+  if ((tagalign || sam || paf) && !bc_path.empty()) Die("chromap-b200: --TagAlign / --SAM / --PAF with barcodes is not on the GPU path");
+  if (paf && (sam || tagalign || pairs || p.trim_adapters)) Die("chromap-b200: --PAF goes with BED-path mapping without adapter trimming (trimmed read lengths are not returned yet)");
   if (!bc_path.empty() && p.remove_pcr_duplicates && p.low_memory_mode && !cell_level_dedup)  // mapping_writer.h:254-262: only the low-memory merge has the bulk-level variant
     Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");
@@ -315,7 +317,7 @@ int main(int argc, char **argv) {
   SeqReader r1, r2, rb;
   RawFile g1, g2, gb;
   Batch cur, next;
-  bool gpu_reader = !host_reader && !sam;  // SAM keeps names, bases and qualities of every read on the host
+  bool gpu_reader = !host_reader && !sam && !paf;  // SAM / PAF keep names (SAM: bases and qualities too) of every read on the host
   auto open_all = [&](bool raw) {
     if (raw) {
       if (!g1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
@@ -332,7 +334,7 @@ int main(int argc, char **argv) {
     if (gpu_reader) {
       if (!LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, par, (uint32_t)p.batch_size, b, pairs, bc_len))
         Die(std::string("chromap-b200: the read files are not plain 4-line FASTQ (") + cmx_last_error(ctx) + "); rerun with --host-reader");
-    } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs || sam, sc ? &rb : nullptr, bc_len, se, sam);
+    } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs || sam || paf, sc ? &rb : nullptr, bc_len, se, sam || paf);
   };
   open_all(gpu_reader);
   if (gpu_reader && !LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, parity, (uint32_t)p.batch_size, &cur, pairs, bc_len)) {
@@ -349,6 +351,7 @@ int main(int argc, char **argv) {
   std::vector<cmx_sam_record> sam_recs, all_sam;
   std::string sam_s1, sam_q1, sam_s2, sam_q2;
   std::vector<uint64_t> sam_off1{0}, sam_off2{0};
+  std::vector<uint16_t> paf_len1, paf_len2;
   std::vector<uint64_t> all_bc, bc_keys;
   uint64_t n_bc_in = 0, n_bc_cor = 0;
   if (!gpu_reader) load(&cur, parity);
@@ -378,6 +381,11 @@ int main(int argc, char **argv) {
       all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
       all_names2.insert(all_names2.end(), cur.names2.begin(), cur.names2.end());
     } else all.insert(all.end(), recs.begin(), recs.begin() + out.n_records);
+    if (paf) {
+      for (uint32_t i = 0; i < cur.n; ++i) { paf_len1.push_back((uint16_t)(cur.o1[i + 1] - cur.o1[i])); if (!se) paf_len2.push_back((uint16_t)(cur.o2[i + 1] - cur.o2[i])); }
+      all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
+      all_names2.insert(all_names2.end(), cur.names2.begin(), cur.names2.end());
+    }
     if (pairs) all_names.insert(all_names.end(), cur.names1.begin(), cur.names1.end());
     if (sc) { all_bc.insert(all_bc.end(), bc_keys.begin(), bc_keys.begin() + out.n_records); n_bc_in += out.n_barcodes_in_whitelist; n_bc_cor += out.n_barcodes_corrected; }
     n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
@@ -411,6 +419,21 @@ int main(int argc, char **argv) {
     keep = 0;
     for (int64_t i = 0; i < bytes; ++i) keep += text[(size_t)i] == '\n';
     keep -= names.size();
+  } else if (paf) {
+    std::vector<const char *> n1, n2;
+    for (const auto &x : all_names) n1.push_back(x.c_str());
+    for (const auto &x : all_names2) n2.push_back(x.c_str());
+    std::vector<uint32_t> lens;
+    for (size_t i = 0; i + 1 < ref.offsets.size(); ++i) lens.push_back((uint32_t)(ref.offsets[i + 1] - ref.offsets[i]));
+    bytes = cmx_format_paf(&p, names.data(), lens.data(), all.data(), all.size(), n1.data(), paf_len1.data(), se ? nullptr : n2.data(), se ? nullptr : paf_len2.data(), 0,
+                           nullptr, 0);
+    if (bytes < 0) Die("chromap-b200: cmx_format_paf failed");
+    text.resize((size_t)bytes + 1);
+    cmx_format_paf(&p, names.data(), lens.data(), all.data(), all.size(), n1.data(), paf_len1.data(), se ? nullptr : n2.data(), se ? nullptr : paf_len2.data(), 0,
+                   text.data(), bytes);
+    keep = 0;
+    for (int64_t i = 0; i < bytes; ++i) keep += text[(size_t)i] == '\n';
+    if (!se) keep /= 2;
   } else if (pairs) {
     cmx_pairs_record *pr = reinterpret_cast<cmx_pairs_record *>(all.data());
     if (cmx_postprocess_gpu(ctx, pr, nullptr, all.size(), &keep) && cmx_postprocess_pairs(ctx, pr, all.size(), &keep)) Die(cmx_last_error(ctx));

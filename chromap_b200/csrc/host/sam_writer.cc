@@ -116,3 +116,74 @@ extern "C" int64_t cmx_format_sam(const cmx_params *p, const char *const *ref_na
   }
   return len;
 }
+
+// PAF text (mapping_writer.cc:177-196 single-end, :249-310 paired-end) from the BED-path records: PAFMapping /
+// PairedPAFMapping carry the same fields plus read names and (trimmed) read lengths.  Order, duplicate rule, Tn5 shift and
+// MAPQ filter are the PAF types' own (paf_mapping.h) -- including what EmplaceBackPairedEndMappingRecord<PairedPAFMapping>
+// (mapping_generator.cc:146-167) does to the fields: it passes (start, negative alignment length, fragment length,
+// positive alignment length) to a constructor that takes (start, fragment length, positive, negative), and both mates'
+// MAPQs were overwritten with the pair's (mapping_generator.h:611-612).  No device needed.
+extern "C" int64_t cmx_format_paf(const cmx_params *p, const char *const *ref_names, const uint32_t *ref_lengths, const cmx_pe_record *records, uint64_t n,
+                                  const char *const *names1, const uint16_t *lengths1, const char *const *names2, const uint16_t *lengths2,
+                                  uint32_t first_read_id, char *buf, int64_t cap) {
+  if (!p || !ref_names || !ref_lengths || (!records && n) || !names1 || !lengths1) return -1;
+  const bool se = names2 == nullptr;
+  if (!se && !lengths2) return -1;
+  struct Rec { uint32_t read_id, rid, start; uint16_t frag, pal, nal; uint8_t mapq, dir, uniq, dups; };
+  std::vector<Rec> recs(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    const cmx_pe_record &r = records[i];
+    Rec &o = recs[i];
+    o.read_id = r.read_id; o.rid = r.rid; o.start = r.fragment_start; o.mapq = r.mapq; o.dir = r.direction; o.uniq = r.is_unique; o.dups = r.num_dups;
+    if (se) { o.frag = r.fragment_length; o.pal = o.nal = 0; }
+    else { o.frag = r.negative_alignment_length; o.pal = r.fragment_length; o.nal = r.positive_alignment_length; }
+  }
+  auto tn5 = [&](Rec &r) {
+    if (se) { if (r.dir == 1) r.start += 4; else r.frag -= 5; }
+    else { r.start += 4; r.pal -= 4; r.frag -= 9; r.nal -= 5; }
+  };
+  if (!p->low_memory_mode && p->tn5_shift) for (auto &r : recs) tn5(r);
+  auto key = [&](const Rec &r) {  // PAFMapping: (start, length, mapq, direction, unique, read id, read length); paired: mapq1 = mapq2 = mapq
+    return std::make_tuple(r.rid, r.start, r.frag, r.mapq, r.dir, r.uniq, r.read_id, r.pal, r.nal);
+  };
+  std::stable_sort(recs.begin(), recs.end(), [&](const Rec &a, const Rec &b) { return key(a) < key(b); });
+  auto same = [&](const Rec &a, const Rec &b) { return a.rid == b.rid && a.start == b.start && (se || a.frag == b.frag); };
+  int64_t len = 0;
+  char line[4096];
+  size_t i = 0;
+  while (i < recs.size()) {
+    size_t j = i + 1, k = i;
+    uint32_t dups = 1;
+    if (p->remove_pcr_duplicates)
+      for (; j < recs.size() && same(recs[j], recs[j - 1]); ++j) {
+        ++dups;
+        if (p->low_memory_mode) { if (recs[j].mapq > recs[k].mapq) k = j; } else k = j;
+      }
+    Rec r = recs[k];
+    i = j;
+    if (r.mapq < p->mapq_threshold) continue;
+    if (p->low_memory_mode && p->tn5_shift) tn5(r);
+    const uint32_t ri = r.read_id - first_read_id;
+    const char *rn = ref_names[r.rid];
+    const uint32_t rl = ref_lengths[r.rid];
+    int l;
+    if (se) {
+      l = snprintf(line, sizeof(line), "%s\t%u\t0\t%u\t%c\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", names1[ri], (uint32_t)lengths1[ri], (uint32_t)lengths1[ri], r.dir ? '+' : '-', rn,
+                   rl, r.start, (uint32_t)(r.start + r.frag), (uint32_t)lengths1[ri], (uint32_t)r.frag, (uint32_t)r.mapq);
+    } else {
+      const uint32_t pos_end = r.start + r.pal, neg_end = r.start + r.frag, neg_start = neg_end - r.nal;
+      const uint32_t l1 = lengths1[ri], l2 = lengths2[ri];
+      if (r.dir)
+        l = snprintf(line, sizeof(line), "%s\t%u\t0\t%u\t+\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n%s\t%u\t0\t%u\t-\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", names1[ri], l1, l1, rn, rl, r.start,
+                     pos_end, l1, (uint32_t)r.pal, (uint32_t)r.mapq, names2[ri], l2, l2, rn, rl, neg_start, neg_end, l2, (uint32_t)r.nal, (uint32_t)r.mapq);
+      else
+        l = snprintf(line, sizeof(line), "%s\t%u\t0\t%u\t-\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n%s\t%u\t0\t%u\t+\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", names1[ri], l1, l1, rn, rl, neg_start,
+                     neg_end, l1, (uint32_t)r.nal, (uint32_t)r.mapq, names2[ri], l2, l2, rn, rl, r.start, pos_end, l2, (uint32_t)r.pal, (uint32_t)r.mapq);
+    }
+    if (l < 0 || l >= (int)sizeof(line)) return -2;
+    if (buf && len + l <= cap) memcpy(buf + len, line, l);
+    len += l;
+    (void)dups;
+  }
+  return len;
+}

@@ -276,6 +276,14 @@ int64_t cmx_format_sam(const cmx_params *p, const char *const *ref_names, const 
                        const uint64_t *ref_offsets, const cmx_sam_record *records, uint64_t n, const cmx_read_set *reads1,
                        const cmx_read_set *reads2, uint32_t first_read_id, char *buf, int64_t cap);
 
+/* --PAF (MAPPINGFORMAT_PAF = 3) text from the BED-path records (host only): PAFMapping / PairedPAFMapping hold the same
+ * fields plus read names and the (trimmed) read lengths; order, duplicate rule, Tn5 shift and MAPQ filter are those types'
+ * own (paf_mapping.h), reproduced with the quirks of mapping_generator.cc:146-167.  Takes the records as cmx_map_batch_pe
+ * returned them (not post-processed).  names2 == NULL: single-end.  buf == NULL returns the length; < 0 on error. */
+int64_t cmx_format_paf(const cmx_params *p, const char *const *ref_names, const uint32_t *ref_lengths, const cmx_pe_record *records, uint64_t n,
+                       const char *const *names1, const uint16_t *lengths1, const char *const *names2, const uint16_t *lengths2,
+                       uint32_t first_read_id, char *buf, int64_t cap);
+
 /* Concurrency of one cmx_map_batch_pe call (no counterpart in the reference, whose knob is -t): a call that carries
  * several whole reference batches is cut into up to n_lanes (1..4, default 4) groups of batches that run the whole
  * pipeline on their own streams, so the latency-bound kernels of one group overlap the issue-bound kernels of

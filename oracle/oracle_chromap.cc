@@ -730,7 +730,7 @@ static uint8_t mapq_se(int num_errors, uint16_t aln_len, int read_len, int max_d
 #define ORC_RAW_MAPQ(diff, a) ((int)(5 * 6.02 * (diff) / (a) + .499))
 // mapping_generator.h:1027-1192 (non-split).
 static uint8_t mapq_pe(int e1, int e2, uint16_t al1, uint16_t al2, int L1, int L2, int force,
-                       const PairState &ps, const ReadState rs[2]) {
+                       const PairState &ps, const ReadState rs[2], uint8_t *mapq1_out = nullptr, uint8_t *mapq2_out = nullptr) {
   uint8_t pe = 0;
   const int unpaired = rs[0].min_err + rs[1].min_err + 3;
   if (ps.n_best <= 1) {
@@ -758,6 +758,8 @@ static uint8_t mapq_pe(int e1, int e2, uint16_t al1, uint16_t al2, int L1, int L
   q2 = q2 > pe ? q2 : pe < q2 + pe * 0.65 ? pe : q2 + pe * 0.65;
   q1 *= 1.2; if (q1 > 60) q1 = 60;
   q2 *= 1.2; if (q2 > 60) q2 = 60;
+  if (mapq1_out) *mapq1_out = q1;
+  if (mapq2_out) *mapq2_out = q2;
   uint8_t q = q1 < q2 ? q1 : q2;
   if (q < 60 && force >= 0 && force < q) q = force;
   return q;
@@ -1101,7 +1103,12 @@ static void ref_span_sam(const orc_params &P, const orc_reference &ref, const Dr
   r.md += std::to_string(nmatch);
 }
 
-struct SamSink { std::vector<SamRec> *recs; const char *name1, *qual1, *name2, *qual2; };
+struct PafRec {  // PAFMapping / PairedPAFMapping (paf_mapping.h) as the reference FILLS them: EmplaceBackPairedEndMappingRecord
+  // (mapping_generator.cc:146-167) passes (start, negative alignment length, fragment length, positive alignment length) to a
+  // constructor that takes (start, fragment length, positive alignment length, negative alignment length) -- kept as it is.
+  u32 read_id, rid, start; std::string name1, name2; uint16_t len1, len2, frag, pal, nal; uint8_t mapq, mapq1, mapq2, dir, uniq, dups;
+};
+struct SamSink { std::vector<SamRec> *recs; const char *name1, *qual1, *name2, *qual2; std::vector<PafRec> *paf = nullptr; };
 
 static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_reference &ref, std::mt19937 &gen,
                         const char *s1, u32 len1, const char *s2, u32 len2, u32 read_id, u32 pair_index,
@@ -1220,6 +1227,24 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
           ++idx;
           continue;
         }
+        if (sam && sam->paf) {  // PairedPAFMapping: BED-branch spans, per-mate MAPQs
+          ref_span(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1);
+          ref_span(P, ref, d2, s2 == 0 ? r[1].data() : neg[1].data(), L[1], st2, en2);
+          const uint16_t pal1 = en1 - st1 + 1, pal2 = en2 - st2 + 1;
+          PafRec o;
+          o.mapq = mapq_pe(d1.err, d2.err, pal1, pal2, L[0], L[1], force, ps, rs);
+          o.mapq1 = o.mapq2 = o.mapq;  // mapping_generator.h:611-612: both mates' mapq fields are overwritten with the pair's before the record is built
+          const uint16_t frag = (uint16_t)(s1 == 0 ? (int)(en2 - st1 + 1) : (int)(en1 - st2 + 1));
+          const uint16_t pos_al = s1 == 0 ? pal1 : pal2, neg_al = s1 == 1 ? pal1 : pal2;
+          o.read_id = read_id; o.rid = (u32)(d1.pos >> 32); o.start = s1 == 0 ? st1 : st2; o.name1 = sam->name1; o.name2 = sam->name2;
+          o.len1 = (uint16_t)L[0]; o.len2 = (uint16_t)L[1];
+          o.frag = neg_al; o.pal = frag; o.nal = pos_al;  // the argument order quirk, see PafRec
+          o.dir = s1 == 0 ? 1 : 0; o.uniq = uniq; o.dups = 1;
+          sam->paf->push_back(o);
+          if (++reported == to_report) break;
+          ++idx;
+          continue;
+        }
         if (sam) {  // mapping_generator.h:575-640 with MAPPINGFORMAT_SAM, mapping_generator.cc:84-107
           SamRec a, b;
           ref_span_sam(P, ref, d1, s1 == 0 ? r[0].data() : neg[0].data(), L[0], st1, en1, a);
@@ -1308,6 +1333,18 @@ static int map_one_read_se(const orc_params &P, const orc_index &ix, const orc_r
       if (d.err > rs.min_err) continue;
       if (idx == sel[reported]) {
         u32 a, b;
+        if (sam && sam->paf) {  // PAFMapping (mapping_generator.cc:31-41)
+          ref_span(P, ref, d, st == 0 ? r.data() : neg.data(), len, a, b);
+          const uint16_t al = b - a + 1;
+          PafRec o;
+          o.read_id = read_id; o.rid = (u32)(d.pos >> 32); o.start = a; o.name1 = sam->name1; o.len1 = (uint16_t)len; o.len2 = 0;
+          o.frag = al; o.pal = o.nal = 0; o.mapq = mapq_se(d.err, al, (int)len, P.error_threshold, rs); o.mapq1 = o.mapq2 = 0;
+          o.dir = st == 0 ? 1 : 0; o.uniq = rs.n_best == 1 ? 1 : 0; o.dups = 1;
+          sam->paf->push_back(o);
+          if (++reported == to_report) break;
+          ++idx;
+          continue;
+        }
         if (sam) {  // mapping_generator.h:302-331 with MAPPINGFORMAT_SAM
           SamRec sr;
           ref_span_sam(P, ref, d, st == 0 ? r.data() : neg.data(), len, a, b, sr);
@@ -2278,6 +2315,101 @@ int64_t orc_map_sam_cores(orc_mapper *m, uint32_t n, const char *seq1, const uin
     }
   }
   return n_out;
+}
+
+
+// ---- PAF (oracle only, groundwork): chromap --PAF for bulk single-end / paired-end reads, non-split ---------------------
+int orc_run_files_paf(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                      const char *out_path) {
+  orc_reference *ref = orc_reference_load(ref_path);
+  orc_index *ix = orc_index_load(index_path);
+  if (!ref || !ix || p->split_alignment) return -1;
+  const bool se = !read2_path || !*read2_path;
+  SeqReader r1, r2;
+  if (!r1.open(read1_path) || (!se && !r2.open(read2_path))) return -3;
+  std::vector<PafRec> recs;
+  std::vector<SamRec> unused;
+  const u32 batch = 500000;
+  u32 read_id = 0;
+  for (;;) {
+    std::vector<std::string> n1, s1, n2, s2;
+    std::string n, s, q;
+    while (n1.size() < batch) {
+      bool a = r1.next(n, s, q);
+      while (a && s.empty()) a = r1.next(n, s, q);
+      if (!a) break;
+      n1.push_back(n); s1.push_back(s);
+      if (!se) {
+        bool b = r2.next(n, s, q);
+        while (b && s.empty()) b = r2.next(n, s, q);
+        if (!b) return -4;
+        n2.push_back(n); s2.push_back(s);
+      }
+    }
+    const u32 cnt = (u32)n1.size();
+    if (cnt == 0) break;
+    std::vector<u32> st(cnt / 5000 + 2), en(cnt / 5000 + 2);
+    const int nt = orc_ref_task_chunks(cnt, st.data(), en.data(), (int)st.size());
+    orc_pe_record dummy[8];
+    for (int t = 0; t < nt; ++t) {
+      std::mt19937 gen(11);
+      for (u32 i = st[t]; i < en[t]; ++i) {
+        SamSink sink{&unused, n1[i].c_str(), "", se ? "" : n2[i].c_str(), "", &recs};
+        if (se) map_one_read_se(*p, *ix, *ref, s1[i].data(), (u32)s1[i].size(), read_id + i, i, dummy, 8, &sink);
+        else map_one_pair(*p, *ix, *ref, gen, s1[i].data(), (u32)s1[i].size(), s2[i].data(), (u32)s2[i].size(), read_id + i, i, dummy, 8, nullptr, &sink);
+      }
+    }
+    read_id += cnt;
+  }
+  r1.close(); if (!se) r2.close();
+  auto tn5 = [&](PafRec &r) {  // paf_mapping.h: PAFMapping::Tn5Shift / PairedPAFMapping::Tn5Shift
+    if (se) { if (r.dir == 1) r.start += 4; else r.frag -= 5; }
+    else { r.start += 4; r.pal -= 4; r.frag -= 9; r.nal -= 5; }
+  };
+  if (!p->low_memory_mode && p->tn5_shift) for (auto &r : recs) tn5(r);
+  auto key = [&](const PafRec &r) {
+    return se ? std::make_tuple(r.rid, r.start, r.frag, (uint8_t)r.mapq, (uint8_t)0, r.dir, r.uniq, r.read_id, r.len1, (uint16_t)0)
+              : std::make_tuple(r.rid, r.start, r.frag, r.mapq1, r.mapq2, r.dir, r.uniq, r.read_id, r.pal, r.nal);
+  };
+  std::stable_sort(recs.begin(), recs.end(), [&](const PafRec &a, const PafRec &b) { return key(a) < key(b); });
+  auto same = [&](const PafRec &a, const PafRec &b) { return a.rid == b.rid && a.start == b.start && (se || a.frag == b.frag); };
+  std::vector<PafRec> keep;
+  size_t i = 0;
+  while (i < recs.size()) {
+    size_t j = i + 1, k = i;
+    u32 dups = 1;
+    if (p->remove_pcr_duplicates)
+      for (; j < recs.size() && same(recs[j], recs[j - 1]); ++j) {
+        ++dups;
+        if (p->low_memory_mode) { if (recs[j].mapq > recs[k].mapq) k = j; } else k = j;
+      }
+    PafRec r = recs[k];
+    if (p->remove_pcr_duplicates || p->low_memory_mode) r.dups = (uint8_t)std::min<u32>(255, dups);
+    if (r.mapq >= p->mapq_threshold) { if (p->low_memory_mode && p->tn5_shift) tn5(r); keep.push_back(r); }
+    i = j;
+  }
+  FILE *f = fopen(out_path, "wb");
+  if (!f) return -5;
+  for (const PafRec &r : keep) {  // mapping_writer.cc:177-196 (single-end), :249-310 (paired-end)
+    const char *rn = ref->names[r.rid].c_str();
+    const u32 rl = ref->lens[r.rid];
+    if (se) {
+      fprintf(f, "%s\t%u\t0\t%u\t%c\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", r.name1.c_str(), (u32)r.len1, (u32)r.len1, r.dir ? '+' : '-', rn, rl, r.start,
+              (u32)(r.start + r.frag), (u32)r.len1, (u32)r.frag, (u32)r.mapq);
+      continue;
+    }
+    const u32 pos_end = r.start + r.pal, neg_end = r.start + r.frag, neg_start = neg_end - r.nal;
+    if (r.dir) {
+      fprintf(f, "%s\t%u\t0\t%u\t+\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", r.name1.c_str(), (u32)r.len1, (u32)r.len1, rn, rl, r.start, pos_end, (u32)r.len1, (u32)r.pal, (u32)r.mapq1);
+      fprintf(f, "%s\t%u\t0\t%u\t-\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", r.name2.c_str(), (u32)r.len2, (u32)r.len2, rn, rl, neg_start, neg_end, (u32)r.len2, (u32)r.nal, (u32)r.mapq2);
+    } else {
+      fprintf(f, "%s\t%u\t0\t%u\t-\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", r.name1.c_str(), (u32)r.len1, (u32)r.len1, rn, rl, neg_start, neg_end, (u32)r.len1, (u32)r.nal, (u32)r.mapq1);
+      fprintf(f, "%s\t%u\t0\t%u\t+\t%s\t%u\t%u\t%u\t%u\t%u\t%u\n", r.name2.c_str(), (u32)r.len2, (u32)r.len2, rn, rl, r.start, pos_end, (u32)r.len2, (u32)r.pal, (u32)r.mapq2);
+    }
+  }
+  fclose(f);
+  orc_index_free(ix); orc_reference_free(ref);
+  return 0;
 }
 
 }  // extern "C"

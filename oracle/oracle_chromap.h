@@ -208,6 +208,10 @@ int64_t orc_map_sam_cores(orc_mapper *m, uint32_t n, const char *seq1, const uin
                           orc_sam_record *out, int64_t cap_out);
 int orc_sg_align_test(const char *win, int wlen, const char *read, int rlen, int w, unsigned *cigar, int cap, int *start, int *end);
 
+// chromap --PAF for bulk reads, non-split (oracle only: groundwork; the CUDA path does not emit PAF).
+int orc_run_files_paf(const orc_params *p, const char *index_path, const char *ref_path, const char *read1_path, const char *read2_path,
+                      const char *out_path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,7 @@ def lib():
         L.orc_run_files.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5 + [i32, C.POINTER(C.c_double), C.POINTER(u64)]
         L.orc_map_sam_cores.restype = i64; L.orc_map_sam_cores.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, i64]
         L.orc_run_files_sam.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5
+        L.orc_run_files_paf.argtypes = [C.POINTER(Params)] + [C.c_char_p] * 5
         L.orc_map_reads_se_bc.restype = i64; L.orc_map_reads_se_bc.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32, vp, vp, i64, i32, vp]
         L.orc_map_reads_se.restype = i64; L.orc_map_reads_se.argtypes = [vp, u32, vp, vp, u32, vp, i64, i32]
         L.orc_postprocess_se.restype = i64; L.orc_postprocess_se.argtypes = [C.POINTER(Params), vp, i64]
@@ -303,6 +304,12 @@ def run_files_sam(params, index_path, ref_path, r1, r2, out):
     rc = lib().orc_run_files_sam(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), (r2 or "").encode(), out.encode())
     if rc != 0:
         raise RuntimeError("orc_run_files_sam failed: %d" % rc)
+
+
+def run_files_paf(params, index_path, ref_path, r1, r2, out):
+    rc = lib().orc_run_files_paf(C.byref(params), index_path.encode(), ref_path.encode(), r1.encode(), (r2 or "").encode(), out.encode())
+    if rc != 0:
+        raise RuntimeError("orc_run_files_paf failed: %d" % rc)
 
 
 class Whitelist:

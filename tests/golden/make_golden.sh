@@ -30,8 +30,12 @@ runse se_lowmem_q0 --low-mem -q 0 --remove-pcr-duplicates --Tn5-shift
 $REF --preset chip --SAM -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o pe_chip.sam -t 1 2> /dev/null
 $REF -q 0 --remove-pcr-duplicates --SAM -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o pe_q0d.sam -t 1 2> /dev/null
 $REF -n 3 -q 0 --SAM -x ref.index -r ref.fa -1 read1.fq -o se_n3.sam -t 1 2> /dev/null
+# PAF (host writer over the BED-path records)
+$REF --preset chip --PAF -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o pe_chip.paf -t 1 2> /dev/null
+$REF -q 0 --remove-pcr-duplicates --Tn5-shift --PAF -x ref.index -r ref.fa -1 read1.fq -2 read2.fq -o pe_q0d.paf -t 1 2> /dev/null
+$REF -q 0 --remove-pcr-duplicates --Tn5-shift --PAF -x ref.index -r ref.fa -1 read1.fq -o se_q0d.paf -t 1 2> /dev/null
 md5sum *.bed > md5.txt
-gzip -9 -n ref.fa read1.fq read2.fq *.bed chip.tagalign *.sam
+gzip -9 -n ref.fa read1.fq read2.fq *.bed chip.tagalign *.sam *.paf
 rm -f ref.index
 # the reference's own test data (README quick start): golden BEDs for SURVEY.md §4's md5s
 cd .. && rm -rf ref_test && mkdir ref_test && cd ref_test

@@ -136,3 +136,37 @@ def test_host_sam_writer_equals_oracle_writer_on_more_parameter_sets(golden_dir,
     r2 = split(read_fastq_records(os.path.join(d, "read2.fq.gz"))) if paired else None
     p = cb.make_params(preset, max_read_length=64, output_format=4, single_end=0 if paired else 1, **kw)
     assert cb.format_sam(p, names, seqs, cores.view(cb.SAM_RECORD), r1, r2) == open(out, "rb").read()
+
+
+@pytest.mark.parametrize("case,kw,paired", [("pe_chip", dict(preset="chip"), True), ("pe_q0d", dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1), True),
+                                            ("se_q0d", dict(preset="", mapq_threshold=0, remove_pcr_duplicates=1, tn5_shift=1), False)])
+def test_host_paf_writer_reproduces_reference_text(golden_dir, tmp_path, case, kw, paired):
+    """cmx_format_paf is host code over the BED-path records (the device's == the oracle's, checked in the gpu tests): with the
+    read names and lengths it writes the reference binary's --PAF file byte for byte, field quirks included; the oracle's own PAF
+    writer (orc_run_files_paf) agrees."""
+    import gzip
+    import numpy as np
+    import chromap_b200 as cb
+    from oracle import oracle_py as orc
+    from tests.util import load_pairs, read_fasta, read_fastq_records
+    d = os.path.join(golden_dir, "synth_small")
+    names, seqs = read_fasta(os.path.join(d, "ref.fa.gz"))
+    ref = orc.Reference(os.path.join(d, "ref.fa.gz"))
+    idx = orc.Index(ref=ref, k=17, w=7)
+    s1, o1, s2, o2 = load_pairs(d)
+    kw = dict(kw)
+    preset = kw.pop("preset")
+    op = orc.make_params(preset, **kw)
+    recs = orc.map_pairs(op, idx, ref, s1, o1, s2, o2)[0] if paired else orc.map_reads_se(op, idx, ref, s1, o1)
+    r1 = read_fastq_records(os.path.join(d, "read1.fq.gz"))
+    r2 = read_fastq_records(os.path.join(d, "read2.fq.gz")) if paired else None
+    p = cb.make_params(preset, max_read_length=64, single_end=0 if paired else 1, **kw)
+    text = cb.format_paf(p, names, [len(s) for s in seqs], recs.view(cb.PE_RECORD), [a for a, _, _ in r1], [len(b) for _, b, _ in r1],
+                         [a for a, _, _ in r2] if paired else None, [len(b) for _, b, _ in r2] if paired else None)
+    want = gzip.open(os.path.join(d, case + ".paf.gz")).read()
+    assert text == want
+    ip = str(tmp_path / "ref.index")
+    idx.save(ip)
+    out = str(tmp_path / "o.paf")
+    orc.run_files_paf(op, ip, os.path.join(d, "ref.fa.gz"), os.path.join(d, "read1.fq.gz"), os.path.join(d, "read2.fq.gz") if paired else None, out)
+    assert open(out, "rb").read() == want

@@ -22,7 +22,7 @@ def test_cli_rejects_unsupported_and_missing_gpu():
     cli = _ensure_cli()
     r = subprocess.run([cli, "--preset", "nope"], capture_output=True, text=True)
     assert r.returncode != 0 and "Unrecognized preset" in r.stderr
-    r = subprocess.run([cli, "--PAF", "-x", "a", "-r", "b"], capture_output=True, text=True)
+    r = subprocess.run([cli, "--summary", "-x", "a", "-r", "b"], capture_output=True, text=True)
     assert r.returncode != 0 and "not on the GPU path" in r.stderr
     import torch
     if not torch.cuda.is_available():
