@@ -30,6 +30,13 @@ def test_cli_rejects_unsupported_and_missing_gpu():
         r = subprocess.run([cli, "-x", os.path.join(d, "ref.index"), "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq"),
                             "-2", os.path.join(d, "read2.fq"), "-o", "/tmp/never.bed"], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+        for fmt in ("--SAM", "--PAF", "--TagAlign"):  # the other output formats parse and reach the same gate
+            r = subprocess.run([cli, fmt, "-x", os.path.join(d, "ref.index"), "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq"),
+                                "-2", os.path.join(d, "read2.fq"), "-o", "/tmp/never.out"], capture_output=True, text=True)
+            assert r.returncode != 0 and "no CPU fallback" in r.stderr, (fmt, r.stderr)
+        r = subprocess.run([cli, "--PAF", "--preset", "atac", "-x", os.path.join(d, "ref.index"), "-r", os.path.join(d, "ref.fa.gz"), "-1", os.path.join(d, "read1.fq"),
+                            "-2", os.path.join(d, "read2.fq"), "-o", "/tmp/never.out"], capture_output=True, text=True)
+        assert r.returncode != 0 and "adapter trimming" in r.stderr
 
 
 @pytest.mark.gpu
