@@ -180,6 +180,11 @@ int64_t cmx_format_pairs(const char *const *names, const uint32_t *lengths, uint
  * (PairedEndMappingWithBarcode, bed_mapping.h:116-167; cell-level dedup as the atac preset sets it) and written as
  * `chrom start end barcode num_dups` (mapping_writer.cc:127-137). */
 int cmx_postprocess_bc(cmx_ctx *ctx, cmx_pe_record *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out);
+/* Multi-GPU: one process per GPU, every process owns whole reference batches and calls this library on its own
+ * device; nothing in the hot path crosses GPUs.  The one exchange step -- duplicate removal over the whole run -- is a single
+ * NCCL all-gather of 16-byte tuples followed by the local decision above; it is driven from chromap_b200/distributed.py over
+ * torch.distributed (which owns the communicator), so there is deliberately no C entry point for it. */
+
 /* The same three routines on the device (LSD radix sort over the reference's record order + run resolution), in place on
  * host buffers: `records` is cmx_pairs_record[] when the context emits pairs, cmx_pe_record[] otherwise; barcode_keys
  * is NULL for bulk data.  Replaces the sort / merge of mapping_processor.h:100-202 and mapping_writer.h:166-376 the
