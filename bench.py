@@ -141,38 +141,118 @@ def gen_pairs(torch, ref, n_seq, seq_len, n_pairs, read_len, seed, dev):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md), read in-process through NVML every
+    20 ms (no fork, a few microseconds per read); falls back to one nvidia-smi query per second if NVML is missing.
+    (Round 1 forked nvidia-smi every 0.1 s on every rank inside a 0.4 s timed region: the driver's N=8 leg lost 19 %
+    to that and to unpinned host threads.)"""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.stop_flag = False
-        self.rows = []
+        self.sm = []
+        self.sm_max = None
+        self.reasons = set()
+        self.how = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(visible_to_physical(gpu_index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.how = "nvidia-smi"
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        if self.nv is not None:
+            nv = self.nv
+            bits = [(name, getattr(nv, attr)) for name, attr in self.REASONS if hasattr(nv, attr)]
+            while not self.stop_flag:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for name, bit in bits:
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+            return
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", "-i", str(visible_to_physical(self.gpu)), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    r = [x.strip() for x in out.split(",")]
+                    self.sm.append(float(r[0])); self.sm_max = float(r[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            for _ in range(10):
+                if self.stop_flag:
+                    break
+                time.sleep(0.1)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"], "samples": 0, "how": self.how}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
+
+
+def visible_to_physical(i):
+    """CUDA device index -> NVML / nvidia-smi index (CUDA_VISIBLE_DEVICES may renumber)."""
+    v = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if v:
+        ids = [x.strip() for x in v.split(",") if x.strip()]
+        if i < len(ids) and ids[i].isdigit():
+            return int(ids[i])
+    return i
+
+
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU (same NUMA node): the map call runs
+    up to four launch threads per rank, and at N=8 unpinned threads migrate across sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(visible_to_physical(gpu_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {w * 64 + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:  # no NVML / not permitted: run unpinned
+        log("NUMA binding skipped:", repr(e))
+    return 0
+
+
+def host_description():
+    """CPU model / sockets / NUMA layout of the box (so that reference-arm numbers from different boxes can be compared)."""
+    d = {"logical_cpus": os.cpu_count(), "usable_cpus": len(os.sched_getaffinity(0))}
+    try:
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=5).stdout
+        for line in out.splitlines():
+            k, _, v = line.partition(":")
+            k = k.strip()
+            if k in ("Model name", "Socket(s)", "Core(s) per socket", "Thread(s) per core", "NUMA node(s)", "CPU max MHz", "CPU MHz"):
+                d[k.lower().replace("(s)", "s").replace(" ", "_")] = v.strip()
+    except Exception:
+        pass
+    try:
+        d["loadavg_1min"] = os.getloadavg()[0]
+    except OSError:
+        pass
+    return d
 
 
 def measured_peaks():
@@ -199,6 +279,7 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    n_bound = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     total_bp = int(a.ref_gbp * 1e9)

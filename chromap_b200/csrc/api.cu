@@ -20,6 +20,9 @@
 #include "../../include/chromap_b200.h"
 #include "index_build.cuh"
 #include "pipeline_kernels.cuh"
+#include "seed_front.cuh"
+#include "cta_pair_candidates.cuh"
+#include "cta_verify_pairing.cuh"
 #include "postprocess.cuh"
 #include "sam_kernels.cuh"
 #include "ingest.cuh"
@@ -108,6 +111,7 @@ struct cmx_ctx {
   DevBuf seq1, off1, seq2, off2, trace;
   Lane lanes[CMX_MAX_LANES];
   IngestSlot ingest[CMX_INGEST_SLOTS];
+  int sf_grid = 148;            // persistent grid of the front-end kernel: SMs x resident CTAs
   int n_lanes = CMX_MAX_LANES;  // lanes a multi-batch call is cut into (cmx_set_lanes; CMX_LANES overrides the default)
   int last_lanes_used = 0;
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
@@ -227,11 +231,19 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   // the overflow-tier kernels may use more than the default 48 KB of (static + dynamic) shared memory
   CU(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * CLUSTER_NT * 8));  // tier-0 hc = 64
   CU(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CU(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CU(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
+  {
+    const size_t sf_smem = 4 * seed_front_tile_bytes(mrl);
+    CU(cudaFuncSetAttribute(seed_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
+    int per_sm = 0, n_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_front_kernel, SF_NT, sf_smem));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    ctx->sf_grid = std::max(1, per_sm) * std::max(1, n_sm);
+  }
   for (Lane &L : ctx->lanes) {
     L.tiers[0].caps = {mrl, 64, 32, 32};
     L.tiers[1].caps = {mrl * 2, 1024, 256, 256};
@@ -467,15 +479,16 @@ int cmx_download_index(cmx_ctx *ctx, uint32_t *n_buckets, uint32_t *n_keys, uint
 }
 
 // ---------------------------------------------------------------------------------------------------
-static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {  // o[11]
+static size_t tier_bytes(const Caps &c, size_t slots, bool interleaved, size_t *o) {  // o[11]
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t r = off; off = (off + bytes + 255) / 256 * 256; return r; };
   const size_t R = 2 * slots;
+  const size_t Rm = interleaved ? 2 * ((slots + 31) / 32 * 32) : R;  // minimizer records: whole groups of 32 pairs
   o[0] = take(R * sizeof(ReadMeta));
   o[1] = take(slots * sizeof(PairMeta));
-  o[2] = take(R * c.maxmm * 8);
-  o[3] = take(R * c.maxmm * 8);
-  o[4] = take(R * c.maxmm * 4);
+  o[2] = take(interleaved ? 0 : R * c.maxmm * 8);  // hashes: tier 0 never stores them
+  o[3] = take(Rm * c.maxmm * 8);
+  o[4] = take(Rm * c.maxmm * 4);
   o[5] = take(R * 2 * (size_t)c.hc * 8);
   o[6] = take(R * 6 * (size_t)c.cc * 8);
   o[7] = take(R * 6 * (size_t)c.cc);
@@ -484,21 +497,21 @@ static size_t tier_bytes(const Caps &c, size_t slots, size_t *o) {  // o[11]
   o[10] = take(R * 2 * (size_t)c.mc * 4);
   return off;
 }
-static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list) {
+static cudaError_t tier_prepare(Tier &t, int n_slots, const int *pair_list, bool interleaved) {
   if (n_slots > t.slots_cap) {
     size_t o[11];
     const size_t want_slots = (size_t)n_slots + n_slots / 8 + 16;
-    const size_t bytes = tier_bytes(t.caps, want_slots, o);
+    const size_t bytes = tier_bytes(t.caps, want_slots, interleaved, o);
     release(t.mem);
     cudaError_t e = ensure(t.mem, bytes);
     if (e != cudaSuccess) return e;
     t.slots_cap = (int)want_slots;
   }
   size_t o[11];
-  tier_bytes(t.caps, t.slots_cap, o);
+  tier_bytes(t.caps, t.slots_cap, interleaved, o);
   char *b = (char *)t.mem.p;
   Scratch &S = t.view;
-  S.caps = t.caps; S.n_slots = n_slots; S.pair_list = pair_list;
+  S.caps = t.caps; S.n_slots = n_slots; S.pair_list = pair_list; S.mm_il = interleaved ? 1 : 0;
   S.rmeta = (ReadMeta *)(b + o[0]); S.pmeta = (PairMeta *)(b + o[1]);
   S.mm_hash = (u64 *)(b + o[2]); S.mm_val = (u64 *)(b + o[3]); S.mm_pos = (u32 *)(b + o[4]);
   S.hits = (u64 *)(b + o[5]); S.cand_pos = (u64 *)(b + o[6]); S.cand_cnt = (u8 *)(b + o[7]);
@@ -631,36 +644,40 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
   const int TB = 128;
   for (int t = 0; t < N_TIERS && n_slots > 0; ++t) {
     Tier &tier = L.tiers[t];
-    CUL(tier_prepare(tier, n_slots, pair_list));
+    CUL(tier_prepare(tier, n_slots, pair_list, t == 0));
     const Scratch S = tier.view;
     cudaEvent_t e0 = L.ev[5], e1 = L.ev[6], e2 = L.ev[7], e3 = L.ev[8], e4 = L.ev[9];
     int cluster_passes = 1;
     CUL(cudaEventRecord(e0, st));
-    if (t == 0 && J.piece_ready) {
-      // reads arrive in pieces on the upload stream: length filter / trimming and minimizers start on a piece as
-      // soon as it has landed, the rest of the upload hides behind them
-      for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += J.piece) {
-        const u32 np = std::min(J.piece, n - p0);
-        CUL(cudaStreamWaitEvent(st, (*J.piece_ready)[J.piece0 + q], 0));
-        Scratch V = S;
-        V.n_slots = (int)np; V.rmeta += 2 * (size_t)p0; V.pmeta += p0;
-        V.mm_hash += 2 * (size_t)p0 * S.caps.maxmm; V.mm_val += 2 * (size_t)p0 * S.caps.maxmm; V.mm_pos += 2 * (size_t)p0 * S.caps.maxmm;
-        DevBatch Bq = B;
-        if (Bq.bc_ok) Bq.bc_ok += p0;
-        Bq.off1 += p0; Bq.off2 += p0; Bq.n_pairs = np;
-        prep_kernel<<<(np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V);
-        minimizer_kernel<<<(2 * np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V, L.ctr);
-        acc.launches += 2;
+    if (t == 0) {
+      // front end: [adapter trimming] + length filter + minimizers + index probe in one kernel over staged read tiles
+      // (seed_front.cuh).  When the reads arrive in pieces on the upload stream, one grid per piece starts as soon as
+      // the piece has landed; the rest of the upload hides behind it.
+      const size_t sf_smem = 4 * seed_front_tile_bytes(S.caps.maxmm);
+      const u32 piece = J.piece_ready ? J.piece : n;
+      for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += piece) {
+        const u32 np = std::min(piece, n - p0);
+        if (J.piece_ready) CUL(cudaStreamWaitEvent(st, (*J.piece_ready)[J.piece0 + q], 0));
+        if (P.trim) {
+          Scratch V = S;
+          V.n_slots = (int)np; V.rmeta += 2 * (size_t)p0; V.pmeta += p0;
+          DevBatch Bq = B;
+          if (Bq.bc_ok) Bq.bc_ok += p0;
+          Bq.off1 += p0; Bq.off2 += p0; Bq.n_pairs = np;
+          prep_kernel<<<(np + TB - 1) / TB, TB, 0, st>>>(P, Bq, V);
+          acc.launches += 1;
+        }
+        const int tiles = (int)((np + SF_TILE - 1) / SF_TILE);
+        seed_front_kernel<<<std::min(tiles, ctx->sf_grid), SF_NT, sf_smem, st>>>(P, ix, B, S, L.ctr, P.trim ? 1 : 0, (int)p0, (int)(p0 + np));
+        acc.launches += 1;
       }
     } else {
       prep_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S);
-      if (t == 0) minimizer_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, B, S, L.ctr);
     }
     if (t == 0) {
       CUL(ensure(L.rescue_list, (size_t)n_slots * 4)); CUL(ensure(L.verify_list, (size_t)n_slots * 8));  // verify_list: cluster's, then verify's
       CUL(cudaMemsetAsync(L.d_count + 1, 0, 3 * sizeof(int), st));
       CUL(cudaEventRecord(L.ev_sub[0], st));
-      probe_kernel<<<148 * 8, 256, 0, st>>>(ix, S, L.ctr);  // persistent: 8 CTAs per SM
       CUL(cudaEventRecord(L.ev_sub[1], st));
       {
         // first-pass tile: enough rows for a typical read (about 2L/(w+1) minimizers, most of them single hits)
@@ -690,18 +707,21 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
       seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, L.ctr, c_seed);
       CUL(cudaEventRecord(e1, st));
-      pair_candidates_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pc * 11, st>>>(P, ix, S, L.ctr, c_pc);
+      {
+        const int lcap = std::min(tier.caps.cc, 512), fcap = 2 * tier.caps.cc;
+        pair_candidates_cta_kernel<<<n_slots, CTA_NT, pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap), st>>>(P, ix, S, L.ctr, c_pc, lcap, fcap);
+      }
       CUL(cudaEventRecord(e2, st));
       if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
-      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
+      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, st>>>(P, R, B, S, L.ctr, c_ver);
       CUL(cudaEventRecord(e3, st));
       if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
       else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)L.nbest.p, c_pair);
       CUL(cudaEventRecord(e4, st));
     }
-    // kernels launched above: tier 0 = [prep + minimizer unless counted per piece] + probe + cluster (1 or 2 passes) +
-    // pair_candidates x2 + verify (x2 unless split) + pairing; overflow tiers = prep + four CTA kernels
-    if (t == 0) acc.launches += (J.piece_ready ? 0 : 2) + 1 + cluster_passes + 2 + (P.split ? 1 : 2) + 1;
+    // kernels launched above: tier 0 = front end (counted per piece) + cluster (1 or 2 passes) + pair_candidates x2 +
+    // verify (x2 unless split) + pairing; overflow tiers = prep + four CTA kernels
+    if (t == 0) acc.launches += cluster_passes + 2 + (P.split ? 1 : 2) + 1;
     else acc.launches += 5;
     CUL(ensure(tier.ovf_list, (size_t)n_slots * 4));
     CUL(cudaMemsetAsync(L.d_count, 0, sizeof(int), st));
@@ -752,6 +772,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     else if (sam && P.se) emit_sam_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutSam *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else if (sam) emit_sam_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutSam *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else if (P.se) emit_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else if (t > 0) emit_cta_kernel<<<S.n_slots, CTA_NT, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     if (t > 0) CUL(cudaEventRecord(L.ev_join[t - 1], es));
   }
@@ -989,10 +1010,12 @@ int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes,
   cub::DeviceScan::ExclusiveSum(nullptr, tb, (const u32 *)g.len.p, (u32 *)g.off.p, (int)n + 1, st);
   CU(ensure(g.tmp, tb));
   CU(cub::DeviceScan::ExclusiveSum(g.tmp.p, tb, (const u32 *)g.len.p, (u32 *)g.off.p, (int)n + 1, st));
-  CU(ensure(g.seq, n_bytes / 2 + 64));  // bases are less than half of a 4-line record
-  if (want_qual) CU(ensure(g.qual, n_bytes / 2 + 64));
+  // sequence bytes never exceed the chunk; a malformed record (quality shorter than sequence) is only reported after the
+  // pack kernel has run, so the buffers are sized by the chunk and the quality copy is bounded by the quality line itself
+  CU(ensure(g.seq, n_bytes + 64));
+  if (want_qual) CU(ensure(g.qual, n_bytes + 64));
   ingest_pack_kernel<<<(unsigned)(((u64)n * 32 + 255) / 256), 256, 0, st>>>((const char *)g.text.p, (const u32 *)g.seq_start.p, (const u32 *)g.qual_start.p,
-                                                                           (const u32 *)g.off.p, n, (char *)g.seq.p, want_qual ? (char *)g.qual.p : nullptr);
+                                                                           (const u32 *)g.off.p, (const u32 *)g.nl.p, n, (char *)g.seq.p, want_qual ? (char *)g.qual.p : nullptr);
   CU(cudaMemcpyAsync(&hs, g.stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
   if (name_spans) CU(cudaMemcpyAsync(name_spans, g.spans.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1063,7 +1086,12 @@ __global__ void stage_minimizers_kernel(DevBatch B, int k, int w, u64 *out_hash,
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= 2 * (int)B.n_pairs) return;
   const int pair = r >> 1, mate = r & 1;
-  out_n[r] = gen_minimizers_any(read_ptr(B, pair, mate), read_raw_len(B, pair, mate), k, w, out_hash + (size_t)r * stride, out_pos + (size_t)r * stride, (int)stride);
+  const u8 *seq = read_ptr(B, pair, mate);
+  u64 *oh = out_hash + (size_t)r * stride;
+  u32 *op = out_pos + (size_t)r * stride;
+  int n = 0;
+  minimizer_scan_any([&](int i) { return seq[i]; }, read_raw_len(B, pair, mate), k, w, [&](u64 h, u32 p) { if (n < (int)stride) { oh[n] = h; op[n] = p; } ++n; });
+  out_n[r] = n;
 }
 
 int cmx_stage_minimizers(cmx_ctx *ctx, const cmx_batch *in, uint64_t *out_hash, uint32_t *out_pos, int32_t *out_n, uint32_t stride) {

@@ -81,9 +81,10 @@ struct Scratch {
   Caps caps;
   int n_slots;
   const int *pair_list;  // slot -> pair index in batch (nullptr = identity)
+  int mm_il;             // 1: minimizer records lane-interleaved in groups of 32 pairs (tier 0), see minimizers.cuh
   ReadMeta *rmeta;       // [2*n_slots]
   PairMeta *pmeta;       // [n_slots]
-  u64 *mm_hash;          // [2n][maxmm]
+  u64 *mm_hash;          // [2n][maxmm]   (overflow tiers only)
   u64 *mm_val;           // [2n][maxmm]   lookup value
   u32 *mm_pos;           // [2n][maxmm]   (pos<<1|strand) | kind<<30   kind: 0 absent 1 singleton 2 multi
   u64 *hits;             // [2n][2][hc]

@@ -43,10 +43,16 @@ __global__ void ingest_record_kernel(const char *text, const u32 *nl, u32 n_rec,
   }
 }
 // one warp per record: copy its bases (and qualities) to their packed place
-__global__ void ingest_pack_kernel(const char *text, const u32 *seq_start, const u32 *qual_start, const u32 *off, u32 n_rec, char *seq, char *qual) {
+// (a record whose quality line is shorter than its sequence is reported by ingest_record_kernel; the copy here never
+// leaves the quality line, so such a chunk cannot read past the text or write past the packed buffers)
+__global__ void ingest_pack_kernel(const char *text, const u32 *seq_start, const u32 *qual_start, const u32 *off, const u32 *nl, u32 n_rec, char *seq,
+                                   char *qual) {
   const u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n_rec) return;
   const u32 o = off[r], l = off[r + 1] - o, s = seq_start[r];
   for (u32 i = lane; i < l; i += 32) seq[o + i] = text[s + i];
-  if (qual) { const u32 q = qual_start[r]; for (u32 i = lane; i < l; i += 32) qual[o + i] = text[q + i]; }
+  if (qual) {
+    const u32 q = qual_start[r], ql = min(l, nl[4 * r + 3] - q);
+    for (u32 i = lane; i < ql; i += 32) qual[o + i] = text[q + i];
+  }
 }

@@ -4,6 +4,7 @@
 // File:line citations are into the reference's src/.
 #pragma once
 #include "device_common.cuh"
+#include "minimizers.cuh"
 
 struct MapqTables {
   const double *inv_log;  // [65536]: 3 / log(alignment_length) as computed by the host libm (mapping_generator.h:956-958)
@@ -102,123 +103,6 @@ __global__ void prep_kernel(DevParams P, DevBatch B, Scratch S) {
   z.len = len2; S.rmeta[2 * slot + 1] = z;
 }
 
-// ------------------------------------------------------------------------------------------------
-// minimizer_generator.cc:7-139 for one read, by one thread.  Emits (hash, pos<<1|strand).
-__device__ inline int gen_minimizers_thread(const u8 *seq, int len, int k, int w, u64 *out_hash, u32 *out_pos, int cap) {
-  const u64 shift = 2 * (k - 1);
-  const u64 mask = (((u64)1) << (2 * k)) - 1;
-  u64 fwd = 0, rev = 0;
-  u64 ring_h[CMX_W_MAX];
-  u32 ring_p[CMX_W_MAX];
-  for (int i = 0; i < w; ++i) { ring_h[i] = ~0ull; ring_p[i] = ~0u; }
-  u64 best_h = ~0ull;
-  u32 best_p = ~0u;
-  int run = 0, slot = 0, best_slot = 0, n = 0;
-#define EMIT(h, p) do { if (n < cap) { out_hash[n] = (h); out_pos[n] = (p); } ++n; } while (0)
-  for (int pos = 0; pos < len; ++pos) {
-    const u32 b = base_code(seq[pos]);
-    u64 cur_h = ~0ull;
-    u32 cur_p = ~0u;
-    if (b < 4) {
-      fwd = ((fwd << 2) | b) & mask;
-      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
-      if (fwd == rev) continue;
-      const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
-      const u32 strand = hf < hr ? 0u : 1u;
-      ++run;
-      if (run >= k) { cur_h = mix64(strand ? hr : hf, mask); cur_p = ((u32)pos << 1) | strand; }
-    } else {
-      run = 0;
-    }
-    ring_h[slot] = cur_h; ring_p[slot] = cur_p;
-    if (run == w + k - 1 && best_h != ~0ull && best_h < cur_h) {
-      for (int j = slot + 1; j < w; ++j) if (best_h == ring_h[j] && ring_p[j] != best_p) EMIT(ring_h[j], ring_p[j]);
-      for (int j = 0; j < slot; ++j) if (best_h == ring_h[j] && ring_p[j] != best_p) EMIT(ring_h[j], ring_p[j]);
-    }
-    if (cur_h <= best_h) {
-      if (run >= w + k && best_h != ~0ull) EMIT(best_h, best_p);
-      best_h = cur_h; best_p = cur_p; best_slot = slot;
-    } else if (slot == best_slot) {
-      if (run >= w + k - 1 && best_h != ~0ull) EMIT(best_h, best_p);
-      best_h = ~0ull;
-      for (int j = slot + 1; j < w; ++j) if (best_h >= ring_h[j]) { best_h = ring_h[j]; best_p = ring_p[j]; best_slot = j; }
-      for (int j = 0; j <= slot; ++j) if (best_h >= ring_h[j]) { best_h = ring_h[j]; best_p = ring_p[j]; best_slot = j; }
-      if (run >= w + k - 1 && best_h != ~0ull) {
-        for (int j = slot + 1; j < w; ++j) if (best_h == ring_h[j] && best_p != ring_p[j]) EMIT(ring_h[j], ring_p[j]);
-        for (int j = 0; j <= slot; ++j) if (best_h == ring_h[j] && best_p != ring_p[j]) EMIT(ring_h[j], ring_p[j]);
-      }
-    }
-    if (++slot == w) slot = 0;
-  }
-  if (best_h != ~0ull) EMIT(best_h, best_p);
-#undef EMIT
-  return n;
-}
-
-// Same algorithm with the w-entry ring held in registers as a shift register (index 0 = oldest, W-1 = newest)
-// so that every scan has static indices; `best_age` = insertions since the current minimum was inserted
-// (the reference's `position_in_buffer == min_position` test is `best_age == W`).  Used when w == W.
-template <int W>
-__device__ __forceinline__ int gen_minimizers_regs(const u8 *seq, int len, int k, u64 *out_hash, u32 *out_pos, int cap) {
-  const u64 shift = 2 * (k - 1);
-  const u64 mask = (((u64)1) << (2 * k)) - 1;
-  u64 fwd = 0, rev = 0;
-  u64 rh[W];
-  u32 rp[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) { rh[i] = ~0ull; rp[i] = ~0u; }
-  u64 best_h = ~0ull;
-  u32 best_p = ~0u;
-  int run = 0, best_age = 0, n = 0;
-#define EMIT(h, p) do { if (n < cap) { out_hash[n] = (h); out_pos[n] = (p); } ++n; } while (0)
-  for (int pos = 0; pos < len; ++pos) {
-    const u32 b = base_code(seq[pos]);
-    u64 cur_h = ~0ull;
-    u32 cur_p = ~0u;
-    if (b < 4) {
-      fwd = ((fwd << 2) | b) & mask;
-      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
-      if (fwd == rev) continue;
-      const u64 hf = mix64(fwd, mask), hr = mix64(rev, mask);
-      const u32 strand = hf < hr ? 0u : 1u;
-      ++run;
-      if (run >= k) { cur_h = mix64(strand ? hr : hf, mask); cur_p = ((u32)pos << 1) | strand; }
-    } else {
-      run = 0;
-    }
-#pragma unroll
-    for (int j = 0; j + 1 < W; ++j) { rh[j] = rh[j + 1]; rp[j] = rp[j + 1]; }
-    rh[W - 1] = cur_h; rp[W - 1] = cur_p;
-    ++best_age;
-    if (run == W + k - 1 && best_h != ~0ull && best_h < cur_h) {
-#pragma unroll
-      for (int j = 0; j + 1 < W; ++j) if (best_h == rh[j] && rp[j] != best_p) EMIT(rh[j], rp[j]);
-    }
-    if (cur_h <= best_h) {
-      if (run >= W + k && best_h != ~0ull) EMIT(best_h, best_p);
-      best_h = cur_h; best_p = cur_p; best_age = 0;
-    } else if (best_age == W) {
-      if (run >= W + k - 1 && best_h != ~0ull) EMIT(best_h, best_p);
-      best_h = ~0ull;
-#pragma unroll
-      for (int j = 0; j < W; ++j) if (best_h >= rh[j]) { best_h = rh[j]; best_p = rp[j]; best_age = W - 1 - j; }
-      if (run >= W + k - 1 && best_h != ~0ull) {
-#pragma unroll
-        for (int j = 0; j < W; ++j) if (best_h == rh[j] && best_p != rp[j]) EMIT(rh[j], rp[j]);
-      }
-    }
-  }
-  if (best_h != ~0ull) EMIT(best_h, best_p);
-#undef EMIT
-  return n;
-}
-__device__ __forceinline__ int gen_minimizers_any(const u8 *seq, int len, int k, int w, u64 *out_hash, u32 *out_pos, int cap) {
-  if (w == 7) return gen_minimizers_regs<7>(seq, len, k, out_hash, out_pos, cap);    // default (-w 7)
-  if (w == 10) return gen_minimizers_regs<10>(seq, len, k, out_hash, out_pos, cap);  // --min-frag-length <= 80
-  if (w == 11) return gen_minimizers_regs<11>(seq, len, k, out_hash, out_pos, cap);  // --min-frag-length > 80
-  return gen_minimizers_thread(seq, len, k, w, out_hash, out_pos, cap);
-}
-
 struct RepStats { u32 len, prev; int count; };
 __device__ __forceinline__ void rep_update(int k, int w, u32 read_pos, RepStats &st) {  // index.cc:507-523
   if (st.prev > read_pos) st.len += k;
@@ -252,55 +136,6 @@ __device__ inline int cluster_hits(int e, int need, u32 n_mm, A hits, int nh, u6
   return n;
 }
 
-// K1a: per read — minimizers (minimizer_generator.cc:7-139).  Integer-ALU bound: 3 x Hash64 per k-mer position.
-__global__ void minimizer_kernel(DevParams P, DevBatch B, Scratch S, Counters *ctr) {
-  const int sr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sr >= 2 * S.n_slots) return;
-  const int slot = sr >> 1, mate = sr & 1;
-  if (S.pmeta[slot].status != ST_OK || (P.se && mate == 1)) return;
-  const int pair = slot_pair(S, slot);
-  ReadMeta &rm = S.rmeta[sr];
-  const Caps c = S.caps;
-  const int n_mm = gen_minimizers_any(read_ptr(B, pair, mate), rm.len, P.k, P.w, S.mm_hash + (size_t)sr * c.maxmm, S.mm_pos + (size_t)sr * c.maxmm, c.maxmm);
-  rm.n_mm = n_mm;
-  if (n_mm > c.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); }
-}
-
-// K1b: the index-probe kernel (khash.h:232-245 semantics on our table).  PROBE_LANES threads per read, one
-// probe chain per minimizer: millions of independent 16-byte random reads in flight — the HBM random-sector
-// kernel of the path.  Writes the table value and the kind (absent / singleton / multi) next to the minimizer.
-#define PROBE_LANES 8
-__global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, Scratch S, Counters *ctr) {
-  // persistent grid-stride loop: statistics are accumulated per thread and reduced once per CTA (three
-  // same-address atomics per warp were the bottleneck of the first version of this kernel)
-  __shared__ u32 s_acc[3];
-  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
-  __syncthreads();
-  u32 steps_total = 0, found = 0, n_mine = 0;
-  const long long total = (long long)2 * S.n_slots * PROBE_LANES;
-  const Caps c = S.caps;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int sr = (int)(t / PROBE_LANES), j = (int)(t % PROBE_LANES);
-    if (S.pmeta[sr >> 1].status != ST_OK) continue;
-    const int n_mm = min(S.rmeta[sr].n_mm, c.maxmm);
-    const u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
-    u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
-    u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
-    for (int i = j; i < n_mm; i += PROBE_LANES) {
-      u64 val = 0;
-      int steps;
-      const int kind = index_lookup(ix, mmh[i], &val, &steps);
-      mmv[i] = val;
-      mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
-      steps_total += steps; found += kind != 0; ++n_mine;
-    }
-  }
-  const u32 a = __reduce_add_sync(0xffffffffu, n_mine), b2 = __reduce_add_sync(0xffffffffu, steps_total), f = __reduce_add_sync(0xffffffffu, found);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[0], a); atomicAdd(&s_acc[1], b2); atomicAdd(&s_acc[2], f); }
-  __syncthreads();
-  if (threadIdx.x == 0) { atomicAdd(&ctr->n_minimizers, (u64)s_acc[0]); atomicAdd(&ctr->n_probe_steps, (u64)s_acc[1]); atomicAdd(&ctr->n_found, (u64)s_acc[2]); }
-}
-
 // K1c: per read — hit lists from the probed values, sort, clustering (candidate_processor.cc:12-71,
 // index.cc:237-349).  Tier 0 takes only "light" reads: as soon as the exact hit count (known from the table
 // values before any occurrence is read) exceeds the tier's capacity the pair is escalated to the CTA tier.
@@ -325,18 +160,19 @@ __global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevInd
   const Caps c = S.caps;
   const int n_mm = rm.n_mm;
   if (n_mm == 0) return;
-  const u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
-  const u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
+  const int ms = mm_stride(S);
+  const u64 *mmv = S.mm_val + mm_base(S, slot, sr & 1);
+  const u32 *mmp = S.mm_pos + mm_base(S, slot, sr & 1);
   long long cnt1 = 0, cnt2 = 0;
   RepStats st = {0u, 0xFFFFFFFFu, 0};
   for (int i = 0; i < n_mm; ++i) {
-    const u32 kind = mmp[i] >> 30;
+    const u32 kind = mmp[(size_t)i * ms] >> 30;
     if (kind == 1) { ++cnt1; ++cnt2; }
     else if (kind == 2) {
-      const u32 n = (u32)mmv[i];
+      const u32 n = (u32)mmv[(size_t)i * ms];
       if (n < (u32)P.f0) cnt1 += n;
       if (n < (u32)P.f1) cnt2 += n;
-      if (n >= (u32)P.f0) rep_update(P.k, P.w, (mmp[i] & 0x3FFFFFFFu) >> 1, st);
+      if (n >= (u32)P.f0) rep_update(P.k, P.w, (mmp[(size_t)i * ms] & 0x3FFFFFFFu) >> 1, st);
     }
   }
   // round 1 (f0) or, if it yields no hits at all, round 2 (f1)  (candidate_processor.cc:30-50)
@@ -350,10 +186,10 @@ __global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevInd
   int np = 0, nn = 0;
   u32 occ_reads = 0;
   for (int i = 0; i < n_mm; ++i) {
-    const u32 kind = mmp[i] >> 30;
+    const u32 kind = mmp[(size_t)i * ms] >> 30;
     if (kind == 0) continue;
-    const u32 rpos = (mmp[i] & 0x3FFFFFFFu) >> 1, rstrand = mmp[i] & 1u;
-    const u64 val = mmv[i];
+    const u32 rpos = (mmp[(size_t)i * ms] & 0x3FFFFFFFu) >> 1, rstrand = mmp[(size_t)i * ms] & 1u;
+    const u64 val = mmv[(size_t)i * ms];
     bool same;
     if (kind == 1) {
       const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
@@ -392,7 +228,7 @@ __global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevInd
 // index.cc:351-489 — mate-guided lookup on one strand for one read (by one thread).
 // Returns +max count or -max count (bail-out); hits appended (sorted) into `hits`, *nh set (may exceed cap).
 __device__ inline int rescue_hits(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv,
-                                  const u32 *mmp, const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len,
+                                  const u32 *mmp, int ms, const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len,
                                   u64 *hits, int cap, int *nh_out) {
   int max_cnt = 0, n_best = 0;
   for (int i = 0; i < n_mate; ++i) {
@@ -406,10 +242,10 @@ __device__ inline int rescue_hits(const DevParams &P, const DevIndex &ix, int st
   int nh = 0;
   RepStats st = {0u, 0xFFFFFFFFu, 0};
   for (int mi = 0; mi < n_mm; ++mi) {
-    const u32 kind = mmp[mi] >> 30;
+    const u32 kind = mmp[(size_t)mi * ms] >> 30;
     if (kind == 0) continue;
-    const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
-    const u64 val = mmv[mi];
+    const u32 rpos = (mmp[(size_t)mi * ms] & 0x3FFFFFFFu) >> 1, rstrand = mmp[(size_t)mi * ms] & 1u;
+    const u64 val = mmv[(size_t)mi * ms];
     bool same;
     if (kind == 1) {
       const u64 cp = hit_to_candidate(P.k, val, rpos, rstrand, &same);
@@ -580,9 +416,10 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       u32 searches = 0;
       for (int mate = 0; mate < 2; ++mate) {
         if (!aug[mate]) continue;
-        const u32 *mmp = S.mm_pos + (size_t)(2 * slot + mate) * c.maxmm;
+        const u32 *mmp = S.mm_pos + mm_base(S, slot, mate);
+        const int ms = mm_stride(S);
         u32 n_multi = 0;
-        for (int i = 0; i < rm[mate].n_mm; ++i) n_multi += (mmp[i] >> 30) == 2;
+        for (int i = 0; i < rm[mate].n_mm; ++i) n_multi += (mmp[(size_t)i * ms] >> 30) == 2;
         searches += n_multi * (u32)(nq[(1 - mate) * 2] + nq[(1 - mate) * 2 + 1]);
       }
       if (searches > PC_RESCUE_HEAVY) { pm.status = ST_OVERFLOW; agg_add(&ctr->ovf_reason[7], 1ull); return; }
@@ -621,13 +458,14 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       }
       if (!a) continue;
       const size_t sr = 2 * slot + mate;
-      const u64 *mmv = S.mm_val + sr * c.maxmm;
-      const u32 *mmp = S.mm_pos + sr * c.maxmm;
+      const u64 *mmv = S.mm_val + mm_base(S, slot, mate);
+      const u32 *mmp = S.mm_pos + mm_base(S, slot, mate);
+      const int ms = mm_stride(S);
       u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
       int pr = 0, nr = 0;
       if (ot.n_cand[0] > 0) {
         int nh;
-        pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
+        pr = rescue_hits(P, ix, 1, range, n_mm, mmv, mmp, ms, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, &nh);
         if (nh > c.hc) { ovf = true; atomicAdd(&ctr->ovf_reason[4], 1ull); break; }
         const int na = cluster_hits(P.e, 1, n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc);
         if (na > c.cc) { ovf = true; atomicAdd(&ctr->ovf_reason[5], 1ull); break; }
@@ -635,7 +473,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       }
       if (ot.n_cand[1] > 0) {
         int nh;
-        nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
+        nr = rescue_hits(P, ix, 0, range, n_mm, mmv, mmp, ms, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, &nh);
         if (nh > c.hc) { ovf = true; atomicAdd(&ctr->ovf_reason[4], 1ull); break; }
         const int na = cluster_hits(P.e, 1, n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc);
         if (na > c.cc) { ovf = true; atomicAdd(&ctr->ovf_reason[5], 1ull); break; }
@@ -1190,8 +1028,47 @@ struct OutRecord {  // == cmx_pe_record
   unsigned short positive_alignment_length, negative_alignment_length;
 };
 
+// start / end of one mate's mapping on the reference: GetRefStartEndPositionForReadFromMapping, BED branch
+// (mapping_generator.h:657-917).  r = the mate's bases as read (the reverse strand is formed on the fly).
+__device__ __forceinline__ void mapping_span(const DevRef &R, int e, const u8 *r, int Lm, int s, u64 dpos, int derr, u32 *st, u32 *en) {
+  const u32 rid = (u32)(dpos >> 32), rp = (u32)dpos;
+  u32 vws = rp + 1u > (u32)(Lm + e) ? rp + 1u - (u32)Lm - (u32)e : 0u;
+  if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)Lm;
+  const u8 *win = R.seq + R.off[rid] + vws;
+  int s0;
+  if (s == 0) s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[i]; });
+  else s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return code_char(neg_code(r, Lm, i)); });
+  *st = vws + (u32)s0;
+  *en = rp;
+}
+// one paired-end record (mapping_generator.cc:110-143) from the chosen draft mappings of the two mates; s1 = strand of mate 1
+__device__ __forceinline__ OutRecord pe_record(const DevParams &P, const DevRef &R, const DevBatch &B, const MapqTables &T, const PairMeta &pm, const ReadMeta *rm,
+                                               int pair, int s1, u64 pos1, int err1, u64 pos2, int err2) {
+  const int L0 = rm[0].len, L1 = rm[1].len;
+  u32 st1, en1, st2, en2;
+  mapping_span(R, P.e, read_ptr(B, pair, 0), L0, s1, pos1, err1, &st1, &en1);
+  mapping_span(R, P.e, read_ptr(B, pair, 1), L1, 1 - s1, pos2, err2, &st2, &en2);
+  const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
+  OutRecord o;
+  o.read_id = B.first_read_id + (u32)pair;
+  o.rid = (u32)(pos1 >> 32);
+  o.fragment_start = s1 == 0 ? st1 : st2;
+  o.fragment_length = (unsigned short)(s1 == 0 ? (int)(en2 - st1 + 1u) : (int)(en1 - st2 + 1u));
+  o.mapq = mapq_pe(T, err1, err2, al1, al2, L0, L1, pm.sup != 0 ? 0 : -1, pm, rm);
+  o.direction = s1 == 0 ? 1 : 0;
+  o.is_unique = (pm.n_best == 1 || rm[0].n_best == 1 || rm[1].n_best == 1) ? 1 : 0;
+  o.num_dups = 1;
+  o.positive_alignment_length = s1 == 0 ? al1 : al2;
+  o.negative_alignment_length = s1 == 1 ? al1 : al2;
+  return o;
+}
+
 // K6: per pair — ProcessBestMappingsForPairedEndReadOnOneDirection (mapping_generator.h:486-654):
 // the selected best pair(s), start coordinates (mapping_generator.h:657-917 BED branch), MAPQ, record.
+// Two phases, so that the threads of a warp run the expensive part together: first every thread walks its sweep to the
+// selected best pair(s) and only notes which mappings they are, then all threads compute their records (tracebacks,
+// MAPQ) side by side.  (With the record computed inside the sweep, each thread reached it at a different iteration and
+// the warp ran 32 tracebacks one after the other: 3.5 active lanes per instruction.)
 __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, const int *pair_sel, OutRecord *out,
                             int *out_n, Counters *ctr) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1205,53 +1082,23 @@ __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scr
   const int mb = P.max_best;
   const int to_report = mb < pm.n_best ? mb : pm.n_best;
   const int *sel = pair_sel + (size_t)pair * mb;
-  const u8 uniq = (pm.n_best == 1 || rm[0].n_best == 1 || rm[1].n_best == 1) ? 1 : 0;
-  const int force = pm.sup != 0 ? 0 : -1;
   int idx = 0, reported = 0;
-  const int e = P.e;
-  const int L[2] = {rm[0].len, rm[1].len};
-  const u8 *rd[2] = {read_ptr(B, pair, 0), read_ptr(B, pair, 1)};
-  auto span = [&](int m, int s, u64 dpos, int derr, u32 *st, u32 *en) {
-    const u32 rid = (u32)(dpos >> 32), rp = (u32)dpos;
-    const int Lm = L[m];
-    u32 vws = rp + 1u > (u32)(Lm + e) ? rp + 1u - (u32)Lm - (u32)e : 0u;
-    if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)Lm;
-    const u8 *win = R.seq + R.off[rid] + vws;
-    const u8 *r = rd[m];
-    int s0;
-    if (s == 0) s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[i]; });
-    else s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return code_char(neg_code(r, Lm, i)); });
-    *st = vws + (u32)s0;
-    *en = rp;
-  };
+  int ch_i1[CMX_MAX_BEST], ch_j[CMX_MAX_BEST];  // chosen mappings; bit 30 of ch_i1 = direction
   for (int dir = 0; dir < 2 && reported != to_report; ++dir) {
     const int s1 = dir, s2 = 1 - dir;
     const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
     const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    pair_sweep_until(P, s1, (u32)L[0], (u32)L[1], p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) -> bool {
+    pair_sweep_until(P, s1, (u32)rm[0].len, (u32)rm[1].len, p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) -> bool {
       if (sum != pm.min_sum) return false;
-      if (idx == sel[reported]) {
-        u32 st1, en1, st2, en2;
-        span(0, s1, p1[i1], e1[i1], &st1, &en1);
-        span(1, s2, p2[j], e2[j], &st2, &en2);
-        const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
-        OutRecord o;
-        o.read_id = B.first_read_id + (u32)pair;
-        o.rid = (u32)(p1[i1] >> 32);
-        o.fragment_start = s1 == 0 ? st1 : st2;
-        o.fragment_length = (unsigned short)(s1 == 0 ? (int)(en2 - st1 + 1u) : (int)(en1 - st2 + 1u));
-        o.mapq = mapq_pe(T, e1[i1], e2[j], al1, al2, L[0], L[1], force, pm, rm);
-        o.direction = s1 == 0 ? 1 : 0;
-        o.is_unique = uniq;
-        o.num_dups = 1;
-        o.positive_alignment_length = s1 == 0 ? al1 : al2;
-        o.negative_alignment_length = s1 == 1 ? al1 : al2;
-        out[(size_t)pair * mb + reported] = o;
-        ++reported;
-      }
+      if (idx == sel[reported]) { ch_i1[reported] = i1 | (dir << 30); ch_j[reported] = j; ++reported; }
       ++idx;
       return reported == to_report;
     });
+  }
+  for (int r = 0; r < reported; ++r) {
+    const int s1 = ch_i1[r] >> 30, i1 = ch_i1[r] & 0x3FFFFFFF, j = ch_j[r];
+    const size_t b1 = ((size_t)(2 * slot + 0) * 2 + s1) * c.mc + i1, b2 = ((size_t)(2 * slot + 1) * 2 + (1 - s1)) * c.mc + j;
+    out[(size_t)pair * mb + r] = pe_record(P, R, B, T, pm, rm, pair, s1, S.map_pos[b1], S.map_err[b1], S.map_pos[b2], S.map_err[b2]);
   }
   out_n[pair] = reported;
   pm.n_rec = reported;
@@ -1579,7 +1426,7 @@ __device__ inline int cta_minimizers(const u8 *seq, int len, int k, int w, u64 *
   __syncthreads();
   int n = 0;
   if (tid == 0) {
-    if (!fast) n = gen_minimizers_any(seq, len, k, w, out_hash, out_pos, cap);
+    if (!fast) minimizer_scan_any([&](int i) { return seq[i]; }, len, k, w, [&](u64 h, u32 p_) { if (n < cap) { out_hash[n] = h; out_pos[n] = p_; } ++n; });
     else if (w == 7) n = emit_minimizers_from_seeds<7>(sh, sp, len, k, out_hash, out_pos, cap);
     else if (w == 10) n = emit_minimizers_from_seeds<10>(sh, sp, len, k, out_hash, out_pos, cap);
     else n = emit_minimizers_from_seeds<11>(sh, sp, len, k, out_hash, out_pos, cap);
@@ -1770,409 +1617,6 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
       rm.n_cand[0] = nc0; rm.n_cand[1] = nc1; rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
     }
   }
-}
-
-// index.cc:351-489 cooperatively.  Thread 0 builds the merged windows.  For a multi-occurrence minimizer the
-// reference runs, per window, a binary search that starts at the previous window's last probe (`prev_l`) and
-// then walks the occurrence list from that last probe — so the result depends on the probe path.  The path is
-// reproduced without touching memory: comparisons against a sorted list only depend on where the probe lies
-// relative to LB = first entry >= window start and LB+E (entries equal to it).  So
-//   phase 1 (all threads, one (minimizer, window) each): LB, E and UB = first entry > window end (3 searches);
-//   phase 2 (one thread per minimizer): replay the chained searches arithmetically -> first emitted index;
-//   phase 3 (all threads): emit [first, max(first, UB)) with a shared counter (order is irrelevant: sorted next).
-#define RESCUE_GROUP 8
-#define RESCUE_MAXWIN 300
-__device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv, const u32 *mmp,
-                                 const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm, int sm_cap,
-                                 u64 *win_lo, u64 *win_hi, int *s_i, int *nh_out, int *s_lb, u8 *s_eq, int *s_ub) {
-  int *s_first = s_lb;  // phase 2 overwrites LB with the first emitted index (row-private, read before written)
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    int max_cnt = 0, n_best = 0;
-    for (int i = 0; i < n_mate; ++i) {
-      const int cnt = mate_cnt[i];
-      if (cnt > max_cnt) { max_cnt = cnt; n_best = 1; }
-      else if (cnt == max_cnt) ++n_best;
-    }
-    s_i[0] = max_cnt;
-    s_i[1] = (n_best >= 300 || n_mate > P.f0 || (max_cnt <= P.min_seeds && n_best >= 200)) ? 1 : 0;
-    int nw = 0;
-    if (!s_i[1]) {
-      for (int i = 0; i < n_mate; ++i) {
-        if (mate_cnt[i] != max_cnt) continue;
-        const u64 lo = mate_pos[i] < range ? 0 : mate_pos[i] - range, hi = mate_pos[i] + range;
-        if (nw > 0 && !(win_hi[nw - 1] < lo)) win_hi[nw - 1] = hi;
-        else { win_lo[nw] = lo; win_hi[nw] = hi; ++nw; }
-      }
-    }
-    s_i[2] = nw;
-    s_i[3] = 0;  // hit counter
-  }
-  __syncthreads();
-  const int max_cnt = s_i[0];
-  *nh_out = 0;
-  if (s_i[1]) { __syncthreads(); return -max_cnt; }
-  const int nw = s_i[2];
-  // singletons: one candidate each
-  for (int mi = tid; mi < n_mm; mi += CTA_NT) {
-    if ((mmp[mi] >> 30) != 1) continue;
-    bool same;
-    const u64 cp = hit_to_candidate(P.k, mmv[mi], (mmp[mi] & 0x3FFFFFFFu) >> 1, mmp[mi] & 1u, &same);
-    if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
-  }
-  // multi-occurrence minimizers in groups of RESCUE_GROUP
-  for (int g0 = 0; g0 < n_mm; g0 += RESCUE_GROUP) {
-    const int gn = min(RESCUE_GROUP, n_mm - g0);
-    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 1
-      const int gi = t / nw, bi = t % nw, mi = g0 + gi;
-      if ((mmp[mi] >> 30) != 2) continue;
-      const u64 val = mmv[mi];
-      const u64 *O = ix.occ + (u32)(val >> 32);
-      const int n = (int)(u32)val;
-      const u64 lo = win_lo[bi], hi = win_hi[bi];
-      int a = 0, b = n;
-      while (a < b) { const int m = (a + b) >> 1; if ((__ldg(&O[m]) >> 1) < lo) a = m + 1; else b = m; }
-      const int lb = a;
-      // entries equal to `lo` and entries inside the window are few: gallop from LB instead of bisecting [LB, n)
-      auto gallop_le = [&](int from, u64 bound) {  // first index >= from with (O[idx] >> 1) > bound
-        int step = 1, lo_i = from, hi_i = from;
-        while (hi_i < n && (__ldg(&O[hi_i]) >> 1) <= bound) { lo_i = hi_i + 1; hi_i += step; step <<= 1; }
-        if (hi_i > n) hi_i = n;
-        while (lo_i < hi_i) { const int m = (lo_i + hi_i) >> 1; if ((__ldg(&O[m]) >> 1) <= bound) lo_i = m + 1; else hi_i = m; }
-        return lo_i;
-      };
-      a = gallop_le(lb, lo);
-      const int eq = a - lb;
-      a = gallop_le(a, hi);
-      s_lb[gi * RESCUE_MAXWIN + bi] = lb; s_eq[gi * RESCUE_MAXWIN + bi] = (u8)min(eq, 255); s_ub[gi * RESCUE_MAXWIN + bi] = a;
-    }
-    __syncthreads();
-    if (tid < gn && (mmp[g0 + tid] >> 30) == 2) {  // phase 2: index.cc:443-459 replayed on (LB, E)
-      const int n = (int)(u32)mmv[g0 + tid];
-      int prev_l = 0;
-      for (int bi = 0; bi < nw; ++bi) {
-        const int lb = s_lb[tid * RESCUE_MAXWIN + bi], ue = lb + s_eq[tid * RESCUE_MAXWIN + bi];
-        int l = prev_l, mid = 0, r = n - 1;
-        while (l <= r) {
-          mid = (l + r) / 2;
-          if (mid < lb) l = mid + 1;
-          else if (mid >= ue) r = mid - 1;
-          else break;
-        }
-        prev_l = mid;
-        s_first[tid * RESCUE_MAXWIN + bi] = mid;
-      }
-    }
-    __syncthreads();
-    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 3
-      const int gi = t / nw, bi = t % nw, mi = g0 + gi;
-      if ((mmp[mi] >> 30) != 2) continue;
-      const u64 val = mmv[mi];
-      const u64 *O = ix.occ + (u32)(val >> 32);
-      const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
-      const int first = s_first[gi * RESCUE_MAXWIN + bi], end = max(first, s_ub[gi * RESCUE_MAXWIN + bi]);
-      for (int oi = first; oi < end; ++oi) {
-        bool same;
-        const u64 cp = hit_to_candidate(P.k, __ldg(&O[oi]), rpos, rstrand, &same);
-        if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&s_i[3], 1); if (at < cap) hits[at] = cp; }
-      }
-    }
-    __syncthreads();
-  }
-  const int nh = s_i[3];
-  *nh_out = nh;
-  if (tid == 0) {
-    RepStats st = {0u, 0xFFFFFFFFu, 0};
-    for (int mi = 0; mi < n_mm; ++mi)
-      if ((mmp[mi] >> 30) == 2 && (u32)mmv[mi] >= (u32)P.f0) rep_update(P.k, P.w, (mmp[mi] & 0x3FFFFFFFu) >> 1, st);
-    *rep_len = st.len;
-  }
-  __syncthreads();
-  if (nh <= cap) cta_sort_keys(hits, nh, sm, sm_cap);
-  return max_cnt;
-}
-
-__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap) {
-  extern __shared__ u64 sm[];
-  __shared__ u64 win_lo[RESCUE_MAXWIN], win_hi[RESCUE_MAXWIN];
-  __shared__ int s_lb[RESCUE_GROUP * RESCUE_MAXWIN], s_ub[RESCUE_GROUP * RESCUE_MAXWIN];
-  __shared__ u8 s_eq[RESCUE_GROUP * RESCUE_MAXWIN];
-  __shared__ int s_i[8];
-  __shared__ int s_flag[4];
-  const int slot = blockIdx.x, tid = threadIdx.x;
-  PairMeta &pm = S.pmeta[slot];
-  if (pm.status != ST_OK) return;
-  const Caps c = S.caps;
-  ReadMeta *rm = S.rmeta + 2 * slot;
-  auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
-  auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
-  if (P.se) {
-    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1];
-    __syncthreads();
-    if (tid == 0) { if (rm[0].n_mm == 0 || a1 == 0) pm.status = ST_DROP; else atomicAdd(&ctr->n_candidates, (u64)a1); }
-    return;
-  }
-  if (rm[0].n_mm == 0 || rm[1].n_mm == 0) { __syncthreads(); if (tid == 0) pm.status = ST_DROP; return; }
-  if (P.split) {
-    const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1], a2 = rm[1].n_cand[0] + rm[1].n_cand[1];
-    __syncthreads();
-    if (tid == 0) { if (!(a1 > 0 && a2 > 0)) pm.status = ST_DROP; else atomicAdd(&ctr->n_candidates, (u64)(a1 + a2)); }
-    return;
-  }
-  if (tid == 0) {
-    for (int mate = 0; mate < 2; ++mate) {
-      const u32 n_mm = rm[mate].n_mm;
-      bool a = true;
-      for (int s = 0; s < 2 && a; ++s) {
-        const u8 *cc = CC(mate, 0, s);
-        for (int i = 0; i < rm[mate].n_cand[s]; ++i) if (cc[i] >= n_mm / 2) { a = false; break; }
-      }
-      s_flag[mate] = a;
-    }
-    s_flag[2] = 0;  // ret
-    s_flag[3] = 0;  // overflow
-  }
-  __syncthreads();
-  const u32 range = 2u * (u32)P.max_insert;
-  for (int mate = 0; mate < 2; ++mate) {
-    if (!s_flag[mate]) continue;
-    ReadMeta &me = rm[mate];
-    const ReadMeta &ot = rm[1 - mate];
-    const int n_mm = me.n_mm;
-    const size_t sr = 2 * slot + mate;
-    const u64 *mmv = S.mm_val + sr * c.maxmm;
-    const u32 *mmp = S.mm_pos + sr * c.maxmm;
-    u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
-    int pr = 0, nr = 0;
-    bool ovf = false;
-    if (ot.n_cand[0] > 0) {
-      int nh;
-      pr = cta_rescue(P, ix, 1, range, n_mm, mmv, mmp, CP(1 - mate, 0, 0), CC(1 - mate, 0, 0), ot.n_cand[0], &me.rep_len, hn, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh, s_lb, s_eq, s_ub);
-      if (nh > c.hc) ovf = true;
-      else {
-        const int na = cta_cluster_par(P.e, 1, (u32)n_mm, hn, nh, CP(mate, 2, 1), CC(mate, 2, 1), c.cc, sm, sm_cap, (u8 *)(sm + sm_cap), &s_i[4]);
-        if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[1] = na;
-      }
-    }
-    if (!ovf && ot.n_cand[1] > 0) {
-      int nh;
-      nr = cta_rescue(P, ix, 0, range, n_mm, mmv, mmp, CP(1 - mate, 0, 1), CC(1 - mate, 0, 1), ot.n_cand[1], &me.rep_len, hp, c.hc, sm, sm_cap, win_lo, win_hi, s_i, &nh, s_lb, s_eq, s_ub);
-      if (nh > c.hc) ovf = true;
-      else {
-        const int na = cta_cluster_par(P.e, 1, (u32)n_mm, hp, nh, CP(mate, 2, 0), CC(mate, 2, 0), c.cc, sm, sm_cap, (u8 *)(sm + sm_cap), &s_i[4]);
-        if (na > c.cc) ovf = true; else if (tid == 0) me.n_aug[0] = na;
-      }
-    }
-    if (ovf) { __syncthreads(); if (tid == 0) pm.status = ST_OVERFLOW; return; }  // uniform: every thread computed the same ovf
-    if (tid == 0 && ((pr < 0 && nr > 0 && -pr >= nr) || (pr > 0 && nr < 0 && pr <= -nr)) && me.n_cand[0] + me.n_cand[1] == 0) s_flag[2] = 1;
-    __syncthreads();
-  }
-  // merges, buffer copy and paired-end filter: the four (mate, strand) merges and the two filter directions touch
-  // disjoint lists, so each runs on its own warp's lane 0; the copy is done by everyone
-  const int wid = tid >> 5, lane = tid & 31;
-  if (tid == 0) s_flag[3] = 0;
-  __syncthreads();
-  if (lane == 0 && wid < 4) {
-    const int mate = wid >> 1, s = wid & 1;
-    ReadMeta &me = rm[mate];
-    if (me.n_aug[s] > 0) {
-      const int n = merge_cands(P.e, CP(mate, 0, s), CC(mate, 0, s), me.n_cand[s], CP(mate, 2, s), CC(mate, 2, s), me.n_aug[s],
-                                CP(mate, 1, s), CC(mate, 1, s), c.cc);
-      if (n > c.cc) s_flag[3] = 1; else me.n_cand[s] = n;
-    }
-  }
-  __syncthreads();
-  if (s_flag[3]) { if (tid == 0) pm.status = ST_OVERFLOW; return; }
-  const int nq[4] = {rm[0].n_cand[0], rm[0].n_cand[1], rm[1].n_cand[0], rm[1].n_cand[1]};
-  int nc1 = nq[0] + nq[1], nc2 = nq[2] + nq[3];
-  const bool both = nc1 > 0 && nc2 > 0;
-  if (both) {
-    for (int q = 0; q < 4; ++q) {
-      const u64 *src = CP(q >> 1, 0, q & 1);
-      const u8 *srcc = CC(q >> 1, 0, q & 1);
-      u64 *dst = CP(q >> 1, 1, q & 1);
-      u8 *dstc = CC(q >> 1, 1, q & 1);
-      for (int i = tid; i < nq[q]; i += CTA_NT) { dst[i] = src[i]; dstc[i] = srcc[i]; }
-    }
-  }
-  __syncthreads();
-  if (both && lane == 0 && wid < 2) {
-    int a, b;
-    if (wid == 0) {
-      pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), nq[0], CP(1, 1, 1), CC(1, 1, 1), nq[3], CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
-      rm[0].n_buf[0] = nq[0]; rm[1].n_buf[1] = nq[3];
-      rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
-    } else {
-      pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), nq[1], CP(1, 1, 0), CC(1, 1, 0), nq[2], CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
-      rm[0].n_buf[1] = nq[1]; rm[1].n_buf[0] = nq[2];
-      rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
-    }
-  }
-  __syncthreads();
-  if (tid != 0) return;
-  pm.sup = s_flag[2];
-  nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
-  nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
-  if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
-  atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
-}
-
-// GenerateDraftMappings for one read by one CTA: candidates sorted cooperatively, every valid candidate is
-// verified by its own thread (lane-per-candidate Myers), thread 0 then replays the reference's order-
-// dependent group / threshold rule over the stored results (verifying a candidate the reference would
-// have skipped is wasted work, never a different result).
-__global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
-  extern __shared__ u64 smk[];
-  u8 *smt = (u8 *)(smk + sm_cap);
-  __shared__ int s_done, s_status;
-  const int sr = blockIdx.x, tid = threadIdx.x;
-  const int slot = sr >> 1, mate = sr & 1;
-  if (tid == 0) s_status = S.pmeta[slot].status;  // the mate's CTA may flag the pair concurrently
-  __syncthreads();
-  if (s_status != ST_OK || (P.se && mate == 1)) return;
-  const int pair = slot_pair(S, slot);
-  ReadMeta &rm = S.rmeta[sr];
-  const Caps c = S.caps;
-  const u8 *read = read_ptr(B, pair, mate);
-  const int L = rm.len, e = P.e;
-  u64 *mp[2] = {S.map_pos + ((size_t)sr * 2 + 0) * c.mc, S.map_pos + ((size_t)sr * 2 + 1) * c.mc};
-  short *me[2] = {S.map_err + ((size_t)sr * 2 + 0) * c.mc, S.map_err + ((size_t)sr * 2 + 1) * c.mc};
-  u64 *cp[2] = {S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
-  u8 *cc[2] = {S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 1) * c.cc};
-  // per-candidate results live in the (now free) augment set: err in the count array, end position in the pos array
-  u64 *rend[2] = {S.cand_pos + (((size_t)sr * 3 + 2) * 2 + 0) * c.cc, S.cand_pos + (((size_t)sr * 3 + 2) * 2 + 1) * c.cc};
-  u8 *rerr[2] = {S.cand_cnt + (((size_t)sr * 3 + 2) * 2 + 0) * c.cc, S.cand_cnt + (((size_t)sr * 3 + 2) * 2 + 1) * c.cc};
-  const int nc[2] = {rm.n_cand[0], rm.n_cand[1]};
-  if (tid == 0) {
-    s_done = 0;
-    Tally t = {e + 1, e + 1, 0, 0};
-    if (nc[0] + nc[1] == 1) {
-      int n_all = 0, idx = 0, strand = 0;
-      for (int i = 0; i < nc[0]; ++i) if (cc[0][i] == rm.n_mm) { idx = i; ++n_all; }
-      for (int i = 0; i < nc[1]; ++i) if (cc[1][i] == rm.n_mm) { idx = i; strand = 1; ++n_all; }
-      if (n_all == 1) {
-        t.min_err = 0; t.n_best = 1; t.n_second_best = 0;
-        const u64 cpos = cp[strand][idx];
-        const u32 rid = (u32)(cpos >> 32);
-        const u32 pos = strand == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
-        if (valid_cand(e, R.len[rid], pos, (u32)L)) {
-          mp[strand][0] = strand == 0 ? cpos + (u64)L - 1 : cpos;
-          me[strand][0] = 0;
-          rm.n_map[strand] = 1; rm.n_map[1 - strand] = 0;
-          s_done = 1;
-        }
-      }
-    }
-    rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
-  }
-  __syncthreads();
-  if (s_done) return;
-  auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
-  cta_sort_pairs<u8>(cp[0], cc[0], nc[0], ~0ull, (u8)0, cless, smk, smt, sm_cap);
-  cta_sort_pairs<u8>(cp[1], cc[1], nc[1], ~0ull, (u8)0, cless, smk, smt, sm_cap);
-  u64 n_ver = 0;
-  for (int s = 0; s < 2; ++s)
-    for (int i = tid; i < nc[s]; i += CTA_NT) {
-      const u64 cpos = cp[s][i];
-      const u32 rid = (u32)(cpos >> 32);
-      const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
-      if (!valid_cand(e, R.len[rid], pos, (u32)L)) { rerr[s][i] = 255; continue; }
-      const u8 *win = R.seq + R.off[rid] + pos - e;
-      int endp = 0, err;
-      if (s == 0) err = banded_align(e, L, [&](int q) { return base_code(__ldg(win + q)); }, [&](int q) { return base_code(read[q]); }, &endp);
-      else err = banded_align(e, L, [&](int q) { return base_code(__ldg(win + q)); }, [&](int q) { return neg_code(read, L, q); }, &endp);
-      rerr[s][i] = (u8)err;
-      rend[s][i] = (u64)endp;
-      ++n_ver;
-    }
-  if (n_ver) atomicAdd(&ctr->n_verified, n_ver);
-  __syncthreads();
-  if (tid != 0) return;
-  Tally t = {rm.min_err, rm.second_min_err, rm.n_best, rm.n_second_best};
-  int nm[2] = {0, 0};
-  for (int s = 0; s < 2; ++s) {
-    auto take = [&](int i) -> bool {  // true if candidate i failed
-      const int err = rerr[s][i];
-      if (err > e) return true;
-      tally(t, err);
-      const u64 cpos = cp[s][i];
-      if (nm[s] < c.mc) {
-        mp[s][nm[s]] = s == 0 ? cpos - (u64)e + rend[s][i] : cpos - (u64)L + 1 - (u64)e + rend[s][i];
-        me[s][nm[s]] = (short)err;
-      }
-      ++nm[s];
-      return false;
-    };
-    if (nc[s] < P.lanes) {
-      for (int i = 0; i < nc[s]; ++i) if (rerr[s][i] != 255) take(i);
-      continue;
-    }
-    int group[8];
-    int ng = 0;
-    u32 threshold = 0;
-    int ci = 0;
-    while (ci < nc[s]) {
-      if (cc[s][ci] < threshold) break;
-      if (rerr[s][ci] == 255) { ++ci; continue; }
-      group[ng++] = ci; ++ci;
-      if (ng < P.lanes) continue;
-      for (int g = 0; g < ng; ++g) if (take(group[g])) threshold = cc[s][group[g]];
-      ng = 0;
-    }
-    for (int g = 0; g < ng; ++g) take(group[g]);
-  }
-  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; return; }
-  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
-  rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
-}
-
-// pairing for one pair by one CTA: the four mapping lists are sorted cooperatively, thread 0 sweeps.
-__global__ void __launch_bounds__(CTA_NT) pairing_cta_kernel(DevParams P, Scratch S, int *pair_nbest, int sm_cap) {
-  extern __shared__ u64 smk[];
-  short *smt = (short *)(smk + sm_cap);
-  const int slot = blockIdx.x, tid = threadIdx.x;
-  PairMeta &pm = S.pmeta[slot];
-  const int pair = slot_pair(S, slot);
-  if (pm.status != ST_OK) { if (tid == 0 && pm.status == ST_DROP) pair_nbest[pair] = 0; return; }
-  const Caps c = S.caps;
-  ReadMeta *rm = S.rmeta + 2 * slot;
-  if (P.se) {
-    __syncthreads();
-    if (tid == 0) {
-      if (rm[0].n_map[0] + rm[0].n_map[1] == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
-      else {
-        pm.min_sum = rm[0].min_err; pm.second_min_sum = rm[0].second_min_err; pm.n_best = rm[0].n_best; pm.n_second_best = rm[0].n_second_best;
-        pair_nbest[pair] = rm[0].n_best;
-      }
-    }
-    return;
-  }
-  if (rm[0].n_map[0] + rm[0].n_map[1] == 0 || rm[1].n_map[0] + rm[1].n_map[1] == 0) {
-    __syncthreads();
-    if (tid == 0) { pm.status = ST_DROP; pair_nbest[pair] = 0; }
-    return;
-  }
-  auto mless = [](u64 pa, short ea, u64 pb, short eb) { return pa != pb ? pa < pb : ea < eb; };
-  u64 *mp[2][2];
-  short *me[2][2];
-  for (int m = 0; m < 2; ++m)
-    for (int s = 0; s < 2; ++s) {
-      mp[m][s] = S.map_pos + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
-      me[m][s] = S.map_err + ((size_t)(2 * slot + m) * 2 + s) * c.mc;
-      cta_sort_pairs<short>(mp[m][s], me[m][s], rm[m].n_map[s], ~0ull, (short)32767, mless, smk, smt, sm_cap);
-    }
-  if (tid != 0) return;
-  int min_sum = 2 * P.e + 1, second = 2 * P.e + 1, n_best = 0, n_second = 0;
-  auto visit = [&](int, int, int sum) {
-    if (sum < min_sum) { second = min_sum; n_second = n_best; min_sum = sum; n_best = 1; }
-    else if (sum == min_sum) n_best++;
-    else if (sum == second) n_second++;
-    else if (sum < second) { second = sum; n_second = 1; }
-  };
-  pair_sweep(P, 0, (u32)rm[0].len, (u32)rm[1].len, mp[0][0], me[0][0], rm[0].n_map[0], mp[1][1], me[1][1], rm[1].n_map[1], visit);
-  pair_sweep(P, 1, (u32)rm[0].len, (u32)rm[1].len, mp[0][1], me[0][1], rm[0].n_map[1], mp[1][0], me[1][0], rm[1].n_map[0], visit);
-  pm.min_sum = min_sum; pm.second_min_sum = second; pm.n_best = n_best; pm.n_second_best = n_second;
-  pair_nbest[pair] = (n_best > P.drop_rep) ? 0 : n_best;
 }
 
 
