@@ -140,6 +140,34 @@ def gen_pairs(torch, ref, n_seq, seq_len, n_pairs, read_len, seed, dev):
     return r1.contiguous().view(-1), r2.contiguous().view(-1), off
 
 
+def gen_whitelist(torch, dev, n_wl, n_cells, bc_len, seed):
+    """BASELINE config 4: a 737 k-entry whitelist of distinct random 16-mers, reads drawn uniformly from 10 k "cells"."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    keys = torch.unique(torch.randint(0, 1 << (2 * bc_len), (int(n_wl * 1.05),), device=dev, generator=g, dtype=torch.int64))[:n_wl]
+    keys = keys[torch.randperm(keys.numel(), device=dev, generator=g)]
+    return keys, keys[:n_cells]
+
+
+def gen_barcodes(torch, cell_keys, n, bc_len, seed, dev):
+    """n barcodes (ASCII, bc_len bases each; key = 2 bits per base, first base in the high bits, utils.h:107-126) uniform over
+    the cells, 2 % with one substituted base, Phred qualities U[2, 40]."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    key = cell_keys[torch.randint(0, cell_keys.numel(), (n,), device=dev, generator=g)]
+    sh = (2 * (bc_len - 1 - torch.arange(bc_len, device=dev)))[None, :]
+    codes = (key[:, None] >> sh) & 3
+    mut = torch.rand(n, device=dev, generator=g) < 0.02
+    pos = torch.randint(0, bc_len, (n,), device=dev, generator=g)
+    add = torch.randint(1, 4, (n,), device=dev, generator=g)
+    rows = torch.nonzero(mut).squeeze(1)
+    codes[rows, pos[rows]] = (codes[rows, pos[rows]] + add[rows]) & 3
+    lut = torch.tensor(list(ACGT), dtype=torch.uint8, device=dev)
+    seq = lut[codes]
+    qual = (torch.randint(2, 41, (n, bc_len), device=dev, generator=g) + 33).to(torch.uint8)
+    return seq.contiguous().view(-1), qual.contiguous().view(-1)
+
+
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md), read in-process through NVML every
     20 ms (no fork, a few microseconds per read); falls back to one nvidia-smi query per second if NVML is missing.
@@ -296,14 +324,36 @@ def run_ours(a):
     t_index = time.time() - t0
     log("rank %d: index built on device in %.1fs: %s" % (rank, t_index, info))
     n = a.pairs_per_step
+    bc_len = 16
+    if a.barcodes:
+        wl_keys, cell_keys = gen_whitelist(torch, dev, a.whitelist_size, a.cells, bc_len, a.seed + 17)
+        # abundance table = the reference's pre-pass over the first barcodes (chromap.cc:492-548): here 2 M synthetic ones
+        sb, _ = gen_barcodes(torch, cell_keys, 2000000, bc_len, a.seed + 19, dev)
+        sh = (2 * (bc_len - 1 - torch.arange(bc_len, device=dev)))[None, :]
+        lutc = torch.zeros(256, dtype=torch.int64, device=dev)
+        for i_, ch in enumerate(ACGT):
+            lutc[ch] = i_
+        skey = (lutc[sb.view(-1, bc_len).long()] << sh).sum(1)
+        uk, cnt = torch.unique(skey, return_counts=True)
+        pos_ = torch.searchsorted(torch.sort(wl_keys).values, uk)
+        wl_sorted = torch.sort(wl_keys).values
+        ok_ = (pos_ < wl_sorted.numel()) & (wl_sorted[pos_.clamp(max=wl_sorted.numel() - 1)] == uk)
+        counts = torch.zeros(wl_sorted.numel(), dtype=torch.int64, device=dev)
+        counts[pos_[ok_]] = cnt[ok_]
+        m.upload_barcode_whitelist(wl_sorted.cpu().numpy().astype(np.uint64), counts.cpu().numpy().astype(np.uint32), int(cnt[ok_].sum()), bc_len)
     pool = max(1, min(a.steps + a.warmup, a.pool))
     # weak scaling: every rank maps its own batches (batch b -> rank b mod world)
     dev_batches, host_batches = [], []
     for b in range(pool):
         gb = b * world + rank
         r1, r2, off = gen_pairs(torch, ref, a.n_seq, seq_len, n, a.read_len, a.seed * 1000003 + gb, dev)
-        dev_batches.append((r1, r2, off))
-        host_batches.append(tuple(t.cpu().pin_memory() for t in (r1, r2, off)))
+        if a.barcodes:
+            bq = gen_barcodes(torch, cell_keys, n, bc_len, a.seed * 7000003 + gb, dev)
+            dev_batches.append((r1, r2, off) + bq)
+            host_batches.append(tuple(t.cpu().pin_memory() for t in (r1, r2, off) + bq))
+        else:
+            dev_batches.append((r1, r2, off))
+            host_batches.append(tuple(t.cpu().pin_memory() for t in (r1, r2, off)))
     torch.cuda.synchronize()
     mb = params.max_num_best_mappings
     out_dev = torch.empty(n * mb * 24, dtype=torch.uint8, device=dev)
@@ -315,15 +365,20 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(i):
-        r1, r2, off = dev_batches[i % pool]
-        _, st = m.map_batch(r1, off, r2, off, first_read_id=(i * world + rank) * n, on_device=True, n_pairs=n, out=out_dev, out_on_device=True)
+    rec_dtype = cb.PAIRS_RECORD if params.output_format == 5 else cb.PE_RECORD
+
+    def step_device(i, out=None):
+        b = dev_batches[i % pool]
+        kw = dict(barcodes=b[3], barcode_quals=b[4], bc_len=bc_len) if a.barcodes else {}
+        _, st = m.map_batch(b[0], b[2], b[1], b[2], first_read_id=(i * world + rank) * n, on_device=True, n_pairs=n,
+                            out=out_dev if out is None else out, out_on_device=True, **kw)
         return st
 
     def step_host(i):
-        r1, r2, off = host_batches[i % pool]
-        _, st = m.map_batch(r1.numpy(), off.numpy().view(np.uint32), r2.numpy(), off.numpy().view(np.uint32),
-                            first_read_id=(i * world + rank) * n, out=out_host.numpy().view(cb.PE_RECORD))
+        b = host_batches[i % pool]
+        kw = dict(barcodes=b[3].numpy(), barcode_quals=b[4].numpy(), bc_len=bc_len) if a.barcodes else {}
+        _, st = m.map_batch(b[0].numpy(), b[2].numpy().view(np.uint32), b[1].numpy(), b[2].numpy().view(np.uint32),
+                            first_read_id=(i * world + rank) * n, out=out_host.numpy().view(rec_dtype), **kw)
         return st
 
     # legs: "device" and "e2e" are the headline numbers (the library's default concurrency: the call's reference
@@ -360,9 +415,52 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         res[name] = dict(dt=dt, stage=stage, n_rec=n_rec, n_map=n_map, clocks=sampler.summary(), steps=steps)
+    # ---- the one collective of the multi-GPU path, outside the timed mapping region: duplicate removal over the
+    # records of up to four mapped batches per rank: tuple pack -> ONE ncclAllGather -> radix sort + survivor rule on the GPU
+    exchange = None
+    if params.remove_pcr_duplicates and params.output_format != 5 and not a.no_exchange:
+        try:
+            m.set_lanes(a.lanes)
+            keep = []
+            for i in range(min(4, pool)):
+                o = torch.empty(n * mb * 24, dtype=torch.uint8, device=dev)
+                st_ = step_device(a.warmup + i, out=o)
+                keep.append(o[:st_["n_records"] * 24])
+            mine = torch.cat(keep)
+            n_loc = mine.numel() // 24
+            uid = [m.comm_unique_id() if rank == 0 else None]
+            if world > 1:
+                dist.broadcast_object_list(uid, src=0)
+            m.comm_init(world, rank, uid[0])
+            surv = torch.empty_like(mine)
+            barrier()
+            n_out, xst = m.dedup_exchange(mine, n=n_loc, on_device=True, out=surv)   # warm-up (NCCL connection set-up)
+            barrier()
+            t0 = time.perf_counter()
+            n_out, xst = m.dedup_exchange(mine, n=n_loc, on_device=True, out=surv)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            vals = torch.tensor([xst["pack_ms"], xst["allgather_ms"], xst["resolve_ms"], wall * 1e3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+            pk, ag, rs, wl_ = (float(x) for x in vals.tolist())
+            exchange = {"what": "cmx_dedup_exchange over the records of %d mapped batches per rank (outside the timed mapping region)" % len(keep),
+                        "records_this_rank": n_loc, "records_global": int(xst["n_global"]), "survivors_this_rank": int(n_out),
+                        "tuple_bytes_sent_per_rank": int(xst["bytes_sent"]), "tuple_bytes_received_per_rank": int(xst["bytes_received"]),
+                        "pack_ms": round(pk, 3), "allgather_ms": round(ag, 3), "sort_resolve_ms": round(rs, 3), "call_ms": round(wl_, 3),
+                        "allgather_GBps_per_rank": round(xst["bytes_received"] / (ag * 1e-3) / 1e9, 1) if ag > 0 else None,
+                        "timing": "CUDA events on the exchange stream, max over ranks"}
+            m.comm_destroy()
+            del keep, mine, surv
+        except Exception as ex:  # NCCL missing on the box: report, do not hide
+            exchange = {"unavailable": repr(ex)[:200]}
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_baseline = cpu_port_baseline(a, m, ref, offsets, seq_len, host_batches[0])
+        if a.barcodes or params.split_alignment:
+            cpu_baseline = {"value": None, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+                            "sample": "not timed for this leg (the default chip leg and --impl reference carry the CPU numbers)"}
+        else:
+            cpu_baseline = cpu_port_baseline(a, m, ref, offsets, seq_len, host_batches[0][:3])
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -374,33 +472,49 @@ def run_ours(a):
     e2e = a.steps * n * world / ee["dt"]
     st = sr["stage"]
     ks = sr["steps"]
-    kern = {k_: st[k_] / ks for k_ in ("minimizer_ms", "probe_ms", "cluster_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms",
-                                            "select_ms", "emit_ms")}
-    kern["seed_overflow_tiers_ms"] = kern["seed_ms"] - kern["minimizer_ms"] - kern["probe_ms"] - kern["cluster_ms"]
+    kern = {k_: st[k_] / ks for k_ in ("front_ms", "cluster_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms", "select_ms", "emit_ms")}
+    kern["seed_overflow_tiers_ms"] = kern["seed_ms"] - kern["front_ms"] - kern["cluster_ms"]
     top = max((k_ for k_ in kern if k_ != "seed_ms"), key=kern.get)
     peaks, peak_src = measured_peaks()
-    # algorithmic bytes of one probe_kernel launch: 16 B per probed table slot + 24 B per minimizer
-    # (hash in, table value out, position word read + rewritten with the kind) -- from the device counters of these launches
-    probe_bytes = (st["n_probe_steps"] * 16 + st["n_minimizers"] * 24) / ks
-    achieved = probe_bytes / (kern["probe_ms"] * 1e-3) / 1e9 if kern["probe_ms"] > 0 else 0.0
-    traffic = None  # dram bytes of one launch from the committed ncu --set full capture of this same workload
-    tp = os.path.join(ROOT, "profiles", "probe_kernel_ncu.json")
+    # Roofline of the index-probe kernel = the fused front end (seed_front_kernel: read bytes in, length filter, minimizers,
+    # table probes, records out).  Algorithmic bytes of one launch, two definitions:
+    #   layout : what OUR table layout needs: 16 B per probed slot + 12 B per minimizer record written + the read bytes +
+    #            192 B of per-pair metadata written
+    #   survey : SURVEY.md 8(d)'s count for the reference's khash: 12 B per probe step + 8 B per found value (+ the read bytes)
+    read_bytes = 2.0 * a.read_len * n
+    bytes_layout = (st["n_probe_steps"] * 16 + st["n_minimizers"] * 12) / ks + read_bytes + 192.0 * n
+    bytes_survey = (st["n_probe_steps"] * 12 + st["n_found"] * 8) / ks + read_bytes
+    fk = kern["front_ms"]
+    achieved = bytes_layout / (fk * 1e-3) / 1e9 if fk > 0 else 0.0
+    achieved_survey = bytes_survey / (fk * 1e-3) / 1e9 if fk > 0 else 0.0
+    traffic = None  # dram bytes + executed warp instructions of one launch from the committed ncu --set full capture of this workload
+    warp_inst = None
+    tp = os.path.join(ROOT, "profiles", "front_kernel_ncu.json")
     if os.path.exists(tp):
         prof = json.load(open(tp))
         if prof.get("pairs_per_step") == n and abs(prof.get("ref_bp", 0) - int(ref.numel())) < 0.01 * ref.numel() and prof.get("preset") == a.preset:
-            traffic = prof["dram_bytes_per_launch"]
+            traffic = prof.get("dram_bytes_per_launch")
+            warp_inst = prof.get("warp_instructions_per_launch")
+    issue = None
+    if warp_inst and fk > 0:
+        sm_clock = (dv["clocks"].get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        peak_issue = 148 * 4 * sm_clock  # warp instructions per second: 148 SMs x 4 schedulers x 1 per clock
+        issue = {"warp_instructions_per_launch": warp_inst, "achieved_per_s": warp_inst / (fk * 1e-3), "peak_per_s": peak_issue,
+                 "frac": warp_inst / (fk * 1e-3) / peak_issue, "note": "the kernel is integer-issue bound (3 x Hash64 per k-mer), not HBM bound"}
+    cells = (st["n_verified"] / ks) * a.read_len * (2 * params.error_threshold + 1)
     line = {
         "metric": "paired-end reads mapped/sec (hg38-scale, 2x50bp)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dv["dt"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "--preset %s, synthetic %.2f Gbp reference (%d seqs, planted repeats, N runs), 2x%d bp PE pairs, %d pairs/step/GPU"
-                               % (a.preset, ref.numel() / 1e9, a.n_seq, a.read_len, n),
+        "config": {"workload": "--preset %s%s, synthetic %.2f Gbp reference (%d seqs, planted repeats, N runs), 2x%d bp PE pairs, %d pairs/step/GPU"
+                               % (a.preset, " + 16 bp cell barcodes (%d-entry whitelist)" % a.whitelist_size if a.barcodes else "", ref.numel() / 1e9, a.n_seq, a.read_len, n),
                    "preset": a.preset, "k": K_MER, "w": WINDOW, "pairs_per_step": n, "ref_bp": int(ref.numel()),
                    "index": {"keys": info["n_keys"], "occurrences": info["n_occ"], "table_slots": info["table_slots"], "build_s": round(t_index, 2)},
                    "l2": "inputs (%.0f MB reads/step) and the %.1f GB index exceed L2; distinct batches cycle through a pool of %d"
                          % (2 * a.read_len * n / 1e6, info["table_slots"] * 16 / 1e9, pool),
-                   "sharding": "batch b -> rank b mod N, index+reference replicated per GPU, no data-path collective"},
-        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * a.read_len * n + 8 * (n + 1)),
+                   "sharding": "batch b -> rank b mod N, index+reference replicated per GPU, no data-path collective in the timed region",
+                   "host": dict(host_description(), cpus_bound_to_gpu_numa_node=n_bound)},
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * a.read_len * n + 8 * (n + 1) + (2 * bc_len * n if a.barcodes else 0)),
                 "d2h_bytes_per_step": int(24 * ee["n_rec"] / a.steps), "ms_per_step": ee["dt"] / a.steps * 1e3},
         "gpu_launches": int(dv["stage"]["n_launches"]),
         "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
@@ -409,15 +523,18 @@ def run_ours(a):
         "lanes": a.lanes,
         "mapped_fraction": dv["n_map"] / (a.steps * n),
         "tier_pairs_per_step": [x / ks for x in st["tier_pairs"]],
-        "roofline": {"kernel": "probe_kernel (minimizer-index probe)", "bound": "hbm",
+        "roofline": {"kernel": "seed_front_kernel (index probe fused with length filter + minimizers, reads staged by cp.async.bulk)", "bound": "hbm",
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": probe_bytes,
-                     "kernel_ms": kern["probe_ms"], "kernel_share_of_step": kern["probe_ms"] / (sr["dt"] / ks * 1e3), "top_stage": top,
+                     "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_layout,
+                     "achieved_survey_8d": achieved_survey, "frac_survey_8d": achieved_survey / peaks["hbm_gbs"], "algorithmic_bytes_survey_8d": bytes_survey,
+                     "kernel_ms": fk, "kernel_share_of_step": fk / (sr["dt"] / ks * 1e3), "top_stage": top, "issue": issue,
                      "timed": "%d steps with one lane (every kernel alone on one stream, %.2f ms/step); the headline legs run %d overlapping lanes" % (ks, sr["dt"] / ks * 1e3, a.lanes),
                      "probe_steps_per_pair": st["n_probe_steps"] / (ks * n), "minimizers_per_pair": st["n_minimizers"] / (ks * n),
                      "verified_candidates_per_pair": st["n_verified"] / (ks * n),
-                     "cell_updates_per_s": (st["n_verified"] / ks) * a.read_len * (2 * params.error_threshold + 1) / (kern["verify_ms"] * 1e-3) if kern["verify_ms"] > 0 else None},
+                     "cell_updates_per_s": cells / (kern["verify_ms"] * 1e-3) if kern["verify_ms"] > 0 else None},
     }
+    if exchange is not None:
+        line["dedup_exchange"] = exchange
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     emit(line)
@@ -477,20 +594,31 @@ def run_reference(a):
     work = a.workdir or ("/dev/shm/chromap_b200_bench" if os.path.isdir("/dev/shm") else "/tmp/chromap_b200_bench")
     os.makedirs(work, exist_ok=True)
     t0 = time.time()
-    idx = m.download_index()
-    with open(os.path.join(work, "ref.index"), "wb") as f:  # index.cc:91-130 / khash.h:374-386 layout
-        np.array([K_MER, WINDOW], dtype=np.int32).tofile(f)
-        np.array([idx["n_keys"], idx["n_buckets"], idx["n_keys"], idx["n_keys"], int(idx["n_buckets"] * 0.77 + 0.5)], dtype=np.uint32).tofile(f)
-        idx["flags"].tofile(f); idx["keys"].tofile(f); idx["vals"].tofile(f)
-        np.array([len(idx["occ"])], dtype=np.uint32).tofile(f)
-        idx["occ"].tofile(f)
-    del idx
     href = ref.cpu().numpy()
     with open(os.path.join(work, "ref.fa"), "wb") as f:
         for i in range(a.n_seq):
             f.write(b">chr%d\n" % (i + 1))
             href[int(offsets[i]):int(offsets[i + 1])].tofile(f)
             f.write(b"\n")
+    # The index the reference binary loads.  Default: the device-built index written in the reference's file format (seconds);
+    # tests/test_gpu_parity.py::test_device_built_index_has_the_content_of_the_reference_binarys_index shows that it holds
+    # exactly what `chromap -i` builds (same occurrence table byte for byte, same key -> value map, same bucket count).
+    # --reference-index chromap lets the reference binary build it itself (minutes at 3 Gbp, single-threaded).
+    index_by = a.reference_index
+    if index_by == "chromap":
+        pr = subprocess.run([binp, "-i", "-r", os.path.join(work, "ref.fa"), "-o", os.path.join(work, "ref.index")], capture_output=True, text=True)
+        if pr.returncode != 0:
+            emit({"impl": "reference", "unavailable": "chromap -i failed: " + pr.stderr[-200:].replace("\n", " | ")})
+            return
+    else:
+        idx = m.download_index()
+        with open(os.path.join(work, "ref.index"), "wb") as f:  # index.cc:91-130 / khash.h:374-386 layout
+            np.array([K_MER, WINDOW], dtype=np.int32).tofile(f)
+            np.array([idx["n_keys"], idx["n_buckets"], idx["n_keys"], idx["n_keys"], int(idx["n_buckets"] * 0.77 + 0.5)], dtype=np.uint32).tofile(f)
+            idx["flags"].tofile(f); idx["keys"].tofile(f); idx["vals"].tofile(f)
+            np.array([len(idx["occ"])], dtype=np.uint32).tofile(f)
+            idx["occ"].tofile(f)
+        del idx
     n_batches = a.warmup + a.steps
     n = 500000  # one reference batch (chromap.h:182) per step
     L = a.read_len
@@ -532,7 +660,10 @@ def run_reference(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": "--preset %s, synthetic %.2f Gbp reference (%d seqs), 2x%d bp PE pairs; reference chromap 0.3.3 -t %d, step = one 500000-pair batch (its own per-batch timer)"
-                                   % (a.preset, total_bp / 1e9, a.n_seq, L, cores), "total_wall_s": round(wall, 1)},
+                                   % (a.preset, total_bp / 1e9, a.n_seq, L, cores), "total_wall_s": round(wall, 1),
+                       "index_built_by": "chromap -i (the reference binary)" if index_by == "chromap" else
+                                         "cmx_build_index + cmx_download_index, reference file format (content == chromap -i, tests/test_gpu_parity.py)",
+                       "per_batch_s": [round(x, 3) for x in timed], "host": host_description()},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
                              "sample": "%d batches of 500000 pairs, reference binary 'Mapped N read pairs in Xs' lines" % a.steps},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -568,7 +699,12 @@ def main():
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--cpu-sample-pairs", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="skip the duplicate-removal exchange leg")
+    ap.add_argument("--barcodes", action="store_true", help="scATAC leg (BASELINE config 4): 16 bp cell barcodes + whitelist correction")
+    ap.add_argument("--whitelist-size", type=int, default=737000)
+    ap.add_argument("--cells", type=int, default=10000)
     ap.add_argument("--workdir", default=None)
+    ap.add_argument("--reference-index", default="ours", choices=["ours", "chromap"], help="--impl reference: who builds the index the reference binary loads")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

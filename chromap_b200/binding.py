@@ -104,7 +104,7 @@ class Records(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "pair_candidates_ms", "verify_ms", "pairing_ms",
-                                         "select_ms", "emit_ms", "d2h_ms", "total_ms", "minimizer_ms", "probe_ms", "cluster_ms")] + \
+                                         "select_ms", "emit_ms", "d2h_ms", "total_ms", "front_ms", "reserved_ms", "cluster_ms")] + \
                [(n, C.c_uint64) for n in ("n_minimizers", "n_probe_steps", "n_found", "n_occ_reads", "n_verified",
                                           "n_launches")] + [("tier_pairs", C.c_uint64 * 3), ("escalations", C.c_uint64 * 8)]
 
@@ -112,6 +112,14 @@ class Timing(C.Structure):
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["tier_pairs"] = list(d["tier_pairs"]); d["escalations"] = list(d["escalations"])
         return d
+
+
+class ExchangeStats(C.Structure):
+    _fields_ = [("pack_ms", C.c_float), ("allgather_ms", C.c_float), ("resolve_ms", C.c_float), ("bytes_sent", C.c_uint64),
+                ("bytes_received", C.c_uint64), ("n_global", C.c_uint64), ("n_ranks", C.c_uint32), ("pad", C.c_uint32)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "pad"}
 
 
 PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u4"), ("fragment_length", "<u2"),
@@ -174,10 +182,17 @@ def load_library():
     L.cmx_last_batch_trace.argtypes = [vp, vp, u32]
     L.cmx_last_batch_timing.argtypes = [vp, C.POINTER(Timing)]
     L.cmx_set_lanes.argtypes = [vp, i32]
+    L.cmx_host_register.argtypes = [vp, u64]
+    L.cmx_host_unregister.argtypes = [vp]
     L.cmx_format_paf.restype = i64
     L.cmx_format_paf.argtypes = [C.POINTER(Params), vp, vp, vp, u64, vp, vp, vp, vp, u32, vp, i64]
     L.cmx_format_sam.restype = i64
     L.cmx_format_sam.argtypes = [C.POINTER(Params), vp, vp, u32, vp, vp, vp, u64, C.POINTER(ReadSet), C.POINTER(ReadSet), u32, vp, i64]
+    L.cmx_comm_unique_id.argtypes = [vp]
+    L.cmx_comm_init.argtypes = [vp, i32, i32, vp]
+    L.cmx_comm_destroy.argtypes = [vp]
+    L.cmx_dedup_exchange.argtypes = [vp, vp, vp, u64, i32, vp, vp, C.POINTER(u64), C.POINTER(ExchangeStats)]
+    L.cmx_exchange_finish.argtypes = [C.POINTER(Params), vp, vp, u64]
     L.cmx_fastq_cut.restype = u64; L.cmx_fastq_cut.argtypes = [vp, u64, u32, C.POINTER(u32)]
     L.cmx_ingest_fastq.argtypes = [vp, i32, vp, u64, i32, vp, C.POINTER(Ingested)]
     _lib = L
@@ -193,6 +208,17 @@ def make_params(preset="", **kw):
     for k, v in kw.items():
         setattr(p, k, int(v))
     return p
+
+
+def exchange_finish(params, recs, barcode_keys=None):
+    """Reference order + deferred Tn5 shift over the survivors of all ranks (host only, mapping_writer.h:285-287)."""
+    L = load_library()
+    recs = np.ascontiguousarray(recs).copy()
+    bcs = np.ascontiguousarray(barcode_keys, dtype=np.uint64).copy() if barcode_keys is not None else None
+    rc = L.cmx_exchange_finish(C.byref(params), recs.ctypes.data if len(recs) else None, _ptr(bcs), len(recs))
+    if rc != 0:
+        raise CmxError("cmx_exchange_finish failed (%d)" % rc)
+    return recs if bcs is None else (recs, bcs)
 
 
 def taskloop_chunks(n, grain=5000):
@@ -318,6 +344,54 @@ class Mapper:
         if out_on_device:
             return out, stats
         return out[:r.n_records], stats
+
+    # ---- multi-GPU exchange (one process per GPU) ----
+    @staticmethod
+    def _prefer_framework_nccl():
+        """When PyTorch is installed, load it (and with it its NCCL) before the library binds to one: the library takes the NCCL
+        the process already holds, so both sides share a copy; without PyTorch the system libnccl.so.2 is used."""
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
+    def comm_unique_id(self):
+        self._prefer_framework_nccl()
+        buf = (C.c_char * 128)()
+        rc = self.L.cmx_comm_unique_id(buf)
+        if rc != 0:
+            raise CmxError("cmx_comm_unique_id failed (%d): NCCL not available" % rc)
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        self._prefer_framework_nccl()
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._check(self.L.cmx_comm_init(self.h, n_ranks, rank, buf), "cmx_comm_init")
+
+    def comm_destroy(self):
+        self.L.cmx_comm_destroy(self.h)
+
+    def dedup_exchange(self, recs, barcode_keys=None, on_device=False, out=None, out_bc=None, n=None):
+        """This rank's records in (numpy, or device pointers / torch tensors with on_device), this rank's survivors out."""
+        if on_device:
+            cnt = int(n)
+            no = C.c_uint64()
+            st = ExchangeStats()
+            self._check(self.L.cmx_dedup_exchange(self.h, _ptr(recs), _ptr(barcode_keys), cnt, 1, _ptr(out), _ptr(out_bc), C.byref(no), C.byref(st)),
+                        "cmx_dedup_exchange")
+            return int(no.value), st.asdict()
+        recs = np.ascontiguousarray(recs)
+        o = np.zeros(max(1, len(recs)), dtype=PE_RECORD)
+        bcs = np.ascontiguousarray(barcode_keys, dtype=np.uint64) if barcode_keys is not None else None
+        obc = np.zeros(max(1, len(recs)), dtype=np.uint64) if bcs is not None else None
+        no = C.c_uint64()
+        st = ExchangeStats()
+        self._check(self.L.cmx_dedup_exchange(self.h, recs.ctypes.data if len(recs) else o.ctypes.data, _ptr(bcs), len(recs), 0, o.ctypes.data, _ptr(obc),
+                                              C.byref(no), C.byref(st)), "cmx_dedup_exchange")
+        k = int(no.value)
+        if bcs is not None:
+            return o[:k].copy(), obc[:k].copy(), st.asdict()
+        return o[:k].copy(), st.asdict()
 
     def fastq_cut(self, text, max_records):
         """(bytes, records) of the first min(max_records, complete) 4-line records of `text` (bytes / uint8 array)."""

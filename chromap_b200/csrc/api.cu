@@ -1,6 +1,7 @@
 // chromap_b200 — C-ABI implementation (include/chromap_b200.h): context, device index / reference,
 // batch pipeline driver (tiers, streams, events), stage entry points.  sm_100a.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -24,6 +25,7 @@
 #include "cta_pair_candidates.cuh"
 #include "cta_verify_pairing.cuh"
 #include "postprocess.cuh"
+#include "exchange.cuh"
 #include "sam_kernels.cuh"
 #include "ingest.cuh"
 
@@ -55,7 +57,7 @@ struct Tier {
 // the issue-bound kernels of another (minimizers, verification).
 #define CMX_MAX_LANES 4
 struct Lane {
-  DevBuf rescue_list, verify_list, nbest, sel, out_rec, out_n, offs, chunk_start, cub_tmp, bc_key, bc_ok, out_compact, bc_out;
+  DevBuf rescue_list, verify_list, emit_list, nbest, sel, out_rec, out_n, offs, chunk_start, cub_tmp, bc_key, bc_ok, out_compact, bc_out;
   Counters *ctr = nullptr;
   int *d_count = nullptr;
   Tier tiers[N_TIERS];
@@ -112,6 +114,7 @@ struct cmx_ctx {
   Lane lanes[CMX_MAX_LANES];
   IngestSlot ingest[CMX_INGEST_SLOTS];
   int sf_grid = 148;            // persistent grid of the front-end kernel: SMs x resident CTAs
+  int pcw_grid = 148 * 16;      // persistent grid of the warp-per-pair rescue pass of tier 0
   int n_lanes = CMX_MAX_LANES;  // lanes a multi-batch call is cut into (cmx_set_lanes; CMX_LANES overrides the default)
   int last_lanes_used = 0;
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
@@ -120,6 +123,9 @@ struct cmx_ctx {
   cudaEvent_t ev[4];
   cmx_timing timing;
   u32 last_n_pairs = 0;
+  // multi-GPU exchange (cmx_comm_init / cmx_dedup_exchange): an NCCL communicator of this context's own
+  void *nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
 };
 
 static int fail(cmx_ctx *c, int code, const char *fmt, ...) {
@@ -237,12 +243,16 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   CU(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
   {
-    const size_t sf_smem = 4 * seed_front_tile_bytes(mrl);
-    CU(cudaFuncSetAttribute(seed_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
+    const size_t sf_smem = seed_front_smem_bytes(mrl);
+    CU(cudaFuncSetAttribute(seed_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
+    CU(cudaFuncSetAttribute(seed_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
     int per_sm = 0, n_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_front_kernel, SF_NT, sf_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_front_kernel<true>, SF_NT, sf_smem));
     CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     ctx->sf_grid = std::max(1, per_sm) * std::max(1, n_sm);
+    int per_sm_w = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, pair_candidates_cta_kernel, 32, pair_candidates_cta_smem(64, 32, mrl, 64)));
+    ctx->pcw_grid = std::max(1, per_sm_w) * std::max(1, n_sm);
   }
   for (Lane &L : ctx->lanes) {
     L.tiers[0].caps = {mrl, 64, 32, 32};
@@ -263,7 +273,7 @@ void cmx_destroy(cmx_ctx *ctx) {
   for (DevBuf *b : {&ctx->bc_seq, &ctx->bc_qual, &ctx->seq1, &ctx->off1, &ctx->seq2, &ctx->off2, &ctx->trace}) release(*b);
   for (Lane &L : ctx->lanes) {
     cudaFree(L.ctr); cudaFree(L.d_count);
-    for (DevBuf *b : {&L.rescue_list, &L.verify_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
+    for (DevBuf *b : {&L.rescue_list, &L.verify_list, &L.emit_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
       release(*b);
     for (auto &t : L.tiers) { release(t.mem); release(t.ovf_list); }
     for (auto &e : L.ev) cudaEventDestroy(e);
@@ -327,6 +337,24 @@ static int alloc_table(cmx_ctx *ctx, u64 n_keys) {
 }
 static int table_shift(u64 n_slots) { int lg = 0; while ((1ull << lg) < n_slots) ++lg; return 64 - lg; }
 
+// The mate-guided lookup (cta_pair_candidates.cuh) relies on every occurrence list holding distinct reference positions
+// (true for any index Index::Construct builds: one k-mer per position).  Adjacent equal positions would break it: refuse.
+__global__ void occ_check_kernel(const u64 *occ, u32 n, unsigned long long *bad) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < n && (occ[i] >> 1) == (occ[i + 1] >> 1)) atomicAdd(bad, 1ull);
+}
+static int check_occurrences(cmx_ctx *ctx) {
+  if (ctx->n_occ < 2) return CMX_OK;
+  unsigned long long *d_bad = nullptr, bad = 0;
+  CU(cudaMalloc(&d_bad, 8));
+  CU(cudaMemset(d_bad, 0, 8));
+  occ_check_kernel<<<(ctx->n_occ + 255) / 256, 256>>>(ctx->occ, ctx->n_occ, d_bad);
+  CU(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_bad);
+  if (bad) return fail(ctx, CMX_ERR_INVALID, "index: %llu adjacent occurrence entries share a reference position (not an index Chromap builds)", bad);
+  return CMX_OK;
+}
+
 int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint32_t *flags, const uint64_t *keys,
                      const uint64_t *vals, const uint64_t *occ, uint32_t n_occ) {
   if (!ctx || !flags || !keys || !vals || (n_occ && !occ)) return CMX_ERR_INVALID;
@@ -363,7 +391,7 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   CU(cudaMalloc(&ctx->occ, (size_t)std::max<u32>(n_occ, 1) * sizeof(u64)));
   if (n_occ) CU(cudaMemcpy(ctx->occ, occ, (size_t)n_occ * sizeof(u64), cudaMemcpyHostToDevice));
   ctx->n_occ = n_occ; ctx->k = k; ctx->w = w;
-  return CMX_OK;
+  return check_occurrences(ctx);
 }
 
 int cmx_upload_barcode_whitelist(cmx_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint64_t num_sample, uint32_t bc_len,
@@ -418,7 +446,7 @@ int cmx_build_index(cmx_ctx *ctx, int k, int w) {
   cudaFree(ctx->slots); cudaFree(ctx->occ);
   ctx->slots = r.slots; ctx->n_slots = r.n_slots; ctx->occ = r.occ; ctx->n_occ = r.n_occ; ctx->n_keys = r.n_keys;
   ctx->k = k; ctx->w = w;
-  return CMX_OK;
+  return check_occurrences(ctx);
 }
 
 // khash geometry + layout on the device: every (key, val) re-inserted with khash's own probe sequence
@@ -653,7 +681,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       // front end: [adapter trimming] + length filter + minimizers + index probe in one kernel over staged read tiles
       // (seed_front.cuh).  When the reads arrive in pieces on the upload stream, one grid per piece starts as soon as
       // the piece has landed; the rest of the upload hides behind it.
-      const size_t sf_smem = 4 * seed_front_tile_bytes(S.caps.maxmm);
+      const size_t sf_smem = seed_front_smem_bytes(S.caps.maxmm);
       const u32 piece = J.piece_ready ? J.piece : n;
       for (u32 q = 0, p0 = 0; p0 < n; ++q, p0 += piece) {
         const u32 np = std::min(piece, n - p0);
@@ -668,7 +696,11 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
           acc.launches += 1;
         }
         const int tiles = (int)((np + SF_TILE - 1) / SF_TILE);
-        seed_front_kernel<<<std::min(tiles, ctx->sf_grid), SF_NT, sf_smem, st>>>(P, ix, B, S, L.ctr, P.trim ? 1 : 0, (int)p0, (int)(p0 + np));
+        // packed-key scan for k = 17, w = 7 and reads the key layout can address (minimizers.cuh); the run-time scan otherwise
+        if (P.k == 17 && P.w == 7 && S.caps.maxmm < (1 << 18))
+          seed_front_kernel<true><<<std::min(tiles, ctx->sf_grid), SF_NT, sf_smem, st>>>(P, ix, B, S, L.ctr, P.trim ? 1 : 0, (int)p0, (int)(p0 + np));
+        else
+          seed_front_kernel<false><<<std::min(tiles, ctx->sf_grid), SF_NT, sf_smem, st>>>(P, ix, B, S, L.ctr, P.trim ? 1 : 0, (int)p0, (int)(p0 + np));
         acc.launches += 1;
       }
     } else {
@@ -709,7 +741,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       CUL(cudaEventRecord(e1, st));
       {
         const int lcap = std::min(tier.caps.cc, 512), fcap = 2 * tier.caps.cc;
-        pair_candidates_cta_kernel<<<n_slots, CTA_NT, pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap), st>>>(P, ix, S, L.ctr, c_pc, lcap, fcap);
+        pair_candidates_cta_kernel<<<n_slots, CTA_NT, pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap), st>>>(P, ix, S, L.ctr, c_pc, lcap, fcap, nullptr, nullptr);
       }
       CUL(cudaEventRecord(e2, st));
       if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
@@ -773,7 +805,15 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     else if (sam) emit_sam_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutSam *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else if (P.se) emit_se_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
     else if (t > 0) emit_cta_kernel<<<S.n_slots, CTA_NT, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
-    else emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr);
+    else {
+      CUL(ensure(L.emit_list, (size_t)S.n_slots * mb * sizeof(int4)));
+      CUL(cudaMemsetAsync(L.d_count + 2, 0, sizeof(int), es));  // (verify's list counter: free by now)
+      emit_kernel<<<(S.n_slots + TB - 1) / TB, TB, 0, es>>>(P, R, B, T, S, (const int *)L.sel.p, (OutRecord *)L.out_rec.p, (int *)L.out_n.p, L.ctr, (int4 *)L.emit_list.p,
+                                                           L.d_count + 2);
+      // the pairs whose start coordinates need the bit-vector traceback (indels); the grid covers the worst case, idle threads leave at once
+      emit_dp_kernel<<<(unsigned)(((size_t)S.n_slots * mb + TB - 1) / TB), TB, 0, es>>>(P, R, B, T, S, (OutRecord *)L.out_rec.p, (const int4 *)L.emit_list.p, L.d_count + 2);
+      acc.launches += 1;
+    }
     if (t > 0) CUL(cudaEventRecord(L.ev_join[t - 1], es));
   }
   for (int t = 1; t < tiers_used; ++t) CUL(cudaStreamWaitEvent(st, L.ev_join[t - 1], 0));
@@ -947,7 +987,7 @@ int cmx_map_batch_pe(cmx_ctx *ctx, const cmx_batch *in, cmx_records *out, void *
   memset(&tm, 0, sizeof(tm));
   // stage times are sums over the lanes' own streams; lanes overlap, so they add up to more than total_ms
   tm.h2d_ms = ms_h2d; tm.d2h_ms = 0;  // record copies run on the lanes' own streams, overlapped with other lanes' kernels
-  tm.seed_ms = acc.ms_seed; tm.minimizer_ms = acc.ms_minimizer; tm.probe_ms = acc.ms_probe; tm.cluster_ms = acc.ms_cluster;
+  tm.seed_ms = acc.ms_seed; tm.front_ms = acc.ms_minimizer + acc.ms_probe; tm.reserved_ms = 0; tm.cluster_ms = acc.ms_cluster;
   tm.pair_candidates_ms = acc.ms_pc; tm.verify_ms = acc.ms_ver; tm.pairing_ms = acc.ms_pair; tm.select_ms = acc.ms_select; tm.emit_ms = acc.ms_emit;
   tm.total_ms = ms_call;
   tm.n_minimizers = acc.c.n_minimizers; tm.n_probe_steps = acc.c.n_probe_steps; tm.n_found = acc.c.n_found; tm.n_occ_reads = acc.c.n_occ_reads;
@@ -1026,6 +1066,15 @@ int cmx_ingest_fastq(cmx_ctx *ctx, int slot, const char *text, uint64_t n_bytes,
   out->n_reads = n; out->seq = (const char *)g.seq.p; out->off = (const uint32_t *)g.off.p; out->qual = want_qual ? (const char *)g.qual.p : nullptr;
   out->min_len = n ? hs.min_len : 0; out->max_len = hs.max_len;
   return CMX_OK;
+}
+
+int cmx_host_register(void *ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return CMX_ERR_INVALID;
+  return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? CMX_OK : CMX_ERR_CUDA;
+}
+int cmx_host_unregister(void *ptr) {
+  if (!ptr) return CMX_ERR_INVALID;
+  return cudaHostUnregister(ptr) == cudaSuccess ? CMX_OK : CMX_ERR_CUDA;
 }
 
 int cmx_set_lanes(cmx_ctx *ctx, int n_lanes) {
@@ -1419,6 +1468,197 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
 #undef PPCU
   cleanup();
   *n_out = nsel;
+  return CMX_OK;
+}
+
+// ---- multi-GPU duplicate-removal exchange (exchange.cuh) -------------------------------------------------
+// NCCL is reached through dlopen: the library has no link-time dependency on it, and inside a process that already
+// holds an NCCL (PyTorch's) that copy is the one used.  Types are declared here (ABI of nccl.h 2.x).
+namespace {
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  // an NCCL the process already holds (PyTorch's) first; otherwise CMX_NCCL_LIB, then the system library.  RTLD_LOCAL: our copy
+  // must not satisfy the symbol lookups of a framework that is loaded later and expects its own (newer) NCCL.
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+  if (!h) { const char *pth = getenv("CMX_NCCL_LIB"); if (pth && *pth) h = dlopen(pth, RTLD_NOW | RTLD_LOCAL); }
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) { api.why = std::string("libnccl.so.2 not found: ") + dlerror(); return api; }
+  api.GetUniqueId = (int (*)(NcclApi::UniqueId *))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+  api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+  api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+  if (!api.ok) api.why = "libnccl.so.2 lacks the expected symbols";
+  return api;
+}
+const int NCCL_UINT8 = 1, NCCL_UINT64 = 5;  // ncclDataType_t
+}  // namespace
+
+int cmx_comm_unique_id(void *id128) {
+  if (!id128) return CMX_ERR_INVALID;
+  NcclApi &N = nccl_api();
+  if (!N.ok) return CMX_ERR_STATE;
+  NcclApi::UniqueId id;
+  if (N.GetUniqueId(&id) != 0) return CMX_ERR_CUDA;
+  memcpy(id128, &id, 128);
+  return CMX_OK;
+}
+
+int cmx_comm_init(cmx_ctx *ctx, int n_ranks, int rank, const void *id128) {
+  if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return CMX_ERR_INVALID;
+  NcclApi &N = nccl_api();
+  if (!N.ok) return fail(ctx, CMX_ERR_STATE, "NCCL unavailable: %s", N.why.c_str());
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->nccl_comm) { N.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  NcclApi::UniqueId id;
+  memcpy(&id, id128, 128);
+  const int rc = N.CommInitRank(&ctx->nccl_comm, n_ranks, id, rank);
+  if (rc != 0) return fail(ctx, CMX_ERR_CUDA, "ncclCommInitRank: %s", N.GetErrorString ? N.GetErrorString(rc) : "error");
+  ctx->comm_rank = rank; ctx->comm_size = n_ranks;
+  return CMX_OK;
+}
+
+int cmx_comm_destroy(cmx_ctx *ctx) {
+  if (!ctx) return CMX_ERR_INVALID;
+  if (ctx->nccl_comm) { nccl_api().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  ctx->comm_rank = 0; ctx->comm_size = 1;
+  return CMX_OK;
+}
+
+// This rank's records in, this rank's survivors out (reference order, duplicate counts set, MAPQ-filtered, Tn5 NOT yet
+// applied: the low-memory merge shifts after the final ordering, mapping_writer.h:285-287 — cmx_exchange_finish below).
+int cmx_dedup_exchange(cmx_ctx *ctx, const void *records, const uint64_t *barcode_keys, uint64_t n, int on_device, void *out_records,
+                       uint64_t *out_barcode_keys, uint64_t *n_out, cmx_exchange_stats *stats) {
+  if (!ctx || (!records && n) || !out_records || !n_out) return CMX_ERR_INVALID;
+  *n_out = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const cmx_params &p = ctx->params;
+  if (p.output_format == 5 || p.single_end || !p.low_memory_mode)
+    return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_exchange: paired-end BED records in low-memory mode only (every preset with duplicate removal)");
+  if (!ctx->nccl_comm) return fail(ctx, CMX_ERR_STATE, "cmx_dedup_exchange: cmx_comm_init first");
+  if (n >= 0x7FFFFFFFull) return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_exchange: more than 2^31-1 records on one rank");
+  NcclApi &N = nccl_api();
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool bc = barcode_keys != nullptr;
+  const int tw = bc ? 3 : 2, R = ctx->comm_size, rank = ctx->comm_rank;
+  PpRecord *d_rec = nullptr, *d_out = nullptr;
+  u64 *d_bc = nullptr, *d_outbc = nullptr, *d_cnt = nullptr, *d_send = nullptr, *d_all = nullptr, *d_k0 = nullptr, *d_k1 = nullptr, *d_nsel = nullptr;
+  u32 *d_i0 = nullptr, *d_i1 = nullptr, *d_sel = nullptr, *d_selc = nullptr;
+  u8 *d_head = nullptr, *d_keep = nullptr, *d_dups = nullptr, *d_dupsc = nullptr;
+  void *d_tmp = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto cleanup = [&]() {
+    if (!on_device) { cudaFree(d_rec); cudaFree(d_bc); cudaFree(d_out); cudaFree(d_outbc); }
+    cudaFree(d_cnt); cudaFree(d_send); cudaFree(d_all); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_nsel); cudaFree(d_i0); cudaFree(d_i1);
+    cudaFree(d_sel); cudaFree(d_selc); cudaFree(d_head); cudaFree(d_keep); cudaFree(d_dups); cudaFree(d_dupsc); cudaFree(d_tmp);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+  };
+#define XCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+#define XNC(call) do { int r_ = (call); if (r_ != 0) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, N.GetErrorString ? N.GetErrorString(r_) : "NCCL error"); } } while (0)
+  for (auto &e : ev) XCU(cudaEventCreate(&e));
+  if (on_device) { d_rec = (PpRecord *)records; d_bc = (u64 *)barcode_keys; d_out = (PpRecord *)out_records; d_outbc = (u64 *)out_barcode_keys; }
+  else {
+    XCU(cudaMalloc(&d_rec, std::max<u64>(n, 1) * sizeof(PpRecord))); XCU(cudaMalloc(&d_out, std::max<u64>(n, 1) * sizeof(PpRecord)));
+    XCU(cudaMemcpyAsync(d_rec, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
+    if (bc) { XCU(cudaMalloc(&d_bc, std::max<u64>(n, 1) * 8)); XCU(cudaMalloc(&d_outbc, std::max<u64>(n, 1) * 8)); XCU(cudaMemcpyAsync(d_bc, barcode_keys, n * 8, cudaMemcpyHostToDevice, st)); }
+  }
+  // sizes: an 8-byte all-gather of the record counts
+  XCU(cudaMalloc(&d_cnt, (size_t)(R + 1) * 8));
+  XCU(cudaMemcpyAsync(d_cnt + R, &n, 8, cudaMemcpyHostToDevice, st));
+  XNC(N.AllGather(d_cnt + R, d_cnt, 1, NCCL_UINT64, ctx->nccl_comm, st));
+  std::vector<u64> cnt(R);
+  XCU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+  XCU(cudaStreamSynchronize(st));
+  u64 n_pad = 1, n_total = 0;
+  for (u64 c : cnt) { n_pad = std::max(n_pad, c); n_total += c; }
+  const u64 n_all = n_pad * (u64)R;
+  if (n_all >= 0xFFFFFFFFull) { cleanup(); return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_exchange: %llu gathered tuples exceed 2^32", (unsigned long long)n_all); }
+  // pack -> ONE all-gather of the tuples -> sort -> decide
+  XCU(cudaMalloc(&d_send, n_pad * tw * 8)); XCU(cudaMalloc(&d_all, n_all * tw * 8));
+  XCU(cudaMalloc(&d_k0, n_all * 8)); XCU(cudaMalloc(&d_k1, n_all * 8)); XCU(cudaMalloc(&d_i0, n_all * 4)); XCU(cudaMalloc(&d_i1, n_all * 4));
+  XCU(cudaMalloc(&d_head, n_all)); XCU(cudaMalloc(&d_keep, n_all)); XCU(cudaMalloc(&d_dups, n_all)); XCU(cudaMalloc(&d_dupsc, std::max<u64>(n, 1)));
+  XCU(cudaMalloc(&d_sel, n_all * 4)); XCU(cudaMalloc(&d_selc, std::max<u64>(n, 1) * 4)); XCU(cudaMalloc(&d_nsel, 16));
+  XCU(cudaEventRecord(ev[0], st));
+  ex_pack_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(d_rec, d_bc, n, n_pad, bc ? 1 : 0, d_send);
+  XCU(cudaEventRecord(ev[1], st));
+  XNC(N.AllGather(d_send, d_all, n_pad * tw * 8, NCCL_UINT8, ctx->nccl_comm, st));
+  XCU(cudaEventRecord(ev[2], st));
+  const unsigned nb = (unsigned)((n_all + 255) / 256);
+  pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n_all);
+  cub::DoubleBuffer<u64> dk(d_k0, d_k1);
+  cub::DoubleBuffer<u32> di(d_i0, d_i1);
+  size_t tmp_bytes = 0, need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, (int)n_all, 0, 64, st);
+  cub::DeviceSelect::Flagged(nullptr, need, d_sel, d_keep, d_selc, d_nsel, (int)n_all, st);
+  tmp_bytes = std::max(tmp_bytes, need);
+  XCU(cudaMalloc(&d_tmp, tmp_bytes));
+  // least significant key first, every pass stable: bulk (b, a); barcoded (low 48 bits of b, barcode, length, a)
+  const int passes_bulk[2] = {4, 3}, passes_bc[4] = {0, 1, 2, 3};
+  for (int q = 0; q < (bc ? 4 : 2); ++q) {
+    const int pass = bc ? passes_bc[q] : passes_bulk[q];
+    ex_key_kernel<<<nb, 256, 0, st>>>(d_all, tw, pass, di.Current(), n_all, dk.Current());
+    XCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dk, di, (int)n_all, 0, pass == 2 ? 16 : 64, st));
+  }
+  // padding sorts last (a = ~0): only the first n_total sorted entries are records
+  if (n_total) {
+    const unsigned nbt = (unsigned)((n_total + 255) / 256);
+    ex_head_kernel<<<nbt, 256, 0, st>>>(d_all, tw, p.remove_pcr_duplicates, di.Current(), n_total, d_head);
+    ex_resolve_kernel<<<nbt, 256, 0, st>>>(d_all, tw, di.Current(), d_head, n_total, n_pad, rank, p.mapq_threshold, d_keep, d_sel, d_dups);
+    XCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_sel, d_keep, d_selc, d_nsel, (int)n_total, st));
+    XCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_dups, d_keep, d_dupsc, d_nsel + 1, (int)n_total, st));
+  } else XCU(cudaMemsetAsync(d_nsel, 0, 16, st));
+  u64 nsel = 0;
+  XCU(cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, st));
+  XCU(cudaStreamSynchronize(st));
+  if (nsel) ex_gather_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, st>>>(d_rec, d_bc, d_selc, d_dupsc, p.remove_pcr_duplicates, nsel, d_out, bc ? d_outbc : nullptr);
+  XCU(cudaEventRecord(ev[3], st));
+  if (!on_device && nsel) {
+    XCU(cudaMemcpyAsync(out_records, d_out, nsel * sizeof(PpRecord), cudaMemcpyDeviceToHost, st));
+    if (bc && out_barcode_keys) XCU(cudaMemcpyAsync(out_barcode_keys, d_outbc, nsel * 8, cudaMemcpyDeviceToHost, st));
+  }
+  XCU(cudaStreamSynchronize(st));
+  XCU(cudaGetLastError());
+  if (stats) {
+    cudaEventElapsedTime(&stats->pack_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&stats->allgather_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->resolve_ms, ev[2], ev[3]);
+    stats->bytes_sent = n_pad * tw * 8; stats->bytes_received = n_all * tw * 8; stats->n_global = n_total; stats->n_ranks = (uint32_t)R;
+  }
+#undef XCU
+#undef XNC
+  cleanup();
+  *n_out = nsel;
+  return CMX_OK;
+}
+
+// Last step after the survivors of all ranks have been brought together (e.g. on rank 0): reference order and the deferred
+// Tn5 shift (mapping_writer.h:285-287).  Host only (no device needed), in place.
+int cmx_exchange_finish(const cmx_params *params, cmx_pe_record *recs, uint64_t *bcs, uint64_t n) {
+  if (!params || (!recs && n)) return CMX_ERR_INVALID;
+  std::vector<u64> order(n);
+  for (u64 i = 0; i < n; ++i) order[i] = i;
+  auto key = [&](u64 i) { const cmx_pe_record &r = recs[i]; return std::make_tuple(r.rid, r.fragment_start, r.fragment_length, bcs ? bcs[i] : 0ull, r.mapq, r.direction, r.is_unique, r.read_id); };
+  std::stable_sort(order.begin(), order.end(), [&](u64 x, u64 y) { return key(x) < key(y); });
+  std::vector<cmx_pe_record> tmp(n);
+  std::vector<u64> tb(bcs ? n : 0);
+  for (u64 i = 0; i < n; ++i) { tmp[i] = recs[order[i]]; if (bcs) tb[i] = bcs[order[i]]; }
+  for (u64 i = 0; i < n; ++i) { recs[i] = tmp[i]; if (bcs) bcs[i] = tb[i]; if (params->tn5_shift) tn5(recs[i]); }
   return CMX_OK;
 }
 

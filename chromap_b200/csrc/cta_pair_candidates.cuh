@@ -10,6 +10,7 @@
 // ---- CTA-wide scans (one value per thread) ---------------------------------------------------------------------
 // exclusive prefix sum; *total = sum over the CTA.  s_warp: CTA_NT / 32 ints.
 __device__ __forceinline__ int cta_scan_add(int v, int *s_warp, int *total) {
+  const int NT = blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int x = v;
 #pragma unroll
@@ -17,14 +18,14 @@ __device__ __forceinline__ int cta_scan_add(int v, int *s_warp, int *total) {
   if (lane == 31) s_warp[wid] = x;
   __syncthreads();
   int base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < CTA_NT / 32; ++i) { const int w = s_warp[i]; if (i < wid) base += w; tot += w; }
+for (int i = 0; i < (NT >> 5); ++i) { const int w = s_warp[i]; if (i < wid) base += w; tot += w; }
   __syncthreads();
   *total = tot;
   return base + x - v;
 }
 // exclusive prefix maximum of non-negative ints (identity 0); *total = maximum over the CTA.
 __device__ __forceinline__ int cta_scan_max(int v, int *s_warp, int *total) {
+  const int NT = blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int x = v;
 #pragma unroll
@@ -32,8 +33,7 @@ __device__ __forceinline__ int cta_scan_max(int v, int *s_warp, int *total) {
   if (lane == 31) s_warp[wid] = x;
   __syncthreads();
   int base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < CTA_NT / 32; ++i) { const int w = s_warp[i]; if (i < wid) base = max(base, w); tot = max(tot, w); }
+for (int i = 0; i < (NT >> 5); ++i) { const int w = s_warp[i]; if (i < wid) base = max(base, w); tot = max(tot, w); }
   __syncthreads();
   *total = tot;
   const int prev = __shfl_up_sync(0xffffffffu, x, 1);
@@ -53,13 +53,14 @@ __device__ __forceinline__ int cta_scan_max(int v, int *s_warp, int *total) {
 // entries (shared or global).  Returns the merged size (the caller treats > cap as overflow, like the reference).
 __device__ inline int cta_merge_cands(int e, const u64 *p1, const u8 *c1, int n1, const u64 *p2, const u8 *c2, int n2, u64 *mp, u8 *mc, u8 *kf, u64 *op,
                                       u8 *oc, int cap, int *s_warp) {
+  const int NT = blockDim.x;
   const int tid = threadIdx.x;
   if (n1 == 0) {  // candidate_processor.cc:349-352: plain copy, no spacing rule
-    for (int i = tid; i < n2 && i < cap; i += CTA_NT) { op[i] = p2[i]; oc[i] = c2[i]; }
+    for (int i = tid; i < n2 && i < cap; i += NT) { op[i] = p2[i]; oc[i] = c2[i]; }
     __syncthreads();
     return n2;
   }
-  for (int i = tid; i < n1; i += CTA_NT) {
+  for (int i = tid; i < n1; i += NT) {
     const u64 p = p1[i];
     int a = 0, b = n2;
     while (a < b) { const int m = (a + b) >> 1; if (p2[m] < p) a = m + 1; else b = m; }
@@ -67,7 +68,7 @@ __device__ inline int cta_merge_cands(int e, const u64 *p1, const u8 *c1, int n1
     if (a < n2 && p2[a] == p && c2[a] > c) c = c2[a];
     mp[i + a] = p; mc[i + a] = c;
   }
-  for (int j = tid; j < n2; j += CTA_NT) {
+  for (int j = tid; j < n2; j += NT) {
     const u64 p = p2[j];
     int a = 0, b = n1;
     while (a < b) { const int m = (a + b) >> 1; if (p1[m] <= p) a = m + 1; else b = m; }
@@ -75,7 +76,7 @@ __device__ inline int cta_merge_cands(int e, const u64 *p1, const u8 *c1, int n1
   }
   __syncthreads();
   const int m = n1 + n2;
-  const int C = (m + CTA_NT - 1) / CTA_NT;
+  const int C = (m + NT - 1) / NT;
   const int r0 = min(m, tid * C), r1 = min(m, r0 + C);
   int mine = 0;
   for (int i = r0; i < r1; ++i) {
@@ -113,8 +114,9 @@ __device__ inline int cta_merge_cands(int e, const u64 *p1, const u8 *c1, int n1
 // qualifying unpaired entries (the first 5 survive), and a compaction.  f1 / f2: byte flags, n1 / n2 entries.
 __device__ inline void cta_pe_filter(u32 dist, const u64 *p1, const u8 *c1, int n1, const u64 *p2, const u8 *c2, int n2, u64 *o1p, u8 *o1c, int *na,
                                      u64 *o2p, u8 *o2c, int *nb, u8 *f1, u8 *f2, int *s_warp) {
+  const int NT = blockDim.x;
   const int tid = threadIdx.x;
-  for (int i = tid; i < n1; i += CTA_NT) {
+  for (int i = tid; i < n1; i += NT) {
     const u64 p = p1[i];
     int a = 0, b = n2;
     while (a < b) { const int m = (a + b) >> 1; if (p > p2[m] + dist) a = m + 1; else b = m; }
@@ -126,7 +128,7 @@ __device__ inline void cta_pe_filter(u32 dist, const u64 *p1, const u8 *c1, int 
     }
     f1[i] = f;
   }
-  for (int j = tid; j < n2; j += CTA_NT) {
+  for (int j = tid; j < n2; j += NT) {
     const u64 q = p2[j];
     int a = 0, b = n1;
     while (a < b) { const int m = (a + b) >> 1; if (q > p1[m] + dist) a = m + 1; else b = m; }
@@ -139,7 +141,7 @@ __device__ inline void cta_pe_filter(u32 dist, const u64 *p1, const u8 *c1, int 
     f2[j] = f;
   }
   __syncthreads();
-  const int C1 = (n1 + CTA_NT - 1) / CTA_NT, C2 = (n2 + CTA_NT - 1) / CTA_NT;
+  const int C1 = (n1 + NT - 1) / NT, C2 = (n2 + NT - 1) / NT;
   const int a0 = min(n1, tid * C1), a1 = min(n1, a0 + C1), b0 = min(n2, tid * C2), b1 = min(n2, b0 + C2);
   // running maxima (one scan per list) and paired counts (both lists packed into one scan: list sizes < 2^15)
   int mx = 0, np = 0;
@@ -185,36 +187,48 @@ __device__ inline void cta_pe_filter(u32 dist, const u64 *p1, const u8 *c1, int 
 // ---- mate-guided lookup (index.cc:351-489), cooperatively --------------------------------------------------------
 // The windows around the mate's best candidates come from its (staged) list.  For a multi-occurrence minimizer the
 // reference runs, per window, a binary search that starts at the previous window's last probe (`prev_l`) and then
-// walks the occurrence list from that last probe — so the result depends on the probe path.  The path is
-// reproduced without touching memory: comparisons against a sorted list only depend on where the probe lies
-// relative to LB = first entry >= window start and LB+E (entries equal to it).  So
-//   phase 1 (all threads, one (minimizer, window) each): LB, E and UB = first entry > window end (3 searches);
-//   phase 2 (one thread per minimizer): replay the chained searches arithmetically -> first emitted index;
-//   phase 3 (all threads): emit [first, max(first, UB)) with a shared counter (order is irrelevant: sorted next).
-// Minimizers are taken in groups so that group size x windows <= RESCUE_CELLS.
+// walks the occurrence list from that last probe (index.cc:443-479) — so what is emitted depends on the probe path, and
+// the path of window b depends on the result of window b-1.  The dependency is thin, though:
+//   * comparisons against a sorted list only depend on where the probe lies relative to LB = first entry >= window start and
+//     E = number of entries equal to it; occurrence entries are distinct positions (one k-mer per reference position, Hash64
+//     is a bijection on k-mers; cmx_upload_index / cmx_build_index verify it and refuse an index that breaks it), so E is 0 or 1;
+//   * with E = 0 the search ends with l = LB, r = LB - 1 and its last probe is LB - 1 or LB (which one depends on the path);
+//     with E = 1 it stops on LB.  So window b can only be entered with prev_l = LB(b-1) - 1 or LB(b-1).
+// One WARP takes one minimizer, one LANE one window: lane b finds LB, E and UB = first entry > window end in the occurrence
+// list (the only memory accesses), replays the search arithmetically for both possible entries, and the chain through
+// the windows is a prefix "scan" over 2-state transition functions (5 shuffle steps).  Emission [first, max(first, UB))
+// goes through a shared counter (order is irrelevant: the hits are sorted next).  No block barrier inside.
 #define RESCUE_MAXWIN 300
-#define RESCUE_CELLS 1024
 struct RescueShared {
   u64 win_lo[RESCUE_MAXWIN], win_hi[RESCUE_MAXWIN];
-  int lb[RESCUE_CELLS], ub[RESCUE_CELLS];
-  u8 eq[RESCUE_CELLS];
   int i[8];
-  int warp[CTA_NT / 32];
+  int warp[4];
 };
+__device__ __forceinline__ int rescue_replay(int l, int n, int lb, int ue) {  // index.cc:443-459 on (LB, E): the last probe
+  int mid = 0, r = n - 1;
+  while (l <= r) {
+    mid = (l + r) / 2;
+    if (mid < lb) l = mid + 1;
+    else if (mid >= ue) r = mid - 1;
+    else break;
+  }
+  return mid;
+}
 // mmv / mmp: this read's minimizer records (shared memory).  mate_pos / mate_cnt: the mate's candidates on the strand
 // that guides the search.  Returns +max count or -max count (bail-out, index.cc:371-380) on every thread; *nh_out =
 // number of hits appended to `hits` (global, sorted here when they fit `cap`).
 __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int strand, u32 range, int n_mm, const u64 *mmv, const u32 *mmp,
                                  const u64 *mate_pos, const u8 *mate_cnt, int n_mate, u32 *rep_len, u64 *hits, int cap, u64 *sm, int sm_cap,
                                  RescueShared &R, int *nh_out) {
-  const int tid = threadIdx.x;
+  const int NT = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // best count and how many candidates carry it
   int mx = 0;
-  for (int i = tid; i < n_mate; i += CTA_NT) mx = max(mx, (int)mate_cnt[i]);
+  for (int i = tid; i < n_mate; i += NT) mx = max(mx, (int)mate_cnt[i]);
   int max_cnt;
   cta_scan_max(mx, R.warp, &max_cnt);
   int nb = 0;
-  for (int i = tid; i < n_mate; i += CTA_NT) nb += mate_cnt[i] == max_cnt;
+  for (int i = tid; i < n_mate; i += NT) nb += mate_cnt[i] == max_cnt;
   int n_best;
   cta_scan_add(nb, R.warp, &n_best);
   *nh_out = 0;
@@ -233,72 +247,69 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
   __syncthreads();
   const int nw = R.i[2];
   // singletons: one candidate each
-  for (int mi = tid; mi < n_mm; mi += CTA_NT) {
+  for (int mi = tid; mi < n_mm; mi += NT) {
     if ((mmp[mi] >> 30) != 1) continue;
     bool same;
     const u64 cp = hit_to_candidate(P.k, mmv[mi], (mmp[mi] & 0x3FFFFFFFu) >> 1, mmp[mi] & 1u, &same);
     if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&R.i[3], 1); if (at < cap) hits[at] = cp; }
   }
-  const int group = max(1, RESCUE_CELLS / max(nw, 1));
-  for (int g0 = 0; g0 < n_mm; g0 += group) {
-    const int gn = min(group, n_mm - g0);
-    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 1
-      const int gi = t / nw, bi = t % nw, mi = g0 + gi;
-      if ((mmp[mi] >> 30) != 2) continue;
-      const u64 val = mmv[mi];
-      const u64 *O = ix.occ + (u32)(val >> 32);
-      const int n = (int)(u32)val;
-      const u64 lo = R.win_lo[bi], hi = R.win_hi[bi];
-      int a = 0, b = n;
-      while (a < b) { const int m = (a + b) >> 1; if ((__ldg(&O[m]) >> 1) < lo) a = m + 1; else b = m; }
-      const int lb = a;
-      // entries equal to `lo` and entries inside the window are few: gallop from LB instead of bisecting [LB, n)
-      auto gallop_le = [&](int from, u64 bound) {  // first index >= from with (O[idx] >> 1) > bound
-        int step = 1, lo_i = from, hi_i = from;
-        while (hi_i < n && (__ldg(&O[hi_i]) >> 1) <= bound) { lo_i = hi_i + 1; hi_i += step; step <<= 1; }
+  // multi-occurrence minimizers: one warp each
+  for (int mi = wid; mi < n_mm; mi += (NT >> 5)) {
+    if ((mmp[mi] >> 30) != 2) continue;
+    const u64 val = mmv[mi];
+    const u64 *O = ix.occ + (u32)(val >> 32);
+    const int n = (int)(u32)val;
+    const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
+    int c_lb = 0, c_e = 0, c_s = 0;  // window before this chunk: LB, E and which of {LB - 1, LB} its last probe was
+    for (int b0 = 0; b0 < nw; b0 += 32) {
+      const int b = b0 + lane;
+      const bool live = b < nw;
+      int lb = 0, eq = 0, ub = 0;
+      if (live) {
+        const u64 lo = R.win_lo[b], hi = R.win_hi[b];
+        int a = 0, z = n;
+        while (a < z) { const int m = (a + z) >> 1; if ((__ldg(&O[m]) >> 1) < lo) a = m + 1; else z = m; }
+        lb = a;
+        eq = (lb < n && (__ldg(&O[lb]) >> 1) == lo) ? 1 : 0;  // distinct positions (checked when the index is installed): E <= 1
+        // entries inside the window are few: gallop from LB + E instead of bisecting [LB, n)
+        int step = 1, lo_i = lb + eq, hi_i = lb + eq;
+        while (hi_i < n && (__ldg(&O[hi_i]) >> 1) <= hi) { lo_i = hi_i + 1; hi_i += step; step <<= 1; }
         if (hi_i > n) hi_i = n;
-        while (lo_i < hi_i) { const int m = (lo_i + hi_i) >> 1; if ((__ldg(&O[m]) >> 1) <= bound) lo_i = m + 1; else hi_i = m; }
-        return lo_i;
-      };
-      a = gallop_le(lb, lo);
-      const int eq = a - lb;
-      a = gallop_le(a, hi);
-      R.lb[t] = lb; R.eq[t] = (u8)min(eq, 255); R.ub[t] = a;
-    }
-    __syncthreads();
-    for (int gi = tid; gi < gn; gi += CTA_NT) {  // phase 2: index.cc:443-459 replayed on (LB, E); LB becomes the first emitted index
-      if ((mmp[g0 + gi] >> 30) != 2) continue;
-      const int n = (int)(u32)mmv[g0 + gi];
-      int prev_l = 0;
-      for (int bi = 0; bi < nw; ++bi) {
-        const int lb = R.lb[gi * nw + bi], ue = lb + R.eq[gi * nw + bi];
-        int l = prev_l, mid = 0, r = n - 1;
-        while (l <= r) {
-          mid = (l + r) / 2;
-          if (mid < lb) l = mid + 1;
-          else if (mid >= ue) r = mid - 1;
-          else break;
+        while (lo_i < hi_i) { const int m = (lo_i + hi_i) >> 1; if ((__ldg(&O[m]) >> 1) <= hi) lo_i = m + 1; else hi_i = m; }
+        ub = lo_i;
+      }
+      // the window before this lane's
+      int p_lb = __shfl_up_sync(0xffffffffu, lb, 1), p_e = __shfl_up_sync(0xffffffffu, eq, 1);
+      if (lane == 0) { p_lb = c_lb; p_e = c_e; }
+      // transition: state s = "the last probe was LB (1) or LB - 1 (0)"; f = (new state if old state 0) | (.. if old state 1) << 1
+      u32 f = 2u;  // identity for lanes past the last window
+      if (live) {
+        int o0, o1;
+        if (b == 0) o0 = o1 = rescue_replay(0, n, lb, lb + eq);  // the first window starts from 0
+        else {
+          o1 = rescue_replay(p_lb, n, lb, lb + eq);
+          o0 = p_e ? o1 : rescue_replay(max(p_lb - 1, 0), n, lb, lb + eq);
         }
-        prev_l = mid;
-        R.lb[gi * nw + bi] = mid;
+        f = (o0 == lb ? 1u : 0u) | (o1 == lb ? 2u : 0u);
       }
-    }
-    __syncthreads();
-    for (int t = tid; t < gn * nw; t += CTA_NT) {  // phase 3
-      const int gi = t / nw, mi = g0 + gi;
-      if ((mmp[mi] >> 30) != 2) continue;
-      const u64 val = mmv[mi];
-      const u64 *O = ix.occ + (u32)(val >> 32);
-      const u32 rpos = (mmp[mi] & 0x3FFFFFFFu) >> 1, rstrand = mmp[mi] & 1u;
-      const int first = R.lb[t], end = max(first, R.ub[t]);
-      for (int oi = first; oi < end; ++oi) {
-        bool same;
-        const u64 cp = hit_to_candidate(P.k, __ldg(&O[oi]), rpos, rstrand, &same);
-        if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&R.i[3], 1); if (at < cap) hits[at] = cp; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 g = __shfl_up_sync(0xffffffffu, f, o);  // the function of the lanes before: apply it first
+        if (lane >= o) f = (((f >> (g & 1u)) & 1u)) | (((f >> ((g >> 1) & 1u)) & 1u) << 1);
       }
+      const int s_out = (int)((f >> c_s) & 1u);
+      if (live) {
+        const int first = lb - 1 + s_out, end = max(first, ub);
+        for (int oi = first; oi < end; ++oi) {
+          bool same;
+          const u64 cp = hit_to_candidate(P.k, __ldg(&O[oi]), rpos, rstrand, &same);
+          if ((same && strand == 0) || (!same && strand == 1)) { const int at = atomicAdd(&R.i[3], 1); if (at < cap) hits[at] = cp; }
+        }
+      }
+      c_lb = __shfl_sync(0xffffffffu, lb, 31); c_e = __shfl_sync(0xffffffffu, eq, 31); c_s = __shfl_sync(0xffffffffu, s_out, 31);
     }
-    __syncthreads();
   }
+  __syncthreads();
   const int nh = R.i[3];
   *nh_out = nh;
   if (tid == 0) {
@@ -313,15 +324,15 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// One CTA per pair.  Dynamic shared memory (bytes): sort buffer sm_cap * 8 | cluster / merge flags 3 * sm_cap |
+// One CTA per pair: CTA_NT threads in the overflow tiers; ONE WARP per pair (blockDim = 32, `list` = the pairs to take) for
+// the tier-0 pairs that need the mate-guided lookup — the block-wide primitives above size themselves from blockDim.  Dynamic shared memory (bytes): sort buffer sm_cap * 8 | cluster / merge flags 3 * sm_cap |
 // four staged candidate lists lcap * 8 each | minimizer values maxmm * 8 | minimizer words maxmm * 4 | list counts
 // 4 * lcap | filter flags 2 * fcap.  Lists longer than lcap stay in global memory (same code, other pointers).
 __host__ __device__ inline size_t pair_candidates_cta_smem(int sm_cap, int lcap, int maxmm, int fcap) {
   return (size_t)sm_cap * 11 + (size_t)lcap * 4 * 9 + (size_t)maxmm * 12 + (size_t)fcap * 2 + 64;
 }
-__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap, int lcap, int fcap) {
-  extern __shared__ u64 sm[];
-  __shared__ RescueShared RS;
+__device__ inline void pair_candidates_cta_pair(const DevParams &P, const DevIndex &ix, const Scratch &S, Counters *ctr, int sm_cap, int lcap, int fcap,
+                                                int slot, u64 *sm, RescueShared &RS) {
   const Caps c = S.caps;
   u8 *aux = (u8 *)(sm + sm_cap);                               // 3 * sm_cap bytes (multiple of 8: sm_cap is a power of two >= 8)
   u64 *s_lp = (u64 *)(aux + 3 * (size_t)sm_cap);               // [4][lcap]
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
   u32 *s_mmp = (u32 *)(s_mmv + c.maxmm);                       // [maxmm]
   u8 *s_lc = (u8 *)(s_mmp + c.maxmm);                          // [4][lcap]
   u8 *fl_a = s_lc + 4 * (size_t)lcap, *fl_b = fl_a + fcap;     // [fcap] each
-  const int slot = blockIdx.x, tid = threadIdx.x;
+  const int NT = blockDim.x, tid = threadIdx.x;
   PairMeta &pm = S.pmeta[slot];
   if (pm.status != ST_OK) return;
   ReadMeta *rm = S.rmeta + 2 * slot;
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
       const u64 *gp = CP(q >> 1, 0, q & 1);
       const u8 *gc = CC(q >> 1, 0, q & 1);
       if (nq[q] <= lcap) {
-        for (int i = tid; i < nq[q]; i += CTA_NT) { s_lp[q * lcap + i] = gp[i]; s_lc[q * lcap + i] = gc[i]; }
+        for (int i = tid; i < nq[q]; i += NT) { s_lp[q * lcap + i] = gp[i]; s_lc[q * lcap + i] = gc[i]; }
         lp[q] = s_lp + q * lcap; lc[q] = s_lc + q * lcap;
       } else { lp[q] = gp; lc[q] = gc; }
     }
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
     int hit = 0;
 #pragma unroll
     for (int s = 0; s < 2; ++s)
-      for (int i = tid; i < nq[mate * 2 + s]; i += CTA_NT) hit |= lc[mate * 2 + s][i] >= half;
+      for (int i = tid; i < nq[mate * 2 + s]; i += NT) hit |= lc[mate * 2 + s][i] >= half;
     need[mate] = !__syncthreads_or(hit);
   }
   const u32 range = 2u * (u32)P.max_insert;
@@ -385,7 +396,11 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
     ReadMeta &me = rm[mate];
     const int n_mm = n_mm2[mate];
     const size_t sr = 2 * slot + mate;
-    for (int i = tid; i < n_mm; i += CTA_NT) { s_mmv[i] = S.mm_val[sr * c.maxmm + i]; s_mmp[i] = S.mm_pos[sr * c.maxmm + i]; }
+    {
+      const size_t mb0 = mm_base(S, slot, mate);
+      const int ms = mm_stride(S);
+      for (int i = tid; i < n_mm; i += NT) { s_mmv[i] = S.mm_val[mb0 + (size_t)i * ms]; s_mmp[i] = S.mm_pos[mb0 + (size_t)i * ms]; }
+    }
     __syncthreads();
     u64 *hp = S.hits + (sr * 2 + 0) * c.hc, *hn = S.hits + (sr * 2 + 1) * c.hc;
     int pr = 0, nr = 0;
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
       if (nq[q] > lcap) {
         u64 *dst = CP(q >> 1, 1, q & 1);
         u8 *dstc = CC(q >> 1, 1, q & 1);
-        for (int i = tid; i < nq[q]; i += CTA_NT) { dst[i] = lp[q][i]; dstc[i] = lc[q][i]; }
+        for (int i = tid; i < nq[q]; i += NT) { dst[i] = lp[q][i]; dstc[i] = lc[q][i]; }
         lp[q] = dst; lc[q] = dstc;
       }
     __syncthreads();
@@ -459,4 +474,16 @@ __global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P
   pm.sup = ret;
   if (!(nc1 > 0 && nc2 > 0)) { pm.status = ST_DROP; return; }
   atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
+}
+
+__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap, int lcap, int fcap,
+                                                                     const int *list, const int *list_count) {
+  extern __shared__ u64 sm[];
+  __shared__ RescueShared RS;
+  if (!list) { pair_candidates_cta_pair(P, ix, S, ctr, sm_cap, lcap, fcap, (int)blockIdx.x, sm, RS); return; }
+  const int n = *list_count;  // persistent: the grid strides over the listed pairs
+  for (int b = blockIdx.x; b < n; b += gridDim.x) {
+    pair_candidates_cta_pair(P, ix, S, ctr, sm_cap, lcap, fcap, list[b], sm, RS);
+    __syncthreads();
+  }
 }

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
           const u32 rid = (u32)(cpos >> 32);
           const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
           const u8 *win = R.seq + R.off[rid] + pos - e;
+          prefetch_span(win, L + 2 * e);
           const u8 *txt = s == 0 ? s_fwd : s_neg;
           err = banded_align(e, L, [&](int q) { return base_code(__ldg(win + q)); }, [&](int q) { return (u32)txt[q]; }, &endp);
           ++n_ver;

@@ -133,6 +133,13 @@ __device__ __forceinline__ int index_lookup(const DevIndex &ix, u64 mm_hash, u64
   }
 }
 
+// Bring the cache lines of [p, p + bytes) towards the SM ahead of a loop that reads them one byte at a time (the banded
+// aligners consume one reference base per column: without this every column waits for its own L2 round trip).
+__device__ __forceinline__ void prefetch_span(const void *p, int bytes) {
+  const char *a = (const char *)((unsigned long long)p & ~127ull), *z = (const char *)p + bytes;
+  for (; a < z; a += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+}
+
 // index.cc:491-505 (u32 wrap kept)
 __device__ __forceinline__ u64 hit_to_candidate(int k, u64 ref_hit, u32 read_pos, u32 read_strand, bool *same) {
   const u32 rp = (u32)(ref_hit >> 1);

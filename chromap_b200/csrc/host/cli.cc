@@ -13,11 +13,14 @@
 #include <vector>
 
 #include "../../../include/chromap_b200.h"
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "seqio.h"
 
 using cmxhost::IndexFile;
+using cmxhost::IndexMap;
 using cmxhost::Reference;
 using cmxhost::SeqReader;
 
@@ -40,30 +43,69 @@ struct Batch {
   void Clear() { dev = false; s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); names1.clear(); names2.clear(); q1.clear(); q2.clear(); bc.clear(); bq.clear(); n = 0; }
 };
 
-// Raw text of one read file for the device-side FASTQ parser: gzread() (plain or gzip) into a growing buffer; whole
-// 4-line records are cut off its front with cmx_fastq_cut, the rest stays for the next batch.
+// Raw text of one read file for the device-side FASTQ parser.  Plain files are read with read(2) straight into a page-locked
+// buffer (no zlib copy, H2D at PCIe speed); gzip files go through gzread.  Whole 4-line records are cut off the front of the
+// buffer (same rule as cmx_fastq_cut, but the scan remembers where it stopped instead of starting over after every refill),
+// the rest stays for the next batch.
 struct RawFile {
   gzFile f = nullptr;
+  int fd = -1;
   std::vector<char> buf;
   size_t have = 0;
-  bool eof = false;
-  bool Open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); have = 0; eof = false; return f != nullptr; }
-  void Close() { if (f) gzclose(f); f = nullptr; }
+  bool eof = false, pinned = false;
+  size_t scan = 0, end_of_last = 0;  // scan state: bytes examined, end of the last whole record among them
+  uint32_t lines = 0, recs = 0;      // newlines of the record under way, whole records found
+  bool Open(const std::string &path) {
+    Close();
+    have = 0; eof = false; scan = end_of_last = 0; lines = recs = 0;
+    unsigned char magic[2] = {0, 0};
+    FILE *t = fopen(path.c_str(), "rb");
+    if (!t) return false;
+    const size_t got = fread(magic, 1, 2, t);
+    fclose(t);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
+    fd = open(path.c_str(), O_RDONLY);
+    if (fd >= 0) posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    return fd >= 0;
+  }
+  void Close() {
+    if (f) gzclose(f);
+    if (fd >= 0) close(fd);
+    f = nullptr; fd = -1;
+    if (pinned) { cmx_host_unregister(buf.data()); pinned = false; }
+  }
+  void Reserve(size_t bytes) {  // grow (rarely): the buffer is pinned once it has its working size
+    if (buf.size() >= bytes) return;
+    if (pinned) { cmx_host_unregister(buf.data()); pinned = false; }
+    buf.resize(bytes + bytes / 4);
+    pinned = cmx_host_register(buf.data(), buf.size()) == 0;
+  }
   // bytes of up to max_records whole records now in the buffer (reading more as needed); *n = their number
   uint64_t Fill(uint32_t max_records, uint32_t *n) {
     for (;;) {
-      const uint64_t cut = cmx_fastq_cut(buf.data(), have, max_records, n);
-      if (*n == max_records || eof) return cut;
-      const size_t want = 64u << 20;
-      if (buf.size() < have + want + 1) buf.resize(have + want + 1);
-      const int got = gzread(f, buf.data() + have, (unsigned)want);
+      while (recs < max_records && scan < have) {
+        const void *q = memchr(buf.data() + scan, '\n', have - scan);
+        if (!q) { scan = have; break; }
+        scan = (size_t)((const char *)q - buf.data()) + 1;
+        if (++lines == 4) { lines = 0; ++recs; end_of_last = scan; }
+      }
+      if (recs == max_records || eof) { *n = recs; return end_of_last; }
+      const size_t want = 32u << 20;
+      Reserve(have + want + 1);
+      long got;
+      if (f) got = gzread(f, buf.data() + have, (unsigned)want);
+      else got = (long)read(fd, buf.data() + have, want);
       if (got <= 0) {
         eof = true;
         if (have > 0 && buf[have - 1] != '\n') buf[have++] = '\n';  // a last line without its newline
       } else have += (size_t)got;
     }
   }
-  void Consume(uint64_t bytes) { memmove(buf.data(), buf.data() + bytes, have - bytes); have -= bytes; }
+  void Consume(uint64_t bytes) {
+    memmove(buf.data(), buf.data() + bytes, have - bytes);
+    have -= bytes;
+    scan = 0; end_of_last = 0; lines = 0; recs = 0;  // the remainder (part of one batch at most) is scanned again: it is short
+  }
 };
 
 // One batch through the device-side parser.  Returns false if a file is not plain 4-line FASTQ (the caller then uses the
@@ -256,18 +298,30 @@ int main(int argc, char **argv) {
   if (!bc_path.empty() && p.remove_pcr_duplicates && p.low_memory_mode && !cell_level_dedup)  // mapping_writer.h:254-262: only the low-memory merge has the bulk-level variant
     Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");
+  // start-up, three things at once (the reference does them one after the other, chromap.h:684-730): the reference sequences
+  // are parsed by one thread, the index file is mapped and read ahead by the kernel, the CUDA context comes up on this thread
   Reference ref;
-  if (!ref.Load(ref_path)) Die("Cannot find sequence file " + ref_path);
-  fprintf(stderr, "Loaded all sequences successfully, number of sequences: %zu, number of bases: %zu.\n", ref.names.size(), ref.concat.size());
-  IndexFile ix;
-  if (!ix.Load(index_path)) Die("Cannot load index file " + index_path);
-  fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %zu.\n", ix.k, ix.w, ix.size, ix.occ.size());
+  bool ref_ok = false;
+  std::thread ref_loader([&]() { ref_ok = ref.Load(ref_path); });
+  IndexMap ix;
+  const bool ix_ok = ix.Open(index_path);
   p.single_end = se ? 1 : 0;
   int rc = cmx_create(&ctx, 0, &p);
+  ref_loader.join();
+  if (!ref_ok) Die("Cannot find sequence file " + ref_path);
+  fprintf(stderr, "Loaded all sequences successfully, number of sequences: %zu, number of bases: %zu.\n", ref.names.size(), ref.concat.size());
+  if (!ix_ok) Die("Cannot load index file " + index_path);
+  fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %u.\n", ix.k, ix.w, ix.size, ix.n_occ);
   if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: unsupported parameter combination");
-  if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
-  if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags.data(), ix.keys.data(), ix.vals.data(), ix.occ.data(), (uint32_t)ix.occ.size())) Die(cmx_last_error(ctx));
-  { IndexFile().flags.swap(ix.flags); std::vector<uint64_t>().swap(ix.keys); std::vector<uint64_t>().swap(ix.vals); std::vector<uint64_t>().swap(ix.occ); }
+  {
+    int rc_ref = 0;
+    std::thread up_ref([&]() { rc_ref = cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data()); });
+    up_ref.join();  // (the two uploads share the context's error string: one after the other)
+    if (rc_ref) Die(cmx_last_error(ctx));
+    if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags, ix.keys, ix.vals, ix.occ, ix.n_occ)) Die(cmx_last_error(ctx));
+    ix.Close();
+  }
+  fprintf(stderr, "Reference and index resident on the device after %.2fs.\n", Now() - t_start);
   // scATAC pre-pass (chromap.h:755-761): barcode length from the first record, whitelist, abundance over the first >= 20 M
   // whitelisted barcodes (chromap.cc:364-386, 388-548)
   const bool sc = !bc_path.empty();
@@ -330,14 +384,17 @@ int main(int argc, char **argv) {
     }
   };
   int parity = 0;
+  // one call carries four reference batches (chromap.h:182: 500 000 pairs each) when the reads are parsed on the device: the
+  // library runs them as overlapping lanes; batch boundaries — which the multi-mapper sampling depends on — stay where they are
+  const uint32_t call_pairs = (uint32_t)p.batch_size * 4u;
   auto load = [&](Batch *b, int par) {
     if (gpu_reader) {
-      if (!LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, par, (uint32_t)p.batch_size, b, pairs, bc_len))
+      if (!LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, par, call_pairs, b, pairs, bc_len))
         Die(std::string("chromap-b200: the read files are not plain 4-line FASTQ (") + cmx_last_error(ctx) + "); rerun with --host-reader");
     } else LoadBatch(r1, r2, (uint32_t)p.batch_size, b, pairs || sam || paf, sc ? &rb : nullptr, bc_len, se, sam || paf);
   };
   open_all(gpu_reader);
-  if (gpu_reader && !LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, parity, (uint32_t)p.batch_size, &cur, pairs, bc_len)) {
+  if (gpu_reader && !LoadBatchGpu(ctx, &g1, se ? nullptr : &g2, sc ? &gb : nullptr, parity, call_pairs, &cur, pairs, bc_len)) {
     fprintf(stderr, "Read files are not plain 4-line FASTQ (%s): using the host reader.\n", cmx_last_error(ctx));
     g1.Close(); g2.Close(); gb.Close();
     gpu_reader = false;

@@ -1,5 +1,11 @@
 #include "seqio.h"
 
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstring>
 
 #include <cctype>
@@ -117,6 +123,41 @@ bool IndexFile::Load(const std::string &path) {
   if (ok && n_occ) { occ.resize(n_occ); ok = fread(occ.data(), 8, n_occ, f) == n_occ; }
   fclose(f);
   return ok;
+}
+
+bool IndexMap::Open(const std::string &path) {
+  Close();
+  const int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) return false;
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 32) { close(fd); return false; }
+  bytes_ = (size_t)st.st_size;
+  base_ = mmap(nullptr, bytes_, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (base_ == MAP_FAILED) { base_ = nullptr; return false; }
+  madvise(base_, bytes_, MADV_SEQUENTIAL);
+  madvise(base_, bytes_, MADV_WILLNEED);
+  const unsigned char *p = (const unsigned char *)base_;
+  uint32_t h[7];
+  memcpy(h, p, 28);
+  k = (int)h[0]; w = (int)h[1]; n_buckets = h[3]; size = h[4];
+  const size_t nf = n_buckets < 16 ? 1 : n_buckets >> 4;
+  size_t off = 28;
+  const size_t need = off + (n_buckets ? nf * 4 + (size_t)n_buckets * 16 : 0) + 4;
+  if (need > bytes_) { Close(); return false; }
+  if (n_buckets) {
+    flags = (const uint32_t *)(p + off); off += nf * 4;
+    keys = (const uint64_t *)(p + off); off += (size_t)n_buckets * 8;
+    vals = (const uint64_t *)(p + off); off += (size_t)n_buckets * 8;
+  }
+  memcpy(&n_occ, p + off, 4); off += 4;
+  if (off + (size_t)n_occ * 8 > bytes_) { Close(); return false; }
+  occ = (const uint64_t *)(p + off);
+  return true;
+}
+void IndexMap::Close() {
+  if (base_) munmap(base_, bytes_);
+  base_ = nullptr; bytes_ = 0; flags = nullptr; keys = vals = occ = nullptr;
 }
 
 bool IndexFile::Save(const std::string &path) const {

@@ -46,4 +46,21 @@ struct IndexFile {
   bool Save(const std::string &path) const;
 };
 
+// The same file mapped read-only instead of copied: the arrays are handed to cmx_upload_index where they lie in the page
+// cache (a 3 Gbp index is 17 GB of hash-table arrays; reading them into vectors first doubles the memory traffic of start-up).
+struct IndexMap {
+  int k = 0, w = 0;
+  uint32_t n_buckets = 0, size = 0;
+  const uint32_t *flags = nullptr;
+  const uint64_t *keys = nullptr, *vals = nullptr, *occ = nullptr;  // 4-byte aligned only: to be copied, not dereferenced
+  uint32_t n_occ = 0;
+  bool Open(const std::string &path);
+  void Close();
+  ~IndexMap() { Close(); }
+
+ private:
+  void *base_ = nullptr;
+  size_t bytes_ = 0;
+};
+
 }  // namespace cmxhost

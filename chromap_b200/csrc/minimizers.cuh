@@ -117,10 +117,98 @@ __device__ __forceinline__ void minimizer_scan(SeqF SEQ, int len, int k_rt, int 
   }
   if (best_h != ~0ull) EMIT(best_h, best_p);
 }
+// The same algorithm for odd k <= 21 and a compile-time w, built for a warp whose 32 lanes scan 32 different reads: the
+// lanes take the reference's branches at different positions, so every branch body costs the whole warp.  Restated with
+// no state but the window itself:
+//   * an entry is ONE 64-bit key = hash << 20 | (0xFFFFF - (pos << 1 | strand)); empty = ~0.  Smaller key = smaller hash,
+//     and among equal hashes the LATER position — exactly the entry the reference's scans settle on (`<=` on insertion,
+//     `>=` in the rescan, minimizer_generator.cc:95-127);
+//   * therefore the reference's running minimum is, after every position, simply the minimum key of the window (w - 1
+//     64-bit minima, branch-free), and its three events read off the old minimum `best`, the new key `cur` and the key `old`
+//     that `cur` overwrites:   cur <= best  -> the minimum is replaced;   old == best -> it leaves the window;
+//   * identical hashes inside one window (low-complexity sequence) are what the tie loops are for; a 32-bit prefix test
+//     keeps them out of the common path.
+// Emission order and content are those of minimizer_scan (checked against it and against the oracle in the stage tests).
+// RingT: the window's storage, ring[q] for q in [0, W) — a register array (`u64[W]`) or a strided view of shared memory
+// (the fused front-end kernel keeps it there: the scan then needs no more registers than the hashes do).
+template <int K, int W, typename SeqF, typename EmitF, typename RingT>
+__device__ __forceinline__ void minimizer_scan_packed(SeqF SEQ, int len, EmitF EMIT, RingT ring) {
+  static_assert((K & 1) && K >= 17 && K <= 21 && W >= 2, "minimizer_scan_packed: odd k, 2k + 20 <= 62");
+  constexpr u64 mask = (((u64)1) << (2 * K)) - 1;
+  constexpr int shift = 2 * (K - 1);
+  constexpr u64 NONE = ~0ull;
+  constexpr u32 PM = 0xFFFFFu;
+  u64 fwd = 0, rev = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) ring[i] = NONE;
+  u64 best = NONE;
+  int run = 0, slot = 0;  // slot = pos mod W: the entry `cur` replaces is the oldest one
+  auto emit_key = [&](u64 key) { EMIT(key >> 20, PM - ((u32)key & PM)); };
+#pragma unroll 1
+  for (int pos = 0; pos < len; ++pos) {
+    const u32 b = base_code(SEQ(pos));
+    u64 cur = NONE;
+    if (b < 4) {
+      fwd = ((fwd << 2) | b) & mask;
+      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
+      ++run;
+      if (run >= K) {
+        const u64 hf = mix64_k<K>(fwd), hr = mix64_k<K>(rev);
+        const u32 strand = hf < hr ? 0u : 1u;
+        cur = (mix64_k<K>(strand ? hr : hf) << 20) | (u64)(PM - (((u32)pos << 1) | strand));
+      }
+    } else {
+      run = 0;
+    }
+    // first full window: entries equal to the minimum, behind the current one, oldest first (minimizer_generator.cc:86-93)
+    if (run == W + K - 1 && best != NONE && (best >> 20) < (cur >> 20)) {
+      for (int j = 1; j < W; ++j) {
+        int q = slot + j; if (q >= W) q -= W;
+        const u64 x = ring[q];
+        if ((x >> 20) == (best >> 20) && x != best) emit_key(x);
+      }
+    }
+    const u64 old = ring[slot];
+    ring[slot] = cur;
+    u64 m = cur;
+#pragma unroll
+    for (int q = 0; q < W; ++q) m = min(m, (u64)ring[q]);
+    u64 out = NONE;  // the minimizer this position retires, if any
+    bool left = false;
+    if (cur <= best) {  // :95-100
+      if (run >= W + K && best != NONE) out = best;
+    } else if (old == best) {  // the minimum leaves the window (:101-127); best != NONE here
+      if (run >= W + K - 1) { out = best; left = m != NONE; }
+    }
+    if (out != NONE) emit_key(out);
+    int same_hi = 0;  // entries sharing the 32 high bits of the new minimum's key: more than one only in low-complexity sequence
+    if (left) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) same_hi += (u32)((u64)ring[q] >> 32) == (u32)(m >> 32);
+    }
+    if (same_hi > 1) {  // entries sharing the new minimum's hash, oldest first
+      for (int j = 1; j <= W; ++j) {
+        int q = slot + j; if (q >= W) q -= W;
+        const u64 x = ring[q];
+        if ((x >> 20) == (m >> 20) && x != m) emit_key(x);
+      }
+    }
+    best = m;
+    if (++slot == W) slot = 0;
+  }
+  if (best != NONE) emit_key(best);
+}
+// the same with the window in registers
+template <int K, int W, typename SeqF, typename EmitF>
+__device__ __forceinline__ void minimizer_scan_packed(SeqF SEQ, int len, EmitF EMIT) {
+  u64 ring[W];
+  minimizer_scan_packed<K, W>(SEQ, len, EMIT, ring);
+}
+
 // dispatch on the (k, w) pairs the presets use; anything else takes the run-time body
 template <typename SeqF, typename EmitF>
 __device__ __forceinline__ void minimizer_scan_any(SeqF SEQ, int len, int k, int w, EmitF EMIT) {
-  if (k == 17 && w == 7) minimizer_scan<17, 7>(SEQ, len, k, w, EMIT);  // default, every preset
+  if (k == 17 && w == 7 && len < (1 << 18)) minimizer_scan_packed<17, 7>(SEQ, len, EMIT);  // default, every preset
   else minimizer_scan<0, 0>(SEQ, len, k, w, EMIT);
 }
 

@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevInd
     const u32 kind = mmp[(size_t)i * ms] >> 30;
     if (kind == 1) { ++cnt1; ++cnt2; }
     else if (kind == 2) {
-      const u32 n = (u32)mmv[(size_t)i * ms];
+      const u64 v_ = mmv[(size_t)i * ms];
+      const u32 n = (u32)v_;
+      if (n < (u32)P.f1) prefetch_span(&ix.occ[(u32)(v_ >> 32)], (int)min(n, 64u) * 8);  // the expansion below reads them: request them now
       if (n < (u32)P.f0) cnt1 += n;
       if (n < (u32)P.f1) cnt2 += n;
       if (n >= (u32)P.f0) rep_update(P.k, P.w, (mmp[(size_t)i * ms] & 0x3FFFFFFFu) >> 1, st);
@@ -348,11 +350,11 @@ __device__ inline void pe_filter_dir(u32 dist, const u64 *p1, const u8 *c1, int 
 
 // K2: per pair — SupplementCandidates (candidate_processor.cc:75-231), MoveCandidiatesToBuffer +
 // ReduceCandidatesForPairedEndRead (chromap.h:1036-1052, candidate_processor.cc:233-263).
-// Two launches: mode 0 handles every pair that needs no mate-guided rescue (the common case: a few loads
-// and two short sweeps) and appends the others to `list`; mode 1 runs the rescue pairs densely packed, so a
-// warp is no longer held up by its one rescuing pair.
+// Two launches: mode 0 handles every pair that needs no mate-guided lookup (the common case: a few loads and two short
+// sweeps) and appends the others to `list`; mode 1 runs those densely packed, one thread per pair — thousands of pairs in
+// flight per SM hide the dependent occurrence-list reads (a warp per pair was measured 9x slower: 32 pairs per SM in flight).
 #define PC_SMALL 8          // lists of at most this many candidates take the local-memory path
-#define PC_RESCUE_HEAVY 48  // more (minimizer, window) searches than this: rescue in the CTA tier
+#define PC_RESCUE_HEAVY 48  // more (minimizer, window) searches than this: the lookup runs in the CTA tier
 __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int mode, int *list, int *list_count) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int slot = tid;
@@ -366,7 +368,6 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   ReadMeta *rm = S.rmeta + 2 * slot;
   auto CP = [&](int mate, int set, int strand) { return S.cand_pos + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
   auto CC = [&](int mate, int set, int strand) { return S.cand_cnt + ((((size_t)(2 * slot + mate)) * 3 + set) * 2 + strand) * c.cc; };
-  bool aug[2];
   if (P.se) {  // single-end (chromap.h:449-453): a read goes on iff it has minimizers and candidates
     if (mode != 0) return;
     const int a1 = rm[0].n_cand[0] + rm[0].n_cand[1];
@@ -399,6 +400,7 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       }
     }
     bool need = false;
+    bool aug[2];
     for (int mate = 0; mate < 2; ++mate) {
       const u32 n_mm = rm[mate].n_mm;
       bool a = true;
@@ -411,8 +413,8 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       if (a && nq[(1 - mate) * 2] + nq[(1 - mate) * 2 + 1] > 0) need = true;
     }
     if (need) {
-      // one thread walks every (multi-occurrence minimizer, mate window) binary search of the rescue; when that
-      // product is large the pair goes to the CTA tier, which runs the searches in parallel (same results)
+      // one thread walks every (multi-occurrence minimizer, mate window) binary search of the lookup; when that product is
+      // large the pair goes to the CTA tier, where a warp takes each minimizer and a lane each window (same results)
       u32 searches = 0;
       for (int mate = 0; mate < 2; ++mate) {
         if (!aug[mate]) continue;
@@ -544,9 +546,14 @@ __device__ __forceinline__ int banded_align(int e, int L, PatF PAT, TxtF TXT, in
   const u32 hi = 1u << (2 * e), band = (hi << 1) - 1u;
   u32 VP = 0, VN = 0;
   int err = 0;
+  // software pipelined: the bases of column i + 1 are requested before column i is worked on, so a column never waits for
+  // its own load (one reference byte and one read byte per column)
+  u32 pat_n = L > 0 ? PAT(2 * e) : 0u, txt_n = L > 0 ? TXT(0) : 0u;
   for (int i = 0; i < L; ++i) {
-    planes_or(W, PAT(i + 2 * e), hi);
-    u32 X = VN | planes_match(W, TXT(i), band);
+    const u32 pat = pat_n, txt = txt_n;
+    if (i + 1 < L) { pat_n = PAT(i + 1 + 2 * e); txt_n = TXT(i + 1); }
+    planes_or(W, pat, hi);
+    u32 X = VN | planes_match(W, txt, band);
     const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
     const u32 HN = VP & D0;
     const u32 HP = VN | ~(VP | D0);
@@ -634,6 +641,7 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
         const u32 rid = (u32)(cpos >> 32);
         const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
         const u8 *win = R.seq + R.off[rid] + pos - e;
+        prefetch_span(win, L + 2 * e);
         int endp = 0, err;
         if (s == 0) err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return base_code(read[i]); }, &endp);
         else err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp);
@@ -910,12 +918,9 @@ __global__ void __launch_bounds__(128) select_kernel(DevParams P, int n_chunks, 
 // ------------------------------------------------------------------------------------------------
 // alignment.cc:656-718 — start coordinate.  PATC(i)/TXTC(i): raw chars (the Hamming shortcut compares raw
 // chars, case-sensitively, :665-669); codes via base_code().
+// the bit-vector part (alignment.cc:671-717), for the mappings whose mismatch count differs from their edit distance
 template <typename PatC, typename TxtC>
-__device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC PATC, TxtC TXTC) {
-  if (min_err == 0) return e;
-  int ham = 0;
-  for (int i = 0; i < L; ++i) if (PATC(i + e) != TXTC(i)) ++ham;
-  if (ham == min_err) return e;
+__device__ __forceinline__ int banded_traceback_dp(int e, int min_err, int L, PatC PATC, TxtC TXTC) {
   PatPlanes W = {0u, 0u, 0u};
   for (int i = 0; i < 2 * e; ++i) planes_or(W, base_code(PATC(L - 1 + 2 * e - i)), 1u << i);
   const u32 hi = 1u << (2 * e), band = (hi << 1) - 1u;
@@ -940,6 +945,14 @@ __device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC 
     if (err == min_err) { start = 2 * e - (1 + i); if (i + 1 == e) return start; }
   }
   return start;
+}
+template <typename PatC, typename TxtC>
+__device__ __forceinline__ int banded_traceback(int e, int min_err, int L, PatC PATC, TxtC TXTC) {
+  if (min_err == 0) return e;
+  int ham = 0;
+  for (int i = 0; i < L; ++i) if (PATC(i + e) != TXTC(i)) ++ham;
+  if (ham == min_err) return e;
+  return banded_traceback_dp(e, min_err, L, PATC, TXTC);
 }
 
 // IEEE double ops without FMA contraction: the reference is x86-64 SSE2 scalar code (no FMA).
@@ -1065,44 +1078,144 @@ __device__ __forceinline__ OutRecord pe_record(const DevParams &P, const DevRef 
 
 // K6: per pair — ProcessBestMappingsForPairedEndReadOnOneDirection (mapping_generator.h:486-654):
 // the selected best pair(s), start coordinates (mapping_generator.h:657-917 BED branch), MAPQ, record.
-// Two phases, so that the threads of a warp run the expensive part together: first every thread walks its sweep to the
-// selected best pair(s) and only notes which mappings they are, then all threads compute their records (tracebacks,
-// MAPQ) side by side.  (With the record computed inside the sweep, each thread reached it at a different iteration and
-// the warp ran 32 tracebacks one after the other: 3.5 active lanes per instruction.)
+// One thread per pair, but the warp works through the expensive parts together, in phases:
+//   A  every thread walks its sweep to the selected best pair(s) and notes which mappings they are;
+//   B  the Hamming shortcut of BandedTraceback (alignment.cc:665-669) for every (pair, mate) whose mapping has errors: the
+//      warp takes these one at a time, 32 positions per step, window and read bytes coalesced;
+//   C  the threads whose mismatch count differs from the edit distance (indels) run the bit-vector traceback side by side;
+//   D  MAPQ and the record.
+// (Computed inside the sweep, each thread reached its traceback at a different iteration and the warp ran them one after
+// the other: 3.5 active lanes per instruction, 2 ms for 2 M pairs.)
 __global__ void emit_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, const int *pair_sel, OutRecord *out,
-                            int *out_n, Counters *ctr) {
+                            int *out_n, Counters *ctr, int4 *dp_list, int *dp_count) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= S.n_slots) return;
-  PairMeta &pm = S.pmeta[slot];
-  const int pair = slot_pair(S, slot);
-  if (pm.status == ST_OVERFLOW) return;  // re-done in the large tier (or reported)
-  if (pm.status != ST_OK || pm.n_best > P.drop_rep || pm.n_best == 0) { out_n[pair] = 0; return; }
+  const int lane = threadIdx.x & 31;
+  const bool in_range = slot < S.n_slots;
+  const int sl = in_range ? slot : 0;
+  PairMeta &pm = S.pmeta[sl];
+  const int pair = slot_pair(S, sl);
   const Caps c = S.caps;
-  const ReadMeta *rm = S.rmeta + 2 * slot;
-  const int mb = P.max_best;
-  const int to_report = mb < pm.n_best ? mb : pm.n_best;
-  const int *sel = pair_sel + (size_t)pair * mb;
-  int idx = 0, reported = 0;
+  const ReadMeta *rm = S.rmeta + 2 * sl;
+  const int mb = P.max_best, e = P.e;
+  int reported = 0;
   int ch_i1[CMX_MAX_BEST], ch_j[CMX_MAX_BEST];  // chosen mappings; bit 30 of ch_i1 = direction
-  for (int dir = 0; dir < 2 && reported != to_report; ++dir) {
-    const int s1 = dir, s2 = 1 - dir;
-    const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    pair_sweep_until(P, s1, (u32)rm[0].len, (u32)rm[1].len, p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) -> bool {
-      if (sum != pm.min_sum) return false;
-      if (idx == sel[reported]) { ch_i1[reported] = i1 | (dir << 30); ch_j[reported] = j; ++reported; }
-      ++idx;
-      return reported == to_report;
-    });
+  bool live = in_range && pm.status != ST_OVERFLOW;  // overflow: re-done in the large tier (or reported)
+  if (live && (pm.status != ST_OK || pm.n_best > P.drop_rep || pm.n_best == 0)) { out_n[pair] = 0; live = false; }
+  if (live) {  // phase A
+    const int to_report = mb < pm.n_best ? mb : pm.n_best;
+    const int *sel = pair_sel + (size_t)pair * mb;
+    int idx = 0;
+    for (int dir = 0; dir < 2 && reported != to_report; ++dir) {
+      const int s1 = dir, s2 = 1 - dir;
+      const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+      const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+      pair_sweep_until(P, s1, (u32)rm[0].len, (u32)rm[1].len, p1, e1, rm[0].n_map[s1], p2, e2, rm[1].n_map[s2], [&](int i1, int j, int sum) -> bool {
+        if (sum != pm.min_sum) return false;
+        if (idx == sel[reported]) { ch_i1[reported] = i1 | (dir << 30); ch_j[reported] = j; ++reported; }
+        ++idx;
+        return reported == to_report;
+      });
+    }
   }
-  for (int r = 0; r < reported; ++r) {
-    const int s1 = ch_i1[r] >> 30, i1 = ch_i1[r] & 0x3FFFFFFF, j = ch_j[r];
-    const size_t b1 = ((size_t)(2 * slot + 0) * 2 + s1) * c.mc + i1, b2 = ((size_t)(2 * slot + 1) * 2 + (1 - s1)) * c.mc + j;
-    out[(size_t)pair * mb + r] = pe_record(P, R, B, T, pm, rm, pair, s1, S.map_pos[b1], S.map_err[b1], S.map_pos[b2], S.map_err[b2]);
+  const int L[2] = {live ? rm[0].len : 0, live ? rm[1].len : 0};
+  const int max_rep = __reduce_max_sync(0xffffffffu, reported);
+  for (int r = 0; r < max_rep; ++r) {
+    const bool have = r < reported;
+    int s1 = 0;
+    u64 dpos[2] = {0, 0};
+    int derr[2] = {0, 0};
+    u32 vws[2] = {0, 0};
+    const u8 *win[2] = {R.seq, R.seq};
+    const u8 *rd[2] = {R.seq, R.seq};
+    int s0[2] = {e, e};
+    if (have) {
+      s1 = ch_i1[r] >> 30;
+      const size_t b1 = ((size_t)(2 * slot + 0) * 2 + s1) * c.mc + (ch_i1[r] & 0x3FFFFFFF), b2 = ((size_t)(2 * slot + 1) * 2 + (1 - s1)) * c.mc + ch_j[r];
+      dpos[0] = S.map_pos[b1]; derr[0] = S.map_err[b1]; dpos[1] = S.map_pos[b2]; derr[1] = S.map_err[b2];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {  // verification window (mapping_generator.h:696-711)
+        const u32 rid = (u32)(dpos[m] >> 32), rp = (u32)dpos[m];
+        u32 v = rp + 1u > (u32)(L[m] + e) ? rp + 1u - (u32)L[m] - (u32)e : 0u;
+        if (rp + (u32)e >= R.len[rid]) v = R.len[rid] - (u32)e - (u32)L[m];
+        vws[m] = v;
+        win[m] = R.seq + R.off[rid] + v;
+        rd[m] = read_ptr(B, pair, m);
+      }
+    }
+    // phase B: mismatch counts by the whole warp, four (pair, mate) tasks per round so that their loads are in flight together
+    int ham[2] = {0, 0};
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      unsigned todo = __ballot_sync(0xffffffffu, have && derr[m] > 0);
+      while (todo) {
+        int src[4], cnt[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          src[t] = todo ? __ffs(todo) - 1 : -1;
+          if (todo) todo &= todo - 1;
+          cnt[t] = 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (src[t] < 0) continue;  // warp-uniform
+          const u8 *w = (const u8 *)__shfl_sync(0xffffffffu, (unsigned long long)win[m], src[t]);
+          const u8 *q = (const u8 *)__shfl_sync(0xffffffffu, (unsigned long long)rd[m], src[t]);
+          const int Lm = __shfl_sync(0xffffffffu, L[m], src[t]);
+          const int neg = __shfl_sync(0xffffffffu, m == 0 ? s1 : 1 - s1, src[t]);
+          for (int i = lane; i < Lm; i += 32) {
+            const u8 a = __ldg(w + i + e);
+            const u8 c0 = neg ? q[Lm - 1 - i] : q[i];
+            const u32 bc = base_code(c0);
+            const u8 tch = neg ? code_char(bc < 4 ? 3u ^ bc : 4u) : c0;  // the reverse strand string holds A C G T N only (sequence_batch.h:123-134)
+            cnt[t] += a != tch;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (src[t] < 0) continue;
+          const int c_ = __reduce_add_sync(0xffffffffu, cnt[t]);
+          if (lane == src[t]) ham[m] = c_;
+        }
+      }
+    }
+    // phase C: mappings whose mismatch count differs from their edit distance (indels, ~5 % of reads) need the bit-vector
+    // traceback: those pairs are put on a list and finished by emit_dp_kernel, one lane each, densely packed — inside this
+    // kernel a warp would run a 50-column traceback for its one or two such lanes at a time
+    const bool deferred = have && ((derr[0] > 0 && ham[0] != derr[0]) || (derr[1] > 0 && ham[1] != derr[1]));
+    if (deferred) dp_list[agg_append(dp_count)] = make_int4(slot, r, ch_i1[r], ch_j[r]);
+    if (have && !deferred) {  // phase D (mapping_generator.cc:110-143)
+      const u32 st1 = vws[0] + (u32)s0[0], en1 = (u32)dpos[0], st2 = vws[1] + (u32)s0[1], en2 = (u32)dpos[1];
+      const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
+      OutRecord o;
+      o.read_id = B.first_read_id + (u32)pair;
+      o.rid = (u32)(dpos[0] >> 32);
+      o.fragment_start = s1 == 0 ? st1 : st2;
+      o.fragment_length = (unsigned short)(s1 == 0 ? (int)(en2 - st1 + 1u) : (int)(en1 - st2 + 1u));
+      o.mapq = mapq_pe(T, derr[0], derr[1], al1, al2, L[0], L[1], pm.sup != 0 ? 0 : -1, pm, rm);
+      o.direction = s1 == 0 ? 1 : 0;
+      o.is_unique = (pm.n_best == 1 || rm[0].n_best == 1 || rm[1].n_best == 1) ? 1 : 0;
+      o.num_dups = 1;
+      o.positive_alignment_length = s1 == 0 ? al1 : al2;
+      o.negative_alignment_length = s1 == 1 ? al1 : al2;
+      out[(size_t)pair * mb + r] = o;
+    }
   }
+  if (!live) return;
   out_n[pair] = reported;
   pm.n_rec = reported;
   if (reported > 0) { agg_add(&ctr->n_mapped, 1ull); if (pm.n_best == 1) agg_add(&ctr->n_unique, 1ull); }
+}
+
+// the pairs emit_kernel left: one thread each, record computed with the full BandedTraceback
+__global__ void emit_dp_kernel(DevParams P, DevRef R, DevBatch B, MapqTables T, Scratch S, OutRecord *out, const int4 *dp_list, const int *dp_count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *dp_count) return;
+  const int4 q = dp_list[t];
+  const int slot = q.x, r = q.y, s1 = q.z >> 30, i1 = q.z & 0x3FFFFFFF, j = q.w;
+  const Caps c = S.caps;
+  const size_t b1 = ((size_t)(2 * slot + 0) * 2 + s1) * c.mc + i1, b2 = ((size_t)(2 * slot + 1) * 2 + (1 - s1)) * c.mc + j;
+  const int pair = slot_pair(S, slot);
+  out[(size_t)pair * P.max_best + r] = pe_record(P, R, B, T, S.pmeta[slot], S.rmeta + 2 * slot, pair, s1, S.map_pos[b1], S.map_err[b1], S.map_pos[b2], S.map_err[b2]);
 }
 
 // compaction of per-pair records into read order
@@ -1189,34 +1302,35 @@ __global__ void collect_overflow_kernel(Scratch S, int *list, int *count) {
 // sm_cap in global memory and finish every tile of sm_cap keys in shared memory (10 global passes instead of
 // 136 for 65536 keys).
 __device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm, int sm_cap) {
+  const int NT = blockDim.x;  // 32 .. CTA_NT threads
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
   if (np2 <= sm_cap) {
-    for (int i = tid; i < np2; i += CTA_NT) sm[i] = i < n ? a[i] : ~0ull;
+    for (int i = tid; i < np2; i += NT) sm[i] = i < n ? a[i] : ~0ull;
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
-          const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+        for (int p = tid; p < (np2 >> 1); p += NT) {
+          const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
           const u64 x = sm[i], y = sm[l];
           const bool up = (i & k) == 0;
           if ((x > y) == up) { sm[i] = y; sm[l] = x; }
         }
         __syncthreads();
       }
-    for (int i = tid; i < n; i += CTA_NT) a[i] = sm[i];
+    for (int i = tid; i < n; i += NT) a[i] = sm[i];
     __syncthreads();
     return;
   }
-  for (int i = n + tid; i < np2; i += CTA_NT) a[i] = ~0ull;
+  for (int i = n + tid; i < np2; i += NT) a[i] = ~0ull;
   __syncthreads();
   for (int k = 2; k <= np2; k <<= 1) {
     int j = k >> 1;
     for (; j >= sm_cap; j >>= 1) {  // wide strides: global memory
-      for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
-        const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+      for (int p = tid; p < (np2 >> 1); p += NT) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
         const u64 x = a[i], y = a[l];
         const bool up = (i & k) == 0;
         if ((x > y) == up) { a[i] = y; a[l] = x; }
@@ -1227,20 +1341,20 @@ __device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm, int sm_cap) {
     // (when k <= sm_cap this also covers the whole k-stage; consecutive small k stages are fused per tile)
     const bool fuse = k <= sm_cap;
     for (int base = 0; base < np2; base += sm_cap) {
-      for (int i = tid; i < sm_cap; i += CTA_NT) sm[i] = a[base + i];
+      for (int i = tid; i < sm_cap; i += NT) sm[i] = a[base + i];
       __syncthreads();
       const int k_lo = fuse ? 2 : k, k_hi = fuse ? sm_cap : k;
       for (int kk = k_lo; kk <= k_hi; kk <<= 1)
         for (int jj = fuse ? (kk >> 1) : j; jj > 0; jj >>= 1) {
-          for (int p = tid; p < (sm_cap >> 1); p += CTA_NT) {
-            const int i = ((p / jj) * (jj << 1)) + (p % jj), l = i + jj;
+          for (int p = tid; p < (sm_cap >> 1); p += NT) {
+            const int i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1)), l = i + jj;
             const u64 x = sm[i], y = sm[l];
             const bool up = ((base + i) & kk) == 0;
             if ((x > y) == up) { sm[i] = y; sm[l] = x; }
           }
           __syncthreads();
         }
-      for (int i = tid; i < sm_cap; i += CTA_NT) a[base + i] = sm[i];
+      for (int i = tid; i < sm_cap; i += NT) a[base + i] = sm[i];
       __syncthreads();
     }
     if (fuse) k = sm_cap;  // stages 2..sm_cap are done
@@ -1260,7 +1374,7 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
-          const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+          const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
           const u64 xk = smk[i], yk = smk[l];
           const T xt = smt[i], yt = smt[l];
           const bool up = (i & k) == 0;
@@ -1279,7 +1393,7 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
     int j = k >> 1;
     for (; j >= sm_cap; j >>= 1) {
       for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
-        const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
         const u64 xk = k_[i], yk = k_[l];
         const T xt = t_[i], yt = t_[l];
         const bool up = (i & k) == 0;
@@ -1296,7 +1410,7 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
       for (int kk = k_lo; kk <= k_hi; kk <<= 1)
         for (int jj = fuse ? (kk >> 1) : j; jj > 0; jj >>= 1) {
           for (int p = tid; p < (sm_cap >> 1); p += CTA_NT) {
-            const int i = ((p / jj) * (jj << 1)) + (p % jj), l = i + jj;
+            const int i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1)), l = i + jj;
             const u64 xk = smk[i], yk = smk[l];
             const T xt = smt[i], yt = smt[l];
             const bool up = ((base + i) & kk) == 0;
@@ -1315,13 +1429,14 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
 // candidate_processor.cc:283-342 with the sorted hits streamed through shared memory; thread 0 scans.
 // Returns the candidate count on every thread.
 __device__ inline int cta_cluster(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int sm_cap, int *s_ret) {
+  const int NT = blockDim.x;  // 32 .. CTA_NT threads
   const int tid = threadIdx.x;
   int n = 0, mcount = 1, eq = 1, best_eq = 1;
   u64 prev = 0, best = 0;
   u32 prev_rid = 0, prev_pos = 0;
   for (int base = 0; base < nh; base += sm_cap) {
     const int m = min(sm_cap, nh - base);
-    for (int i = tid; i < m; i += CTA_NT) sm[i] = hits[base + i];
+    for (int i = tid; i < m; i += NT) sm[i] = hits[base + i];
     __syncthreads();
     if (tid == 0) {
       int i0 = 0;
@@ -1437,6 +1552,7 @@ __device__ inline int cta_minimizers(const u8 *seq, int len, int k, int w, u64 *
 
 // exclusive scan of one int per thread over the CTA; *total gets the sum.
 __device__ inline int cta_excl_scan(int v, int *s_warp, int *total) {
+  const int NT = blockDim.x;  // 32 .. CTA_NT threads
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int x = v;
 #pragma unroll
@@ -1446,7 +1562,7 @@ __device__ inline int cta_excl_scan(int v, int *s_warp, int *total) {
   int base = 0;
   for (int i = 0; i < wid; ++i) base += s_warp[i];
   int tot = 0;
-  for (int i = 0; i < CTA_NT / 32; ++i) tot += s_warp[i];
+  for (int i = 0; i < (NT >> 5); ++i) tot += s_warp[i];
   __syncthreads();
   *total = tot;
   return base + x - v;
@@ -1460,12 +1576,13 @@ __device__ inline int cta_excl_scan(int v, int *s_warp, int *total) {
 // Lists longer than the shared-memory tile use the streaming version above.  `aux` = 3 * sm_cap bytes.
 __device__ inline int cta_cluster_par(int e, int need, u32 n_mm, const u64 *hits, int nh, u64 *cpos, u8 *ccnt, int cap, u64 *sm, int sm_cap,
                                       u8 *aux, int *s_ret) {
+  const int NT = blockDim.x;  // 32 .. CTA_NT threads
   if (nh > sm_cap) return cta_cluster(e, need, n_mm, hits, nh, cpos, ccnt, cap, sm, sm_cap, s_ret);
   const int tid = threadIdx.x;
   u8 *flag = aux, *vld = aux + sm_cap, *cnt = aux + 2 * sm_cap;
-  for (int i = tid; i < nh; i += CTA_NT) sm[i] = hits[i];
+  for (int i = tid; i < nh; i += NT) sm[i] = hits[i];
   __syncthreads();
-  for (int i = tid; i < nh; i += CTA_NT) {
+  for (int i = tid; i < nh; i += NT) {
     bool b = i == 0;
     if (!b) {
       const u64 h = sm[i], q = sm[i - 1];
@@ -1474,7 +1591,7 @@ __device__ inline int cta_cluster_par(int e, int need, u32 n_mm, const u64 *hits
     flag[i] = b; vld[i] = 0;
   }
   __syncthreads();
-  const int C = (nh + CTA_NT - 1) / CTA_NT;
+  const int C = (nh + NT - 1) / NT;
   const int r0 = tid * C, r1 = min(nh, r0 + C);
   for (int i = r0; i < r1; ++i) {
     if (!flag[i]) continue;

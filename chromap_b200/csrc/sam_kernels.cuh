@@ -19,52 +19,62 @@
 #define SAM_HD inline
 #endif
 
-// Same arithmetic and tie rules as ksw_semi_global3.  WIN(j): base code of the window at j (0..wlen-1), RD(i): base code of
-// the read at i.  Scores: match / -mismatch between codes < 4, 0 if either is "other" (mapping_generator.h:661-670).
-// Returns the number of CIGAR operations (BAM encoding len<<4|op, M=0 I=1 D=2) or -1 if they do not fit `cap`.
+// Semi-global affine alignment of the read against its verification window with the scores and tie rules of
+// ksw_semi_global3 (ksw.cc:505-626), for the one shape the SAM path uses it in (mapping_generator.h:723-760, 807-855):
+// window = read length + 2e, band w = 2e + 1, the read may start anywhere in the first w window positions for free.
+//
+// Formulated on DIAGONALS instead of columns: cell (i, j) of the band is (i, d = j - i), d = 0 .. w.  The three inputs of a
+// cell then sit at fixed places — the diagonal predecessor at the same d of the previous row, the vertical gap state at
+// d + 1 of the previous row, the horizontal gap state at d - 1 of this row — so the whole band state is two small arrays of
+// w + 2 integers that are updated in place and live in registers (the loop over d is unrolled; e <= 8 gives 18 cells),
+// and a row touches nothing else but its w + 1 direction bytes.  No per-column score arrays, no row buffers.
+//   m = diagonal + score;  h = max(m, e, f) with ties to m, then to the larger of (m, e) over f;
+//   e' = max(e - e_del, m - (o_del + e_del)), f' = max(f - e_ins, m - (o_ins + e_ins)), the "continue the gap" bit set only
+//   when strictly larger (ksw's rule: gaps open from m, not from h).
+// Direction byte: bits 0-1 the source of h (0 diagonal, 1 vertical, 2 horizontal), bits 2-3 / 4-5 the gap continuation
+// states, read back by the traceback exactly as ksw does.  WIN(j): base code of the window at j, RD(i): base code of the
+// read at i; scores: match / -mismatch between codes < 4, 0 if either is "other" (mapping_generator.h:661-670).
+// Returns the number of CIGAR operations (BAM encoding len << 4 | op, M = 0, I = 1, D = 2) or -1 if they do not fit `cap`.
+#define SAM_BAND (2 * SAM_MAX_E + 2)  // cells per row
 template <typename WinF, typename ReadF>
-SAM_HD int sam_sg_align(int wlen, int rlen, int w, int match, int mismatch, int o_del, int e_del, int o_ins, int e_ins, WinF WIN, ReadF RD,
-                        unsigned int *cigar, int cap, int *start, int *end) {
+SAM_HD int sam_band_align(int rlen, int e, int match, int mismatch, int o_del, int e_del, int o_ins, int e_ins, WinF WIN, ReadF RD, unsigned int *cigar, int cap,
+                          int *start, int *end) {
   const int NEG = -0x40000000;
-  int H[SAM_MAX_L + 2 * SAM_MAX_E + 2], E[SAM_MAX_L + 2 * SAM_MAX_E + 2];
-  unsigned char z[(2 * (2 * SAM_MAX_E + 1) + 1) * SAM_MAX_L];
+  const int w = 2 * e + 1, wlen = rlen + 2 * e;
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-  const int n_col = wlen < 2 * w + 1 ? wlen : 2 * w + 1;
-  H[0] = 0; E[0] = NEG;
-  int j = 1;
-  for (; j <= wlen && j <= w; ++j) { H[j] = 0; E[j] = NEG; }
-  for (; j <= wlen; ++j) H[j] = E[j] = NEG;
+  int hd[SAM_BAND], ed[SAM_BAND + 1];
+  unsigned char dirs[SAM_BAND * SAM_MAX_L];
+#pragma unroll
+  for (int d = 0; d < SAM_BAND; ++d) { hd[d] = 0; ed[d] = NEG; }  // free start on every diagonal of the band
+  ed[SAM_BAND] = NEG;
   for (int i = 0; i < rlen; ++i) {
-    int f = NEG;
-    const int beg = i, en = i + w + 1 < wlen ? i + w + 1 : wlen;
-    int h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : NEG;
     const unsigned int rc = RD(i);
-    unsigned char *zi = &z[i * n_col];
-    for (j = beg; j < en; ++j) {
-      int m = H[j], e = E[j];
-      H[j] = h1;
-      const unsigned int wc = WIN(j);
-      m += (rc < 4u && wc < 4u) ? (rc == wc ? match : -mismatch) : 0;
-      unsigned char d = m >= e ? 0 : 1;
-      int h = m >= e ? m : e;
-      d = h >= f ? d : 2;
-      h = h >= f ? h : f;
-      h1 = h;
-      int t = m - oe_del;
-      e -= e_del;
-      if (e > t) d |= 1 << 2; else e = t;
-      E[j] = e;
-      t = m - oe_ins;
+    unsigned char *row = &dirs[i * (w + 1)];
+    int f = NEG;
+#pragma unroll
+    for (int d = 0; d < SAM_BAND; ++d) {
+      if (d > w || i + d >= wlen) break;
+      const unsigned int wc = WIN(i + d);
+      const int m = hd[d] + ((rc < 4u && wc < 4u) ? (rc == wc ? match : -mismatch) : 0);
+      int ev = d < w ? ed[d + 1] : NEG;  // the cell above lies outside the previous row's band on the last diagonal
+      unsigned char dir = m >= ev ? 0 : 1;
+      int h = m >= ev ? m : ev;
+      if (!(h >= f)) { dir = 2; h = f; }
+      hd[d] = h;
+      const int td = m - oe_del, ti = m - oe_ins;
+      ev -= e_del;
+      if (ev > td) dir |= 1 << 2; else ev = td;
+      ed[d] = ev;
       f -= e_ins;
-      if (f > t) d |= 2 << 4; else f = t;
-      zi[j - beg] = d;
+      if (f > ti) dir |= 2 << 4; else f = ti;
+      row[d] = dir;
     }
-    H[en] = h1; E[en] = NEG;
   }
-  int score = H[wlen], best = wlen;
-  for (j = 1; j < w; ++j) if (H[wlen - j] > score) { score = H[wlen - j]; best = wlen - j; }
+  // the read ends on the last row: best of the last w window positions, the rightmost first (ksw.cc:585-590)
+  int score = hd[w - 1], best = wlen;
+  for (int j = 1; j < w; ++j) if (hd[w - 1 - j] > score) { score = hd[w - 1 - j]; best = wlen - j; }
   *end = best;
-  // traceback from (rlen-1, best-1); operations come out last-to-first, equal neighbours merged
+  // traceback from (rlen - 1, best - 1): operations come out last to first, equal neighbours merged
   int n = 0, i = rlen - 1, k = best - 1, which = 0;
   bool ovf = false;
   auto push = [&](unsigned int op, unsigned int len) {
@@ -73,7 +83,7 @@ SAM_HD int sam_sg_align(int wlen, int rlen, int w, int match, int mismatch, int 
     else ovf = true;
   };
   while (i >= 0 && k >= 0) {
-    which = z[i * n_col + (k - i)] >> (which << 1) & 3;
+    which = dirs[i * (w + 1) + (k - i)] >> (which << 1) & 3;
     if (which == 0) { push(0u, 1u); --i; --k; }
     else if (which == 1) { push(1u, 1u); --i; }
     else { push(2u, 1u); --k; }
@@ -109,11 +119,11 @@ __device__ __noinline__ bool sam_span(const DevParams &P, const DevRef &R, const
   const u8 *win = R.seq + R.off[rid] + vws;
   int s0 = 0, e0 = 0, n;
   if (strand == 0)
-    n = sam_sg_align(L + 2 * e, L, 2 * e + 1, 1, 4, 6, 1, 6, 1, [&](int j) { return base_code(__ldg(win + j)); }, [&](int i) { return base_code(read[i]); }, cigar,
-                     SAM_MAX_CIGAR, &s0, &e0);
+    n = sam_band_align(L, e, 1, 4, 6, 1, 6, 1, [&](int j) { return base_code(__ldg(win + j)); }, [&](int i) { return base_code(read[i]); }, cigar, SAM_MAX_CIGAR, &s0,
+                       &e0);
   else
-    n = sam_sg_align(L + 2 * e, L, 2 * e + 1, 1, 4, 6, 1, 6, 1, [&](int j) { return base_code(__ldg(win + j)); }, [&](int i) { return neg_code(read, L, i); }, cigar,
-                     SAM_MAX_CIGAR, &s0, &e0);
+    n = sam_band_align(L, e, 1, 4, 6, 1, 6, 1, [&](int j) { return base_code(__ldg(win + j)); }, [&](int i) { return neg_code(read, L, i); }, cigar, SAM_MAX_CIGAR, &s0,
+                       &e0);
   *st = vws + (u32)s0;
   *en = vws + (u32)e0 - 1u;
   if (n < 0) return false;

@@ -40,16 +40,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 #define SF_TILE 64   // pairs per tile
 #define SF_NT 128    // threads: warps 0-1 take mate 1 of the tile's pairs, warps 2-3 mate 2
-#define SF_PROBE_BATCH 8
+#define SF_PROBE_BATCH 4
+#define SF_KEY_ROWS 16  // minimizers per read buffered in shared memory between the scan and the probe
 struct FrontShared {
   u64 bar[2];
   u32 acc[3];
 };
-// dynamic shared memory: 2 stages x 2 mates x tile_bytes, tile_bytes = SF_TILE * maxmm + 32 (a multiple of 16)
+// dynamic shared memory: 2 stages x 2 mates x tile_bytes (tile_bytes = SF_TILE * maxmm + 32, a multiple of 16), then the key
+// buffer [SF_KEY_ROWS][SF_NT] u64 and the minimizer windows [8][SF_NT] u64 (one column per thread: conflict-free)
 __host__ __device__ inline size_t seed_front_tile_bytes(int maxmm) { return ((size_t)SF_TILE * maxmm + 32 + 15) / 16 * 16; }
+__host__ __device__ inline size_t seed_front_smem_bytes(int maxmm) { return 4 * seed_front_tile_bytes(maxmm) + (size_t)(SF_KEY_ROWS + 8) * SF_NT * 8; }
 
 // prepped = 1: prep_kernel ran before (adapter trimming): lengths and pair status are taken from the scratch.
 // Pairs [slot_begin, slot_end) of the tier (a call whose reads arrive in pieces launches one grid per piece).
+// FAST: k = 17, w = 7 (every preset): the packed-key scan only; otherwise the run-time scan only — one kernel per case keeps
+// the other's registers and code out of the way.
+template <bool FAST>
 __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int prepped, int slot_begin,
                                                            int slot_end) {
   extern __shared__ __align__(16) u8 sf_smem[];
@@ -57,6 +63,8 @@ __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIn
   const int tid = threadIdx.x;
   const int maxmm = S.caps.maxmm;
   const size_t tb = seed_front_tile_bytes(maxmm);
+  u64 *kbuf = (u64 *)(sf_smem + 4 * tb);
+  u64 *rbuf = kbuf + SF_KEY_ROWS * SF_NT;
   const int n_tiles = (slot_end - slot_begin + SF_TILE - 1) / SF_TILE;
   if (tid == 0) { mbar_init(&fs.bar[0], 1); mbar_init(&fs.bar[1], 1); mbar_fence_init(); }
   if (tid < 3) fs.acc[tid] = 0;
@@ -148,22 +156,31 @@ __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIn
       const size_t mb = mm_base(S, slot, mate);
       u64 *mmv = S.mm_val + mb;
       u32 *mmp = S.mm_pos + mb;
-      // minimizers: the hash is parked in the value array (replaced by the table value below)
-      minimizer_scan_any([&](int i) { return rd[i]; }, len, P.k, P.w, [&](u64 h, u32 p) {
-        if (n_mm < maxmm) { mmv[(size_t)n_mm * 32] = h; mmp[(size_t)n_mm * 32] = p; }
+      // minimizers as {hash, position | strand}: the first SF_KEY_ROWS of a read wait for their probe in shared memory
+      // (column `tid` of kbuf), later ones — long reads only — are parked in the record arrays themselves
+      u64 *kcol = kbuf + tid;
+      const int key_rows = P.k <= 22 ? SF_KEY_ROWS : 0;  // hash << 20 | position must fit 64 bits
+      auto emit = [&](u64 h, u32 p) {
+        if (n_mm < key_rows) kcol[n_mm * SF_NT] = (h << 20) | p;  // p < 2^20 (reads are far shorter than 2^19), h < 2^44
+        else if (n_mm < maxmm) { mmv[(size_t)n_mm * 32] = h; mmp[(size_t)n_mm * 32] = p; }
         ++n_mm;
-      });
+      };
+      if constexpr (FAST) minimizer_scan_packed<17, 7>([&](int i) { return rd[i]; }, len, emit, StridedU64{rbuf + tid, SF_NT});  // window in shared memory
+      else minimizer_scan<0, 0>([&](int i) { return rd[i]; }, len, P.k, P.w, emit);
       if (n_mm > maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); }
       else {
         // probes, eight at a time: the first slots of eight chains are in flight together (one 16-byte load each; the
-        // rare second step of a chain is issued when the first has come back)
+        // rare second step of a chain is issued when the first has come back).  One write per record, no read-back.
         for (int i0 = 0; i0 < n_mm; i0 += SF_PROBE_BATCH) {
           u64 h[SF_PROBE_BATCH], s[SF_PROBE_BATCH];
+          u32 pw[SF_PROBE_BATCH];
           ulonglong2 kv[SF_PROBE_BATCH];
 #pragma unroll
           for (int q = 0; q < SF_PROBE_BATCH; ++q)
             if (i0 + q < n_mm) {
-              h[q] = mmv[(size_t)(i0 + q) * 32];
+              const int i = i0 + q;
+              if (i < key_rows) { const u64 key = kcol[i * SF_NT]; h[q] = key >> 20; pw[q] = (u32)key & 0xFFFFFu; }
+              else { h[q] = mmv[(size_t)i * 32]; pw[q] = mmp[(size_t)i * 32]; }
               s[q] = (h[q] * 0x9E3779B97F4A7C15ull) >> ix.shift;
               kv[q] = __ldg(&ix.slots[s[q]]);
             }
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIn
                 c = __ldg(&ix.slots[sl]);
               }
               mmv[(size_t)(i0 + q) * 32] = val;
-              mmp[(size_t)(i0 + q) * 32] |= kind << 30;
+              mmp[(size_t)(i0 + q) * 32] = pw[q] | (kind << 30);
               found += kind != 0;
             }
         }

@@ -242,7 +242,9 @@ int cmx_last_batch_trace(cmx_ctx *ctx, cmx_pair_trace *out, uint32_t n_pairs);
 /* Kernel timing of the last cmx_map_batch_pe (CUDA events on the launching stream), in ms. */
 typedef struct {
   float h2d_ms, seed_ms, pair_candidates_ms, verify_ms, pairing_ms, select_ms, emit_ms, d2h_ms, total_ms;
-  float minimizer_ms, probe_ms, cluster_ms; /* tier-0 parts of seed_ms (prep + these three + overflow tiers) */
+  float front_ms, reserved_ms, cluster_ms;  /* tier-0 parts of seed_ms: front_ms = the fused front-end kernel (length filter +
+                                             * minimizers + index probe, seed_front.cuh), cluster_ms = hit lists + clustering;
+                                             * seed_ms - front_ms - cluster_ms = seeding of the overflow tiers */
   uint64_t n_minimizers, n_probe_steps, n_found, n_occ_reads, n_verified, n_launches;
   uint64_t tier_pairs[3];      /* pairs processed per scratch tier */
   uint64_t escalations[8];     /* tier-0 escalations by cause (see Counters::ovf_reason) */
@@ -289,12 +291,48 @@ int64_t cmx_format_paf(const cmx_params *p, const char *const *ref_names, const 
                        const char *const *names1, const uint16_t *lengths1, const char *const *names2, const uint16_t *lengths2,
                        uint32_t first_read_id, char *buf, int64_t cap);
 
+
+/* Page-lock (pin) a host buffer the caller owns, so that cmx_ingest_fastq / cmx_map_batch_pe copy from it at PCIe speed and
+ * asynchronously (cudaHostRegister / cudaHostUnregister).  Optional: unpinned buffers work, slower.  No counterpart in the
+ * reference (its loader hands kseq buffers to the mapping threads directly, sequence_batch.cc:9-60). */
+int cmx_host_register(void *ptr, uint64_t bytes);
+int cmx_host_unregister(void *ptr);
+
 /* Concurrency of one cmx_map_batch_pe call (no counterpart in the reference, whose knob is -t): a call that carries
  * several whole reference batches is cut into up to n_lanes (1..4, default 4) groups of batches that run the whole
  * pipeline on their own streams, so the latency-bound kernels of one group overlap the issue-bound kernels of
  * another.  Results do not depend on it.  With 1 lane the kernels of a call run back to back on one stream and
  * cmx_timing's stage times are exclusive; with more lanes they are sums over overlapping streams. */
 int cmx_set_lanes(cmx_ctx *ctx, int n_lanes);
+
+
+/* ---- multi-GPU: the one exchange step ---------------------------------------------------------------------
+ * One process per GPU; read batches are sharded over the ranks with no data-path collective.  Duplicate removal is defined
+ * over the whole run (the reference's low-memory merge, mapping_writer.h:166-376), so after mapping every rank packs its
+ * records into 16-byte tuples {rid | start, length | mapq | direction | unique | read_id} (24 bytes with a cell barcode), ONE
+ * ncclAllGather moves them over NVLink (preceded by an 8-byte all-gather of the counts that sizes it), and every rank sorts
+ * the gathered tuples on its GPU and decides which of ITS OWN records survive: the first record in the reference's order
+ * carrying the group's highest MAPQ (mapping_writer.h:268-270), duplicate count saturating at 255 (:282-284), MAPQ filter
+ * afterwards (:281).  The reference is single-process: there is no call site this replaces; it takes the place of the
+ * duplicate test inside OutputMappingsInVector / the temp-file merge (mapping_writer.h:254-287) for a sharded run.
+ * NCCL is loaded with dlopen at the first call (no link-time dependency); CMX_ERR_STATE if it is not there. */
+int cmx_comm_unique_id(void *id128);                                             /* rank 0: ncclGetUniqueId, 128 bytes */
+int cmx_comm_init(cmx_ctx *ctx, int n_ranks, int rank, const void *id128);       /* ncclCommInitRank on the context's device */
+int cmx_comm_destroy(cmx_ctx *ctx);
+typedef struct {
+  float pack_ms, allgather_ms, resolve_ms;   /* CUDA events on the context's stream */
+  uint64_t bytes_sent, bytes_received;       /* tuple bytes this rank contributed / received in the all-gather */
+  uint64_t n_global;                         /* records of all ranks */
+  uint32_t n_ranks, pad;
+} cmx_exchange_stats;
+/* records (and barcode_keys, NULL for bulk data): this rank's cmx_pe_record array, host or device (on_device); paired-end,
+ * low-memory mode (every preset that removes duplicates).  out_records / out_barcode_keys (same kind of memory, capacity n):
+ * this rank's survivors in the reference's order, num_dups set, MAPQ-filtered, Tn5 NOT yet applied. */
+int cmx_dedup_exchange(cmx_ctx *ctx, const void *records, const uint64_t *barcode_keys, uint64_t n, int on_device, void *out_records,
+                       uint64_t *out_barcode_keys, uint64_t *n_out, cmx_exchange_stats *stats);
+/* After the survivors of all ranks have been brought together (any transport; they are a small fraction of the run): the
+ * reference's order and the deferred Tn5 shift (mapping_writer.h:285-287).  Host only (no device needed), in place. */
+int cmx_exchange_finish(const cmx_params *params, cmx_pe_record *records, uint64_t *barcode_keys, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -232,6 +232,57 @@ def test_index_built_on_device_equals_reference_semantics(synth):
     assert bed == gzip.open(os.path.join(synth["d"], "default.bed.gz")).read()
 
 
+def test_device_built_index_has_the_content_of_the_reference_binarys_index(tmp_path):
+    """`chromap -i` (the unmodified reference binary, oracle/_ref) and cmx_build_index on the same 20 Mbp reference with planted
+    repeats and N runs: same k / w, same bucket count, the SAME occurrence table byte for byte, and every key of the reference's
+    hash table present on the device with the same value (and no other key).  Only the bucket ORDER inside khash's arrays is not
+    compared: it is a function of khash's resize history (kh_resize re-inserts in bucket order), not of the content; lookups do
+    not depend on it.  This is what lets bench.py's reference arm run on an index written by cmx_download_index."""
+    import subprocess
+    binp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "chromap")
+    if not os.path.exists(binp):
+        pytest.skip("oracle/_ref/chromap not built")
+    rng = np.random.default_rng(3)
+    seqs = []
+    fam = rng.integers(0, 4, 300)
+    for si in range(4):
+        s = rng.integers(0, 4, 5000000)
+        seg = rng.integers(0, 4, 5000)
+        for st in rng.integers(0, len(s) - 5000, 30):
+            s[st:st + 5000] = seg
+        for st in rng.integers(0, len(s) - 300, 800):
+            s[st:st + 300] = fam
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[s].copy()
+        for st in rng.integers(0, len(a) - 200, 40):
+            a[st:st + int(rng.integers(1, 200))] = ord("N")
+        seqs.append(a)
+    fa = tmp_path / "ref.fa"
+    with open(fa, "wb") as f:
+        for i, a in enumerate(seqs):
+            f.write(b">s%d\n" % i); a.tofile(f); f.write(b"\n")
+    idx = tmp_path / "ref.index"
+    r = subprocess.run([binp, "-i", "-r", str(fa), "-o", str(idx)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    a = orc.Index(str(idx)).arrays()
+    m = cb.Mapper(cb.make_params("", max_read_length=64))
+    m.upload_reference(seqs, ["s%d" % i for i in range(len(seqs))])
+    m.build_index(17, 7)
+    info = m.index_info()
+    d = m.download_index()
+    assert d["n_buckets"] == a["n_buckets"]
+    assert info["n_occ"] == len(a["occ"]) and np.array_equal(d["occ"], a["occ"])
+    nb = a["n_buckets"]
+    occupied = ((a["flags"][np.arange(nb) >> 4] >> ((np.arange(nb) & 15) << 1)) & 3) == 0
+    keys, vals = a["keys"][occupied], a["vals"][occupied]
+    assert len(keys) == info["n_keys"] == d["n_keys"]
+    f, k, v = m.stage_probe(keys >> np.uint64(1))
+    assert f.all() and np.array_equal(k, keys) and np.array_equal(v, vals)
+    # the file layout we write holds the same multiset of (key, value) pairs
+    occ_d = ((d["flags"][np.arange(nb) >> 4] >> ((np.arange(nb) & 15) << 1)) & 3) == 0
+    o1, o2 = np.argsort(keys), np.argsort(d["keys"][occ_d])
+    assert np.array_equal(keys[o1], d["keys"][occ_d][o2]) and np.array_equal(vals[o1], d["vals"][occ_d][o2])
+
+
 def test_reference_quickstart_golden(golden_dir):
     """BASELINE config 1 (reference test/ data): md5 e311f0a0… / 63b977e6…"""
     import hashlib
@@ -432,6 +483,36 @@ def test_postprocess_on_device_equals_host(kind, low_mem, dedup, tn5, q):
         else:
             want, got = m.postprocess(recs), m.postprocess_gpu(recs)
         assert_same_records(got, want)
+
+
+@pytest.mark.parametrize("bc", [False, True])
+@pytest.mark.parametrize("dedup,tn5,q", [(1, 0, 30), (1, 1, 0), (0, 1, 3)])
+def test_native_dedup_exchange_world_of_one_equals_host_postprocess(bc, dedup, tn5, q):
+    """cmx_dedup_exchange (tuple pack, ncclAllGather, radix sort, survivor rule on the GPU) with a communicator of one rank +
+    cmx_exchange_finish == the host low-memory post-processing.  The N > 1 run is tools/multi_gpu_map.py under torchrun."""
+    rng = np.random.default_rng(31 + dedup * 4 + tn5 * 2 + q + (8 if bc else 0))
+    p = cb.make_params("", max_read_length=64, tn5_shift=tn5, low_memory_mode=1, remove_pcr_duplicates=dedup, mapq_threshold=q)
+    m = cb.Mapper(p)
+    m.comm_init(1, 0, m.comm_unique_id())
+    for n in (0, 1, 1000, 200000):
+        recs = _random_records(rng, n, False)
+        if n >= 1000:
+            recs[: n // 3] = recs[0]
+            recs["read_id"][: n // 3] = np.arange(n // 3, dtype=np.uint32) + 7 * n
+            recs["mapq"][: n // 3] = rng.choice([0, 30, 60], n // 3)
+        if bc:
+            bcs = rng.integers(0, 5, n).astype(np.uint64) * 0x123456789
+            want, wbc = m.postprocess_bc(recs, bcs)
+            surv, sbc, st = m.dedup_exchange(recs, bcs)
+            got, gbc = cb.exchange_finish(p, surv, sbc)
+            assert np.array_equal(wbc, gbc)
+        else:
+            want = m.postprocess(recs)
+            surv, st = m.dedup_exchange(recs)
+            got = cb.exchange_finish(p, surv)
+        assert st["n_global"] == n and st["n_ranks"] == 1
+        assert_same_records(got, want)
+    m.comm_destroy()
 
 
 @pytest.mark.parametrize("bc", [False, True])

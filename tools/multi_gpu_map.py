@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU end-to-end check (run under torchrun on N GPUs): every rank maps the reference batches it owns
-(batch b -> rank b mod N), the ranks run the one NCCL exchange (duplicate removal, chromap_b200.distributed),
+(batch b -> rank b mod N), the ranks run the one NCCL exchange (duplicate removal, cmx_dedup_exchange),
 rank 0 writes the BED — which must equal the single-process result byte for byte.
 
   torchrun --nproc-per-node 2 tools/multi_gpu_map.py --dir tests/golden/synth_small --preset chip --batch 1000
@@ -45,8 +45,11 @@ def main():
         r, _ = m.map_batch(s1[o1[b0]:o1[b1]], o1[b0:b1 + 1] - o1[b0], s2[o2[b0]:o2[b1]], o2[b0:b1 + 1] - o2[b0], first_read_id=b0)
         mine.append(r.copy())
     mine = np.concatenate(mine) if mine else np.zeros(0, dtype=cb.PE_RECORD)
-    surv = cd.dedup_exchange(mine, p, device=dev)       # the NCCL all-gather
-    final = cd.gather_and_finish(surv, p)
+    cd.init_comm(m)                                       # the library's own NCCL communicator
+    surv, xst = cd.dedup_exchange(m, mine)                # pack -> ONE ncclAllGather -> sort / decide on the GPU
+    final = cd.gather_and_finish(p, surv)
+    if rank == 0:
+        print("multi_gpu_map: exchange", xst, flush=True)
     if rank == 0:
         bed = m.format_bed(final)
         # single-process result on this rank's GPU for comparison
