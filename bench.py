@@ -418,7 +418,7 @@ def run_ours(a):
     # ---- the one collective of the multi-GPU path, outside the timed mapping region: duplicate removal over the
     # records of up to four mapped batches per rank: tuple pack -> ONE ncclAllGather -> radix sort + survivor rule on the GPU
     exchange = None
-    if params.remove_pcr_duplicates and params.output_format != 5 and not a.no_exchange:
+    if params.remove_pcr_duplicates and params.output_format != 5 and not a.no_exchange and not a.barcodes:  # (bulk records: the barcoded leg keeps its keys on the host)
         try:
             m.set_lanes(a.lanes)
             keep = []

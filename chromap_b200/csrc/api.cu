@@ -63,8 +63,8 @@ struct Lane {
   Tier tiers[N_TIERS];
   cudaStream_t stream = nullptr, aux[N_TIERS - 1] = {nullptr, nullptr};  // aux: emit of the overflow tiers, beside tier 0's
   cudaEvent_t ev_fork = nullptr, ev_join[N_TIERS - 1] = {nullptr, nullptr};
-  cudaEvent_t ev[10];
-  cudaEvent_t ev_sub[2];
+  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev_sub[2] = {};
   cudaEvent_t ev_done = nullptr;
   u32 p0 = 0, n = 0;  // pair range of the last call
   int tiers_used = 0;
@@ -120,7 +120,7 @@ struct cmx_ctx {
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
   std::vector<cudaEvent_t> ev_up;
   cudaEvent_t ev_bc = nullptr;
-  cudaEvent_t ev[4];
+  cudaEvent_t ev[4] = {};
   cmx_timing timing;
   u32 last_n_pairs = 0;
   // multi-GPU exchange (cmx_comm_init / cmx_dedup_exchange): an NCCL communicator of this context's own
@@ -189,25 +189,28 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   if (params->max_num_best_mappings < 1 || params->max_num_best_mappings > CMX_MAX_BEST) return CMX_ERR_INVALID;
   if (params->batch_size < 1 || params->max_read_length < params->min_read_length) return CMX_ERR_INVALID;
   if (params->single_end && (params->split_alignment || params->output_format == 5)) return CMX_ERR_INVALID;  // single-end: BED / TagAlign only
+  if (params->output_format == 5 && params->remove_pcr_duplicates && !params->low_memory_mode) return CMX_ERR_INVALID;  // pairs dedup: low-memory rule only
   cmx_ctx *ctx = new cmx_ctx;
+  // a failing CUDA call releases what has been built so far (streams, events, device buffers)
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cmx_destroy(ctx); return CMX_ERR_CUDA; } } while (0)
   ctx->device = device;
   ctx->params = *params;
-  CU(cudaSetDevice(device));
-  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
-  for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
+  CUC(cudaSetDevice(device));
+  CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+  for (auto &e : ctx->ev) CUC(cudaEventCreate(&e));
   if (const char *ev = getenv("CMX_LANES")) ctx->n_lanes = std::max(1, std::min(CMX_MAX_LANES, atoi(ev)));
   for (Lane &L : ctx->lanes) {
-    CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-    for (auto &a : L.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
-    for (auto &e : L.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : L.ev) CU(cudaEventCreate(&e));
-    for (auto &e : L.ev_sub) CU(cudaEventCreate(&e));
-    CU(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
-    CU(cudaMalloc(&L.ctr, sizeof(Counters)));
-    CU(cudaMalloc(&L.d_count, sizeof(int) * 4));
+    CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    for (auto &a : L.aux) CUC(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+    for (auto &e : L.ev_join) CUC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : L.ev) CUC(cudaEventCreate(&e));
+    for (auto &e : L.ev_sub) CUC(cudaEventCreate(&e));
+    CUC(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    CUC(cudaMalloc(&L.ctr, sizeof(Counters)));
+    CUC(cudaMalloc(&L.d_count, sizeof(int) * 4));
   }
   // MAPQ tables from the host libm, so truncations match the reference bit for bit (mapping_generator.h:920-1022)
   {
@@ -222,36 +225,41 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
       while (lo < hi) { const long long mid = (lo + hi) / 2; if (pen(mid) >= v) hi = mid; else lo = mid + 1; }
       thr[v] = (int)lo;
     }
-    CU(cudaMalloc(&ctx->inv_log, 65536 * sizeof(double)));
-    CU(cudaMalloc(&ctx->pen_thr, 96 * sizeof(int)));
-    CU(cudaMemcpy(ctx->inv_log, il.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->pen_thr, thr.data(), 96 * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->inv_log, 65536 * sizeof(double)));
+    CUC(cudaMalloc(&ctx->pen_thr, 96 * sizeof(int)));
+    CUC(cudaMemcpy(ctx->inv_log, il.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->pen_thr, thr.data(), 96 * sizeof(int), cudaMemcpyHostToDevice));
   }
   {
     std::vector<u32> mt(624);
     mt[0] = 11u;
     for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (u32)i;
-    CU(cudaMalloc(&ctx->mt_init, 624 * sizeof(u32)));
-    CU(cudaMemcpy(ctx->mt_init, mt.data(), 624 * sizeof(u32), cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->mt_init, 624 * sizeof(u32)));
+    CUC(cudaMemcpy(ctx->mt_init, mt.data(), 624 * sizeof(u32), cudaMemcpyHostToDevice));
   }
   // the overflow-tier kernels may use more than the default 48 KB of (static + dynamic) shared memory
-  CU(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * CLUSTER_NT * 8));  // tier-0 hc = 64
-  CU(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  CU(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CU(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  CU(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  CU(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CUC(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * CLUSTER_NT * 8));  // tier-0 hc = 64
+  CUC(cudaFuncSetAttribute(seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CUC(cudaFuncSetAttribute(pair_candidates_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUC(cudaFuncSetAttribute(verify_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CUC(cudaFuncSetAttribute(pairing_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CUC(cudaFuncSetAttribute(verify_split_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int mrl = params->max_read_length;
+  if ((size_t)2 * mrl * 64 > 48 * 1024) {  // per-thread read-code columns of the verification kernels (long reads)
+    if ((size_t)2 * mrl * 64 > 200 * 1024) { cmx_destroy(ctx); return CMX_ERR_INVALID; }
+    CUC(cudaFuncSetAttribute(verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mrl * 64));
+    CUC(cudaFuncSetAttribute(verify_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mrl * 64));
+  }
   {
     const size_t sf_smem = seed_front_smem_bytes(mrl);
-    CU(cudaFuncSetAttribute(seed_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
-    CU(cudaFuncSetAttribute(seed_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
+    CUC(cudaFuncSetAttribute(seed_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
+    CUC(cudaFuncSetAttribute(seed_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_smem));
     int per_sm = 0, n_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_front_kernel<true>, SF_NT, sf_smem));
-    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_front_kernel<true>, SF_NT, sf_smem));
+    CUC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     ctx->sf_grid = std::max(1, per_sm) * std::max(1, n_sm);
     int per_sm_w = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, pair_candidates_cta_kernel, 32, pair_candidates_cta_smem(64, 32, mrl, 64)));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, pair_candidates_cta_kernel, 32, pair_candidates_cta_smem(64, 32, mrl, 64)));
     ctx->pcw_grid = std::max(1, per_sm_w) * std::max(1, n_sm);
   }
   for (Lane &L : ctx->lanes) {
@@ -260,6 +268,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
     L.tiers[2].caps = {mrl * 4, 65536, 8192, 8192};
   }
   memset(&ctx->timing, 0, sizeof(ctx->timing));
+#undef CUC
   *out = ctx;
   return CMX_OK;
 }
@@ -267,6 +276,7 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
 void cmx_destroy(cmx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cmx_comm_destroy(ctx);
   cudaFree(ctx->ref_seq); cudaFree(ctx->ref_off); cudaFree(ctx->ref_len);
   cudaFree(ctx->slots); cudaFree(ctx->occ); cudaFree(ctx->inv_log); cudaFree(ctx->pen_thr); cudaFree(ctx->mt_init);
   cudaFree(ctx->wl_slots); cudaFree(ctx->wl_pow);
@@ -276,8 +286,8 @@ void cmx_destroy(cmx_ctx *ctx) {
     for (DevBuf *b : {&L.rescue_list, &L.verify_list, &L.emit_list, &L.nbest, &L.sel, &L.out_rec, &L.out_n, &L.offs, &L.chunk_start, &L.cub_tmp, &L.bc_key, &L.bc_ok, &L.out_compact, &L.bc_out})
       release(*b);
     for (auto &t : L.tiers) { release(t.mem); release(t.ovf_list); }
-    for (auto &e : L.ev) cudaEventDestroy(e);
-    for (auto &e : L.ev_sub) cudaEventDestroy(e);
+    for (auto &e : L.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : L.ev_sub) if (e) cudaEventDestroy(e);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.stream) cudaStreamDestroy(L.stream);
     for (auto &a : L.aux) if (a) cudaStreamDestroy(a);
@@ -288,7 +298,7 @@ void cmx_destroy(cmx_ctx *ctx) {
     for (DevBuf *b : {&g.text, &g.nl, &g.seq_start, &g.qual_start, &g.len, &g.off, &g.seq, &g.qual, &g.spans, &g.tmp, &g.stats, &g.count}) release(*b);
     if (g.stream) cudaStreamDestroy(g.stream);
   }
-  for (auto &e : ctx->ev) cudaEventDestroy(e);
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->ev_up) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
@@ -725,10 +735,10 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr, 0, (int *)L.rescue_list.p, L.d_count + 1);
       pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, L.ctr, 1, (int *)L.rescue_list.p, L.d_count + 1);
       CUL(cudaEventRecord(e2, st));
-      if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
+      if (P.split) verify_split_kernel<<<(2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, st>>>(P, R, B, S, L.ctr);
       else {
         verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr, 0, (int *)L.verify_list.p, L.d_count + 2);
-        verify_kernel<<<(2 * n_slots + 63) / 64, 64, 0, st>>>(P, R, B, S, L.ctr, 1, (int *)L.verify_list.p, L.d_count + 2);
+        verify_kernel<<<(2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, st>>>(P, R, B, S, L.ctr, 1, (int *)L.verify_list.p, L.d_count + 2);
       }
       CUL(cudaEventRecord(e3, st));
       if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);

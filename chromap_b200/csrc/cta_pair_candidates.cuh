@@ -465,7 +465,6 @@ __device__ inline void pair_candidates_cta_pair(const DevParams &P, const DevInd
     cta_pe_filter((u32)P.max_insert, lp[0], lc[0], nq[0], lp[3], lc[3], nq[3], CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b, fl_a, fl_b, RS.warp);
     cta_pe_filter((u32)P.max_insert, lp[1], lc[1], nq[1], lp[2], lc[2], nq[2], CP(0, 0, 1), CC(0, 0, 1), &a2, CP(1, 0, 0), CC(1, 0, 0), &b2, fl_a, fl_b, RS.warp);
     if (tid == 0) {
-      rm[0].n_buf[0] = nq[0]; rm[0].n_buf[1] = nq[1]; rm[1].n_buf[0] = nq[2]; rm[1].n_buf[1] = nq[3];
       rm[0].n_cand[0] = a; rm[1].n_cand[1] = b; rm[0].n_cand[1] = a2; rm[1].n_cand[0] = b2;
     }
     nc1 = a + a2; nc2 = b + b2;

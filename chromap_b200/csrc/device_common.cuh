@@ -24,19 +24,18 @@ struct Caps {  // per-read (per-strand where applicable) scratch capacities of o
 // pair status
 enum { ST_OK = 0, ST_DROP = 1, ST_OVERFLOW = 2 };
 
-struct ReadMeta {
+struct ReadMeta {  // 64 bytes = two 32-byte sectors: what seeding / candidate pairing touch in the first, verification / pairing / emit in the second
   int len;  // after adapter trimming
   int n_mm;
-  int n_hits[2];
   int n_cand[2];
-  int n_buf[2];
-  int n_aug[2];
-  int n_map[2];
   int n_cand_gen[2];
-  int min_err, second_min_err, n_best, n_second_best;
   u32 rep_len;
-  int pad;
+  int pad0;
+  int n_map[2];
+  int min_err, second_min_err, n_best, n_second_best;
+  int n_aug[2];
 };
+static_assert(sizeof(ReadMeta) == 64, "ReadMeta: two sectors");
 
 struct PairMeta {
   int status;

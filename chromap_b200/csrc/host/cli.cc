@@ -53,11 +53,12 @@ struct RawFile {
   std::vector<char> buf;
   size_t have = 0;
   bool eof = false, pinned = false;
+  size_t fpos = 0;                   // plain files: offset of the next unread byte
   size_t scan = 0, end_of_last = 0;  // scan state: bytes examined, end of the last whole record among them
   uint32_t lines = 0, recs = 0;      // newlines of the record under way, whole records found
   bool Open(const std::string &path) {
     Close();
-    have = 0; eof = false; scan = end_of_last = 0; lines = recs = 0;
+    have = 0; eof = false; scan = end_of_last = 0; lines = recs = 0; fpos = 0;
     unsigned char magic[2] = {0, 0};
     FILE *t = fopen(path.c_str(), "rb");
     if (!t) return false;
@@ -90,11 +91,30 @@ struct RawFile {
         if (++lines == 4) { lines = 0; ++recs; end_of_last = scan; }
       }
       if (recs == max_records || eof) { *n = recs; return end_of_last; }
-      const size_t want = 32u << 20;
+      const size_t want = f ? (32u << 20) : (128u << 20);
       Reserve(have + want + 1);
       long got;
       if (f) got = gzread(f, buf.data() + have, (unsigned)want);
-      else got = (long)read(fd, buf.data() + have, want);
+      else {  // plain file: four threads pread() a quarter each (one thread copies out of the page cache at about 5 GB/s)
+        const int nt = 4;
+        const size_t slice = want / nt;
+        long part[4] = {0, 0, 0, 0};
+        std::thread th[4];
+        for (int t = 0; t < nt; ++t)
+          th[t] = std::thread([&, t]() {
+            size_t done = 0;
+            while (done < slice) {
+              const ssize_t r = pread(fd, buf.data() + have + t * slice + done, slice - done, (off_t)(fpos + t * slice + done));
+              if (r <= 0) break;
+              done += (size_t)r;
+            }
+            part[t] = (long)done;
+          });
+        for (int t = 0; t < nt; ++t) th[t].join();
+        got = 0;
+        for (int t = 0; t < nt; ++t) { got += part[t]; if ((size_t)part[t] < slice) break; }  // a short slice is the end of the file
+        fpos += (size_t)got;
+      }
       if (got <= 0) {
         eof = true;
         if (have > 0 && buf[have - 1] != '\n') buf[have++] = '\n';  // a last line without its newline
@@ -181,6 +201,7 @@ static uint32_t LoadBatch(SeqReader &r1, SeqReader &r2, uint32_t max_pairs, Batc
         b->bc += s; b->bq += q;
       }
     }
+    if (r1.Corrupted() || (!se && r2.Corrupted()) || (rb && rb->Corrupted())) Die("Didn't reach the end of sequence file, which might be corrupted!");  // sequence_batch.cc:46-55
     if (!a && !c && !d) break;
     if (a != c || c != d) Die("Numbers of reads and barcodes don't match!");
     ++b->n;
@@ -204,6 +225,8 @@ int main(int argc, char **argv) {
   if (cmx_apply_preset(&p, preset.c_str()) != 0) Die("Unrecognized preset parameters " + preset + "\n");
   if (preset == "atac") cell_level_dedup = true;  // chromap_driver.cc:254
   if (!preset.empty()) fprintf(stderr, "Preset parameters for %s are used.\n", preset.c_str());
+  for (int i = 1; i + 1 < argc; ++i)
+    if (!strcmp(argv[i], "--min-frag-length")) { const int l = atoi(argv[i + 1]); if (l <= 60) { k = 17; w = 7; } else if (l <= 80) { k = 19; w = 10; } else { k = 23; w = 11; } }
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto val = [&]() -> std::string { if (i + 1 >= argc) Die("Option " + a + " is missing an argument"); return argv[++i]; };
@@ -219,7 +242,7 @@ int main(int argc, char **argv) {
     else if (a == "-t" || a == "--num-threads") threads = atoi(val().c_str());
     else if (a == "-k" || a == "--kmer") k = atoi(val().c_str());
     else if (a == "-w" || a == "--window") w = atoi(val().c_str());
-    else if (a == "--min-frag-length") { const int l = atoi(val().c_str()); if (l <= 60) { k = 17; w = 7; } else if (l <= 80) { k = 19; w = 10; } else { k = 23; w = 11; } }
+    else if (a == "--min-frag-length") val();  // applied before this loop: -k / -w always win over it (chromap_driver.cc:277-295)
     else if (a == "-e" || a == "--error-threshold") p.error_threshold = atoi(val().c_str());
     else if (a == "-s" || a == "--min-num-seeds") p.min_num_seeds = atoi(val().c_str());
     else if (a == "-f" || a == "--max-seed-frequencies") { const std::string v = val(); if (sscanf(v.c_str(), "%d,%d", &p.max_seed_freq0, &p.max_seed_freq1) != 2) Die("-f expects two comma separated integers"); }
@@ -295,6 +318,8 @@ int main(int argc, char **argv) {
   if (se && pairs) Die("chromap-b200: pairs output needs paired-end reads");
   if ((tagalign || sam || paf) && !bc_path.empty()) Die("chromap-b200: --TagAlign / --SAM / --PAF with barcodes is not on the GPU path");
   if (paf && (sam || tagalign || pairs || p.trim_adapters)) Die("chromap-b200: --PAF goes with BED-path mapping without adapter trimming (trimmed read lengths are not returned yet)");
+  if (pairs && p.remove_pcr_duplicates && !p.low_memory_mode)  // RemovePCRDuplicate keeps the LAST record of a run (mapping_processor.h:181-197): not on the GPU path for pairs
+    Die("chromap-b200: duplicate removal of Hi-C pairs needs --low-mem (or --preset hic)");
   if (!bc_path.empty() && p.remove_pcr_duplicates && p.low_memory_mode && !cell_level_dedup)  // mapping_writer.h:254-262: only the low-memory merge has the bulk-level variant
     Die("chromap-b200: bulk-level duplicate removal of barcoded data is not on the GPU path (use --preset atac or --remove-pcr-duplicates-at-cell-level)");
   if (out_path.empty()) Die("No output file specified!");

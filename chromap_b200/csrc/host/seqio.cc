@@ -89,7 +89,10 @@ bool SeqReader::Next(std::string *name, std::string *seq, std::string *qual) {
     if (!GetLine(&line)) break;
     qual->append(line);
   }
-  return true;
+  // kseq.h:213-218: a missing or differently long quality string is an error (-2); the reference's loader then stops with
+  // "Didn't reach the end of sequence file, which might be corrupted!" (sequence_batch.cc:46-55)
+  if (qual->size() != seq->size()) corrupted_ = true;
+  return !corrupted_;
 }
 
 bool Reference::Load(const std::string &path) {

@@ -15,8 +15,9 @@ class SeqReader {
  public:
   bool Open(const std::string &path);
   void Close();
-  // false at end of file.  `qual` stays empty for FASTA.
+  // false at end of file or on a corrupted record (Corrupted() tells which).  `qual` stays empty for FASTA.
   bool Next(std::string *name, std::string *seq, std::string *qual);
+  bool Corrupted() const { return corrupted_; }
   ~SeqReader() { Close(); }
 
  private:
@@ -27,6 +28,7 @@ class SeqReader {
   size_t pos_ = 0, end_ = 0;
   bool eof_ = false;
   int pending_ = 0;  // header character already consumed
+  bool corrupted_ = false;
 };
 
 struct Reference {

@@ -187,7 +187,8 @@ static int build_index_on_device(const u8 *d_ref, const std::vector<u64> &off, c
     for (u64 s = 0; s < len[r]; s += IB_CHUNK) { c_off.push_back(off[r]); c_len.push_back(len[r]); c_rid.push_back((u32)r); c_start.push_back((u32)s); }
   }
   const size_t n_chunks = c_off.size();
-  const u64 cap = total / 3 + 1024 * off.size() + 4096;  // average spacing (w+1)/2 ~ 4 for w=7; generous
+  // minimizer density is about 2 / (w + 1) per base: 1/4 for w = 7; the buffer follows w (with 30 % slack) so that small windows fit
+  const u64 cap = (u64)((double)total * std::min(1.0, 2.6 / (double)(w + 1))) + 1024 * off.size() + 4096;
   u64 *d_coff = nullptr, *h1 = nullptr, *t1 = nullptr, *h2 = nullptr, *t2 = nullptr, *d_occ = nullptr;
   u32 *d_clen = nullptr, *d_crid = nullptr, *d_cstart = nullptr, *d_multi = nullptr, *d_occidx = nullptr;
   unsigned long long *d_cnt = nullptr;

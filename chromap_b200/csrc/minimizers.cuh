@@ -198,11 +198,74 @@ __device__ __forceinline__ void minimizer_scan_packed(SeqF SEQ, int len, EmitF E
   }
   if (best != NONE) emit_key(best);
 }
-// the same with the window in registers
+// the same with the window in registers, as a shift register (oldest entry first) so that every access has a static index
 template <int K, int W, typename SeqF, typename EmitF>
 __device__ __forceinline__ void minimizer_scan_packed(SeqF SEQ, int len, EmitF EMIT) {
+  static_assert((K & 1) && K >= 17 && K <= 21 && W >= 2, "minimizer_scan_packed: odd k, 2k + 20 <= 62");
+  constexpr u64 mask = (((u64)1) << (2 * K)) - 1;
+  constexpr int shift = 2 * (K - 1);
+  constexpr u64 NONE = ~0ull;
+  constexpr u32 PM = 0xFFFFFu;
+  u64 fwd = 0, rev = 0;
   u64 ring[W];
-  minimizer_scan_packed<K, W>(SEQ, len, EMIT, ring);
+#pragma unroll
+  for (int i = 0; i < W; ++i) ring[i] = NONE;
+  u64 best = NONE;
+  int run = 0;
+  auto emit_key = [&](u64 key) { EMIT(key >> 20, PM - ((u32)key & PM)); };
+#pragma unroll 1
+  for (int pos = 0; pos < len; ++pos) {
+    const u32 b = base_code(SEQ(pos));
+    u64 cur = NONE;
+    if (b < 4) {
+      fwd = ((fwd << 2) | b) & mask;
+      rev = (rev >> 2) | (((u64)(3 ^ b)) << shift);
+      ++run;
+      if (run >= K) {
+        const u64 hf = mix64_k<K>(fwd), hr = mix64_k<K>(rev);
+        const u32 strand = hf < hr ? 0u : 1u;
+        cur = (mix64_k<K>(strand ? hr : hf) << 20) | (u64)(PM - (((u32)pos << 1) | strand));
+      }
+    } else {
+      run = 0;
+    }
+    if (run == W + K - 1 && best != NONE && (best >> 20) < (cur >> 20)) {  // ring[1 .. W-1]: the entries before `cur`, oldest first
+#pragma unroll
+      for (int q = 1; q < W; ++q) {
+        const u64 x = ring[q];
+        if ((x >> 20) == (best >> 20) && x != best) emit_key(x);
+      }
+    }
+    const u64 old = ring[0];
+#pragma unroll
+    for (int q = 0; q + 1 < W; ++q) ring[q] = ring[q + 1];
+    ring[W - 1] = cur;
+    u64 m = ring[0];
+#pragma unroll
+    for (int q = 1; q < W; ++q) m = min(m, ring[q]);
+    u64 out = NONE;
+    bool left = false;
+    if (cur <= best) {
+      if (run >= W + K && best != NONE) out = best;
+    } else if (old == best) {
+      if (run >= W + K - 1) { out = best; left = m != NONE; }
+    }
+    if (out != NONE) emit_key(out);
+    int same_hi = 0;
+    if (left) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) same_hi += (u32)(ring[q] >> 32) == (u32)(m >> 32);
+    }
+    if (same_hi > 1) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        const u64 x = ring[q];
+        if ((x >> 20) == (m >> 20) && x != m) emit_key(x);
+      }
+    }
+    best = m;
+  }
+  if (best != NONE) emit_key(best);
 }
 
 // dispatch on the (k, w) pairs the presets use; anything else takes the run-time body

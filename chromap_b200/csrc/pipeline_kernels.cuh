@@ -212,7 +212,6 @@ __global__ void __launch_bounds__(CLUSTER_NT) cluster_kernel(DevParams P, DevInd
   sort_u64(hp, np);
   sort_u64(hn, nn);
   rm.rep_len = st.len;
-  rm.n_hits[0] = np; rm.n_hits[1] = nn;
   int need = n_mm - st.count;
   need = need > 1 ? need : 1;
   need = need > P.min_seeds ? P.min_seeds : need;
@@ -433,7 +432,6 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
       int nc1 = nq[0] + nq[1], nc2 = nq[2] + nq[3];
       if (nc1 > 0 && nc2 > 0) {
         int a, b;
-        rm[0].n_buf[0] = nq[0]; rm[0].n_buf[1] = nq[1]; rm[1].n_buf[0] = nq[2]; rm[1].n_buf[1] = nq[3];
         pe_filter_dir((u32)P.max_insert, lp[0], lc[0], nq[0], lp[3], lc[3], nq[3], CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
         rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
         nc1 = a; nc2 = b;
@@ -500,19 +498,20 @@ __global__ void pair_candidates_kernel(DevParams P, DevIndex ix, Scratch S, Coun
   int nc1 = rm[0].n_cand[0] + rm[0].n_cand[1], nc2 = rm[1].n_cand[0] + rm[1].n_cand[1];
   if (nc1 > 0 && nc2 > 0) {
     // move candidates to the buffer set (1), filter back into set 0
+    int nbuf[2][2];
     for (int mate = 0; mate < 2; ++mate)
       for (int s = 0; s < 2; ++s) {
         const int n = rm[mate].n_cand[s];
         u64 *src = CP(mate, 0, s), *dst = CP(mate, 1, s);
         u8 *srcc = CC(mate, 0, s), *dstc = CC(mate, 1, s);
         for (int i = 0; i < n; ++i) { dst[i] = src[i]; dstc[i] = srcc[i]; }
-        rm[mate].n_buf[s] = n;
+        nbuf[mate][s] = n;
       }
     int a, b;
-    pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), rm[0].n_buf[0], CP(1, 1, 1), CC(1, 1, 1), rm[1].n_buf[1],
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 0), CC(0, 1, 0), nbuf[0][0], CP(1, 1, 1), CC(1, 1, 1), nbuf[1][1],
                   CP(0, 0, 0), CC(0, 0, 0), &a, CP(1, 0, 1), CC(1, 0, 1), &b);
     rm[0].n_cand[0] = a; rm[1].n_cand[1] = b;
-    pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), rm[0].n_buf[1], CP(1, 1, 0), CC(1, 1, 0), rm[1].n_buf[0],
+    pe_filter_dir((u32)P.max_insert, CP(0, 1, 1), CC(0, 1, 1), nbuf[0][1], CP(1, 1, 0), CC(1, 1, 0), nbuf[1][0],
                   CP(0, 0, 1), CC(0, 0, 1), &a, CP(1, 0, 0), CC(1, 0, 0), &b);
     rm[0].n_cand[1] = a; rm[1].n_cand[0] = b;
     nc1 = rm[0].n_cand[0] + rm[0].n_cand[1];
@@ -632,19 +631,30 @@ __global__ void verify_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Coun
   }
   u64 n_verified = 0;
   if (mode == 0 && !done && nc[0] + nc[1] > 0) { list[agg_append(list_count)] = sr; return; }
-  if (!done) {
+  if (!done && nc[0] + nc[1] > 0) {  // (pass 0 never gets here: it has listed the read; it is launched without the code buffer)
     auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };  // candidate.h:23-33
     sort_pairs<u8>(cp[0], cc[0], nc[0], cless);
     sort_pairs<u8>(cp[1], cc[1], nc[1], cless);
+    // the read's base codes, forward and reverse-complemented, in this thread's column of shared memory (byte i of thread t at
+    // [i][t]: conflict-free): both strands then run the SAME alignment code (a warp no longer splits by strand), and a column
+    // of the band costs one shared-memory byte instead of a global load + decode
+    extern __shared__ u8 v_codes[];
+    const int NTB = blockDim.x;
+    u8 *c_fwd = v_codes + threadIdx.x, *c_neg = v_codes + (size_t)c.maxmm * NTB + threadIdx.x;
+    for (int i = 0; i < L; ++i) {
+      const u32 b = base_code(read[i]);
+      c_fwd[(size_t)i * NTB] = (u8)b;
+      c_neg[(size_t)(L - 1 - i) * NTB] = (u8)(b < 4 ? 3u ^ b : 4u);
+    }
     for (int s = 0; s < 2; ++s) {
+      const u8 *txt = s == 0 ? c_fwd : c_neg;
       auto run_one = [&](u64 cpos) -> bool {  // returns true if the candidate failed (> e errors)
         const u32 rid = (u32)(cpos >> 32);
         const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
         const u8 *win = R.seq + R.off[rid] + pos - e;
         prefetch_span(win, L + 2 * e);
-        int endp = 0, err;
-        if (s == 0) err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return base_code(read[i]); }, &endp);
-        else err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp);
+        int endp = 0;
+        const int err = banded_align(e, L, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return (u32)txt[(size_t)i * NTB]; }, &endp);
         ++n_verified;
         if (err > e) return true;
         tally(t, err);
@@ -1048,6 +1058,7 @@ __device__ __forceinline__ void mapping_span(const DevRef &R, int e, const u8 *r
   u32 vws = rp + 1u > (u32)(Lm + e) ? rp + 1u - (u32)Lm - (u32)e : 0u;
   if (rp + (u32)e >= R.len[rid]) vws = R.len[rid] - (u32)e - (u32)Lm;
   const u8 *win = R.seq + R.off[rid] + vws;
+  if (derr != 0) { prefetch_span(win, Lm + 2 * e); prefetch_span(r, Lm); }
   int s0;
   if (s == 0) s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return r[i]; });
   else s0 = banded_traceback(e, derr, Lm, [&](int i) { return __ldg(win + i); }, [&](int i) { return code_char(neg_code(r, Lm, i)); });
@@ -1730,8 +1741,7 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   if (tid == 0) {
     if (nc0 > c.cc || nc1 > c.cc) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW);
     else {
-      rm.n_hits[0] = np; rm.n_hits[1] = nn;
-      rm.n_cand[0] = nc0; rm.n_cand[1] = nc1; rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
+          rm.n_cand[0] = nc0; rm.n_cand[1] = nc1; rm.n_cand_gen[0] = nc0; rm.n_cand_gen[1] = nc1;
     }
   }
 }
@@ -1780,28 +1790,21 @@ __device__ __forceinline__ int banded_align_dropoff(int e, int L, bool from3, Pa
 }
 
 struct SplitResult { int nerr, actual, endp, gap, rml; };  // nerr = -(matched length) or e+1
-// one candidate of the split driver (draft_mapping_generator.cc:410-487): drop-off alignment, retry without the first 20-e bases
-__device__ __forceinline__ SplitResult verify_split_candidate(int e, const u8 *win, const u8 *read, int L, int s) {
+// one candidate of the split driver (draft_mapping_generator.cc:410-487): drop-off alignment, retry without the first 20-e bases.
+// TXT(i): base code of the strand's sequence at i (the read, or its reverse complement for s = 1) — one code path for both strands.
+template <typename TxtF>
+__device__ __forceinline__ SplitResult verify_split_candidate(int e, const u8 *win, TxtF TXT, int L, int s) {
   SplitResult r;
   int endp = L, gap = 0, nerr, rml = 0;
   const int allow_gap = 20 - e;
-  if (s == 0) {
-    nerr = banded_align_dropoff(e, L, false, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return base_code(read[i]); }, &endp, &rml);
-    if (endp < 0 && allow_gap > 0) {
-      const int b_err = nerr, b_end = -endp, b_rml = rml;
-      nerr = banded_align_dropoff(e, L - allow_gap, false, [&](int i) { return base_code(__ldg(win + allow_gap + i)); },
-                                  [&](int i) { return base_code(read[allow_gap + i]); }, &endp, &rml);
-      if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
-      else { gap = allow_gap; endp += gap; rml += gap; }
-    }
-  } else {
-    nerr = banded_align_dropoff(e, L, true, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp, &rml);
-    if (endp < 0 && allow_gap > 0) {
-      const int b_err = nerr, b_end = -endp, b_rml = rml;
-      nerr = banded_align_dropoff(e, L - allow_gap, true, [&](int i) { return base_code(__ldg(win + i)); }, [&](int i) { return neg_code(read, L, i); }, &endp, &rml);
-      if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
-      else { gap = allow_gap; endp += gap; rml += gap; }
-    }
+  const bool from3 = s != 0;
+  nerr = banded_align_dropoff(e, L, from3, [&](int i) { return base_code(__ldg(win + i)); }, TXT, &endp, &rml);
+  if (endp < 0 && allow_gap > 0) {
+    const int b_err = nerr, b_end = -endp, b_rml = rml;
+    const int sh = from3 ? 0 : allow_gap;  // the + strand drops the read's first bases, the - strand aligns from the 3' end anyway
+    nerr = banded_align_dropoff(e, L - allow_gap, from3, [&](int i) { return base_code(__ldg(win + sh + i)); }, [&](int i) { return TXT(sh + i); }, &endp, &rml);
+    if (nerr > e || endp < 0) { nerr = b_err; endp = b_end; rml = b_rml; }
+    else { gap = allow_gap; endp += gap; rml += gap; }
   }
   if (endp + 1 - e - nerr - gap >= 30) { r.actual = nerr; r.nerr = -(endp - e - nerr - gap); }
   else { r.nerr = e + 1; r.actual = e + 1; }
@@ -1824,7 +1827,18 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
   auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
   u64 n_verified = 0;
   int nm[2] = {0, 0};
+  // the read's base codes, forward and reverse-complemented, in this thread's column of shared memory (see verify_kernel)
+  extern __shared__ u8 v_codes[];
+  const int NTB = blockDim.x;
+  u8 *c_fwd = v_codes + threadIdx.x, *c_neg = v_codes + (size_t)c.maxmm * NTB + threadIdx.x;
+  if (rm.n_cand[0] + rm.n_cand[1] > 0)
+    for (int i = 0; i < L; ++i) {
+      const u32 b = base_code(read[i]);
+      c_fwd[(size_t)i * NTB] = (u8)b;
+      c_neg[(size_t)(L - 1 - i) * NTB] = (u8)(b < 4 ? 3u ^ b : 4u);
+    }
   for (int s = 0; s < 2; ++s) {
+    const u8 *txt = s == 0 ? c_fwd : c_neg;
     u64 *cp = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
     u8 *cc = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
     u64 *mp = S.map_pos + ((size_t)sr * 2 + s) * c.mc;
@@ -1839,7 +1853,8 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
       const u32 rid = (u32)(cpos >> 32);
       const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
       if (!valid_cand(e, R.len[rid], pos, (u32)L)) continue;
-      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, read, L, s);
+      prefetch_span(R.seq + R.off[rid] + pos - e, L + 2 * e);
+      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int i) { return (u32)txt[(size_t)i * NTB]; }, L, s);
       ++n_verified;
       if (r.nerr <= e) {
         if (r.nerr < t.min_err) {
@@ -1895,7 +1910,8 @@ __global__ void __launch_bounds__(CTA_NT) verify_split_cta_kernel(DevParams P, D
       const u32 rid = (u32)(cpos >> 32);
       const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
       if (!valid_cand(e, R.len[rid], pos, (u32)L)) { vld[s][i] = 0; continue; }
-      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, read, L, s);
+      const SplitResult r = s == 0 ? verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int q) { return base_code(read[q]); }, L, 0)
+                                   : verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int q) { return neg_code(read, L, q); }, L, 1);
       vld[s][i] = 1;
       res[s][i] = ((u64)(u32)(r.nerr + 1024) << 48) | ((u64)(r.actual & 0xff) << 40) | ((u64)(r.gap & 0xff) << 32) | ((u64)(r.rml & 0xffff) << 16) | (u64)(r.endp & 0xffff);
       ++n_ver;
@@ -2075,11 +2091,12 @@ __global__ void emit_split_kernel(DevParams P, DevRef R, DevBatch B, MapqTables 
   };
   int idx = 0, reported = 0;
   const int DS1[4] = {0, 1, 0, 1}, DS2[4] = {1, 0, 0, 1};
+  // phase 1: which mappings are reported (the enumeration of mapping_generator.h:389-415); phase 2: spans, MAPQ, records — all
+  // threads of a warp enter phase 2 together instead of reaching their tracebacks at different loop iterations
+  int ch_dir[CMX_MAX_BEST], ch_i1[CMX_MAX_BEST], ch_i2[CMX_MAX_BEST];
   for (int dir = 0; dir < 4 && reported != to_report; ++dir) {
     const int s1 = DS1[dir], s2 = DS2[dir];
-    const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
     const short *e1 = S.map_err + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *e2 = S.map_err + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
-    const int *w1 = S.map_split + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *w2 = S.map_split + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
     const int want1 = rm[0].min_err, want2 = rm[1].min_err;
     if (rm[0].n_map[s1] == 0 || rm[1].n_map[s2] == 0) continue;
     for (int i1 = 0; i1 < rm[0].n_map[s1] && reported != to_report; ++i1) {
@@ -2087,30 +2104,36 @@ __global__ void emit_split_kernel(DevParams P, DevRef R, DevBatch B, MapqTables 
       for (int i2 = 0; i2 < rm[1].n_map[s2]; ++i2) {
         if (e2[i2] != want2) continue;
         if (idx == sel[reported]) {
-          u32 st1, en1, st2, en2;
-          span(0, s1, p1[i1], w1[i1], &st1, &en1);
-          span(1, s2, p2[i2], w2[i2], &st2, &en2);
-          const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
-          u8 q1 = mapq_se_split(T, P, rm[0].n_cand[s1], rm[0].min_err, al1, L[0], 2, rm[0]);
-          u8 q2 = mapq_se_split(T, P, rm[1].n_cand[s2], rm[1].min_err, al2, L[1], 2, rm[1]);
-          q1 = (u8)xmul((double)q1, 1.2); if (q1 > 60) q1 = 60;
-          q2 = (u8)xmul((double)q2, 1.2); if (q2 > 60) q2 = 60;
-          const u8 q = q1 < q2 ? q1 : q2;
-          int rid1 = (int)(u32)(p1[i1] >> 32), rid2 = (int)(u32)(p2[i2] >> 32);
-          int pos1 = (int)(s1 == 0 ? st1 : en1), pos2 = (int)(s2 == 0 ? st2 : en2);
-          u8 str1 = s1 == 0 ? 1 : 0, str2 = s2 == 0 ? 1 : 0;
-          const bool smaller = rid1 < rid2 || (rid1 == rid2 && pos1 < pos2);
-          if (!smaller) { int tt = rid1; rid1 = rid2; rid2 = tt; tt = pos1; pos1 = pos2; pos2 = tt; const u8 ts = str1; str1 = str2; str2 = ts; }
-          OutPairs o;
-          o.read_id = B.first_read_id + (u32)pair; o.rid1 = (u32)rid1; o.rid2 = (u32)rid2; o.pos1 = (u32)pos1; o.pos2 = (u32)pos2;
-          o.strand1 = str1; o.strand2 = str2; o.mapq = q; o.is_unique = uniq;
-          out[(size_t)pair * mb + reported] = o;
+          ch_dir[reported] = dir; ch_i1[reported] = i1; ch_i2[reported] = i2;
           ++reported;
           if (reported == to_report) break;
         }
         ++idx;
       }
     }
+  }
+  for (int r = 0; r < reported; ++r) {
+    const int s1 = DS1[ch_dir[r]], s2 = DS2[ch_dir[r]], i1 = ch_i1[r], i2 = ch_i2[r];
+    const u64 *p1 = S.map_pos + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *p2 = S.map_pos + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    const int *w1 = S.map_split + ((size_t)(2 * slot + 0) * 2 + s1) * c.mc, *w2 = S.map_split + ((size_t)(2 * slot + 1) * 2 + s2) * c.mc;
+    u32 st1, en1, st2, en2;
+    span(0, s1, p1[i1], w1[i1], &st1, &en1);
+    span(1, s2, p2[i2], w2[i2], &st2, &en2);
+    const unsigned short al1 = (unsigned short)(en1 - st1 + 1u), al2 = (unsigned short)(en2 - st2 + 1u);
+    u8 q1 = mapq_se_split(T, P, rm[0].n_cand[s1], rm[0].min_err, al1, L[0], 2, rm[0]);
+    u8 q2 = mapq_se_split(T, P, rm[1].n_cand[s2], rm[1].min_err, al2, L[1], 2, rm[1]);
+    q1 = (u8)xmul((double)q1, 1.2); if (q1 > 60) q1 = 60;
+    q2 = (u8)xmul((double)q2, 1.2); if (q2 > 60) q2 = 60;
+    const u8 q = q1 < q2 ? q1 : q2;
+    int rid1 = (int)(u32)(p1[i1] >> 32), rid2 = (int)(u32)(p2[i2] >> 32);
+    int pos1 = (int)(s1 == 0 ? st1 : en1), pos2 = (int)(s2 == 0 ? st2 : en2);
+    u8 str1 = s1 == 0 ? 1 : 0, str2 = s2 == 0 ? 1 : 0;
+    const bool smaller = rid1 < rid2 || (rid1 == rid2 && pos1 < pos2);
+    if (!smaller) { int tt = rid1; rid1 = rid2; rid2 = tt; tt = pos1; pos1 = pos2; pos2 = tt; const u8 ts = str1; str1 = str2; str2 = ts; }
+    OutPairs o;
+    o.read_id = B.first_read_id + (u32)pair; o.rid1 = (u32)rid1; o.rid2 = (u32)rid2; o.pos1 = (u32)pos1; o.pos2 = (u32)pos2;
+    o.strand1 = str1; o.strand2 = str2; o.mapq = q; o.is_unique = uniq;
+    out[(size_t)pair * mb + r] = o;
   }
   out_n[pair] = reported;
   pm.n_rec = reported;

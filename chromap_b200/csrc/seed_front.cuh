@@ -56,7 +56,7 @@ __host__ __device__ inline size_t seed_front_smem_bytes(int maxmm) { return 4 * 
 // FAST: k = 17, w = 7 (every preset): the packed-key scan only; otherwise the run-time scan only — one kernel per case keeps
 // the other's registers and code out of the way.
 template <bool FAST>
-__global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int prepped, int slot_begin,
+__global__ void __launch_bounds__(SF_NT, 5) seed_front_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int prepped, int slot_begin,
                                                            int slot_end) {
   extern __shared__ __align__(16) u8 sf_smem[];
   __shared__ FrontShared fs;
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIn
   const int maxmm = S.caps.maxmm;
   const size_t tb = seed_front_tile_bytes(maxmm);
   u64 *kbuf = (u64 *)(sf_smem + 4 * tb);
-  u64 *rbuf = kbuf + SF_KEY_ROWS * SF_NT;
+  u64 *rbuf = kbuf + SF_KEY_ROWS * SF_NT;  // (the shared-memory window variant of the scan)
+  (void)rbuf;
   const int n_tiles = (slot_end - slot_begin + SF_TILE - 1) / SF_TILE;
   if (tid == 0) { mbar_init(&fs.bar[0], 1); mbar_init(&fs.bar[1], 1); mbar_fence_init(); }
   if (tid < 3) fs.acc[tid] = 0;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(SF_NT, 6) seed_front_kernel(DevParams P, DevIn
         else if (n_mm < maxmm) { mmv[(size_t)n_mm * 32] = h; mmp[(size_t)n_mm * 32] = p; }
         ++n_mm;
       };
-      if constexpr (FAST) minimizer_scan_packed<17, 7>([&](int i) { return rd[i]; }, len, emit, StridedU64{rbuf + tid, SF_NT});  // window in shared memory
+      if constexpr (FAST) minimizer_scan_packed<17, 7>([&](int i) { return rd[i]; }, len, emit);  // window in registers
       else minimizer_scan<0, 0>([&](int i) { return rd[i]; }, len, P.k, P.w, emit);
       if (n_mm > maxmm) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[1], 1ull); }
       else {
