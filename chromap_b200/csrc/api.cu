@@ -248,7 +248,6 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   if ((size_t)2 * mrl * 64 > 48 * 1024) {  // per-thread read-code columns of the verification kernels (long reads)
     if ((size_t)2 * mrl * 64 > 200 * 1024) { cmx_destroy(ctx); return CMX_ERR_INVALID; }
     CUC(cudaFuncSetAttribute(verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mrl * 64));
-    CUC(cudaFuncSetAttribute(verify_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mrl * 64));
   }
   {
     const size_t sf_smem = seed_front_smem_bytes(mrl);
@@ -735,7 +734,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       pair_candidates_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, ix, S, L.ctr, 0, (int *)L.rescue_list.p, L.d_count + 1);
       pair_candidates_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(P, ix, S, L.ctr, 1, (int *)L.rescue_list.p, L.d_count + 1);
       CUL(cudaEventRecord(e2, st));
-      if (P.split) verify_split_kernel<<<(2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, st>>>(P, R, B, S, L.ctr);
+      if (P.split) verify_split_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr);
       else {
         verify_kernel<<<(2 * n_slots + TB - 1) / TB, TB, 0, st>>>(P, R, B, S, L.ctr, 0, (int *)L.verify_list.p, L.d_count + 2);
         verify_kernel<<<(2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, st>>>(P, R, B, S, L.ctr, 1, (int *)L.verify_list.p, L.d_count + 2);
@@ -747,7 +746,7 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
     } else {  // overflow tiers: one CTA per read / pair; shared-memory sort buffers sized to the tier
       auto cap_of = [](int n) { int c = 1; while (c < n) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
       const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
-      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, L.ctr, c_seed);
+      seed_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, st>>>(P, ix, B, S, L.tiers[0].view, L.ctr, c_seed);
       CUL(cudaEventRecord(e1, st));
       {
         const int lcap = std::min(tier.caps.cc, 512), fcap = 2 * tier.caps.cc;

@@ -204,16 +204,6 @@ struct RescueShared {
   int i[8];
   int warp[4];
 };
-__device__ __forceinline__ int rescue_replay(int l, int n, int lb, int ue) {  // index.cc:443-459 on (LB, E): the last probe
-  int mid = 0, r = n - 1;
-  while (l <= r) {
-    mid = (l + r) / 2;
-    if (mid < lb) l = mid + 1;
-    else if (mid >= ue) r = mid - 1;
-    else break;
-  }
-  return mid;
-}
 // mmv / mmp: this read's minimizer records (shared memory).  mate_pos / mate_cnt: the mate's candidates on the strand
 // that guides the search.  Returns +max count or -max count (bail-out, index.cc:371-380) on every thread; *nh_out =
 // number of hits appended to `hits` (global, sorted here when they fit `cap`).
@@ -267,7 +257,7 @@ __device__ inline int cta_rescue(const DevParams &P, const DevIndex &ix, int str
       int lb = 0, eq = 0, ub = 0;
       if (live) {
         const u64 lo = R.win_lo[b], hi = R.win_hi[b];
-        int a = 0, z = n;
+        int a = 0, z = n;  // (two-way here: with a warp's 32 searches in flight the four-way variant's extra loads cost more than its shorter chain saves)
         while (a < z) { const int m = (a + z) >> 1; if ((__ldg(&O[m]) >> 1) < lo) a = m + 1; else z = m; }
         lb = a;
         eq = (lb < n && (__ldg(&O[lb]) >> 1) == lo) ? 1 : 0;  // distinct positions (checked when the index is installed): E <= 1

@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
       const int v = v0 + tid;
       int err = e + 1, endp = 0, idx = 0;
       u64 cpos = 0;
+      if (v + CTA_NT < nv) {  // the window this thread aligns in the next step: request its lines now (a cold window is a DRAM round trip)
+        const u64 nx = cp[s][vlist[v + CTA_NT]];
+        const u32 npos = s == 0 ? (u32)nx : (u32)nx - (u32)L + 1u;
+        prefetch_span(R.seq + R.off[(u32)(nx >> 32)] + npos - e, L + 2 * e);
+      }
       if (v < nv) {
         idx = vlist[v];
         if (idx < stop || v < free_until) {

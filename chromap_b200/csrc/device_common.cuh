@@ -30,7 +30,7 @@ struct ReadMeta {  // 64 bytes = two 32-byte sectors: what seeding / candidate p
   int n_cand[2];
   int n_cand_gen[2];
   u32 rep_len;
-  int pad0;
+  int mm_done;  // 1: the front end left this read's probed minimizer records in the tier's scratch
   int n_map[2];
   int min_err, second_min_err, n_best, n_second_best;
   int n_aug[2];
@@ -137,6 +137,37 @@ __device__ __forceinline__ int index_lookup(const DevIndex &ix, u64 mm_hash, u64
 __device__ __forceinline__ void prefetch_span(const void *p, int bytes) {
   const char *a = (const char *)((unsigned long long)p & ~127ull), *z = (const char *)p + bytes;
   for (; a < z; a += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+}
+
+// First index in the sorted occurrence list O[0..n) whose position (entry >> 1) is >= lo.  Four-way instead of two-way: a
+// search over a list of 10^5 occurrences is a chain of dependent loads, and three independent loads per step halve the chain
+// (8 round trips instead of 17); the last <= 8 entries are fetched together.  Same result as a binary lower bound.
+__device__ __forceinline__ int occ_lower_bound(const u64 *O, int n, u64 lo) {
+  int a = 0, z = n;
+  while (z - a > 8) {
+    const int q = (z - a) >> 2, m1 = a + q, m2 = m1 + q, m3 = m2 + q;
+    const u64 v1 = __ldg(&O[m1]) >> 1, v2 = __ldg(&O[m2]) >> 1, v3 = __ldg(&O[m3]) >> 1;
+    if (v3 < lo) a = m3 + 1;
+    else if (v2 < lo) { a = m2 + 1; z = m3; }
+    else if (v1 < lo) { a = m1 + 1; z = m2; }
+    else z = m1;
+  }
+  int below = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) below += (a + i < z && (__ldg(&O[a + i]) >> 1) < lo) ? 1 : 0;
+  return a + below;
+}
+// index.cc:443-459 replayed on (LB, E): the reference's binary search that starts at l, with every comparison against the list
+// replaced by the probe's position relative to LB and LB + E.  Returns the last probe (where the reference starts emitting).
+__device__ __forceinline__ int rescue_replay(int l, int n, int lb, int ue) {
+  int mid = 0, r = n - 1;
+  while (l <= r) {
+    mid = (l + r) / 2;
+    if (mid < lb) l = mid + 1;
+    else if (mid >= ue) r = mid - 1;
+    else break;
+  }
+  return mid;
 }
 
 // index.cc:491-505 (u32 wrap kept)

@@ -272,14 +272,12 @@ __device__ inline int rescue_hits(const DevParams &P, const DevIndex &ix, int st
         hi = mate_pos[cj] + range;
         ci = cj + 1;
       }
-      int l = prev_l, mid = 0, r = (int)n - 1;
-      while (l <= r) {
-        mid = (l + r) / 2;
-        const u64 p = __ldg(&ix.occ[off + mid]) >> 1;
-        if (p < lo) l = mid + 1;
-        else if (p > lo) r = mid - 1;
-        else break;
-      }
+      // the reference's search (index.cc:443-459) starts at the previous window's last probe and ends on a probe that depends on
+      // its path; only the comparisons touch memory, and they only depend on where a probe lies relative to LB and LB + E: find
+      // LB with the four-way search, then replay the path arithmetically (E <= 1: distinct positions, checked at index upload)
+      const int lbq = occ_lower_bound(ix.occ + off, (int)n, lo);
+      const int eqq = (lbq < (int)n && (__ldg(&ix.occ[off + lbq]) >> 1) == lo) ? 1 : 0;
+      const int mid = rescue_replay(prev_l, (int)n, lbq, lbq + eqq);
       prev_l = mid;
       for (u32 oi = (u32)mid; oi < n; ++oi) {
         const u64 rh = __ldg(&ix.occ[off + oi]);
@@ -1636,7 +1634,9 @@ __device__ inline int cta_cluster_par(int e, int need, u32 n_mm, const u64 *hits
   return total;
 }
 
-__global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
+// S0: tier 0's scratch.  A pair that reaches an overflow tier because of its hit / candidate / mapping counts has already been
+// through the front end there: its probed minimizer records are copied instead of being computed and probed again (mm_done flag).
+__global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex ix, DevBatch B, Scratch S, Scratch S0, Counters *ctr, int sm_cap) {
   extern __shared__ u64 sm[];  // [sm_cap] sort buffer, then per-minimizer arrays sized by the tier's maxmm
   int *s_off = (int *)(sm + sm_cap);
   u32 *s_c1 = (u32 *)(s_off + S.caps.maxmm + 1), *s_c2 = s_c1 + S.caps.maxmm;
@@ -1654,7 +1654,11 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   u64 *mmh = S.mm_hash + (size_t)sr * c.maxmm;
   u64 *mmv = S.mm_val + (size_t)sr * c.maxmm;
   u32 *mmp = S.mm_pos + (size_t)sr * c.maxmm;
-  {
+  const ReadMeta &r0 = S0.rmeta[2 * pair + mate];
+  const bool reuse = r0.mm_done == 1 && r0.n_mm <= c.maxmm && r0.len == rm.len;  // uniform: global values
+  if (reuse) {
+    if (tid == 0) { rm.n_mm = r0.n_mm; s_i[0] = r0.n_mm; s_steps = 0; s_i[5] = 0; }
+  } else {
     const int n0 = cta_minimizers(read_ptr(B, pair, mate), rm.len, P.k, P.w, mmh, mmp, c.maxmm, sm, &s_i[6]);
     if (tid == 0) {
       rm.n_mm = n0;
@@ -1667,18 +1671,27 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
   const int n_mm = s_i[0];
   if (n_mm > c.maxmm) { if (tid == 0) atomicExch(&S.pmeta[slot].status, ST_OVERFLOW); return; }
   if (n_mm == 0) return;
+  const size_t b0 = mm_base(S0, pair, mate);
+  const int ms0 = mm_stride(S0);
   for (int i = tid; i < n_mm; i += CTA_NT) {
     u64 val = 0;
-    int steps;
-    const int kind = index_lookup(ix, mmh[i], &val, &steps);
-    mmv[i] = val;
-    mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
+    int steps = 0, kind;
+    if (reuse) {
+      val = S0.mm_val[b0 + (size_t)i * ms0];
+      const u32 pw = S0.mm_pos[b0 + (size_t)i * ms0];
+      kind = (int)(pw >> 30);
+      mmv[i] = val; mmp[i] = pw;
+    } else {
+      kind = index_lookup(ix, mmh[i], &val, &steps);
+      mmv[i] = val;
+      mmp[i] = (mmp[i] & 0x3FFFFFFFu) | ((u32)kind << 30);
+      atomicAdd(&s_steps, (unsigned long long)steps);
+      if (kind) atomicAdd(&s_i[5], 1);
+    }
     u32 c1 = 0, c2 = 0;
     if (kind == 1) { c1 = c2 = 1; }
     else if (kind == 2) { const u32 n = (u32)val; if (n < (u32)P.f0) c1 = n; if (n < (u32)P.f1) c2 = n; }
     s_c1[i] = c1; s_c2[i] = c2;
-    atomicAdd(&s_steps, (unsigned long long)steps);
-    if (kind) atomicAdd(&s_i[5], 1);
   }
   __syncthreads();
   if (tid == 0) {
@@ -1697,9 +1710,11 @@ __global__ void __launch_bounds__(CTA_NT) seed_cta_kernel(DevParams P, DevIndex 
     s_i[1] = round2;
     s_i[2] = st.count;
     rm.rep_len = st.len;
-    atomicAdd(&ctr->n_minimizers, (u64)n_mm);
-    atomicAdd(&ctr->n_probe_steps, (u64)s_steps);
-    atomicAdd(&ctr->n_found, (u64)s_i[5]);
+    if (!reuse) {  // (a reused read was counted by the front end)
+      atomicAdd(&ctr->n_minimizers, (u64)n_mm);
+      atomicAdd(&ctr->n_probe_steps, (u64)s_steps);
+      atomicAdd(&ctr->n_found, (u64)s_i[5]);
+    }
   }
   __syncthreads();
   const int T = s_off[n_mm];
@@ -1827,18 +1842,8 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
   auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
   u64 n_verified = 0;
   int nm[2] = {0, 0};
-  // the read's base codes, forward and reverse-complemented, in this thread's column of shared memory (see verify_kernel)
-  extern __shared__ u8 v_codes[];
-  const int NTB = blockDim.x;
-  u8 *c_fwd = v_codes + threadIdx.x, *c_neg = v_codes + (size_t)c.maxmm * NTB + threadIdx.x;
-  if (rm.n_cand[0] + rm.n_cand[1] > 0)
-    for (int i = 0; i < L; ++i) {
-      const u32 b = base_code(read[i]);
-      c_fwd[(size_t)i * NTB] = (u8)b;
-      c_neg[(size_t)(L - 1 - i) * NTB] = (u8)(b < 4 ? 3u ^ b : 4u);
-    }
+  prefetch_span(read, L);
   for (int s = 0; s < 2; ++s) {
-    const u8 *txt = s == 0 ? c_fwd : c_neg;
     u64 *cp = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
     u8 *cc = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
     u64 *mp = S.map_pos + ((size_t)sr * 2 + s) * c.mc;
@@ -1854,7 +1859,11 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
       const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
       if (!valid_cand(e, R.len[rid], pos, (u32)L)) continue;
       prefetch_span(R.seq + R.off[rid] + pos - e, L + 2 * e);
-      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int i) { return (u32)txt[(size_t)i * NTB]; }, L, s);
+      // one code path for both strands (a warp does not split by strand): base i of the strand's sequence, decoded on the fly
+      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int i) -> u32 {
+        const u32 b = base_code(read[s ? L - 1 - i : i]);
+        return s ? (b < 4 ? 3u ^ b : 4u) : b;
+      }, L, s);
       ++n_verified;
       if (r.nerr <= e) {
         if (r.nerr < t.min_err) {

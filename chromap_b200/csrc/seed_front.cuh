@@ -207,13 +207,15 @@ __global__ void __launch_bounds__(SF_NT, 5) seed_front_kernel(DevParams P, DevIn
         n_mine += (u32)n_mm;
       }
     }
+    const int mm_done = (live && status == ST_OK && n_mm <= maxmm) ? 1 : 0;
     if (slot < slot_end && !prepped) {
       ReadMeta z;
       memset(&z, 0, sizeof(z));
-      z.len = len; z.n_mm = n_mm;
+      z.len = len; z.n_mm = n_mm; z.mm_done = mm_done;
       S.rmeta[2 * slot + mate] = z;
     } else if (live && status == ST_OK) {
       S.rmeta[2 * slot + mate].n_mm = n_mm;
+      S.rmeta[2 * slot + mate].mm_done = mm_done;
     }
     __syncthreads();  // everyone is done with this stage before it is refilled
   }

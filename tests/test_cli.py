@@ -177,3 +177,18 @@ def test_cli_sam(tmp_path, golden_dir):
         r = subprocess.run([cli, "--SAM", "-x", idx, "-r", os.path.join(d, "ref.fa.gz"), "-o", out] + extra + reads, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == gzip.open(os.path.join(d, want)).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,args,paired", [("pe_chip", ["--preset", "chip"], True), ("pe_q0d", ["-q", "0", "--remove-pcr-duplicates", "--Tn5-shift"], True),
+                                              ("se_q0d", ["-q", "0", "--remove-pcr-duplicates", "--Tn5-shift"], False)])
+def test_cli_paf_equals_reference_binary_output(case, args, paired, tmp_path, golden_dir):
+    """--PAF through the GPU path end to end (records from the device, text by cmx_format_paf) == the reference binary's PAF."""
+    cli = _ensure_cli()
+    d = os.path.join(golden_dir, "synth_small")
+    idx = str(tmp_path / "ref.index")
+    subprocess.check_call([cli, "-i", "-r", os.path.join(d, "ref.fa.gz"), "-o", idx], stderr=subprocess.DEVNULL)
+    out = str(tmp_path / "out.paf")
+    reads = ["-1", os.path.join(d, "read1.fq.gz")] + (["-2", os.path.join(d, "read2.fq.gz")] if paired else [])
+    subprocess.check_call([cli] + args + ["--PAF", "-x", idx, "-r", os.path.join(d, "ref.fa.gz")] + reads + ["-o", out], stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == gzip.open(os.path.join(d, case + ".paf.gz")).read()
