@@ -450,6 +450,35 @@ def run_ours(a):
                         "pack_ms": round(pk, 3), "allgather_ms": round(ag, 3), "sort_resolve_ms": round(rs, 3), "call_ms": round(wl_, 3),
                         "allgather_GBps_per_rank": round(xst["bytes_received"] / (ag * 1e-3) / 1e9, 1) if ag > 0 else None,
                         "timing": "CUDA events on the exchange stream, max over ranks"}
+            # the same step as a range shuffle (cmx_dedup_shuffle): every record travels once to the rank that owns its key
+            # range, which runs the single-GPU post-processing on it
+            try:
+                cap = 2 * n_loc + 4096
+                part = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
+                barrier()
+                n_part, sst = m.dedup_shuffle(mine, n=n_loc, on_device=True, out=part, capacity=cap)   # warm-up
+                barrier()
+                t0 = time.perf_counter()
+                n_part, sst = m.dedup_shuffle(mine, n=n_loc, on_device=True, out=part, capacity=cap)
+                torch.cuda.synchronize()
+                wall = time.perf_counter() - t0
+                vals = torch.tensor([sst["partition_ms"], sst["shuffle_ms"], sst["postprocess_ms"], wall * 1e3, float(sst["n_received"])], device=dev,
+                                    dtype=torch.float64)
+                tot = torch.tensor([float(n_part)], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                pt, sh, pp, wl2, nr_max = (float(x) for x in vals.tolist())
+                exchange["shuffle"] = {"what": "cmx_dedup_shuffle over the same records: sample-sort partition -> grouped ncclSend/ncclRecv -> sort + "
+                                               "duplicate rule on the owner of each key range",
+                                       "records_out_global": int(tot.item()), "records_received_max_over_ranks": int(nr_max),
+                                       "balance_max_over_mean": round(nr_max * world / max(1, int(sst["n_global"])), 3),
+                                       "record_bytes_sent_this_rank": int(sst["bytes_sent"]), "record_bytes_received_this_rank": int(sst["bytes_received"]),
+                                       "partition_ms": round(pt, 3), "shuffle_ms": round(sh, 3), "postprocess_ms": round(pp, 3), "call_ms": round(wl2, 3),
+                                       "shuffle_GBps_per_rank": round(sst["bytes_received"] / (sh * 1e-3) / 1e9, 1) if sh > 0 and sst["bytes_received"] else None}
+                del part
+            except Exception as ex:
+                exchange["shuffle"] = {"unavailable": repr(ex)[:200]}
             m.comm_destroy()
             del keep, mine, surv
         except Exception as ex:  # NCCL missing on the box: report, do not hide

@@ -122,6 +122,14 @@ class ExchangeStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "pad"}
 
 
+class ShuffleStats(C.Structure):
+    _fields_ = [("partition_ms", C.c_float), ("shuffle_ms", C.c_float), ("postprocess_ms", C.c_float), ("n_ranks", C.c_uint32),
+                ("bytes_sent", C.c_uint64), ("bytes_received", C.c_uint64), ("n_received", C.c_uint64), ("n_global", C.c_uint64)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 PE_RECORD = np.dtype([("read_id", "<u4"), ("rid", "<u4"), ("fragment_start", "<u4"), ("fragment_length", "<u2"),
                       ("mapq", "u1"), ("direction", "u1"), ("is_unique", "u1"), ("num_dups", "u1"),
                       ("positive_alignment_length", "<u2"), ("negative_alignment_length", "<u2")], align=True)
@@ -192,6 +200,7 @@ def load_library():
     L.cmx_comm_init.argtypes = [vp, i32, i32, vp]
     L.cmx_comm_destroy.argtypes = [vp]
     L.cmx_dedup_exchange.argtypes = [vp, vp, vp, u64, i32, vp, vp, C.POINTER(u64), C.POINTER(ExchangeStats)]
+    L.cmx_dedup_shuffle.argtypes = [vp, vp, vp, u64, i32, vp, vp, u64, C.POINTER(u64), C.POINTER(ShuffleStats)]
     L.cmx_exchange_finish.argtypes = [C.POINTER(Params), vp, vp, u64]
     L.cmx_fastq_cut.restype = u64; L.cmx_fastq_cut.argtypes = [vp, u64, u32, C.POINTER(u32)]
     L.cmx_ingest_fastq.argtypes = [vp, i32, vp, u64, i32, vp, C.POINTER(Ingested)]
@@ -388,6 +397,36 @@ class Mapper:
         st = ExchangeStats()
         self._check(self.L.cmx_dedup_exchange(self.h, recs.ctypes.data if len(recs) else o.ctypes.data, _ptr(bcs), len(recs), 0, o.ctypes.data, _ptr(obc),
                                               C.byref(no), C.byref(st)), "cmx_dedup_exchange")
+        k = int(no.value)
+        if bcs is not None:
+            return o[:k].copy(), obc[:k].copy(), st.asdict()
+        return o[:k].copy(), st.asdict()
+
+    def dedup_shuffle(self, recs, barcode_keys=None, on_device=False, out=None, out_bc=None, n=None, capacity=None):
+        """This rank's records in; out: the records of this rank's KEY RANGE after duplicate removal over the whole run
+        (reference order, num_dups set, MAPQ-filtered, Tn5 applied).  Ranks' outputs concatenated in rank order = the run's output."""
+        if on_device:
+            no = C.c_uint64()
+            st = ShuffleStats()
+            self._check(self.L.cmx_dedup_shuffle(self.h, _ptr(recs), _ptr(barcode_keys), int(n), 1, _ptr(out), _ptr(out_bc), int(capacity), C.byref(no),
+                                                 C.byref(st)), "cmx_dedup_shuffle")
+            return int(no.value), st.asdict()
+        recs = np.ascontiguousarray(recs)
+        bcs = np.ascontiguousarray(barcode_keys, dtype=np.uint64) if barcode_keys is not None else None
+        cap = int(capacity) if capacity is not None else 2 * len(recs) + 4096
+        while True:
+            o = np.zeros(max(1, cap), dtype=PE_RECORD)
+            obc = np.zeros(max(1, cap), dtype=np.uint64) if bcs is not None else None
+            no = C.c_uint64()
+            st = ShuffleStats()
+            rc = self.L.cmx_dedup_shuffle(self.h, recs.ctypes.data if len(recs) else o.ctypes.data, _ptr(bcs), len(recs), 0, o.ctypes.data, _ptr(obc), cap,
+                                          C.byref(no), C.byref(st))
+            if rc != 0 and int(no.value) > cap:
+                # the key range of this rank holds more than the guess.  The shuffle is collective: every rank must repeat it,
+                # so the caller is told instead of retrying here on one rank only.
+                raise CmxError("cmx_dedup_shuffle: capacity %d too small, %d needed" % (cap, int(no.value)))
+            self._check(rc, "cmx_dedup_shuffle")
+            break
         k = int(no.value)
         if bcs is not None:
             return o[:k].copy(), obc[:k].copy(), st.asdict()

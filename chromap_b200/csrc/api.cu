@@ -118,6 +118,10 @@ struct cmx_ctx {
   int n_lanes = CMX_MAX_LANES;  // lanes a multi-batch call is cut into (cmx_set_lanes; CMX_LANES overrides the default)
   int last_lanes_used = 0;
   cudaStream_t stream = nullptr, up_stream = nullptr, down_stream = nullptr;
+  // page-locked staging of h2d_big (allocated at the first big upload, kept: page-locking costs more than the copy)
+  char *stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  cudaStream_t stage_stream = nullptr;
   std::vector<cudaEvent_t> ev_up;
   cudaEvent_t ev_bc = nullptr;
   cudaEvent_t ev[4] = {};
@@ -301,8 +305,56 @@ void cmx_destroy(cmx_ctx *ctx) {
   for (auto &e : ctx->ev_up) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->stage[0]) cudaFreeHost(ctx->stage[0]);
+  if (ctx->stage[1]) cudaFreeHost(ctx->stage[1]);
+  for (auto &e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+  if (ctx->stage_stream) cudaStreamDestroy(ctx->stage_stream);
   if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
   delete ctx;
+}
+
+// Pageable or file-mapped host memory -> device faster than one thread can copy it into the driver's staging area: eight
+// threads fill one of two page-locked 32 MB buffers while cudaMemcpyAsync drains the other (a 3 Gbp index is 18 GB of
+// arrays that the CLI hands over where they lie in the page cache).  Pinned or device sources go straight through.
+static const size_t STAGE_BYTES = 32u << 20;
+static cudaError_t h2d_big(cmx_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  cudaPointerAttributes at;
+  const bool plain = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  if (!plain || bytes < STAGE_BYTES / 2) return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+  if (!ctx->stage_stream) {
+    if (cudaMallocHost(&ctx->stage[0], STAGE_BYTES) != cudaSuccess || cudaMallocHost(&ctx->stage[1], STAGE_BYTES) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stage_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->stage_stream = nullptr;
+      return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    }
+  }
+  cudaStream_t st = ctx->stage_stream;
+  cudaError_t rc = cudaSuccess;
+  size_t i = 0;
+  for (size_t o = 0; o < bytes && rc == cudaSuccess; o += STAGE_BYTES, ++i) {
+    const int b = (int)(i & 1);
+    const size_t n = std::min(STAGE_BYTES, bytes - o);
+    if (i >= 2) rc = cudaEventSynchronize(ctx->stage_ev[b]);
+    if (rc != cudaSuccess) break;
+    const int nt = 8;
+    const size_t slice = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+    char *stage = ctx->stage[b];
+    std::thread th[8];
+    for (int t = 0; t < nt; ++t)
+      th[t] = std::thread([=]() {
+        const size_t a = std::min(n, (size_t)t * slice), z = std::min(n, a + slice);
+        if (z > a) memcpy(stage + a, (const char *)src + o + a, z - a);
+      });
+    for (int t = 0; t < nt; ++t) th[t].join();
+    rc = cudaMemcpyAsync((char *)dst + o, stage, n, cudaMemcpyHostToDevice, st);
+    if (rc == cudaSuccess) rc = cudaEventRecord(ctx->stage_ev[b], st);
+  }
+  const cudaError_t rs = cudaStreamSynchronize(st);
+  return rc == cudaSuccess ? rs : rc;
 }
 
 int cmx_upload_reference(cmx_ctx *ctx, uint32_t n_seq, const uint64_t *offsets, const char *concat) {
@@ -324,8 +376,9 @@ int cmx_upload_reference(cmx_ctx *ctx, uint32_t n_seq, const uint64_t *offsets, 
   ctx->ref_bytes = cur + PAD;
   CU(cudaMalloc(&ctx->ref_seq, ctx->ref_bytes));
   CU(cudaMemset(ctx->ref_seq, 0, ctx->ref_bytes));
+  CU(cudaDeviceSynchronize());  // (the staged copies below run on their own stream)
   for (u32 i = 0; i < n_seq; ++i)
-    CU(cudaMemcpy(ctx->ref_seq + doff[i], concat + offsets[i], dlen[i], cudaMemcpyDefault));  // host or device source
+    CU(h2d_big(ctx, ctx->ref_seq + doff[i], concat + offsets[i], dlen[i]));  // host or device source
   CU(cudaMalloc(&ctx->ref_off, n_seq * sizeof(u64)));
   CU(cudaMalloc(&ctx->ref_len, n_seq * sizeof(u32)));
   CU(cudaMemcpy(ctx->ref_off, doff.data(), n_seq * sizeof(u64), cudaMemcpyHostToDevice));
@@ -377,7 +430,7 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   unsigned long long *d_cnt = nullptr;
   u64 *d_k = nullptr, *d_v = nullptr;
   CU(cudaMalloc(&d_flags, nfw * 4)); CU(cudaMalloc(&d_cnt, 8));
-  CU(cudaMemcpy(d_flags, flags, nfw * 4, cudaMemcpyHostToDevice));
+  CU(h2d_big(ctx, d_flags, flags, nfw * 4));
   CU(cudaMemset(d_cnt, 0, 8));
   khash_count_kernel<<<(unsigned)((nfw + 255) / 256), 256>>>(d_flags, nbk, d_cnt);
   unsigned long long n_keys = 0;
@@ -389,8 +442,9 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   CU(cudaMalloc(&d_k, std::min<size_t>(nbk, CH) * 8 + 16)); CU(cudaMalloc(&d_v, std::min<size_t>(nbk, CH) * 8 + 16));
   for (u64 b0 = 0; b0 < nbk; b0 += CH) {
     const u64 n = std::min<u64>(CH, nbk - b0);
-    CU(cudaMemcpy(d_k, keys + b0, n * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_v, vals + b0, n * 8, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(0));  // the previous chunk's insert kernel is done with d_k / d_v (the staged copies run on their own stream)
+    CU(h2d_big(ctx, d_k, keys + b0, n * 8));
+    CU(h2d_big(ctx, d_v, vals + b0, n * 8));
     khash_insert_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_flags, d_k, d_v, b0, n, ctx->slots, ctx->n_slots - 1, table_shift(ctx->n_slots));
     CU(cudaGetLastError());
   }
@@ -398,7 +452,7 @@ int cmx_upload_index(cmx_ctx *ctx, int k, int w, uint32_t n_buckets, const uint3
   cudaFree(d_flags); cudaFree(d_cnt); cudaFree(d_k); cudaFree(d_v);
   cudaFree(ctx->occ); ctx->occ = nullptr;
   CU(cudaMalloc(&ctx->occ, (size_t)std::max<u32>(n_occ, 1) * sizeof(u64)));
-  if (n_occ) CU(cudaMemcpy(ctx->occ, occ, (size_t)n_occ * sizeof(u64), cudaMemcpyHostToDevice));
+  if (n_occ) CU(h2d_big(ctx, ctx->occ, occ, (size_t)n_occ * sizeof(u64)));
   ctx->n_occ = n_occ; ctx->k = k; ctx->w = w;
   return check_occurrences(ctx);
 }
@@ -750,11 +804,15 @@ static int run_lane(cmx_ctx *ctx, Lane &L, const DevBatch &Bfull, LaneJob &J) {
       CUL(cudaEventRecord(e1, st));
       {
         const int lcap = std::min(tier.caps.cc, 512), fcap = 2 * tier.caps.cc;
-        pair_candidates_cta_kernel<<<n_slots, CTA_NT, pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap), st>>>(P, ix, S, L.ctr, c_pc, lcap, fcap, nullptr, nullptr);
+        // the last tier's shared-memory lists leave room for two CTAs per SM only: sixteen warps each instead of four keep as
+        // many dependent occurrence-list searches in flight as the smaller tiers do
+        const size_t pc_smem = pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap);
+        const int pc_nt = pc_smem > 64 * 1024 ? PC_CTA_NT_MAX : CTA_NT;
+        pair_candidates_cta_kernel<<<n_slots, pc_nt, pc_smem, st>>>(P, ix, S, L.ctr, c_pc, lcap, fcap, nullptr, nullptr);
       }
       CUL(cudaEventRecord(e2, st));
       if (P.split) verify_split_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9, st>>>(P, R, B, S, L.ctr, c_ver);
-      else verify_cta_kernel<<<2 * n_slots, CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, st>>>(P, R, B, S, L.ctr, c_ver);
+      else verify_cta_kernel<<<2 * n_slots, tier.caps.cc > 1024 ? VERIFY_NT_MAX : CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, st>>>(P, R, B, S, L.ctr, c_ver);
       CUL(cudaEventRecord(e3, st));
       if (P.split) pairing_split_kernel<<<(n_slots + TB - 1) / TB, TB, 0, st>>>(P, S, (int *)L.nbest.p);
       else pairing_cta_kernel<<<n_slots, CTA_NT, (size_t)c_pair * 10, st>>>(P, S, (int *)L.nbest.p, c_pair);
@@ -1414,9 +1472,71 @@ int64_t cmx_format_bed_bc(const char *const *names, const cmx_pe_record *recs, c
   return len;
 }
 
-// Sort + duplicate removal + MAPQ filter (+ Tn5 shift) on the device, in place on host buffers: same results as
-// cmx_postprocess / cmx_postprocess_bc / cmx_postprocess_pairs (postprocess.cuh).  The record kind follows the
-// context: pairs when output_format == 5, barcoded BED when barcode_keys != NULL, else bulk BED.
+// Sort + duplicate removal + MAPQ filter (+ Tn5 shift) over device-resident records: d_a[0, n) (and d_bca) in, the result in
+// d_b[0, *nsel) (and d_bcb); d_a is used as scratch.  All four buffers hold n entries.  Work is queued on ctx->stream and
+// waited for.
+static int pp_device(cmx_ctx *ctx, const PpParams &P, PpRecord *d_a, u64 *d_bca, u64 n, PpRecord *d_b, u64 *d_bcb, u64 *nsel_out) {
+  *nsel_out = 0;
+  if (n == 0) return CMX_OK;
+  if (n > 0x7FFFFFFFull) return fail(ctx, CMX_ERR_INVALID, "post-processing: more than 2^31-1 records in one call");
+  const bool bc = P.kind == PP_BED_BC;
+  cudaStream_t st = ctx->stream;
+  u64 *d_k0 = nullptr, *d_k1 = nullptr, *d_nsel = nullptr;
+  u32 *d_i0 = nullptr, *d_i1 = nullptr;
+  u8 *d_head = nullptr, *d_keep = nullptr;
+  void *d_tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_nsel); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_head); cudaFree(d_keep); cudaFree(d_tmp); };
+#define PPCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+  PPCU(cudaMalloc(&d_k0, n * 8)); PPCU(cudaMalloc(&d_k1, n * 8)); PPCU(cudaMalloc(&d_i0, n * 4)); PPCU(cudaMalloc(&d_i1, n * 4));
+  PPCU(cudaMalloc(&d_head, n)); PPCU(cudaMalloc(&d_keep, n)); PPCU(cudaMalloc(&d_nsel, 16));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, d_a, n);  // chromap.h:1322-1355: before the sort
+  pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n);
+  cub::DoubleBuffer<u64> dk(d_k0, d_k1);
+  cub::DoubleBuffer<u32> di(d_i0, d_i1);
+  size_t tmp_bytes = 0, need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, (int)n, 0, 64, st);
+  cub::DeviceSelect::Flagged(nullptr, need, d_a, d_keep, d_b, d_nsel, (int)n, st);
+  tmp_bytes = std::max(tmp_bytes, need);
+  cub::DeviceSelect::Flagged(nullptr, need, d_bca, d_keep, d_bcb, d_nsel, (int)n, st);
+  tmp_bytes = std::max(tmp_bytes, need);
+  PPCU(cudaMalloc(&d_tmp, tmp_bytes));
+  // only the bits a key word can hold are sorted: word 0 (rid | start, or rid1 | rid2) up to its largest value in this call;
+  // pp_key_word bounds the others: the 32-bit alignment lengths; length alone; mapq | direction | unique | read id
+  u64 max0 = 0;
+  PPCU(cudaMemsetAsync(d_nsel, 0, 16, st));
+  pp_max_key0_kernel<<<std::min(nb, 1184u), 256, 0, st>>>(P.kind, d_a, n, d_nsel);
+  PPCU(cudaMemcpyAsync(&max0, d_nsel, 8, cudaMemcpyDeviceToHost, st));
+  PPCU(cudaStreamSynchronize(st));
+  int bits0 = 1;
+  while (bits0 < 64 && (max0 >> bits0)) ++bits0;
+  for (int w = pp_n_words(P.kind) - 1; w >= 0; --w) {  // least significant word first; every pass is stable
+    pp_key_kernel<<<nb, 256, 0, st>>>(P.kind, w, d_a, bc ? d_bca : nullptr, di.Current(), n, dk.Current());
+    int bits = 64;
+    if (w == 0) bits = bits0;
+    else if (P.kind == PP_PAIRS) bits = w == 2 ? 40 : 64;
+    else if (bc) bits = w == 1 ? 16 : (w == 3 ? 56 : 64);
+    else if (w == 2) bits = 32;
+    PPCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dk, di, (int)n, 0, bits, st));
+  }
+  pp_gather_kernel<<<nb, 256, 0, st>>>(d_a, bc ? d_bca : nullptr, di.Current(), n, d_b, d_bcb);
+  pp_head_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, P.dedup, d_b, bc ? d_bcb : nullptr, n, d_head);
+  pp_resolve_kernel<<<nb, 256, 0, st>>>(P, d_b, bc ? d_bcb : nullptr, d_head, n, d_a, bc ? d_bca : nullptr, d_keep);
+  PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_a, d_keep, d_b, d_nsel, (int)n, st));
+  if (bc) PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_bca, d_keep, d_bcb, d_nsel + 1, (int)n, st));
+  u64 nsel = 0;
+  PPCU(cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, st));
+  PPCU(cudaStreamSynchronize(st));
+  PPCU(cudaGetLastError());
+#undef PPCU
+  cleanup();
+  *nsel_out = nsel;
+  return CMX_OK;
+}
+
+// The same in place on host buffers: same results as cmx_postprocess / cmx_postprocess_bc / cmx_postprocess_pairs
+// (postprocess.cuh).  The record kind follows the context: pairs when output_format == 5, barcoded BED when
+// barcode_keys != NULL, else bulk BED.
 int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uint64_t n, uint64_t *n_out) {
   if (!ctx || (!records && n) || !n_out) return CMX_ERR_INVALID;
   *n_out = 0;
@@ -1431,46 +1551,16 @@ int cmx_postprocess_gpu(cmx_ctx *ctx, void *records, uint64_t *barcode_keys, uin
   const bool bc = P.kind == PP_BED_BC;
   cudaStream_t st = ctx->stream;
   PpRecord *d_a = nullptr, *d_b = nullptr;
-  u64 *d_bca = nullptr, *d_bcb = nullptr, *d_k0 = nullptr, *d_k1 = nullptr, *d_nsel = nullptr;
-  u32 *d_i0 = nullptr, *d_i1 = nullptr;
-  u8 *d_head = nullptr, *d_keep = nullptr;
-  void *d_tmp = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_a); cudaFree(d_b); cudaFree(d_bca); cudaFree(d_bcb); cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_nsel);
-    cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_head); cudaFree(d_keep); cudaFree(d_tmp);
-  };
+  u64 *d_bca = nullptr, *d_bcb = nullptr;
+  auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_b); cudaFree(d_bca); cudaFree(d_bcb); };
 #define PPCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
   PPCU(cudaMalloc(&d_a, n * sizeof(PpRecord))); PPCU(cudaMalloc(&d_b, n * sizeof(PpRecord)));
   if (bc) { PPCU(cudaMalloc(&d_bca, n * 8)); PPCU(cudaMalloc(&d_bcb, n * 8)); }
-  PPCU(cudaMalloc(&d_k0, n * 8)); PPCU(cudaMalloc(&d_k1, n * 8)); PPCU(cudaMalloc(&d_i0, n * 4)); PPCU(cudaMalloc(&d_i1, n * 4));
-  PPCU(cudaMalloc(&d_head, n)); PPCU(cudaMalloc(&d_keep, n)); PPCU(cudaMalloc(&d_nsel, 16));
   PPCU(cudaMemcpyAsync(d_a, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
   if (bc) PPCU(cudaMemcpyAsync(d_bca, barcode_keys, n * 8, cudaMemcpyHostToDevice, st));
-  const unsigned nb = (unsigned)((n + 255) / 256);
-  if (!P.low_mem && P.tn5 && P.kind != PP_PAIRS) pp_tn5_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, d_a, n);  // chromap.h:1322-1355: before the sort
-  pp_iota_kernel<<<nb, 256, 0, st>>>(d_i0, n);
-  cub::DoubleBuffer<u64> dk(d_k0, d_k1);
-  cub::DoubleBuffer<u32> di(d_i0, d_i1);
-  size_t tmp_bytes = 0, need = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, (int)n, 0, 64, st);
-  cub::DeviceSelect::Flagged(nullptr, need, d_a, d_keep, d_b, d_nsel, (int)n, st);
-  tmp_bytes = std::max(tmp_bytes, need);
-  cub::DeviceSelect::Flagged(nullptr, need, d_bca, d_keep, d_bcb, d_nsel, (int)n, st);
-  tmp_bytes = std::max(tmp_bytes, need);
-  PPCU(cudaMalloc(&d_tmp, tmp_bytes));
-  for (int w = pp_n_words(P.kind) - 1; w >= 0; --w) {  // least significant word first; every pass is stable
-    pp_key_kernel<<<nb, 256, 0, st>>>(P.kind, w, d_a, bc ? d_bca : nullptr, di.Current(), n, dk.Current());
-    PPCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dk, di, (int)n, 0, 64, st));
-  }
-  pp_gather_kernel<<<nb, 256, 0, st>>>(d_a, bc ? d_bca : nullptr, di.Current(), n, d_b, d_bcb);
-  pp_head_kernel<<<nb, 256, 0, st>>>(P.kind, P.se, P.dedup, d_b, bc ? d_bcb : nullptr, n, d_head);
-  pp_resolve_kernel<<<nb, 256, 0, st>>>(P, d_b, bc ? d_bcb : nullptr, d_head, n, d_a, bc ? d_bca : nullptr, d_keep);
-  PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_a, d_keep, d_b, d_nsel, (int)n, st));
-  if (bc) PPCU(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_bca, d_keep, d_bcb, d_nsel + 1, (int)n, st));
   u64 nsel = 0;
-  PPCU(cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, st));
-  PPCU(cudaStreamSynchronize(st));
-  PPCU(cudaGetLastError());
+  const int rc = pp_device(ctx, P, d_a, d_bca, n, d_b, d_bcb, &nsel);
+  if (rc != CMX_OK) { cleanup(); return rc; }
   if (nsel) PPCU(cudaMemcpyAsync(records, d_b, nsel * sizeof(PpRecord), cudaMemcpyDeviceToHost, st));
   if (bc && nsel) PPCU(cudaMemcpyAsync(barcode_keys, d_bcb, nsel * 8, cudaMemcpyDeviceToHost, st));
   PPCU(cudaStreamSynchronize(st));
@@ -1490,6 +1580,10 @@ struct NcclApi {
   int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool ok = false;
   std::string why;
@@ -1510,8 +1604,12 @@ NcclApi &nccl_api() {
   api.CommInitRank = (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
   api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
   api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+  api.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclSend");
+  api.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclRecv");
+  api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
   api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
   if (!api.ok) api.why = "libnccl.so.2 lacks the expected symbols";
   return api;
 }
@@ -1653,6 +1751,153 @@ int cmx_dedup_exchange(cmx_ctx *ctx, const void *records, const uint64_t *barcod
 #undef XNC
   cleanup();
   *n_out = nsel;
+  return CMX_OK;
+}
+
+// The same step as a range shuffle (exchange.cuh, second half): this rank's records in; out = the records of THIS RANK'S KEY
+// RANGE after duplicate removal over the whole run, in the reference's order, num_dups set, MAPQ-filtered, Tn5 applied —
+// the run's output is the ranks' outputs one after the other in rank order.  Work per rank is proportional to its share of
+// the run (the all-gather variant above sorts every rank's tuples on every rank).
+int cmx_dedup_shuffle(cmx_ctx *ctx, const void *records, const uint64_t *barcode_keys, uint64_t n, int on_device, void *out_records,
+                      uint64_t *out_barcode_keys, uint64_t out_capacity, uint64_t *n_out, cmx_shuffle_stats *stats) {
+  if (!ctx || (!records && n) || (!out_records && out_capacity) || !n_out) return CMX_ERR_INVALID;
+  *n_out = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const cmx_params &p = ctx->params;
+  if (p.output_format == 5 || p.single_end || !p.low_memory_mode)
+    return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_shuffle: paired-end BED records in low-memory mode only (every preset with duplicate removal)");
+  if (!ctx->nccl_comm) return fail(ctx, CMX_ERR_STATE, "cmx_dedup_shuffle: cmx_comm_init first");
+  if (n >= 0x7FFFFFFFull) return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_shuffle: more than 2^31-1 records on one rank");
+  NcclApi &N = nccl_api();
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool bc = barcode_keys != nullptr;
+  const int R = ctx->comm_size, rank = ctx->comm_rank;
+  PpRecord *d_rec = nullptr, *d_send = nullptr, *d_recv = nullptr, *d_res = nullptr;
+  u64 *d_bc = nullptr, *d_sendbc = nullptr, *d_recvbc = nullptr, *d_resbc = nullptr, *d_a = nullptr, *d_samp = nullptr, *d_all0 = nullptr, *d_all1 = nullptr,
+      *d_split = nullptr, *d_off = nullptr, *d_offall = nullptr;
+  u32 *d_d0 = nullptr, *d_d1 = nullptr, *d_i0 = nullptr, *d_i1 = nullptr;
+  void *d_tmp = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto cleanup = [&]() {
+    if (!on_device) { cudaFree(d_rec); cudaFree(d_bc); }
+    cudaFree(d_send); cudaFree(d_recv); cudaFree(d_res); cudaFree(d_sendbc); cudaFree(d_recvbc); cudaFree(d_resbc); cudaFree(d_a); cudaFree(d_samp);
+    cudaFree(d_all0); cudaFree(d_all1); cudaFree(d_split); cudaFree(d_off); cudaFree(d_offall); cudaFree(d_d0); cudaFree(d_d1); cudaFree(d_i0); cudaFree(d_i1);
+    cudaFree(d_tmp);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+  };
+#define XCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+#define XNC(call) do { int r_ = (call); if (r_ != 0) { cleanup(); return fail(ctx, CMX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, N.GetErrorString ? N.GetErrorString(r_) : "NCCL error"); } } while (0)
+  for (auto &e : ev) XCU(cudaEventCreate(&e));
+  const u64 n1 = std::max<u64>(n, 1);
+  if (on_device) { d_rec = (PpRecord *)records; d_bc = (u64 *)barcode_keys; }
+  else {
+    XCU(cudaMalloc(&d_rec, n1 * sizeof(PpRecord)));
+    XCU(cudaMemcpyAsync(d_rec, records, n * sizeof(PpRecord), cudaMemcpyHostToDevice, st));
+    if (bc) { XCU(cudaMalloc(&d_bc, n1 * 8)); XCU(cudaMemcpyAsync(d_bc, barcode_keys, n * 8, cudaMemcpyHostToDevice, st)); }
+  }
+  const u64 n_samp = (u64)R * SH_SAMPLE;
+  XCU(cudaMalloc(&d_a, n1 * 8)); XCU(cudaMalloc(&d_samp, SH_SAMPLE * 8)); XCU(cudaMalloc(&d_all0, n_samp * 8)); XCU(cudaMalloc(&d_all1, n_samp * 8));
+  XCU(cudaMalloc(&d_split, (size_t)std::max(R - 1, 1) * 8)); XCU(cudaMalloc(&d_off, (size_t)(R + 1) * 8)); XCU(cudaMalloc(&d_offall, (size_t)R * (R + 1) * 8));
+  XCU(cudaMalloc(&d_d0, n1 * 4)); XCU(cudaMalloc(&d_d1, n1 * 4)); XCU(cudaMalloc(&d_i0, n1 * 4)); XCU(cudaMalloc(&d_i1, n1 * 4));
+  XCU(cudaMalloc(&d_send, n1 * sizeof(PpRecord)));
+  if (bc) XCU(cudaMalloc(&d_sendbc, n1 * 8));
+  size_t tmp_bytes = 0, need = 0;
+  {
+    cub::DoubleBuffer<u64> ks(d_all0, d_all1);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ks, (int)n_samp, 0, 64, st);
+    cub::DoubleBuffer<u32> dd(d_d0, d_d1), di(d_i0, d_i1);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, dd, di, (int)n1, 0, 32, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+  }
+  XCU(cudaMalloc(&d_tmp, tmp_bytes));
+  // ---- partition: splitters from an all-gathered sample, destination of every record, records grouped by destination
+  XCU(cudaEventRecord(ev[0], st));
+  const unsigned nb = (unsigned)((n1 + 255) / 256);
+  if (n) sh_key_kernel<<<nb, 256, 0, st>>>(d_rec, n, d_a);
+  sh_sample_kernel<<<(SH_SAMPLE + 255) / 256, 256, 0, st>>>(d_a, n, d_samp);
+  XNC(N.AllGather(d_samp, d_all0, SH_SAMPLE, NCCL_UINT64, ctx->nccl_comm, st));
+  cub::DoubleBuffer<u64> ks(d_all0, d_all1);
+  XCU(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, ks, (int)n_samp, 0, 64, st));
+  std::vector<u64> samp(n_samp), split(std::max(R - 1, 1), 0);
+  XCU(cudaMemcpyAsync(samp.data(), ks.Current(), n_samp * 8, cudaMemcpyDeviceToHost, st));
+  XCU(cudaStreamSynchronize(st));
+  const u64 valid = (u64)(std::lower_bound(samp.begin(), samp.end(), (u64)EX_PAD) - samp.begin());  // padding sorts last
+  for (int j = 1; j < R; ++j) split[j - 1] = valid ? samp[valid * (u64)j / (u64)R] : 0ull;           // the same on every rank
+  XCU(cudaMemcpyAsync(d_split, split.data(), split.size() * 8, cudaMemcpyHostToDevice, st));
+  int dest_bits = 1;
+  while ((1 << dest_bits) < R) ++dest_bits;
+  cub::DoubleBuffer<u32> dd(d_d0, d_d1), di(d_i0, d_i1);
+  if (n) {
+    sh_dest_kernel<<<nb, 256, 0, st>>>(d_a, n, d_split, R - 1, dd.Current());
+    pp_iota_kernel<<<nb, 256, 0, st>>>(di.Current(), n);
+    XCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, dd, di, (int)n, 0, dest_bits, st));  // stable: mapping order kept inside a destination
+    pp_gather_kernel<<<nb, 256, 0, st>>>(d_rec, bc ? d_bc : nullptr, di.Current(), n, d_send, d_sendbc);
+  }
+  sh_bounds_kernel<<<(R + 1 + 63) / 64, 64, 0, st>>>(dd.Current(), n, R, d_off);
+  XNC(N.AllGather(d_off, d_offall, (size_t)(R + 1), NCCL_UINT64, ctx->nccl_comm, st));
+  std::vector<u64> offall((size_t)R * (R + 1));
+  XCU(cudaMemcpyAsync(offall.data(), d_offall, offall.size() * 8, cudaMemcpyDeviceToHost, st));
+  XCU(cudaStreamSynchronize(st));
+  auto cnt = [&](int from, int to) { return offall[(size_t)from * (R + 1) + to + 1] - offall[(size_t)from * (R + 1) + to]; };
+  u64 n_recv = 0, n_global = 0;
+  std::vector<u64> roff(R + 1, 0);
+  for (int q = 0; q < R; ++q) { roff[q] = n_recv; n_recv += cnt(q, rank); n_global += offall[(size_t)q * (R + 1) + R]; }
+  roff[R] = n_recv;
+  if (n_recv >= 0x7FFFFFFFull) { cleanup(); return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_shuffle: %llu records in this rank's key range exceed 2^31-1", (unsigned long long)n_recv); }
+  const u64 nr1 = std::max<u64>(n_recv, 1);
+  XCU(cudaMalloc(&d_recv, nr1 * sizeof(PpRecord))); XCU(cudaMalloc(&d_res, nr1 * sizeof(PpRecord)));
+  if (bc) { XCU(cudaMalloc(&d_recvbc, nr1 * 8)); XCU(cudaMalloc(&d_resbc, nr1 * 8)); }
+  // ---- shuffle: every record travels once, to the rank that owns its key range
+  XCU(cudaEventRecord(ev[1], st));
+  XNC(N.GroupStart());
+  for (int q = 0; q < R; ++q) {
+    const u64 so = offall[(size_t)rank * (R + 1) + q], sc = cnt(rank, q), rc = cnt(q, rank);
+    if (q == rank) {  // this rank's own share stays on the device
+      if (sc) {
+        XCU(cudaMemcpyAsync(d_recv + roff[q], d_send + so, sc * sizeof(PpRecord), cudaMemcpyDeviceToDevice, st));
+        if (bc) XCU(cudaMemcpyAsync(d_recvbc + roff[q], d_sendbc + so, sc * 8, cudaMemcpyDeviceToDevice, st));
+      }
+      continue;
+    }
+    if (sc) {
+      XNC(N.Send(d_send + so, sc * sizeof(PpRecord), NCCL_UINT8, q, ctx->nccl_comm, st));
+      if (bc) XNC(N.Send(d_sendbc + so, sc * 8, NCCL_UINT8, q, ctx->nccl_comm, st));
+    }
+    if (rc) {
+      XNC(N.Recv(d_recv + roff[q], rc * sizeof(PpRecord), NCCL_UINT8, q, ctx->nccl_comm, st));
+      if (bc) XNC(N.Recv(d_recvbc + roff[q], rc * 8, NCCL_UINT8, q, ctx->nccl_comm, st));
+    }
+  }
+  XNC(N.GroupEnd());
+  XCU(cudaEventRecord(ev[2], st));
+  // ---- the ordinary single-GPU post-processing of what arrived
+  PpParams P;
+  P.kind = bc ? PP_BED_BC : PP_BED; P.low_mem = 1; P.dedup = p.remove_pcr_duplicates; P.tn5 = p.tn5_shift; P.mapq_threshold = p.mapq_threshold; P.se = 0;
+  u64 nsel = 0;
+  const int prc = pp_device(ctx, P, d_recv, d_recvbc, n_recv, d_res, d_resbc, &nsel);
+  if (prc != CMX_OK) { cleanup(); return prc; }
+  XCU(cudaEventRecord(ev[3], st));
+  *n_out = nsel;
+  if (nsel > out_capacity) { cleanup(); return fail(ctx, CMX_ERR_INVALID, "cmx_dedup_shuffle: %llu records for a capacity of %llu", (unsigned long long)nsel, (unsigned long long)out_capacity); }
+  if (nsel) {
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    XCU(cudaMemcpyAsync(out_records, d_res, nsel * sizeof(PpRecord), kind, st));
+    if (bc && out_barcode_keys) XCU(cudaMemcpyAsync(out_barcode_keys, d_resbc, nsel * 8, kind, st));
+  }
+  XCU(cudaStreamSynchronize(st));
+  XCU(cudaGetLastError());
+  if (stats) {
+    cudaEventElapsedTime(&stats->partition_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&stats->shuffle_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->postprocess_ms, ev[2], ev[3]);
+    const u64 rb = sizeof(PpRecord) + (bc ? 8 : 0);
+    stats->bytes_sent = (n - cnt(rank, rank)) * rb; stats->bytes_received = (n_recv - cnt(rank, rank)) * rb;
+    stats->n_received = n_recv; stats->n_global = n_global; stats->n_ranks = (uint32_t)R;
+  }
+#undef XCU
+#undef XNC
+  cleanup();
   return CMX_OK;
 }
 

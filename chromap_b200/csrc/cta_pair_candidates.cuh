@@ -199,10 +199,11 @@ __device__ inline void cta_pe_filter(u32 dist, const u64 *p1, const u8 *c1, int 
 // the windows is a prefix "scan" over 2-state transition functions (5 shuffle steps).  Emission [first, max(first, UB))
 // goes through a shared counter (order is irrelevant: the hits are sorted next).  No block barrier inside.
 #define RESCUE_MAXWIN 300
+#define PC_CTA_NT_MAX 512  // threads of pair_candidates_cta_kernel at most (the block-wide primitives size themselves from blockDim)
 struct RescueShared {
   u64 win_lo[RESCUE_MAXWIN], win_hi[RESCUE_MAXWIN];
   int i[8];
-  int warp[4];
+  int warp[PC_CTA_NT_MAX / 32];
 };
 // mmv / mmp: this read's minimizer records (shared memory).  mate_pos / mate_cnt: the mate's candidates on the strand
 // that guides the search.  Returns +max count or -max count (bail-out, index.cc:371-380) on every thread; *nh_out =
@@ -465,7 +466,7 @@ __device__ inline void pair_candidates_cta_pair(const DevParams &P, const DevInd
   atomicAdd(&ctr->n_candidates, (u64)(nc1 + nc2));
 }
 
-__global__ void __launch_bounds__(CTA_NT) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap, int lcap, int fcap,
+__global__ void __launch_bounds__(PC_CTA_NT_MAX) pair_candidates_cta_kernel(DevParams P, DevIndex ix, Scratch S, Counters *ctr, int sm_cap, int lcap, int fcap,
                                                                      const int *list, const int *list_count) {
   extern __shared__ u64 sm[];
   __shared__ RescueShared RS;

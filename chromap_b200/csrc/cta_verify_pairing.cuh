@@ -25,7 +25,7 @@ __device__ __forceinline__ Tally tally_merge(const Tally &a, const Tally &b, int
   r.n_second_best = n;
   return r;
 }
-__device__ __forceinline__ Tally cta_tally_reduce(Tally t, int sentinel, Tally *s_t /* [CTA_NT / 32] */) {
+__device__ __forceinline__ Tally cta_tally_reduce(Tally t, int sentinel, Tally *s_t /* one per warp */) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     Tally u;
@@ -36,8 +36,7 @@ __device__ __forceinline__ Tally cta_tally_reduce(Tally t, int sentinel, Tally *
   if ((threadIdx.x & 31) == 0) s_t[threadIdx.x >> 5] = t;
   __syncthreads();
   Tally r = s_t[0];
-#pragma unroll
-  for (int i = 1; i < CTA_NT / 32; ++i) r = tally_merge(r, s_t[i], sentinel);
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = tally_merge(r, s_t[i], sentinel);
   __syncthreads();
   return r;
 }
@@ -55,13 +54,15 @@ __device__ __forceinline__ Tally cta_tally_reduce(Tally t, int sentinel, Tally *
 // straddle a step), one banded alignment per thread; the step that finds the failing group fixes `stop`, and the walk
 // ends at the first step that starts at or beyond it.  Accepted mappings are written in list order (prefix sum per
 // step), the error tally is merged at the end.  Work the reference would have skipped is limited to one step.
-__global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
+#define VERIFY_NT_MAX 256  // threads of verify_cta_kernel at most
+__global__ void __launch_bounds__(VERIFY_NT_MAX) verify_cta_kernel(DevParams P, DevRef R, DevBatch B, Scratch S, Counters *ctr, int sm_cap) {
   extern __shared__ u64 smk[];  // [sm_cap] sort keys, afterwards the list of valid candidate indices (u16) | [sm_cap] sort tags | read codes
   u8 *smt = (u8 *)(smk + sm_cap);
   u8 *s_fwd = smt + sm_cap, *s_neg = s_fwd + S.caps.maxmm;  // base codes of the read and of its reverse complement
   __shared__ int s_i[8];
-  __shared__ int s_warp[CTA_NT / 32];
-  __shared__ Tally s_t[CTA_NT / 32];
+  __shared__ int s_warp[VERIFY_NT_MAX / 32];
+  __shared__ Tally s_t[VERIFY_NT_MAX / 32];
+  const int NT = blockDim.x;  // 128 in the middle tier, 256 in the last one (a multiple of the group size either way)
   const int sr = blockIdx.x, tid = threadIdx.x;
   const int slot = sr >> 1, mate = sr & 1;
   if (tid == 0) s_i[0] = S.pmeta[slot].status;  // the mate's CTA may flag the pair concurrently
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
       if (ok) return;
     }
   }
-  for (int i = tid; i < L; i += CTA_NT) {
+  for (int i = tid; i < L; i += NT) {
     const u32 b = base_code(read[i]);
     s_fwd[i] = (u8)b;
     s_neg[L - 1 - i] = (u8)(b < 4 ? 3u ^ b : 4u);
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
     const int n = nc[s];
     if (n == 0) continue;
     // compacted list of valid candidates, in list order
-    const int C = (n + CTA_NT - 1) / CTA_NT;
+    const int C = (n + NT - 1) / NT;
     const int r0 = min(n, tid * C), r1 = min(n, r0 + C);
     int mine = 0;
     for (int i = r0; i < r1; ++i) {
@@ -136,13 +137,13 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
     int stop = n;                               // candidates at list indices >= stop are not taken ...
     int free_until = 0;                         // ... except those of rank < free_until (the failing group itself)
     int out_base = 0;
-    for (int v0 = 0; v0 < nv; v0 += CTA_NT) {
+    for (int v0 = 0; v0 < nv; v0 += NT) {
       if ((int)vlist[v0] >= stop && v0 >= free_until) break;
       const int v = v0 + tid;
       int err = e + 1, endp = 0, idx = 0;
       u64 cpos = 0;
-      if (v + CTA_NT < nv) {  // the window this thread aligns in the next step: request its lines now (a cold window is a DRAM round trip)
-        const u64 nx = cp[s][vlist[v + CTA_NT]];
+      if (v + NT < nv) {  // the window this thread aligns in the next step: request its lines now (a cold window is a DRAM round trip)
+        const u64 nx = cp[s][vlist[v + NT]];
         const u32 npos = s == 0 ? (u32)nx : (u32)nx - (u32)L + 1u;
         prefetch_span(R.seq + R.off[(u32)(nx >> 32)] + npos - e, L + 2 * e);
       }
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(CTA_NT) verify_cta_kernel(DevParams P, DevRef 
         __syncthreads();
         int first_fail = -1;
 #pragma unroll
-        for (int w = 0; w < CTA_NT / 32; ++w) if (first_fail < 0 && s_warp[w]) first_fail = v0 + w * 32 + __ffs((unsigned)s_warp[w]) - 1;
+        for (int w = 0; w < (NT >> 5); ++w) if (first_fail < 0 && s_warp[w]) first_fail = v0 + w * 32 + __ffs((unsigned)s_warp[w]) - 1;
         if (first_fail >= 0) {
           const int g0 = first_fail / P.lanes * P.lanes, g1 = g0 + P.lanes;  // ranks of the failing group (inside this step)
           int last_fail = first_fail;

@@ -139,6 +139,9 @@ __device__ __forceinline__ void prefetch_span(const void *p, int bytes) {
   for (; a < z; a += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
 }
 
+// One line towards L2, long before it is read (fire and forget).
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // First index in the sorted occurrence list O[0..n) whose position (entry >> 1) is >= lo.  Four-way instead of two-way: a
 // search over a list of 10^5 occurrences is a chain of dependent loads, and three independent loads per step halve the chain
 // (8 round trips instead of 17); the last <= 8 entries are fetched together.  Same result as a binary lower bound.

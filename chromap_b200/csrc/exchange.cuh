@@ -81,3 +81,43 @@ __global__ void ex_gather_kernel(const PpRecord *recs, const u64 *bcs, const u32
   out[i] = r;
   if (bcs) out_bc[i] = bcs[sel[i]];
 }
+
+// ---- the same step as a range shuffle (cmx_dedup_shuffle) ---------------------------------------------------------------
+// The all-gather above makes every rank sort the tuples of ALL ranks: its cost per rank grows with the size of the run.
+// The shuffle keeps it at the size of the rank's share: the records' primary key word a = rid << 32 | fragment_start is
+// range-partitioned over the ranks (splitters from an all-gathered sample — a sample sort), each record travels once, to
+// the rank that owns its key range (grouped ncclSend / ncclRecv over NVLink), and that rank runs the ordinary
+// single-GPU post-processing (postprocess.cuh: the reference's order, duplicate rule, MAPQ filter, Tn5) on what it
+// received.  Duplicates agree in `a`, so a group never straddles two ranks; the run's output is the ranks' outputs in
+// rank order.
+#define SH_SAMPLE 4096  // sample keys per rank
+
+__global__ void sh_key_kernel(const PpRecord *recs, u64 n, u64 *a) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = ((u64)recs[i].w[1] << 32) | recs[i].w[2];
+}
+// SH_SAMPLE evenly spaced records of this rank (the local order is the mapping order: unrelated to the key); ranks with
+// fewer records than that pad with EX_PAD, which the splitter choice ignores
+__global__ void sh_sample_kernel(const u64 *a, u64 n, u64 *sample) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SH_SAMPLE) return;
+  const u64 take = n < SH_SAMPLE ? n : SH_SAMPLE;
+  sample[i] = i < take ? a[(u64)i * n / take] : EX_PAD;
+}
+// destination rank = number of splitters <= a  (rank r owns  splitter[r-1] <= a < splitter[r])
+__global__ void sh_dest_kernel(const u64 *a, u64 n, const u64 *splitters, int n_split, u32 *dest) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 x = a[i];
+  int lo = 0, hi = n_split;
+  while (lo < hi) { const int m = (lo + hi) >> 1; if (splitters[m] <= x) lo = m + 1; else hi = m; }
+  dest[i] = (u32)lo;
+}
+// first position of every destination in the destination-sorted order: off[d] = lower_bound(sorted, d), off[R] = n
+__global__ void sh_bounds_kernel(const u32 *sorted_dest, u64 n, int R, u64 *off) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d > R) return;
+  u64 lo = 0, hi = n;
+  while (lo < hi) { const u64 m = (lo + hi) >> 1; if (sorted_dest[m] < (u32)d) lo = m + 1; else hi = m; }
+  off[d] = lo;
+}

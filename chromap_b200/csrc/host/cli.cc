@@ -14,8 +14,12 @@
 
 #include "../../../include/chromap_b200.h"
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "seqio.h"
 
@@ -47,18 +51,35 @@ struct Batch {
 // buffer (no zlib copy, H2D at PCIe speed); gzip files go through gzread.  Whole 4-line records are cut off the front of the
 // buffer (same rule as cmx_fastq_cut, but the scan remembers where it stopped instead of starting over after every refill),
 // the rest stays for the next batch.
+struct RawBuf {  // uninitialised page-aligned bytes (a std::vector would zero-fill hundreds of megabytes before they are read into)
+  char *p = nullptr;
+  size_t n = 0;
+  char *data() { return p; }
+  const char *data() const { return p; }
+  size_t size() const { return n; }
+  char &operator[](size_t i) { return p[i]; }
+  void Grow(size_t bytes, size_t keep) {
+    char *q = (char *)aligned_alloc(4096, (bytes + 4095) & ~(size_t)4095);
+    if (!q) { fprintf(stderr, "chromap-b200: out of memory\n"); exit(255); }
+    if (keep) memcpy(q, p, keep);
+    free(p);
+    p = q; n = bytes;
+  }
+  ~RawBuf() { free(p); }
+};
 struct RawFile {
   gzFile f = nullptr;
   int fd = -1;
-  std::vector<char> buf;
+  RawBuf buf;
   size_t have = 0;
   bool eof = false, pinned = false;
   size_t fpos = 0;                   // plain files: offset of the next unread byte
-  size_t scan = 0, end_of_last = 0;  // scan state: bytes examined, end of the last whole record among them
-  uint32_t lines = 0, recs = 0;      // newlines of the record under way, whole records found
+  size_t scan = 0;                   // scan state: bytes examined (see Fill)
+  size_t chunk = 0;                  // bytes per read; 0 = 32 MB (gzip) / 128 MB (plain).  Set by the host test only.
+  size_t file_bytes = 0, first_cut = 0;  // plain files: size; bytes of the first batch handed out (to size the record store)
   bool Open(const std::string &path) {
     Close();
-    have = 0; eof = false; scan = end_of_last = 0; lines = recs = 0; fpos = 0;
+    have = 0; eof = false; scan = 0; nl = 0; fpos = 0;
     unsigned char magic[2] = {0, 0};
     FILE *t = fopen(path.c_str(), "rb");
     if (!t) return false;
@@ -66,7 +87,7 @@ struct RawFile {
     fclose(t);
     if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
     fd = open(path.c_str(), O_RDONLY);
-    if (fd >= 0) posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    if (fd >= 0) { posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL); struct stat sb; if (fstat(fd, &sb) == 0) file_bytes = (size_t)sb.st_size; }
     return fd >= 0;
   }
   void Close() {
@@ -75,58 +96,127 @@ struct RawFile {
     f = nullptr; fd = -1;
     if (pinned) { cmx_host_unregister(buf.data()); pinned = false; }
   }
-  void Reserve(size_t bytes) {  // grow (rarely): the buffer is pinned once it has its working size
+  void Reserve(size_t bytes, bool exact = false) {  // grow (rarely): the buffer is pinned once it has its working size
     if (buf.size() >= bytes) return;
     if (pinned) { cmx_host_unregister(buf.data()); pinned = false; }
-    buf.resize(bytes + bytes / 4);
+    buf.Grow(exact ? bytes : bytes + bytes / 4, have);
     pinned = cmx_host_register(buf.data(), buf.size()) == 0;
   }
-  // bytes of up to max_records whole records now in the buffer (reading more as needed); *n = their number
+  // Size (and page-lock) the buffer for calls of max_records before the first one: bytes per record from the head of the file.
+  // Run at start-up, beside the index upload, so that the mapping phase never allocates.
+  void Prepare(uint32_t max_records) {
+    if (f || fd < 0 || !file_bytes) return;
+    std::vector<char> head(1u << 20);
+    const ssize_t got = pread(fd, head.data(), head.size(), 0);
+    if (got <= 0) return;
+    const uint64_t lines = CountNewlines(head.data(), (size_t)got);
+    if (lines < 8) return;
+    const double per_record = (double)got / ((double)lines / 4.0);
+    const size_t want = (size_t)(per_record * max_records * 1.1) + (128u << 20) + 4096;
+    Reserve(std::min(want, file_bytes + 4096), true);
+  }
+  // bytes of up to max_records whole records now in the buffer (reading more as needed); *n = their number.
+  // Newlines are counted in bulk (SSE2 compare + popcount, by the threads that read the data); only the stretch that holds
+  // the last newline wanted is walked line by line.  State: nl = newlines in buf[0, scan).
+  uint64_t nl = 0;
+  static uint64_t CountNewlines(const char *p, size_t n) {
+    uint64_t c = 0;
+    size_t i = 0;
+#if defined(__SSE2__)
+    const __m128i v = _mm_set1_epi8('\n');
+    for (; i + 64 <= n; i += 64) {
+      const unsigned m0 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(p + i)), v));
+      const unsigned m1 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(p + i + 16)), v));
+      const unsigned m2 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(p + i + 32)), v));
+      const unsigned m3 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(p + i + 48)), v));
+      c += (uint64_t)__builtin_popcountll(((uint64_t)m0) | ((uint64_t)m1 << 16) | ((uint64_t)m2 << 32) | ((uint64_t)m3 << 48));
+    }
+#endif
+    for (; i < n; ++i) c += p[i] == '\n';
+    return c;
+  }
+  // advance the scan over buf[scan, scan + len) whose newline count is known; returns true once 4 * max_records are in
+  bool Advance(size_t len, uint64_t count, uint64_t target) {
+    if (nl + count < target) { nl += count; scan += len; return false; }
+    while (nl < target) {  // the last newline wanted lies in this stretch
+      const void *q = memchr(buf.data() + scan, '\n', have - scan);
+      scan = (size_t)((const char *)q - buf.data()) + 1;
+      ++nl;
+    }
+    return true;
+  }
   uint64_t Fill(uint32_t max_records, uint32_t *n) {
+    const uint64_t target = 4ull * max_records;
+    if (max_records == 0) { *n = 0; return 0; }
+    if (scan < have && nl < target) {  // what an earlier call left behind (less than one read chunk)
+      const size_t len = have - scan;
+      if (Advance(len, CountNewlines(buf.data() + scan, len), target)) { *n = max_records; return scan; }
+    }
     for (;;) {
-      while (recs < max_records && scan < have) {
-        const void *q = memchr(buf.data() + scan, '\n', have - scan);
-        if (!q) { scan = have; break; }
-        scan = (size_t)((const char *)q - buf.data()) + 1;
-        if (++lines == 4) { lines = 0; ++recs; end_of_last = scan; }
+      if (nl >= target) { *n = max_records; return scan; }
+      if (eof) {  // the file ended first: whole records only; up to three lines of an unfinished one stay behind
+        const uint64_t whole = nl / 4;
+        size_t e = have;
+        for (uint64_t extra = nl - 4 * whole; extra > 0 && e > 0; --extra) {
+          const void *q = memrchr(buf.data(), '\n', e - 1);  // the newline before the last line's own
+          e = q ? (size_t)((const char *)q - buf.data()) + 1 : 0;
+        }
+        if (nl == 0) e = 0;
+        *n = (uint32_t)whole;
+        return whole ? e : 0;
       }
-      if (recs == max_records || eof) { *n = recs; return end_of_last; }
-      const size_t want = f ? (32u << 20) : (128u << 20);
+      const size_t want = chunk ? chunk : (f ? (32u << 20) : (128u << 20));
       Reserve(have + want + 1);
-      long got;
-      if (f) got = gzread(f, buf.data() + have, (unsigned)want);
-      else {  // plain file: four threads pread() a quarter each (one thread copies out of the page cache at about 5 GB/s)
-        const int nt = 4;
+      if (f) {
+        const long got = gzread(f, buf.data() + have, (unsigned)want);
+        if (got <= 0) eof = true;
+        else {
+          have += (size_t)got;
+          if (Advance((size_t)got, CountNewlines(buf.data() + scan, (size_t)got), target)) { *n = max_records; return scan; }
+        }
+      } else {  // plain file: eight threads pread() a slice each (one thread copies out of the page cache at 3-5 GB/s)
+        const int nt = 8;
         const size_t slice = want / nt;
-        long part[4] = {0, 0, 0, 0};
-        std::thread th[4];
+        size_t part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint64_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        std::thread th[8];
         for (int t = 0; t < nt; ++t)
           th[t] = std::thread([&, t]() {
             size_t done = 0;
+            char *dst = buf.data() + have + t * slice;
             while (done < slice) {
-              const ssize_t r = pread(fd, buf.data() + have + t * slice + done, slice - done, (off_t)(fpos + t * slice + done));
+              const ssize_t r = pread(fd, dst + done, slice - done, (off_t)(fpos + t * slice + done));
               if (r <= 0) break;
               done += (size_t)r;
             }
-            part[t] = (long)done;
+            part[t] = done;
+            cnt[t] = CountNewlines(dst, done);
           });
         for (int t = 0; t < nt; ++t) th[t].join();
-        got = 0;
-        for (int t = 0; t < nt; ++t) { got += part[t]; if ((size_t)part[t] < slice) break; }  // a short slice is the end of the file
-        fpos += (size_t)got;
+        size_t got = 0;
+        int used = 0;
+        for (int t = 0; t < nt; ++t) { got += part[t]; ++used; if (part[t] < slice) break; }  // a short slice is the end of the file
+        fpos += got;
+        if (got == 0) eof = true;
+        else {
+          have += got;
+          bool done = false;
+          for (int t = 0; t < used && !done; ++t) done = Advance(part[t], cnt[t], target);
+          if (done) { *n = max_records; return scan; }
+        }
       }
-      if (got <= 0) {
-        eof = true;
-        if (have > 0 && buf[have - 1] != '\n') buf[have++] = '\n';  // a last line without its newline
-      } else have += (size_t)got;
+      if (eof && have > 0 && buf[have - 1] != '\n') { buf[have++] = '\n'; ++nl; scan = have; }  // a last line without its newline
     }
   }
-  void Consume(uint64_t bytes) {
+  void Consume(uint64_t bytes) {  // the remainder (less than one read chunk) is counted again by the next Fill
+    if (!first_cut) first_cut = bytes;
     memmove(buf.data(), buf.data() + bytes, have - bytes);
     have -= bytes;
-    scan = 0; end_of_last = 0; lines = 0; recs = 0;  // the remainder (part of one batch at most) is scanned again: it is short
+    scan = 0; nl = 0;
   }
 };
+
+static double g_t_fill = 0, g_t_ingest = 0;  // loader thread: reading + cutting, device-side parsing (summed over calls)
 
 // One batch through the device-side parser.  Returns false if a file is not plain 4-line FASTQ (the caller then uses the
 // host reader); dies on real input errors, like LoadBatch.
@@ -134,12 +224,15 @@ static bool LoadBatchGpu(cmx_ctx *ctx, RawFile *f1, RawFile *f2, RawFile *fb, in
   b->Clear();
   uint32_t n1 = 0, n2 = 0, nb = 0;
   uint64_t c1 = 0, c2 = 0, cb = 0;  // the files are read (and inflated) side by side
+  const double t_f0 = Now();
   std::thread t2, tb;
   if (f2) t2 = std::thread([&]() { c2 = f2->Fill(max_pairs, &n2); });
   if (fb) tb = std::thread([&]() { cb = fb->Fill(max_pairs, &nb); });
   c1 = f1->Fill(max_pairs, &n1);
   if (f2) t2.join();
   if (fb) tb.join();
+  const double t_f1 = Now();
+  g_t_fill += t_f1 - t_f0;
   if ((f2 && n2 != n1) || (fb && nb != n1)) Die("Numbers of reads and barcodes don't match!");
   if (n1 == 0) {
     if (f1->have || (f2 && f2->have) || (fb && fb->have)) return false;  // trailing bytes that are no whole record: not 4-line FASTQ
@@ -155,9 +248,12 @@ static bool LoadBatchGpu(cmx_ctx *ctx, RawFile *f1, RawFile *f2, RawFile *fb, in
     if (gb.min_len != bc_len || gb.max_len != bc_len) Die("ERROR: barcode lengths are not equal in the sample!");
   }
   if (keep_names) for (uint32_t i = 0; i < n1; ++i) b->names1.emplace_back(f1->buf.data() + spans[2 * i], spans[2 * i + 1]);
+  g_t_ingest += Now() - t_f1;
+  const double t_c0 = Now();
   f1->Consume(c1);
   if (f2) f2->Consume(c2);
   if (fb) fb->Consume(cb);
+  g_t_fill += Now() - t_c0;
   b->n = n1; b->dev = true;
   b->dev_in.n_pairs = n1; b->dev_in.seq1 = g1.seq; b->dev_in.off1 = g1.off; b->dev_in.on_device = 1;
   if (f2) { b->dev_in.seq2 = g2.seq; b->dev_in.off2 = g2.off; }
@@ -327,25 +423,48 @@ int main(int argc, char **argv) {
   // are parsed by one thread, the index file is mapped and read ahead by the kernel, the CUDA context comes up on this thread
   Reference ref;
   bool ref_ok = false;
-  std::thread ref_loader([&]() { ref_ok = ref.Load(ref_path); });
+  double t_ref_parsed = 0;
+  std::thread ref_loader([&]() { ref_ok = ref.Load(ref_path); t_ref_parsed = Now(); });
   IndexMap ix;
   const bool ix_ok = ix.Open(index_path);
   p.single_end = se ? 1 : 0;
   int rc = cmx_create(&ctx, 0, &p);
+  if (!ix_ok) Die("Cannot load index file " + index_path);
+  if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: unsupported parameter combination");
+  // the index arrays go to the device while the reference sequences are still being parsed — and while the read files are
+  // opened, their page-locked buffers sized from the first records, and the first call's reads brought in
+  RawFile g1, g2, gb;
+  bool gpu_reader = !host_reader && !sam && !paf;  // SAM / PAF keep names (SAM: bases and qualities too) of every read on the host
+  bool raw_ready = false;
+  const uint32_t first_call_pairs = (uint32_t)p.batch_size * 4u;
+  std::thread raw_prep;
+  if (gpu_reader) {
+    raw_prep = std::thread([&]() {
+      const bool with_bc = !bc_path.empty();
+      if (!g1.Open(r1_path) || (!se && !g2.Open(r2_path)) || (with_bc && !gb.Open(bc_path))) return;  // reported by open_all below
+      auto warm = [&](RawFile *f) { uint32_t n = 0; f->Prepare(first_call_pairs); f->Fill(first_call_pairs, &n); };
+      std::thread a, b;
+      if (!se) a = std::thread([&]() { warm(&g2); });
+      if (with_bc) b = std::thread([&]() { warm(&gb); });
+      warm(&g1);
+      if (a.joinable()) a.join();
+      if (b.joinable()) b.join();
+      raw_ready = true;
+    });
+  }
+  const double t_ix = Now();
+  if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags, ix.keys, ix.vals, ix.occ, ix.n_occ)) Die(cmx_last_error(ctx));
+  fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %u.\n", ix.k, ix.w, ix.size, ix.n_occ);
+  ix.Close();
+  const double t_ix_done = Now();
   ref_loader.join();
   if (!ref_ok) Die("Cannot find sequence file " + ref_path);
   fprintf(stderr, "Loaded all sequences successfully, number of sequences: %zu, number of bases: %zu.\n", ref.names.size(), ref.concat.size());
-  if (!ix_ok) Die("Cannot load index file " + index_path);
-  fprintf(stderr, "Kmer size: %d, window size: %d.\nLookup table size: %u, occurrence table size: %u.\n", ix.k, ix.w, ix.size, ix.n_occ);
-  if (rc) Die(rc == CMX_ERR_NO_DEVICE ? "chromap-b200: no CUDA device (there is no CPU fallback)" : "chromap-b200: unsupported parameter combination");
-  {
-    int rc_ref = 0;
-    std::thread up_ref([&]() { rc_ref = cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data()); });
-    up_ref.join();  // (the two uploads share the context's error string: one after the other)
-    if (rc_ref) Die(cmx_last_error(ctx));
-    if (cmx_upload_index(ctx, ix.k, ix.w, ix.n_buckets, ix.flags, ix.keys, ix.vals, ix.occ, ix.n_occ)) Die(cmx_last_error(ctx));
-    ix.Close();
-  }
+  const double t_ref = Now();
+  if (cmx_upload_reference(ctx, (uint32_t)ref.names.size(), ref.offsets.data(), ref.concat.data())) Die(cmx_last_error(ctx));
+  fprintf(stderr, "Start-up: context %.2fs, index to the device %.2fs, reference parsed (concurrently) after %.2fs, reference to the device %.2fs.\n", t_ix - t_start,
+          t_ix_done - t_ix, t_ref_parsed - t_start, Now() - t_ref);
+  if (raw_prep.joinable()) raw_prep.join();
   fprintf(stderr, "Reference and index resident on the device after %.2fs.\n", Now() - t_start);
   // scATAC pre-pass (chromap.h:755-761): barcode length from the first record, whitelist, abundance over the first >= 20 M
   // whitelisted barcodes (chromap.cc:364-386, 388-548)
@@ -394,11 +513,10 @@ int main(int argc, char **argv) {
   // double-buffered batch loop: the loader thread prepares batch b+1 while the GPU maps batch b (chromap.h:871-877).
   // Reads are parsed on the device (cmx_ingest_fastq) when the files are plain 4-line FASTQ, else by the host reader.
   SeqReader r1, r2, rb;
-  RawFile g1, g2, gb;
   Batch cur, next;
-  bool gpu_reader = !host_reader && !sam && !paf;  // SAM / PAF keep names (SAM: bases and qualities too) of every read on the host
   auto open_all = [&](bool raw) {
     if (raw) {
+      if (raw_ready) return;  // opened, sized and filled at start-up
       if (!g1.Open(r1_path)) Die("Cannot find sequence file " + r1_path);
       if (!se && !g2.Open(r2_path)) Die("Cannot find sequence file " + r2_path);
       if (sc && !gb.Open(bc_path)) Die("Cannot find sequence file " + bc_path);
@@ -426,8 +544,11 @@ int main(int argc, char **argv) {
     open_all(false);
   }
   std::vector<cmx_pe_record> all, recs;
+  bool recs_pinned = false;
   uint64_t n_pairs = 0, n_mapped = 0, n_unique = 0, n_cand = 0;
   const double t_map = Now();
+  double t_calls = 0, t_collect = 0, t_wait = 0;
+  int n_calls = 0;
   uint32_t read_id = 0;
   std::vector<std::string> all_names, all_names2;
   std::vector<cmx_sam_record> sam_recs, all_sam;
@@ -441,7 +562,15 @@ int main(int argc, char **argv) {
     cur.first_id = read_id;
     parity ^= 1;
     std::thread loader([&]() { load(&next, parity); });
-    recs.resize((size_t)cur.n * p.max_num_best_mappings);
+    if (recs.size() < (size_t)cur.n * p.max_num_best_mappings) {  // the call's output buffer: page-locked, so the records come back at PCIe speed
+      if (recs_pinned) { cmx_host_unregister(recs.data()); recs_pinned = false; }
+      recs.resize((size_t)cur.n * p.max_num_best_mappings);
+      recs_pinned = cmx_host_register(recs.data(), recs.size() * sizeof(cmx_pe_record)) == 0;
+    }
+    if (n_calls == 0 && gpu_reader && g1.file_bytes && g1.first_cut) {  // records of the whole run, from the first call's bytes per pair
+      const double est = (double)g1.file_bytes / (double)g1.first_cut * cur.n * 1.02 + 1024;
+      if (est < 4e9) all.reserve((size_t)est);
+    }
     cmx_batch in{};
     if (cur.dev) in = cur.dev_in;
     else {
@@ -456,6 +585,8 @@ int main(int argc, char **argv) {
     const double t0 = Now();
     if (cmx_map_batch_pe(ctx, &in, &out, nullptr)) Die(cmx_last_error(ctx));
     fprintf(stderr, se ? "Mapped %u reads in %.2fs.\n" : "Mapped %u read pairs in %.2fs.\n", cur.n, Now() - t0);
+    t_calls += Now() - t0; ++n_calls;
+    const double t_col0 = Now();
     if (sam) {
       all_sam.insert(all_sam.end(), sam_recs.begin(), sam_recs.begin() + out.n_records);
       for (uint32_t i = 0; i < cur.n; ++i) { sam_off1.push_back(sam_off1.back() + (cur.o1[i + 1] - cur.o1[i])); if (!se) sam_off2.push_back(sam_off2.back() + (cur.o2[i + 1] - cur.o2[i])); }
@@ -472,10 +603,15 @@ int main(int argc, char **argv) {
     if (sc) { all_bc.insert(all_bc.end(), bc_keys.begin(), bc_keys.begin() + out.n_records); n_bc_in += out.n_barcodes_in_whitelist; n_bc_cor += out.n_barcodes_corrected; }
     n_pairs += cur.n; n_mapped += out.n_mapped_pairs; n_unique += out.n_uniquely_mapped_pairs; n_cand += out.n_candidates;
     read_id += cur.n;
+    const double t_j0 = Now();
+    t_collect += t_j0 - t_col0;
     loader.join();
+    t_wait += Now() - t_j0;
     std::swap(cur, next);
   }
   fprintf(stderr, "Mapped all reads in %.2fs.\n", Now() - t_map);
+  fprintf(stderr, "Mapping phase: %d calls: mapping %.3fs, collecting records %.3fs, waiting for the loader %.3fs (loader: reading + cutting %.3fs, parsing on the device %.3fs, first batch included).\n",
+          n_calls, t_calls, t_collect, t_wait, g_t_fill, g_t_ingest);
   fprintf(stderr, "Number of reads: %llu.\nNumber of mapped reads: %llu.\nNumber of uniquely mapped reads: %llu.\nNumber of candidates: %llu.\n",
           (unsigned long long)((se ? 1 : 2) * n_pairs), (unsigned long long)((se ? 1 : 2) * n_mapped), (unsigned long long)((se ? 1 : 2) * n_unique),
           (unsigned long long)n_cand);

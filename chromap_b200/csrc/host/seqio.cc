@@ -81,6 +81,7 @@ bool SeqReader::Next(std::string *name, std::string *seq, std::string *qual) {
     seq->push_back((char)c);
     GetLine(&line);
     seq->append(line);
+    if (seq->size() > 1 && seq->back() == '\r') seq->pop_back();  // kseq.h:141 tests the whole accumulated string (append mode)
   }
   if (c == '>' || c == '@') pending_ = c;
   if (c != '+') return true;
@@ -88,6 +89,7 @@ bool SeqReader::Next(std::string *name, std::string *seq, std::string *qual) {
   while (qual->size() < seq->size()) {
     if (!GetLine(&line)) break;
     qual->append(line);
+    if (qual->size() > 1 && qual->back() == '\r') qual->pop_back();
   }
   // kseq.h:213-218: a missing or differently long quality string is an error (-2); the reference's loader then stops with
   // "Didn't reach the end of sequence file, which might be corrupted!" (sequence_batch.cc:46-55)
@@ -95,17 +97,77 @@ bool SeqReader::Next(std::string *name, std::string *seq, std::string *qual) {
   return !corrupted_;
 }
 
+// One line appended to *dst (no intermediate string); the same '\r' rule as GetLine.  Returns false at end of file.
+bool SeqReader::AppendLine(std::string *dst) {
+  const size_t before = dst->size();
+  bool any = false;
+  for (;;) {
+    if (pos_ >= end_) {
+      if (eof_) break;
+      const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+      if (n <= 0) { eof_ = true; break; }
+      pos_ = 0;
+      end_ = (size_t)n;
+    }
+    any = true;
+    const void *nlp = memchr(buf_.data() + pos_, '\n', end_ - pos_);
+    const size_t i = nlp ? (size_t)((const unsigned char *)nlp - buf_.data()) : end_;
+    dst->append((const char *)buf_.data() + pos_, i - pos_);
+    if (i < end_) { pos_ = i + 1; break; }
+    pos_ = end_;
+  }
+  if (dst->size() - before > 1 && dst->back() == '\r') dst->pop_back();
+  return any;
+}
+
+// Next() for a reference: the sequence goes straight to the end of *dst (3 Gbp pass through one copy instead of three).
+bool SeqReader::NextAppend(std::string *name, std::string *dst) {
+  name->clear();
+  int c;
+  if (pending_ == 0) {
+    while ((c = GetC()) != -1 && c != '>' && c != '@') {}
+    if (c == -1) return false;
+  }
+  pending_ = 0;
+  std::string line;
+  GetLine(&line);
+  size_t sp = 0;
+  while (sp < line.size() && !isspace((unsigned char)line[sp])) ++sp;
+  name->assign(line, 0, sp);
+  const size_t start = dst->size();
+  while ((c = GetC()) != -1 && c != '>' && c != '+' && c != '@') {
+    if (c == '\n') continue;
+    dst->push_back((char)c);
+    AppendLine(dst);
+    if (dst->size() - start > 1 && dst->back() == '\r') dst->pop_back();
+  }
+  if (c == '>' || c == '@') pending_ = c;
+  if (c != '+') return true;
+  GetLine(&line);  // rest of the '+' line; the quality is consumed by length (kseq.h:205-218)
+  const size_t len = dst->size() - start;
+  size_t q = 0;
+  while (q < len) {
+    if (!GetLine(&line)) break;
+    q += line.size();
+    if (q > 1 && !line.empty() && line.back() == '\r') --q;
+  }
+  if (q != len) corrupted_ = true;
+  return !corrupted_;
+}
+
 bool Reference::Load(const std::string &path) {
   SeqReader rd;
   if (!rd.Open(path)) return false;
   names.clear(); concat.clear(); offsets.assign(1, 0);
-  std::string n, s, q;
-  while (rd.Next(&n, &s, &q)) {
-    if (s.empty()) continue;
+  struct stat st;
+  if (stat(path.c_str(), &st) == 0 && st.st_size > 0) concat.reserve((size_t)st.st_size);  // a plain file: never grown again
+  std::string n;
+  while (rd.NextAppend(&n, &concat)) {
+    if (concat.size() == offsets.back()) continue;  // empty records are skipped (sequence_batch.cc:84-118)
     names.push_back(n);
-    concat.append(s);
     offsets.push_back(concat.size());
   }
+  concat.resize(offsets.back());  // (a record cut short by a corrupted file leaves nothing behind)
   return !names.empty();
 }
 

@@ -17,12 +17,15 @@ class SeqReader {
   void Close();
   // false at end of file or on a corrupted record (Corrupted() tells which).  `qual` stays empty for FASTA.
   bool Next(std::string *name, std::string *seq, std::string *qual);
+  // the same record with its sequence appended to *dst instead of returned (reference loading)
+  bool NextAppend(std::string *name, std::string *dst);
   bool Corrupted() const { return corrupted_; }
   ~SeqReader() { Close(); }
 
  private:
   int GetC();
   bool GetLine(std::string *s);
+  bool AppendLine(std::string *dst);
   gzFile f_ = nullptr;
   std::vector<unsigned char> buf_;
   size_t pos_ = 0, end_ = 0;

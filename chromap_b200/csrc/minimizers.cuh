@@ -229,11 +229,13 @@ __device__ __forceinline__ void minimizer_scan_packed(SeqF SEQ, int len, EmitF E
     } else {
       run = 0;
     }
-    if (run == W + K - 1 && best != NONE && (best >> 20) < (cur >> 20)) {  // ring[1 .. W-1]: the entries before `cur`, oldest first
+    if (run == W + K - 1) {  // once per N-free stretch (the same position in every lane of a warp whose reads have no N)
+      if (best != NONE && (best >> 20) < (cur >> 20)) {  // ring[1 .. W-1]: the entries before `cur`, oldest first
 #pragma unroll
-      for (int q = 1; q < W; ++q) {
-        const u64 x = ring[q];
-        if ((x >> 20) == (best >> 20) && x != best) emit_key(x);
+        for (int q = 1; q < W; ++q) {
+          const u64 x = ring[q];
+          if ((x >> 20) == (best >> 20) && x != best) emit_key(x);
+        }
       }
     }
     const u64 old = ring[0];

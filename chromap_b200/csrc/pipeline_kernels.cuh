@@ -1373,16 +1373,17 @@ __device__ inline void cta_sort_keys(u64 *a, int n, u64 *sm, int sm_cap) {
 // same for (key, tag) pairs under `less`; pads with (pad_key, pad_tag) which must compare greatest.
 template <typename T, typename Less>
 __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_tag, Less less, u64 *smk, T *smt, int sm_cap) {
+  const int NT = blockDim.x;
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int tid = threadIdx.x;
   if (n <= 1) { __syncthreads(); return; }
   if (np2 <= sm_cap) {
-    for (int i = tid; i < np2; i += CTA_NT) { smk[i] = i < n ? k_[i] : pad_key; smt[i] = i < n ? t_[i] : pad_tag; }
+    for (int i = tid; i < np2; i += NT) { smk[i] = i < n ? k_[i] : pad_key; smt[i] = i < n ? t_[i] : pad_tag; }
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+        for (int p = tid; p < (np2 >> 1); p += NT) {
           const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
           const u64 xk = smk[i], yk = smk[l];
           const T xt = smt[i], yt = smt[l];
@@ -1392,16 +1393,16 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
         }
         __syncthreads();
       }
-    for (int i = tid; i < n; i += CTA_NT) { k_[i] = smk[i]; t_[i] = smt[i]; }
+    for (int i = tid; i < n; i += NT) { k_[i] = smk[i]; t_[i] = smt[i]; }
     __syncthreads();
     return;
   }
-  for (int i = n + tid; i < np2; i += CTA_NT) { k_[i] = pad_key; t_[i] = pad_tag; }
+  for (int i = n + tid; i < np2; i += NT) { k_[i] = pad_key; t_[i] = pad_tag; }
   __syncthreads();
   for (int k = 2; k <= np2; k <<= 1) {
     int j = k >> 1;
     for (; j >= sm_cap; j >>= 1) {
-      for (int p = tid; p < (np2 >> 1); p += CTA_NT) {
+      for (int p = tid; p < (np2 >> 1); p += NT) {
         const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;  // j is a power of two
         const u64 xk = k_[i], yk = k_[l];
         const T xt = t_[i], yt = t_[l];
@@ -1413,12 +1414,12 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
     }
     const bool fuse = k <= sm_cap;
     for (int base = 0; base < np2; base += sm_cap) {
-      for (int i = tid; i < sm_cap; i += CTA_NT) { smk[i] = k_[base + i]; smt[i] = t_[base + i]; }
+      for (int i = tid; i < sm_cap; i += NT) { smk[i] = k_[base + i]; smt[i] = t_[base + i]; }
       __syncthreads();
       const int k_lo = fuse ? 2 : k, k_hi = fuse ? sm_cap : k;
       for (int kk = k_lo; kk <= k_hi; kk <<= 1)
         for (int jj = fuse ? (kk >> 1) : j; jj > 0; jj >>= 1) {
-          for (int p = tid; p < (sm_cap >> 1); p += CTA_NT) {
+          for (int p = tid; p < (sm_cap >> 1); p += NT) {
             const int i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1)), l = i + jj;
             const u64 xk = smk[i], yk = smk[l];
             const T xt = smt[i], yt = smt[l];
@@ -1428,7 +1429,7 @@ __device__ inline void cta_sort_pairs(u64 *k_, T *t_, int n, u64 pad_key, T pad_
           }
           __syncthreads();
         }
-      for (int i = tid; i < sm_cap; i += CTA_NT) { k_[base + i] = smk[i]; t_[base + i] = smt[i]; }
+      for (int i = tid; i < sm_cap; i += NT) { k_[base + i] = smk[i]; t_[base + i] = smt[i]; }
       __syncthreads();
     }
     if (fuse) k = sm_cap;
@@ -1625,7 +1626,7 @@ __device__ inline int cta_cluster_par(int e, int need, u32 n_mm, const u64 *hits
   __syncthreads();
   int mine = 0;
   for (int i = r0; i < r1; ++i) mine += vld[i];
-  __shared__ int s_warp[CTA_NT / 32];
+  __shared__ int s_warp[32];  // (up to 1024 threads)
   int total;
   int at = cta_excl_scan(mine, s_warp, &total);
   for (int i = r0; i < r1; ++i)
@@ -1841,48 +1842,54 @@ __global__ void verify_split_kernel(DevParams P, DevRef R, DevBatch B, Scratch S
   Tally t = {e + 1, e + 1, 0, 0};
   auto cless = [](u64 pa, u8 ca, u64 pb, u8 cb) { return ca != cb ? ca > cb : pa < pb; };
   u64 n_verified = 0;
-  int nm[2] = {0, 0};
+  int nm0 = 0, nm1 = 0;
   prefetch_span(read, L);
-  for (int s = 0; s < 2; ++s) {
-    u64 *cp = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
-    u8 *cc = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + s) * c.cc;
-    u64 *mp = S.map_pos + ((size_t)sr * 2 + s) * c.mc;
-    short *me = S.map_err + ((size_t)sr * 2 + s) * c.mc;
-    int *ms = S.map_split + ((size_t)sr * 2 + s) * c.mc;
-    const int nc = rm.n_cand[s];
-    sort_pairs<u8>(cp, cc, nc, cless);
-    u32 threshold = 0;
-    for (int ci = 0; ci < nc; ++ci) {
-      if (cc[ci] < threshold) break;
-      const u64 cpos = cp[ci];
-      const u32 rid = (u32)(cpos >> 32);
-      const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
-      if (!valid_cand(e, R.len[rid], pos, (u32)L)) continue;
-      prefetch_span(R.seq + R.off[rid] + pos - e, L + 2 * e);
-      // one code path for both strands (a warp does not split by strand): base i of the strand's sequence, decoded on the fly
-      const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int i) -> u32 {
-        const u32 b = base_code(read[s ? L - 1 - i : i]);
-        return s ? (b < 4 ? 3u ^ b : 4u) : b;
-      }, L, s);
-      ++n_verified;
-      if (r.nerr <= e) {
-        if (r.nerr < t.min_err) {
-          t.second_min_err = t.min_err; t.n_second_best = t.n_best; t.min_err = r.nerr; t.n_best = 1;
-          threshold = nc > 50 ? (u32)cc[ci] : (u32)cc[ci] / 2;
-        } else if (r.nerr == t.min_err) t.n_best++;
-        else if (r.nerr == t.second_min_err) t.n_second_best++;
-        else if (r.nerr < t.second_min_err) { t.n_second_best = 1; t.second_min_err = r.nerr; }
-        if (nm[s] < c.mc) {
-          mp[nm[s]] = s == 0 ? cpos - (u64)e + (u64)r.endp : cpos - (u64)r.gap;
-          me[nm[s]] = (short)r.nerr;
-          ms[nm[s]] = ((r.actual & 0xff) << 24) | ((r.gap & 0xff) << 16) | (r.rml & 0xffff);
-        }
-        ++nm[s];
+  u64 *const cp0 = S.cand_pos + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *const cp1 = cp0 + c.cc;
+  u8 *const cc0 = S.cand_cnt + (((size_t)sr * 3 + 0) * 2 + 0) * c.cc, *const cc1 = cc0 + c.cc;
+  const int nc0 = rm.n_cand[0], nc1 = rm.n_cand[1];
+  sort_pairs<u8>(cp0, cc0, nc0, cless);
+  sort_pairs<u8>(cp1, cc1, nc1, cless);
+  // The reference walks strand 0's candidates, then strand 1's, with a pruning threshold per strand.  Here ONE loop takes
+  // "this read's next candidate" whatever its strand: the lanes of a warp (different reads) then run the alignment body
+  // together even when their candidates lie on different strands — a read's true locus is on one strand only, so the
+  // two-loop form left half of the lanes idle in each.  Same candidates, same order, same results.
+  int s = 0, ci = 0;
+  u32 threshold = 0;
+  for (;;) {
+    if (s >= 2) break;
+    const int nc = s ? nc1 : nc0;
+    const u32 cnt = ci < nc ? (u32)(s ? cc1 : cc0)[ci] : 0u;
+    if (ci >= nc || cnt < threshold) { ++s; ci = 0; threshold = 0; continue; }  // strand finished or pruned (draft_mapping_generator.cc:412-414)
+    const u64 cpos = (s ? cp1 : cp0)[ci];
+    ++ci;
+    const u32 rid = (u32)(cpos >> 32);
+    const u32 pos = s == 0 ? (u32)cpos : (u32)cpos - (u32)L + 1u;
+    if (!valid_cand(e, R.len[rid], pos, (u32)L)) continue;
+    prefetch_span(R.seq + R.off[rid] + pos - e, L + 2 * e);
+    const SplitResult r = verify_split_candidate(e, R.seq + R.off[rid] + pos - e, [&](int i) -> u32 {
+      const u32 b = base_code(read[s ? L - 1 - i : i]);
+      return s ? (b < 4 ? 3u ^ b : 4u) : b;
+    }, L, s);
+    ++n_verified;
+    if (r.nerr <= e) {
+      if (r.nerr < t.min_err) {
+        t.second_min_err = t.min_err; t.n_second_best = t.n_best; t.min_err = r.nerr; t.n_best = 1;
+        threshold = nc > 50 ? cnt : cnt / 2;
+      } else if (r.nerr == t.min_err) t.n_best++;
+      else if (r.nerr == t.second_min_err) t.n_second_best++;
+      else if (r.nerr < t.second_min_err) { t.n_second_best = 1; t.second_min_err = r.nerr; }
+      const int k = s ? nm1 : nm0;
+      if (k < c.mc) {
+        const size_t mo = ((size_t)sr * 2 + s) * c.mc + k;
+        S.map_pos[mo] = s == 0 ? cpos - (u64)e + (u64)r.endp : cpos - (u64)r.gap;
+        S.map_err[mo] = (short)r.nerr;
+        S.map_split[mo] = ((r.actual & 0xff) << 24) | ((r.gap & 0xff) << 16) | (r.rml & 0xffff);
       }
+      if (s) ++nm1; else ++nm0;
     }
   }
-  if (nm[0] > c.mc || nm[1] > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
-  rm.n_map[0] = nm[0]; rm.n_map[1] = nm[1];
+  if (nm0 > c.mc || nm1 > c.mc) { S.pmeta[slot].status = ST_OVERFLOW; atomicAdd(&ctr->ovf_reason[6], 1ull); return; }
+  rm.n_map[0] = nm0; rm.n_map[1] = nm1;
   rm.min_err = t.min_err; rm.second_min_err = t.second_min_err; rm.n_best = t.n_best; rm.n_second_best = t.n_second_best;
   if (n_verified) agg_add(&ctr->n_verified, n_verified);
 }

@@ -89,6 +89,13 @@ __global__ void pp_key_kernel(int kind, int word, const PpRecord *recs, const u6
   const u32 j = idx[i];
   keys[i] = pp_key_word(kind, word, recs[j], bcs ? bcs[j] : 0ull);
 }
+// largest value of key word 0 (the barcode plays no part in it): sizes the most significant radix passes
+__global__ void pp_max_key0_kernel(int kind, const PpRecord *recs, u64 n, u64 *out) {
+  u64 m = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) m = max(m, pp_key_word(kind, 0, recs[i], 0ull));
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
 __global__ void pp_gather_kernel(const PpRecord *recs, const u64 *bcs, const u32 *idx, u64 n, PpRecord *out, u64 *out_bc) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -1,11 +1,15 @@
 """Multi-GPU layer, one process per GPU: read batches are sharded over ranks (batch b -> rank b mod N, no collective
 inside the hot path); the ONE exchange step is duplicate removal over the whole run (mapping_writer.h:166-376 semantics).
 
-The exchange itself is native: `cmx_dedup_exchange` (include/chromap_b200.h, csrc/exchange.cuh) packs this rank's
-device-resident records into 16-byte tuples, moves them with ONE ncclAllGather over NVLink and decides on the GPU
-which of this rank's records survive.  This module only does the plumbing torch.distributed is here for: handing the
-NCCL unique id of the library's communicator to the other ranks, and bringing the (few) survivors to the rank that
-writes the output.  There is no CPU path: without a GPU the library refuses to create a context.
+Two native forms of that step (include/chromap_b200.h, csrc/exchange.cuh):
+  * `cmx_dedup_shuffle` — a range shuffle (sample sort): every record travels once, by grouped ncclSend / ncclRecv over
+    NVLink, to the rank that owns its key range, which runs the single-GPU post-processing on what it received.  The run's
+    output is the ranks' outputs in rank order; work per rank follows its share of the run.
+  * `cmx_dedup_exchange` — packs this rank's records into 16-byte tuples, moves them with ONE ncclAllGather and decides on
+    the GPU which of this rank's records survive (no record leaves its rank; every rank sorts all tuples).
+This module only does the plumbing torch.distributed is here for: handing the NCCL unique id of the library's
+communicator to the other ranks, and bringing the finished parts to the rank that writes the output.  There is no CPU
+path: without a GPU the library refuses to create a context.
 """
 import numpy as np
 import torch.distributed as dist
@@ -32,6 +36,25 @@ def dedup_exchange(mapper, recs, barcode_keys=None):
     """This rank's records -> this rank's survivors (reference order, num_dups set, MAPQ-filtered, Tn5 not yet applied)
     plus the device-side timing / byte counts of the exchange.  The collective is the library's ncclAllGather."""
     return mapper.dedup_exchange(recs, barcode_keys)
+
+
+def dedup_shuffle(mapper, recs, barcode_keys=None, capacity=None):
+    """This rank's records -> the finished records of this rank's KEY RANGE (sample-sort shuffle over NVLink, then the
+    single-GPU post-processing on the receiving rank): `cmx_dedup_shuffle`.  Work per rank follows its share of the run."""
+    return mapper.dedup_shuffle(recs, barcode_keys, capacity=capacity)
+
+
+def gather_ranges(part, barcode_keys=None, group=None, dst=0):
+    """The ranks' key ranges one after the other in rank order = the run's output (nothing left to sort or shift)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    objs = [None] * world if rank == dst else None
+    dist.gather_object((part.tobytes(), barcode_keys.tobytes() if barcode_keys is not None else None), objs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    recs = np.concatenate([np.frombuffer(o[0], dtype=PE_RECORD) for o in objs])
+    if barcode_keys is not None:
+        return recs, np.concatenate([np.frombuffer(o[1], dtype=np.uint64) for o in objs])
+    return recs
 
 
 def gather_and_finish(params, survivors, barcode_keys=None, group=None, dst=0):

@@ -330,6 +330,24 @@ typedef struct {
  * this rank's survivors in the reference's order, num_dups set, MAPQ-filtered, Tn5 NOT yet applied. */
 int cmx_dedup_exchange(cmx_ctx *ctx, const void *records, const uint64_t *barcode_keys, uint64_t n, int on_device, void *out_records,
                        uint64_t *out_barcode_keys, uint64_t *n_out, cmx_exchange_stats *stats);
+/* The same step as a range shuffle (a sample sort): the records' key word rid << 32 | fragment_start is range-partitioned over
+ * the ranks (splitters from an all-gathered sample of 4096 keys per rank), every record travels once — grouped ncclSend /
+ * ncclRecv — to the rank that owns its key range, and that rank runs the single-GPU post-processing (cmx_postprocess_gpu's
+ * kernels) on what it received.  Duplicates agree in that key word, so a group never straddles two ranks.  Work per rank is
+ * proportional to its share of the run, whereas cmx_dedup_exchange sorts the tuples of ALL ranks on every rank.
+ * out_records / out_barcode_keys (capacity out_capacity, same kind of memory as the input): the records of THIS RANK'S KEY
+ * RANGE in the reference's order, num_dups set, MAPQ-filtered, Tn5 applied (mapping_writer.h:254-287); the run's output is the
+ * ranks' outputs one after the other in rank order.  CMX_ERR_INVALID with *n_out = the needed capacity if out_capacity is
+ * too small (nothing is written then). */
+typedef struct {
+  float partition_ms, shuffle_ms, postprocess_ms; /* CUDA events on the context's stream */
+  uint32_t n_ranks;
+  uint64_t bytes_sent, bytes_received;            /* record bytes that left / reached this rank over NVLink */
+  uint64_t n_received;                            /* records in this rank's key range before duplicate removal */
+  uint64_t n_global;                              /* records of all ranks */
+} cmx_shuffle_stats;
+int cmx_dedup_shuffle(cmx_ctx *ctx, const void *records, const uint64_t *barcode_keys, uint64_t n, int on_device, void *out_records,
+                      uint64_t *out_barcode_keys, uint64_t out_capacity, uint64_t *n_out, cmx_shuffle_stats *stats);
 /* After the survivors of all ranks have been brought together (any transport; they are a small fraction of the run): the
  * reference's order and the deferred Tn5 shift (mapping_writer.h:285-287).  Host only (no device needed), in place. */
 int cmx_exchange_finish(const cmx_params *params, cmx_pe_record *records, uint64_t *barcode_keys, uint64_t n);

@@ -65,3 +65,42 @@ def dedup_exchange(recs, params, group=None):
     if params.remove_pcr_duplicates:
         out["num_dups"] = torch.clamp(gsize, max=255)[mine].numpy().astype(np.uint8)
     return out
+
+
+SH_SAMPLE = 4096
+_PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def shuffle_partition(recs, group=None):
+    """exchange.cuh's range partition: splitters from an all-gathered sample of SH_SAMPLE keys per rank, destination of a
+    record = number of splitters <= its key word a = rid << 32 | fragment_start.  Returns (dest per record, splitters)."""
+    world = dist.get_world_size(group)
+    a = (recs["rid"].astype(np.uint64) << np.uint64(32)) | recs["fragment_start"].astype(np.uint64)
+    n = len(a)
+    take = min(n, SH_SAMPLE)
+    samp = np.full(SH_SAMPLE, _PAD, dtype=np.uint64)
+    if take:
+        samp[:take] = a[(np.arange(take, dtype=np.uint64) * np.uint64(n)) // np.uint64(take)]
+    t = torch.from_numpy(samp.view(np.int64))
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    alls = np.sort(torch.cat(out).numpy().view(np.uint64))
+    valid = int(np.searchsorted(alls, _PAD, side="left"))
+    split = np.array([alls[valid * j // world] if valid else 0 for j in range(1, world)], dtype=np.uint64)
+    return np.searchsorted(split, a, side="right").astype(np.int64), split
+
+
+def dedup_shuffle(recs, params, postprocess, group=None):
+    """Test double of cmx_dedup_shuffle: records travel to the rank that owns their key range, `postprocess` (the
+    single-process low-memory post-processing) runs there.  The ranks' results in rank order are the run's output."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dest, _ = shuffle_partition(recs, group)
+    order = np.argsort(dest, kind="stable")
+    parts = [recs[order][dest[order] == d] for d in range(world)]
+    got = [None] * world
+    for src in range(world):  # the grouped send / recv, spelled as one scatter per source rank
+        box = [None]
+        dist.scatter_object_list(box, [p.tobytes() for p in parts] if rank == src else None, src=src, group=group)
+        got[src] = np.frombuffer(box[0], dtype=recs.dtype)
+    mine = np.concatenate(got) if got else recs[:0]
+    return postprocess(mine)

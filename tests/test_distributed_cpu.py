@@ -46,12 +46,18 @@ for preset, kw in (("chip", {}), ("atac", {}), ("", dict(low_memory_mode=1, mapq
         recs_all = recs if preset != "atac" else recs[np.array([cd.shard_owner(int(b), world) != world - 1 for b in recs["read_id"] // batch])]
     surv = xp.dedup_exchange(mine, p)
     final = cd.gather_and_finish(p, surv)                    # cmx_exchange_finish: order + deferred Tn5
+    # the range-shuffle form of the same step: sample-sort partition, records travel once, ordinary post-processing on the
+    # receiving rank, the ranks' parts in rank order are the run's output
+    op = orc.make_params(preset, **kw)
+    part = xp.dedup_shuffle(mine, p, lambda r: orc.postprocess(op, r))
+    ranged = cd.gather_ranges(part)
     if rank == 0:
-        op = orc.make_params(preset, **kw)
         want = orc.postprocess(op, recs_all)
         assert len(final) == len(want), (preset, len(final), len(want))
+        assert len(ranged) == len(want), (preset, len(ranged), len(want))
         for f in cb.PE_RECORD.names:
             assert np.array_equal(final[f], want[f]), (preset, f)
+            assert np.array_equal(ranged[f], want[f]), ("shuffle", preset, f)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
@@ -72,5 +78,5 @@ def test_dedup_exchange_gloo(tmp_path, world):
 def test_exchange_entry_points_refuse_without_a_communicator():
     import chromap_b200 as cb
     L = cb.load_library()
-    for name in ("cmx_comm_unique_id", "cmx_comm_init", "cmx_comm_destroy", "cmx_dedup_exchange", "cmx_exchange_finish"):
+    for name in ("cmx_comm_unique_id", "cmx_comm_init", "cmx_comm_destroy", "cmx_dedup_exchange", "cmx_dedup_shuffle", "cmx_exchange_finish"):
         assert hasattr(L, name)

@@ -518,6 +518,17 @@ def test_native_dedup_exchange_world_of_one_equals_host_postprocess(bc, dedup, t
             got = cb.exchange_finish(p, surv)
         assert st["n_global"] == n and st["n_ranks"] == 1
         assert_same_records(got, want)
+        # the range-shuffle form (cmx_dedup_shuffle): with one rank the whole key range is this rank's
+        if bc:
+            part, pbc, sst = m.dedup_shuffle(recs, bcs)
+            assert np.array_equal(wbc, pbc)
+        else:
+            part, sst = m.dedup_shuffle(recs)
+        assert sst["n_global"] == n and sst["n_received"] == n and sst["n_ranks"] == 1 and sst["bytes_sent"] == 0
+        assert_same_records(part, want)
+        if n >= 1000:  # too small an output buffer is refused, with the needed capacity
+            with pytest.raises(cb.CmxError):
+                m.dedup_shuffle(recs, bcs if bc else None, capacity=len(want) - 1)
     m.comm_destroy()
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU end-to-end check (run under torchrun on N GPUs): every rank maps the reference batches it owns
-(batch b -> rank b mod N), the ranks run the one NCCL exchange (duplicate removal, cmx_dedup_exchange),
-rank 0 writes the BED — which must equal the single-process result byte for byte.
+(batch b -> rank b mod N), the ranks run the one NCCL exchange (duplicate removal) in both its forms — cmx_dedup_exchange
+(all-gather of tuples) and cmx_dedup_shuffle (range shuffle of records) — rank 0 writes the BED — which must equal the single-process result byte for byte.
 
   torchrun --nproc-per-node 2 tools/multi_gpu_map.py --dir tests/golden/synth_small --preset chip --batch 1000
 """
@@ -48,10 +48,14 @@ def main():
     cd.init_comm(m)                                       # the library's own NCCL communicator
     surv, xst = cd.dedup_exchange(m, mine)                # pack -> ONE ncclAllGather -> sort / decide on the GPU
     final = cd.gather_and_finish(p, surv)
+    part, sst = cd.dedup_shuffle(m, mine, capacity=2 * n + 4096)  # range shuffle: records travel once, post-processing on the owner
+    ranged = cd.gather_ranges(part)
     if rank == 0:
         print("multi_gpu_map: exchange", xst, flush=True)
+        print("multi_gpu_map: shuffle", sst, flush=True)
     if rank == 0:
         bed = m.format_bed(final)
+        bed_sh = m.format_bed(ranged)
         # single-process result on this rank's GPU for comparison
         allr = []
         for b0 in range(0, n, a.batch):
@@ -59,9 +63,9 @@ def main():
             r, _ = m.map_batch(s1[o1[b0]:o1[b1]], o1[b0:b1 + 1] - o1[b0], s2[o2[b0]:o2[b1]], o2[b0:b1 + 1] - o2[b0], first_read_id=b0)
             allr.append(r.copy())
         want = m.format_bed(m.postprocess(np.concatenate(allr)))
-        ok = bed == want
-        print("multi_gpu_map: world=%d records=%d bed_md5=%s single_md5=%s %s" % (world, len(final), hashlib.md5(bed).hexdigest(),
-              hashlib.md5(want).hexdigest(), "IDENTICAL" if ok else "DIFFERENT"), flush=True)
+        ok = bed == want and bed_sh == want
+        print("multi_gpu_map: world=%d records=%d bed_md5=%s shuffle_md5=%s single_md5=%s %s" % (world, len(final), hashlib.md5(bed).hexdigest(),
+              hashlib.md5(bed_sh).hexdigest(), hashlib.md5(want).hexdigest(), "IDENTICAL" if ok else "DIFFERENT"), flush=True)
         if not ok:
             sys.exit(1)
     dist.barrier()

@@ -124,7 +124,9 @@ def main():
                        lines=sum(1 for _ in open(out_ref, "rb")), reference_wall_s=round(t_ref, 1), ours_wall_s=round(t_ours, 1),
                        reference_mapping=[l for l in r1.stderr.splitlines() if l.startswith("Mapped all")],
                        ours_mapping=[l for l in r2.stderr.splitlines() if l.startswith("Mapped all")],
-                       ours_startup=[l for l in r2.stderr.splitlines() if l.startswith("Reference and index resident")],
+                       ours_startup=[l for l in r2.stderr.splitlines() if l.startswith("Reference and index resident") or l.startswith("Start-up:")],
+                       ours_phases=[l for l in r2.stderr.splitlines() if l.startswith("Mapping phase:") or l.startswith("Mapped ") and "read pairs in" in l
+                                    or l.startswith("Sorted") or l.startswith("Post") or l.startswith("Wrote") or l.startswith("Output")],
                        ours_total=[l for l in r2.stderr.splitlines() if l.startswith("Total time")],
                        reference_total=[l for l in r1.stderr.splitlines() if l.startswith("Total time")])
         else:
