@@ -200,6 +200,12 @@ int cmx_create(cmx_ctx **out, int device, const cmx_params *params) {
   ctx->device = device;
   ctx->params = *params;
   CUC(cudaSetDevice(device));
+  // The path's HBM traffic is random 16-byte table slots and short occurrence runs; CMX_L2_FETCH = 32 | 64 | 128 sets the L2
+  // fetch-granularity hint for an A/B run (unset: the driver's default — the setting every committed number was measured with).
+  if (const char *ev = getenv("CMX_L2_FETCH")) {
+    const int gran = atoi(ev);
+    if (gran == 32 || gran == 64 || gran == 128) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran) != cudaSuccess) cudaGetLastError(); }
+  }
   CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));

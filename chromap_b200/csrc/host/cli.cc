@@ -165,7 +165,9 @@ struct RawFile {
         *n = (uint32_t)whole;
         return whole ? e : 0;
       }
-      const size_t want = chunk ? chunk : (f ? (32u << 20) : (128u << 20));
+      size_t want = chunk ? chunk : (f ? (32u << 20) : (128u << 20));
+      if (!f && !chunk && file_bytes)  // a plain file: never ask for more than is left (+ a few bytes, so that the end is seen as a short read)
+        want = std::max<size_t>(64, std::min(want, file_bytes - std::min(file_bytes, fpos) + 8));
       Reserve(have + want + 1);
       if (f) {
         const long got = gzread(f, buf.data() + have, (unsigned)want);

@@ -160,9 +160,6 @@ __global__ void __launch_bounds__(SF_NT, 5) seed_front_kernel(DevParams P, DevIn
       u64 *kcol = kbuf + tid;
       const int key_rows = P.k <= 22 ? SF_KEY_ROWS : 0;  // hash << 20 | position must fit 64 bits
       auto emit = [&](u64 h, u32 p) {
-        // the table slot this minimizer will probe is requested into L2 the moment the minimizer is known: by the time the
-        // scan of the read is over, the probe below finds it there instead of waiting on HBM
-        prefetch_l2(&ix.slots[(h * 0x9E3779B97F4A7C15ull) >> ix.shift]);
         if (n_mm < key_rows) kcol[n_mm * SF_NT] = (h << 20) | p;  // p < 2^20 (reads are far shorter than 2^19), h < 2^44
         else if (n_mm < maxmm) { mmv[(size_t)n_mm * 32] = h; mmp[(size_t)n_mm * 32] = p; }
         ++n_mm;

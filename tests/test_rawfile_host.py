@@ -33,12 +33,18 @@ int main() {
     if (!ref.empty() && ref.back() != '\n') ref.push_back('\n');
     RawFile rf;
     if (!rf.Open(path)) { printf("open failed\n"); return 2; }
-    rf.chunk = 64 + g() %% 8192;
+    rf.chunk = it %% 3 == 0 ? 0 : 64 + g() %% 8192;   // 0: the production chunk size (clamped to what is left of the file)
+    if (it %% 6 == 0) rf.Prepare(1 + g() %% 500);       // the start-up sizing from the head of the file
     size_t pos = 0;                               // bytes handed out so far
     for (int call = 0; call < 1000; ++call) {
       const uint32_t want = 1 + g() %% 97;
       uint32_t n = 0;
       const uint64_t bytes = rf.Fill(want, &n);
+      if (call == 0 && it %% 2 == 0) {  // the start-up thread fills the first call ahead of time: asking again must give the same answer
+        uint32_t n2 = 0;
+        const uint64_t b2 = rf.Fill(want, &n2);
+        if (b2 != bytes || n2 != n) { if (bad < 5) printf("REFILL it=%%d %%llu/%%llu %%u/%%u\n", it, (unsigned long long)b2, (unsigned long long)bytes, n2, n); ++bad; }
+      }
       // the walk: up to `want` records = 4 lines each starting at pos
       size_t p = pos; uint32_t rn = 0;
       while (rn < want) {

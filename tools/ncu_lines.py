@@ -17,7 +17,7 @@ for r in rows:
     if r[0] == "File Path":
         cur_file = r[1].split("/")[-1]
     elif r[0] == "Function Name":
-        base = r[1].split("(")[0]
+        base = r[1].replace("void ", "").split("(")[0].split("<")[0]
         k = 0
         while (base, k, cur_file) in seen:
             k += 1
