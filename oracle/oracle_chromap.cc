@@ -1597,6 +1597,10 @@ int orc_minimizers(const char *seq, uint32_t len, uint32_t seq_index, int k, int
 }
 int orc_banded_align(int e, const char *pattern, const char *text, int read_len, int *end_pos) { return banded_align(e, pattern, text, read_len, end_pos); }
 void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len, int *start_pos) { banded_traceback(e, min_errors, pattern, text, read_len, start_pos); }
+// the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
+int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {
+  return from_3_end ? align_dropoff_3end(e, pattern, text, read_len, end_pos, read_len_out) : align_dropoff(e, pattern, text, read_len, end_pos, read_len_out);
+}
 
 orc_mapper *orc_mapper_create(const orc_params *p, const orc_index *ix, const orc_reference *ref) {
   if (p->error_threshold >= 16) return nullptr;

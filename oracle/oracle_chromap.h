@@ -83,6 +83,7 @@ int orc_banded_align(int e, const char *pattern, const char *text, int read_len,
 // alignment.cc:656-718.
 void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len,
                           int *start_pos);
+int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out);
 
 // One PE record as emitted by mapping_generator.cc:110-123 (before sort/dedup).
 typedef struct {
