@@ -20,14 +20,14 @@ static std::string make_text(std::mt19937 &g, int n_rec, int tail_lines, bool fi
   if (!final_newline && !t.empty() && t.back() == '\n') t.pop_back();
   return t;
 }
-int main() {
+int main(int argc, char **argv) {
   std::mt19937 g(5);
   long bad = 0, cases = 0;
   for (int it = 0; it < 300; ++it) {
     const int n_rec = (int)(g() %% 400), tail = (int)(g() %% 4);
     const bool fin = g() %% 2;
     std::string text = make_text(g, n_rec, tail, fin);
-    const std::string path = "/tmp/cmx_rawfile_test.fq";
+    const std::string path = argc > 1 ? argv[1] : "/tmp/cmx_rawfile_test.fq";
     FILE *f = fopen(path.c_str(), "wb"); fwrite(text.data(), 1, text.size(), f); fclose(f);
     std::string ref = text;                       // what the reader works on: the text with its last newline made up
     if (!ref.empty() && ref.back() != '\n') ref.push_back('\n');
@@ -78,7 +78,7 @@ def test_raw_fastq_reader_cuts_like_a_line_walk(tmp_path):
     lib = os.path.join(ROOT, "chromap_b200")
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), str(src), os.path.join(ROOT, "chromap_b200/csrc/host/seqio.cc"), "-L" + lib, "-lchromap_b200",
                     "-Wl,-rpath," + lib, "-lz", "-lpthread"], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([str(exe), str(tmp_path / "reads.fq")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bad=0" in r.stdout
 
@@ -89,7 +89,7 @@ REF_SRC = r'''
 #include <cstring>
 #include <random>
 using namespace cmxhost;
-int main() {
+int main(int argc, char **argv) {
   std::mt19937 g(9);
   long bad = 0;
   for (int it = 0; it < 400; ++it) {
@@ -112,7 +112,7 @@ int main() {
       if (fastq) { t += "+"; nl(); for (size_t i = 0; i < seq.size(); ++i) t.push_back('I'); nl(); }
     }
     if (g() %% 5 == 0 && !t.empty() && t.back() == '\n') t.pop_back();
-    const std::string path = "/tmp/cmx_ref_test.fa";
+    const std::string path = argc > 1 ? argv[1] : "/tmp/cmx_ref_test.fa";
     FILE *f = fopen(path.c_str(), "wb"); fwrite(t.data(), 1, t.size(), f); fclose(f);
     // the record-at-a-time reader (the one the read files go through) is the specification
     std::vector<std::string> names; std::string concat; std::vector<uint64_t> offs{0};
@@ -135,6 +135,6 @@ def test_reference_loader_equals_record_reader(tmp_path):
     src.write_text(REF_SRC % dict(root=ROOT))
     exe = tmp_path / "r"
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), str(src), os.path.join(ROOT, "chromap_b200/csrc/host/seqio.cc"), "-lz"], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([str(exe), str(tmp_path / "ref.fa")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bad=0" in r.stdout
