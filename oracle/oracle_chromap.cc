@@ -251,16 +251,18 @@ static void gen_candidates(const orc_params &P, const orc_index &ix, ReadState &
 }
 
 // index.cc:351-489: mate-guided lookup on one strand.  Returns +max count or -max count on bail-out.
-static int rescue_hits(const orc_params &P, const orc_index &ix, int strand, u32 range,
-                       const std::vector<Mm> &mm, const std::vector<Cand> &mate, u32 &rep_len,
-                       std::vector<u64> &hits) {
+// probe(i, key, val, hit): the table entry of minimizer i (false = absent) and its read-side hit word (position << 1 | strand);
+// the mapper probes its khash index, the device tests hand in records that were probed elsewhere.
+template <typename Probe>
+static int rescue_core(int k, int w, int max_seed_freq0, int min_num_seeds, int strand, u32 range, size_t n_mm, Probe probe,
+                       const u64 *occ, const std::vector<Cand> &mate, u32 &rep_len, std::vector<u64> &hits) {
   int max_cnt = 0, n_best = 0;
   for (const Cand &c : mate) {
     if (c.cnt > max_cnt) { max_cnt = c.cnt; n_best = 1; }
     else if (c.cnt == max_cnt) ++n_best;
   }
-  if (n_best >= 300 || mate.size() > (size_t)P.max_seed_freq0 ||
-      (max_cnt <= P.min_num_seeds && n_best >= 200))
+  if (n_best >= 300 || mate.size() > (size_t)max_seed_freq0 ||
+      (max_cnt <= min_num_seeds && n_best >= 200))
     return -max_cnt;
   std::vector<std::pair<u64, u64>> win;
   for (const Cand &c : mate)
@@ -273,12 +275,12 @@ static int rescue_hits(const orc_params &P, const orc_index &ix, int strand, u32
   }
   win.resize(nw);
   RepStats st;
-  for (const Mm &m : mm) {
-    u64 key, val;
-    if (!ix.lookup(m.hash, key, val)) continue;
+  for (size_t mi = 0; mi < n_mm; ++mi) {
+    u64 key, val, mhit;
+    if (!probe(mi, key, val, mhit)) continue;
     if (key & 1) {
-      const bool same = ((val ^ m.hit) & 1) == 0;
-      if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(ix.k, val, m.hit));
+      const bool same = ((val ^ mhit) & 1) == 0;
+      if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(k, val, mhit));
       continue;
     }
     const u32 off = (u32)(val >> 32), n = (u32)val;
@@ -288,24 +290,31 @@ static int rescue_hits(const orc_params &P, const orc_index &ix, int strand, u32
       const u64 lo = win[bi].first;
       while (l <= r) {  // index.cc:447-459 — `mid` is the last probe, not a lower bound
         mid = (l + r) / 2;
-        const u64 p = ix.occ[off + mid] >> 1;
+        const u64 p = occ[off + mid] >> 1;
         if (p < lo) l = mid + 1;
         else if (p > lo) r = mid - 1;
         else break;
       }
       prev_l = mid;
       for (u32 oi = (u32)mid; oi < n; ++oi) {
-        const u64 rh = ix.occ[off + oi];
+        const u64 rh = occ[off + oi];
         if ((rh >> 1) > win[bi].second) break;
-        const bool same = ((rh ^ m.hit) & 1) == 0;
-        if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(ix.k, rh, m.hit));
+        const bool same = ((rh ^ mhit) & 1) == 0;
+        if ((same && strand == 0) || (!same && strand == 1)) hits.push_back(hit_to_candidate(k, rh, mhit));
       }
     }
-    if (n >= (u32)P.max_seed_freq0) rep_update(ix.k, ix.w, (u32)(m.hit >> 1), st);
+    if (n >= (u32)max_seed_freq0) rep_update(k, w, (u32)(mhit >> 1), st);
   }
   std::sort(hits.begin(), hits.end());
   rep_len = st.len;
   return max_cnt;
+}
+static int rescue_hits(const orc_params &P, const orc_index &ix, int strand, u32 range,
+                       const std::vector<Mm> &mm, const std::vector<Cand> &mate, u32 &rep_len,
+                       std::vector<u64> &hits) {
+  return rescue_core(ix.k, ix.w, P.max_seed_freq0, P.min_num_seeds, strand, range, mm.size(),
+                     [&](size_t i, u64 &key, u64 &val, u64 &mhit) { mhit = mm[i].hit; return ix.lookup(mm[i].hash, key, val); },
+                     ix.occ.data(), mate, rep_len, hits);
 }
 
 // candidate_processor.cc:345-414.
@@ -1597,6 +1606,23 @@ int orc_minimizers(const char *seq, uint32_t len, uint32_t seq_index, int k, int
 }
 int orc_banded_align(int e, const char *pattern, const char *text, int read_len, int *end_pos) { return banded_align(e, pattern, text, read_len, end_pos); }
 void orc_banded_traceback(int e, int min_errors, const char *pattern, const char *text, int read_len, int *start_pos) { banded_traceback(e, min_errors, pattern, text, read_len, start_pos); }
+// the mate-guided lookup (index.cc:351-489) over records that were probed elsewhere, for tests of the device formulations:
+// kind[i] 0 absent / 1 singleton / 2 multi, val[i] the table value, mm_hit[i] = read position << 1 | strand
+int orc_rescue_test(int k, int w, int max_seed_freq0, int min_num_seeds, int strand, uint32_t range, int n_mm, const uint8_t *kind,
+                    const uint64_t *val, const uint64_t *mm_hit, const uint64_t *occ, const uint64_t *mate_pos, const uint8_t *mate_cnt,
+                    int n_mate, uint32_t *rep_len, uint64_t *hits, int cap, int *nh) {
+  std::vector<Cand> mate((size_t)n_mate);
+  for (int i = 0; i < n_mate; ++i) { mate[i].pos = mate_pos[i]; mate[i].cnt = mate_cnt[i]; }
+  std::vector<u64> out;
+  u32 rl = 0;
+  const int r = rescue_core(k, w, max_seed_freq0, min_num_seeds, strand, range, (size_t)n_mm,
+                            [&](size_t i, u64 &key, u64 &v, u64 &mhit) { mhit = mm_hit[i]; v = val[i]; key = kind[i] == 1 ? 1 : 0; return kind[i] != 0; },
+                            occ, mate, rl, out);
+  *rep_len = rl;
+  *nh = (int)out.size();
+  for (size_t i = 0; i < out.size() && (int)i < cap; ++i) hits[i] = out[i];
+  return r;
+}
 // the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
 int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {
   return from_3_end ? align_dropoff_3end(e, pattern, text, read_len, end_pos, read_len_out) : align_dropoff(e, pattern, text, read_len, end_pos, read_len_out);
