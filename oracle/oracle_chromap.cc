@@ -1623,6 +1623,35 @@ int orc_rescue_test(int k, int w, int max_seed_freq0, int min_num_seeds, int str
   for (size_t i = 0; i < out.size() && (int)i < cap; ++i) hits[i] = out[i];
   return r;
 }
+// GenerateDraftMappings (non-split, draft_mapping_generator.cc:9-357) for one read over given candidate lists, for tests of
+// the device formulations.  ref: one sequence of ref_len bases (followed by >= 64 NUL); cand_pos / cand_cnt: [2][n_cand[s]]
+// laid out strand after strand; out_pos / out_err: [2][cap].  stats: min_err, n_best, second_min_err, n_second_best.
+void orc_verify_test(int e, const char *ref_seq, uint32_t ref_len, const char *read, uint32_t L, int n_mm, const int *n_cand,
+                     const uint64_t *cand_pos, const uint8_t *cand_cnt, int cap, int *n_map, uint64_t *out_pos, int16_t *out_err, int *stats) {
+  orc_params P;
+  orc_default_params(&P);
+  P.error_threshold = e;
+  orc_reference ref;
+  ref.names.push_back("t");
+  ref.lens.push_back(ref_len);
+  std::string sq(ref_seq, ref_len);
+  sq.append(64, '\0');
+  ref.seqs.push_back(std::move(sq));
+  ReadState rs;
+  rs.reset();
+  rs.mm.resize((size_t)n_mm);
+  size_t o = 0;
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < n_cand[s]; ++i, ++o) { Cand c; c.pos = cand_pos[o]; c.cnt = cand_cnt[o]; rs.cand[s].push_back(c); }
+  std::string neg;
+  revcomp(read, L, neg);
+  verify_read(P, ref, read, neg, L, rs);
+  for (int s = 0; s < 2; ++s) {
+    n_map[s] = (int)rs.map[s].size();
+    for (size_t i = 0; i < rs.map[s].size() && (int)i < cap; ++i) { out_pos[(size_t)s * cap + i] = rs.map[s][i].pos; out_err[(size_t)s * cap + i] = (int16_t)rs.map[s][i].err; }
+  }
+  stats[0] = rs.min_err; stats[1] = rs.n_best; stats[2] = rs.second_min_err; stats[3] = rs.n_second_best;
+}
 // the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
 int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {
   return from_3_end ? align_dropoff_3end(e, pattern, text, read_len, end_pos, read_len_out) : align_dropoff(e, pattern, text, read_len, end_pos, read_len_out);

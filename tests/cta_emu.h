@@ -22,7 +22,7 @@ using std::max;
 using std::min;
 
 struct EmuDim { int x; };
-static thread_local EmuDim threadIdx, blockDim;
+static thread_local EmuDim threadIdx, blockDim, blockIdx;
 
 struct EmuCta {
   int nt = 0;
@@ -49,6 +49,19 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T x, int o) { con
 template <typename T> static inline T __shfl_down_sync(unsigned, T x, int o) { const int l = threadIdx.x & 31; return emu_shfl(x, l + o < 32 ? l + o : -1); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T x, int o) { return emu_shfl(x, (threadIdx.x & 31) ^ o); }
 template <typename T> static inline T __shfl_sync(unsigned, T x, int src) { return emu_shfl(x, src & 31); }
+
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+  const int w = threadIdx.x >> 5;
+  g_cta->xch[threadIdx.x] = pred ? 1u : 0u;
+  pthread_barrier_wait(&g_cta->warp[w]);
+  unsigned m = 0;
+  const int n_in_warp = std::min(32, g_cta->nt - w * 32);
+  for (int l = 0; l < n_in_warp; ++l) m |= (unsigned)(g_cta->xch[w * 32 + l] & 1u) << l;
+  pthread_barrier_wait(&g_cta->warp[w]);
+  return m;
+}
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 // run `body` as a CTA of nt threads (nt a multiple of 32)
 static inline void emu_launch(int nt, const std::function<void()> &body) {
