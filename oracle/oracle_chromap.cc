@@ -1652,6 +1652,26 @@ void orc_verify_test(int e, const char *ref_seq, uint32_t ref_len, const char *r
   }
   stats[0] = rs.min_err; stats[1] = rs.n_best; stats[2] = rs.second_min_err; stats[3] = rs.n_second_best;
 }
+// best-pair statistics of one read pair (mapping_generator.h:160-197 + :346-484, non-split) over given draft mappings, for
+// tests of the device formulations.  n_map: {mate 1 +, mate 1 -, mate 2 +, mate 2 -}; pos / err: the four lists one after the
+// other, in any order (SortMappingsByPositions is applied here).  stats: min_sum, n_best, second_min_sum, n_second_best.
+void orc_pair_stats_test(int e, int max_insert_size, int min_read_length, uint32_t L1, uint32_t L2, const int *n_map, const uint64_t *pos,
+                         const int16_t *err, int *stats) {
+  orc_params P;
+  orc_default_params(&P);
+  P.error_threshold = e; P.max_insert_size = max_insert_size; P.min_read_length = min_read_length;
+  std::vector<Draft> m[4];
+  size_t o = 0;
+  for (int q = 0; q < 4; ++q)
+    for (int i = 0; i < n_map[q]; ++i, ++o) m[q].push_back({(int)err[o], pos[o]});
+  auto by_pos = [](const Draft &a, const Draft &b) { return a.pos != b.pos ? a.pos < b.pos : a.err < b.err; };
+  for (int q = 0; q < 4; ++q) std::sort(m[q].begin(), m[q].end(), by_pos);
+  PairState ps;
+  ps.min_sum = 2 * e + 1; ps.n_best = 0; ps.second_min_sum = ps.min_sum; ps.n_second_best = 0;
+  pair_dir(P, 0, L1, L2, m[0], m[3], ps, ps.best[0]);
+  pair_dir(P, 1, L1, L2, m[1], m[2], ps, ps.best[1]);
+  stats[0] = ps.min_sum; stats[1] = ps.n_best; stats[2] = ps.second_min_sum; stats[3] = ps.n_second_best;
+}
 // the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
 int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {
   return from_3_end ? align_dropoff_3end(e, pattern, text, read_len, end_pos, read_len_out) : align_dropoff(e, pattern, text, read_len, end_pos, read_len_out);
