@@ -1119,54 +1119,11 @@ struct PafRec {  // PAFMapping / PairedPAFMapping (paf_mapping.h) as the referen
 };
 struct SamSink { std::vector<SamRec> *recs; const char *name1, *qual1, *name2, *qual2; std::vector<PafRec> *paf = nullptr; };
 
-static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_reference &ref, std::mt19937 &gen,
-                        const char *s1, u32 len1, const char *s2, u32 len2, u32 read_id, u32 pair_index,
-                        orc_pe_record *out, int cap, orc_pair_trace *tr, const SamSink *sam = nullptr) {
-  if (tr) memset(tr, 0, sizeof(*tr));
-  if (len1 < (u32)P.min_read_length || len2 < (u32)P.min_read_length) return 0;
-  std::string r[2] = {std::string(s1, len1), std::string(s2, len2)}, neg[2];
-  revcomp(r[0].data(), len1, neg[0]);
-  revcomp(r[1].data(), len2, neg[1]);
-  if (P.trim_adapters) trim_adapters(P, r[0], r[1], neg[0], neg[1]);
-  const u32 L[2] = {(u32)r[0].size(), (u32)r[1].size()};
-  if (tr) { tr->trimmed_len[0] = L[0]; tr->trimmed_len[1] = L[1]; }
-  ReadState rs[2];
-  rs[0].reset(); rs[1].reset();
-  gen_minimizers(r[0].data(), L[0], pair_index, ix.k, ix.w, rs[0].mm);
-  gen_minimizers(r[1].data(), L[1], pair_index, ix.k, ix.w, rs[1].mm);
-  if (tr) { tr->n_minimizers[0] = rs[0].mm.size(); tr->n_minimizers[1] = rs[1].mm.size(); }
-  if (rs[0].mm.empty() || rs[1].mm.empty()) return 0;
-  gen_candidates(P, ix, rs[0]);
-  gen_candidates(P, ix, rs[1]);
-  if (tr) for (int m = 0; m < 2; ++m) { tr->n_pos_candidates_gen[m] = rs[m].cand[0].size(); tr->n_neg_candidates_gen[m] = rs[m].cand[1].size(); }
-  int sup = 0;
-  if (!P.split_alignment) sup = supplement(P, ix, rs);
-  if (tr) tr->supplement_result = sup;
-  size_t nc1 = rs[0].cand[0].size() + rs[0].cand[1].size(), nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
-  if (nc1 > 0 && nc2 > 0 && !P.split_alignment) {
-    for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) { rs[m].cand[s].swap(rs[m].buf[s]); rs[m].cand[s].clear(); }
-    pe_filter_dir(P.max_insert_size, rs[0].buf[0], rs[1].buf[1], rs[0].cand[0], rs[1].cand[1]);
-    pe_filter_dir(P.max_insert_size, rs[0].buf[1], rs[1].buf[0], rs[0].cand[1], rs[1].cand[0]);
-    nc1 = rs[0].cand[0].size() + rs[0].cand[1].size();
-    nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
-  }
-  if (tr) for (int m = 0; m < 2; ++m) {
-    tr->n_pos_candidates[m] = rs[m].cand[0].size(); tr->n_neg_candidates[m] = rs[m].cand[1].size();
-    tr->repetitive_seed_length[m] = rs[m].rep_len;
-  }
-  if (!(nc1 > 0 && nc2 > 0)) return 0;
-  if (P.split_alignment) {
-    verify_read_split(P, ref, r[0].data(), neg[0], L[0], rs[0]);
-    verify_read_split(P, ref, r[1].data(), neg[1], L[1], rs[1]);
-  } else {
-    verify_read(P, ref, r[0].data(), neg[0], L[0], rs[0]);
-    verify_read(P, ref, r[1].data(), neg[1], L[1], rs[1]);
-  }
-  if (tr) for (int m = 0; m < 2; ++m) {
-    tr->n_pos_mappings[m] = rs[m].map[0].size(); tr->n_neg_mappings[m] = rs[m].map[1].size();
-    tr->min_errors[m] = rs[m].min_err; tr->second_min_errors[m] = rs[m].second_min_err;
-    tr->n_best[m] = rs[m].n_best; tr->n_second_best[m] = rs[m].n_second_best;
-  }
+// The part of the taskloop body after verification (chromap.h:1099-1143): SortMappingsByPositions, best pairs, sampling,
+// spans, MAPQ, records.  Separate from map_one_pair so that tests can enter it with prepared draft mappings (orc_emit_test).
+static int finish_pair(const orc_params &P, const orc_reference &ref, std::mt19937 &gen, const std::string r[2], const std::string neg[2],
+                       const u32 L[2], ReadState rs[2], int sup, u32 read_id, orc_pe_record *out, int cap, orc_pair_trace *tr,
+                       const SamSink *sam) {
   if (rs[0].map[0].size() + rs[0].map[1].size() == 0 || rs[1].map[0].size() + rs[1].map[1].size() == 0) return 0;
   // mapping_metadata.h:70-78 sorts by position only; equal positions are interchangeable for the
   // output (the lower-error one is the only one that can be in a best pair), so (pos, err) is used.
@@ -1305,6 +1262,57 @@ static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_refe
   }
   if (tr) tr->n_records = reported;
   return reported;
+}
+
+static int map_one_pair(const orc_params &P, const orc_index &ix, const orc_reference &ref, std::mt19937 &gen,
+                        const char *s1, u32 len1, const char *s2, u32 len2, u32 read_id, u32 pair_index,
+                        orc_pe_record *out, int cap, orc_pair_trace *tr, const SamSink *sam = nullptr) {
+  if (tr) memset(tr, 0, sizeof(*tr));
+  if (len1 < (u32)P.min_read_length || len2 < (u32)P.min_read_length) return 0;
+  std::string r[2] = {std::string(s1, len1), std::string(s2, len2)}, neg[2];
+  revcomp(r[0].data(), len1, neg[0]);
+  revcomp(r[1].data(), len2, neg[1]);
+  if (P.trim_adapters) trim_adapters(P, r[0], r[1], neg[0], neg[1]);
+  const u32 L[2] = {(u32)r[0].size(), (u32)r[1].size()};
+  if (tr) { tr->trimmed_len[0] = L[0]; tr->trimmed_len[1] = L[1]; }
+  ReadState rs[2];
+  rs[0].reset(); rs[1].reset();
+  gen_minimizers(r[0].data(), L[0], pair_index, ix.k, ix.w, rs[0].mm);
+  gen_minimizers(r[1].data(), L[1], pair_index, ix.k, ix.w, rs[1].mm);
+  if (tr) { tr->n_minimizers[0] = rs[0].mm.size(); tr->n_minimizers[1] = rs[1].mm.size(); }
+  if (rs[0].mm.empty() || rs[1].mm.empty()) return 0;
+  gen_candidates(P, ix, rs[0]);
+  gen_candidates(P, ix, rs[1]);
+  if (tr) for (int m = 0; m < 2; ++m) { tr->n_pos_candidates_gen[m] = rs[m].cand[0].size(); tr->n_neg_candidates_gen[m] = rs[m].cand[1].size(); }
+  int sup = 0;
+  if (!P.split_alignment) sup = supplement(P, ix, rs);
+  if (tr) tr->supplement_result = sup;
+  size_t nc1 = rs[0].cand[0].size() + rs[0].cand[1].size(), nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
+  if (nc1 > 0 && nc2 > 0 && !P.split_alignment) {
+    for (int m = 0; m < 2; ++m) for (int s = 0; s < 2; ++s) { rs[m].cand[s].swap(rs[m].buf[s]); rs[m].cand[s].clear(); }
+    pe_filter_dir(P.max_insert_size, rs[0].buf[0], rs[1].buf[1], rs[0].cand[0], rs[1].cand[1]);
+    pe_filter_dir(P.max_insert_size, rs[0].buf[1], rs[1].buf[0], rs[0].cand[1], rs[1].cand[0]);
+    nc1 = rs[0].cand[0].size() + rs[0].cand[1].size();
+    nc2 = rs[1].cand[0].size() + rs[1].cand[1].size();
+  }
+  if (tr) for (int m = 0; m < 2; ++m) {
+    tr->n_pos_candidates[m] = rs[m].cand[0].size(); tr->n_neg_candidates[m] = rs[m].cand[1].size();
+    tr->repetitive_seed_length[m] = rs[m].rep_len;
+  }
+  if (!(nc1 > 0 && nc2 > 0)) return 0;
+  if (P.split_alignment) {
+    verify_read_split(P, ref, r[0].data(), neg[0], L[0], rs[0]);
+    verify_read_split(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  } else {
+    verify_read(P, ref, r[0].data(), neg[0], L[0], rs[0]);
+    verify_read(P, ref, r[1].data(), neg[1], L[1], rs[1]);
+  }
+  if (tr) for (int m = 0; m < 2; ++m) {
+    tr->n_pos_mappings[m] = rs[m].map[0].size(); tr->n_neg_mappings[m] = rs[m].map[1].size();
+    tr->min_errors[m] = rs[m].min_err; tr->second_min_errors[m] = rs[m].second_min_err;
+    tr->n_best[m] = rs[m].n_best; tr->n_second_best[m] = rs[m].n_second_best;
+  }
+  return finish_pair(P, ref, gen, r, neg, L, rs, sup, read_id, out, cap, tr, sam);
 }
 
 // Single-end: the taskloop body of MapSingleEndReads (chromap.h:383-470) + GenerateBestMappingsForSingleEndRead /
@@ -1671,6 +1679,35 @@ void orc_pair_stats_test(int e, int max_insert_size, int min_read_length, uint32
   pair_dir(P, 0, L1, L2, m[0], m[3], ps, ps.best[0]);
   pair_dir(P, 1, L1, L2, m[1], m[2], ps, ps.best[1]);
   stats[0] = ps.min_sum; stats[1] = ps.n_best; stats[2] = ps.second_min_sum; stats[3] = ps.n_second_best;
+}
+// The part of the taskloop body after verification (SortMappingsByPositions, best pairs, sampling with a fresh
+// std::mt19937(11), spans, MAPQ, BED records) for one pair over given draft mappings, for tests of the device emit kernels.
+// n_map / pos / err as in orc_pair_stats_test; tally: {min_err, n_best, second_min_err, n_second_best} of mate 1 then mate 2.
+int orc_emit_test(const orc_params *p, const char *ref_seq, uint32_t ref_len, const char *read1, uint32_t L1, const char *read2, uint32_t L2,
+                  const int *n_map, const uint64_t *pos, const int16_t *err, const int *tally, const uint32_t *rep_len, int sup, uint32_t read_id,
+                  orc_pe_record *out, int cap) {
+  orc_reference ref;
+  ref.names.push_back("t");
+  ref.lens.push_back(ref_len);
+  std::string sq(ref_seq, ref_len);
+  sq.append(64, '\0');
+  ref.seqs.push_back(std::move(sq));
+  const std::string r[2] = {std::string(read1, L1), std::string(read2, L2)};
+  std::string neg[2];
+  revcomp(r[0].data(), L1, neg[0]);
+  revcomp(r[1].data(), L2, neg[1]);
+  const u32 L[2] = {L1, L2};
+  ReadState rs[2];
+  size_t o = 0;
+  for (int m = 0; m < 2; ++m) {
+    rs[m].reset();
+    for (int st = 0; st < 2; ++st)
+      for (int i = 0; i < n_map[2 * m + st]; ++i, ++o) rs[m].map[st].push_back({(int)err[o], pos[o]});
+    rs[m].min_err = tally[4 * m]; rs[m].n_best = tally[4 * m + 1]; rs[m].second_min_err = tally[4 * m + 2]; rs[m].n_second_best = tally[4 * m + 3];
+    rs[m].rep_len = rep_len[m];
+  }
+  std::mt19937 gen(11);
+  return finish_pair(*p, ref, gen, r, neg, L, rs, sup, read_id, out, cap, nullptr, nullptr);
 }
 // the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
 int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {

@@ -60,6 +60,23 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   pthread_barrier_wait(&g_cta->warp[w]);
   return m;
 }
+template <typename T, typename Op>
+static inline T emu_reduce(T x, Op op) {  // every lane gets op over the warp
+  const int w = threadIdx.x >> 5;
+  g_cta->xch[threadIdx.x] = (u64)(long long)x;
+  pthread_barrier_wait(&g_cta->warp[w]);
+  const int n_in_warp = std::min(32, g_cta->nt - w * 32);
+  T r = (T)(long long)g_cta->xch[w * 32];
+  for (int l = 1; l < n_in_warp; ++l) r = op(r, (T)(long long)g_cta->xch[w * 32 + l]);
+  pthread_barrier_wait(&g_cta->warp[w]);
+  return r;
+}
+static inline int __reduce_add_sync(unsigned, int x) { return emu_reduce<int>(x, [](int a, int b) { return a + b; }); }
+static inline unsigned __reduce_add_sync(unsigned, unsigned x) { return emu_reduce<unsigned>(x, [](unsigned a, unsigned b) { return a + b; }); }
+static inline int __reduce_max_sync(unsigned, int x) { return emu_reduce<int>(x, [](int a, int b) { return a > b ? a : b; }); }
+static inline int __reduce_min_sync(unsigned, int x) { return emu_reduce<int>(x, [](int a, int b) { return a < b ? a : b; }); }
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
