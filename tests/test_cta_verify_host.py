@@ -1,7 +1,8 @@
-"""`verify_cta_kernel` (chromap_b200/csrc/cta_verify_pairing.cuh) — GenerateDraftMappings for one read by one CTA: fast path,
+"""`verify_kernel` (tier 0: every pair; the reference's drivers replayed by one thread per read, fast path in a pass of its own) and
+`verify_cta_kernel` (chromap_b200/csrc/cta_verify_pairing.cuh) — GenerateDraftMappings for one read by one CTA: fast path,
 cooperative candidate sort, the lane-group / threshold rule of the reference's SIMD driver restated as "one threshold value T,
 one stop index", accepted mappings written in list order by prefix sums, the error tally merged by reduction — run UNCHANGED
-as a kernel on the host emulation of a CTA (tests/cta_emu.h) against the oracle's `verify_read` (draft_mapping_generator.cc:9-357;
+as kernels on the host emulation of a CTA (tests/cta_emu.h) against the oracle's `verify_read` (draft_mapping_generator.cc:9-357;
 the code the oracle's mapper runs, pinned to the reference binary by tests/test_oracle_golden.py).  Inputs: planted repeat
 copies with 0 .. e + 3 edits so that whole groups pass, whole groups fail and groups fail in part; candidates off both ends of
 the reference; single-candidate reads for the fast path; block sizes 128 and 256 as the tiers launch them; e = 4 (8 lanes) and
@@ -22,6 +23,7 @@ struct ulonglong2 { u64 x, y; };
 static u64 *g_dyn_smem = nullptr;
 static inline void atomicAdd(u64 *p, u64 v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline void agg_add(u64 *addr, u64 v) { atomicAdd(addr, v); }   // (the device version first adds up the converged lanes)
+static inline int agg_append(int *count) { return __atomic_fetch_add(count, 1, __ATOMIC_RELAXED); }
 '''
 
 MAIN = r'''
@@ -107,24 +109,36 @@ int main() {
     S.map_err = map_err.data(); S.map_split = map_split.data();
     rmeta[0].len = L; rmeta[0].n_mm = n_mm; rmeta[0].n_cand[0] = nc[0]; rmeta[0].n_cand[1] = nc[1];
     for (int s = 0; s < 2; ++s) for (int i = 0; i < nc[s]; ++i) { cand_pos[(size_t)s * 1024 + i] = cpos[s][i]; cand_cnt[(size_t)s * 1024 + i] = ccnt[s][i]; }
-    Counters ctr{};
-    const int sm_cap = 1024;
-    std::vector<u64> dyn((size_t)sm_cap + sm_cap / 8 + 2 * 160 / 8 + 8);
-    g_dyn_smem = dyn.data();
-    emu_launch(nt, [&]() { verify_cta_kernel(P, R, B, S, &ctr, sm_cap); });
-    ++cases;
+    for (int form = 0; form < 2; ++form) {   // 0: verify_kernel (tier 0: fast-path pass, then the listed reads one thread each); 1: verify_cta_kernel
+      std::vector<ReadMeta> rm2 = rmeta; std::vector<PairMeta> pm2 = pmeta;
+      std::vector<u64> cp2 = cand_pos, mp2((size_t)2 * 2 * cap);
+      std::vector<u8> cc2 = cand_cnt;
+      std::vector<short> me2((size_t)2 * 2 * cap);
+      Scratch S2 = S;
+      S2.rmeta = rm2.data(); S2.pmeta = pm2.data(); S2.cand_pos = cp2.data(); S2.cand_cnt = cc2.data(); S2.map_pos = mp2.data(); S2.map_err = me2.data();
+      Counters ctr{};
+      const int sm_cap = 1024;
+      std::vector<u64> dyn((size_t)sm_cap + sm_cap / 8 + 2 * 160 * 64 / 8 + 8);
+      g_dyn_smem = dyn.data();
+      if (form == 0) {
+        int list[4] = {0, 0, 0, 0}, list_count = 0;
+        emu_launch(32, [&]() { verify_kernel(P, R, B, S2, &ctr, 0, list, &list_count); });
+        if (list_count) emu_launch(64, [&]() { verify_kernel(P, R, B, S2, &ctr, 1, list, &list_count); });
+      } else emu_launch(nt, [&]() { verify_cta_kernel(P, R, B, S2, &ctr, sm_cap); });
+      ++cases;
+      bool ok = pm2[0].status == ST_OK && rm2[0].n_map[0] == w_n[0] && rm2[0].n_map[1] == w_n[1] && rm2[0].min_err == w_st[0] && rm2[0].n_best == w_st[1] &&
+                rm2[0].second_min_err == w_st[2] && rm2[0].n_second_best == w_st[3];
+      for (int s = 0; ok && s < 2; ++s)
+        for (int i = 0; ok && i < w_n[s]; ++i) ok = mp2[(size_t)s * cap + i] == w_pos[(size_t)s * cap + i] && me2[(size_t)s * cap + i] == w_err[(size_t)s * cap + i];
+      if (!ok) {
+        if (bad < 6) printf("MISMATCH it=%%d form=%%d e=%%d nt=%%d L=%%d cands %%d+%%d maps %%d/%%d %%d/%%d tally %%d,%%d,%%d,%%d / %%d,%%d,%%d,%%d\n", it, form, e, nt, L, nc[0], nc[1], rm2[0].n_map[0],
+                            w_n[0], rm2[0].n_map[1], w_n[1], rm2[0].min_err, rm2[0].n_best, rm2[0].second_min_err, rm2[0].n_second_best, w_st[0], w_st[1], w_st[2], w_st[3]);
+        ++bad;
+      }
+    }
     if (nc[0] + nc[1] == 1) ++fast;
     if (nc[0] >= P.lanes || nc[1] >= P.lanes) ++ruled;
-    bool ok = pmeta[0].status == ST_OK && rmeta[0].n_map[0] == w_n[0] && rmeta[0].n_map[1] == w_n[1] && rmeta[0].min_err == w_st[0] && rmeta[0].n_best == w_st[1] &&
-              rmeta[0].second_min_err == w_st[2] && rmeta[0].n_second_best == w_st[3];
-    for (int s = 0; ok && s < 2; ++s)
-      for (int i = 0; ok && i < w_n[s]; ++i) ok = map_pos[(size_t)s * cap + i] == w_pos[(size_t)s * cap + i] && map_err[(size_t)s * cap + i] == w_err[(size_t)s * cap + i];
     mappings += w_n[0] + w_n[1];
-    if (!ok) {
-      if (bad < 6) printf("MISMATCH it=%%d e=%%d nt=%%d L=%%d cands %%d+%%d maps %%d/%%d %%d/%%d tally %%d,%%d,%%d,%%d / %%d,%%d,%%d,%%d\n", it, e, nt, L, nc[0], nc[1], rmeta[0].n_map[0],
-                          w_n[0], rmeta[0].n_map[1], w_n[1], rmeta[0].min_err, rmeta[0].n_best, rmeta[0].second_min_err, rmeta[0].n_second_best, w_st[0], w_st[1], w_st[2], w_st[3]);
-      ++bad;
-    }
   }
   printf("reads=%%ld single_candidate=%%ld group_rule=%%ld mappings=%%ld bad=%%ld\n", cases, fast, ruled, mappings, bad);
   return bad != 0;
@@ -145,12 +159,12 @@ def test_verify_cta_kernel_equals_the_oracles_draft_mapping_generation(tmp_path)
     d = re.sub(r'asm volatile\(.*?\)\s*;', ';', d.replace("#include <cuda_runtime.h>", ""))
     parts = [d,
              _between(k, "struct Counters", "// Counter updates: every lane adds to the same address"),
-             _between(k, "struct PatPlanes", "// K3: per read — GenerateDraftMappings"),
+             _between(k, "struct PatPlanes", "// ------------------------------------------------------------------------------------------------\n// mapping_generator.h:346-484 (non-split): two-pointer sweep"),
              _between(k, "// same for (key, tag) pairs under `less`", "// candidate_processor.cc:283-342 with the sorted hits streamed"),
              _between(c, "// ---- CTA-wide scans (one value per thread)", "// ---- MergeCandidates (candidate_processor.cc:345-414)"),
              _between(v, "// Tally (min, #min, second distinct min, #second) of a multiset", "// Best-pair statistics for one pair by one CTA")]
     body = re.sub(r"#pragma unroll[^\n]*", "", "\n".join(parts)).replace("#pragma once", "")
-    body = body.replace("extern __shared__ u64 smk[];", "u64 *smk = g_dyn_smem;")
+    body = body.replace("extern __shared__ u64 smk[];", "u64 *smk = g_dyn_smem;").replace("extern __shared__ u8 v_codes[];", "u8 *v_codes = (u8 *)g_dyn_smem;")
     src = tmp_path / "t.cc"
     src.write_text(PRE % dict(emu=os.path.join(ROOT, "tests", "cta_emu.h")) + body + MAIN.replace("%%", "%"))
     exe = tmp_path / "t"
