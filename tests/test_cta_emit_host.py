@@ -224,7 +224,7 @@ def test_emit_kernels_equal_the_oracles_post_verification_stage(tmp_path):
     exe = tmp_path / "t"
     lib = os.path.join(ROOT, "oracle", "liboracle.so")
     assert os.path.exists(lib), "oracle/liboracle.so not built (__graft_entry__.build())"
-    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-pthread", "-o", str(exe), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-fopenmp"])
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-o", str(exe), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-fopenmp"])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-2500:] + out.stderr[-800:]
     f = dict(kv.split("=") for kv in out.stdout.split() if "=" in kv)

@@ -1,0 +1,352 @@
+"""The device pipeline after the front end — cluster -> pair_candidates -> verify -> pairing (tier 0, thread kernels), prep ->
+seed_cta -> pair_candidates_cta -> verify_cta -> pairing_cta (overflow tiers, one CTA per read / pair), overflow collection
+between the tiers, select, emit (+ deferred tracebacks) / emit_cta — compiled from the UNCHANGED kernel sources
+(device_common.cuh, minimizers.cuh, pipeline_kernels.cuh, cta_pair_candidates.cuh, cta_verify_pairing.cuh) and run on the host
+emulation of CTAs (tests/cta_emu.h) with the launch sequence, grid / block sizes, shared-memory sizes and scratch layout of
+api.cu's run_lane (the layout code itself is cut out of api.cu), against the oracle's mapper (`orc_map_pairs`, pinned to the
+reference binary by tests/test_oracle_golden.py): every pair's records, field by field.
+The front end (seed_front_kernel: cp.async.bulk / mbarrier PTX) is the one kernel that cannot run here; its output — probed
+minimizer records in the lane-interleaved layout — is produced from the oracle's minimizers and khash lookups.
+Two runs: the real tier capacities (64 / 32 / 32 ...) on a reference with repeat families, reads longer than the first tier
+allows, N's and junk pairs; and tiny first- and second-tier capacities that push most ordinary pairs through the CTA kernels and
+some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PRE = r'''
+#include "%(emu)s"
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+struct ulonglong2 { u64 x, y; };
+#define __host__
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __ldg(p) (*(p))
+static u64 *g_dyn_smem = nullptr;
+static inline u64 atomicAdd(u64 *p, u64 v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline u32 atomicAdd(u32 *p, u32 v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+static inline u64 atomicCAS(u64 *p, u64 cmp, u64 val) { __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return cmp; }
+static inline void agg_add(u64 *addr, u64 v) { atomicAdd(addr, v); }     // (device: one atomic per group of converged lanes)
+static inline int agg_append(int *count) { return atomicAdd(count, 1); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline u32 __funnelshift_r(u32 lo, u32 hi, u32 s) { return (u32)((((u64)hi << 32) | lo) >> (s & 31)); }
+'''
+
+MAIN = r'''
+extern "C" {
+#include "%(orc_h)s"
+}
+%(tier_bytes)s
+struct HostTier {
+  Caps caps;
+  std::vector<char> mem;
+  Scratch view;
+  std::vector<int> list;   // pair list of this tier (empty = identity)
+};
+static void tier_prepare_host(HostTier &t, int n_slots, const int *pair_list, bool interleaved) {
+  size_t o[11];
+  const size_t bytes = tier_bytes(t.caps, (size_t)n_slots + 1, interleaved, o);
+  t.mem.assign(bytes + 256, (char)0x5A);   // (scratch is not cleared on the device either)
+  char *b = t.mem.data();
+  Scratch &S = t.view;
+  S.caps = t.caps; S.n_slots = n_slots; S.pair_list = pair_list; S.mm_il = interleaved ? 1 : 0;
+  S.rmeta = (ReadMeta *)(b + o[0]); S.pmeta = (PairMeta *)(b + o[1]);
+  S.mm_hash = (u64 *)(b + o[2]); S.mm_val = (u64 *)(b + o[3]); S.mm_pos = (u32 *)(b + o[4]);
+  S.hits = (u64 *)(b + o[5]); S.cand_pos = (u64 *)(b + o[6]); S.cand_cnt = (u8 *)(b + o[7]);
+  S.map_pos = (u64 *)(b + o[8]); S.map_err = (short *)(b + o[9]); S.map_split = (int *)(b + o[10]);
+}
+static std::vector<u64> g_smem;
+template <typename F>
+static void launch(int grid, int block, size_t smem_bytes, F body) {   // kernel<<<grid, block, smem>>>(...)
+  g_smem.assign(smem_bytes / 8 + 2, 0xA5A5A5A5A5A5A5A5ull);
+  g_dyn_smem = g_smem.data();
+  emu_grid(grid, block, body);
+}
+static char comp(char c) { switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; default: return 'N'; } }
+static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend()); for (auto &c : r) c = comp(c); return r; }
+
+struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
+
+static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base) {
+  std::mt19937 g((unsigned)seed);
+  RunStats rs;
+  // ---- reference: two sequences, a 300 bp family with many copies, a 2 kb segmental repeat, an N run
+  std::string seq[2] = {std::string(70000, 'A'), std::string(50000, 'A')};
+  for (auto &s : seq) for (auto &c : s) c = "ACGT"[g() %% 4];
+  std::string fam(300, 'A'); for (auto &c : fam) c = "ACGT"[g() %% 4];
+  for (int q = 0; q < 90; ++q) { std::string f2 = fam; for (int x = 0; x < (int)(g() %% 4); ++x) f2[g() %% 300] = "ACGT"[g() %% 4]; std::string &s = seq[g() %% 2]; s.replace(500 + g() %% (s.size() - 1500), 300, f2); }
+  std::string seg(2000, 'A'); for (auto &c : seg) c = "ACGT"[g() %% 4];
+  for (int q = 0; q < 12; ++q) { std::string &s = seq[g() %% 2]; s.replace(1000 + g() %% (s.size() - 4000), 2000, seg); }
+  seq[0].replace(30000, 80, std::string(80, 'N'));
+  for (int q = 0; q < 3000; ++q) { std::string &s = seq[g() %% 2]; const size_t at = g() %% s.size(); s[at] = (char)tolower(s[at]); }
+  std::string concat = seq[0] + seq[1];
+  const uint64_t offs[3] = {0, seq[0].size(), seq[0].size() + seq[1].size()};
+  const char *names[2] = {"chrA", "chrB"};
+  orc_reference *oref = orc_reference_from_memory(2, concat.data(), offs, names);
+  orc_index *oix = orc_index_build(oref, 17, 7);
+  // ---- reads
+  std::string s1, s2;
+  std::vector<u32> o1{0}, o2{0};
+  for (int p = 0; p < n_pairs; ++p) {
+    const int kind = (int)(g() %% 20);
+    int L1 = read_len_base + (int)(g() %% 11) - 5, L2 = read_len_base + (int)(g() %% 11) - 5;
+    if (kind == 0) L1 = mrl + 5 + (int)(g() %% 40);                   // longer than the first tier allows
+    if (kind == 1) L2 = 20;                                           // below the length filter
+    const std::string &rsq = seq[g() %% 2];
+    const int frag = std::max(L1, L2) + (int)(g() %% 350);
+    size_t at = 200 + g() %% (rsq.size() - frag - 400);
+    std::string F = rsq.substr(at, (size_t)frag);
+    if (kind == 2) { F = fam + std::string(rsq, at, (size_t)std::max(0, frag - 300)); F.resize((size_t)frag, 'A'); }   // inside the repeat family
+    if (kind == 3) for (auto &c : F) c = "ACGT"[g() %% 4];                                                             // junk
+    std::string a = F.substr(0, (size_t)L1), b = revc(F.substr((size_t)(frag - L2), (size_t)L2));
+    if (g() & 1) std::swap(a, b);
+    for (std::string *r : {&a, &b}) {
+      for (auto &c : *r) c = (char)toupper(c);
+      const int ne = (int)(g() %% 4);
+      for (int x = 0; x < ne; ++x) {
+        const int k = (int)(g() %% 5), p2 = (int)(g() %% r->size());
+        if (k < 3) (*r)[p2] = "ACGT"[g() %% 4];
+        else if (k == 3) { r->erase((size_t)p2, 1); r->push_back("ACGT"[g() %% 4]); }
+        else (*r)[p2] = 'N';
+      }
+    }
+    if ((int)a.size() != L1) a.resize((size_t)L1, 'A');
+    if ((int)b.size() != L2) b.resize((size_t)L2, 'A');
+    s1 += a; o1.push_back((u32)s1.size()); s2 += b; o2.push_back((u32)s2.size());
+  }
+  const int n = n_pairs;
+  // ---- oracle
+  orc_params op; orc_default_params(&op); orc_apply_preset(&op, "chip");
+  op.max_num_best_mappings = max_best;
+  orc_mapper *om = orc_mapper_create(&op, oix, oref);
+  std::vector<orc_pe_record> want((size_t)n * max_best + 8);
+  const u32 first_read_id = 5000;
+  const long n_want = (long)orc_map_pairs(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want.data(), (long)want.size(), nullptr);
+  // ---- device objects
+  DevParams P{};
+  P.e = op.error_threshold; P.min_seeds = op.min_num_seeds; P.f0 = op.max_seed_freq0; P.f1 = op.max_seed_freq1; P.max_best = max_best; P.max_insert = op.max_insert_size;
+  P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = 0; P.k = 17; P.w = 7; P.lanes = P.e < 8 ? 8 : 4; P.split = 0; P.se = 0;
+  const uint32_t *kf; const uint64_t *kk, *kv, *kocc; uint32_t n_occ = 0;
+  const uint32_t nb = orc_index_arrays(oix, &kf, &kk, &kv, &kocc, &n_occ);
+  // the library's table: 16-byte slots {hash << 1 | singleton, value}, slot = (hash * phi64) >> shift, linear probing, load <= 0.5
+  u64 n_keys = 0;
+  for (uint32_t i = 0; i < nb; ++i) if (((kf[i >> 4] >> ((i & 0xfU) << 1)) & 3) == 0) ++n_keys;
+  u64 n_slots_t = 16; while (n_slots_t < 2 * n_keys) n_slots_t <<= 1;
+  int lg = 0; while ((1ull << lg) < n_slots_t) ++lg;
+  std::vector<ulonglong2> slots((size_t)n_slots_t, ulonglong2{CMX_EMPTY_KEY, 0});
+  for (uint32_t i = 0; i < nb; ++i) {
+    if (((kf[i >> 4] >> ((i & 0xfU) << 1)) & 3) != 0) continue;
+    u64 sidx = ((u64)(kk[i] >> 1) * 0x9E3779B97F4A7C15ull) >> (64 - lg);
+    while (slots[sidx].x != CMX_EMPTY_KEY) sidx = (sidx + 1) & (n_slots_t - 1);
+    slots[sidx] = ulonglong2{(u64)kk[i], (u64)kv[i]};
+  }
+  DevIndex ix{};
+  ix.slots = slots.data(); ix.n_slots_mask = n_slots_t - 1; ix.shift = 64 - lg; ix.occ = (const u64 *)kocc; ix.n_occ = n_occ; ix.k = 17; ix.w = 7;
+  std::string refmem(64, '\0');
+  u64 roff[2]; u32 rlen[2];
+  for (int q = 0; q < 2; ++q) { roff[q] = refmem.size(); rlen[q] = (u32)seq[q].size(); refmem += seq[q]; refmem.append(64 + (64 - refmem.size() %% 64) %% 64, '\0'); }
+  refmem.append(128, '\0');
+  DevRef R{(const u8 *)refmem.data(), roff, rlen, 2};
+  DevBatch B{};
+  B.seq1 = (const u8 *)s1.data(); B.off1 = o1.data(); B.seq2 = (const u8 *)s2.data(); B.off2 = o2.data(); B.n_pairs = (u32)n; B.first_read_id = first_read_id;
+  std::vector<double> il_; std::vector<int> thr_;
+  {
+%(tables)s
+    il_ = il; thr_ = thr;
+  }
+  MapqTables T{il_.data(), thr_.data()};
+  u32 mt_init[624];
+  mt_init[0] = 11u;
+  for (int i = 1; i < 624; ++i) mt_init[i] = 1812433253u * (mt_init[i - 1] ^ (mt_init[i - 1] >> 30)) + (u32)i;
+  // ---- run_lane, tier by tier
+  HostTier tiers[3];
+  for (int t = 0; t < 3; ++t) tiers[t].caps = caps3[t];
+  Counters ctr{};
+  std::vector<int> nbest((size_t)n, 0), sel((size_t)n * max_best, 0), out_n((size_t)n + 1, 0);
+  std::vector<OutRecord> out_rec((size_t)n * max_best);
+  int n_slots = n, tiers_used = 0;
+  const int *pair_list = nullptr;
+  const int TB = 128;
+  g_emu_leavable = true;
+  for (int t = 0; t < 3 && n_slots > 0; ++t) {
+    HostTier &tier = tiers[t];
+    tier_prepare_host(tier, n_slots, pair_list, t == 0);
+    const Scratch S = tier.view;
+    rs.tier_pairs[t] = n_slots;
+    if (t == 0) {
+      // the front end's output (seed_front_kernel), from the oracle's minimizers and table lookups
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const int len[2] = {(int)(o1[slot + 1] - o1[slot]), (int)(o2[slot + 1] - o2[slot])};
+        int status = ST_OK;
+        if (len[0] < P.min_read_len || len[1] < P.min_read_len) status = ST_DROP;
+        else if (len[0] > S.caps.maxmm || len[1] > S.caps.maxmm) status = ST_OVERFLOW;
+        PairMeta pm{}; pm.status = status;
+        S.pmeta[slot] = pm;
+        for (int mate = 0; mate < 2; ++mate) {
+          ReadMeta z; memset(&z, 0, sizeof(z));
+          z.len = len[mate];
+          if (status == ST_OK) {
+            const char *rd = mate == 0 ? s1.data() + o1[slot] : s2.data() + o2[slot];
+            std::vector<uint64_t> mh(2048), mhit(2048);
+            const int nm = orc_minimizers(rd, (u32)len[mate], 0, 17, 7, mh.data(), mhit.data(), 2048);
+            z.n_mm = nm;
+            if (nm > S.caps.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; }
+            else {
+              const size_t mb_ = mm_base(S, slot, mate);
+              const int ms = mm_stride(S);
+              for (int i = 0; i < nm; ++i) {
+                uint64_t key = 0, val = 0;
+                const int found = orc_index_lookup(oix, mh[i], &key, &val);
+                const u32 kind = found ? ((key & 1) ? 1u : 2u) : 0u;
+                S.mm_val[mb_ + (size_t)i * ms] = found ? val : 0;
+                S.mm_pos[mb_ + (size_t)i * ms] = ((u32)mhit[i] & 0x3FFFFFFFu) | (kind << 30);
+              }
+              z.mm_done = 1;
+            }
+          }
+          S.rmeta[2 * slot + mate] = z;
+        }
+      }
+      std::vector<int> vlist((size_t)2 * n_slots + 8), rlist((size_t)n_slots + 8);
+      int d_count[4] = {0, 0, 0, 0};
+      int rows0 = (2 * mrl / (7 + 1) + 15) / 16 * 16;
+      rows0 = std::max(16, std::min(rows0, S.caps.hc));
+      launch((2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)rows0 * CLUSTER_NT * 8, [&]() { cluster_kernel(P, ix, S, &ctr, 0, rows0, vlist.data(), &d_count[3]); });
+      if (rows0 < S.caps.hc)
+        launch((2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)S.caps.hc * CLUSTER_NT * 8, [&]() { cluster_kernel(P, ix, S, &ctr, 1, S.caps.hc, vlist.data(), &d_count[3]); });
+      launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pair_candidates_kernel(P, ix, S, &ctr, 0, rlist.data(), &d_count[1]); });
+      launch((n_slots + 63) / 64, 64, 0, [&]() { pair_candidates_kernel(P, ix, S, &ctr, 1, rlist.data(), &d_count[1]); });
+      launch((2 * n_slots + TB - 1) / TB, TB, 0, [&]() { verify_kernel(P, R, B, S, &ctr, 0, vlist.data(), &d_count[2]); });
+      launch((2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, [&]() { verify_kernel(P, R, B, S, &ctr, 1, vlist.data(), &d_count[2]); });
+      launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pairing_kernel(P, S, nbest.data()); });
+    } else {
+      auto cap_of = [](int c_) { int c = 1; while (c < c_) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
+      const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
+      launch((n_slots + TB - 1) / TB, TB, 0, [&]() { prep_kernel(P, B, S); });
+      launch(2 * n_slots, CTA_NT, (size_t)c_seed * 11 + (size_t)(tier.caps.maxmm + 1) * 12 + 16, [&]() { seed_cta_kernel(P, ix, B, S, tiers[0].view, &ctr, c_seed); });
+      const int lcap = std::min(tier.caps.cc, 512), fcap = 2 * tier.caps.cc;
+      const size_t pc_smem = pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap);
+      const int pc_nt = pc_smem > 64 * 1024 ? PC_CTA_NT_MAX : CTA_NT;
+      launch(n_slots, pc_nt, pc_smem, [&]() { pair_candidates_cta_kernel(P, ix, S, &ctr, c_pc, lcap, fcap, nullptr, nullptr); });
+      launch(2 * n_slots, tier.caps.cc > 1024 ? VERIFY_NT_MAX : CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, [&]() { verify_cta_kernel(P, R, B, S, &ctr, c_ver); });
+      launch(n_slots, CTA_NT, (size_t)c_pair * 10, [&]() { pairing_cta_kernel(P, S, nbest.data(), c_pair); });
+    }
+    std::vector<int> ovf((size_t)n_slots + 8);
+    int n_ovf = 0;
+    launch((n_slots + 255) / 256, 256, 0, [&]() { collect_overflow_kernel(S, ovf.data(), &n_ovf); });
+    tiers_used = t + 1;
+    if (n_ovf > 0 && t + 1 < 3) {
+      ovf.resize((size_t)n_ovf);
+      std::sort(ovf.begin(), ovf.end());
+      tiers[t + 1].list = ovf;
+      pair_list = tiers[t + 1].list.data();
+    } else if (n_ovf > 0) { printf("pairs left after the last tier: %%d\n", n_ovf); ++rs.bad; }
+    n_slots = n_ovf;
+  }
+  // one reference batch = all pairs here: taskloop chunks of n / (n / 5000) ...: a single chunk for n < 10000
+  int chunks[2] = {0, n};
+  launch(1, 128, 0, [&]() { select_kernel(P, 1, chunks, nbest.data(), sel.data(), mt_init); });
+  for (int t = tiers_used - 1; t >= 0; --t) {
+    const Scratch S = tiers[t].view;
+    if (t > 0) launch(S.n_slots, CTA_NT, 0, [&]() { emit_cta_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
+    else {
+      std::vector<int4> emit_list((size_t)S.n_slots * max_best + 8);
+      int dp_count = 0;
+      launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr, emit_list.data(), &dp_count); });
+      launch((int)(((size_t)S.n_slots * max_best + TB - 1) / TB), TB, 0, [&]() { emit_dp_kernel(P, R, B, T, S, out_rec.data(), emit_list.data(), &dp_count); });
+    }
+  }
+  g_emu_leavable = false;
+  // ---- compare, pair by pair
+  long wi = 0;
+  for (int p = 0; p < n; ++p) {
+    long w0 = wi;
+    while (wi < n_want && want[wi].read_id == first_read_id + (u32)p) ++wi;
+    const int nw = (int)(wi - w0);
+    ++rs.pairs;
+    rs.records += nw;
+    bool ok = out_n[p] == nw;
+    for (int r = 0; ok && r < nw; ++r) ok = memcmp(&out_rec[(size_t)p * max_best + r], &want[w0 + r], sizeof(OutRecord)) == 0;
+    if (!ok) {
+      if (rs.bad < 8) {
+        printf("PAIR %%d (seed %%d): records %%d / %%d", p, seed, out_n[p], nw);
+        if (nw > 0 && out_n[p] > 0) { const OutRecord &a = out_rec[(size_t)p * max_best]; const orc_pe_record &b = want[w0];
+          printf("  rid %%u/%%u start %%u/%%u len %%u/%%u mapq %%u/%%u dir %%u/%%u uniq %%u/%%u", a.rid, b.rid, a.fragment_start, b.fragment_start, a.fragment_length, b.fragment_length, a.mapq, b.mapq, a.direction, b.direction, a.is_unique, b.is_unique); }
+        printf("\n");
+      }
+      ++rs.bad;
+    }
+  }
+  if (wi != n_want) { printf("oracle records not consumed: %%ld of %%ld\n", wi, n_want); ++rs.bad; }
+  orc_mapper_free(om); orc_index_free(oix); orc_reference_free(oref);
+  return rs;
+}
+
+int main() {
+  static_assert(sizeof(OutRecord) == sizeof(orc_pe_record), "record layout");
+  long bad = 0;
+  {  // the tiers as the library sets them up (api.cu: {mrl, 64, 32, 32}, {2 mrl, 1024, 256, 256}, {4 mrl, 65536, 8192, 8192})
+    const int mrl = 80;
+    const Caps caps[3] = {{mrl, 64, 32, 32}, {mrl * 2, 1024, 256, 256}, {mrl * 4, 65536, 8192, 8192}};
+    const RunStats r = run_case(3, 150, mrl, caps, 1, 60);
+    printf("real_tiers: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
+    bad += r.bad;
+  }
+  {  // a first tier too small for most pairs: ordinary pairs through the CTA kernels; -n 3
+    const int mrl = 80;
+    const Caps caps[3] = {{mrl, 6, 2, 2}, {mrl * 2, 40, 6, 6}, {mrl * 4, 65536, 8192, 8192}};   // ... and a second tier that sends some on to the last one
+    const RunStats r = run_case(4, 64, mrl, caps, 3, 60);
+    printf("small_first_tier: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
+    bad += r.bad;
+  }
+  printf("total_bad=%%ld\n", bad);
+  return bad != 0;
+}
+'''
+
+
+def _between(s, a, b):
+    i = s.index(a)
+    return s[i:s.index(b, i)]
+
+
+def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
+    src_dir = os.path.join(ROOT, "chromap_b200", "csrc")
+    files = ["device_common.cuh", "minimizers.cuh", "pipeline_kernels.cuh", "cta_pair_candidates.cuh", "cta_verify_pairing.cuh"]
+    text = "\n".join(open(os.path.join(src_dir, f)).read() for f in files)
+    api = open(os.path.join(src_dir, "api.cu")).read()
+    text = re.sub(r'#include [<"][^\n]*', "", text).replace("#pragma once", "")
+    text = re.sub(r'asm volatile\(.*?\)\s*;', ';', text)
+    text = re.sub(r"#pragma unroll[^\n]*", "", text)
+    text = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1 *\2 = (\1 *)g_dyn_smem;", text)
+    # the two counter helpers use __activemask: the harness supplies plain atomics instead
+    a = text.index("// Counter updates: every lane adds to the same address")
+    b = text.index("// ------------------------------------------------------------------------------------------------\n// K0: per pair")
+    text = text[:a] + text[b:]
+    tables = _between(api, "    std::vector<double> il(65536, 0.0);", "    CUC(cudaMalloc(&ctx->inv_log")
+    tier_bytes = _between(api, "static size_t tier_bytes(", "static cudaError_t tier_prepare(")
+    main = MAIN % dict(orc_h=os.path.join(ROOT, "oracle", "oracle_chromap.h"), tier_bytes=tier_bytes.replace("%", "%%"), tables=tables.replace("%", "%%"))
+    src = tmp_path / "t.cc"
+    src.write_text(PRE % dict(emu=os.path.join(ROOT, "tests", "cta_emu.h")) + text + main.replace("%%", "%"))
+    exe = tmp_path / "t"
+    lib = os.path.join(ROOT, "oracle", "liboracle.so")
+    assert os.path.exists(lib), "oracle/liboracle.so not built (__graft_entry__.build())"
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-w", "-o", str(exe), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-fopenmp"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=2400)
+    assert out.returncode == 0 and "total_bad=0" in out.stdout, out.stdout[-3000:] + out.stderr[-800:]
+    m1 = re.search(r"real_tiers: pairs=(\d+) records=(\d+) tier0=(\d+) tier1=(\d+) tier2=(\d+)", out.stdout)
+    m2 = re.search(r"small_first_tier: pairs=(\d+) records=(\d+) tier0=(\d+) tier1=(\d+) tier2=(\d+)", out.stdout)
+    assert int(m1.group(2)) > 70 and int(m1.group(4)) > 5, out.stdout          # records, and pairs that climbed to the second tier
+    assert int(m2.group(2)) > 40 and int(m2.group(4)) > 30 and int(m2.group(5)) > 3, out.stdout   # most pairs through the CTA kernels, some up to the last tier (512 / 256-thread CTAs)
