@@ -7,9 +7,11 @@ api.cu's run_lane (the layout code itself is cut out of api.cu), against the ora
 reference binary by tests/test_oracle_golden.py): every pair's records, field by field.
 The front end (seed_front_kernel: cp.async.bulk / mbarrier PTX) is the one kernel that cannot run here; its output — probed
 minimizer records in the lane-interleaved layout — is produced from the oracle's minimizers and khash lookups.
-Two runs: the real tier capacities (64 / 32 / 32 ...) on a reference with repeat families, reads longer than the first tier
+Runs: `--preset chip` with the real tier capacities (64 / 32 / 32 ...) on a reference with repeat families, reads longer than the first tier
 allows, N's and junk pairs; and tiny first- and second-tier capacities that push most ordinary pairs through the CTA kernels and
-some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3."""
+some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3; `--preset atac` (adapter
+trimming by prep_kernel on read-through pairs); `--preset hic` (split alignment: verify_split / pairing_split / emit_split and the
+CTA form, chimeric reads, pairs records); single-end (emit_se_kernel, a fresh generator per read), each also through the CTA tiers."""
 import os
 import re
 import subprocess
@@ -79,7 +81,8 @@ static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend
 
 struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
 
-static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base) {
+enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3 };
+static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base) {
   std::mt19937 g((unsigned)seed);
   RunStats rs;
   // ---- reference: two sequences, a 300 bp family with many copies, a 2 kb segmental repeat, an N run
@@ -111,6 +114,17 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
     if (kind == 2) { F = fam + std::string(rsq, at, (size_t)std::max(0, frag - 300)); F.resize((size_t)frag, 'A'); }   // inside the repeat family
     if (kind == 3) for (auto &c : F) c = "ACGT"[g() %% 4];                                                             // junk
     std::string a = F.substr(0, (size_t)L1), b = revc(F.substr((size_t)(frag - L2), (size_t)L2));
+    if (mode == MODE_ATAC && g() %% 3 == 0 && std::min(L1, L2) > 40) {   // a fragment shorter than the reads: both mates run through into adapter sequence
+      const int fl = 35 + (int)(g() %% (unsigned)(std::min(L1, L2) - 36));
+      const std::string f2 = F.substr(0, (size_t)fl);
+      a = f2 + std::string("CTGTCTCTTATACACATCTCCGAGCCCACGAGACAGGTTCAGAGTTCTACAGTCCGACGATCCTGTCTCTTATACACATCTCCGAGCCCACGAGAC").substr(0, (size_t)(L1 - fl));
+      b = revc(f2) + std::string("CTGTCTCTTATACACATCTGACGCTGCCGACGAAGGTTCAGAGTTCTACAGTCCGACGATCACTGTCTCTTATACACATCTGACGCTGCCGACGA").substr(0, (size_t)(L2 - fl));
+    }
+    if (mode == MODE_HIC && g() %% 3 == 0 && L1 > 60) {    // a chimeric read: the far side of a ligation junction comes from another locus
+      const std::string &r2 = seq[g() %% 2];
+      const int cut = 30 + (int)(g() %% (unsigned)(L1 - 45));
+      a = a.substr(0, (size_t)cut) + r2.substr(300 + g() %% (r2.size() - 1000), (size_t)(L1 - cut));
+    }
     if (g() & 1) std::swap(a, b);
     for (std::string *r : {&a, &b}) {
       for (auto &c : *r) c = (char)toupper(c);
@@ -128,16 +142,19 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
   }
   const int n = n_pairs;
   // ---- oracle
-  orc_params op; orc_default_params(&op); orc_apply_preset(&op, "chip");
+  orc_params op; orc_default_params(&op); orc_apply_preset(&op, mode == MODE_ATAC ? "atac" : mode == MODE_HIC ? "hic" : "chip");
   op.max_num_best_mappings = max_best;
+  op.single_end = mode == MODE_SE;
   orc_mapper *om = orc_mapper_create(&op, oix, oref);
   std::vector<orc_pe_record> want((size_t)n * max_best + 8);
   const u32 first_read_id = 5000;
-  const long n_want = (long)orc_map_pairs(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want.data(), (long)want.size(), nullptr);
+  const long n_want = mode == MODE_SE ? (long)orc_map_reads_se(om, (u32)n, s1.data(), o1.data(), first_read_id, want.data(), (long)want.size(), 1)
+                                      : (long)orc_map_pairs(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want.data(), (long)want.size(), nullptr);
   // ---- device objects
   DevParams P{};
   P.e = op.error_threshold; P.min_seeds = op.min_num_seeds; P.f0 = op.max_seed_freq0; P.f1 = op.max_seed_freq1; P.max_best = max_best; P.max_insert = op.max_insert_size;
-  P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = 0; P.k = 17; P.w = 7; P.lanes = P.e < 8 ? 8 : 4; P.split = 0; P.se = 0;
+  P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = op.trim_adapters; P.k = 17; P.w = 7; P.lanes = P.e < 8 ? 8 : 4; P.split = op.split_alignment;
+  P.se = mode == MODE_SE;
   const uint32_t *kf; const uint64_t *kk, *kv, *kocc; uint32_t n_occ = 0;
   const uint32_t nb = orc_index_arrays(oix, &kf, &kk, &kv, &kocc, &n_occ);
   // the library's table: 16-byte slots {hash << 1 | singleton, value}, slot = (hash * phi64) >> shift, linear probing, load <= 0.5
@@ -187,17 +204,21 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
     rs.tier_pairs[t] = n_slots;
     if (t == 0) {
       // the front end's output (seed_front_kernel), from the oracle's minimizers and table lookups
+      if (P.trim) launch((n_slots + TB - 1) / TB, TB, 0, [&]() { prep_kernel(P, B, S); });   // adapter trimming first (the front end then runs "prepped")
       for (int slot = 0; slot < n_slots; ++slot) {
-        const int len[2] = {(int)(o1[slot + 1] - o1[slot]), (int)(o2[slot + 1] - o2[slot])};
+        int len[2] = {(int)(o1[slot + 1] - o1[slot]), P.se ? 0 : (int)(o2[slot + 1] - o2[slot])};
         int status = ST_OK;
-        if (len[0] < P.min_read_len || len[1] < P.min_read_len) status = ST_DROP;
-        else if (len[0] > S.caps.maxmm || len[1] > S.caps.maxmm) status = ST_OVERFLOW;
-        PairMeta pm{}; pm.status = status;
-        S.pmeta[slot] = pm;
+        if (P.trim) { status = S.pmeta[slot].status; len[0] = S.rmeta[2 * slot].len; len[1] = S.rmeta[2 * slot + 1].len; }
+        else {
+          if (len[0] < P.min_read_len || (!P.se && len[1] < P.min_read_len)) status = ST_DROP;
+          else if (len[0] > S.caps.maxmm || len[1] > S.caps.maxmm) status = ST_OVERFLOW;
+          PairMeta pm{}; pm.status = status;
+          S.pmeta[slot] = pm;
+        }
         for (int mate = 0; mate < 2; ++mate) {
           ReadMeta z; memset(&z, 0, sizeof(z));
           z.len = len[mate];
-          if (status == ST_OK) {
+          if (status == ST_OK && !(P.se && mate == 1)) {
             const char *rd = mate == 0 ? s1.data() + o1[slot] : s2.data() + o2[slot];
             std::vector<uint64_t> mh(2048), mhit(2048);
             const int nm = orc_minimizers(rd, (u32)len[mate], 0, 17, 7, mh.data(), mhit.data(), 2048);
@@ -228,9 +249,13 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
         launch((2 * n_slots + CLUSTER_NT - 1) / CLUSTER_NT, CLUSTER_NT, (size_t)S.caps.hc * CLUSTER_NT * 8, [&]() { cluster_kernel(P, ix, S, &ctr, 1, S.caps.hc, vlist.data(), &d_count[3]); });
       launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pair_candidates_kernel(P, ix, S, &ctr, 0, rlist.data(), &d_count[1]); });
       launch((n_slots + 63) / 64, 64, 0, [&]() { pair_candidates_kernel(P, ix, S, &ctr, 1, rlist.data(), &d_count[1]); });
-      launch((2 * n_slots + TB - 1) / TB, TB, 0, [&]() { verify_kernel(P, R, B, S, &ctr, 0, vlist.data(), &d_count[2]); });
-      launch((2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, [&]() { verify_kernel(P, R, B, S, &ctr, 1, vlist.data(), &d_count[2]); });
-      launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pairing_kernel(P, S, nbest.data()); });
+      if (P.split) launch((2 * n_slots + TB - 1) / TB, TB, 0, [&]() { verify_split_kernel(P, R, B, S, &ctr); });
+      else {
+        launch((2 * n_slots + TB - 1) / TB, TB, 0, [&]() { verify_kernel(P, R, B, S, &ctr, 0, vlist.data(), &d_count[2]); });
+        launch((2 * n_slots + 63) / 64, 64, (size_t)2 * S.caps.maxmm * 64, [&]() { verify_kernel(P, R, B, S, &ctr, 1, vlist.data(), &d_count[2]); });
+      }
+      if (P.split) launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pairing_split_kernel(P, S, nbest.data()); });
+      else launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pairing_kernel(P, S, nbest.data()); });
     } else {
       auto cap_of = [](int c_) { int c = 1; while (c < c_) c <<= 1; return std::min(c, CTA_SORT_SMEM_MAX); };
       const int c_seed = cap_of(2 * tier.caps.hc), c_pc = cap_of(tier.caps.hc), c_ver = cap_of(tier.caps.cc), c_pair = cap_of(tier.caps.mc);
@@ -240,8 +265,10 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
       const size_t pc_smem = pair_candidates_cta_smem(c_pc, lcap, tier.caps.maxmm, fcap);
       const int pc_nt = pc_smem > 64 * 1024 ? PC_CTA_NT_MAX : CTA_NT;
       launch(n_slots, pc_nt, pc_smem, [&]() { pair_candidates_cta_kernel(P, ix, S, &ctr, c_pc, lcap, fcap, nullptr, nullptr); });
-      launch(2 * n_slots, tier.caps.cc > 1024 ? VERIFY_NT_MAX : CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, [&]() { verify_cta_kernel(P, R, B, S, &ctr, c_ver); });
-      launch(n_slots, CTA_NT, (size_t)c_pair * 10, [&]() { pairing_cta_kernel(P, S, nbest.data(), c_pair); });
+      if (P.split) launch(2 * n_slots, CTA_NT, (size_t)c_ver * 9, [&]() { verify_split_cta_kernel(P, R, B, S, &ctr, c_ver); });
+      else launch(2 * n_slots, tier.caps.cc > 1024 ? VERIFY_NT_MAX : CTA_NT, (size_t)c_ver * 9 + 2 * (size_t)tier.caps.maxmm + 16, [&]() { verify_cta_kernel(P, R, B, S, &ctr, c_ver); });
+      if (P.split) launch((n_slots + TB - 1) / TB, TB, 0, [&]() { pairing_split_kernel(P, S, nbest.data()); });
+      else launch(n_slots, CTA_NT, (size_t)c_pair * 10, [&]() { pairing_cta_kernel(P, S, nbest.data(), c_pair); });
     }
     std::vector<int> ovf((size_t)n_slots + 8);
     int n_ovf = 0;
@@ -260,7 +287,9 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
   launch(1, 128, 0, [&]() { select_kernel(P, 1, chunks, nbest.data(), sel.data(), mt_init); });
   for (int t = tiers_used - 1; t >= 0; --t) {
     const Scratch S = tiers[t].view;
-    if (t > 0) launch(S.n_slots, CTA_NT, 0, [&]() { emit_cta_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
+    if (P.split) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_split_kernel(P, R, B, T, S, sel.data(), (OutPairs *)out_rec.data(), out_n.data(), &ctr); });
+    else if (P.se) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_se_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
+    else if (t > 0) launch(S.n_slots, CTA_NT, 0, [&]() { emit_cta_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
     else {
       std::vector<int4> emit_list((size_t)S.n_slots * max_best + 8);
       int dp_count = 0;
@@ -295,20 +324,26 @@ static RunStats run_case(int seed, int n_pairs, int mrl, const Caps *caps3, int 
 }
 
 int main() {
-  static_assert(sizeof(OutRecord) == sizeof(orc_pe_record), "record layout");
+  static_assert(sizeof(OutRecord) == sizeof(orc_pe_record) && sizeof(OutPairs) == sizeof(orc_pe_record), "record layouts");
   long bad = 0;
-  {  // the tiers as the library sets them up (api.cu: {mrl, 64, 32, 32}, {2 mrl, 1024, 256, 256}, {4 mrl, 65536, 8192, 8192})
-    const int mrl = 80;
-    const Caps caps[3] = {{mrl, 64, 32, 32}, {mrl * 2, 1024, 256, 256}, {mrl * 4, 65536, 8192, 8192}};
-    const RunStats r = run_case(3, 150, mrl, caps, 1, 60);
-    printf("real_tiers: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
-    bad += r.bad;
-  }
-  {  // a first tier too small for most pairs: ordinary pairs through the CTA kernels; -n 3
-    const int mrl = 80;
-    const Caps caps[3] = {{mrl, 6, 2, 2}, {mrl * 2, 40, 6, 6}, {mrl * 4, 65536, 8192, 8192}};   // ... and a second tier that sends some on to the last one
-    const RunStats r = run_case(4, 64, mrl, caps, 3, 60);
-    printf("small_first_tier: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
+  const int mrl = 80;
+  const Caps real[3] = {{mrl, 64, 32, 32}, {mrl * 2, 1024, 256, 256}, {mrl * 4, 65536, 8192, 8192}};   // api.cu's tiers
+  const Caps small[3] = {{mrl, 6, 2, 2}, {mrl * 2, 40, 6, 6}, {mrl * 4, 65536, 8192, 8192}};            // most pairs through the CTA kernels, some to the last tier
+  const Caps real_long[3] = {{150, 64, 32, 32}, {300, 1024, 256, 256}, {600, 65536, 8192, 8192}};
+  const Caps small_long[3] = {{150, 6, 2, 2}, {300, 40, 6, 6}, {600, 65536, 8192, 8192}};
+  struct Case { const char *name; int mode, seed, n, max_best, len; const Caps *caps; int mrl; };
+  const Case cases[] = {
+      {"real_tiers", MODE_CHIP, 3, 130, 1, 60, real, mrl},
+      {"small_first_tier", MODE_CHIP, 4, 64, 3, 60, small, mrl},
+      {"atac_trimming", MODE_ATAC, 5, 70, 1, 60, real, mrl},
+      {"hic_split", MODE_HIC, 6, 60, 1, 120, real_long, 150},
+      {"hic_split_cta", MODE_HIC, 7, 24, 1, 120, small_long, 150},
+      {"single_end", MODE_SE, 8, 90, 2, 60, real, mrl},
+      {"single_end_cta", MODE_SE, 9, 40, 1, 60, small, mrl},
+  };
+  for (const Case &c : cases) {
+    const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len);
+    printf("%%s: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", c.name, r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
     bad += r.bad;
   }
   printf("total_bad=%%ld\n", bad);
@@ -346,7 +381,8 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-w", "-o", str(exe), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-fopenmp"])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=2400)
     assert out.returncode == 0 and "total_bad=0" in out.stdout, out.stdout[-3000:] + out.stderr[-800:]
-    m1 = re.search(r"real_tiers: pairs=(\d+) records=(\d+) tier0=(\d+) tier1=(\d+) tier2=(\d+)", out.stdout)
-    m2 = re.search(r"small_first_tier: pairs=(\d+) records=(\d+) tier0=(\d+) tier1=(\d+) tier2=(\d+)", out.stdout)
-    assert int(m1.group(2)) > 70 and int(m1.group(4)) > 5, out.stdout          # records, and pairs that climbed to the second tier
-    assert int(m2.group(2)) > 40 and int(m2.group(4)) > 30 and int(m2.group(5)) > 3, out.stdout   # most pairs through the CTA kernels, some up to the last tier (512 / 256-thread CTAs)
+    got = {m.group(1): [int(x) for x in m.groups()[1:]] for m in re.finditer(r"(\w+): pairs=(\d+) records=(\d+) tier0=(\d+) tier1=(\d+) tier2=(\d+)", out.stdout)}
+    assert got["real_tiers"][1] > 60 and got["real_tiers"][3] > 5, out.stdout                      # records; pairs that climbed to the second tier
+    assert got["small_first_tier"][1] > 40 and got["small_first_tier"][3] > 30 and got["small_first_tier"][4] > 3, out.stdout   # CTA kernels, up to the last tier
+    assert got["atac_trimming"][1] > 30 and got["hic_split"][1] > 25 and got["single_end"][1] > 40, out.stdout
+    assert got["hic_split_cta"][3] > 5 and got["single_end_cta"][3] > 10, out.stdout
