@@ -33,7 +33,7 @@ int main() {
   std::mt19937 g(61);
   long bad = 0, n_pairs = 0, with_best = 0, n_sel = 0, sampled = 0, rejections = 0;
   // ---- pairing
-  for (int it = 0; it < 110; ++it) {
+  for (int it = 0; it < 70; ++it) {
     const int e = it %% 2 ? 8 : 4, mc = 512;
     DevParams P{};
     P.e = e; P.max_insert = it %% 3 ? 2000 : 1000; P.min_read_len = 30; P.drop_rep = 500000; P.max_best = 1;
@@ -88,7 +88,7 @@ int main() {
   u32 mt_init[624];
   mt_init[0] = 11u;
   for (int i = 1; i < 624; ++i) mt_init[i] = 1812433253u * (mt_init[i - 1] ^ (mt_init[i - 1] >> 30)) + (u32)i;   // std::mt19937(11) right after seeding
-  for (int it = 0; it < 20; ++it) {
+  for (int it = 0; it < 12; ++it) {
     DevParams P{};
     P.max_best = 1 + (int)(g() %% 8); P.se = it %% 10 == 9;
     const int mb = P.max_best;
@@ -156,4 +156,4 @@ def test_pairing_kernels_and_multimapper_sampling(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-2000:] + out.stderr[-800:]
     f = dict(kv.split("=") for kv in out.stdout.split() if "=" in kv)
-    assert int(f["with_best"]) > 60 and int(f["sampled_pairs"]) > 500, out.stdout
+    assert int(f["with_best"]) > 40 and int(f["sampled_pairs"]) > 300, out.stdout

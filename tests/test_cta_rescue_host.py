@@ -30,7 +30,7 @@ int main() {
   std::mt19937 g(29);
   long bad = 0, cases = 0, total_hits = 0, bails = 0, on_boundary = 0;
   const int NTS[4] = {32, 128, 256, 512};
-  for (int it = 0; it < 230; ++it) {
+  for (int it = 0; it < 130; ++it) {
     const int nt = NTS[it %% 4];
     DevParams P{};
     P.k = 17; P.w = 7; P.e = 8; P.min_seeds = 2; P.f0 = (it %% 5 == 0) ? 40 : 500; P.f1 = 1000;
@@ -149,4 +149,4 @@ def test_both_device_forms_of_the_mate_guided_lookup_equal_the_oracle(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-1500:] + out.stderr[-800:]
     f = dict(kv.split("=") for kv in out.stdout.split() if "=" in kv)
-    assert int(f["hits"]) > 10000 and int(f["bails"]) > 10 and int(f["boundary_windows"]) > 1000, out.stdout
+    assert int(f["hits"]) > 5000 and int(f["bails"]) > 6 and int(f["boundary_windows"]) > 800, out.stdout

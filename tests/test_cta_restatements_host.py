@@ -28,7 +28,7 @@ int main() {
   std::mt19937 g(17);
   long bad = 0, n_merge = 0, n_filter = 0, kept_unpaired = 0;
   const int NTS[5] = {32, 64, 128, 256, 512};
-  for (int it = 0; it < 300; ++it) {
+  for (int it = 0; it < 160; ++it) {
     const int nt = NTS[it %% 5], e = 1 + (int)(g() %% 12);
     const int n_seq = 1 + (int)(g() %% 3);
     const u32 span = 50 + g() %% 5000;
@@ -100,4 +100,4 @@ def test_cta_merge_and_pe_filter_equal_the_sequential_sweeps(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-1500:] + out.stderr[-500:]
     f = dict(kv.split("=") for kv in out.stdout.split() if "=" in kv)
-    assert int(f["unpaired_flagged"]) > 30, out.stdout   # the unpaired-candidate rule was exercised
+    assert int(f["unpaired_flagged"]) > 15, out.stdout   # the unpaired-candidate rule was exercised

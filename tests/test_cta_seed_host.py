@@ -55,7 +55,7 @@ int main() {
     for (int i = 0; i < n; ++i) if (pk[i] != pw[i].first || pt[i] != pw[i].second) { if (bad < 5) printf("PAIRS n=%%d sm=%%d nt=%%d at %%d\n", n, sm_cap, nt, i); ++bad; break; }
   }
   // ---- clustering
-  for (int it = 0; it < 90; ++it) {
+  for (int it = 0; it < 54; ++it) {
     const int nt = NTS[it %% 3], e = 1 + (int)(g() %% 12), need = 1 + (int)(g() %% 2);
     const int nh = (int)(g() %% (it %% 4 == 0 ? 5000 : 600));
     const u32 n_mm = 1 + g() %% 30;
@@ -81,7 +81,7 @@ int main() {
   }
   // ---- minimizers of a long read by the CTA
   const int KW[6][2] = {{17, 7}, {21, 10}, {15, 11}, {16, 7}, {17, 5}, {19, 7}};
-  for (int it = 0; it < 84; ++it) {
+  for (int it = 0; it < 54; ++it) {
     const int k = KW[it %% 6][0], w = KW[it %% 6][1];
     const int len = 30 + (int)(g() %% 900);
     std::string r((size_t)len, 'A');

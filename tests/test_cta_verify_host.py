@@ -37,7 +37,7 @@ static char comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? '
 int main() {
   std::mt19937 g(53);
   long bad = 0, cases = 0, fast = 0, ruled = 0, mappings = 0;
-  for (int it = 0; it < 260; ++it) {
+  for (int it = 0; it < 150; ++it) {
     const int e = it %% 2 ? 8 : 4, nt = it %% 3 == 0 ? 256 : 128;
     const int L = 40 + (int)(g() %% 100);
     const u32 ref_len = 30000 + g() %% 20000;
@@ -174,4 +174,4 @@ def test_verify_cta_kernel_equals_the_oracles_draft_mapping_generation(tmp_path)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1800)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout[-2000:] + out.stderr[-800:]
     f = dict(kv.split("=") for kv in out.stdout.split() if "=" in kv)
-    assert int(f["single_candidate"]) >= 10 and int(f["group_rule"]) > 100 and int(f["mappings"]) > 1000, out.stdout
+    assert int(f["single_candidate"]) >= 6 and int(f["group_rule"]) > 60 and int(f["mappings"]) > 600, out.stdout
