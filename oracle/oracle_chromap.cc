@@ -1709,6 +1709,15 @@ int orc_emit_test(const orc_params *p, const char *ref_seq, uint32_t ref_len, co
   std::mt19937 gen(11);
   return finish_pair(*p, ref, gen, r, neg, L, rs, sup, read_id, out, cap, nullptr, nullptr);
 }
+// CorrectBarcodeAt (chromap.cc:572-799) for one barcode, for tests of the device kernel: returns 1 if the (possibly corrected)
+// barcode is in the whitelist; *out_key = the 2-bit key of the barcode afterwards; counters as the mapper keeps them.
+int orc_correct_barcode_test(const orc_whitelist *wl, int err_threshold, double prob_threshold, const char *bc, const char *qual, uint32_t len,
+                             uint64_t *out_key, uint64_t *n_in_whitelist, uint64_t *n_corrected) {
+  std::string b(bc, len);
+  const bool ok = correct_barcode(*wl, err_threshold, prob_threshold, &b[0], qual, len, n_in_whitelist, n_corrected);
+  *out_key = barcode_seed(b.data(), len);
+  return ok ? 1 : 0;
+}
 // the two drop-off aligners of the split path (alignment.cc:197-283 / :285-376), for tests of the device formulation
 int orc_align_dropoff(int e, const char *pattern, const char *text, int read_len, int from_3_end, int *end_pos, int *read_len_out) {
   return from_3_end ? align_dropoff_3end(e, pattern, text, read_len, end_pos, read_len_out) : align_dropoff(e, pattern, text, read_len, end_pos, read_len_out);
