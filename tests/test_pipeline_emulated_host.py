@@ -11,7 +11,8 @@ Runs: `--preset chip` with the real tier capacities (64 / 32 / 32 ...) on a refe
 allows, N's and junk pairs; and tiny first- and second-tier capacities that push most ordinary pairs through the CTA kernels and
 some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3; `--preset atac` (adapter
 trimming by prep_kernel on read-through pairs); `--preset hic` (split alignment: verify_split / pairing_split / emit_split and the
-CTA form, chimeric reads, pairs records); single-end (emit_se_kernel, a fresh generator per read), each also through the CTA tiers."""
+CTA form, chimeric reads, pairs records); single-end (emit_se_kernel, a fresh generator per read), each also through the CTA tiers; `--SAM` (emit_sam_kernel: spans and CIGARs by
+the diagonal-band aligner, against the oracle's SAM cores)."""
 import os
 import re
 import subprocess
@@ -30,6 +31,7 @@ struct ulonglong2 { u64 x, y; };
 #define __host__
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __noinline__
 #define __ldg(p) (*(p))
 static u64 *g_dyn_smem = nullptr;
 static inline u64 atomicAdd(u64 *p, u64 v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -81,7 +83,7 @@ static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend
 
 struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
 
-enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3 };
+enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3, MODE_SAM = 4 };
 static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base) {
   std::mt19937 g((unsigned)seed);
   RunStats rs;
@@ -148,7 +150,10 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   orc_mapper *om = orc_mapper_create(&op, oix, oref);
   std::vector<orc_pe_record> want((size_t)n * max_best + 8);
   const u32 first_read_id = 5000;
-  const long n_want = mode == MODE_SE ? (long)orc_map_reads_se(om, (u32)n, s1.data(), o1.data(), first_read_id, want.data(), (long)want.size(), 1)
+  std::vector<orc_sam_record> want_sam;
+  long n_want_sam = 0;
+  if (mode == MODE_SAM) { want_sam.resize((size_t)n * max_best + 8); n_want_sam = (long)orc_map_sam_cores(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want_sam.data(), (long)want_sam.size()); }
+  const long n_want = mode == MODE_SAM ? 0 : mode == MODE_SE ? (long)orc_map_reads_se(om, (u32)n, s1.data(), o1.data(), first_read_id, want.data(), (long)want.size(), 1)
                                       : (long)orc_map_pairs(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want.data(), (long)want.size(), nullptr);
   // ---- device objects
   DevParams P{};
@@ -193,6 +198,8 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   Counters ctr{};
   std::vector<int> nbest((size_t)n, 0), sel((size_t)n * max_best, 0), out_n((size_t)n + 1, 0);
   std::vector<OutRecord> out_rec((size_t)n * max_best);
+  std::vector<OutSam> out_sam(mode == MODE_SAM ? (size_t)n * max_best : 1);
+  memset(out_sam.data(), 0, out_sam.size() * sizeof(OutSam));
   int n_slots = n, tiers_used = 0;
   const int *pair_list = nullptr;
   const int TB = 128;
@@ -287,7 +294,8 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   launch(1, 128, 0, [&]() { select_kernel(P, 1, chunks, nbest.data(), sel.data(), mt_init); });
   for (int t = tiers_used - 1; t >= 0; --t) {
     const Scratch S = tiers[t].view;
-    if (P.split) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_split_kernel(P, R, B, T, S, sel.data(), (OutPairs *)out_rec.data(), out_n.data(), &ctr); });
+    if (mode == MODE_SAM) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_sam_kernel(P, R, B, T, S, sel.data(), out_sam.data(), out_n.data(), &ctr); });
+    else if (P.split) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_split_kernel(P, R, B, T, S, sel.data(), (OutPairs *)out_rec.data(), out_n.data(), &ctr); });
     else if (P.se) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_se_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
     else if (t > 0) launch(S.n_slots, CTA_NT, 0, [&]() { emit_cta_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
     else {
@@ -299,6 +307,28 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   }
   g_emu_leavable = false;
   // ---- compare, pair by pair
+  if (mode == MODE_SAM) {
+    static_assert(sizeof(OutSam) == sizeof(orc_sam_record), "SAM record layout");
+    long si = 0;
+    for (int p = 0; p < n; ++p) {
+      long w0 = si;
+      while (si < n_want_sam && want_sam[si].read_id == first_read_id + (u32)p) ++si;
+      const int nw = (int)(si - w0);
+      ++rs.pairs; rs.records += nw;
+      bool ok = out_n[p] == nw;
+      for (int r = 0; ok && r < nw; ++r) {
+        const OutSam &a = out_sam[(size_t)p * max_best + r]; const orc_sam_record &b = want_sam[w0 + r];
+        ok = a.read_id == b.read_id && a.rid == b.rid && a.pos[0] == b.pos[0] && a.pos[1] == b.pos[1] && a.end[0] == b.end[0] && a.end[1] == b.end[1] && a.strand[0] == b.strand[0] &&
+             a.strand[1] == b.strand[1] && a.mapq == b.mapq && a.is_unique == b.is_unique && a.secondary == b.secondary && a.n_cigar[0] == b.n_cigar[0] && a.n_cigar[1] == b.n_cigar[1] &&
+             a.overflow == b.overflow;
+        for (int m = 0; ok && m < 2; ++m) for (int q = 0; ok && q < a.n_cigar[m]; ++q) ok = a.cigar[m][q] == b.cigar[m][q];
+      }
+      if (!ok) { if (rs.bad < 8) printf("SAM PAIR %%d (seed %%d): records %%d / %%d\n", p, seed, out_n[p], nw); ++rs.bad; }
+    }
+    if (si != n_want_sam) { printf("oracle SAM cores not consumed: %%ld of %%ld\n", si, n_want_sam); ++rs.bad; }
+    orc_mapper_free(om); orc_index_free(oix); orc_reference_free(oref);
+    return rs;
+  }
   long wi = 0;
   for (int p = 0; p < n; ++p) {
     long w0 = wi;
@@ -340,6 +370,7 @@ int main() {
       {"hic_split_cta", MODE_HIC, 7, 16, 1, 120, small_long, 150},
       {"single_end", MODE_SE, 8, 60, 2, 60, real, mrl},
       {"single_end_cta", MODE_SE, 9, 28, 1, 60, small, mrl},
+      {"sam_cores", MODE_SAM, 10, 56, 2, 60, real, mrl},
   };
   for (const Case &c : cases) {
     const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len);
@@ -359,8 +390,8 @@ def _between(s, a, b):
 
 def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     src_dir = os.path.join(ROOT, "chromap_b200", "csrc")
-    files = ["device_common.cuh", "minimizers.cuh", "pipeline_kernels.cuh", "cta_pair_candidates.cuh", "cta_verify_pairing.cuh"]
-    text = "\n".join(open(os.path.join(src_dir, f)).read() for f in files)
+    files = ["device_common.cuh", "minimizers.cuh", "pipeline_kernels.cuh", "cta_pair_candidates.cuh", "cta_verify_pairing.cuh", "sam_kernels.cuh"]
+    text = "\n".join(open(os.path.join(src_dir, f)).read() for f in files).replace("#ifdef __CUDACC__", "#if 1")
     api = open(os.path.join(src_dir, "api.cu")).read()
     text = re.sub(r'#include [<"][^\n]*', "", text).replace("#pragma once", "")
     text = re.sub(r'asm volatile\(.*?\)\s*;', ';', text)
@@ -385,4 +416,4 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     assert got["real_tiers"][1] > 45 and got["real_tiers"][3] > 5, out.stdout                      # records; pairs that climbed to the second tier
     assert got["small_first_tier"][1] > 30 and got["small_first_tier"][3] > 20 and got["small_first_tier"][4] > 3, out.stdout   # CTA kernels, up to the last tier
     assert got["atac_trimming"][1] > 20 and got["hic_split"][1] > 18 and got["single_end"][1] > 25, out.stdout
-    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6, out.stdout
+    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25, out.stdout
