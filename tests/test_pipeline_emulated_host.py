@@ -1,12 +1,14 @@
-"""The device pipeline after the front end — cluster -> pair_candidates -> verify -> pairing (tier 0, thread kernels), prep ->
+"""The whole device pipeline — seed_front -> cluster -> pair_candidates -> verify -> pairing (tier 0, thread kernels), prep ->
 seed_cta -> pair_candidates_cta -> verify_cta -> pairing_cta (overflow tiers, one CTA per read / pair), overflow collection
 between the tiers, select, emit (+ deferred tracebacks) / emit_cta — compiled from the UNCHANGED kernel sources
-(device_common.cuh, minimizers.cuh, pipeline_kernels.cuh, cta_pair_candidates.cuh, cta_verify_pairing.cuh) and run on the host
+(device_common.cuh, minimizers.cuh, pipeline_kernels.cuh, seed_front.cuh, cta_pair_candidates.cuh, cta_verify_pairing.cuh, sam_kernels.cuh) and run on the host
 emulation of CTAs (tests/cta_emu.h) with the launch sequence, grid / block sizes, shared-memory sizes and scratch layout of
 api.cu's run_lane (the layout code itself is cut out of api.cu), against the oracle's mapper (`orc_map_pairs`, pinned to the
 reference binary by tests/test_oracle_golden.py): every pair's records, field by field.
-The front end (seed_front_kernel: cp.async.bulk / mbarrier PTX) is the one kernel that cannot run here; its output — probed
-minimizer records in the lane-interleaved layout — is produced from the oracle's minimizers and khash lookups.
+The front end runs too (seed_front_kernel: persistent grid, double-buffered read tiles, packed-key minimizer scan, table probes,
+lane-interleaved records): only its six PTX wrappers (mbarrier.* / cp.async.bulk) are replaced by host equivalents — an mbarrier
+word with byte and arrival counts, a copy that signals its bytes — and its records are also compared one by one with the
+oracle's minimizers and khash lookups.
 Runs: `--preset chip` with the real tier capacities (64 / 32 / 32 ...) on a reference with repeat families, reads longer than the first tier
 allows, N's and junk pairs; and tiny first- and second-tier capacities that push most ordinary pairs through the CTA kernels and
 some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3; `--preset atac` (adapter
@@ -46,6 +48,34 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline u32 __funnelshift_r(u32 lo, u32 hi, u32 s) { return (u32)((((u64)hi << 32) | lo) >> (s & 31)); }
+// ---- host equivalents of seed_front.cuh's six PTX wrappers (mbarrier + cp.async.bulk); everything else of that file is compiled as it is.
+// An mbarrier word: bits 0-31 = bytes still expected, bits 32-47 = arrivals still expected, bits 48-63 = completed phases.  The
+// "copy engine" copies at issue time and then signals its bytes, like complete_tx.
+#include <sched.h>
+static inline void emu_mbar_settle(u64 *bar) {   // a phase completes when no arrival and no byte is outstanding: re-arm with one arrival
+  u64 v = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+  if ((v & 0xFFFFFFFFFFFFull) == 0) __atomic_store_n(bar, ((v >> 48) + 1) << 48 | (1ull << 32), __ATOMIC_RELEASE);
+}
+static inline u32 smem_u32(const void *p) { return (u32)(size_t)p; }
+static inline void mbar_init(u64 *bar, u32 count) { __atomic_store_n(bar, (u64)count << 32, __ATOMIC_RELEASE); }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {   // (called by one thread, before its copies)
+  u64 v = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+  v = (v & 0xFFFF000000000000ull) | ((((v >> 32) & 0xFFFF) - 1) << 32) | (u64)((u32)v + bytes);
+  __atomic_store_n(bar, v, __ATOMIC_RELEASE);
+  emu_mbar_settle(bar);
+}
+static inline bool mbar_try_wait(u64 *bar, u32 parity) {
+  const bool done = (((__atomic_load_n(bar, __ATOMIC_ACQUIRE) >> 48) & 1u) != parity);
+  if (!done) sched_yield();
+  return done;
+}
+static inline void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  memcpy(dst, src, bytes);
+  u64 v = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+  __atomic_store_n(bar, (v & 0xFFFFFFFF00000000ull) | (u64)((u32)v - bytes), __ATOMIC_RELEASE);
+  emu_mbar_settle(bar);
+}
 '''
 
 MAIN = r'''
@@ -84,7 +114,7 @@ static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend
 struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
 
 enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3, MODE_SAM = 4 };
-static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base) {
+static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base, bool front_only = false, int K = 17, int W = 7) {
   std::mt19937 g((unsigned)seed);
   RunStats rs;
   // ---- reference: two sequences, a 300 bp family with many copies, a 2 kb segmental repeat, an N run
@@ -100,7 +130,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   const uint64_t offs[3] = {0, seq[0].size(), seq[0].size() + seq[1].size()};
   const char *names[2] = {"chrA", "chrB"};
   orc_reference *oref = orc_reference_from_memory(2, concat.data(), offs, names);
-  orc_index *oix = orc_index_build(oref, 17, 7);
+  orc_index *oix = orc_index_build(oref, K, W);
   // ---- reads
   std::string s1, s2;
   std::vector<u32> o1{0}, o2{0};
@@ -158,7 +188,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   // ---- device objects
   DevParams P{};
   P.e = op.error_threshold; P.min_seeds = op.min_num_seeds; P.f0 = op.max_seed_freq0; P.f1 = op.max_seed_freq1; P.max_best = max_best; P.max_insert = op.max_insert_size;
-  P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = op.trim_adapters; P.k = 17; P.w = 7; P.lanes = P.e < 8 ? 8 : 4; P.split = op.split_alignment;
+  P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = op.trim_adapters; P.k = K; P.w = W; P.lanes = P.e < 8 ? 8 : 4; P.split = op.split_alignment;
   P.se = mode == MODE_SE;
   const uint32_t *kf; const uint64_t *kk, *kv, *kocc; uint32_t n_occ = 0;
   const uint32_t nb = orc_index_arrays(oix, &kf, &kk, &kv, &kocc, &n_occ);
@@ -175,7 +205,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
     slots[sidx] = ulonglong2{(u64)kk[i], (u64)kv[i]};
   }
   DevIndex ix{};
-  ix.slots = slots.data(); ix.n_slots_mask = n_slots_t - 1; ix.shift = 64 - lg; ix.occ = (const u64 *)kocc; ix.n_occ = n_occ; ix.k = 17; ix.w = 7;
+  ix.slots = slots.data(); ix.n_slots_mask = n_slots_t - 1; ix.shift = 64 - lg; ix.occ = (const u64 *)kocc; ix.n_occ = n_occ; ix.k = K; ix.w = W;
   std::string refmem(64, '\0');
   u64 roff[2]; u32 rlen[2];
   for (int q = 0; q < 2; ++q) { roff[q] = refmem.size(); rlen[q] = (u32)seq[q].size(); refmem += seq[q]; refmem.append(64 + (64 - refmem.size() %% 64) %% 64, '\0'); }
@@ -210,42 +240,39 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
     const Scratch S = tier.view;
     rs.tier_pairs[t] = n_slots;
     if (t == 0) {
-      // the front end's output (seed_front_kernel), from the oracle's minimizers and table lookups
-      if (P.trim) launch((n_slots + TB - 1) / TB, TB, 0, [&]() { prep_kernel(P, B, S); });   // adapter trimming first (the front end then runs "prepped")
+      // the front end: [adapter trimming] + length filter + minimizers + table probes over staged read tiles (seed_front_kernel, a
+      // persistent grid: three CTAs here, so that every CTA walks several tiles through both stages of its double buffer)
+      if (P.trim) launch((n_slots + TB - 1) / TB, TB, 0, [&]() { prep_kernel(P, B, S); });
+      {
+        const int tiles = (n_slots + SF_TILE - 1) / SF_TILE;
+        launch(front_only ? 2 : std::min(tiles, 3), SF_NT, seed_front_smem_bytes(S.caps.maxmm) + 16, [&]() { if (K == 17 && W == 7) seed_front_kernel<true>(P, ix, B, S, &ctr, P.trim ? 1 : 0, 0, n_slots); else seed_front_kernel<false>(P, ix, B, S, &ctr, P.trim ? 1 : 0, 0, n_slots); });
+      }
+      // cross-check of its records against the oracle's minimizers and khash lookups (what the kernel must have written)
       for (int slot = 0; slot < n_slots; ++slot) {
-        int len[2] = {(int)(o1[slot + 1] - o1[slot]), P.se ? 0 : (int)(o2[slot + 1] - o2[slot])};
-        int status = ST_OK;
-        if (P.trim) { status = S.pmeta[slot].status; len[0] = S.rmeta[2 * slot].len; len[1] = S.rmeta[2 * slot + 1].len; }
-        else {
-          if (len[0] < P.min_read_len || (!P.se && len[1] < P.min_read_len)) status = ST_DROP;
-          else if (len[0] > S.caps.maxmm || len[1] > S.caps.maxmm) status = ST_OVERFLOW;
-          PairMeta pm{}; pm.status = status;
-          S.pmeta[slot] = pm;
-        }
-        for (int mate = 0; mate < 2; ++mate) {
-          ReadMeta z; memset(&z, 0, sizeof(z));
-          z.len = len[mate];
-          if (status == ST_OK && !(P.se && mate == 1)) {
-            const char *rd = mate == 0 ? s1.data() + o1[slot] : s2.data() + o2[slot];
-            std::vector<uint64_t> mh(2048), mhit(2048);
-            const int nm = orc_minimizers(rd, (u32)len[mate], 0, 17, 7, mh.data(), mhit.data(), 2048);
-            z.n_mm = nm;
-            if (nm > S.caps.maxmm) { S.pmeta[slot].status = ST_OVERFLOW; }
-            else {
-              const size_t mb_ = mm_base(S, slot, mate);
-              const int ms = mm_stride(S);
-              for (int i = 0; i < nm; ++i) {
-                uint64_t key = 0, val = 0;
-                const int found = orc_index_lookup(oix, mh[i], &key, &val);
-                const u32 kind = found ? ((key & 1) ? 1u : 2u) : 0u;
-                S.mm_val[mb_ + (size_t)i * ms] = found ? val : 0;
-                S.mm_pos[mb_ + (size_t)i * ms] = ((u32)mhit[i] & 0x3FFFFFFFu) | (kind << 30);
-              }
-              z.mm_done = 1;
-            }
+        if (S.pmeta[slot].status != ST_OK) continue;
+        for (int mate = 0; mate < (P.se ? 1 : 2); ++mate) {
+          const ReadMeta &z = S.rmeta[2 * slot + mate];
+          const char *rd = mate == 0 ? s1.data() + o1[slot] : s2.data() + o2[slot];
+          std::vector<uint64_t> mh(4096), mhit(4096);
+          const int nm = orc_minimizers(rd, (u32)z.len, 0, K, W, mh.data(), mhit.data(), 4096);
+          bool ok = z.n_mm == nm && z.mm_done == 1;
+          const size_t mb_ = mm_base(S, slot, mate);
+          const int ms = mm_stride(S);
+          for (int i = 0; ok && i < nm; ++i) {
+            uint64_t key = 0, val = 0;
+            const int found = orc_index_lookup(oix, mh[i], &key, &val);
+            const u32 kind = found ? ((key & 1) ? 1u : 2u) : 0u;
+            ok = S.mm_pos[mb_ + (size_t)i * ms] == (((u32)mhit[i] & 0x3FFFFFFFu) | (kind << 30)) && (!found || S.mm_val[mb_ + (size_t)i * ms] == val);
           }
-          S.rmeta[2 * slot + mate] = z;
+          if (!ok) { if (rs.bad < 8) printf("FRONT END pair %%d mate %%d: n_mm %%d / %%d\n", slot, mate, z.n_mm, nm); ++rs.bad; }
         }
+      }
+      if (front_only) {   // (many tiles per CTA: both stages of the double buffer are refilled and both barrier phases flip)
+        rs.pairs = n_slots;
+        for (int slot = 0; slot < n_slots; ++slot) rs.records += S.rmeta[2 * slot].n_mm + S.rmeta[2 * slot + 1].n_mm;
+        g_emu_leavable = false;
+        orc_mapper_free(om); orc_index_free(oix); orc_reference_free(oref);
+        return rs;
       }
       std::vector<int> vlist((size_t)2 * n_slots + 8), rlist((size_t)n_slots + 8);
       int d_count[4] = {0, 0, 0, 0};
@@ -361,7 +388,7 @@ int main() {
   const Caps small[3] = {{mrl, 6, 2, 2}, {mrl * 2, 40, 6, 6}, {mrl * 4, 65536, 8192, 8192}};            // most pairs through the CTA kernels, some to the last tier
   const Caps real_long[3] = {{150, 64, 32, 32}, {300, 1024, 256, 256}, {600, 65536, 8192, 8192}};
   const Caps small_long[3] = {{150, 6, 2, 2}, {300, 40, 6, 6}, {600, 65536, 8192, 8192}};
-  struct Case { const char *name; int mode, seed, n, max_best, len; const Caps *caps; int mrl; };
+  struct Case { const char *name; int mode, seed, n, max_best, len; const Caps *caps; int mrl; bool front_only = false; int k = 17, w = 7; };
   const Case cases[] = {
       {"real_tiers", MODE_CHIP, 3, 100, 1, 60, real, mrl},
       {"small_first_tier", MODE_CHIP, 4, 48, 3, 60, small, mrl},
@@ -371,9 +398,12 @@ int main() {
       {"single_end", MODE_SE, 8, 60, 2, 60, real, mrl},
       {"single_end_cta", MODE_SE, 9, 28, 1, 60, small, mrl},
       {"sam_cores", MODE_SAM, 10, 56, 2, 60, real, mrl},
+      {"front_end_only", MODE_CHIP, 11, 600, 1, 60, real, mrl, true},
+      {"front_end_k21_w10", MODE_CHIP, 12, 200, 1, 60, real, mrl, true, 21, 10},     // the run-time scan (seed_front_kernel<false>)
+      {"front_end_k16_w5", MODE_CHIP, 13, 200, 1, 60, real, mrl, true, 16, 5},       // even k: strand-symmetric k-mers
   };
   for (const Case &c : cases) {
-    const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len);
+    const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len, c.front_only, c.k, c.w);
     printf("%%s: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", c.name, r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
     bad += r.bad;
   }
@@ -390,8 +420,13 @@ def _between(s, a, b):
 
 def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     src_dir = os.path.join(ROOT, "chromap_b200", "csrc")
-    files = ["device_common.cuh", "minimizers.cuh", "pipeline_kernels.cuh", "cta_pair_candidates.cuh", "cta_verify_pairing.cuh", "sam_kernels.cuh"]
+    files = ["device_common.cuh", "minimizers.cuh", "pipeline_kernels.cuh", "seed_front.cuh", "cta_pair_candidates.cuh", "cta_verify_pairing.cuh", "sam_kernels.cuh"]
     text = "\n".join(open(os.path.join(src_dir, f)).read() for f in files).replace("#ifdef __CUDACC__", "#if 1")
+    # seed_front.cuh's six PTX wrappers (mbarrier, cp.async.bulk) are the only device code replaced: host equivalents in PRE
+    a = text.index("// ---- mbarrier + bulk copy (PTX ISA 8.x, sm_90+)")
+    b = text.index("// ---- the kernel ------", a)
+    text = text[:a] + text[b:]
+    text = text.replace("extern __shared__ __align__(16) u8 sf_smem[];", "u8 *sf_smem = (u8 *)g_dyn_smem;")
     api = open(os.path.join(src_dir, "api.cu")).read()
     text = re.sub(r'#include [<"][^\n]*', "", text).replace("#pragma once", "")
     text = re.sub(r'asm volatile\(.*?\)\s*;', ';', text)
@@ -416,4 +451,4 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     assert got["real_tiers"][1] > 45 and got["real_tiers"][3] > 5, out.stdout                      # records; pairs that climbed to the second tier
     assert got["small_first_tier"][1] > 30 and got["small_first_tier"][3] > 20 and got["small_first_tier"][4] > 3, out.stdout   # CTA kernels, up to the last tier
     assert got["atac_trimming"][1] > 20 and got["hic_split"][1] > 18 and got["single_end"][1] > 25, out.stdout
-    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25, out.stdout
+    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25 and got["front_end_only"][1] > 5000 and got["front_end_k21_w10"][1] > 800 and got["front_end_k16_w5"][1] > 1500, out.stdout
