@@ -86,6 +86,7 @@ extern "C" {
 struct HostTier {
   Caps caps;
   std::vector<char> mem;
+  std::vector<std::vector<char>> parts;   // EMU_EXACT_SCRATCH: every scratch array its own exactly sized allocation (AddressSanitizer then sees overruns between them)
   Scratch view;
   std::vector<int> list;   // pair list of this tier (empty = identity)
 };
@@ -100,6 +101,17 @@ static void tier_prepare_host(HostTier &t, int n_slots, const int *pair_list, bo
   S.mm_hash = (u64 *)(b + o[2]); S.mm_val = (u64 *)(b + o[3]); S.mm_pos = (u32 *)(b + o[4]);
   S.hits = (u64 *)(b + o[5]); S.cand_pos = (u64 *)(b + o[6]); S.cand_cnt = (u8 *)(b + o[7]);
   S.map_pos = (u64 *)(b + o[8]); S.map_err = (short *)(b + o[9]); S.map_split = (int *)(b + o[10]);
+  if (getenv("EMU_EXACT_SCRATCH")) {
+    const Caps &c = t.caps;
+    const size_t slots = (size_t)n_slots, R = 2 * slots, Rm = interleaved ? 2 * ((slots + 31) / 32 * 32) : R;
+    const size_t sz[11] = {R * sizeof(ReadMeta), slots * sizeof(PairMeta), interleaved ? 0 : R * c.maxmm * 8, Rm * c.maxmm * 8, Rm * c.maxmm * 4, R * 2 * (size_t)c.hc * 8,
+                           R * 6 * (size_t)c.cc * 8, R * 6 * (size_t)c.cc, R * 2 * (size_t)c.mc * 8, R * 2 * (size_t)c.mc * 2, R * 2 * (size_t)c.mc * 4};
+    t.parts.assign(11, std::vector<char>());
+    for (int i = 0; i < 11; ++i) t.parts[(size_t)i].assign(sz[i] ? sz[i] : 8, (char)0x5A);
+    S.rmeta = (ReadMeta *)t.parts[0].data(); S.pmeta = (PairMeta *)t.parts[1].data(); S.mm_hash = (u64 *)t.parts[2].data(); S.mm_val = (u64 *)t.parts[3].data();
+    S.mm_pos = (u32 *)t.parts[4].data(); S.hits = (u64 *)t.parts[5].data(); S.cand_pos = (u64 *)t.parts[6].data(); S.cand_cnt = (u8 *)t.parts[7].data();
+    S.map_pos = (u64 *)t.parts[8].data(); S.map_err = (short *)t.parts[9].data(); S.map_split = (int *)t.parts[10].data();
+  }
 }
 static std::vector<u64> g_smem;
 template <typename F>
@@ -450,6 +462,8 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     san = os.environ.get("CMX_EMU_SANITIZE", "")
     flags = ["-fsanitize=" + san, "-g", "-fno-omit-frame-pointer"] if san in ("address", "thread") else []
     subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-w"] + flags + ["-o", str(exe), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-fopenmp"])
+    if san == "address":
+        os.environ["EMU_EXACT_SCRATCH"] = "1"
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=7200, env=env)
     assert out.returncode == 0 and "total_bad=0" in out.stdout, out.stdout[-3000:] + out.stderr[-800:]
