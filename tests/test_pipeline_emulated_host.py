@@ -14,7 +14,8 @@ allows, N's and junk pairs; and tiny first- and second-tier capacities that push
 some of them up to the last tier (512-thread pair_candidates_cta, 256-thread verify_cta), with -n 3; `--preset atac` (adapter
 trimming by prep_kernel on read-through pairs); `--preset hic` (split alignment: verify_split / pairing_split / emit_split and the
 CTA form, chimeric reads, pairs records); single-end (emit_se_kernel, a fresh generator per read), each also through the CTA tiers; `--SAM` (emit_sam_kernel: spans and CIGARs by
-the diagonal-band aligner, against the oracle's SAM cores)."""
+the diagonal-band aligner, against the oracle's SAM cores); a 420-copy repeat family (thousands of hits and hundreds of candidates per
+read, the real capacities up to the last tier)."""
 import os
 import re
 import subprocess
@@ -126,14 +127,14 @@ static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend
 struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
 
 enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3, MODE_SAM = 4 };
-static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base, bool front_only = false, int K = 17, int W = 7) {
+static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base, bool front_only = false, int K = 17, int W = 7, int fam_copies = 90) {
   std::mt19937 g((unsigned)seed);
   RunStats rs;
   // ---- reference: two sequences, a 300 bp family with many copies, a 2 kb segmental repeat, an N run
-  std::string seq[2] = {std::string(70000, 'A'), std::string(50000, 'A')};
+  std::string seq[2] = {std::string(fam_copies > 200 ? 260000 : 70000, 'A'), std::string(fam_copies > 200 ? 200000 : 50000, 'A')};
   for (auto &s : seq) for (auto &c : s) c = "ACGT"[g() %% 4];
   std::string fam(300, 'A'); for (auto &c : fam) c = "ACGT"[g() %% 4];
-  for (int q = 0; q < 90; ++q) { std::string f2 = fam; for (int x = 0; x < (int)(g() %% 4); ++x) f2[g() %% 300] = "ACGT"[g() %% 4]; std::string &s = seq[g() %% 2]; s.replace(500 + g() %% (s.size() - 1500), 300, f2); }
+  for (int q = 0; q < fam_copies; ++q) { std::string f2 = fam; for (int x = 0; x < (int)(g() %% 4); ++x) f2[g() %% 300] = "ACGT"[g() %% 4]; std::string &s = seq[g() %% 2]; s.replace(500 + g() %% (s.size() - 1500), 300, f2); }
   std::string seg(2000, 'A'); for (auto &c : seg) c = "ACGT"[g() %% 4];
   for (int q = 0; q < 12; ++q) { std::string &s = seq[g() %% 2]; s.replace(1000 + g() %% (s.size() - 4000), 2000, seg); }
   seq[0].replace(30000, 80, std::string(80, 'N'));
@@ -155,7 +156,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
     const int frag = std::max(L1, L2) + (int)(g() %% 350);
     size_t at = 200 + g() %% (rsq.size() - frag - 400);
     std::string F = rsq.substr(at, (size_t)frag);
-    if (kind == 2) { F = fam + std::string(rsq, at, (size_t)std::max(0, frag - 300)); F.resize((size_t)frag, 'A'); }   // inside the repeat family
+    if (kind == 2 || (fam_copies > 200 && kind %% 2 == 0)) { F = fam + std::string(rsq, at, (size_t)std::max(0, frag - 300)); F.resize((size_t)frag, 'A'); }   // inside the repeat family
     if (kind == 3) for (auto &c : F) c = "ACGT"[g() %% 4];                                                             // junk
     std::string a = F.substr(0, (size_t)L1), b = revc(F.substr((size_t)(frag - L2), (size_t)L2));
     if (mode == MODE_ATAC && g() %% 3 == 0 && std::min(L1, L2) > 40) {   // a fragment shorter than the reads: both mates run through into adapter sequence
@@ -400,7 +401,7 @@ int main() {
   const Caps small[3] = {{mrl, 6, 2, 2}, {mrl * 2, 40, 6, 6}, {mrl * 4, 65536, 8192, 8192}};            // most pairs through the CTA kernels, some to the last tier
   const Caps real_long[3] = {{150, 64, 32, 32}, {300, 1024, 256, 256}, {600, 65536, 8192, 8192}};
   const Caps small_long[3] = {{150, 6, 2, 2}, {300, 40, 6, 6}, {600, 65536, 8192, 8192}};
-  struct Case { const char *name; int mode, seed, n, max_best, len; const Caps *caps; int mrl; bool front_only = false; int k = 17, w = 7; };
+  struct Case { const char *name; int mode, seed, n, max_best, len; const Caps *caps; int mrl; bool front_only = false; int k = 17, w = 7, fam_copies = 90; };
   const Case cases[] = {
       {"real_tiers", MODE_CHIP, 3, 100, 1, 60, real, mrl},
       {"small_first_tier", MODE_CHIP, 4, 48, 3, 60, small, mrl},
@@ -410,12 +411,13 @@ int main() {
       {"single_end", MODE_SE, 8, 60, 2, 60, real, mrl},
       {"single_end_cta", MODE_SE, 9, 28, 1, 60, small, mrl},
       {"sam_cores", MODE_SAM, 10, 56, 2, 60, real, mrl},
+      {"heavy_repeats", MODE_CHIP, 14, 14, 2, 60, real, mrl, false, 17, 7, 420},       // a 420-copy family: thousands of hits, hundreds of candidates per read, up to the last tier
       {"front_end_only", MODE_CHIP, 11, 600, 1, 60, real, mrl, true},
       {"front_end_k21_w10", MODE_CHIP, 12, 200, 1, 60, real, mrl, true, 21, 10},     // the run-time scan (seed_front_kernel<false>)
       {"front_end_k16_w5", MODE_CHIP, 13, 200, 1, 60, real, mrl, true, 16, 5},       // even k: strand-symmetric k-mers
   };
   for (const Case &c : cases) {
-    const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len, c.front_only, c.k, c.w);
+    const RunStats r = run_case(c.mode, c.seed, c.n, c.mrl, c.caps, c.max_best, c.len, c.front_only, c.k, c.w, c.fam_copies);
     printf("%%s: pairs=%%ld records=%%ld tier0=%%ld tier1=%%ld tier2=%%ld bad=%%ld\n", c.name, r.pairs, r.records, r.tier_pairs[0], r.tier_pairs[1], r.tier_pairs[2], r.bad);
     bad += r.bad;
   }
@@ -479,4 +481,4 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     assert got["real_tiers"][1] > 45 and got["real_tiers"][3] > 5, out.stdout                      # records; pairs that climbed to the second tier
     assert got["small_first_tier"][1] > 30 and got["small_first_tier"][3] > 20 and got["small_first_tier"][4] > 3, out.stdout   # CTA kernels, up to the last tier
     assert got["atac_trimming"][1] > 20 and got["hic_split"][1] > 18 and got["single_end"][1] > 25, out.stdout
-    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25 and got["front_end_only"][1] > 5000 and got["front_end_k21_w10"][1] > 800 and got["front_end_k16_w5"][1] > 1500, out.stdout
+    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25 and got["heavy_repeats"][4] > 3 and got["front_end_only"][1] > 5000 and got["front_end_k21_w10"][1] > 800 and got["front_end_k16_w5"][1] > 1500, out.stdout
