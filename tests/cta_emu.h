@@ -163,3 +163,12 @@ static inline void emu_launch(int nt, const std::function<void()> &body, int blo
 static inline void emu_grid(int grid, int nt, const std::function<void()> &body) {
   for (int b = 0; b < grid; ++b) emu_launch(nt, body, b, grid);
 }
+// the same for kernels without barriers or warp primitives (elementwise kernels): the CUDA threads one after the other on the
+// calling OS thread
+static inline void emu_grid_serial(int grid, int nt, const std::function<void()> &body) {
+  for (int b = 0; b < grid; ++b)
+    for (int t = 0; t < nt; ++t) {
+      threadIdx.x = t; blockDim.x = nt; blockIdx.x = b; gridDim.x = grid;
+      body();
+    }
+}
