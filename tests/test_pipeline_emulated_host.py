@@ -126,7 +126,7 @@ static std::string revc(const std::string &s) { std::string r(s.rbegin(), s.rend
 
 struct RunStats { long pairs = 0, records = 0, tier_pairs[3] = {0, 0, 0}, bad = 0; };
 
-enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3, MODE_SAM = 4 };
+enum { MODE_CHIP = 0, MODE_ATAC = 1, MODE_HIC = 2, MODE_SE = 3, MODE_SAM = 4, MODE_SAM_SE = 5 };
 static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *caps3, int max_best, int read_len_base, bool front_only = false, int K = 17, int W = 7, int fam_copies = 90) {
   std::mt19937 g((unsigned)seed);
   RunStats rs;
@@ -189,20 +189,21 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   // ---- oracle
   orc_params op; orc_default_params(&op); orc_apply_preset(&op, mode == MODE_ATAC ? "atac" : mode == MODE_HIC ? "hic" : "chip");
   op.max_num_best_mappings = max_best;
-  op.single_end = mode == MODE_SE;
+  const bool is_se = mode == MODE_SE || mode == MODE_SAM_SE, is_sam = mode == MODE_SAM || mode == MODE_SAM_SE;
+  op.single_end = is_se;
   orc_mapper *om = orc_mapper_create(&op, oix, oref);
   std::vector<orc_pe_record> want((size_t)n * max_best + 8);
   const u32 first_read_id = 5000;
   std::vector<orc_sam_record> want_sam;
   long n_want_sam = 0;
-  if (mode == MODE_SAM) { want_sam.resize((size_t)n * max_best + 8); n_want_sam = (long)orc_map_sam_cores(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want_sam.data(), (long)want_sam.size()); }
-  const long n_want = mode == MODE_SAM ? 0 : mode == MODE_SE ? (long)orc_map_reads_se(om, (u32)n, s1.data(), o1.data(), first_read_id, want.data(), (long)want.size(), 1)
+  if (is_sam) { want_sam.resize((size_t)n * max_best + 8); n_want_sam = (long)orc_map_sam_cores(om, (u32)n, s1.data(), o1.data(), is_se ? nullptr : s2.data(), is_se ? nullptr : o2.data(), first_read_id, want_sam.data(), (long)want_sam.size()); }
+  const long n_want = is_sam ? 0 : mode == MODE_SE ? (long)orc_map_reads_se(om, (u32)n, s1.data(), o1.data(), first_read_id, want.data(), (long)want.size(), 1)
                                       : (long)orc_map_pairs(om, (u32)n, s1.data(), o1.data(), s2.data(), o2.data(), first_read_id, want.data(), (long)want.size(), nullptr);
   // ---- device objects
   DevParams P{};
   P.e = op.error_threshold; P.min_seeds = op.min_num_seeds; P.f0 = op.max_seed_freq0; P.f1 = op.max_seed_freq1; P.max_best = max_best; P.max_insert = op.max_insert_size;
   P.min_read_len = op.min_read_length; P.drop_rep = op.drop_repetitive_reads; P.trim = op.trim_adapters; P.k = K; P.w = W; P.lanes = P.e < 8 ? 8 : 4; P.split = op.split_alignment;
-  P.se = mode == MODE_SE;
+  P.se = is_se;
   const uint32_t *kf; const uint64_t *kk, *kv, *kocc; uint32_t n_occ = 0;
   const uint32_t nb = orc_index_arrays(oix, &kf, &kk, &kv, &kocc, &n_occ);
   // the library's table: 16-byte slots {hash << 1 | singleton, value}, slot = (hash * phi64) >> shift, linear probing, load <= 0.5
@@ -241,7 +242,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   Counters ctr{};
   std::vector<int> nbest((size_t)n, 0), sel((size_t)n * max_best, 0), out_n((size_t)n + 1, 0);
   std::vector<OutRecord> out_rec((size_t)n * max_best);
-  std::vector<OutSam> out_sam(mode == MODE_SAM ? (size_t)n * max_best : 1);
+  std::vector<OutSam> out_sam(is_sam ? (size_t)n * max_best : 1);
   memset(out_sam.data(), 0, out_sam.size() * sizeof(OutSam));
   int n_slots = n, tiers_used = 0;
   const int *pair_list = nullptr;
@@ -334,7 +335,8 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   launch(1, 128, 0, [&]() { select_kernel(P, 1, chunks, nbest.data(), sel.data(), mt_init); });
   for (int t = tiers_used - 1; t >= 0; --t) {
     const Scratch S = tiers[t].view;
-    if (mode == MODE_SAM) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_sam_kernel(P, R, B, T, S, sel.data(), out_sam.data(), out_n.data(), &ctr); });
+    if (mode == MODE_SAM_SE) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_sam_se_kernel(P, R, B, T, S, sel.data(), out_sam.data(), out_n.data(), &ctr); });
+    else if (mode == MODE_SAM) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_sam_kernel(P, R, B, T, S, sel.data(), out_sam.data(), out_n.data(), &ctr); });
     else if (P.split) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_split_kernel(P, R, B, T, S, sel.data(), (OutPairs *)out_rec.data(), out_n.data(), &ctr); });
     else if (P.se) launch((S.n_slots + TB - 1) / TB, TB, 0, [&]() { emit_se_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
     else if (t > 0) launch(S.n_slots, CTA_NT, 0, [&]() { emit_cta_kernel(P, R, B, T, S, sel.data(), out_rec.data(), out_n.data(), &ctr); });
@@ -347,7 +349,7 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
   }
   g_emu_leavable = false;
   // ---- compare, pair by pair
-  if (mode == MODE_SAM) {
+  if (is_sam) {
     static_assert(sizeof(OutSam) == sizeof(orc_sam_record), "SAM record layout");
     long si = 0;
     for (int p = 0; p < n; ++p) {
@@ -358,10 +360,11 @@ static RunStats run_case(int mode, int seed, int n_pairs, int mrl, const Caps *c
       bool ok = out_n[p] == nw;
       for (int r = 0; ok && r < nw; ++r) {
         const OutSam &a = out_sam[(size_t)p * max_best + r]; const orc_sam_record &b = want_sam[w0 + r];
-        ok = a.read_id == b.read_id && a.rid == b.rid && a.pos[0] == b.pos[0] && a.pos[1] == b.pos[1] && a.end[0] == b.end[0] && a.end[1] == b.end[1] && a.strand[0] == b.strand[0] &&
-             a.strand[1] == b.strand[1] && a.mapq == b.mapq && a.is_unique == b.is_unique && a.secondary == b.secondary && a.n_cigar[0] == b.n_cigar[0] && a.n_cigar[1] == b.n_cigar[1] &&
+        ok = a.read_id == b.read_id && a.rid == b.rid && a.pos[0] == b.pos[0] && a.end[0] == b.end[0] && a.strand[0] == b.strand[0] && a.n_cigar[0] == b.n_cigar[0] &&
+             (is_se || (a.pos[1] == b.pos[1] && a.end[1] == b.end[1] && a.strand[1] == b.strand[1] && a.n_cigar[1] == b.n_cigar[1])) && a.mapq == b.mapq && a.is_unique == b.is_unique &&
+             a.secondary == b.secondary &&
              a.overflow == b.overflow;
-        for (int m = 0; ok && m < 2; ++m) for (int q = 0; ok && q < a.n_cigar[m]; ++q) ok = a.cigar[m][q] == b.cigar[m][q];
+        for (int m = 0; ok && m < (is_se ? 1 : 2); ++m) for (int q = 0; ok && q < a.n_cigar[m]; ++q) ok = a.cigar[m][q] == b.cigar[m][q];
       }
       if (!ok) { if (rs.bad < 8) printf("SAM PAIR %%d (seed %%d): records %%d / %%d\n", p, seed, out_n[p], nw); ++rs.bad; }
     }
@@ -411,6 +414,7 @@ int main() {
       {"single_end", MODE_SE, 8, 60, 2, 60, real, mrl},
       {"single_end_cta", MODE_SE, 9, 28, 1, 60, small, mrl},
       {"sam_cores", MODE_SAM, 10, 56, 2, 60, real, mrl},
+      {"sam_cores_single_end", MODE_SAM_SE, 15, 40, 2, 60, real, mrl},
       {"heavy_repeats", MODE_CHIP, 14, 14, 2, 60, real, mrl, false, 17, 7, 420},       // a 420-copy family: thousands of hits, hundreds of candidates per read, up to the last tier
       {"front_end_only", MODE_CHIP, 11, 600, 1, 60, real, mrl, true},
       {"front_end_k21_w10", MODE_CHIP, 12, 200, 1, 60, real, mrl, true, 21, 10},     // the run-time scan (seed_front_kernel<false>)
@@ -482,4 +486,4 @@ def test_device_pipeline_on_emulated_ctas_equals_the_oracle(tmp_path):
     assert got["real_tiers"][1] > 45 and got["real_tiers"][3] > 5, out.stdout                      # records; pairs that climbed to the second tier
     assert got["small_first_tier"][1] > 30 and got["small_first_tier"][3] > 20 and got["small_first_tier"][4] > 3, out.stdout   # CTA kernels, up to the last tier
     assert got["atac_trimming"][1] > 20 and got["hic_split"][1] > 18 and got["single_end"][1] > 25, out.stdout
-    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25 and got["heavy_repeats"][4] > 3 and got["front_end_only"][1] > 5000 and got["front_end_k21_w10"][1] > 800 and got["front_end_k16_w5"][1] > 1500, out.stdout
+    assert got["hic_split_cta"][3] > 3 and got["single_end_cta"][3] > 6 and got["sam_cores"][1] > 25 and got["sam_cores_single_end"][1] > 20 and got["heavy_repeats"][4] > 3 and got["front_end_only"][1] > 5000 and got["front_end_k21_w10"][1] > 800 and got["front_end_k16_w5"][1] > 1500, out.stdout
