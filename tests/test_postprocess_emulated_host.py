@@ -198,6 +198,29 @@ int main() {
       ++cases;
       if (nb != (long)off[n] || memcmp(want.data(), text.data(), (size_t)nb) != 0) { if (bad < 6) printf("BED TEXT bc=%%d: %%llu / %%ld bytes\n", with_bc, (unsigned long long)off[n], nb); ++bad; }
     }
+    // pairs lines (pairs_len_kernel / pairs_write_kernel) against the oracle's writer, below its header
+    {
+      const size_t n = 3000;
+      const u32 first_read_id = 77;
+      std::vector<PpRecord> recs = random_records(g, n, PP_PAIRS);
+      std::string rn; std::vector<u64> roff{0}; std::vector<std::string> rnv;
+      for (size_t i = 0; i < n; ++i) { rnv.push_back("read" + std::to_string(i * 13 %% 977) + (i %% 5 ? "" : "/long_name_part")); rn += rnv.back(); roff.push_back(rn.size()); }
+      std::vector<const char *> rnp; for (auto &x : rnv) rnp.push_back(x.c_str());
+      for (size_t i = 0; i < n; ++i) { recs[i].w[0] = first_read_id + (u32)((i * 7) %% n); recs[i].w[3] = g() %% 3 ? g() %% 100000 : 4294967294u; recs[i].w[4] = g() %% 100000; }
+      std::vector<u32> len(n + 1, 0);
+      launch(n, [&]() { pairs_len_kernel(recs.data(), n, noff.data(), roff.data(), first_read_id, len.data()); });
+      std::vector<u64> off(n + 1, 0);
+      for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + len[i];
+      std::string text((size_t)off[n], '?');
+      launch(n, [&]() { pairs_write_kernel(recs.data(), n, cat.data(), noff.data(), rn.data(), roff.data(), first_read_id, off.data(), &text[0]); });
+      std::string want((size_t)off[n] + 65536, '!');
+      const long nb = (long)orc_format_pairs(oref, (const orc_pairs_record *)recs.data(), (long)n, rnp.data(), first_read_id, &want[0], (long)want.size());
+      want.resize((size_t)std::max(0l, nb));
+      size_t body = 0;
+      while (body < want.size() && want[body] == '#') { body = want.find('\n', body); body = body == std::string::npos ? want.size() : body + 1; }
+      ++cases;
+      if (want.size() - body != text.size() || memcmp(want.data() + body, text.data(), text.size()) != 0) { if (bad < 6) printf("PAIRS TEXT: %%zu / %%zu bytes\n", text.size(), want.size() - body); ++bad; }
+    }
     orc_reference_free(oref);
   }
   printf("cases=%%ld records_kept=%%ld bad=%%ld\n", cases, kept, bad);
